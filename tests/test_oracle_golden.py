@@ -1,0 +1,138 @@
+"""Pin the CPU oracle (oracle/conformer_oracle.py) against golden vectors produced by the real reference
+(tests/golden/make_golden.py).  Tolerances: fp32 oracle vs fp32 reference, different op order only."""
+import json
+import os
+
+import pytest
+import torch
+
+from efficientconformer_b200.config import (CTC_SMALL_ENCODER_PARAMS as P, CTC_SMALL_VOCAB as V, resolve_blocks,
+                                            state_dict_layout, stage_lengths)
+from efficientconformer_b200.synthetic import seeded_state_dict, synthetic_mel, synthetic_audio
+from oracle import conformer_oracle as O
+
+
+def rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return seeded_state_dict(P, V, seed=0, prefix_encoder="encoder.")
+
+
+def test_state_dict_layout_matches_reference(golden_dir):
+    layouts = json.load(open(os.path.join(golden_dir, "state_dict_layouts.json")))
+    for name, entry in layouts.items():
+        ref = {k: tuple(s) for k, s in entry["keys"]}
+        mine = {("encoder." + k if not k.startswith("fc.") else k): tuple(s)
+                for k, s in state_dict_layout(entry["encoder_params"], entry["vocab_size"])}
+        assert mine == ref, (name, set(mine) ^ set(ref))
+        # order of the reference state_dict is reproduced too
+        assert [k for k, _ in entry["keys"]] == list(mine.keys()), name
+
+
+def test_ctc_small_params_are_the_shipped_config(golden_dir):
+    layouts = json.load(open(os.path.join(golden_dir, "state_dict_layouts.json")))
+    assert layouts["EfficientConformerCTCSmall"]["encoder_params"] == P
+    specs = resolve_blocks(P)
+    assert [s.dim_head for s in specs] == [90] * 5 + [42] * 5 + [60] * 5
+    assert [s.conv_stride for s in specs] == [1, 1, 1, 1, 2, 1, 1, 1, 1, 2, 1, 1, 1, 1, 1]
+    assert stage_lengths(P, 1000)[1] == 125
+
+
+def test_config1_logits_loss_greedy(sd, golden_dir):
+    g = torch.load(os.path.join(golden_dir, "ctc_small_b2_t500.pt"))
+    mel = synthetic_mel(2, 500, seed=g["mel_seed"])
+    taps = {}
+    logits, out_len = O.model_ctc_forward_mel(sd, P, mel, g["mel_len"], taps=taps)
+    assert torch.equal(out_len, g["out_len"])
+    assert rel_l2(logits, g["logits"]) < 2e-5
+    for k, v in g["taps"].items():
+        assert rel_l2(taps[k], v) < 2e-5, k
+    loss, per = O.ctc_loss(logits, out_len, g["targets"], g["target_len"])
+    assert abs(float(loss) - float(g["loss"])) / abs(float(g["loss"])) < 1e-5
+    assert torch.allclose(per, g["loss_per_utt"], rtol=1e-5)
+    assert O.greedy_ids(g["logits"], g["out_len"]) == g["greedy"]
+
+
+def test_config1_fp64_oracle_close_to_fp32_reference(sd, golden_dir):
+    g = torch.load(os.path.join(golden_dir, "ctc_small_b2_t500.pt"))
+    mel = synthetic_mel(2, 500, seed=g["mel_seed"]).double()
+    logits, _ = O.model_ctc_forward_mel(sd, P, mel, g["mel_len"])
+    assert rel_l2(logits.float(), g["logits"]) < 2e-5
+
+
+def test_audio_front_end(sd, golden_dir):
+    g = torch.load(os.path.join(golden_dir, "ctc_small_audio_b2_t200.pt"))
+    audio = synthetic_audio(2, g["t_mel"], seed=g["audio_seed"])
+    sd2 = dict(sd)
+    sd2["encoder.preprocessing.Spectrogram.window"] = g["window"]
+    sd2["encoder.preprocessing.MelScale.fb"] = g["fb"]
+    mel, mel_len = O.audio_to_mel(sd2, P, audio, g["audio_len"], prefix="encoder.")
+    assert torch.equal(mel_len, g["mel_len"])
+    assert mel.shape[-1] == g["t_mel"]
+    assert (mel - g["mel"].float()).abs().max() < 2e-2          # golden mel stored as fp16
+    logits, out_len = O.model_ctc_forward_mel(sd2, P, mel, mel_len)
+    assert torch.equal(out_len, g["out_len"])
+    assert rel_l2(logits, g["logits"]) < 1e-4
+
+
+def test_modules_awkward_lengths(sd, golden_dir):
+    g = torch.load(os.path.join(golden_dir, "ctc_small_modules.pt"))
+    enc = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
+    specs = resolve_blocks(P)
+    for key, e in g.items():
+        if key.startswith("sub_"):
+            Tm = int(key[5:])
+            gen = torch.Generator().manual_seed(9000 + Tm)
+            m = torch.randn(2, 80, Tm, generator=gen)
+            ml = torch.tensor([Tm, max(1, Tm // 2)])
+            h, l = O.conv2d_subsampling(enc, P, m, ml)
+            out = O.EXACT.linear(h.transpose(1, 2), enc["linear.weight"], enc["linear.bias"])
+            assert torch.equal(l, e["out_len"])
+            assert rel_l2(out, e["out"]) < 1e-5, key
+            continue
+        bi, Tq = int(key[1:key.index("_")]), int(key[key.index("T") + 1:])
+        spec = specs[bi]
+        gen = torch.Generator().manual_seed(100 * bi + Tq)
+        x = torch.randn(2, Tq, spec.dim_model, generator=gen)
+        out, w = O.conformer_block(enc, f"blocks.{bi}", x, e["x_len"], spec)
+        assert out.shape == e["block"].shape, key
+        assert rel_l2(out, e["block"]) < 2e-5, key
+        if "ffn1" in e:
+            p = f"blocks.{bi}"
+            assert rel_l2(O.feed_forward(enc, f"{p}.feed_forward_module1", x), e["ffn1"]) < 1e-5, key
+            m = f"{p}.multi_head_self_attention_module"
+            a_in = O.layer_norm(x, enc[f"{m}.norm.weight"], enc[f"{m}.norm.bias"])
+            att, w = O.relpos_attention(enc, f"{m}.mhsa", a_in, e["x_len"], spec)
+            assert rel_l2(att, e["mhsa"]) < 1e-5, key
+            assert (w - e["att_w"]).abs().max() < 1e-5, key
+            assert rel_l2(O.conv_module(enc, f"{p}.convolution_module", x, spec), e["conv"]) < 1e-5, key
+
+
+def test_ctc_loss_and_greedy_known_answers(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "ctc_loss_small.pt"))
+    loss, per = O.ctc_loss(g["logits"], g["logits_len"], g["targets"], g["target_len"])
+    assert torch.allclose(per, g["loss_per_utt"], rtol=1e-5, atol=1e-5)
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    # collapse rule on hand-made sequences: merge repeats, then drop blanks
+    lg = torch.full((1, 8, 4), -5.0)
+    for t, tok in enumerate([1, 1, 0, 1, 2, 2, 0, 3]):
+        lg[0, t, tok] = 5.0
+    assert O.greedy_ids(lg, torch.tensor([8])) == [[1, 1, 2, 3]]
+    assert O.greedy_ids(lg, torch.tensor([2])) == [[1]]
+    assert O.greedy_ids(lg, torch.tensor([0])) == [[]]
+
+
+def test_operand_rounding_emulation_predicts_tf32_within_gate(sd, golden_dir):
+    """The parity gate is 1e-3 (BASELINE.json north_star).  TF32 operands (what the tcgen05 kind::tf32 path
+    feeds the tensor cores) must leave headroom; bf16 operands do not, which is why parity runs in tf32 mode."""
+    g = torch.load(os.path.join(golden_dir, "ctc_small_b2_t500.pt"))
+    mel = synthetic_mel(2, 500, seed=g["mel_seed"])
+    lt, _ = O.model_ctc_forward_mel(sd, P, mel, g["mel_len"], nm=O.Numerics("tf32"))
+    lb, _ = O.model_ctc_forward_mel(sd, P, mel, g["mel_len"], nm=O.Numerics("bf16"))
+    et, eb = rel_l2(lt, g["logits"]), rel_l2(lb, g["logits"])
+    print("emulated rel-L2: tf32 %.2e  bf16 %.2e" % (et, eb))
+    assert et < 1e-3
+    assert eb > et
