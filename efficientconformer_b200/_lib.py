@@ -1,0 +1,122 @@
+"""ctypes binding of libeffconf_b200.so (the C ABI declared in include/effconf_b200.h).
+
+The product path has no CPU or PyTorch fallback: if the shared library is missing or the device is not sm_100,
+every entry point raises.  Structures mirror the header field-for-field."""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libeffconf_b200.so")
+
+EC_MAX_BLOCKS = 32
+PREC_TF32, PREC_BF16 = 0, 1
+PRECISIONS = {"tf32": PREC_TF32, "bf16": PREC_BF16}
+_fp = C.POINTER(C.c_float)
+
+
+class BlockCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("dim_model", "dim_expand", "num_heads", "kernel_size", "group_size", "conv_stride",
+                                          "ff_ratio", "reserved")]
+
+
+class Config(C.Structure):
+    _fields_ = [("n_mels", C.c_int32), ("sub_filters", C.c_int32), ("num_blocks", C.c_int32), ("vocab", C.c_int32),
+                ("blocks", BlockCfg * EC_MAX_BLOCKS)]
+
+
+class FfnRaw(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ln_w", "ln_b", "w1", "b1", "w2", "b2")]
+
+
+class BlockRaw(C.Structure):
+    _fields_ = [("ffn1", FfnRaw), ("ffn2", FfnRaw)] + [(n, C.c_void_p) for n in (
+        "att_ln_w", "att_ln_b", "u", "v", "wq", "bq", "wk", "bk", "wv", "bv", "wo", "bo", "wpos", "bpos",
+        "conv_ln_w", "conv_ln_b", "pw1_w", "pw1_b", "dw_w", "dw_b", "bn_w", "bn_b", "bn_rm", "bn_rv", "pw2_w", "pw2_b",
+        "norm_w", "norm_b", "res_w", "res_b")]
+
+
+class RawWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("sub_conv_w", "sub_conv_b", "sub_bn_w", "sub_bn_b", "sub_bn_rm", "sub_bn_rv",
+                                          "lin_w", "lin_b", "fc_w", "fc_b")] + [("blocks", BlockRaw * EC_MAX_BLOCKS)]
+
+
+_SIGNATURES = {
+    "ec_last_error": (C.c_char_p, []),
+    "ec_version": (C.c_int, []),
+    "ec_device_check": (C.c_int, []),
+    "ec_engine_create": (C.c_int, [C.POINTER(Config), C.c_int, C.POINTER(C.c_void_p)]),
+    "ec_engine_destroy": (None, [C.c_void_p]),
+    "ec_engine_weight_bytes": (C.c_size_t, [C.c_void_p]),
+    "ec_engine_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "ec_engine_prepare": (C.c_int, [C.c_void_p, C.POINTER(RawWeights), C.c_void_p, C.c_void_p]),
+    "ec_engine_relpos_rows": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "ec_engine_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ec_engine_out_frames": (C.c_int, [C.c_void_p, C.c_int]),
+    "ec_profile_categories": (C.c_int, []),
+    "ec_profile_category_name": (C.c_char_p, [C.c_int]),
+    "ec_engine_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "ec_engine_last_launches": (C.c_int, [C.c_void_p]),
+    "ec_engine_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_int32)]),
+    "ec_ctc_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "ec_ctc_loss": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ec_ctc_greedy": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ec_op_cast": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ec_op_layernorm": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+                                  C.c_void_p]),
+    "ec_op_gemm": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_void_p,
+                             C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ec_op_pointwise_glu": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "ec_op_glu_scratch_rows": (C.c_int, [C.c_int]),
+    "ec_op_fold_bn": (C.c_int, [C.c_void_p] * 6 + [C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ec_op_relpos_attention": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ec_op_dwconv_bn_swish": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p]),
+    "ec_op_subsample_conv": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library.  Raises if it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} not found: build it with `python -m efficientconformer_b200.build` "
+                               "(or __graft_entry__.build()); the CUDA library is the only implementation of the hot path")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status: int):
+    if status != 0:
+        raise RuntimeError("effconf_b200: " + lib().ec_last_error().decode())
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def act_dtype(precision: int):
+    return torch.float32 if precision == PREC_TF32 else torch.bfloat16

@@ -1,0 +1,275 @@
+// Relative-position (grouped) multi-head self-attention core, flash style, relative shift done in-kernel.
+//
+// Restates reference models/attentions.py:549-620 (RelPosMultiHeadSelfAttention.forward) and :645-718
+// (GroupedRelPosMultiHeadSelfAttention.forward) between the Q/K/V projections and the output projection:
+//   P = (-T) mod G zero frames appended after the projection (:107-121), qu = q + u, qv = q + v (:674-675),
+//   the contiguous (B, Tp, D) buffer is reinterpreted as (B, T' = Tp/G, H, d = G*D/H) (:681-685),
+//   S[i,j] = (qu_i . k_j + qv_i . E[h, T'-1+j-i]) / sqrt(d)                (:690-692 with rel_to_abs :526-547)
+//   key group j masked iff j*G >= x_len[b] (:695-701), softmax over j, O = W v (:704-707), first T frames kept (:713).
+// Never materialises the (B,H,T',2T'-1) relative scores nor the (B,H,T',T') weights.
+//
+// v1 implementation: one CTA = 64 query groups of one (batch, head); 4 warps x 16 rows; key tiles of 64;
+// mma.sync m16n8k8 TF32 with fp32 accumulation and fp32 online softmax.  For each (query tile, key tile) the needed
+// diagonal band of E (127 rows) is staged in shared memory, G = Qv . Eband^T is computed per warp (16 x 80), written to
+// a per-warp smem strip and read back with the per-row shift  S_E[r, j] = G[r, j - r + 15].
+#include "ec_common.cuh"
+#include <mutex>
+
+namespace ec {
+
+struct AttnDev {
+  const float* qkv; const float* E; const float* u; const float* v; const int* x_len;
+  int B, T, D, H, G, d, Tg;
+  void* out; int ld_out;
+  float scale_log2;
+};
+
+__device__ __forceinline__ uint32_t tf32_bits(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int kAttBM = 64, kAttBN = 64, kGW = 80, kGStride = 81;
+
+template <int DPT, typename OutT>
+__global__ void __launch_bounds__(128) relpos_attn_kernel(const AttnDev p) {
+  constexpr int DP = DPT * 8, STR = DP + 4;
+  extern __shared__ float sm[];
+  float* Qu = sm;
+  float* Qv = Qu + kAttBM * STR;
+  float* Ks = Qv + kAttBM * STR;
+  float* Vs = Ks + kAttBN * STR;
+  float* Es = Vs + kAttBN * STR;
+  float* Gs = Es + 128 * STR;
+
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * kAttBM;
+  const int D = p.D, G = p.G, d = p.d, Tg = p.Tg, T = p.T;
+  const int xl = p.x_len != nullptr ? p.x_len[b] : T;
+  const size_t row3 = static_cast<size_t>(3) * D;
+  const float* qkv_b = p.qkv + static_cast<size_t>(b) * T * row3;
+
+  // ---- stage Qu / Qv (tf32-rounded) ----
+  for (int idx = tid; idx < kAttBM * DP; idx += 128) {
+    const int r = idx / DP, c = idx % DP;
+    const int i = i0 + r;
+    float qu = 0.f, qv = 0.f;
+    if (c < d && i < Tg) {
+      const int f = h * d + c;
+      const int frame = i * G + f / D, ch = f % D;
+      const float q = frame < T ? __ldg(qkv_b + frame * row3 + ch) : 0.f;   // appended pad frames are exact zeros
+      qu = q + __ldg(p.u + ch);
+      qv = q + __ldg(p.v + ch);
+    }
+    Qu[r * STR + c] = round_tf32(qu);
+    Qv[r * STR + c] = round_tf32(qv);
+  }
+
+  float o[DPT][4];
+#pragma unroll
+  for (int n = 0; n < DPT; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  float* Gw = Gs + w * 16 * kGStride;
+  const int eo = (3 - w) * 16;                       // this warp's first row inside the staged E band
+  const size_t e_row = static_cast<size_t>(G) * D;
+
+  for (int j0 = 0; j0 < Tg; j0 += kAttBN) {
+    __syncthreads();
+    // ---- stage K, V tile and the E band ----
+    for (int idx = tid; idx < kAttBN * DP; idx += 128) {
+      const int r = idx / DP, c = idx % DP;
+      const int j = j0 + r;
+      float kv = 0.f, vv = 0.f;
+      if (c < d && j < Tg) {
+        const int f = h * d + c;
+        const int frame = j * G + f / D, ch = f % D;
+        if (frame < T) {
+          kv = __ldg(qkv_b + frame * row3 + D + ch);
+          vv = __ldg(qkv_b + frame * row3 + 2 * D + ch);
+        }
+      }
+      Ks[r * STR + c] = round_tf32(kv);
+      Vs[r * STR + c] = round_tf32(vv);
+    }
+    const int ebase = Tg - 1 + j0 - i0 - (kAttBM - 1);
+    for (int idx = tid; idx < 128 * DP; idx += 128) {
+      const int r = idx / DP, c = idx % DP;
+      const int e = ebase + r;
+      float ev = 0.f;
+      if (c < d && e >= 0 && e <= 2 * Tg - 2) ev = __ldg(p.E + e * e_row + h * d + c);
+      Es[r * STR + c] = round_tf32(ev);
+    }
+    __syncthreads();
+
+    // ---- G = Qv_w . Eband_w^T  (16 x 80) -> per-warp smem strip ----
+    {
+      float acc[kGW / 8][4];
+#pragma unroll
+      for (int n = 0; n < kGW / 8; ++n) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f; }
+#pragma unroll
+      for (int kt = 0; kt < DPT; ++kt) {
+        const float* qa = Qv + (w * 16 + g) * STR + kt * 8 + t;
+        const uint32_t a0 = __float_as_uint(qa[0]), a1 = __float_as_uint(qa[8 * STR]);
+        const uint32_t a2 = __float_as_uint(qa[4]), a3 = __float_as_uint(qa[8 * STR + 4]);
+#pragma unroll
+        for (int n = 0; n < kGW / 8; ++n) {
+          const float* eb = Es + (eo + n * 8 + g) * STR + kt * 8 + t;
+          mma_tf32(acc[n], a0, a1, a2, a3, __float_as_uint(eb[0]), __float_as_uint(eb[4]));
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < kGW / 8; ++n) {
+        float* g0 = Gw + g * kGStride + n * 8 + 2 * t;
+        g0[0] = acc[n][0]; g0[1] = acc[n][1];
+        g0[8 * kGStride] = acc[n][2]; g0[8 * kGStride + 1] = acc[n][3];
+      }
+    }
+    __syncwarp();
+
+    // ---- S = Qu_w . K^T (16 x 64) ----
+    float s[kAttBN / 8][4];
+#pragma unroll
+    for (int n = 0; n < kAttBN / 8; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; }
+#pragma unroll
+    for (int kt = 0; kt < DPT; ++kt) {
+      const float* qa = Qu + (w * 16 + g) * STR + kt * 8 + t;
+      const uint32_t a0 = __float_as_uint(qa[0]), a1 = __float_as_uint(qa[8 * STR]);
+      const uint32_t a2 = __float_as_uint(qa[4]), a3 = __float_as_uint(qa[8 * STR + 4]);
+#pragma unroll
+      for (int n = 0; n < kAttBN / 8; ++n) {
+        const float* kb = Ks + (n * 8 + g) * STR + kt * 8 + t;
+        mma_tf32(s[n], a0, a1, a2, a3, __float_as_uint(kb[0]), __float_as_uint(kb[4]));
+      }
+    }
+    // ---- relative shift, scale, key mask ----
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int n = 0; n < kAttBN / 8; ++n) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = g + ((e & 2) ? 8 : 0);
+        const int jl = n * 8 + 2 * t + (e & 1);
+        const int j = j0 + jl;
+        const float val = (s[n][e] + Gw[r * kGStride + jl - r + 15]) * p.scale_log2;
+        const bool valid = j < Tg && j * G < xl;
+        s[n][e] = valid ? val : -INFINITY;
+        mx[e >> 1] = fmaxf(mx[e >> 1], s[n][e]);
+      }
+    }
+    // ---- online softmax (base 2) ----
+    float corr[2], m_use[2];
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      float m = mx[hrow];
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      const float m_new = fmaxf(m_run[hrow], m);
+      m_use[hrow] = (m_new == -INFINITY) ? 0.f : m_new;
+      corr[hrow] = exp2f(m_run[hrow] - m_use[hrow]);
+      m_run[hrow] = m_new;
+      l_run[hrow] *= corr[hrow];
+    }
+#pragma unroll
+    for (int n = 0; n < kAttBN / 8; ++n) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pe = exp2f(s[n][e] - m_use[e >> 1]);
+        s[n][e] = pe;
+        l_run[e >> 1] += pe;
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < DPT; ++n) { o[n][0] *= corr[0]; o[n][1] *= corr[0]; o[n][2] *= corr[1]; o[n][3] *= corr[1]; }
+    // ---- O += P . V  (k index of the k-tile is permuted: slot t <-> key 2t, slot t+4 <-> key 2t+1) ----
+#pragma unroll
+    for (int kt = 0; kt < kAttBN / 8; ++kt) {
+      const uint32_t a0 = tf32_bits(s[kt][0]), a1 = tf32_bits(s[kt][2]), a2 = tf32_bits(s[kt][1]), a3 = tf32_bits(s[kt][3]);
+      const float* vb = Vs + (kt * 8 + 2 * t) * STR + g;
+#pragma unroll
+      for (int n = 0; n < DPT; ++n) mma_tf32(o[n], a0, a1, a2, a3, __float_as_uint(vb[n * 8]), __float_as_uint(vb[STR + n * 8]));
+    }
+  }
+
+  // ---- normalise and scatter to (B, T, D): grouped row i / head h / col c -> frame i*G + (h*d+c)/D, channel (h*d+c)%D ----
+  using Tr = ActTraits<OutT>;
+  OutT* out = reinterpret_cast<OutT*>(p.out);
+#pragma unroll
+  for (int hrow = 0; hrow < 2; ++hrow) {
+    float l = l_run[hrow];
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    const int i = i0 + w * 16 + g + hrow * 8;
+    if (i >= Tg) continue;
+#pragma unroll
+    for (int n = 0; n < DPT; ++n) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = n * 8 + 2 * t + e;
+        if (c < d) {
+          const int f = h * d + c;
+          const int frame = i * G + f / D, ch = f % D;
+          if (frame < T) out[(static_cast<size_t>(b) * T + frame) * p.ld_out + ch] = Tr::to(o[n][hrow * 2 + e] * inv);
+        }
+      }
+    }
+  }
+}
+
+template <int DPT, typename OutT>
+static int launch_attn_inst(const AttnDev& p, cudaStream_t stream) {
+  constexpr int STR = DPT * 8 + 4;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(kAttBM) * STR * 2 + kAttBN * STR * 2 + 128 * STR + 4 * 16 * kGStride);
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(relpos_attn_kernel<DPT, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  EC_CUDA(attr_err);
+  EC_REQUIRE(smem <= 227 * 1024, "attention tile does not fit in shared memory");
+  dim3 grid(cdiv(p.Tg, kAttBM), p.H, p.B);
+  relpos_attn_kernel<DPT, OutT><<<grid, 128, smem, stream>>>(p);
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+
+template <typename T>
+static int launch_attn_t(const AttnDev& p, cudaStream_t stream) {
+  const int dpt = cdiv(p.d, 8);
+  switch (dpt) {
+    case 3: return launch_attn_inst<3, T>(p, stream);
+    case 5: return launch_attn_inst<5, T>(p, stream);
+    case 6: return launch_attn_inst<6, T>(p, stream);
+    case 7: return launch_attn_inst<7, T>(p, stream);
+    case 8: return launch_attn_inst<8, T>(p, stream);
+    case 10: return launch_attn_inst<10, T>(p, stream);
+    case 12: return launch_attn_inst<12, T>(p, stream);
+    case 17: return launch_attn_inst<17, T>(p, stream);
+    default: EC_FAIL("unsupported attention head dim " + std::to_string(p.d));
+  }
+}
+
+int launch_relpos_attention(int precision, const AttnArgs& a, cudaStream_t stream) {
+  EC_REQUIRE(a.G >= 1 && a.G % 2 == 1, "attention group size must be odd");
+  EC_REQUIRE((a.G * a.D) % a.H == 0, "G*D must be divisible by H");
+  AttnDev p{};
+  p.qkv = a.qkv; p.E = a.E; p.u = a.u; p.v = a.v; p.x_len = a.x_len;
+  p.B = a.B; p.T = a.T; p.D = a.D; p.H = a.H; p.G = a.G;
+  p.d = (a.G * a.D) / a.H;
+  const int P = (a.G - a.T % a.G) % a.G;
+  p.Tg = (a.T + P) / a.G;
+  p.out = a.out; p.ld_out = a.ld_out;
+  p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(p.d));
+  if (precision == EC_PREC_TF32) return launch_attn_t<float>(p, stream);
+  if (precision == EC_PREC_BF16) return launch_attn_t<__nv_bfloat16>(p, stream);
+  EC_FAIL("unknown precision");
+}
+
+}  // namespace ec

@@ -1,0 +1,140 @@
+// CTC head on device: per-frame log-sum-exp + argmax, CTC negative log-likelihood (alpha recursion), greedy collapse.
+//
+//   launch_logsoftmax_argmax : log_softmax denominators and argmax ids      (reference models/losses.py:66, model_ctc.py:99)
+//   launch_ctc_loss          : nn.CTCLoss(blank=0, reduction='none', zero_infinity=False) then .mean()   (models/losses.py:54,65-69)
+//   launch_greedy_collapse   : merge repeats then drop blanks == the reference's per-frame loop          (models/model_ctc.py:105-130)
+// The reference loops over (b, t) on the host with one device sync per comparison; here it is one thread per utterance.
+#include "ec_common.cuh"
+
+namespace ec {
+
+__global__ void __launch_bounds__(256) logsoftmax_argmax_kernel(const float* __restrict__ logits, int rows, int V,
+                                                                float* __restrict__ lse, int* __restrict__ amax) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* x = logits + static_cast<size_t>(row) * V;
+  float m = -INFINITY; int mi = 0x7fffffff;
+  for (int c = lane; c < V; c += 32) {
+    const float v = x[c];
+    if (v > m) { m = v; mi = c; }           // strictly greater keeps the lowest index inside a lane (c ascending)
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+  }
+  float s = 0.f;
+  for (int c = lane; c < V; c += 32) s += expf(x[c] - m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) { lse[row] = m + logf(s); amax[row] = mi; }
+}
+
+int launch_logsoftmax_argmax(const float* logits, int rows, int V, float* lse, int* argmax, cudaStream_t stream) {
+  if (rows == 0) return EC_OK;
+  logsoftmax_argmax_kernel<<<cdiv(rows, 8), 256, 0, stream>>>(logits, rows, V, lse, argmax);
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+  const float m = fmaxf(a, fmaxf(b, c));
+  if (m == -INFINITY) return -INFINITY;
+  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+}
+
+// One CTA per utterance; alpha over the 2U+1 extended labels double-buffered in shared memory (Graves et al. 2006).
+__global__ void __launch_bounds__(256) ctc_alpha_kernel(const float* __restrict__ logits, const float* __restrict__ lse, int T, int V,
+                                                        const int* __restrict__ logits_len, const long long* __restrict__ targets,
+                                                        int target_stride, const long long* __restrict__ target_len,
+                                                        float* __restrict__ loss_per_utt) {
+  extern __shared__ float alpha_sm[];
+  const int b = blockIdx.x;
+  const int U = static_cast<int>(target_len[b]);
+  const int S = 2 * U + 1;
+  int Tb = logits_len[b];
+  if (Tb > T) Tb = T;
+  float* a0 = alpha_sm;
+  float* a1 = alpha_sm + S;
+  int* ext = reinterpret_cast<int*>(alpha_sm + 2 * S);
+  const long long* y = targets + static_cast<size_t>(b) * target_stride;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) ext[s] = (s & 1) ? static_cast<int>(y[s >> 1]) : 0;
+  __syncthreads();
+  const float* lg = logits + static_cast<size_t>(b) * T * V;
+  const float* ls = lse + static_cast<size_t>(b) * T;
+  if (Tb <= 0) {
+    if (threadIdx.x == 0) loss_per_utt[b] = INFINITY;
+    return;
+  }
+  for (int s = threadIdx.x; s < S; s += blockDim.x) a0[s] = s < 2 ? lg[ext[s]] - ls[0] : -INFINITY;
+  __syncthreads();
+  float* prev = a0; float* cur = a1;
+  for (int t = 1; t < Tb; ++t) {
+    const float* lgt = lg + static_cast<size_t>(t) * V;
+    const float lst = ls[t];
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+      const int e = ext[s];
+      const float x0 = prev[s];
+      const float x1 = s > 0 ? prev[s - 1] : -INFINITY;
+      const float x2 = (s > 1 && e != 0 && e != ext[s - 2]) ? prev[s - 2] : -INFINITY;
+      const float acc = lse3(x0, x1, x2);
+      cur[s] = acc == -INFINITY ? -INFINITY : acc + (lgt[e] - lst);
+    }
+    __syncthreads();
+    float* tmp = prev; prev = cur; cur = tmp;
+  }
+  if (threadIdx.x == 0) {
+    const float l = S > 1 ? lse3(prev[S - 1], prev[S - 2], -INFINITY) : prev[0];
+    loss_per_utt[b] = -l;
+  }
+}
+
+__global__ void mean_kernel(const float* x, int n, float* out) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 32) s += x[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (threadIdx.x == 0) *out = s / n;
+}
+
+int launch_ctc_loss(const float* logits, const float* lse, int B, int T, int V, const int* logits_len, const long long* targets,
+                    int target_stride, const long long* target_len, float* loss_per_utt, float* loss_mean, cudaStream_t stream) {
+  EC_REQUIRE(B > 0 && target_stride >= 0, "bad CTC shapes");
+  const size_t smem = sizeof(float) * 3 * (2 * static_cast<size_t>(target_stride) + 1);
+  EC_REQUIRE(smem <= 48 * 1024, "CTC target too long for the shared-memory alpha buffers");
+  ctc_alpha_kernel<<<B, 256, smem, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, loss_per_utt);
+  EC_CUDA(cudaGetLastError());
+  if (loss_mean != nullptr) {
+    mean_kernel<<<1, 32, 0, stream>>>(loss_per_utt, B, loss_mean);
+    EC_CUDA(cudaGetLastError());
+  }
+  return EC_OK;
+}
+
+__global__ void greedy_collapse_kernel(const int* __restrict__ amax, int B, int T, const int* __restrict__ logits_len,
+                                       int* __restrict__ ids, int* __restrict__ counts) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int n = 0, prev = 0;
+  int Tb = logits_len[b];
+  if (Tb > T) Tb = T;
+  const int* a = amax + static_cast<size_t>(b) * T;
+  int* o = ids + static_cast<size_t>(b) * T;
+  for (int t = 0; t < Tb; ++t) {
+    const int tok = a[t];
+    if (tok != 0 && tok != prev) o[n++] = tok;
+    prev = tok;
+  }
+  counts[b] = n;
+  for (int t = n; t < T; ++t) o[t] = 0;
+}
+
+int launch_greedy_collapse(const int* argmax, int B, int T, const int* logits_len, int* ids, int* counts, cudaStream_t stream) {
+  greedy_collapse_kernel<<<cdiv(B, 64), 64, 0, stream>>>(argmax, B, T, logits_len, ids, counts);
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+
+}  // namespace ec

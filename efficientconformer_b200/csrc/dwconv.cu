@@ -1,0 +1,113 @@
+// Fused depthwise Conv1d (k taps, stride s, 'same' zero halo) + eval BatchNorm1d (folded into taps/bias) + Swish.
+//
+// Restates reference models/modules.py:515-517 with Conv1d "same" pre-padding (models/layers.py:99-100,131-136):
+//   out[b, t, c] = swish( b'_c + sum_k w'[c,k] * in[b, t*s + k - (K-1)/2, c] ),   T_out = (T-1)//s + 1,
+// on channels-last activations (the GLU output of the pw1 GEMM epilogue), with NO length masking (padded frames
+// are computed densely like the reference).  Bandwidth-bound: each input element is read from global once per CTA
+// (16-byte vector loads into shared memory, halo included), each thread then slides a register window over time for
+// one channel, so shared memory is read ~(R*s+K-1)/R times per output; the output is written once.
+#include "ec_common.cuh"
+
+namespace ec {
+
+constexpr int kDwR = 16;        // outputs per thread (register run along time)
+constexpr int kDwRuns = 4;      // runs per CTA  -> 64 output frames per CTA
+constexpr int kDwMaxK = 31;
+
+template <typename T, int STRIDE, int K>
+__global__ void __launch_bounds__(1024) dwconv_bn_swish_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                               int T_in, int T_out, int C, T* __restrict__ y) {
+  using Tr = ActTraits<T>;
+  extern __shared__ __align__(16) uint8_t dw_smem[];
+  T* tile = reinterpret_cast<T*>(dw_smem);
+  const int b = blockIdx.y;
+  const int to0 = blockIdx.x * (kDwR * kDwRuns);
+  const int pad = (K - 1) / 2;
+  const int rows = (kDwR * kDwRuns - 1) * STRIDE + K;    // input frames needed by this CTA
+  const int ti0 = to0 * STRIDE - pad;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+
+  // ---- global -> shared, 16-byte vectors; the (rows x C) slab is contiguous in memory (channels-last) ----
+  constexpr int VEC = 16 / sizeof(T);
+  const T* xb = x + static_cast<size_t>(b) * T_in * C;
+  const int total = rows * C;
+  if (C % VEC == 0) {
+    for (int i = tid * VEC; i < total; i += nthr * VEC) {
+      const int r = i / C;
+      const int tt = ti0 + r;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (tt >= 0 && tt < T_in) val = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(tt) * C + (i - r * C));
+      *reinterpret_cast<uint4*>(tile + i) = val;
+    }
+  } else {
+    for (int i = tid; i < total; i += nthr) {
+      const int r = i / C;
+      const int tt = ti0 + r;
+      tile[i] = (tt >= 0 && tt < T_in) ? xb[static_cast<size_t>(tt) * C + (i - r * C)] : Tr::to(0.f);
+    }
+  }
+  __syncthreads();
+
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  float wk[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) wk[k] = __ldg(w + c * K + k);
+  const float bc = __ldg(bias + c);
+  const int run0 = threadIdx.y * kDwR;                  // first local output of this thread
+  float acc[kDwR];
+#pragma unroll
+  for (int r = 0; r < kDwR; ++r) acc[r] = bc;
+  // input-stationary sweep: every staged input frame is read once and scattered into the outputs it feeds
+  constexpr int in_rows = (kDwR - 1) * STRIDE + K;
+  const T* col = tile + static_cast<size_t>(run0 * STRIDE) * C + c;
+#pragma unroll
+  for (int i = 0; i < in_rows; ++i) {
+    const float v = Tr::from(col[static_cast<size_t>(i) * C]);
+#pragma unroll
+    for (int r = 0; r < kDwR; ++r) {
+      const int k = i - r * STRIDE;            // compile-time after full unrolling
+      if (k >= 0 && k < K) acc[r] = fmaf(v, wk[k], acc[r]);
+    }
+  }
+  T* yb = y + static_cast<size_t>(b) * T_out * C;
+#pragma unroll
+  for (int r = 0; r < kDwR; ++r) {
+    const int to = to0 + run0 + r;
+    if (to < T_out) yb[static_cast<size_t>(to) * C + c] = Tr::to(swishf_(acc[r]));
+  }
+}
+
+template <typename T>
+static int launch_dw_t(const DwConvArgs& a, cudaStream_t stream) {
+  EC_REQUIRE(a.k % 2 == 1 && a.k <= kDwMaxK, "depthwise kernel size must be odd and <= 31");
+  EC_REQUIRE(a.stride == 1 || a.stride == 2, "depthwise stride must be 1 or 2");
+  EC_REQUIRE(a.C <= 256, "depthwise conv supports up to 256 channels per CTA row");   // TODO(large models): channel tiling
+  const int T_out = (a.T - 1) / a.stride + 1;
+  const int cx = round_up(a.C, 32);
+  dim3 block(cx, kDwRuns);
+  dim3 grid(cdiv(T_out, kDwR * kDwRuns), a.B);
+  const int rows = (kDwR * kDwRuns - 1) * a.stride + a.k;
+  const size_t smem = align_up(static_cast<size_t>(rows) * a.C * sizeof(T), 16);
+  const T* x = reinterpret_cast<const T*>(a.x);
+  T* y = reinterpret_cast<T*>(a.y);
+#define EC_DW_CASE(S, KK)                                                                                              \
+  if (a.stride == S && a.k == KK) {                                                                                    \
+    static cudaError_t e = cudaFuncSetAttribute(dwconv_bn_swish_kernel<T, S, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+    EC_CUDA(e);                                                                                                        \
+    dwconv_bn_swish_kernel<T, S, KK><<<grid, block, smem, stream>>>(x, a.w, a.b, a.T, T_out, a.C, y);                  \
+    EC_CUDA(cudaGetLastError());                                                                                       \
+    return EC_OK;                                                                                                      \
+  }
+  EC_DW_CASE(1, 15) EC_DW_CASE(2, 15) EC_DW_CASE(1, 31) EC_DW_CASE(2, 31)
+#undef EC_DW_CASE
+  EC_FAIL("depthwise kernel size " + std::to_string(a.k) + " is not instantiated (15 and 31 are)");
+}
+
+int launch_dwconv_bn_swish(int precision, const DwConvArgs& a, cudaStream_t stream) {
+  if (precision == EC_PREC_TF32) return launch_dw_t<float>(a, stream);
+  if (precision == EC_PREC_BF16) return launch_dw_t<__nv_bfloat16>(a, stream);
+  EC_FAIL("unknown precision");
+}
+
+}  // namespace ec

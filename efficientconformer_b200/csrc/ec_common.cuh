@@ -1,0 +1,127 @@
+// Shared declarations of the effconf_b200 CUDA library (internal).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include "ec_ptx.cuh"
+#include "../../include/effconf_b200.h"
+
+namespace ec {
+
+// ---- error convention: C-ABI functions return 0 on success; message retrievable with ec_last_error() ----------
+void set_error(const std::string& msg);
+#define EC_FAIL(msg)                                                                    \
+  do {                                                                                  \
+    ::ec::set_error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + (msg)); \
+    return EC_ERR;                                                                      \
+  } while (0)
+#define EC_REQUIRE(cond, msg) \
+  do {                        \
+    if (!(cond)) EC_FAIL(msg); \
+  } while (0)
+#define EC_CUDA(call)                                                  \
+  do {                                                                 \
+    cudaError_t _e = (call);                                           \
+    if (_e != cudaSuccess) EC_FAIL(std::string("CUDA: ") + cudaGetErrorString(_e)); \
+  } while (0)
+#define EC_TRY(call)              \
+  do {                            \
+    int _s = (call);              \
+    if (_s != EC_OK) return _s;   \
+  } while (0)
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline int round_up(int a, int b) { return cdiv(a, b) * b; }
+inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// ---- activation storage type: float (TF32 mode, values pre-rounded to 10 mantissa bits) or bf16 ----------------
+template <typename T> struct ActTraits;
+template <> struct ActTraits<float> {
+  static constexpr bool kTf32 = true;
+  static constexpr int kBlockK = 32;  // elements per 128-byte swizzle row
+  static constexpr int kUmmaK = 8;
+  __device__ static float to(float x) { return round_tf32(x); }
+  __device__ static float from(float x) { return x; }
+};
+template <> struct ActTraits<__nv_bfloat16> {
+  static constexpr bool kTf32 = false;
+  static constexpr int kBlockK = 64;
+  static constexpr int kUmmaK = 16;
+  __device__ static __nv_bfloat16 to(float x) { return __float2bfloat16_rn(x); }
+  __device__ static float from(__nv_bfloat16 x) { return __bfloat162float(x); }
+};
+
+// ---- kernel launch entry points (defined in the .cu files; all stream-ordered, never synchronise) --------------
+enum GemmAct { GEMM_ACT_NONE = 0, GEMM_ACT_SWISH = 1 };
+
+struct GemmArgs {
+  const void* A;        // [M, K] row-major, activation type
+  const void* W;        // [N, K] row-major (nn.Linear layout), activation type
+  int M, N, K;
+  const float* bias;    // [N] (GLU: prepared interleaved order) or nullptr
+  float alpha;          // out = alpha * act(acc + bias) + residual
+  int act;              // GemmAct
+  int glu_nb;           // 0: plain.  >0: W rows are tiles of [nb value rows | nb gate rows]; output channel count = glu_channels
+  int glu_channels;
+  const float* residual; int ld_res;   // fp32 [M, *] or nullptr
+  float* out_f32; int ld_out;          // optional fp32 output
+  void* out_act; int ld_act;           // optional activation-type output (rounded)
+};
+int launch_gemm(int precision, const GemmArgs& a, cudaStream_t stream);
+
+struct LayerNormArgs {
+  const float* x; int rows, dim;
+  const float* gamma; const float* beta; float eps;
+  void* y_act; float* y_f32;           // outputs (either may be null): activation type (GEMM operand) / fp32 (residual stream)
+  // optional compacted activation-type copy of every `copy_stride`-th frame of each sequence (conv_res operand)
+  void* copy_out; int copy_stride; int frames_per_seq; int frames_out_per_seq;
+};
+int launch_layernorm(int precision, const LayerNormArgs& a, cudaStream_t stream);
+
+struct AttnArgs {
+  const float* qkv;      // [B*T, 3D] fp32: q | k | v (biases already added)
+  const float* E;        // [2*Tp - G, D] fp32 projected relative sinusoid rows
+  const float* u; const float* v;   // [D]
+  const int* x_len;      // [B] valid frames at this stage, or nullptr
+  int B, T, D, H, G;
+  void* out; int ld_out; // [B*T, D] activation type
+};
+int launch_relpos_attention(int precision, const AttnArgs& a, cudaStream_t stream);
+
+struct DwConvArgs {
+  const void* x;         // [B, T, C] activation type (GLU output)
+  const float* w;        // [C, k] BatchNorm-folded depthwise taps
+  const float* b;        // [C]    BatchNorm-folded bias
+  int B, T, C, k, stride;
+  void* y;               // [B, T_out, C] activation type = swish(conv)
+};
+int launch_dwconv_bn_swish(int precision, const DwConvArgs& a, cudaStream_t stream);
+
+struct SubsampleArgs {
+  const float* mel;      // [B, F, T] fp32
+  const float* w;        // [C, 9] BatchNorm-folded 3x3 taps
+  const float* b;        // [C]
+  int B, F, T, C;
+  void* y;               // [B, T_out, C*F/2] activation type, feature = c*(F/2) + f
+};
+int launch_subsample_conv(int precision, const SubsampleArgs& a, cudaStream_t stream);
+
+int launch_cast_rows(int precision, const float* src, void* dst, size_t n, cudaStream_t stream);   // fp32 -> activation type
+int launch_fold_bn(const float* w, const float* b, const float* g, const float* beta, const float* rm, const float* rv,
+                   float eps, int C, int taps, float* w_out, float* b_out, cudaStream_t stream);
+int launch_glu_interleave(int precision, const float* w, const float* b, int channels, int K, int nb, int tiles,
+                          void* w_out, float* b_out, cudaStream_t stream);
+struct BlockStrides { int n; int s[EC_MAX_BLOCKS]; };
+int launch_stage_lengths(const long long* x_len, int B, int t_mel, const BlockStrides& st, int* out, cudaStream_t stream);
+int launch_i64_to_i32(const long long* src, int n, int* dst, int clamp_max, cudaStream_t stream);
+int launch_i32_to_i64(const int* src, int n, long long* dst, cudaStream_t stream);
+
+int launch_logsoftmax_argmax(const float* logits, int rows, int V, float* lse, int* argmax, cudaStream_t stream);
+int launch_ctc_loss(const float* logits, const float* lse, int B, int T, int V, const int* logits_len, const long long* targets,
+                    int target_stride, const long long* target_len, float* loss_per_utt, float* loss_mean, cudaStream_t stream);
+int launch_greedy_collapse(const int* argmax, int B, int T, const int* logits_len, int* ids, int* counts, cudaStream_t stream);
+
+}  // namespace ec

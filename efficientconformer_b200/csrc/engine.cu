@@ -1,0 +1,531 @@
+// Engine: weight preparation, workspace planning and the kernel sequence of one encoder forward, plus the C ABI.
+//
+// Restates the control flow of reference models/encoders.py:106-142 (ConformerEncoder.forward after the audio front
+// end) and models/blocks.py:119-137 (ConformerBlock.forward) as a fixed, stream-ordered launch sequence that is
+// CUDA-graph capturable: no allocation, no host synchronisation, no data-dependent host control flow.
+#include "ec_common.cuh"
+#include <cstring>
+#include <vector>
+
+namespace ec {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+struct Arena {   // bump allocator over a caller-provided buffer (or a dry run when base == nullptr)
+  uint8_t* base; size_t off;
+  explicit Arena(void* b) : base(reinterpret_cast<uint8_t*>(b)), off(0) {}
+  void* take(size_t bytes) {
+    off = align_up(off, 256);
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+struct FfnW { float *ln_w, *ln_b; void* w1; float* b1; void* w2; float* b2; };
+struct BlockW {
+  FfnW ffn1, ffn2;
+  float *att_ln_w, *att_ln_b, *u, *v; void* wqkv; float* bqkv; void* wo; float* bo; void* wpos; float* bpos;
+  float *conv_ln_w, *conv_ln_b; void* pw1; float* pw1_b; float *dw_w, *dw_b; void* pw2; float* pw2_b;
+  void* res_w; float* res_b;
+  float *norm_w, *norm_b;
+  int glu_nb, glu_tiles;
+};
+struct Weights {
+  float *sub_w, *sub_b; void* lin_w; float* lin_b; void* fc_w; float* fc_b;
+  BlockW blk[EC_MAX_BLOCKS];
+};
+
+}  // namespace ec
+
+namespace ec {
+// kernel categories of one forward (profiling / launch accounting)
+enum ProfCat { PC_SUBSAMPLE = 0, PC_LIN, PC_LAYERNORM, PC_FFN_W1, PC_FFN_W2, PC_QKV, PC_POS, PC_ATTN, PC_OUT, PC_PW1_GLU, PC_DWCONV,
+               PC_RES, PC_PW2, PC_FC, PC_MISC, PC_COUNT };
+static const char* kProfNames[PC_COUNT] = {"subsample_conv", "gemm_sub_linear", "layernorm", "gemm_ffn_w1_swish", "gemm_ffn_w2_res",
+                                           "gemm_qkv", "gemm_pos", "relpos_attention", "gemm_att_out_res", "gemm_pw1_glu",
+                                           "dwconv_bn_swish", "gemm_conv_res", "gemm_pw2_res", "gemm_fc", "misc"};
+struct ProfEntry { int cat; double flops, bytes; cudaEvent_t e0, e1; };
+}  // namespace ec
+
+struct ec_engine {
+  ec_config cfg;
+  int precision;
+  size_t esize;
+  ec::Weights w;
+  size_t weight_bytes;
+  bool prepared;
+  // profiling: CUDA events around every launch of the last forward (eager launches only, not under graph capture)
+  bool prof_enabled = false;
+  std::vector<ec::ProfEntry> prof;
+  std::vector<cudaEvent_t> event_pool;
+  size_t events_used = 0;
+  int last_launches = 0;
+};
+
+namespace ec {
+
+static void pick_glu(int channels, int* nb, int* tiles) {
+  *tiles = cdiv(channels, 128);
+  *nb = round_up(cdiv(channels, *tiles), 8);
+}
+
+// Lays the prepared-weights arena out (dry run when arena == nullptr); fills e->w with pointers.
+static size_t layout_weights(ec_engine* e, void* arena) {
+  Arena a(arena);
+  const ec_config& c = e->cfg;
+  const size_t es = e->esize;
+  Weights& w = e->w;
+  auto f32 = [&](size_t n) { return reinterpret_cast<float*>(a.take(n * 4)); };
+  auto act = [&](size_t n) { return a.take(n * es); };
+  const int C = c.sub_filters, F2 = c.n_mels / 2, D0 = c.blocks[0].dim_model;
+  w.sub_w = f32(C * 9); w.sub_b = f32(C);
+  w.lin_w = act(static_cast<size_t>(D0) * C * F2); w.lin_b = f32(D0);
+  for (int i = 0; i < c.num_blocks; ++i) {
+    const ec_block_cfg& bc = c.blocks[i];
+    const int D = bc.dim_model, De = bc.dim_expand, Fr = bc.ff_ratio;
+    BlockW& b = w.blk[i];
+    auto ffn = [&](FfnW& f, int d) {
+      f.ln_w = f32(d); f.ln_b = f32(d);
+      f.w1 = act(static_cast<size_t>(Fr) * d * d); f.b1 = f32(Fr * d);
+      f.w2 = act(static_cast<size_t>(Fr) * d * d); f.b2 = f32(d);
+    };
+    ffn(b.ffn1, D);
+    b.att_ln_w = f32(D); b.att_ln_b = f32(D); b.u = f32(D); b.v = f32(D);
+    b.wqkv = act(static_cast<size_t>(3) * D * D); b.bqkv = f32(3 * D);
+    b.wo = act(static_cast<size_t>(D) * D); b.bo = f32(D);
+    b.wpos = act(static_cast<size_t>(D) * D); b.bpos = f32(D);
+    b.conv_ln_w = f32(D); b.conv_ln_b = f32(D);
+    pick_glu(De, &b.glu_nb, &b.glu_tiles);
+    b.pw1 = act(static_cast<size_t>(b.glu_tiles) * 2 * b.glu_nb * D); b.pw1_b = f32(b.glu_tiles * 2 * b.glu_nb);
+    b.dw_w = f32(De * bc.kernel_size); b.dw_b = f32(De);
+    b.pw2 = act(static_cast<size_t>(De) * De); b.pw2_b = f32(De);
+    if (D != De) { b.res_w = act(static_cast<size_t>(De) * D); b.res_b = f32(De); } else { b.res_w = nullptr; b.res_b = nullptr; }
+    ffn(b.ffn2, De);
+    b.norm_w = f32(De); b.norm_b = f32(De);
+  }
+  if (c.vocab > 0) {
+    const int Dl = c.blocks[c.num_blocks - 1].dim_expand;
+    w.fc_w = act(static_cast<size_t>(c.vocab) * Dl); w.fc_b = f32(c.vocab);
+  } else { w.fc_w = nullptr; w.fc_b = nullptr; }
+  return align_up(a.off, 256);
+}
+
+struct Shapes {   // per-block frame counts for one (batch, t_mel)
+  int t0;                         // frames after subsampling
+  int t_in[EC_MAX_BLOCKS], t_out[EC_MAX_BLOCKS];
+  int t_final;
+};
+static void compute_shapes(const ec_config& c, int t_mel, Shapes* s) {
+  int t = (t_mel - 1) / 2 + 1;
+  s->t0 = t;
+  for (int i = 0; i < c.num_blocks; ++i) {
+    s->t_in[i] = t;
+    if (c.blocks[i].conv_stride > 1) t = (t - 1) / c.blocks[i].conv_stride + 1;
+    s->t_out[i] = t;
+  }
+  s->t_final = t;
+}
+
+struct Workspace {
+  int* lens; void* sub_a; float *xa, *xb; void *xn, *xs, *h; float* qkv; float* ebuf; void *o, *gl, *hc; float* r;
+  size_t bytes;
+};
+static void layout_workspace(const ec_engine* e, int B, int t_mel, void* base, Workspace* ws) {
+  const ec_config& c = e->cfg;
+  const size_t es = e->esize;
+  Shapes sh; compute_shapes(c, t_mel, &sh);
+  size_t mx_x = static_cast<size_t>(B) * sh.t0 * c.blocks[0].dim_model, mx_h = 0, mx_qkv = 0, mx_e = 0, mx_g = 0, mx_hc = 0, mx_xs = 0;
+  for (int i = 0; i < c.num_blocks; ++i) {
+    const ec_block_cfg& b = c.blocks[i];
+    const size_t Mi = static_cast<size_t>(B) * sh.t_in[i], Mo = static_cast<size_t>(B) * sh.t_out[i];
+    mx_x = std::max(mx_x, std::max(Mi * b.dim_model, Mo * b.dim_expand));
+    mx_h = std::max(mx_h, std::max(Mi * b.dim_model, Mo * b.dim_expand) * b.ff_ratio);
+    mx_qkv = std::max(mx_qkv, Mi * 3 * b.dim_model);
+    const int P = (b.group_size - sh.t_in[i] % b.group_size) % b.group_size;
+    mx_e = std::max(mx_e, static_cast<size_t>(2 * (sh.t_in[i] + P) - b.group_size) * b.dim_model);
+    mx_g = std::max(mx_g, Mi * b.dim_expand);
+    mx_hc = std::max(mx_hc, Mo * b.dim_expand);
+    if (b.dim_model != b.dim_expand) mx_xs = std::max(mx_xs, Mo * b.dim_model);
+  }
+  Arena a(base);
+  ws->lens = reinterpret_cast<int*>(a.take(sizeof(int) * (c.num_blocks + 1) * B));
+  ws->sub_a = a.take(static_cast<size_t>(B) * sh.t0 * c.sub_filters * (c.n_mels / 2) * es);
+  ws->xa = reinterpret_cast<float*>(a.take(mx_x * 4));
+  ws->xb = reinterpret_cast<float*>(a.take(mx_x * 4));
+  ws->xn = a.take(mx_x * es);
+  ws->xs = a.take(std::max<size_t>(mx_xs, 1) * es);
+  ws->h = a.take(mx_h * es);
+  ws->qkv = reinterpret_cast<float*>(a.take(mx_qkv * 4));
+  ws->ebuf = reinterpret_cast<float*>(a.take(mx_e * 4));
+  ws->o = a.take(mx_x * es);
+  ws->gl = a.take(mx_g * es);
+  ws->hc = a.take(mx_hc * es);
+  ws->r = reinterpret_cast<float*>(a.take(std::max<size_t>(mx_hc, 1) * 4));
+  ws->bytes = align_up(a.off, 256);
+}
+
+// ---- launch accounting / optional per-launch CUDA-event timing -------------------------------------------------------
+struct ProfScope {
+  ec_engine* e; cudaStream_t st; bool on;
+  ProfScope(ec_engine* e_, cudaStream_t st_, int cat, double flops, double bytes) : e(e_), st(st_), on(e_->prof_enabled) {
+    e->last_launches++;
+    if (!on) return;
+    auto ev = [&]() {
+      if (e->events_used == e->event_pool.size()) { cudaEvent_t x; cudaEventCreate(&x); e->event_pool.push_back(x); }
+      return e->event_pool[e->events_used++];
+    };
+    ProfEntry pe{cat, flops, bytes, ev(), ev()};
+    cudaEventRecord(pe.e0, st);
+    e->prof.push_back(pe);
+  }
+  ~ProfScope() { if (on) cudaEventRecord(e->prof.back().e1, st); }
+};
+
+static int gemm(ec_engine* e, cudaStream_t st, int cat, const void* A, const void* W, int M, int N, int K, const float* bias, float alpha,
+                int act, const float* residual, float* out_f32, void* out_act, int glu_nb = 0, int glu_channels = 0) {
+  GemmArgs g{};
+  g.A = A; g.W = W; g.M = M; g.N = N; g.K = K; g.bias = bias; g.alpha = alpha; g.act = act;
+  g.glu_nb = glu_nb; g.glu_channels = glu_channels;
+  const int ncols = glu_nb > 0 ? glu_channels : N;
+  g.residual = residual; g.ld_res = ncols; g.out_f32 = out_f32; g.ld_out = ncols; g.out_act = out_act; g.ld_act = ncols;
+  // algorithmic work: real (unpadded) dims; every tensor crosses memory once
+  const double n_real = glu_nb > 0 ? 2.0 * glu_channels : N;
+  const double flops = 2.0 * M * n_real * K;
+  const double bytes = (static_cast<double>(M) * K + n_real * K) * e->esize + static_cast<double>(M) * ncols *
+                       ((out_f32 ? 4 : 0) + (out_act ? e->esize : 0) + (residual ? 4 : 0));
+  ProfScope ps(e, st, cat, flops, bytes);
+  return launch_gemm(e->precision, g, st);
+}
+static int lnorm(ec_engine* e, cudaStream_t st, const float* x, int rows, int dim, const float* g, const float* b, void* y_act,
+                 float* y_f32, void* copy_out = nullptr, int copy_stride = 1, int fps = 0, int fops = 0) {
+  LayerNormArgs a{};
+  a.x = x; a.rows = rows; a.dim = dim; a.gamma = g; a.beta = b; a.eps = 1e-6f; a.y_act = y_act; a.y_f32 = y_f32;
+  a.copy_out = copy_out; a.copy_stride = copy_stride; a.frames_per_seq = fps; a.frames_out_per_seq = fops;
+  const double el = static_cast<double>(rows) * dim;
+  ProfScope ps(e, st, PC_LAYERNORM, 8.0 * el, el * (4 + (y_act ? e->esize : 0) + (y_f32 ? 4 : 0)) + (copy_out ? el / copy_stride * e->esize : 0));
+  return launch_layernorm(e->precision, a, st);
+}
+
+}  // namespace ec
+
+using namespace ec;
+
+extern "C" {
+
+const char* ec_last_error(void) { return g_last_error.c_str(); }
+int ec_version(void) { return 100; }
+
+int ec_device_check(void) {
+  int dev = 0;
+  EC_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  EC_CUDA(cudaGetDeviceProperties(&prop, dev));
+  EC_REQUIRE(prop.major == 10, std::string("effconf_b200 needs an sm_100 (B200) device; found sm_") + std::to_string(prop.major) +
+                                   std::to_string(prop.minor) + " -- there is no fallback path");
+  return EC_OK;
+}
+
+int ec_engine_create(const ec_config* cfg, int precision, ec_engine** out) {
+  EC_REQUIRE(cfg != nullptr && out != nullptr, "null argument");
+  EC_REQUIRE(precision == EC_PREC_TF32 || precision == EC_PREC_BF16, "unknown precision");
+  EC_REQUIRE(cfg->num_blocks >= 1 && cfg->num_blocks <= EC_MAX_BLOCKS, "num_blocks out of range");
+  EC_REQUIRE(cfg->n_mels > 0 && cfg->n_mels % 2 == 0 && cfg->sub_filters > 0, "bad front-end config");
+  for (int i = 0; i < cfg->num_blocks; ++i) {
+    const ec_block_cfg& b = cfg->blocks[i];
+    EC_REQUIRE(b.dim_model > 0 && b.dim_expand > 0 && b.num_heads > 0 && b.ff_ratio > 0, "bad block dims");
+    EC_REQUIRE(b.group_size % 2 == 1, "attention group size must be odd");
+    EC_REQUIRE((b.group_size * b.dim_model) % b.num_heads == 0, "G*D must be divisible by H");
+    EC_REQUIRE(b.conv_stride == 1 || b.conv_stride == 2, "conv_stride must be 1 or 2");
+    EC_REQUIRE(b.conv_stride == 1 || b.dim_model != b.dim_expand, "strided block without expansion (MaxPool residual) is not implemented");
+    if (i > 0) EC_REQUIRE(cfg->blocks[i - 1].dim_expand == b.dim_model, "block dims do not chain");
+  }
+  ec_engine* e = new ec_engine();
+  e->cfg = *cfg; e->precision = precision; e->esize = precision == EC_PREC_TF32 ? 4 : 2; e->prepared = false;
+  e->weight_bytes = layout_weights(e, nullptr);
+  *out = e;
+  return EC_OK;
+}
+void ec_engine_destroy(ec_engine* e) {
+  if (e == nullptr) return;
+  for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
+  delete e;
+}
+size_t ec_engine_weight_bytes(const ec_engine* e) { return e->weight_bytes; }
+size_t ec_engine_workspace_bytes(const ec_engine* e, int batch, int t_mel) {
+  Workspace ws; layout_workspace(e, batch, t_mel, nullptr, &ws);
+  return ws.bytes;
+}
+int ec_engine_out_frames(const ec_engine* e, int t_mel) {
+  Shapes sh; compute_shapes(e->cfg, t_mel, &sh);
+  return sh.t_final;
+}
+int ec_engine_relpos_rows(const ec_engine* e, int t_mel, int32_t* rows_per_block, int32_t* frames_per_block) {
+  Shapes sh; compute_shapes(e->cfg, t_mel, &sh);
+  for (int i = 0; i < e->cfg.num_blocks; ++i) {
+    const int G = e->cfg.blocks[i].group_size, T = sh.t_in[i];
+    const int P = (G - T % G) % G;
+    if (rows_per_block) rows_per_block[i] = 2 * (T + P) - G;
+    if (frames_per_block) frames_per_block[i] = T;
+  }
+  return EC_OK;
+}
+
+int ec_engine_prepare(ec_engine* e, const ec_raw_weights* raw, void* arena, void* stream_) {
+  EC_REQUIRE(e && raw && arena, "null argument");
+  EC_TRY(ec_device_check());
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  layout_weights(e, arena);
+  const ec_config& c = e->cfg;
+  const int prec = e->precision;
+  Weights& w = e->w;
+  auto cp = [&](float* dst, const float* src, size_t n) -> int {
+    EC_REQUIRE(src != nullptr, "missing raw weight pointer");
+    EC_CUDA(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, st));
+    return EC_OK;
+  };
+  auto cast = [&](void* dst, const float* src, size_t n) -> int {
+    EC_REQUIRE(src != nullptr, "missing raw weight pointer");
+    return launch_cast_rows(prec, src, dst, n, st);
+  };
+  const int C = c.sub_filters, F2 = c.n_mels / 2, D0 = c.blocks[0].dim_model;
+  EC_REQUIRE(raw->sub_conv_w && raw->sub_conv_b && raw->sub_bn_w && raw->sub_bn_b && raw->sub_bn_rm && raw->sub_bn_rv, "missing subsampling weights");
+  EC_TRY(launch_fold_bn(raw->sub_conv_w, raw->sub_conv_b, raw->sub_bn_w, raw->sub_bn_b, raw->sub_bn_rm, raw->sub_bn_rv, 1e-5f, C, 9, w.sub_w, w.sub_b, st));
+  EC_TRY(cast(w.lin_w, raw->lin_w, static_cast<size_t>(D0) * C * F2));
+  EC_TRY(cp(w.lin_b, raw->lin_b, D0));
+  for (int i = 0; i < c.num_blocks; ++i) {
+    const ec_block_cfg& bc = c.blocks[i];
+    const ec_block_raw& r = raw->blocks[i];
+    BlockW& b = w.blk[i];
+    const int D = bc.dim_model, De = bc.dim_expand, Fr = bc.ff_ratio;
+    auto ffn = [&](FfnW& f, const ec_ffn_raw& fr, int d) -> int {
+      EC_TRY(cp(f.ln_w, fr.ln_w, d)); EC_TRY(cp(f.ln_b, fr.ln_b, d));
+      EC_TRY(cast(f.w1, fr.w1, static_cast<size_t>(Fr) * d * d)); EC_TRY(cp(f.b1, fr.b1, Fr * d));
+      EC_TRY(cast(f.w2, fr.w2, static_cast<size_t>(Fr) * d * d)); EC_TRY(cp(f.b2, fr.b2, d));
+      return EC_OK;
+    };
+    EC_TRY(ffn(b.ffn1, r.ffn1, D));
+    EC_TRY(cp(b.att_ln_w, r.att_ln_w, D)); EC_TRY(cp(b.att_ln_b, r.att_ln_b, D));
+    EC_TRY(cp(b.u, r.u, D)); EC_TRY(cp(b.v, r.v, D));
+    const size_t dd = static_cast<size_t>(D) * D;
+    uint8_t* wqkv = reinterpret_cast<uint8_t*>(b.wqkv);
+    EC_TRY(cast(wqkv, r.wq, dd)); EC_TRY(cast(wqkv + dd * e->esize, r.wk, dd)); EC_TRY(cast(wqkv + 2 * dd * e->esize, r.wv, dd));
+    EC_TRY(cp(b.bqkv, r.bq, D)); EC_TRY(cp(b.bqkv + D, r.bk, D)); EC_TRY(cp(b.bqkv + 2 * D, r.bv, D));
+    EC_TRY(cast(b.wo, r.wo, dd)); EC_TRY(cp(b.bo, r.bo, D));
+    EC_TRY(cast(b.wpos, r.wpos, dd)); EC_TRY(cp(b.bpos, r.bpos, D));
+    EC_TRY(cp(b.conv_ln_w, r.conv_ln_w, D)); EC_TRY(cp(b.conv_ln_b, r.conv_ln_b, D));
+    EC_REQUIRE(r.pw1_w && r.pw1_b, "missing pw1 weights");
+    EC_TRY(launch_glu_interleave(prec, r.pw1_w, r.pw1_b, De, D, b.glu_nb, b.glu_tiles, b.pw1, b.pw1_b, st));
+    EC_REQUIRE(r.dw_w && r.dw_b && r.bn_w && r.bn_b && r.bn_rm && r.bn_rv, "missing depthwise / BatchNorm weights");
+    EC_TRY(launch_fold_bn(r.dw_w, r.dw_b, r.bn_w, r.bn_b, r.bn_rm, r.bn_rv, 1e-5f, De, bc.kernel_size, b.dw_w, b.dw_b, st));
+    EC_TRY(cast(b.pw2, r.pw2_w, static_cast<size_t>(De) * De)); EC_TRY(cp(b.pw2_b, r.pw2_b, De));
+    if (D != De) { EC_TRY(cast(b.res_w, r.res_w, static_cast<size_t>(De) * D)); EC_TRY(cp(b.res_b, r.res_b, De)); }
+    EC_TRY(ffn(b.ffn2, r.ffn2, De));
+    EC_TRY(cp(b.norm_w, r.norm_w, De)); EC_TRY(cp(b.norm_b, r.norm_b, De));
+  }
+  if (c.vocab > 0) {
+    const int Dl = c.blocks[c.num_blocks - 1].dim_expand;
+    EC_TRY(cast(w.fc_w, raw->fc_w, static_cast<size_t>(c.vocab) * Dl)); EC_TRY(cp(w.fc_b, raw->fc_b, c.vocab));
+  }
+  e->prepared = true;
+  return EC_OK;
+}
+
+int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const long long* x_len, const void* const* relpos,
+                      void* workspace, float* out_x, float* logits, long long* out_len, void* stream_) {
+  EC_REQUIRE(e && mel && relpos && workspace, "null argument");
+  EC_REQUIRE(e->prepared, "ec_engine_prepare has not been called");
+  EC_REQUIRE(B > 0 && t_mel > 0, "empty batch");
+  EC_REQUIRE(out_x != nullptr || logits != nullptr, "no output requested");
+  EC_REQUIRE(logits == nullptr || e->cfg.vocab > 0, "engine was built without an fc head");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  const ec_config& c = e->cfg;
+  const Weights& w = e->w;
+  const int prec = e->precision;
+  Shapes sh; compute_shapes(c, t_mel, &sh);
+  Workspace ws; layout_workspace(e, B, t_mel, workspace, &ws);
+
+  e->last_launches = 0;
+  e->prof.clear(); e->events_used = 0;
+  if (e->prof_enabled) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    EC_REQUIRE(cs == cudaStreamCaptureStatusNone, "profiling mode cannot be used under CUDA graph capture");
+  }
+  const double es = static_cast<double>(e->esize);
+
+  BlockStrides bs{}; bs.n = c.num_blocks;
+  for (int i = 0; i < c.num_blocks; ++i) bs.s[i] = c.blocks[i].conv_stride;
+  { ProfScope ps(e, st, PC_MISC, 0, 0); EC_TRY(launch_stage_lengths(x_len, B, t_mel, bs, ws.lens, st)); }
+
+  // ---- front end: Conv2d+BN+Swish producer, then Linear (K = C*F/2) ----
+  const int feat = c.sub_filters * (c.n_mels / 2);
+  {
+    SubsampleArgs sa{mel, w.sub_w, w.sub_b, B, c.n_mels, t_mel, c.sub_filters, ws.sub_a};
+    ProfScope ps(e, st, PC_SUBSAMPLE, 18.0 * B * sh.t0 * feat, 4.0 * B * c.n_mels * t_mel + es * B * sh.t0 * feat);
+    EC_TRY(launch_subsample_conv(prec, sa, st));
+  }
+  const int D0 = c.blocks[0].dim_model;
+  float* x = ws.xa; float* x_alt = ws.xb;
+  EC_TRY(gemm(e, st, PC_LIN, ws.sub_a, w.lin_w, B * sh.t0, D0, feat, w.lin_b, 1.f, GEMM_ACT_NONE, nullptr, x, nullptr));
+
+  for (int i = 0; i < c.num_blocks; ++i) {
+    const ec_block_cfg& bc = c.blocks[i];
+    const BlockW& b = w.blk[i];
+    const int D = bc.dim_model, De = bc.dim_expand, Fr = bc.ff_ratio;
+    const int T = sh.t_in[i], To = sh.t_out[i];
+    const int M = B * T, Mo = B * To;
+    const int* lens = ws.lens + static_cast<size_t>(i) * B;
+    // FFN1: x1 = x + 0.5 * W2 swish(W1 LN(x))
+    EC_TRY(lnorm(e, st, x, M, D, b.ffn1.ln_w, b.ffn1.ln_b, ws.xn, nullptr));
+    EC_TRY(gemm(e, st, PC_FFN_W1, ws.xn, b.ffn1.w1, M, Fr * D, D, b.ffn1.b1, 1.f, GEMM_ACT_SWISH, nullptr, nullptr, ws.h));
+    EC_TRY(gemm(e, st, PC_FFN_W2, ws.h, b.ffn1.w2, M, D, Fr * D, b.ffn1.b2, 0.5f, GEMM_ACT_NONE, x, x_alt, nullptr));
+    std::swap(x, x_alt);
+    // MHSA: x2 = x1 + Wo attn(LN(x1))
+    EC_TRY(lnorm(e, st, x, M, D, b.att_ln_w, b.att_ln_b, ws.xn, nullptr));
+    EC_TRY(gemm(e, st, PC_QKV, ws.xn, b.wqkv, M, 3 * D, D, b.bqkv, 1.f, GEMM_ACT_NONE, nullptr, ws.qkv, nullptr));
+    const int G = bc.group_size, P = (G - T % G) % G, e_rows = 2 * (T + P) - G;
+    EC_REQUIRE(relpos[i] != nullptr, "missing relative position table");
+    EC_TRY(gemm(e, st, PC_POS, relpos[i], b.wpos, e_rows, D, D, b.bpos, 1.f, GEMM_ACT_NONE, nullptr, ws.ebuf, nullptr));
+    {
+      AttnArgs aa{ws.qkv, ws.ebuf, b.u, b.v, lens, B, T, D, bc.num_heads, G, ws.o, D};
+      const double Tg = static_cast<double>(T + P) / G, dh = static_cast<double>(G) * D / bc.num_heads;
+      ProfScope ps(e, st, PC_ATTN, B * bc.num_heads * (4.0 * Tg * Tg * dh + 2.0 * Tg * (2 * Tg - 1) * dh),
+                   4.0 * M * 3 * D + 4.0 * e_rows * D + es * M * D);
+      EC_TRY(launch_relpos_attention(prec, aa, st));
+    }
+    EC_TRY(gemm(e, st, PC_OUT, ws.o, b.wo, M, D, D, b.bo, 1.f, GEMM_ACT_NONE, x, x_alt, nullptr));
+    std::swap(x, x_alt);
+    // Conv module: x3 = conv_res(x2) + pw2 swish(bn(dw(glu(pw1 LN(x2)))))
+    const bool proj = D != De;
+    EC_TRY(lnorm(e, st, x, M, D, b.conv_ln_w, b.conv_ln_b, ws.xn, nullptr, proj ? ws.xs : nullptr, bc.conv_stride, T, To));
+    EC_TRY(gemm(e, st, PC_PW1_GLU, ws.xn, b.pw1, M, b.glu_tiles * 2 * b.glu_nb, D, b.pw1_b, 1.f, GEMM_ACT_NONE, nullptr, nullptr, ws.gl, b.glu_nb, De));
+    {
+      DwConvArgs da{ws.gl, b.dw_w, b.dw_b, B, T, De, bc.kernel_size, bc.conv_stride, ws.hc};
+      ProfScope ps(e, st, PC_DWCONV, 2.0 * Mo * De * bc.kernel_size, es * (static_cast<double>(M) * De + static_cast<double>(Mo) * De));
+      EC_TRY(launch_dwconv_bn_swish(prec, da, st));
+    }
+    const float* res = x;
+    if (proj) {
+      EC_TRY(gemm(e, st, PC_RES, ws.xs, b.res_w, Mo, De, D, b.res_b, 1.f, GEMM_ACT_NONE, nullptr, ws.r, nullptr));
+      res = ws.r;
+    }
+    EC_TRY(gemm(e, st, PC_PW2, ws.hc, b.pw2, Mo, De, De, b.pw2_b, 1.f, GEMM_ACT_NONE, res, x_alt, nullptr));
+    std::swap(x, x_alt);
+    // FFN2 + block LayerNorm
+    EC_TRY(lnorm(e, st, x, Mo, De, b.ffn2.ln_w, b.ffn2.ln_b, ws.xn, nullptr));
+    EC_TRY(gemm(e, st, PC_FFN_W1, ws.xn, b.ffn2.w1, Mo, Fr * De, De, b.ffn2.b1, 1.f, GEMM_ACT_SWISH, nullptr, nullptr, ws.h));
+    EC_TRY(gemm(e, st, PC_FFN_W2, ws.h, b.ffn2.w2, Mo, De, Fr * De, b.ffn2.b2, 0.5f, GEMM_ACT_NONE, x, x_alt, nullptr));
+    std::swap(x, x_alt);
+    const bool last = i == c.num_blocks - 1;
+    float* y = (last && out_x != nullptr) ? out_x : x_alt;
+    EC_TRY(lnorm(e, st, x, Mo, De, b.norm_w, b.norm_b, (last && logits != nullptr) ? ws.xn : nullptr, y));
+    if (!(last && out_x != nullptr)) std::swap(x, x_alt);
+  }
+  if (logits != nullptr) {
+    const int Dl = c.blocks[c.num_blocks - 1].dim_expand;
+    EC_TRY(gemm(e, st, PC_FC, ws.xn, w.fc_w, B * sh.t_final, c.vocab, Dl, w.fc_b, 1.f, GEMM_ACT_NONE, nullptr, logits, nullptr));
+  }
+  if (out_len != nullptr) { ProfScope ps(e, st, PC_MISC, 0, 0); EC_TRY(launch_i32_to_i64(ws.lens + static_cast<size_t>(c.num_blocks) * B, B, out_len, st)); }
+  return EC_OK;
+}
+
+// ---------------------------------------------------------------- profiling / accounting
+int ec_profile_categories(void) { return PC_COUNT; }
+const char* ec_profile_category_name(int cat) { return (cat >= 0 && cat < PC_COUNT) ? kProfNames[cat] : ""; }
+int ec_engine_set_profiling(ec_engine* e, int enabled) { e->prof_enabled = enabled != 0; return EC_OK; }
+int ec_engine_last_launches(const ec_engine* e) { return e->last_launches; }
+/* sums the CUDA-event durations of the last (eager, profiled) forward per category; synchronises the recorded events */
+int ec_engine_profile_read(ec_engine* e, double* ms, double* flops, double* bytes, int32_t* launches) {
+  for (int i = 0; i < PC_COUNT; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
+  for (const ProfEntry& pe : e->prof) {
+    EC_CUDA(cudaEventSynchronize(pe.e1));
+    float t = 0.f;
+    EC_CUDA(cudaEventElapsedTime(&t, pe.e0, pe.e1));
+    ms[pe.cat] += t; flops[pe.cat] += pe.flops; bytes[pe.cat] += pe.bytes; launches[pe.cat] += 1;
+  }
+  return EC_OK;
+}
+
+// ---------------------------------------------------------------- CTC head
+size_t ec_ctc_scratch_bytes(int batch, int t, int vocab) {
+  (void)vocab;
+  return align_up(static_cast<size_t>(batch) * t * 4, 256) * 2 + align_up(static_cast<size_t>(batch) * 4, 256);
+}
+static void ctc_scratch(void* scratch, int B, int T, float** lse, int** amax, int** len32) {
+  uint8_t* p = reinterpret_cast<uint8_t*>(scratch);
+  *lse = reinterpret_cast<float*>(p);
+  *amax = reinterpret_cast<int*>(p + align_up(static_cast<size_t>(B) * T * 4, 256));
+  *len32 = reinterpret_cast<int*>(p + 2 * align_up(static_cast<size_t>(B) * T * 4, 256));
+}
+int ec_ctc_loss(const float* logits, int B, int T, int V, const long long* logits_len, const long long* targets, int target_stride,
+                const long long* target_len, void* scratch, float* loss_per_utt, float* loss_mean, void* stream_) {
+  EC_REQUIRE(logits && logits_len && targets && target_len && scratch && loss_per_utt, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  float* lse; int* amax; int* len32;
+  ctc_scratch(scratch, B, T, &lse, &amax, &len32);
+  EC_TRY(launch_i64_to_i32(logits_len, B, len32, T, st));
+  EC_TRY(launch_logsoftmax_argmax(logits, B * T, V, lse, amax, st));
+  return launch_ctc_loss(logits, lse, B, T, V, len32, targets, target_stride, target_len, loss_per_utt, loss_mean, st);
+}
+int ec_ctc_greedy(const float* logits, int B, int T, int V, const long long* logits_len, void* scratch, int32_t* ids, int32_t* counts,
+                  void* stream_) {
+  EC_REQUIRE(logits && logits_len && scratch && ids && counts, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  float* lse; int* amax; int* len32;
+  ctc_scratch(scratch, B, T, &lse, &amax, &len32);
+  EC_TRY(launch_i64_to_i32(logits_len, B, len32, T, st));
+  EC_TRY(launch_logsoftmax_argmax(logits, B * T, V, lse, amax, st));
+  return launch_greedy_collapse(amax, B, T, len32, ids, counts, st);
+}
+
+// ---------------------------------------------------------------- single-operator entry points
+int ec_op_cast(int precision, const float* src, void* dst, size_t n, void* stream) {
+  return launch_cast_rows(precision, src, dst, n, reinterpret_cast<cudaStream_t>(stream));
+}
+int ec_op_layernorm(int precision, const float* x, int rows, int dim, const float* gamma, const float* beta, float eps, void* y_act,
+                    float* y_f32, void* stream) {
+  LayerNormArgs a{};
+  a.x = x; a.rows = rows; a.dim = dim; a.gamma = gamma; a.beta = beta; a.eps = eps; a.y_act = y_act; a.y_f32 = y_f32;
+  return launch_layernorm(precision, a, reinterpret_cast<cudaStream_t>(stream));
+}
+int ec_op_gemm(int precision, const void* A, const void* W, int M, int N, int K, const float* bias, float alpha, int act,
+               const float* residual, float* out_f32, void* out_act, void* stream) {
+  GemmArgs g{};
+  g.A = A; g.W = W; g.M = M; g.N = N; g.K = K; g.bias = bias; g.alpha = alpha; g.act = act;
+  g.residual = residual; g.ld_res = N; g.out_f32 = out_f32; g.ld_out = N; g.out_act = out_act; g.ld_act = N;
+  return launch_gemm(precision, g, reinterpret_cast<cudaStream_t>(stream));
+}
+int ec_op_pointwise_glu(int precision, const void* A, const float* w_raw, const float* b_raw, int M, int channels, int K, void* w_scratch,
+                        float* b_scratch, void* out_act, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  int nb, tiles; pick_glu(channels, &nb, &tiles);
+  EC_TRY(launch_glu_interleave(precision, w_raw, b_raw, channels, K, nb, tiles, w_scratch, b_scratch, st));
+  GemmArgs g{};
+  g.A = A; g.W = w_scratch; g.M = M; g.N = tiles * 2 * nb; g.K = K; g.bias = b_scratch; g.alpha = 1.f; g.act = GEMM_ACT_NONE;
+  g.glu_nb = nb; g.glu_channels = channels; g.out_act = out_act; g.ld_act = channels;
+  return launch_gemm(precision, g, st);
+}
+int ec_op_glu_scratch_rows(int channels) { int nb, tiles; pick_glu(channels, &nb, &tiles); return tiles * 2 * nb; }
+int ec_op_fold_bn(const float* w, const float* b, const float* g, const float* beta, const float* rm, const float* rv, float eps, int C,
+                  int taps, float* w_out, float* b_out, void* stream) {
+  return launch_fold_bn(w, b, g, beta, rm, rv, eps, C, taps, w_out, b_out, reinterpret_cast<cudaStream_t>(stream));
+}
+int ec_op_relpos_attention(int precision, const float* qkv, const float* E, const float* u, const float* v, const int32_t* x_len,
+                           int batch, int t, int dim, int heads, int group, void* out, void* stream) {
+  AttnArgs a{qkv, E, u, v, x_len, batch, t, dim, heads, group, out, dim};
+  return launch_relpos_attention(precision, a, reinterpret_cast<cudaStream_t>(stream));
+}
+int ec_op_dwconv_bn_swish(int precision, const void* x, const float* w_folded, const float* b_folded, int batch, int t, int channels,
+                          int k, int stride, void* y, void* stream) {
+  DwConvArgs a{x, w_folded, b_folded, batch, t, channels, k, stride, y};
+  return launch_dwconv_bn_swish(precision, a, reinterpret_cast<cudaStream_t>(stream));
+}
+int ec_op_subsample_conv(int precision, const float* mel, const float* w_folded, const float* b_folded, int batch, int n_mels, int t,
+                         int channels, void* y, void* stream) {
+  SubsampleArgs a{mel, w_folded, b_folded, batch, n_mels, t, channels, y};
+  return launch_subsample_conv(precision, a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

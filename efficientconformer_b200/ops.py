@@ -1,0 +1,98 @@
+"""Tensor-level wrappers of the single-operator C entry points (ec_op_*), used by the unit parity tests.
+Every function takes/returns CUDA tensors and launches on the current stream; nothing here has a fallback."""
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr, stream_ptr, act_dtype, PRECISIONS
+
+
+def _p(precision):
+    return PRECISIONS[precision] if isinstance(precision, str) else precision
+
+
+def cast(x, precision):
+    """fp32 -> activation type (TF32-rounded fp32 or bf16)."""
+    pr = _p(precision)
+    x = x.float().contiguous()
+    out = torch.empty(x.shape, dtype=act_dtype(pr), device=x.device)
+    check(lib().ec_op_cast(pr, ptr(x), ptr(out), x.numel(), stream_ptr()))
+    return out
+
+
+def layernorm(x, gamma, beta, precision, eps=1e-6, want_f32=True, want_act=True):
+    pr = _p(precision)
+    x = x.float().contiguous()
+    rows, dim = x.numel() // x.shape[-1], x.shape[-1]
+    ya = torch.empty(x.shape, dtype=act_dtype(pr), device=x.device) if want_act else None
+    yf = torch.empty_like(x) if want_f32 else None
+    check(lib().ec_op_layernorm(pr, ptr(x), rows, dim, ptr(gamma.float().contiguous()), ptr(beta.float().contiguous()), eps,
+                                ptr(ya), ptr(yf), stream_ptr()))
+    return ya, yf
+
+
+def gemm(a_act, w_act, bias, precision, alpha=1.0, act=0, residual=None, want_f32=True, want_act=False):
+    """a_act [M,K], w_act [N,K] already in the activation type."""
+    pr = _p(precision)
+    M, K = a_act.shape
+    N = w_act.shape[0]
+    of = torch.empty(M, N, dtype=torch.float32, device=a_act.device) if want_f32 else None
+    oa = torch.empty(M, N, dtype=act_dtype(pr), device=a_act.device) if want_act else None
+    check(lib().ec_op_gemm(pr, ptr(a_act), ptr(w_act), M, N, K, ptr(bias), alpha, act, ptr(residual), ptr(of), ptr(oa), stream_ptr()))
+    return of, oa
+
+
+def pointwise_glu(a_act, w_raw, b_raw, precision):
+    pr = _p(precision)
+    M, K = a_act.shape
+    Cc = w_raw.shape[0] // 2
+    rows = lib().ec_op_glu_scratch_rows(Cc)
+    ws = torch.empty(rows, K, dtype=act_dtype(pr), device=a_act.device)
+    bs = torch.empty(rows, dtype=torch.float32, device=a_act.device)
+    out = torch.empty(M, Cc, dtype=act_dtype(pr), device=a_act.device)
+    w2 = w_raw.float().reshape(2 * Cc, K).contiguous()
+    check(lib().ec_op_pointwise_glu(pr, ptr(a_act), ptr(w2), ptr(b_raw.float().contiguous()), M, Cc, K, ptr(ws), ptr(bs), ptr(out),
+                                    stream_ptr()))
+    return out
+
+
+def fold_bn(w, b, g, beta, rm, rv, eps=1e-5):
+    Cc = w.shape[0]
+    taps = w.numel() // Cc
+    wo = torch.empty(Cc, taps, dtype=torch.float32, device=w.device)
+    bo = torch.empty(Cc, dtype=torch.float32, device=w.device)
+    check(lib().ec_op_fold_bn(ptr(w.float().contiguous()), ptr(b.float().contiguous()), ptr(g.float().contiguous()),
+                              ptr(beta.float().contiguous()), ptr(rm.float().contiguous()), ptr(rv.float().contiguous()), eps, Cc, taps,
+                              ptr(wo), ptr(bo), stream_ptr()))
+    return wo, bo
+
+
+def relpos_attention(qkv, E, u, v, x_len, heads, group, precision):
+    """qkv [B,T,3D] fp32, E [2Tp-G, D] fp32, x_len int32 [B] or None -> [B,T,D] activation type."""
+    pr = _p(precision)
+    B, T, D3 = qkv.shape
+    D = D3 // 3
+    out = torch.empty(B, T, D, dtype=act_dtype(pr), device=qkv.device)
+    xl = x_len.to(torch.int32).contiguous() if x_len is not None else None
+    check(lib().ec_op_relpos_attention(pr, ptr(qkv.float().contiguous()), ptr(E.float().contiguous()), ptr(u.float().contiguous()),
+                                       ptr(v.float().contiguous()), ptr(xl), B, T, D, heads, group, ptr(out), stream_ptr()))
+    return out
+
+
+def dwconv_bn_swish(x_act, w_folded, b_folded, stride, precision):
+    pr = _p(precision)
+    B, T, Cc = x_act.shape
+    k = w_folded.shape[1]
+    To = (T - 1) // stride + 1
+    y = torch.empty(B, To, Cc, dtype=act_dtype(pr), device=x_act.device)
+    check(lib().ec_op_dwconv_bn_swish(pr, ptr(x_act.contiguous()), ptr(w_folded), ptr(b_folded), B, T, Cc, k, stride, ptr(y), stream_ptr()))
+    return y
+
+
+def subsample_conv(mel, w_folded, b_folded, precision):
+    pr = _p(precision)
+    B, F, T = mel.shape
+    Cc = w_folded.shape[0]
+    To = (T - 1) // 2 + 1
+    y = torch.empty(B, To, Cc * (F // 2), dtype=act_dtype(pr), device=mel.device)
+    check(lib().ec_op_subsample_conv(pr, ptr(mel.float().contiguous()), ptr(w_folded), ptr(b_folded), B, F, T, Cc, ptr(y), stream_ptr()))
+    return y

@@ -1,0 +1,148 @@
+/* effconf_b200 -- C ABI of the B200-native Efficient Conformer encoder hot path.
+ *
+ * Drop-in boundary.  Every entry point takes plain pointers, sizes and a cudaStream_t
+ * (passed as void*); no torch types.  All pointers are DEVICE pointers unless stated.  Calls are stream-ordered,
+ * never synchronise, allocate nothing (caller provides weights arena + workspace), hold no global tensors and are
+ * CUDA-graph capturable.  Return value: EC_OK (0) or EC_ERR (1); ec_last_error() gives the thread-local message.
+ * There is NO CPU fallback: a device that is not sm_100 makes ec_engine_create fail.
+ *
+ * Reference interfaces replaced (burchim/EfficientConformer, paths relative to the reference root):
+ *   ec_engine_forward      <- ConformerEncoder.forward after AudioPreprocessing  models/encoders.py:106-142
+ *                             (+ ModelCTC.fc, models/model_ctc.py:66, when logits != NULL)
+ *   ec_ctc_loss            <- LossCTC.forward                                     models/losses.py:56-71
+ *   ec_ctc_greedy          <- ModelCTC.gready_search_decoding (ids, pre-tokenizer) models/model_ctc.py:99-133
+ *   ec_op_*                <- the individual modules, for unit parity tests:
+ *       ec_op_layernorm        nn.LayerNorm(eps=1e-6)                 models/modules.py:386,433,511; blocks.py:96
+ *       ec_op_gemm, ec_op_pointwise_glu  Linear / pointwise Conv1d (+Swish/GLU/residual)  models/layers.py:67,136; modules.py:385-392,513-519
+ *       ec_op_relpos_attention (Grouped)RelPosMultiHeadSelfAttention core       models/attentions.py:549-620, 645-718
+ *       ec_op_dwconv_bn_swish  depthwise Conv1d + BatchNorm1d(eval) + Swish     models/modules.py:515-517
+ *       ec_op_subsample_conv   Conv2d(1->C,3x3,s2)+BatchNorm2d(eval)+Swish      models/modules.py:226-249
+ */
+#ifndef EFFCONF_B200_H_
+#define EFFCONF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EC_OK 0
+#define EC_ERR 1
+#define EC_MAX_BLOCKS 32
+
+/* numerics mode of the tensor-core operands (accumulation, residual stream, LayerNorm, softmax are always fp32) */
+#define EC_PREC_TF32 0 /* parity mode: operands rounded to TF32 (fp32 storage), tcgen05 kind::tf32 */
+#define EC_PREC_BF16 1 /* fast mode: bf16 operands and bf16 inter-kernel activations, tcgen05 kind::f16 */
+
+typedef struct ec_block_cfg {
+  int32_t dim_model;   /* D  */
+  int32_t dim_expand;  /* D' */
+  int32_t num_heads;   /* H  */
+  int32_t kernel_size; /* depthwise k (odd) */
+  int32_t group_size;  /* attention group size G (odd) */
+  int32_t conv_stride; /* 1 or 2 */
+  int32_t ff_ratio;
+  int32_t reserved;
+} ec_block_cfg;
+
+typedef struct ec_config {
+  int32_t n_mels;      /* 80 */
+  int32_t sub_filters; /* C of the single Conv2d subsampling layer */
+  int32_t num_blocks;
+  int32_t vocab;       /* fc rows; 0 = encoder only */
+  ec_block_cfg blocks[EC_MAX_BLOCKS];
+} ec_config;
+
+/* fp32 parameter pointers in the reference's own layouts (state_dict tensors, contiguous) */
+typedef struct ec_ffn_raw { const float *ln_w, *ln_b, *w1, *b1, *w2, *b2; } ec_ffn_raw;
+typedef struct ec_block_raw {
+  ec_ffn_raw ffn1, ffn2;
+  const float *att_ln_w, *att_ln_b, *u, *v, *wq, *bq, *wk, *bk, *wv, *bv, *wo, *bo, *wpos, *bpos;
+  const float *conv_ln_w, *conv_ln_b, *pw1_w, *pw1_b, *dw_w, *dw_b, *bn_w, *bn_b, *bn_rm, *bn_rv, *pw2_w, *pw2_b;
+  const float *norm_w, *norm_b;
+  const float *res_w, *res_b; /* conv_res.1 (NULL when dim_model == dim_expand) */
+} ec_block_raw;
+typedef struct ec_raw_weights {
+  const float *sub_conv_w, *sub_conv_b, *sub_bn_w, *sub_bn_b, *sub_bn_rm, *sub_bn_rv;
+  const float *lin_w, *lin_b;
+  const float *fc_w, *fc_b; /* NULL when vocab == 0 */
+  ec_block_raw blocks[EC_MAX_BLOCKS];
+} ec_raw_weights;
+
+typedef struct ec_engine ec_engine;
+
+const char* ec_last_error(void);
+int ec_version(void);
+/* queries the current device; fails unless compute capability is 10.x */
+int ec_device_check(void);
+
+int ec_engine_create(const ec_config* cfg, int precision, ec_engine** out);
+void ec_engine_destroy(ec_engine* e);
+/* bytes of the prepared-weights arena (device), and of the per-call workspace for a (batch, t_mel) shape */
+size_t ec_engine_weight_bytes(const ec_engine* e);
+size_t ec_engine_workspace_bytes(const ec_engine* e, int batch, int t_mel);
+/* convert/fold/concatenate the raw fp32 parameters into the arena (eval-mode BatchNorm folded into the conv taps).
+ * Must be re-run whenever parameters change.  The arena must stay alive while the engine is used. */
+int ec_engine_prepare(ec_engine* e, const ec_raw_weights* raw, void* arena, void* stream);
+/* number of rows / pointer slots of the relative sinusoid tables: block i needs a [rows_i, dim_model_i] table of the
+ * activation type (fp32 TF32-rounded, or bf16), rows_i = 2*Tp_i - G_i, holding reference table rows
+ * [max_len - Tp + G/2, max_len - G%2 + Tp - G/2)  (models/attentions.py:1309).  Built by the host (same fp32 formula). */
+int ec_engine_relpos_rows(const ec_engine* e, int t_mel, int32_t* rows_per_block /* [num_blocks] */, int32_t* frames_per_block);
+
+/* mel [B, n_mels, T] fp32; x_len [B] int64 mel-frame lengths or NULL (all T);
+ * relpos[i]: table of block i (activation type);
+ * out_x [B, T_out, D_last] fp32 (may be NULL if logits given); logits [B, T_out, vocab] fp32 or NULL;
+ * out_len [B] int64 or NULL.  */
+int ec_engine_forward(ec_engine* e, int batch, int t_mel, const float* mel, const long long* x_len,
+                      const void* const* relpos, void* workspace, float* out_x, float* logits, long long* out_len,
+                      void* stream);
+int ec_engine_out_frames(const ec_engine* e, int t_mel);
+
+/* Launch accounting and optional per-launch CUDA-event timing (the measurement hook that replaces the reference's
+ * torch.autograd.profiler use in Model.eval_time_encoder, models/model.py:627-674).  With profiling enabled a forward
+ * must be launched eagerly (not under graph capture); ec_engine_profile_read then returns, per kernel category,
+ * the summed device time [ms], algorithmic FLOPs, algorithmic bytes and launch count (arrays of ec_profile_categories()). */
+int ec_profile_categories(void);
+const char* ec_profile_category_name(int cat);
+int ec_engine_set_profiling(ec_engine* e, int enabled);
+int ec_engine_last_launches(const ec_engine* e);
+int ec_engine_profile_read(ec_engine* e, double* ms, double* flops, double* bytes, int32_t* launches);
+
+/* CTC head.  logits [B, T, V] fp32, logits_len [B] int64, targets [B, target_stride] int64 (blank = 0), target_len [B] int64.
+ * scratch: at least B*T*(sizeof(float)+sizeof(int)) + B*sizeof(int) bytes.  loss_per_utt [B], loss_mean [1] fp32. */
+size_t ec_ctc_scratch_bytes(int batch, int t, int vocab);
+int ec_ctc_loss(const float* logits, int batch, int t, int vocab, const long long* logits_len, const long long* targets,
+                int target_stride, const long long* target_len, void* scratch, float* loss_per_utt, float* loss_mean,
+                void* stream);
+/* ids [B, T] int32 (collapsed token ids, zero padded), counts [B] int32 */
+int ec_ctc_greedy(const float* logits, int batch, int t, int vocab, const long long* logits_len, void* scratch,
+                  int32_t* ids, int32_t* counts, void* stream);
+
+/* ---- single-operator entry points (unit parity tests; same kernels the engine launches) ---------------------------- */
+int ec_op_cast(int precision, const float* src, void* dst, size_t n, void* stream);
+int ec_op_layernorm(int precision, const float* x, int rows, int dim, const float* gamma, const float* beta, float eps,
+                    void* y_act /* activation type or NULL */, float* y_f32 /* or NULL */, void* stream);
+/* out = alpha * act(A @ W^T + bias) + residual.  A [M,K], W [N,K] in the activation type (use ec_op_cast).  act: 0 none, 1 swish. */
+int ec_op_gemm(int precision, const void* A, const void* W, int M, int N, int K, const float* bias, float alpha, int act,
+               const float* residual, float* out_f32, void* out_act, void* stream);
+/* pointwise Conv1d(K -> 2*channels) + GLU: out[m, c] = (A w_c + b_c) * sigmoid(A w_{C+c} + b_{C+c}).  w_raw [2C, K], b_raw [2C] fp32
+ * (reference layout); w_scratch / b_scratch hold ec_op_glu_scratch_rows(channels) rows of the interleaved copy. */
+int ec_op_pointwise_glu(int precision, const void* A, const float* w_raw, const float* b_raw, int M, int channels, int K,
+                        void* w_scratch, float* b_scratch, void* out_act, void* stream);
+int ec_op_glu_scratch_rows(int channels);
+/* eval BatchNorm folded into conv taps: w_out [C, taps], b_out [C] */
+int ec_op_fold_bn(const float* w, const float* b, const float* g, const float* beta, const float* rm, const float* rv, float eps,
+                  int C, int taps, float* w_out, float* b_out, void* stream);
+int ec_op_relpos_attention(int precision, const float* qkv, const float* E, const float* u, const float* v,
+                           const int32_t* x_len, int batch, int t, int dim, int heads, int group, void* out, void* stream);
+int ec_op_dwconv_bn_swish(int precision, const void* x, const float* w_folded, const float* b_folded, int batch, int t,
+                          int channels, int k, int stride, void* y, void* stream);
+int ec_op_subsample_conv(int precision, const float* mel, const float* w_folded, const float* b_folded, int batch,
+                         int n_mels, int t, int channels, void* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EFFCONF_B200_H_ */

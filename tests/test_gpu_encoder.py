@@ -1,0 +1,215 @@
+"""End-to-end parity on the B200 through the public API (ConformerEncoder / ModelCTC -> C ABI -> CUDA kernels):
+  * against the committed golden vectors produced by the real reference (BASELINE config 1 and awkward-length modules),
+  * against the CPU oracle on seeded inputs (B=4 x 80 x 1000 ragged),
+  * size-independent properties at BASELINE's full size (B=32 x 80 x 1000): batch-order equivariance, determinism,
+    agreement of the eager and CUDA-graph paths, finite outputs.
+Tolerance: BASELINE.json north_star asks for 1e-3 relative on logits / loss and identical greedy ids; the parity (TF32
+operand) mode must meet it, the bf16 fast mode is reported against the reference's own bf16-autocast deviation (1.1e-2)."""
+import os
+
+import pytest
+import torch
+
+from efficientconformer_b200.config import CTC_SMALL_ENCODER_PARAMS as P, CTC_SMALL_VOCAB as V, resolve_blocks
+from efficientconformer_b200.synthetic import seeded_state_dict, synthetic_mel, synthetic_audio, ragged_lengths, synthetic_targets
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL_TF32 = 1e-3
+TOL_BF16 = 1.5e-2
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def max_rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max())
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return seeded_state_dict(P, V, seed=0, prefix_encoder="encoder.")
+
+
+def make_model(sd, precision, golden=None):
+    from efficientconformer_b200 import ModelCTC
+    m = ModelCTC(P, {"vocab_size": V}, precision=precision)
+    missing = m.load_state_dict(sd, strict=False)
+    assert all(k.startswith("encoder.preprocessing.") for k in missing.missing_keys) and not missing.unexpected_keys
+    return m.to(DEV).eval()
+
+
+@pytest.mark.parametrize("precision,tol", [("tf32", TOL_TF32), ("bf16", TOL_BF16)])
+def test_config1_against_reference_golden(sd, golden_dir, precision, tol):
+    from efficientconformer_b200.model_ctc import ctc_loss, greedy_ids
+    g = torch.load(os.path.join(golden_dir, "ctc_small_b2_t500.pt"))
+    model = make_model(sd, precision)
+    mel = synthetic_mel(2, 500, seed=g["mel_seed"]).to(DEV)
+    logits, out_len, att = model.forward_mel(mel, g["mel_len"].to(DEV))
+    assert torch.equal(out_len.cpu(), g["out_len"])
+    assert len(att) == 15
+    e_l2, e_max = rel_l2(logits, g["logits"]), max_rel(logits, g["logits"])
+    print(f"[{precision}] logits vs reference: rel-L2 {e_l2:.3e}  max-abs/absmax {e_max:.3e}")
+    assert e_l2 < tol and e_max < 2 * tol
+    loss, per = ctc_loss(logits, out_len, g["targets"], g["target_len"])
+    assert abs(float(loss) - float(g["loss"])) / abs(float(g["loss"])) < tol
+    ids = greedy_ids(logits, out_len)
+    if precision == "tf32":
+        # ids must match wherever the reference's own top-2 margin exceeds the parity tolerance (random-init logits are near-tied)
+        top2 = g["logits"].topk(2, dim=-1).values
+        safe = (top2[..., 0] - top2[..., 1]) > 4 * tol * g["logits"].abs().max()
+        pred = logits.argmax(-1).cpu()
+        assert torch.equal(pred[safe], g["logits"].argmax(-1)[safe])
+        if bool(safe.all()):
+            assert ids == g["greedy"]
+
+
+def test_audio_level_forward_matches_reference(sd, golden_dir):
+    g = torch.load(os.path.join(golden_dir, "ctc_small_audio_b2_t200.pt"))
+    model = make_model(sd, "tf32")
+    audio = synthetic_audio(2, g["t_mel"], seed=g["audio_seed"]).to(DEV)
+    logits, out_len, _ = model.forward((audio, None, g["audio_len"].to(DEV), None))
+    assert torch.equal(out_len.cpu(), g["out_len"])
+    assert rel_l2(logits, g["logits"]) < 2 * TOL_TF32      # + cuFFT-vs-CPU STFT differences in the host front end
+    enc_out, enc_len, att = model.encoder(audio, g["audio_len"].to(DEV))   # reference ConformerEncoder.forward contract
+    assert enc_out.shape == (2, out_len.max().item(), 240) and att == [None] * 15 and torch.equal(enc_len.cpu(), g["out_len"])
+
+
+def test_encoder_only_and_no_lengths(sd):
+    from efficientconformer_b200 import ConformerEncoder
+    from oracle import conformer_oracle as O
+    enc_sd = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
+    enc = ConformerEncoder(P, precision="tf32")
+    enc.load_state_dict(enc_sd, strict=False)
+    enc = enc.to(DEV).eval()
+    mel = synthetic_mel(2, 131, seed=11)
+    x, x_len, lg = enc.forward_mel(mel.to(DEV), None)
+    assert x_len is None and lg is None
+    ref, _ = O.encoder_forward_mel(enc_sd, P, mel, None)
+    assert x.shape == ref.shape
+    assert rel_l2(x, ref) < TOL_TF32
+
+
+def test_ragged_batch_against_oracle(sd):
+    from oracle import conformer_oracle as O
+    from efficientconformer_b200.model_ctc import ctc_loss, greedy_ids
+    B, T = 4, 1000
+    mel = synthetic_mel(B, T, seed=21)
+    mel_len = torch.tensor([1000, 900, 700, 445])
+    ref, ref_len = O.model_ctc_forward_mel(sd, P, mel, mel_len)
+    model = make_model(sd, "tf32")
+    logits, out_len, _ = model.forward_mel(mel.to(DEV), mel_len.to(DEV))
+    assert torch.equal(out_len.cpu(), ref_len)
+    e = rel_l2(logits, ref)
+    print(f"[tf32] B=4 T=1000 ragged: rel-L2 {e:.3e} max {max_rel(logits, ref):.3e}")
+    assert e < TOL_TF32
+    y, y_len = synthetic_targets(ref_len, V, seed=4)
+    loss, _ = ctc_loss(logits, out_len, y, y_len)
+    ref_loss, _ = O.ctc_loss(ref, ref_len, y, y_len)
+    assert abs(float(loss) - float(ref_loss)) / abs(float(ref_loss)) < TOL_TF32
+
+
+def test_block_goldens_awkward_lengths(sd, golden_dir):
+    """Single-block engines on the reference's block outputs for T in {1,2,4,17,250,251,...} incl. stride-2 / expand blocks."""
+    import ctypes as C
+    from efficientconformer_b200 import ConformerEncoder
+    g = torch.load(os.path.join(golden_dir, "ctc_small_modules.pt"))
+    specs = resolve_blocks(P)
+    enc_sd = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
+    from oracle import conformer_oracle as O
+    worst = 0.0
+    for key, e in g.items():
+        if key.startswith("sub_"):
+            continue
+        bi, Tq = int(key[1:key.index("_")]), int(key[key.index("T") + 1:])
+        spec = specs[bi]
+        from efficientconformer_b200 import ops
+        # the golden stores the reference block's output for a seeded block INPUT: compose the block from the C entry points
+        gen = torch.Generator().manual_seed(100 * bi + Tq)
+        x = torch.randn(2, Tq, spec.dim_model, generator=gen)
+        out = run_block_with_ops(ops, enc_sd, f"blocks.{bi}", x.to(DEV), e["x_len"].to(DEV), spec, "tf32")
+        err = rel_l2(out, e["block"])
+        worst = max(worst, err)
+        assert out.shape == e["block"].shape, key
+        assert err < TOL_TF32, (key, err)
+    print(f"worst block rel-L2 vs reference goldens: {worst:.3e}")
+
+
+def run_block_with_ops(ops, sd, p, x, x_len, spec, prec):
+    """One ConformerBlock (reference models/blocks.py:119-137) composed from the single-operator C entry points --
+    the same kernels, epilogues and buffer layouts ec_engine_forward uses."""
+    from efficientconformer_b200.encoders import relative_sinusoid_rows
+    c = lambda k: sd[f"{p}.{k}"].to(DEV)
+    B, T, D = x.shape
+    De, G, H = spec.dim_expand, spec.group_size, spec.num_heads
+    x2 = x.reshape(B * T, D).contiguous()
+
+    def ffn(tag, xin, d):
+        xn, _ = ops.layernorm(xin, c(f"{tag}.layers.0.weight"), c(f"{tag}.layers.0.bias"), prec, want_f32=False)
+        _, h = ops.gemm(xn, ops.cast(c(f"{tag}.layers.1.weight"), prec), c(f"{tag}.layers.1.bias"), prec, act=1, want_f32=False, want_act=True)
+        y, _ = ops.gemm(h, ops.cast(c(f"{tag}.layers.4.weight"), prec), c(f"{tag}.layers.4.bias"), prec, alpha=0.5, residual=xin)
+        return y
+    x2 = ffn("feed_forward_module1", x2, D)
+    m = "multi_head_self_attention_module"
+    xn, _ = ops.layernorm(x2, c(f"{m}.norm.weight"), c(f"{m}.norm.bias"), prec, want_f32=False)
+    wqkv = torch.cat([c(f"{m}.mhsa.{n}_layer.weight") for n in ("query", "key", "value")])
+    bqkv = torch.cat([c(f"{m}.mhsa.{n}_layer.bias") for n in ("query", "key", "value")])
+    qkv, _ = ops.gemm(xn, ops.cast(wqkv, prec), bqkv, prec)
+    Tp = T + (-T) % G
+    R = ops.cast(relative_sinusoid_rows(Tp, D, G, spec.max_pos).to(DEV), prec)
+    E, _ = ops.gemm(R, ops.cast(c(f"{m}.mhsa.pos_layer.weight"), prec), c(f"{m}.mhsa.pos_layer.bias"), prec)
+    o = ops.relpos_attention(qkv.reshape(B, T, 3 * D), E, c(f"{m}.mhsa.u"), c(f"{m}.mhsa.v"), x_len, H, G, prec)
+    x2, _ = ops.gemm(o.reshape(B * T, D), ops.cast(c(f"{m}.mhsa.output_layer.weight"), prec), c(f"{m}.mhsa.output_layer.bias"), prec, residual=x2)
+    cm = "convolution_module.layers"
+    xn, _ = ops.layernorm(x2, c(f"{cm}.0.weight"), c(f"{cm}.0.bias"), prec, want_f32=False)
+    gl = ops.pointwise_glu(xn, c(f"{cm}.2.weight"), c(f"{cm}.2.bias"), prec)
+    wf, bf = ops.fold_bn(c(f"{cm}.4.weight"), c(f"{cm}.4.bias"), c(f"{cm}.5.weight"), c(f"{cm}.5.bias"), c(f"{cm}.5.running_mean"), c(f"{cm}.5.running_var"))
+    hc = ops.dwconv_bn_swish(gl.reshape(B, T, De), wf, bf, spec.conv_stride, prec)
+    To = hc.shape[1]
+    if spec.dim_model != De:
+        xs = ops.cast(x2.reshape(B, T, D)[:, ::spec.conv_stride].reshape(B * To, D), prec)
+        res, _ = ops.gemm(xs, ops.cast(c("conv_res.1.weight")[:, :, 0], prec), c("conv_res.1.bias"), prec)
+    else:
+        res = x2
+    x3, _ = ops.gemm(hc.reshape(B * To, De), ops.cast(c(f"{cm}.7.weight")[:, :, 0], prec), c(f"{cm}.7.bias"), prec, residual=res)
+    x3 = ffn("feed_forward_module2", x3, De)
+    _, y = ops.layernorm(x3, c("norm.weight"), c("norm.bias"), prec, want_act=False)
+    return y.reshape(B, To, De)
+
+
+def test_full_size_properties(sd):
+    """BASELINE target shape B=32 x 80 x 1000 (the oracle takes ~1 s per utterance batch here, so check properties):
+    utterances are independent in eval mode -> permuting the batch permutes the logits; CUDA-graph replay == eager launch;
+    two runs are bit-identical; a B=4 slice agrees with the oracle."""
+    from oracle import conformer_oracle as O
+    B, T = 32, 1000
+    model = make_model(sd, "tf32")
+    mel = synthetic_mel(B, T, seed=31).to(DEV)
+    mel_len = ragged_lengths(B, T, seed=3).to(DEV)
+    lg1, len1, _ = model.forward_mel(mel, mel_len)
+    lg2, _, _ = model.forward_mel(mel, mel_len)
+    assert torch.isfinite(lg1).all()
+    assert torch.equal(lg1, lg2), "deterministic"
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0)).to(DEV)
+    lg3, len3, _ = model.forward_mel(mel[perm].contiguous(), mel_len[perm].contiguous())
+    assert torch.equal(len3, len1[perm])
+    assert rel_l2(lg3, lg1[perm]) < 1e-6, "batch-order equivariance"
+    model.encoder.use_cuda_graph = False
+    lg4, _, _ = model.forward_mel(mel, mel_len)
+    assert torch.equal(lg4, lg1), "CUDA-graph replay equals eager launch sequence"
+    idx = [0, 7, 19, 31]
+    ref, ref_len = O.model_ctc_forward_mel(sd, P, mel[idx].cpu(), mel_len[idx].cpu())
+    assert torch.equal(ref_len, len1[idx].cpu())
+    assert rel_l2(lg1[idx], ref) < TOL_TF32
+
+
+def test_no_fallback_paths(sd):
+    from efficientconformer_b200 import ConformerEncoder
+    enc = ConformerEncoder(P)
+    with pytest.raises(NotImplementedError):
+        enc.train().to(DEV).forward_mel(torch.zeros(1, 80, 16, device=DEV))
+    with pytest.raises(RuntimeError):
+        enc.eval().forward_mel(torch.zeros(1, 80, 16))       # CPU tensor: no CPU path in the product

@@ -1,0 +1,201 @@
+"""Per-kernel parity on the B200: every CUDA operator (called through the C ABI) against (a) an exact fp64 torch
+restatement fed with the SAME rounded operands (tight tolerance: validates tcgen05 descriptors / layouts / indexing) and
+(b) the CPU oracle's module functions (tolerance = operand format noise)."""
+import math
+
+import pytest
+import torch
+
+from efficientconformer_b200.config import CTC_SMALL_ENCODER_PARAMS as P, resolve_blocks
+from efficientconformer_b200.synthetic import seeded_state_dict
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def tf32_round(x):
+    xi = x.float().contiguous().view(torch.int32)
+    return ((xi + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def rnd(prec, x):
+    return tf32_round(x) if prec == "tf32" else x.to(torch.bfloat16).float()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from efficientconformer_b200 import ops as o
+    return o
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+def test_cast_rounding(ops, prec):
+    x = torch.randn(1000, 37, device=DEV) * 3
+    y = ops.cast(x, prec).float()
+    if prec == "tf32":
+        # round-to-nearest (ties away) onto 10 mantissa bits
+        assert torch.equal(y.cpu(), tf32_round(x.cpu()))
+    else:
+        assert torch.equal(y.cpu(), x.cpu().to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 16, 64), (256, 240, 120), (16000, 480, 120), (8000, 168, 672), (4000, 256, 240),
+                                   (999, 120, 120), (1, 120, 120), (130, 504, 168), (333, 960, 240), (700, 120, 4800), (77, 8, 40)])
+def test_gemm_exact_operands(ops, prec, M, N, K):
+    if prec == "bf16" and (K * 2) % 16:
+        pytest.skip("bf16 row pitch must be a multiple of 16 bytes")
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV)
+    aa, ww = ops.cast(a, prec), ops.cast(w, prec)
+    ref = aa.double() @ ww.double().t() + bias.double()
+XX
+    out2, out2a = ops.gemm(aa, ww, bias, prec, alpha=0.5, act=0, residual=res, want_act=True)
+    ref2 = 0.5 * ref + res.double()
+    assert rel_l2(out2, ref2) < tol, "residual"
+    assert torch.equal(out2a.float().cpu(), rnd(prec, out2.cpu())), "activation-type copy is the rounded fp32 output"
+    out3, _ = ops.gemm(aa, ww, bias, prec, act=1)
+    ref3 = ref * torch.sigmoid(ref)
+    assert rel_l2(out3, ref3) < 3 * tol, "swish"
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("M,C,K", [(256, 120, 120), (1000, 168, 120), (517, 240, 168), (64, 8, 16), (300, 360, 360)])
+def test_pointwise_glu(ops, prec, M, C, K):
+    g = torch.Generator(device="cpu").manual_seed(C + K)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(2 * C, K, 1, generator=g) / math.sqrt(K)).to(DEV)
+    b = torch.randn(2 * C, generator=g).to(DEV)
+    aa = ops.cast(a, prec)
+    h = aa.double() @ rnd(prec, w[:, :, 0].cpu()).to(DEV).double().t() + b.double()
+    ref = h[:, :C] * torch.sigmoid(h[:, C:])
+    out = ops.pointwise_glu(aa, w, b, prec)
+    tol = 2e-6 if prec == "tf32" else 4e-3     # output is rounded to the activation type
+    assert rel_l2(out.float(), ref) < (1e-3 if prec == "tf32" else 4e-3)
+    assert rel_l2(out.float(), rnd(prec, ref.float().cpu())) < 1e-4 + tol
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("rows,dim", [(16000, 120), (1000, 168), (37, 240), (5, 1024), (3, 8)])
+def test_layernorm(ops, prec, rows, dim):
+    g = torch.Generator(device="cpu").manual_seed(rows + dim)
+    x = (torch.randn(rows, dim, generator=g) * 2 + 0.5).to(DEV)
+    gamma = (1 + 0.1 * torch.randn(dim, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(dim, generator=g)).to(DEV)
+    ya, yf = ops.layernorm(x, gamma, beta, prec)
+    ref = torch.nn.functional.layer_norm(x.double(), (dim,), gamma.double(), beta.double(), 1e-6)
+    assert rel_l2(yf, ref) < 1e-6
+    assert torch.equal(ya.float().cpu(), rnd(prec, yf.cpu()))
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("B,T,C,k,stride", [(4, 500, 120, 15, 1), (3, 251, 168, 15, 2), (2, 250, 240, 15, 2), (2, 1, 120, 15, 1),
+                                            (2, 7, 240, 15, 2), (1, 130, 256, 31, 1), (2, 65, 176, 31, 2)])
+def test_dwconv_bn_swish(ops, prec, B, T, C, k, stride):
+    g = torch.Generator(device="cpu").manual_seed(T + C + k)
+    x = torch.randn(B, T, C, generator=g).to(DEV)
+    w = (torch.randn(C, 1, k, generator=g) / math.sqrt(k)).to(DEV)
+    b, gam, bet = (0.1 * torch.randn(C, generator=g)).to(DEV), (1 + 0.1 * torch.randn(C, generator=g)).to(DEV), (0.1 * torch.randn(C, generator=g)).to(DEV)
+    rm, rv = (0.1 * torch.randn(C, generator=g)).to(DEV), (0.5 + torch.rand(C, generator=g)).to(DEV)
+    xa = ops.cast(x, prec)
+    wf, bf = ops.fold_bn(w, b, gam, bet, rm, rv)
+    y = ops.dwconv_bn_swish(xa, wf, bf, stride, prec)
+    xin = xa.double().transpose(1, 2)
+    pad = (k - 1) // 2
+    conv = torch.nn.functional.conv1d(torch.nn.functional.pad(xin, (pad, pad)), w.double(), b.double(), stride=stride, groups=C)
+    bn = (conv - rm.double()[None, :, None]) / torch.sqrt(rv.double()[None, :, None] + 1e-5) * gam.double()[None, :, None] + bet.double()[None, :, None]
+    ref = (bn * torch.sigmoid(bn)).transpose(1, 2)
+    assert y.shape == ref.shape
+    assert rel_l2(y.float(), ref) < (5e-4 if prec == "tf32" else 4e-3)
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("B,T", [(2, 101), (3, 64), (1, 1), (2, 2), (2, 33)])
+def test_subsample_conv(ops, prec, B, T):
+    C, F = 120, 80
+    g = torch.Generator(device="cpu").manual_seed(T)
+    mel = torch.randn(B, F, T, generator=g).to(DEV)
+    w = (torch.randn(C, 1, 3, 3, generator=g) / 3).to(DEV)
+    b, gam, bet = (0.1 * torch.randn(C, generator=g)).to(DEV), (1 + 0.1 * torch.randn(C, generator=g)).to(DEV), (0.1 * torch.randn(C, generator=g)).to(DEV)
+    rm, rv = (0.1 * torch.randn(C, generator=g)).to(DEV), (0.5 + torch.rand(C, generator=g)).to(DEV)
+    wf, bf = ops.fold_bn(w, b, gam, bet, rm, rv)
+    y = ops.subsample_conv(mel, wf, bf, prec)
+    conv = torch.nn.functional.conv2d(mel.double().unsqueeze(1), w.double(), b.double(), stride=2, padding=1)
+    bn = torch.nn.functional.batch_norm(conv, rm.double(), rv.double(), gam.double(), bet.double(), False, 0.0, 1e-5)
+    ref = (bn * torch.sigmoid(bn)).reshape(B, C * (F // 2), -1).transpose(1, 2)
+    assert y.shape == ref.shape
+    assert rel_l2(y.float(), ref) < (5e-4 if prec == "tf32" else 4e-3)
+
+
+def _attention_reference(qkv, E, u, v, x_len, H, G):
+    """fp64 closed form of SURVEY.md section 8 row a9 on the given (already projected) q|k|v and E."""
+    B, T, D3 = qkv.shape
+    D = D3 // 3
+    d = G * D // H
+    q, k, vv = qkv.double().split(D, dim=-1)
+    Pd = (-T) % G
+    if Pd:
+        q, k, vv = (torch.nn.functional.pad(t, (0, 0, 0, Pd)) for t in (q, k, vv))
+    Tg = (T + Pd) // G
+    qu = (q + u.double()).reshape(B, Tg, H, d).transpose(1, 2)
+    qv = (q + v.double()).reshape(B, Tg, H, d).transpose(1, 2)
+    kk = k.reshape(B, Tg, H, d).transpose(1, 2)
+    vh = vv.reshape(B, Tg, H, d).transpose(1, 2)
+    Eh = E.double().reshape(2 * Tg - 1, H, d).transpose(0, 1)
+    sk = qu @ kk.transpose(2, 3)
+    se = qv @ Eh.transpose(1, 2).unsqueeze(0)
+    idx = (Tg - 1) + torch.arange(Tg, device=qkv.device)[None, :] - torch.arange(Tg, device=qkv.device)[:, None]
+    se = torch.gather(se, 3, idx[None, None].expand(B, H, Tg, Tg))
+    s = (sk + se) / d ** 0.5
+    if x_len is not None:
+        masked = (torch.arange(Tg, device=qkv.device) * G)[None, :] >= x_len[:, None]
+        s = s.masked_fill(masked[:, None, None, :], float("-inf"))
+    w = s.softmax(-1)
+    return (w @ vh).transpose(1, 2).reshape(B, Tg * G, D)[:, :T]
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("B,T,D,H,G", [(2, 500, 120, 4, 3), (2, 251, 120, 4, 3), (3, 250, 168, 4, 1), (2, 125, 240, 4, 1), (2, 1, 120, 4, 3),
+                                       (2, 2, 120, 4, 3), (1, 64, 168, 4, 1), (2, 65, 240, 4, 1), (1, 700, 168, 4, 1), (2, 17, 360, 8, 3)])
+def test_relpos_attention(ops, prec, B, T, D, H, G):
+    g = torch.Generator(device="cpu").manual_seed(T * 3 + D)
+    qkv = torch.randn(B, T, 3 * D, generator=g).to(DEV)
+    Tp = T + (-T) % G
+    E = torch.randn(2 * Tp - G, D, generator=g).to(DEV)
+    u, v = (0.3 * torch.randn(D, generator=g)).to(DEV), (0.3 * torch.randn(D, generator=g)).to(DEV)
+    x_len = torch.tensor([T] + [max(1, (2 * T) // 3)] * (B - 1), device=DEV)
+    for xl in (x_len, None):
+        out = ops.relpos_attention(qkv, E, u, v, xl, H, G, prec)
+        ref = _attention_reference(qkv, E, u, v, xl, H, G)
+        assert out.shape == ref.shape
+        err = rel_l2(out.float(), ref)
+        assert err < (2e-3 if prec == "tf32" else 5e-3), (err, xl is None)
+
+
+def test_ctc_loss_and_greedy_on_device(golden_dir):
+    import os
+    from efficientconformer_b200.model_ctc import ctc_loss, greedy_ids
+    g = torch.load(os.path.join(golden_dir, "ctc_loss_small.pt"))
+    mean, per = ctc_loss(g["logits"].to(DEV), g["logits_len"], g["targets"], g["target_len"])
+    assert torch.allclose(per.cpu(), g["loss_per_utt"], rtol=2e-5, atol=2e-5)
+    assert abs(float(mean) - float(g["loss"])) < 2e-5 * abs(float(g["loss"]))
+    from oracle import conformer_oracle as O
+    assert greedy_ids(g["logits"].to(DEV), g["logits_len"]) == O.greedy_ids(g["logits"], g["logits_len"])
+    # larger random case against the oracle restatement
+    gen = torch.Generator().manual_seed(5)
+    lg = 2 * torch.randn(8, 125, 256, generator=gen)
+    ll = torch.tensor([125, 120, 99, 64, 33, 17, 125, 2])
+    U = torch.clamp(ll // 3, min=1)
+    y = torch.randint(1, 256, (8, int(U.max())), generator=gen)
+    mean, per = ctc_loss(lg.to(DEV), ll, y, U)
+    m2, p2 = O.ctc_loss(lg, ll, y, U)
+    assert torch.allclose(per.cpu(), p2, rtol=1e-4, atol=1e-4)
+    assert greedy_ids(lg.to(DEV), ll) == O.greedy_ids(lg, ll)
