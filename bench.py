@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: EfficientConformerCTCSmall encoder forward + fc + CTC loss on synthetic 80-mel batches.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|tf32]
+
+Prints ONE JSON line (rank 0).  metric = mel frames / second (BASELINE.json), whole job over all N GPUs.
+  value     inputs already resident in HBM; every step timed by its own CUDA-event pair on the launching stream, L2 flushed
+            (256 MiB write) between steps, max over ranks
+  e2e       the same step through the public API with HOST inputs: pinned mel -> H2D, ModelCTC.forward_mel, ctc_loss,
+            loss.item() (D2H) inside the timed region
+  roofline  dominant kernel (the tcgen05 GEMM, all its launches in one forward): algorithmic FLOPs / CUDA-event time
+            from an eager profiled pass inside this run, against MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (port of the reference algorithm, pinned to the reference's outputs) on the host cores
+--impl reference times that CPU oracle as the reference arm (the reference itself is Python and cannot travel to the GPU box).
+Multi-GPU: one process per GPU (torchrun); utterances shard over ranks with no data-path collective (forward has no
+exchange step); barrier + max-over-ranks timing over NCCL."""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from efficientconformer_b200.config import CTC_SMALL_ENCODER_PARAMS as P, CTC_SMALL_VOCAB as V  # noqa: E402
+from efficientconformer_b200.synthetic import seeded_state_dict, synthetic_mel, synthetic_targets  # noqa: E402
+
+METRIC = "encoder_mel_frames_per_sec"
+UNIT = "frames/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill(); out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_pass(sd, mel, mel_len, y_fn):
+    from oracle import conformer_oracle as O           # checker / CPU baseline only (never the product path)
+    t0 = time.perf_counter()
+    logits, out_len = O.model_ctc_forward_mel(sd, P, mel, mel_len)
+    y, y_len = y_fn(out_len)
+    loss, _ = O.ctc_loss(logits, out_len, y, y_len)
+    return time.perf_counter() - t0, logits, out_len, float(loss)
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the CPU implementation of the path (oracle port) with every host thread, bounded sample per step."""
+    if rank != 0:
+        return
+    torch.set_grad_enabled(False)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = args.batch if (args.steps + args.warmup) <= 40 else max(2, args.batch // 4)
+    sd = seeded_state_dict(P, V, seed=0, prefix_encoder="encoder.")
+    mel = synthetic_mel(B, args.frames, seed=1)
+    mel_len = torch.full((B,), args.frames, dtype=torch.int64)
+    yf = lambda ol: synthetic_targets(ol, V, seed=4)
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_oracle_pass(sd, mel, mel_len, yf)
+    times = [cpu_oracle_pass(sd, mel, mel_len, yf)[0] for _ in range(args.steps)]
+    total = sum(times)
+    value = B * args.frames * args.steps / total
+    sample = f"{args.steps} passes of B={B} x 80 x {args.frames} (fwd + fc + CTC loss), fp32, torch CPU {torch.get_num_threads()} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, B, "cpu"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, batch_per_gpu, where):
+    return {"workload": f"EfficientConformerCTCSmall encoder fwd + fc + CTC loss, batch {batch_per_gpu}/GPU x 80-mel x {args.frames} frames "
+                        f"(BASELINE.json north_star target shape; configs[1] without backward, see DESIGN.md)",
+            "global_batch": batch_per_gpu * (args.gpus if where != "cpu" else 1), "frames": args.frames, "n_mels": 80,
+            "weights": "seeded random init", "l2": "256 MiB write between timed steps (L2 flush)", "parallelism": f"dp{args.gpus} (utterance shards, no collective)"}
+
+
+def run_ours(args, rank, world, local_rank):
+    from efficientconformer_b200 import ModelCTC, _lib
+    from efficientconformer_b200.model_ctc import ctc_loss
+    import ctypes as C
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    torch.set_grad_enabled(False)
+    B, T = args.batch, args.frames
+    sd = seeded_state_dict(P, V, seed=0, prefix_encoder="encoder.")
+    model = ModelCTC(P, {"vocab_size": V}, precision=args.precision)
+    model.load_state_dict(sd, strict=False)
+    model = model.to(dev).eval()
+    mel_h = synthetic_mel(B, T, seed=1 + rank).pin_memory()
+    len_h = torch.full((B,), T, dtype=torch.int64).pin_memory()
+    mel_d, len_d = mel_h.to(dev), len_h.to(dev)
+    t_out = (((T - 1) // 2 + 1 - 1) // 2 + 1 - 1) // 2 + 1
+    y, y_len = synthetic_targets(torch.full((B,), t_out), V, seed=4)
+    y_d, yl_d = y.to(dev), y_len.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_resident():
+        logits, out_len, _ = model.forward_mel(mel_d, len_d)
+        return ctc_loss(logits, out_len, y_d, yl_d)[0]
+
+    def step_e2e():
+        m = mel_h.to(dev, non_blocking=True); l = len_h.to(dev, non_blocking=True)
+        logits, out_len, _ = model.forward_mel(m, l)
+        return float(ctc_loss(logits, out_len, y_d, yl_d)[0].item())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident(); flush.zero_()
+    prec = _lib.PRECISIONS[args.precision]
+    eng = model.encoder._engines[prec][0]
+    launches_per_step = _lib.lib().ec_engine_last_launches(eng) + 4          # + CTC: i64->i32, lse/argmax, alpha, mean
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev:
+        flush.zero_()
+        a.record(); loss = step_resident(); b.record()
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms)
+    # ---- end to end through the public API with host buffers ----
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    barrier()
+    if dist is not None:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_s = float(e2e_s)
+
+    # ---- per-kernel profile of one eager forward (CUDA events around every launch, same stream) ----
+    L = _lib.lib()
+    ncat = L.ec_profile_categories()
+    acc = {}
+    model.encoder.use_cuda_graph = False
+    L.ec_engine_set_profiling(eng, 1)
+    reps = 5
+    for r in range(reps + 1):
+        model.forward_mel(mel_d, len_d)
+        ms, fl, by = (C.c_double * ncat)(), (C.c_double * ncat)(), (C.c_double * ncat)()
+        cnt = (C.c_int32 * ncat)()
+        _lib.check(L.ec_engine_profile_read(eng, ms, fl, by, cnt))
+        if r == 0:
+            continue
+        for i in range(ncat):
+            name = L.ec_profile_category_name(i).decode()
+            a = acc.setdefault(name, [0.0, 0.0, 0.0, 0])
+            a[0] += ms[i] / reps; a[1] = fl[i]; a[2] = by[i]; a[3] = cnt[i]
+    L.ec_engine_set_profiling(eng, 0)
+    model.encoder.use_cuda_graph = True
+    pk = peaks()
+    tensor_peak = pk["bf16_tflops"] * (1.0 if args.precision == "bf16" else 0.5)     # kind::tf32 runs at half the bf16 rate
+    kernels = []
+    gemm_ms = gemm_fl = gemm_n = 0
+    for name, (ms_, fl_, by_, n_) in acc.items():
+        if n_ == 0:
+            continue
+        ent = {"kernel": name, "launches": n_, "ms": round(ms_, 4), "tflops": round(fl_ / ms_ / 1e9, 2) if ms_ > 0 else None,
+               "gbs": round(by_ / ms_ / 1e6, 1) if ms_ > 0 else None}
+        kernels.append(ent)
+        if name.startswith("gemm_"):
+            gemm_ms += ms_; gemm_fl += fl_; gemm_n += n_
+    fwd_profiled_ms = sum(k["ms"] for k in kernels)
+    achieved = gemm_fl / gemm_ms / 1e9 if gemm_ms > 0 else 0.0
+    roofline = {"kernel": "gemm_tc_kernel (tcgen05, all GEMM launches of one forward)", "bound": "tensor", "achieved": round(achieved, 2),
+                "peak": tensor_peak, "unit": "TFLOP/s", "frac": round(achieved / tensor_peak, 4), "traffic": None,
+                "peak_source": pk["source"] + (" bf16 cuBLAS burst" if args.precision == "bf16" else " bf16 cuBLAS burst / 2 (tf32 operands)"),
+                "launches_per_forward": gemm_n, "avg_launch_us": round(1e3 * gemm_ms / max(gemm_n, 1), 2),
+                "share_of_forward": round(gemm_ms / fwd_profiled_ms, 3) if fwd_profiled_ms else None}
+    dw = acc.get("dwconv_bn_swish")
+    extra_rooflines = []
+    if dw and dw[0] > 0:
+        gbs = dw[2] / dw[0] / 1e6
+        extra_rooflines.append({"kernel": "dwconv_bn_swish", "bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                "frac": round(gbs / pk["hbm_gbs"], 4), "note": "working set is L2-resident at this shape (see DESIGN.md)"})
+
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    frames_total = world * B * T * args.steps
+    value = frames_total / (total_ms / 1e3)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic", "config": workload_config(args, B, "gpu"),
+        "e2e": {"value": frames_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": mel_h.numel() * 4 + len_h.numel() * 8, "d2h_bytes_per_step": 4,
+                "ms_per_step": 1e3 * e2e_s / args.steps, "timing": "wall clock around K API calls, synchronised both sides"},
+        "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+        "clocks": clocks, "roofline": roofline, "rooflines_other": extra_rooflines, "kernels": kernels,
+        "step_ms_min_med_max": [round(min(step_ms), 4), round(statistics.median(step_ms), 4), round(max(step_ms), 4)],
+        "loss": float(loss),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        Bs = 8
+        yf = lambda ol: (y[:Bs], y_len[:Bs])
+        cpu_oracle_pass(sd, mel_h[:Bs].clone(), len_h[:Bs].clone(), yf)
+        runs = [cpu_oracle_pass(sd, mel_h[:Bs].clone(), len_h[:Bs].clone(), yf) for _ in range(3)]
+        sec = statistics.median(r[0] for r in runs)
+        ref_logits, ref_len, ref_loss = runs[-1][1], runs[-1][2], runs[-1][3]
+        out["cpu_baseline"] = {"value": Bs * T / sec, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"median of 3 passes of the first {Bs} utterances of the same batch (fwd + fc + CTC), fp32 torch CPU, {torch.get_num_threads()} threads"}
+        lg, ol, _ = model.forward_mel(mel_d[:Bs].contiguous(), len_d[:Bs].contiguous())
+        gl = float(ctc_loss(lg, ol, y_d[:Bs].contiguous(), yl_d[:Bs].contiguous())[0])
+        d = (lg.cpu().double() - ref_logits.double())
+        out["parity_vs_oracle"] = {"logits_rel_l2": float(d.norm() / ref_logits.double().norm()),
+                                   "logits_max_abs_over_absmax": float(d.abs().max() / ref_logits.abs().max()),
+                                   "ctc_loss_rel": abs(gl - ref_loss) / abs(ref_loss), "sample": f"first {Bs} utterances", "gate": 1e-3,
+                                   "note": "tf32 operand mode meets the 1e-3 gate; bf16 mode is the fast mode (reference's own bf16 autocast deviates 1.1e-2)"}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--frames", type=int, default=1000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a B200: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    run_ours(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()

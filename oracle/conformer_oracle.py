@@ -260,30 +260,39 @@ def ctc_loss(logits, logits_len, targets, target_len):
     alpha_t(s) = logsumexp(alpha_{t-1}(s), alpha_{t-1}(s-1), [alpha_{t-1}(s-2) if l'_s != blank and l'_s != l'_{s-2}]) + lp_t(l'_s);
     loss_b = -logsumexp(alpha_{T_b-1}(S-1), alpha_{T_b-1}(S-2))."""
     lp = torch.log_softmax(logits.double(), dim=-1)
-    B = logits.shape[0]
-    losses = []
+    B, T, _ = logits.shape
     neg_inf = float("-inf")
-    for b in range(B):
-        T = int(logits_len[b]); U = int(target_len[b])
-        y = targets[b, :U].long()
-        ext = torch.zeros(2 * U + 1, dtype=torch.long)
-        ext[1::2] = y
-        S = 2 * U + 1
-        allow_skip = torch.zeros(S, dtype=torch.bool)
-        if S > 2:
-            allow_skip[2:] = (ext[2:] != 0) & (ext[2:] != ext[:-2])
-        alpha = torch.full((S,), neg_inf, dtype=torch.float64)
-        alpha[0] = lp[b, 0, 0]
-        if S > 1:
-            alpha[1] = lp[b, 0, ext[1]]
-        for t in range(1, T):
-            a1 = torch.cat([torch.tensor([neg_inf], dtype=torch.float64), alpha[:-1]])
-            a2 = torch.cat([torch.full((2,), neg_inf, dtype=torch.float64), alpha[:-2]]) if S > 2 else torch.full((S,), neg_inf, dtype=torch.float64)
-            a2 = torch.where(allow_skip, a2, torch.full_like(a2, neg_inf))
-            alpha = torch.logsumexp(torch.stack([alpha, a1, a2]), dim=0) + lp[b, t, ext]
-        tail = alpha[-2:] if S > 1 else alpha[-1:]
-        losses.append(-torch.logsumexp(tail, dim=0))
-    return torch.stack(losses).mean().to(logits.dtype), torch.stack(losses).to(logits.dtype)
+    logits_len = logits_len.long().clamp(max=T)
+    target_len = target_len.long()
+    Umax = max(int(target_len.max()), 0)
+    S = 2 * Umax + 1
+    # the recursion only moves upward in s, so states above an utterance's own 2U+1 never feed its read-out:
+    # all utterances share the widest extended sequence and are advanced together (vectorised over the batch)
+    ext = torch.zeros(B, S, dtype=torch.long)
+    if Umax:
+        ext[:, 1::2] = targets[:, :Umax].long()
+    lp_ext = lp.gather(2, ext[:, None, :].expand(B, T, S))
+    allow_skip = torch.zeros(B, S, dtype=torch.bool)
+    if S > 2:
+        allow_skip[:, 2:] = (ext[:, 2:] != 0) & (ext[:, 2:] != ext[:, :-2])
+    alpha = torch.full((B, S), neg_inf, dtype=torch.float64)
+    alpha[:, 0] = lp_ext[:, 0, 0]
+    if S > 1:
+        alpha[:, 1] = lp_ext[:, 0, 1]
+    pad1 = torch.full((B, 1), neg_inf, dtype=torch.float64)
+    pad2 = torch.full((B, 2), neg_inf, dtype=torch.float64)
+    for t in range(1, T):
+        a1 = torch.cat([pad1, alpha[:, :-1]], dim=1)
+        a2 = torch.cat([pad2, alpha[:, :-2]], dim=1) if S > 2 else torch.full_like(alpha, neg_inf)
+        a2 = torch.where(allow_skip, a2, torch.full_like(a2, neg_inf))
+        new = torch.logsumexp(torch.stack([alpha, a1, a2]), dim=0) + lp_ext[:, t]
+        alpha = torch.where((t < logits_len)[:, None], new, alpha)
+    last = 2 * target_len                                        # index S_b - 1
+    end1 = alpha.gather(1, last[:, None])[:, 0]
+    end2 = torch.where(last > 0, alpha.gather(1, (last - 1).clamp(min=0)[:, None])[:, 0], torch.full_like(end1, neg_inf))
+    losses = -torch.logsumexp(torch.stack([end1, end2]), dim=0)
+    losses = torch.where(logits_len > 0, losses, torch.full_like(losses, float("inf")))
+    return losses.mean().to(logits.dtype), losses.to(logits.dtype)
 
 
 def greedy_ids(logits, logits_len):
