@@ -29,6 +29,16 @@ __device__ __forceinline__ uint32_t tf32_bits(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return r;
 }
+// Ampere-style async copy global -> shared with zero fill (src_bytes in {0, size}); LDGSTS on sm_100a.
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
 __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -56,20 +66,51 @@ __global__ void __launch_bounds__(128) relpos_attn_kernel(const AttnDev p) {
   const size_t row3 = static_cast<size_t>(3) * D;
   const float* qkv_b = p.qkv + static_cast<size_t>(b) * T * row3;
 
-  // ---- stage Qu / Qv (tf32-rounded) ----
-  for (int idx = tid; idx < kAttBM * DP; idx += 128) {
-    const int r = idx / DP, c = idx % DP;
-    const int i = i0 + r;
-    float qu = 0.f, qv = 0.f;
-    if (c < d && i < Tg) {
-      const int f = h * d + c;
-      const int frame = i * G + f / D, ch = f % D;
-      const float q = frame < T ? __ldg(qkv_b + frame * row3 + ch) : 0.f;   // appended pad frames are exact zeros
-      qu = q + __ldg(p.u + ch);
-      qv = q + __ldg(p.v + ch);
+  grid_dependency_wait();
+  grid_launch_dependents();
+  // (frame offset, channel) of this head's first feature inside a grouped row: flat f = h*d + c -> frame i*G + f/D, channel f%D
+  const int f0 = h * d;
+  const int foff0 = f0 / D, ch0 = f0 - foff0 * D;
+  const bool vec2 = ((d | D) & 1) == 0;          // pairs (c, c+1) never straddle a frame and stay 8-byte aligned
+  auto locate = [&](int c, int& foff, int& ch) {  // c < d <= G*D, so at most G-1 wraps
+    foff = foff0; ch = ch0 + c;
+    while (ch >= D) { ch -= D; ++foff; }
+  };
+
+  // ---- stage Qu / Qv (q + u, q + v rounded to tf32): 8-byte loads, 8 pairs in flight per thread ----
+  if (vec2) {
+    constexpr int PR = DP / 2;
+#pragma unroll 4
+    for (int idx = tid; idx < kAttBM * PR; idx += 128) {
+      const int r = idx / PR, c = (idx % PR) * 2;
+      const int i = i0 + r;
+      float2 qu = make_float2(0.f, 0.f), qv = qu;
+      if (c < d && i < Tg) {
+        int foff, ch; locate(c, foff, ch);
+        const int frame = i * G + foff;
+        float2 q = make_float2(0.f, 0.f);                       // appended pad frames are exact zeros
+        if (frame < T) q = __ldg(reinterpret_cast<const float2*>(qkv_b + frame * row3 + ch));
+        const float2 uu = __ldg(reinterpret_cast<const float2*>(p.u + ch)), vv = __ldg(reinterpret_cast<const float2*>(p.v + ch));
+        qu = make_float2(q.x + uu.x, q.y + uu.y); qv = make_float2(q.x + vv.x, q.y + vv.y);
+      }
+      *reinterpret_cast<float2*>(Qu + r * STR + c) = make_float2(round_tf32(qu.x), round_tf32(qu.y));
+      *reinterpret_cast<float2*>(Qv + r * STR + c) = make_float2(round_tf32(qv.x), round_tf32(qv.y));
     }
-    Qu[r * STR + c] = round_tf32(qu);
-    Qv[r * STR + c] = round_tf32(qv);
+  } else {
+    for (int idx = tid; idx < kAttBM * DP; idx += 128) {
+      const int r = idx / DP, c = idx % DP;
+      const int i = i0 + r;
+      float qu = 0.f, qv = 0.f;
+      if (c < d && i < Tg) {
+        int foff, ch; locate(c, foff, ch);
+        const int frame = i * G + foff;
+        const float q = frame < T ? __ldg(qkv_b + frame * row3 + ch) : 0.f;
+        qu = q + __ldg(p.u + ch);
+        qv = q + __ldg(p.v + ch);
+      }
+      Qu[r * STR + c] = round_tf32(qu);
+      Qv[r * STR + c] = round_tf32(qv);
+    }
   }
 
   float o[DPT][4];
@@ -82,30 +123,52 @@ __global__ void __launch_bounds__(128) relpos_attn_kernel(const AttnDev p) {
 
   for (int j0 = 0; j0 < Tg; j0 += kAttBN) {
     __syncthreads();
-    // ---- stage K, V tile and the E band ----
-    for (int idx = tid; idx < kAttBN * DP; idx += 128) {
-      const int r = idx / DP, c = idx % DP;
-      const int j = j0 + r;
-      float kv = 0.f, vv = 0.f;
-      if (c < d && j < Tg) {
-        const int f = h * d + c;
-        const int frame = j * G + f / D, ch = f % D;
-        if (frame < T) {
-          kv = __ldg(qkv_b + frame * row3 + D + ch);
-          vv = __ldg(qkv_b + frame * row3 + 2 * D + ch);
-        }
-      }
-      Ks[r * STR + c] = round_tf32(kv);
-      Vs[r * STR + c] = round_tf32(vv);
-    }
+    // ---- stage the K, V tile and the E band with cp.async (global -> shared, zero-fill outside the valid region).
+    // K / V / E arrive already rounded to TF32 by the producing GEMM epilogues (round_out), so no register pass is needed.
     const int ebase = Tg - 1 + j0 - i0 - (kAttBM - 1);
-    for (int idx = tid; idx < 128 * DP; idx += 128) {
-      const int r = idx / DP, c = idx % DP;
-      const int e = ebase + r;
-      float ev = 0.f;
-      if (c < d && e >= 0 && e <= 2 * Tg - 2) ev = __ldg(p.E + e * e_row + h * d + c);
-      Es[r * STR + c] = round_tf32(ev);
+    if (vec2) {
+      constexpr int PR = DP / 2;
+      for (int idx = tid; idx < kAttBN * PR; idx += 128) {
+        const int r = idx / PR, c = (idx % PR) * 2;
+        const int j = j0 + r;
+        const float* src = qkv_b;
+        uint32_t bytes = 0;
+        if (c < d && j < Tg) {
+          int foff, ch; locate(c, foff, ch);
+          const int frame = j * G + foff;
+          if (frame < T) { src = qkv_b + frame * row3 + D + ch; bytes = 8; }
+        }
+        cp_async_8(smem_u32(Ks + r * STR + c), src, bytes);
+        cp_async_8(smem_u32(Vs + r * STR + c), src + D, bytes);
+      }
+      for (int idx = tid; idx < 128 * PR; idx += 128) {
+        const int r = idx / PR, c = (idx % PR) * 2;
+        const int e = ebase + r;
+        const bool ok = c < d && e >= 0 && e <= 2 * Tg - 2;
+        cp_async_8(smem_u32(Es + r * STR + c), ok ? p.E + e * e_row + f0 + c : p.E, ok ? 8u : 0u);
+      }
+    } else {
+      for (int idx = tid; idx < kAttBN * DP; idx += 128) {
+        const int r = idx / DP, c = idx % DP;
+        const int j = j0 + r;
+        const float* src = qkv_b;
+        uint32_t bytes = 0;
+        if (c < d && j < Tg) {
+          int foff, ch; locate(c, foff, ch);
+          const int frame = j * G + foff;
+          if (frame < T) { src = qkv_b + frame * row3 + D + ch; bytes = 4; }
+        }
+        cp_async_4(smem_u32(Ks + r * STR + c), src, bytes);
+        cp_async_4(smem_u32(Vs + r * STR + c), src + D, bytes);
+      }
+      for (int idx = tid; idx < 128 * DP; idx += 128) {
+        const int r = idx / DP, c = idx % DP;
+        const int e = ebase + r;
+        const bool ok = c < d && e >= 0 && e <= 2 * Tg - 2;
+        cp_async_4(smem_u32(Es + r * STR + c), ok ? p.E + e * e_row + f0 + c : p.E, ok ? 4u : 0u);
+      }
     }
+    cp_async_wait_all();
     __syncthreads();
 
     // ---- G = Qv_w . Eband_w^T  (16 x 80) -> per-warp smem strip ----
@@ -214,8 +277,8 @@ __global__ void __launch_bounds__(128) relpos_attn_kernel(const AttnDev p) {
       for (int e = 0; e < 2; ++e) {
         const int c = n * 8 + 2 * t + e;
         if (c < d) {
-          const int f = h * d + c;
-          const int frame = i * G + f / D, ch = f % D;
+          int foff, ch; locate(c, foff, ch);
+          const int frame = i * G + foff;
           if (frame < T) out[(static_cast<size_t>(b) * T + frame) * p.ld_out + ch] = Tr::to(o[n][hrow * 2 + e] * inv);
         }
       }
@@ -235,9 +298,7 @@ static int launch_attn_inst(const AttnDev& p, cudaStream_t stream) {
   EC_CUDA(attr_err);
   EC_REQUIRE(smem <= 227 * 1024, "attention tile does not fit in shared memory");
   dim3 grid(cdiv(p.Tg, kAttBM), p.H, p.B);
-  relpos_attn_kernel<DPT, OutT><<<grid, 128, smem, stream>>>(p);
-  EC_CUDA(cudaGetLastError());
-  return EC_OK;
+  return launch_pdl(relpos_attn_kernel<DPT, OutT>, grid, dim3(128), smem, stream, p);
 }
 
 template <typename T>

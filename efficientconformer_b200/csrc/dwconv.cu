@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(1024) dwconv_bn_swish_kernel(const T* __restri
   using Tr = ActTraits<T>;
   extern __shared__ __align__(16) uint8_t dw_smem[];
   T* tile = reinterpret_cast<T*>(dw_smem);
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int b = blockIdx.y;
   const int to0 = blockIdx.x * (kDwR * kDwRuns);
   const int pad = (K - 1) / 2;
@@ -95,9 +97,7 @@ static int launch_dw_t(const DwConvArgs& a, cudaStream_t stream) {
   if (a.stride == S && a.k == KK) {                                                                                    \
     static cudaError_t e = cudaFuncSetAttribute(dwconv_bn_swish_kernel<T, S, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
     EC_CUDA(e);                                                                                                        \
-    dwconv_bn_swish_kernel<T, S, KK><<<grid, block, smem, stream>>>(x, a.w, a.b, a.T, T_out, a.C, y);                  \
-    EC_CUDA(cudaGetLastError());                                                                                       \
-    return EC_OK;                                                                                                      \
+    return launch_pdl(dwconv_bn_swish_kernel<T, S, KK>, grid, block, smem, stream, x, a.w, a.b, a.T, T_out, a.C, y);   \
   }
   EC_DW_CASE(1, 15) EC_DW_CASE(2, 15) EC_DW_CASE(1, 31) EC_DW_CASE(2, 31)
 #undef EC_DW_CASE

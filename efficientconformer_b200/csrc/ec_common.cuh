@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <utility>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -32,6 +33,21 @@ void set_error(const std::string& msg);
     int _s = (call);              \
     if (_s != EC_OK) return _s;   \
   } while (0)
+
+// Kernel launch with the programmatic-stream-serialization attribute (PDL): the kernel may start while its predecessor
+// drains; every kernel of the forward chain executes griddepcontrol.wait before touching predecessor output.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  EC_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+  return EC_OK;
+}
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int round_up(int a, int b) { return cdiv(a, b) * b; }
@@ -69,6 +85,12 @@ struct GemmArgs {
   const float* residual; int ld_res;   // fp32 [M, *] or nullptr
   float* out_f32; int ld_out;          // optional fp32 output
   void* out_act; int ld_act;           // optional activation-type output (rounded)
+  int round_out;                       // round the fp32 output to TF32 (feeds the TF32 mma.sync attention)
+  // fused LayerNorm epilogue (N <= 256, plain epilogue): mode 1: ln_out = LN1(out); mode 2: out <- LN1(out), ln_out = LN2(out)
+  // (LN2 = identity copy when ln2_g == nullptr).  copy_out: activation-type copy of every copy_stride-th frame of `out` (mode 1).
+  int ln_mode; const float *ln1_g, *ln1_b, *ln2_g, *ln2_b; float ln_eps;
+  void* ln_out;
+  void* copy_out; int copy_stride, frames_per_seq, frames_out_per_seq;
 };
 int launch_gemm(int precision, const GemmArgs& a, cudaStream_t stream);
 

@@ -10,20 +10,22 @@ namespace ec {
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kLnMaxPerLane = 32;   // dim <= 1024
 
-template <typename T>
+template <typename T, int NPL>      // NPL = elements per lane kept in registers (dim <= 32 * NPL)
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int rows, int dim,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                         T* __restrict__ y_act, float* __restrict__ y_f32, T* __restrict__ copy_out,
                                                         int copy_stride, int frames_per_seq, int frames_out_per_seq) {
   using Tr = ActTraits<T>;
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const float* xr = x + static_cast<size_t>(warp) * dim;
-  float v[kLnMaxPerLane];
+  float v[NPL];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; ++i) {
+  for (int i = 0; i < NPL; ++i) {
     const int c = lane + 32 * i;
     v[i] = (c < dim) ? xr[c] : 0.f;
     sum += v[i];
@@ -33,7 +35,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const float mu = sum / dim;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; ++i) {
+  for (int i = 0; i < NPL; ++i) {
     const int c = lane + 32 * i;
     const float d = (c < dim) ? v[i] - mu : 0.f;
     sq += d * d;
@@ -47,7 +49,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     if (t % copy_stride == 0) copy_row = copy_out + (static_cast<size_t>(seq) * frames_out_per_seq + t / copy_stride) * dim;
   }
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; ++i) {
+  for (int i = 0; i < NPL; ++i) {
     const int c = lane + 32 * i;
     if (c < dim) {
       const float o = (v[i] - mu) * rstd * gamma[c] + beta[c];
@@ -67,10 +69,10 @@ static int launch_layernorm_t(const LayerNormArgs& a, cudaStream_t stream) {
   T* copy = reinterpret_cast<T*>(a.copy_out);
   const int cs = a.copy_stride > 0 ? a.copy_stride : 1;
   const int fps = a.frames_per_seq > 0 ? a.frames_per_seq : a.rows;
-  layernorm_kernel<T><<<grid, threads, 0, stream>>>(a.x, a.rows, a.dim, a.gamma, a.beta, a.eps, reinterpret_cast<T*>(a.y_act), a.y_f32,
-                                                    copy, cs, fps, a.frames_out_per_seq);
-  EC_CUDA(cudaGetLastError());
-  return EC_OK;
+  T* ya = reinterpret_cast<T*>(a.y_act);
+  if (a.dim <= 128) return launch_pdl(layernorm_kernel<T, 4>, grid, dim3(threads), 0, stream, a.x, a.rows, a.dim, a.gamma, a.beta, a.eps, ya, a.y_f32, copy, cs, fps, a.frames_out_per_seq);
+  if (a.dim <= 256) return launch_pdl(layernorm_kernel<T, 8>, grid, dim3(threads), 0, stream, a.x, a.rows, a.dim, a.gamma, a.beta, a.eps, ya, a.y_f32, copy, cs, fps, a.frames_out_per_seq);
+  return launch_pdl(layernorm_kernel<T, kLnMaxPerLane>, grid, dim3(threads), 0, stream, a.x, a.rows, a.dim, a.gamma, a.beta, a.eps, ya, a.y_f32, copy, cs, fps, a.frames_out_per_seq);
 }
 
 int launch_layernorm(int precision, const LayerNormArgs& a, cudaStream_t stream) {
@@ -157,6 +159,7 @@ int launch_glu_interleave(int precision, const float* w, const float* b, int cha
 // x_len == nullptr -> full length.  out is [(n_blocks+1), B].
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void stage_lengths_kernel(const long long* x_len, int B, int t_mel, BlockStrides st, int* out) {
+  grid_dependency_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   long long l = x_len != nullptr ? x_len[b] : t_mel;
@@ -180,6 +183,7 @@ __global__ void i64_to_i32_kernel(const long long* src, int n, int* dst, int cla
   if (i < n) { long long v = src[i]; if (v > clamp_max) v = clamp_max; if (v < 0) v = 0; dst[i] = static_cast<int>(v); }
 }
 __global__ void i32_to_i64_kernel(const int* src, int n, long long* dst) {
+  grid_dependency_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i];
 }

@@ -4,6 +4,7 @@
 // end) and models/blocks.py:119-137 (ConformerBlock.forward) as a fixed, stream-ordered launch sequence that is
 // CUDA-graph capturable: no allocation, no host synchronisation, no data-dependent host control flow.
 #include "ec_common.cuh"
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -11,6 +12,12 @@ namespace ec {
 
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+
+static int g_pdl = -1;   // -1: read EFFCONF_PDL (default on)
+bool pdl_enabled() {
+  if (g_pdl < 0) { const char* e = getenv("EFFCONF_PDL"); g_pdl = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return g_pdl != 0;
+}
 
 struct Arena {   // bump allocator over a caller-provided buffer (or a dry run when base == nullptr)
   uint8_t* base; size_t off;
@@ -62,6 +69,7 @@ struct ec_engine {
   std::vector<cudaEvent_t> event_pool;
   size_t events_used = 0;
   int last_launches = 0;
+  bool fuse_ln = true;     // LayerNorms in the epilogue of the producing GEMM (needs dim <= 256)
 };
 
 namespace ec {
@@ -183,9 +191,19 @@ struct ProfScope {
   ~ProfScope() { if (on) cudaEventRecord(e->prof.back().e1, st); }
 };
 
+struct LnFuse {            // optional fused LayerNorm epilogue of a GEMM
+  int mode = 0; const float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr; void* y = nullptr;
+  void* copy_out = nullptr; int copy_stride = 1, fps = 0, fops = 0;
+};
 static int gemm(ec_engine* e, cudaStream_t st, int cat, const void* A, const void* W, int M, int N, int K, const float* bias, float alpha,
-                int act, const float* residual, float* out_f32, void* out_act, int glu_nb = 0, int glu_channels = 0) {
+                int act, const float* residual, float* out_f32, void* out_act, int glu_nb = 0, int glu_channels = 0,
+                const LnFuse* ln = nullptr, int round_out = 0) {
   GemmArgs g{};
+  g.round_out = round_out;
+  if (ln != nullptr && ln->mode != 0) {
+    g.ln_mode = ln->mode; g.ln1_g = ln->g1; g.ln1_b = ln->b1; g.ln2_g = ln->g2; g.ln2_b = ln->b2; g.ln_eps = 1e-6f; g.ln_out = ln->y;
+    g.copy_out = ln->copy_out; g.copy_stride = ln->copy_stride; g.frames_per_seq = ln->fps; g.frames_out_per_seq = ln->fops;
+  }
   g.A = A; g.W = W; g.M = M; g.N = N; g.K = K; g.bias = bias; g.alpha = alpha; g.act = act;
   g.glu_nb = glu_nb; g.glu_channels = glu_channels;
   const int ncols = glu_nb > 0 ? glu_channels : N;
@@ -368,7 +386,13 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
   }
   const int D0 = c.blocks[0].dim_model;
   float* x = ws.xa; float* x_alt = ws.xb;
-  EC_TRY(gemm(e, st, PC_LIN, ws.sub_a, w.lin_w, B * sh.t0, D0, feat, w.lin_b, 1.f, GEMM_ACT_NONE, nullptr, x, nullptr));
+  bool fuse = e->fuse_ln;
+  for (int i = 0; i < c.num_blocks; ++i) fuse = fuse && c.blocks[i].dim_model <= 256 && c.blocks[i].dim_expand <= 256;
+  {
+    LnFuse ln;   // fused: xn = LN_ffn1(x0) for block 0
+    if (fuse) { ln.mode = 1; ln.g1 = w.blk[0].ffn1.ln_w; ln.b1 = w.blk[0].ffn1.ln_b; ln.y = ws.xn; }
+    EC_TRY(gemm(e, st, PC_LIN, ws.sub_a, w.lin_w, B * sh.t0, D0, feat, w.lin_b, 1.f, GEMM_ACT_NONE, nullptr, x, nullptr, 0, 0, &ln));
+  }
 
   for (int i = 0; i < c.num_blocks; ++i) {
     const ec_block_cfg& bc = c.blocks[i];
@@ -377,17 +401,23 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
     const int T = sh.t_in[i], To = sh.t_out[i];
     const int M = B * T, Mo = B * To;
     const int* lens = ws.lens + static_cast<size_t>(i) * B;
-    // FFN1: x1 = x + 0.5 * W2 swish(W1 LN(x))
-    EC_TRY(lnorm(e, st, x, M, D, b.ffn1.ln_w, b.ffn1.ln_b, ws.xn, nullptr));
+    const bool proj = D != De;
+    const bool last = i == c.num_blocks - 1;
+    // FFN1: x1 = x + 0.5 * W2 swish(W1 LN(x))          [fused: epilogue also emits xn = LN_att(x1)]
+    if (!fuse) EC_TRY(lnorm(e, st, x, M, D, b.ffn1.ln_w, b.ffn1.ln_b, ws.xn, nullptr));
     EC_TRY(gemm(e, st, PC_FFN_W1, ws.xn, b.ffn1.w1, M, Fr * D, D, b.ffn1.b1, 1.f, GEMM_ACT_SWISH, nullptr, nullptr, ws.h));
-    EC_TRY(gemm(e, st, PC_FFN_W2, ws.h, b.ffn1.w2, M, D, Fr * D, b.ffn1.b2, 0.5f, GEMM_ACT_NONE, x, x_alt, nullptr));
+    {
+      LnFuse ln;
+      if (fuse) { ln.mode = 1; ln.g1 = b.att_ln_w; ln.b1 = b.att_ln_b; ln.y = ws.xn; }
+      EC_TRY(gemm(e, st, PC_FFN_W2, ws.h, b.ffn1.w2, M, D, Fr * D, b.ffn1.b2, 0.5f, GEMM_ACT_NONE, x, x_alt, nullptr, 0, 0, &ln));
+    }
     std::swap(x, x_alt);
-    // MHSA: x2 = x1 + Wo attn(LN(x1))
-    EC_TRY(lnorm(e, st, x, M, D, b.att_ln_w, b.att_ln_b, ws.xn, nullptr));
-    EC_TRY(gemm(e, st, PC_QKV, ws.xn, b.wqkv, M, 3 * D, D, b.bqkv, 1.f, GEMM_ACT_NONE, nullptr, ws.qkv, nullptr));
+    // MHSA: x2 = x1 + Wo attn(LN(x1))                   [fused: epilogue emits xn = LN_conv(x2) and the strided copy xs]
+    if (!fuse) EC_TRY(lnorm(e, st, x, M, D, b.att_ln_w, b.att_ln_b, ws.xn, nullptr));
+    EC_TRY(gemm(e, st, PC_QKV, ws.xn, b.wqkv, M, 3 * D, D, b.bqkv, 1.f, GEMM_ACT_NONE, nullptr, ws.qkv, nullptr, 0, 0, nullptr, 1));
     const int G = bc.group_size, P = (G - T % G) % G, e_rows = 2 * (T + P) - G;
     EC_REQUIRE(relpos[i] != nullptr, "missing relative position table");
-    EC_TRY(gemm(e, st, PC_POS, relpos[i], b.wpos, e_rows, D, D, b.bpos, 1.f, GEMM_ACT_NONE, nullptr, ws.ebuf, nullptr));
+    EC_TRY(gemm(e, st, PC_POS, relpos[i], b.wpos, e_rows, D, D, b.bpos, 1.f, GEMM_ACT_NONE, nullptr, ws.ebuf, nullptr, 0, 0, nullptr, 1));
     {
       AttnArgs aa{ws.qkv, ws.ebuf, b.u, b.v, lens, B, T, D, bc.num_heads, G, ws.o, D};
       const double Tg = static_cast<double>(T + P) / G, dh = static_cast<double>(G) * D / bc.num_heads;
@@ -395,11 +425,17 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
                    4.0 * M * 3 * D + 4.0 * e_rows * D + es * M * D);
       EC_TRY(launch_relpos_attention(prec, aa, st));
     }
-    EC_TRY(gemm(e, st, PC_OUT, ws.o, b.wo, M, D, D, b.bo, 1.f, GEMM_ACT_NONE, x, x_alt, nullptr));
+    {
+      LnFuse ln;
+      if (fuse) {
+        ln.mode = 1; ln.g1 = b.conv_ln_w; ln.b1 = b.conv_ln_b; ln.y = ws.xn;
+        if (proj) { ln.copy_out = ws.xs; ln.copy_stride = bc.conv_stride; ln.fps = T; ln.fops = To; }
+      }
+      EC_TRY(gemm(e, st, PC_OUT, ws.o, b.wo, M, D, D, b.bo, 1.f, GEMM_ACT_NONE, x, x_alt, nullptr, 0, 0, &ln));
+    }
     std::swap(x, x_alt);
-    // Conv module: x3 = conv_res(x2) + pw2 swish(bn(dw(glu(pw1 LN(x2)))))
-    const bool proj = D != De;
-    EC_TRY(lnorm(e, st, x, M, D, b.conv_ln_w, b.conv_ln_b, ws.xn, nullptr, proj ? ws.xs : nullptr, bc.conv_stride, T, To));
+    // Conv module: x3 = conv_res(x2) + pw2 swish(bn(dw(glu(pw1 LN(x2)))))     [fused: epilogue emits xn = LN_ffn2(x3)]
+    if (!fuse) EC_TRY(lnorm(e, st, x, M, D, b.conv_ln_w, b.conv_ln_b, ws.xn, nullptr, proj ? ws.xs : nullptr, bc.conv_stride, T, To));
     EC_TRY(gemm(e, st, PC_PW1_GLU, ws.xn, b.pw1, M, b.glu_tiles * 2 * b.glu_nb, D, b.pw1_b, 1.f, GEMM_ACT_NONE, nullptr, nullptr, ws.gl, b.glu_nb, De));
     {
       DwConvArgs da{ws.gl, b.dw_w, b.dw_b, B, T, De, bc.kernel_size, bc.conv_stride, ws.hc};
@@ -411,17 +447,30 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
       EC_TRY(gemm(e, st, PC_RES, ws.xs, b.res_w, Mo, De, D, b.res_b, 1.f, GEMM_ACT_NONE, nullptr, ws.r, nullptr));
       res = ws.r;
     }
-    EC_TRY(gemm(e, st, PC_PW2, ws.hc, b.pw2, Mo, De, De, b.pw2_b, 1.f, GEMM_ACT_NONE, res, x_alt, nullptr));
+    {
+      LnFuse ln;
+      if (fuse) { ln.mode = 1; ln.g1 = b.ffn2.ln_w; ln.b1 = b.ffn2.ln_b; ln.y = ws.xn; }
+      EC_TRY(gemm(e, st, PC_PW2, ws.hc, b.pw2, Mo, De, De, b.pw2_b, 1.f, GEMM_ACT_NONE, res, x_alt, nullptr, 0, 0, &ln));
+    }
     std::swap(x, x_alt);
-    // FFN2 + block LayerNorm
-    EC_TRY(lnorm(e, st, x, Mo, De, b.ffn2.ln_w, b.ffn2.ln_b, ws.xn, nullptr));
+    // FFN2 + block LayerNorm        [fused: epilogue normalises in place (block norm) and emits the next GEMM's operand]
+    if (!fuse) EC_TRY(lnorm(e, st, x, Mo, De, b.ffn2.ln_w, b.ffn2.ln_b, ws.xn, nullptr));
     EC_TRY(gemm(e, st, PC_FFN_W1, ws.xn, b.ffn2.w1, Mo, Fr * De, De, b.ffn2.b1, 1.f, GEMM_ACT_SWISH, nullptr, nullptr, ws.h));
-    EC_TRY(gemm(e, st, PC_FFN_W2, ws.h, b.ffn2.w2, Mo, De, Fr * De, b.ffn2.b2, 0.5f, GEMM_ACT_NONE, x, x_alt, nullptr));
-    std::swap(x, x_alt);
-    const bool last = i == c.num_blocks - 1;
     float* y = (last && out_x != nullptr) ? out_x : x_alt;
-    EC_TRY(lnorm(e, st, x, Mo, De, b.norm_w, b.norm_b, (last && logits != nullptr) ? ws.xn : nullptr, y));
-    if (!(last && out_x != nullptr)) std::swap(x, x_alt);
+    if (fuse) {
+      LnFuse ln;
+      ln.mode = 2; ln.g1 = b.norm_w; ln.b1 = b.norm_b;
+      if (!last) { ln.g2 = w.blk[i + 1].ffn1.ln_w; ln.b2 = w.blk[i + 1].ffn1.ln_b; ln.y = ws.xn; }
+      else { ln.g2 = nullptr; ln.b2 = nullptr; ln.y = logits != nullptr ? ws.xn : nullptr; }     // fc operand = rounded copy of the block output
+      EC_TRY(gemm(e, st, PC_FFN_W2, ws.h, b.ffn2.w2, Mo, De, Fr * De, b.ffn2.b2, 0.5f, GEMM_ACT_NONE, x, y, nullptr, 0, 0, &ln));
+      if (!(last && out_x != nullptr)) x_alt = x, x = y;
+    } else {
+      EC_TRY(gemm(e, st, PC_FFN_W2, ws.h, b.ffn2.w2, Mo, De, Fr * De, b.ffn2.b2, 0.5f, GEMM_ACT_NONE, x, x_alt, nullptr));
+      std::swap(x, x_alt);
+      y = (last && out_x != nullptr) ? out_x : x_alt;
+      EC_TRY(lnorm(e, st, x, Mo, De, b.norm_w, b.norm_b, (last && logits != nullptr) ? ws.xn : nullptr, y));
+      if (!(last && out_x != nullptr)) std::swap(x, x_alt);
+    }
   }
   if (logits != nullptr) {
     const int Dl = c.blocks[c.num_blocks - 1].dim_expand;
@@ -435,6 +484,9 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
 int ec_profile_categories(void) { return PC_COUNT; }
 const char* ec_profile_category_name(int cat) { return (cat >= 0 && cat < PC_COUNT) ? kProfNames[cat] : ""; }
 int ec_engine_set_profiling(ec_engine* e, int enabled) { e->prof_enabled = enabled != 0; return EC_OK; }
+/* option 0: fuse LayerNorm into the GEMM epilogues (default 1).  Global option via ec_set_pdl: programmatic dependent launch. */
+int ec_engine_set_fuse_ln(ec_engine* e, int enabled) { e->fuse_ln = enabled != 0; return EC_OK; }
+int ec_set_pdl(int enabled) { g_pdl = enabled != 0 ? 1 : 0; return EC_OK; }
 int ec_engine_last_launches(const ec_engine* e) { return e->last_launches; }
 /* sums the CUDA-event durations of the last (eager, profiled) forward per category; synchronises the recorded events */
 int ec_engine_profile_read(ec_engine* e, double* ms, double* flops, double* bytes, int32_t* launches) {
@@ -495,6 +547,16 @@ int ec_op_gemm(int precision, const void* A, const void* W, int M, int N, int K,
   GemmArgs g{};
   g.A = A; g.W = W; g.M = M; g.N = N; g.K = K; g.bias = bias; g.alpha = alpha; g.act = act;
   g.residual = residual; g.ld_res = N; g.out_f32 = out_f32; g.ld_out = N; g.out_act = out_act; g.ld_act = N;
+  return launch_gemm(precision, g, reinterpret_cast<cudaStream_t>(stream));
+}
+int ec_op_gemm_ln(int precision, const void* A, const void* W, int M, int N, int K, const float* bias, float alpha, const float* residual,
+                  float* out_f32, int ln_mode, const float* g1, const float* b1, const float* g2, const float* b2, float eps, void* ln_out,
+                  void* copy_out, int copy_stride, int frames_per_seq, int frames_out_per_seq, void* stream) {
+  GemmArgs g{};
+  g.A = A; g.W = W; g.M = M; g.N = N; g.K = K; g.bias = bias; g.alpha = alpha; g.act = GEMM_ACT_NONE;
+  g.residual = residual; g.ld_res = N; g.out_f32 = out_f32; g.ld_out = N;
+  g.ln_mode = ln_mode; g.ln1_g = g1; g.ln1_b = b1; g.ln2_g = g2; g.ln2_b = b2; g.ln_eps = eps; g.ln_out = ln_out;
+  g.copy_out = copy_out; g.copy_stride = copy_stride; g.frames_per_seq = frames_per_seq; g.frames_out_per_seq = frames_out_per_seq;
   return launch_gemm(precision, g, reinterpret_cast<cudaStream_t>(stream));
 }
 int ec_op_pointwise_glu(int precision, const void* A, const float* w_raw, const float* b_raw, int M, int channels, int K, void* w_scratch,

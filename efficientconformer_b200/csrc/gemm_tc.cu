@@ -1,14 +1,19 @@
-// tcgen05 GEMM with fused epilogues:  out = alpha * act(A @ W^T + bias) [+ residual]   (optionally GLU over column halves)
+// tcgen05 GEMM with fused epilogues:
+//     out = alpha * act(A @ W^T + bias) [+ residual]          (optionally GLU over column halves)
+//     [+ LayerNorm(out) / LayerNorm(LayerNorm(out)) written in the activation type for the next GEMM]
 //
 // Replaces every dense contraction on the hot path (reference models/layers.py:67 F.linear, :136 pointwise F.conv1d):
 // FFN projections, QKV / positional / output projections, pointwise convs of the convolution module, conv_res,
-// the subsampling Linear and the CTC fc head.
+// the subsampling Linear and the CTC fc head -- and, through the fused epilogue, the five nn.LayerNorm(eps=1e-6) of a
+// block (reference models/modules.py:386,433,511; models/blocks.py:96,135).
 //
 // One CTA = one 128 x BLOCK_N output tile over the whole K.  Warp roles (192 threads):
 //   warp 0   TMA producer  : cp.async.bulk.tensor loads of the A (128 x 128B) and W (BLOCK_N x 128B) k-slices, 128B swizzle
 //   warp 1   MMA issuer    : allocates TMEM, one thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 32B), fp32 accumulator in TMEM
-//   warps 2-5 epilogue     : tcgen05.ld (thread = output row) -> bias/activation -> padded smem transpose -> coalesced
-//                            residual add + fp32 / activation-type stores
+//   warps 2-5 epilogue     : tcgen05.ld (thread = output row) -> padded smem transpose -> (lane = output column)
+//                            bias / Swish / GLU / alpha / residual in registers with 32 independent rows in flight ->
+//                            coalesced fp32 / activation-type stores; optional per-row LayerNorm statistics by a
+//                            register reduce-scatter across the warp, then normalise sweeps over the CTA's own output.
 // K and N tails are zero-filled by TMA out-of-bounds handling, so D, 4D, head dims etc. need no host-side padding
 // (only 16-byte row pitches).  Operand type float => kind::tf32, __nv_bfloat16 => kind::f16.
 #include "ec_common.cuh"
@@ -28,6 +33,13 @@ struct GemmDev {
   const float* residual; int ld_res;
   float* out_f32; int ld_out;
   void* out_act; int ld_act;
+  int round_out;     // round the fp32 output to TF32 (it feeds a TF32 mma.sync consumer)
+  // fused LayerNorm (kLN instantiation only; requires a single N tile)
+  int ln_mode;       // 1: y = LN1(out);  2: out <- LN1(out), y = LN2(out) (LN2 identity when ln2_g == nullptr)
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  float ln_eps;
+  void* ln_out; int ld_ln;                 // y, activation type (may be null)
+  void* copy_out; int copy_stride, frames_per_seq, frames_out_per_seq;   // strided compaction of `out` (LN1 mode), activation type
 };
 
 constexpr int kBlockM = 128;
@@ -35,8 +47,24 @@ constexpr int kATileBytes = kBlockM * 128;
 constexpr int kStagingBytes = 4 * 32 * 33 * 4;
 constexpr int kMaxStages = 8;
 
-template <typename T>
-__global__ void __launch_bounds__(192, 2)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+// After the call, lane l holds in s[0] the sum over all lanes of s[l] (31 shuffles for 32 values).
+__device__ __forceinline__ void warp_reduce_scatter32(float (&s)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? s[i] : s[i + off];
+      const float keep = upper ? s[i + off] : s[i];
+      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
+template <typename T, bool kLN>
+__global__ void __launch_bounds__(192, kLN ? 1 : 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
   using Tr = ActTraits<T>;
   extern __shared__ uint8_t smem_raw[];
@@ -74,6 +102,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on we read its output.
+  grid_dependency_wait();
+  grid_launch_dependents();
 
   if (warp_idx == 0) {
     if (lane == 0) {
@@ -111,57 +142,157 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp_idx % 4) ----------------
     const int q = warp_idx & 3;
     float* stg = staging + q * (32 * 33);
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
     const bool glu = p.glu_nb > 0;
     const int cols = glu ? p.glu_nb : p.block_n;            // logical output columns of this tile
     const int out_col0 = glu ? tile_n * p.glu_nb : w_row0;
     const int n_limit = glu ? p.glu_channels : p.N;
-    const int bias0 = w_row0;
+    const int row0 = m0 + q * 32;
+    const int rows_valid = min(32, p.M - row0);             // may be <= 0 for the tail tile
     T* out_act = reinterpret_cast<T*>(p.out_act);
+    float s1[kLN ? 32 : 1], s2[kLN ? 32 : 1];               // LayerNorm partial sums: lane = column, index = row
+    if constexpr (kLN) {
+#pragma unroll
+      for (int r = 0; r < 32; ++r) { s1[r] = 0.f; s2[r] = 0.f; }
+    }
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
     for (int c0 = 0; c0 < cols; c0 += 32) {
+      const int n = out_col0 + c0 + lane;
+      const bool n_ok = (c0 + lane) < cols && n < n_limit;
+      // per-column constants first (their latency hides behind the TMEM load + transpose)
+      float bias_a = 0.f, bias_g = 0.f;
+      if (p.bias != nullptr && n_ok) {
+        if (glu) { bias_a = __ldg(p.bias + w_row0 + c0 + lane); bias_g = __ldg(p.bias + w_row0 + p.glu_nb + c0 + lane); }
+        else bias_a = __ldg(p.bias + n);
+      }
+      float rr[32];
+      const bool has_res = p.residual != nullptr;
+      if (has_res) {
+        const float* rp = p.residual + static_cast<size_t>(row0) * p.ld_res + n;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) rr[r] = (n_ok && r < rows_valid) ? __ldg(rp + static_cast<size_t>(r) * p.ld_res) : 0.f;
+      }
       uint32_t v[32];
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
       tmem_ld_32x32(taddr, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+      __syncwarp();
+      float t[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) t[r] = stg[r * 33 + lane] + bias_a;
+      __syncwarp();
       if (glu) {
-        uint32_t g[32];
-        tmem_ld_32x32(taddr + static_cast<uint32_t>(p.glu_nb), g);
+        tmem_ld_32x32(taddr + static_cast<uint32_t>(p.glu_nb), v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int cj = c0 + j;
-          float a = __uint_as_float(v[j]), gt = __uint_as_float(g[j]);
-          if (cj < cols) {   // bias is stored in the interleaved (prepared) order: [nb value | nb gate] per tile
-            a += __ldg(p.bias + bias0 + cj);
-            gt += __ldg(p.bias + bias0 + p.glu_nb + cj);
-          }
-          stg[lane * 33 + j] = a * sigmoidf_(gt);
-        }
-      } else {
-        tmem_ld_wait();
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float a = __uint_as_float(v[j]);
-          const int n = out_col0 + c0 + j;
-          if (p.bias != nullptr && n < n_limit) a += __ldg(p.bias + n);
-          if (p.act == GEMM_ACT_SWISH) a = swishf_(a);
-          stg[lane * 33 + j] = a;
-        }
+        for (int r = 0; r < 32; ++r) t[r] *= fast_sigmoid(stg[r * 33 + lane] + bias_g);
+        __syncwarp();
       }
-      __syncwarp();
-      const int n = out_col0 + c0 + lane;
-      const bool n_ok = (c0 + lane) < cols && n < n_limit;
-#pragma unroll 4
+      if (p.act == GEMM_ACT_SWISH) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) t[r] *= fast_sigmoid(t[r]);
+      }
+#pragma unroll
       for (int r = 0; r < 32; ++r) {
-        const int m = m0 + q * 32 + r;
-        if (m < p.M && n_ok) {
-          float t = p.alpha * stg[r * 33 + lane];
-          if (p.residual != nullptr) t += __ldg(p.residual + static_cast<size_t>(m) * p.ld_res + n);
-          if (p.out_f32 != nullptr) p.out_f32[static_cast<size_t>(m) * p.ld_out + n] = t;
-          if (out_act != nullptr) out_act[static_cast<size_t>(m) * p.ld_act + n] = Tr::to(t);
+        t[r] *= p.alpha;
+        if (has_res) t[r] += rr[r];
+        if (p.round_out) t[r] = round_tf32(t[r]);
+      }
+      if (n_ok) {
+        if (p.out_f32 != nullptr) {
+          float* op = p.out_f32 + static_cast<size_t>(row0) * p.ld_out + n;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) if (r < rows_valid) op[static_cast<size_t>(r) * p.ld_out] = t[r];
+        }
+        if (out_act != nullptr) {
+          T* op = out_act + static_cast<size_t>(row0) * p.ld_act + n;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) if (r < rows_valid) op[static_cast<size_t>(r) * p.ld_act] = Tr::to(t[r]);
         }
       }
-      __syncwarp();
+      if constexpr (kLN) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const float tv = (n_ok && r < rows_valid) ? t[r] : 0.f;
+          s1[r] += tv; s2[r] = fmaf(tv, tv, s2[r]);
+        }
+      }
+    }
+    if constexpr (kLN) {
+      // ---- fused LayerNorm(s): this CTA holds every column of its 128 rows.  Row statistics come from the per-lane
+      // partial sums by a reduce-scatter (lane r ends up with row r); the values are re-read from this warp's own
+      // fp32 output (each thread reads back exactly the addresses it wrote), normalised and written once more. ----
+      const float inv_n = 1.0f / static_cast<float>(p.N);
+      float mu[32], rs[32];
+      auto finish_stats = [&]() {
+        warp_reduce_scatter32(s1, lane);
+        warp_reduce_scatter32(s2, lane);
+        const float mean = s1[0] * inv_n;
+        const float var = fmaxf(s2[0] * inv_n - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + p.ln_eps);
+#pragma unroll
+        for (int r = 0; r < 32; ++r) { mu[r] = __shfl_sync(0xffffffffu, mean, r); rs[r] = __shfl_sync(0xffffffffu, rstd, r); }
+      };
+      finish_stats();
+      const float* g_fin = p.ln1_g; const float* b_fin = p.ln1_b;
+      if (p.ln_mode == 2) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) { s1[r] = 0.f; s2[r] = 0.f; }
+        for (int c0 = 0; c0 < cols; c0 += 32) {
+          const int n = out_col0 + c0 + lane;
+          const bool n_ok = (c0 + lane) < cols && n < n_limit;
+          const float g = n_ok ? __ldg(p.ln1_g + n) : 0.f, b = n_ok ? __ldg(p.ln1_b + n) : 0.f;
+          float* op = p.out_f32 + static_cast<size_t>(row0) * p.ld_out + n;
+          float x[32];
+#pragma unroll
+          for (int r = 0; r < 32; ++r) x[r] = (n_ok && r < rows_valid) ? op[static_cast<size_t>(r) * p.ld_out] : 0.f;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            const float y = (x[r] - mu[r]) * rs[r] * g + b;
+            if (n_ok && r < rows_valid) {
+              op[static_cast<size_t>(r) * p.ld_out] = y;
+              s1[r] += y; s2[r] = fmaf(y, y, s2[r]);
+            }
+          }
+        }
+        g_fin = p.ln2_g; b_fin = p.ln2_b;
+        if (g_fin != nullptr) finish_stats();
+      }
+      if (p.ln_out != nullptr || p.copy_out != nullptr) {
+        T* ln_out = reinterpret_cast<T*>(p.ln_out);
+        T* copy_out = reinterpret_cast<T*>(p.copy_out);
+        for (int c0 = 0; c0 < cols; c0 += 32) {
+          const int n = out_col0 + c0 + lane;
+          const bool n_ok = (c0 + lane) < cols && n < n_limit;
+          const float g = (g_fin != nullptr && n_ok) ? __ldg(g_fin + n) : 1.f, b = (g_fin != nullptr && n_ok) ? __ldg(b_fin + n) : 0.f;
+          const float* op = p.out_f32 + static_cast<size_t>(row0) * p.ld_out + n;
+          float x[32];
+#pragma unroll
+          for (int r = 0; r < 32; ++r) x[r] = (n_ok && r < rows_valid) ? op[static_cast<size_t>(r) * p.ld_out] : 0.f;
+          if (n_ok) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              if (r < rows_valid) {
+                const int m = row0 + r;
+                if (ln_out != nullptr) {
+                  const float y = g_fin != nullptr ? (x[r] - mu[r]) * rs[r] * g + b : x[r];
+                  ln_out[static_cast<size_t>(m) * p.ld_ln + n] = Tr::to(y);
+                }
+                if (copy_out != nullptr) {
+                  const int seq = m / p.frames_per_seq, tt = m - seq * p.frames_per_seq;
+                  if (tt % p.copy_stride == 0)
+                    copy_out[(static_cast<size_t>(seq) * p.frames_out_per_seq + tt / p.copy_stride) * p.N + n] = Tr::to(x[r]);
+                }
+              }
+            }
+          }
+        }
+      }
     }
   }
   tc_fence_before();
@@ -213,7 +344,7 @@ static int pick_block_n(int N) {
   return round_up(cdiv(N, tiles), 16);
 }
 
-template <typename T>
+template <typename T, bool kLN>
 static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) {
   using Tr = ActTraits<T>;
   EC_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "empty GEMM");
@@ -232,7 +363,9 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   p.num_k_blocks = cdiv(a.K, Tr::kBlockK);
   const int stage_bytes = kATileBytes + p.block_n * 128;
   const int fixed = kStagingBytes + (2 * kMaxStages + 2) * 8 + 1024;
-  const int budget = (p.num_k_blocks <= 8 ? 110 : 208) * 1024;
+  // up to 148 CTAs: one CTA per SM anyway -> deep ring (hides the TMA->MMA->refill round trip); otherwise 2 CTAs per SM
+  const int ctas = cdiv(a.M, kBlockM) * tiles_n;
+  const int budget = (ctas <= 148 || kLN) ? 208 * 1024 : 113 * 1024;
   int stages = (budget - fixed) / stage_bytes;
   if (stages < 2) stages = 2;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -249,8 +382,20 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   p.residual = a.residual; p.ld_res = a.ld_res;
   p.out_f32 = a.out_f32; p.ld_out = a.ld_out;
   p.out_act = a.out_act; p.ld_act = a.ld_act;
+  p.round_out = a.round_out;
   EC_REQUIRE(a.out_f32 != nullptr || a.out_act != nullptr, "GEMM needs at least one output");
   EC_REQUIRE(a.glu_nb == 0 || a.bias != nullptr, "GLU GEMM needs a bias");
+  if (kLN) {
+    EC_REQUIRE(a.ln_mode == 1 || a.ln_mode == 2, "bad LayerNorm mode");
+    EC_REQUIRE(tiles_n == 1 && a.glu_nb == 0 && a.act == GEMM_ACT_NONE, "fused LayerNorm needs the whole row in one plain tile (N <= 256)");
+    EC_REQUIRE(a.out_f32 != nullptr && a.ld_out == a.N, "fused LayerNorm normalises the fp32 output in place");
+    EC_REQUIRE(a.ln1_g != nullptr && a.ln1_b != nullptr, "missing LayerNorm parameters");
+    p.ln_mode = a.ln_mode; p.ln1_g = a.ln1_g; p.ln1_b = a.ln1_b; p.ln2_g = a.ln2_g; p.ln2_b = a.ln2_b; p.ln_eps = a.ln_eps;
+    p.ln_out = a.ln_out; p.ld_ln = a.N;
+    p.copy_out = a.copy_out; p.copy_stride = a.copy_stride > 0 ? a.copy_stride : 1;
+    p.frames_per_seq = a.frames_per_seq > 0 ? a.frames_per_seq : a.M; p.frames_out_per_seq = a.frames_out_per_seq;
+    EC_REQUIRE(a.copy_out == nullptr || a.ln_mode == 1, "the strided copy is only available with a single LayerNorm");
+  }
 
   CUtensorMap tmA, tmB;
   EC_TRY(make_operand_map(&tmA, precision, a.A, a.M, a.K, kBlockM));
@@ -260,18 +405,18 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<T, kLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   EC_CUDA(attr_err);
   dim3 grid(cdiv(a.M, kBlockM), tiles_n);
-  gemm_tc_kernel<T><<<grid, 192, smem, stream>>>(tmA, tmB, p);
-  EC_CUDA(cudaGetLastError());
+  EC_TRY(launch_pdl(gemm_tc_kernel<T, kLN>, grid, dim3(192), smem, stream, tmA, tmB, p));
   return EC_OK;
 }
 
 int launch_gemm(int precision, const GemmArgs& a, cudaStream_t stream) {
-  if (precision == EC_PREC_TF32) return launch_gemm_t<float>(precision, a, stream);
-  if (precision == EC_PREC_BF16) return launch_gemm_t<__nv_bfloat16>(precision, a, stream);
+  if (precision == EC_PREC_TF32) return a.ln_mode ? launch_gemm_t<float, true>(precision, a, stream) : launch_gemm_t<float, false>(precision, a, stream);
+  if (precision == EC_PREC_BF16)
+    return a.ln_mode ? launch_gemm_t<__nv_bfloat16, true>(precision, a, stream) : launch_gemm_t<__nv_bfloat16, false>(precision, a, stream);
   EC_FAIL("unknown precision");
 }
 

@@ -41,6 +41,23 @@ def gemm(a_act, w_act, bias, precision, alpha=1.0, act=0, residual=None, want_f3
     return of, oa
 
 
+def gemm_ln(a_act, w_act, bias, precision, g1, b1, g2=None, b2=None, mode=1, alpha=1.0, residual=None, eps=1e-6,
+            copy_stride=0, frames_per_seq=0):
+    """GEMM with the fused LayerNorm epilogue.  Returns (out_f32, ln_out_act, copy_out_act or None)."""
+    pr = _p(precision)
+    M, K = a_act.shape
+    N = w_act.shape[0]
+    of = torch.empty(M, N, dtype=torch.float32, device=a_act.device)
+    ya = torch.empty(M, N, dtype=act_dtype(pr), device=a_act.device)
+    cp, fops = None, 0
+    if copy_stride:
+        fops = (frames_per_seq - 1) // copy_stride + 1
+        cp = torch.zeros((M // frames_per_seq) * fops, N, dtype=act_dtype(pr), device=a_act.device)
+    check(lib().ec_op_gemm_ln(pr, ptr(a_act), ptr(w_act), M, N, K, ptr(bias), alpha, ptr(residual), ptr(of), mode, ptr(g1), ptr(b1),
+                              ptr(g2), ptr(b2), eps, ptr(ya), ptr(cp), copy_stride, frames_per_seq, fops, stream_ptr()))
+    return of, ya, cp
+
+
 def pointwise_glu(a_act, w_raw, b_raw, precision):
     pr = _p(precision)
     M, K = a_act.shape

@@ -109,6 +109,11 @@ const char* ec_profile_category_name(int cat);
 int ec_engine_set_profiling(ec_engine* e, int enabled);
 int ec_engine_last_launches(const ec_engine* e);
 int ec_engine_profile_read(ec_engine* e, double* ms, double* flops, double* bytes, int32_t* launches);
+/* Execution options.  fuse_ln (per engine, default 1): the five LayerNorms of a block run in the epilogue of the producing
+ * GEMM instead of as separate kernels (needs model dims <= 256).  pdl (process wide, default 1, env EFFCONF_PDL=0 disables):
+ * launch every kernel with programmatic stream serialization so its prologue overlaps the predecessor's tail. */
+int ec_engine_set_fuse_ln(ec_engine* e, int enabled);
+int ec_set_pdl(int enabled);
 
 /* CTC head.  logits [B, T, V] fp32, logits_len [B] int64, targets [B, target_stride] int64 (blank = 0), target_len [B] int64.
  * scratch: at least B*T*(sizeof(float)+sizeof(int)) + B*sizeof(int) bytes.  loss_per_utt [B], loss_mean [1] fp32. */
@@ -127,6 +132,13 @@ int ec_op_layernorm(int precision, const float* x, int rows, int dim, const floa
 /* out = alpha * act(A @ W^T + bias) + residual.  A [M,K], W [N,K] in the activation type (use ec_op_cast).  act: 0 none, 1 swish. */
 int ec_op_gemm(int precision, const void* A, const void* W, int M, int N, int K, const float* bias, float alpha, int act,
                const float* residual, float* out_f32, void* out_act, void* stream);
+/* GEMM + fused LayerNorm epilogue (N <= 256): out_f32 = alpha*(A W^T + bias) + residual;
+ * ln_mode 1: ln_out = LN(out; g1,b1) (activation type), optional copy_out = activation-type copy of every copy_stride-th frame of out;
+ * ln_mode 2: out_f32 <- LN(out; g1,b1) in place, ln_out = LN(out_f32; g2,b2), or a plain activation-type copy when g2 == NULL. */
+int ec_op_gemm_ln(int precision, const void* A, const void* W, int M, int N, int K, const float* bias, float alpha,
+                  const float* residual, float* out_f32, int ln_mode, const float* g1, const float* b1, const float* g2,
+                  const float* b2, float eps, void* ln_out, void* copy_out, int copy_stride, int frames_per_seq,
+                  int frames_out_per_seq, void* stream);
 /* pointwise Conv1d(K -> 2*channels) + GLU: out[m, c] = (A w_c + b_c) * sigmoid(A w_{C+c} + b_{C+c}).  w_raw [2C, K], b_raw [2C] fp32
  * (reference layout); w_scratch / b_scratch hold ec_op_glu_scratch_rows(channels) rows of the interleaved copy. */
 int ec_op_pointwise_glu(int precision, const void* A, const float* w_raw, const float* b_raw, int M, int channels, int K,

@@ -206,6 +206,32 @@ def test_full_size_properties(sd):
     assert rel_l2(lg1[idx], ref) < TOL_TF32
 
 
+@pytest.mark.parametrize("fuse_ln,pdl", [(0, 0), (1, 0), (0, 1)])
+def test_execution_options_do_not_change_results(sd, fuse_ln, pdl):
+    """Fused-LayerNorm epilogues and programmatic dependent launch are pure scheduling/fusion options: logits must agree
+    with the default (fused, PDL) path to fp32 round-off and still meet the parity gate against the oracle."""
+    from oracle import conformer_oracle as O
+    from efficientconformer_b200 import _lib
+    mel = synthetic_mel(3, 333, seed=77)
+    mel_len = torch.tensor([333, 200, 77])
+    base = make_model(sd, "tf32")
+    ref_gpu, _, _ = base.forward_mel(mel.to(DEV), mel_len.to(DEV))
+    L = _lib.lib()
+    try:
+        L.ec_set_pdl(pdl)
+        m = make_model(sd, "tf32")
+        m.forward_mel(mel.to(DEV), mel_len.to(DEV))                       # creates the engine
+        eng = m.encoder._engines[_lib.PREC_TF32][0]
+        L.ec_engine_set_fuse_ln(eng, fuse_ln)
+        m.encoder._plans.clear()                                          # drop graphs captured with the old option
+        lg, ol, _ = m.forward_mel(mel.to(DEV), mel_len.to(DEV))
+    finally:
+        L.ec_set_pdl(1)
+    assert rel_l2(lg, ref_gpu) < 2e-5
+    ref, _ = O.model_ctc_forward_mel(sd, P, mel, mel_len)
+    assert rel_l2(lg, ref) < TOL_TF32
+
+
 def test_no_fallback_paths(sd):
     from efficientconformer_b200 import ConformerEncoder
     enc = ConformerEncoder(P)

@@ -70,6 +70,42 @@ def test_gemm_exact_operands(ops, prec, M, N, K):
 
 
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("M,N,K,fps,stride", [(16000, 120, 480, 500, 2), (8000, 168, 168, 250, 2), (4000, 240, 960, 125, 1), (999, 120, 4800, 333, 2),
+                                              (37, 256, 64, 37, 1), (130, 8, 40, 13, 2)])
+def test_gemm_fused_layernorm(ops, prec, M, N, K, fps, stride):
+    if prec == "bf16" and (K * 2) % 16:
+        pytest.skip("bf16 row pitch must be a multiple of 16 bytes")
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = (torch.randn(M, N, generator=g) * 2 + 0.3).to(DEV)
+    g1, b1 = (1 + 0.1 * torch.randn(N, generator=g)).to(DEV), (0.1 * torch.randn(N, generator=g)).to(DEV)
+    g2, b2 = (1 + 0.1 * torch.randn(N, generator=g)).to(DEV), (0.1 * torch.randn(N, generator=g)).to(DEV)
+    aa, ww = ops.cast(a, prec), ops.cast(w, prec)
+    x_ref = 0.5 * (aa.double() @ ww.double().t() + bias.double()) + res.double()
+    ln = lambda x, gg, bb: torch.nn.functional.layer_norm(x, (N,), gg.double(), bb.double(), 1e-6)
+    # mode 1: out = x, ln_out = LN1(x), strided compaction copy of x
+    out, y, cp = ops.gemm_ln(aa, ww, bias, prec, g1, b1, mode=1, alpha=0.5, residual=res, copy_stride=stride, frames_per_seq=fps)
+    tol = 2e-6 if K <= 1024 else 2e-5
+    assert rel_l2(out, x_ref) < tol
+    y_ref = ln(x_ref, g1, b1)
+    assert rel_l2(y.float(), y_ref) < (4e-4 if prec == "tf32" else 4e-3)          # + rounding to the activation type
+    assert rel_l2(y.float(), rnd(prec, y_ref.float().cpu())) < 2e-4 + (0 if prec == "tf32" else 2e-3)
+    sel = x_ref.reshape(M // fps, fps, N)[:, ::stride].reshape(-1, N)
+    assert cp.shape == sel.shape
+    assert rel_l2(cp.float(), sel) < (4e-4 if prec == "tf32" else 4e-3)
+    # mode 2: out = LN1(x) in place, ln_out = LN2(out)
+    out2, y2, _ = ops.gemm_ln(aa, ww, bias, prec, g1, b1, g2, b2, mode=2, alpha=0.5, residual=res)
+    assert rel_l2(out2, y_ref) < 5e-6 + tol
+    assert rel_l2(y2.float(), ln(y_ref, g2, b2)) < (4e-4 if prec == "tf32" else 4e-3)
+    # mode 2 with identity second stage: activation-type copy of the normalised output
+    out3, y3, _ = ops.gemm_ln(aa, ww, bias, prec, g1, b1, None, None, mode=2, alpha=0.5, residual=res)
+    assert torch.equal(out3, out2)
+    assert torch.equal(y3.float().cpu(), rnd(prec, out3.cpu()))
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
 @pytest.mark.parametrize("M,C,K", [(256, 120, 120), (1000, 168, 120), (517, 240, 168), (64, 8, 16), (300, 360, 360)])
 def test_pointwise_glu(ops, prec, M, C, K):
     g = torch.Generator(device="cpu").manual_seed(C + K)
@@ -169,9 +205,10 @@ def _attention_reference(qkv, E, u, v, x_len, H, G):
                                        (2, 2, 120, 4, 3), (1, 64, 168, 4, 1), (2, 65, 240, 4, 1), (1, 700, 168, 4, 1), (2, 17, 360, 8, 3)])
 def test_relpos_attention(ops, prec, B, T, D, H, G):
     g = torch.Generator(device="cpu").manual_seed(T * 3 + D)
-    qkv = torch.randn(B, T, 3 * D, generator=g).to(DEV)
+    # contract: q|k|v and E arrive TF32-rounded (the producing GEMM epilogues round their fp32 output, round_out)
+    qkv = tf32_round(torch.randn(B, T, 3 * D, generator=g)).to(DEV)
     Tp = T + (-T) % G
-    E = torch.randn(2 * Tp - G, D, generator=g).to(DEV)
+    E = tf32_round(torch.randn(2 * Tp - G, D, generator=g)).to(DEV)
     u, v = (0.3 * torch.randn(D, generator=g)).to(DEV), (0.3 * torch.randn(D, generator=g)).to(DEV)
     x_len = torch.tensor([T] + [max(1, (2 * T) // 3)] * (B - 1), device=DEV)
     for xl in (x_len, None):
