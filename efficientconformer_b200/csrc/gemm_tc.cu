@@ -25,6 +25,7 @@ struct GemmDev {
   int M, N, K;
   int block_n;       // UMMA N (multiple of 16, <= 256)
   int num_k_blocks, stages;
+  int pipe_bytes;    // bytes of the operand ring (the fused-LayerNorm row tile aliases it after the mainloop)
   int tmem_cols;
   const float* bias;
   float alpha;
@@ -49,20 +50,6 @@ constexpr int kMaxStages = 8;
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
-// After the call, lane l holds in s[0] the sum over all lanes of s[l] (31 shuffles for 32 values).
-__device__ __forceinline__ void warp_reduce_scatter32(float (&s)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = upper ? s[i] : s[i + off];
-      const float keep = upper ? s[i + off] : s[i];
-      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-}
-
 template <typename T, bool kLN>
 __global__ void __launch_bounds__(192, kLN ? 1 : 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
@@ -75,9 +62,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stage_bytes = kATileBytes + p.block_n * 128;
-  float* staging = reinterpret_cast<float*>(base_ptr + p.stages * stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base_ptr + p.stages * stage_bytes + kStagingBytes);
-  const uint32_t bars_addr = base + p.stages * stage_bytes + kStagingBytes;
+  float* staging = reinterpret_cast<float*>(base_ptr + p.pipe_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base_ptr + p.pipe_bytes + kStagingBytes);
+  const uint32_t bars_addr = base + p.pipe_bytes + kStagingBytes;
   // bars[0..kMaxStages) full, [kMaxStages..2kMaxStages) empty, [2kMaxStages] tmem_full, then the TMEM address holder
   auto full_bar = [&](int s) { return bars_addr + 8u * s; };
   auto empty_bar = [&](int s) { return bars_addr + 8u * (kMaxStages + s); };
@@ -149,11 +136,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row0 = m0 + q * 32;
     const int rows_valid = min(32, p.M - row0);             // may be <= 0 for the tail tile
     T* out_act = reinterpret_cast<T*>(p.out_act);
-    float s1[kLN ? 32 : 1], s2[kLN ? 32 : 1];               // LayerNorm partial sums: lane = column, index = row
-    if constexpr (kLN) {
-#pragma unroll
-      for (int r = 0; r < 32; ++r) { s1[r] = 0.f; s2[r] = 0.f; }
-    }
+    // kLN: the warp's 32 x N fp32 output rows are kept in shared memory (aliasing the drained pipeline stages; odd row
+    // pitch => conflict-free in both the lane = column and the thread = row orientation) until the LayerNorm(s) are done.
+    const int tile_pitch = p.N | 1;
+    float* tile = reinterpret_cast<float*>(base_ptr) + static_cast<size_t>(q) * 32 * tile_pitch;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     for (int c0 = 0; c0 < cols; c0 += 32) {
@@ -203,7 +189,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (has_res) t[r] += rr[r];
         if (p.round_out) t[r] = round_tf32(t[r]);
       }
-      if (n_ok) {
+      if constexpr (kLN) {
+        if (n_ok) {
+#pragma unroll
+          for (int r = 0; r < 32; ++r) tile[r * tile_pitch + n] = t[r];
+        }
+      } else if (n_ok) {
         if (p.out_f32 != nullptr) {
           float* op = p.out_f32 + static_cast<size_t>(row0) * p.ld_out + n;
 #pragma unroll
@@ -215,80 +206,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int r = 0; r < 32; ++r) if (r < rows_valid) op[static_cast<size_t>(r) * p.ld_act] = Tr::to(t[r]);
         }
       }
-      if constexpr (kLN) {
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          const float tv = (n_ok && r < rows_valid) ? t[r] : 0.f;
-          s1[r] += tv; s2[r] = fmaf(tv, tv, s2[r]);
-        }
-      }
     }
     if constexpr (kLN) {
-      // ---- fused LayerNorm(s): this CTA holds every column of its 128 rows.  Row statistics come from the per-lane
-      // partial sums by a reduce-scatter (lane r ends up with row r); the values are re-read from this warp's own
-      // fp32 output (each thread reads back exactly the addresses it wrote), normalised and written once more. ----
+      // ---- fused LayerNorm(s) over the rows this warp owns (every column of a row is in this CTA) ----
       const float inv_n = 1.0f / static_cast<float>(p.N);
-      float mu[32], rs[32];
-      auto finish_stats = [&]() {
-        warp_reduce_scatter32(s1, lane);
-        warp_reduce_scatter32(s2, lane);
-        const float mean = s1[0] * inv_n;
-        const float var = fmaxf(s2[0] * inv_n - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + p.ln_eps);
-#pragma unroll
-        for (int r = 0; r < 32; ++r) { mu[r] = __shfl_sync(0xffffffffu, mean, r); rs[r] = __shfl_sync(0xffffffffu, rstd, r); }
+      float mean, rstd;                                    // of row `lane` (thread = row orientation)
+      auto row_stats = [&]() {                             // two-pass (mean, then centred squares) like nn.LayerNorm
+        __syncwarp();
+        const float* tr = tile + lane * tile_pitch;
+        float s = 0.f;
+        for (int n = 0; n < p.N; ++n) s += tr[n];
+        mean = s * inv_n;
+        float sq = 0.f;
+        for (int n = 0; n < p.N; ++n) { const float dlt = tr[n] - mean; sq = fmaf(dlt, dlt, sq); }
+        rstd = rsqrtf(sq * inv_n + p.ln_eps);
+        __syncwarp();
       };
-      finish_stats();
+      row_stats();
       const float* g_fin = p.ln1_g; const float* b_fin = p.ln1_b;
-      if (p.ln_mode == 2) {
+      if (p.ln_mode == 2) {                                // block norm in place, then the next module's LayerNorm
+        for (int c0 = 0; c0 < p.N; c0 += 32) {
+          const int n = c0 + lane;
+          if (n < p.N) {
+            const float g = __ldg(p.ln1_g + n), b = __ldg(p.ln1_b + n);
 #pragma unroll
-        for (int r = 0; r < 32; ++r) { s1[r] = 0.f; s2[r] = 0.f; }
-        for (int c0 = 0; c0 < cols; c0 += 32) {
-          const int n = out_col0 + c0 + lane;
-          const bool n_ok = (c0 + lane) < cols && n < n_limit;
-          const float g = n_ok ? __ldg(p.ln1_g + n) : 0.f, b = n_ok ? __ldg(p.ln1_b + n) : 0.f;
-          float* op = p.out_f32 + static_cast<size_t>(row0) * p.ld_out + n;
-          float x[32];
-#pragma unroll
-          for (int r = 0; r < 32; ++r) x[r] = (n_ok && r < rows_valid) ? op[static_cast<size_t>(r) * p.ld_out] : 0.f;
-#pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            const float y = (x[r] - mu[r]) * rs[r] * g + b;
-            if (n_ok && r < rows_valid) {
-              op[static_cast<size_t>(r) * p.ld_out] = y;
-              s1[r] += y; s2[r] = fmaf(y, y, s2[r]);
+            for (int r = 0; r < 32; ++r) {
+              const float m_r = __shfl_sync(0xffffffffu, mean, r), rs_r = __shfl_sync(0xffffffffu, rstd, r);
+              tile[r * tile_pitch + n] = (tile[r * tile_pitch + n] - m_r) * rs_r * g + b;
             }
+          } else {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) { __shfl_sync(0xffffffffu, mean, r); __shfl_sync(0xffffffffu, rstd, r); }
           }
         }
         g_fin = p.ln2_g; b_fin = p.ln2_b;
-        if (g_fin != nullptr) finish_stats();
+        if (g_fin != nullptr) row_stats(); else __syncwarp();
       }
-      if (p.ln_out != nullptr || p.copy_out != nullptr) {
-        T* ln_out = reinterpret_cast<T*>(p.ln_out);
-        T* copy_out = reinterpret_cast<T*>(p.copy_out);
-        for (int c0 = 0; c0 < cols; c0 += 32) {
-          const int n = out_col0 + c0 + lane;
-          const bool n_ok = (c0 + lane) < cols && n < n_limit;
-          const float g = (g_fin != nullptr && n_ok) ? __ldg(g_fin + n) : 1.f, b = (g_fin != nullptr && n_ok) ? __ldg(b_fin + n) : 0.f;
-          const float* op = p.out_f32 + static_cast<size_t>(row0) * p.ld_out + n;
-          float x[32];
+      T* ln_out = reinterpret_cast<T*>(p.ln_out);
+      T* copy_out = reinterpret_cast<T*>(p.copy_out);
+      for (int c0 = 0; c0 < p.N; c0 += 32) {
+        const int n = c0 + lane;
+        const bool n_ok = n < p.N;
+        const float g = (g_fin != nullptr && n_ok) ? __ldg(g_fin + n) : 1.f, b = (g_fin != nullptr && n_ok) ? __ldg(b_fin + n) : 0.f;
 #pragma unroll
-          for (int r = 0; r < 32; ++r) x[r] = (n_ok && r < rows_valid) ? op[static_cast<size_t>(r) * p.ld_out] : 0.f;
-          if (n_ok) {
-#pragma unroll
-            for (int r = 0; r < 32; ++r) {
-              if (r < rows_valid) {
-                const int m = row0 + r;
-                if (ln_out != nullptr) {
-                  const float y = g_fin != nullptr ? (x[r] - mu[r]) * rs[r] * g + b : x[r];
-                  ln_out[static_cast<size_t>(m) * p.ld_ln + n] = Tr::to(y);
-                }
-                if (copy_out != nullptr) {
-                  const int seq = m / p.frames_per_seq, tt = m - seq * p.frames_per_seq;
-                  if (tt % p.copy_stride == 0)
-                    copy_out[(static_cast<size_t>(seq) * p.frames_out_per_seq + tt / p.copy_stride) * p.N + n] = Tr::to(x[r]);
-                }
-              }
+        for (int r = 0; r < 32; ++r) {
+          const float m_r = __shfl_sync(0xffffffffu, mean, r), rs_r = __shfl_sync(0xffffffffu, rstd, r);
+          if (n_ok && r < rows_valid) {
+            const int m = row0 + r;
+            const float x = tile[r * tile_pitch + n];
+            p.out_f32[static_cast<size_t>(m) * p.ld_out + n] = x;
+            if (ln_out != nullptr) ln_out[static_cast<size_t>(m) * p.ld_ln + n] = Tr::to(g_fin != nullptr ? (x - m_r) * rs_r * g + b : x);
+            if (copy_out != nullptr) {
+              const int seq = m / p.frames_per_seq, tt = m - seq * p.frames_per_seq;
+              if (tt % p.copy_stride == 0)
+                copy_out[(static_cast<size_t>(seq) * p.frames_out_per_seq + tt / p.copy_stride) * p.N + n] = Tr::to(x);
             }
           }
         }
@@ -401,7 +372,10 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   EC_TRY(make_operand_map(&tmA, precision, a.A, a.M, a.K, kBlockM));
   EC_TRY(make_operand_map(&tmB, precision, a.W, a.N, a.K, p.block_n));
 
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + fixed;
+  size_t pipe_bytes = static_cast<size_t>(stages) * stage_bytes;
+  if (kLN) pipe_bytes = std::max(pipe_bytes, static_cast<size_t>(kBlockM) * (a.N | 1) * sizeof(float));   // row tile aliases the stages
+  p.pipe_bytes = static_cast<int>(pipe_bytes);
+  const size_t smem = pipe_bytes + fixed;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {

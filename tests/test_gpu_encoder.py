@@ -227,9 +227,12 @@ def test_execution_options_do_not_change_results(sd, fuse_ln, pdl):
         lg, ol, _ = m.forward_mel(mel.to(DEV), mel_len.to(DEV))
     finally:
         L.ec_set_pdl(1)
-    assert rel_l2(lg, ref_gpu) < 2e-5
+    # TF32 operand rounding amplifies last-bit differences (a different but equally exact summation order flips some
+    # roundings), so the variants agree to the operand-noise level, not bit-wise; each must meet the parity gate on its own.
+    assert rel_l2(lg, ref_gpu) < TOL_TF32
     ref, _ = O.model_ctc_forward_mel(sd, P, mel, mel_len)
     assert rel_l2(lg, ref) < TOL_TF32
+    assert rel_l2(ref_gpu, ref) < TOL_TF32
 
 
 def test_no_fallback_paths(sd):
