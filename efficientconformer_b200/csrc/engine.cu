@@ -74,9 +74,11 @@ struct ec_engine {
 
 namespace ec {
 
+// GLU tiles are [nb value rows | nb gate rows]; the epilogue stores 32-column slabs, so with more than one tile the
+// tile width must be a multiple of 32 (a single tile is clipped by the tensor bound instead).
 static void pick_glu(int channels, int* nb, int* tiles) {
   *tiles = cdiv(channels, 128);
-  *nb = round_up(cdiv(channels, *tiles), 8);
+  *nb = *tiles == 1 ? round_up(channels, 8) : round_up(cdiv(channels, *tiles), 32);
 }
 
 // Lays the prepared-weights arena out (dry run when arena == nullptr); fills e->w with pointers.

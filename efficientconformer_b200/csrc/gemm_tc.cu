@@ -8,15 +8,17 @@
 // block (reference models/modules.py:386,433,511; models/blocks.py:96,135).
 //
 // One CTA = one 128 x BLOCK_N output tile over the whole K.  Warp roles (192 threads):
-//   warp 0   TMA producer  : cp.async.bulk.tensor loads of the A (128 x 128B) and W (BLOCK_N x 128B) k-slices, 128B swizzle
-//   warp 1   MMA issuer    : allocates TMEM, one thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 32B), fp32 accumulator in TMEM
-//   warps 2-5 epilogue     : tcgen05.ld (thread = output row) -> padded smem transpose -> (lane = output column)
-//                            bias / Swish / GLU / alpha / residual in registers with 32 independent rows in flight ->
-//                            coalesced fp32 / activation-type stores; optional per-row LayerNorm statistics by a
-//                            register reduce-scatter across the warp, then normalise sweeps over the CTA's own output.
+//   warp 0    TMA producer : cp.async.bulk.tensor loads of the A (128 x 128B) and W (BLOCK_N x 128B) k-slices, 128B swizzle
+//   warp 1    MMA issuer   : allocates TMEM, one thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 32B), fp32 accumulator in TMEM
+//   warps 2-5 epilogue     : thread = output row.  Per 32-column chunk: tcgen05.ld -> bias (smem broadcast) / Swish / GLU /
+//                            alpha / residual (TMA-prefetched swizzled slab) in registers -> swizzled smem slab (conflict-free
+//                            16-byte stores) -> TMA bulk tensor store (coalesced, clips the M / N tails).  LayerNorm row
+//                            statistics are per-thread (chunk-wise Chan/Welford merge, no shuffles); the fp32 row tile stays
+//                            in shared memory (aliasing the drained operand ring) for the normalise passes.
 // K and N tails are zero-filled by TMA out-of-bounds handling, so D, 4D, head dims etc. need no host-side padding
 // (only 16-byte row pitches).  Operand type float => kind::tf32, __nv_bfloat16 => kind::f16.
 #include "ec_common.cuh"
+#include <algorithm>
 #include <mutex>
 
 namespace ec {
@@ -25,34 +27,86 @@ struct GemmDev {
   int M, N, K;
   int block_n;       // UMMA N (multiple of 16, <= 256)
   int num_k_blocks, stages;
-  int pipe_bytes;    // bytes of the operand ring (the fused-LayerNorm row tile aliases it after the mainloop)
+  int pipe_bytes;    // operand ring bytes (epilogue staging aliases it after the mainloop)
+  int warp_stage_bytes;
   int tmem_cols;
   const float* bias;
   float alpha;
   int act;
   int glu_nb, glu_channels;
-  const float* residual; int ld_res;
-  float* out_f32; int ld_out;
-  void* out_act; int ld_act;
+  int has_res, has_out_f32, has_out_act;
   int round_out;     // round the fp32 output to TF32 (it feeds a TF32 mma.sync consumer)
   // fused LayerNorm (kLN instantiation only; requires a single N tile)
-  int ln_mode;       // 1: y = LN1(out);  2: out <- LN1(out), y = LN2(out) (LN2 identity when ln2_g == nullptr)
+  int ln_mode;       // 1: y = LN1(out);  2: out <- LN1(out), y = LN2(out) (plain copy when ln2_g == nullptr)
   const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
   float ln_eps;
-  void* ln_out; int ld_ln;                 // y, activation type (may be null)
-  void* copy_out; int copy_stride, frames_per_seq, frames_out_per_seq;   // strided compaction of `out` (LN1 mode), activation type
+  int has_ln_out;
+  void* copy_out; int copy_stride, frames_per_seq, frames_out_per_seq;   // strided compaction of `out` (LN mode 1), activation type
 };
 
 constexpr int kBlockM = 128;
 constexpr int kATileBytes = kBlockM * 128;
-constexpr int kStagingBytes = 4 * 32 * 33 * 4;
+constexpr int kSlabBytes = 4096;             // 32 rows x 128 B
+constexpr int kResRingBytes = 4 * 2 * kSlabBytes;
+constexpr int kVecFloats = 288;              // bias / LayerNorm vectors in smem (256 + one chunk of slack)
+constexpr int kVecBytes = 5 * kVecFloats * 4;
 constexpr int kMaxStages = 8;
+constexpr int kNumBars = 2 * kMaxStages + 1 + 8;
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
+// ---- TMA store / bulk-group helpers -------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// 32 x 32 slab layouts written by thread = row (lane), matching the TMA swizzle modes:
+//   fp32: 128-byte rows, 16-byte chunk j4 in [0,8) XOR (row & 7)          (CU_TENSOR_MAP_SWIZZLE_128B)
+//   bf16:  64-byte rows, 16-byte chunk j8 in [0,4) XOR ((row >> 1) & 3)   (CU_TENSOR_MAP_SWIZZLE_64B)
+__device__ __forceinline__ uint32_t slab_f32_off(int row, int j4) { return row * 128 + ((j4 ^ (row & 7)) << 4); }
+__device__ __forceinline__ uint32_t slab_b16_off(int row, int j8) { return row * 64 + ((j8 ^ ((row >> 1) & 3)) << 4); }
+
+__device__ __forceinline__ void slab_store_f32(uint8_t* slab, int row, const float (&t)[32]) {
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4)
+    *reinterpret_cast<float4*>(slab + slab_f32_off(row, j4)) = make_float4(t[4 * j4], t[4 * j4 + 1], t[4 * j4 + 2], t[4 * j4 + 3]);
+}
+__device__ __forceinline__ void slab_load_f32(const uint8_t* slab, int row, float (&t)[32]) {
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 x = *reinterpret_cast<const float4*>(slab + slab_f32_off(row, j4));
+    t[4 * j4] = x.x; t[4 * j4 + 1] = x.y; t[4 * j4 + 2] = x.z; t[4 * j4 + 3] = x.w;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void slab_store_act(uint8_t* slab, int row, const float (&t)[32]) {
+  if constexpr (sizeof(T) == 4) {
+    float r[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = round_tf32(t[j]);
+    slab_store_f32(slab, row, r);
+  } else {
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+      uint4 pk;
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(t[8 * j8], t[8 * j8 + 1]), h1 = __floats2bfloat162_rn(t[8 * j8 + 2], t[8 * j8 + 3]);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(t[8 * j8 + 4], t[8 * j8 + 5]), h3 = __floats2bfloat162_rn(t[8 * j8 + 6], t[8 * j8 + 7]);
+      pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(slab + slab_b16_off(row, j8)) = pk;
+    }
+  }
+}
+
 template <typename T, bool kLN>
 __global__ void __launch_bounds__(192, kLN ? 1 : 2)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmOutF,
+               const __grid_constant__ CUtensorMap tmOutA, const __grid_constant__ CUtensorMap tmLn, const GemmDev p) {
   using Tr = ActTraits<T>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -62,14 +116,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stage_bytes = kATileBytes + p.block_n * 128;
-  float* staging = reinterpret_cast<float*>(base_ptr + p.pipe_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base_ptr + p.pipe_bytes + kStagingBytes);
-  const uint32_t bars_addr = base + p.pipe_bytes + kStagingBytes;
-  // bars[0..kMaxStages) full, [kMaxStages..2kMaxStages) empty, [2kMaxStages] tmem_full, then the TMEM address holder
+  const int res_bytes = p.has_res ? kResRingBytes : 0;
+  uint8_t* res_ring = base_ptr + p.pipe_bytes;
+  float* vecs = reinterpret_cast<float*>(base_ptr + p.pipe_bytes + res_bytes);          // bias | ln1_g | ln1_b | ln2_g | ln2_b
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base_ptr + p.pipe_bytes + res_bytes + kVecBytes);
+  const uint32_t bars_addr = base + p.pipe_bytes + res_bytes + kVecBytes;
+  // bars: [0,8) full, [8,16) empty, [16] tmem_full, [17,25) residual slots (warp q, slot s -> 17 + 2q + s), then the TMEM address
   auto full_bar = [&](int s) { return bars_addr + 8u * s; };
   auto empty_bar = [&](int s) { return bars_addr + 8u * (kMaxStages + s); };
   const uint32_t tmem_full_bar = bars_addr + 8u * (2 * kMaxStages);
-  volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(bars + 2 * kMaxStages + 1);
+  auto res_bar = [&](int q, int s) { return bars_addr + 8u * (2 * kMaxStages + 1 + 2 * q + s); };
+  volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(bars + kNumBars);
 
   const int m0 = blockIdx.x * kBlockM;
   const int tile_n = blockIdx.y;
@@ -80,6 +137,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(res_bar(i >> 1, i & 1), 1);
     fence_barrier_init();
   }
   if (warp_idx == 1) {
@@ -126,145 +184,198 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_commit(tmem_full_bar);        // accumulator complete
     }
   } else {
-    // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp_idx % 4) ----------------
+    // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp_idx % 4); thread = output row ----------------
     const int q = warp_idx & 3;
-    float* stg = staging + q * (32 * 33);
+    const int et = (warp_idx - 2) * 32 + lane;               // 0..127 among the epilogue threads
     const bool glu = p.glu_nb > 0;
-    const int cols = glu ? p.glu_nb : p.block_n;            // logical output columns of this tile
+    const int cols = glu ? p.glu_nb : p.block_n;             // logical output columns of this tile (multiple of 32 unless last tile)
     const int out_col0 = glu ? tile_n * p.glu_nb : w_row0;
     const int n_limit = glu ? p.glu_channels : p.N;
     const int row0 = m0 + q * 32;
-    const int rows_valid = min(32, p.M - row0);             // may be <= 0 for the tail tile
-    T* out_act = reinterpret_cast<T*>(p.out_act);
-    // kLN: the warp's 32 x N fp32 output rows are kept in shared memory (aliasing the drained pipeline stages; odd row
-    // pitch => conflict-free in both the lane = column and the thread = row orientation) until the LayerNorm(s) are done.
-    const int tile_pitch = p.N | 1;
-    float* tile = reinterpret_cast<float*>(base_ptr) + static_cast<size_t>(q) * 32 * tile_pitch;
+    float* sbias = vecs;
+    float *sg1 = vecs + kVecFloats, *sb1 = vecs + 2 * kVecFloats, *sg2 = vecs + 3 * kVecFloats, *sb2 = vecs + 4 * kVecFloats;
+    // ---- per-column vectors -> smem (zero beyond the valid range) ----
+    for (int i = et; i < kVecFloats; i += 128) {
+      float bv = 0.f;
+      if (p.bias != nullptr) {
+        if (glu) { if (i < 2 * p.glu_nb) bv = __ldg(p.bias + w_row0 + i); }
+        else if (i < p.block_n && out_col0 + i < n_limit) bv = __ldg(p.bias + out_col0 + i);
+      }
+      sbias[i] = bv;
+      if constexpr (kLN) {
+        const bool ok = i < p.N;
+        sg1[i] = ok ? __ldg(p.ln1_g + i) : 0.f; sb1[i] = ok ? __ldg(p.ln1_b + i) : 0.f;
+        sg2[i] = (ok && p.ln2_g != nullptr) ? __ldg(p.ln2_g + i) : 0.f; sb2[i] = (ok && p.ln2_g != nullptr) ? __ldg(p.ln2_b + i) : 0.f;
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");           // epilogue warps only
+    // ---- residual slabs: 2-deep TMA ring per warp ----
+    const int n_chunks = (min(cols, n_limit - out_col0) + 31) / 32;
+    uint8_t* my_res = res_ring + q * 2 * kSlabBytes;
+    auto issue_res = [&](int c) {
+      mbar_arrive_expect_tx(res_bar(q, c & 1), kSlabBytes);
+      tma_load_2d(smem_u32(my_res + (c & 1) * kSlabBytes), &tmRes, res_bar(q, c & 1), out_col0 + c * 32, row0);
+    };
+    if (p.has_res && lane == 0) {
+      issue_res(0);
+      if (n_chunks > 1) issue_res(1);
+    }
+    uint8_t* wstage = base_ptr + q * p.warp_stage_bytes;     // aliases the operand ring: only touched after tmem_full
+    uint8_t* slabA = wstage + (kLN ? n_chunks : 1) * kSlabBytes;
+    float mean = 0.f, m2 = 0.f, cnt = 0.f;                   // running LayerNorm statistics of this thread's row
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    for (int c0 = 0; c0 < cols; c0 += 32) {
-      const int n = out_col0 + c0 + lane;
-      const bool n_ok = (c0 + lane) < cols && n < n_limit;
-      // per-column constants first (their latency hides behind the TMEM load + transpose)
-      float bias_a = 0.f, bias_g = 0.f;
-      if (p.bias != nullptr && n_ok) {
-        if (glu) { bias_a = __ldg(p.bias + w_row0 + c0 + lane); bias_g = __ldg(p.bias + w_row0 + p.glu_nb + c0 + lane); }
-        else bias_a = __ldg(p.bias + n);
-      }
-      float rr[32];
-      const bool has_res = p.residual != nullptr;
-      if (has_res) {
-        const float* rp = p.residual + static_cast<size_t>(row0) * p.ld_res + n;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) rr[r] = (n_ok && r < rows_valid) ? __ldg(rp + static_cast<size_t>(r) * p.ld_res) : 0.f;
-      }
+    for (int c = 0; c < n_chunks; ++c) {
+      const int c0 = c * 32;
       uint32_t v[32];
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
       tmem_ld_32x32(taddr, v);
       tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
-      __syncwarp();
       float t[32];
 #pragma unroll
-      for (int r = 0; r < 32; ++r) t[r] = stg[r * 33 + lane] + bias_a;
-      __syncwarp();
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + 4 * j4);
+        t[4 * j4] = __uint_as_float(v[4 * j4]) + b4.x; t[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b4.y;
+        t[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b4.z; t[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b4.w;
+      }
       if (glu) {
         tmem_ld_32x32(taddr + static_cast<uint32_t>(p.glu_nb), v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
-        __syncwarp();
-#pragma unroll
-        for (int r = 0; r < 32; ++r) t[r] *= fast_sigmoid(stg[r * 33 + lane] + bias_g);
-        __syncwarp();
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sbias + p.glu_nb + c0 + 4 * j4);
+          t[4 * j4] *= fast_sigmoid(__uint_as_float(v[4 * j4]) + b4.x); t[4 * j4 + 1] *= fast_sigmoid(__uint_as_float(v[4 * j4 + 1]) + b4.y);
+          t[4 * j4 + 2] *= fast_sigmoid(__uint_as_float(v[4 * j4 + 2]) + b4.z); t[4 * j4 + 3] *= fast_sigmoid(__uint_as_float(v[4 * j4 + 3]) + b4.w);
+        }
       }
       if (p.act == GEMM_ACT_SWISH) {
 #pragma unroll
-        for (int r = 0; r < 32; ++r) t[r] *= fast_sigmoid(t[r]);
+        for (int j = 0; j < 32; ++j) t[j] *= fast_sigmoid(t[j]);
       }
+      if (p.has_res) {
+        mbar_wait(res_bar(q, c & 1), (c >> 1) & 1);
+        float rr[32];
+        slab_load_f32(my_res + (c & 1) * kSlabBytes, lane, rr);
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        t[r] *= p.alpha;
-        if (has_res) t[r] += rr[r];
-        if (p.round_out) t[r] = round_tf32(t[r]);
+        for (int j = 0; j < 32; ++j) t[j] = fmaf(p.alpha, t[j], rr[j]);
+        __syncwarp();
+        if (lane == 0 && c + 2 < n_chunks) issue_res(c + 2);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) t[j] *= p.alpha;
+      }
+      if (p.round_out) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) t[j] = round_tf32(t[j]);
       }
       if constexpr (kLN) {
-        if (n_ok) {
+        // chunk statistics (two-pass inside the chunk), merged into the running row statistics (Chan et al.)
+        const int nc = min(32, p.N - c0);
+        float cs = 0.f;
 #pragma unroll
-          for (int r = 0; r < 32; ++r) tile[r * tile_pitch + n] = t[r];
+        for (int j = 0; j < 32; ++j) cs += (j < nc) ? t[j] : 0.f;
+        const float cm = cs / static_cast<float>(nc);
+        float cq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { const float dlt = t[j] - cm; cq += (j < nc) ? dlt * dlt : 0.f; }
+        const float tot = cnt + static_cast<float>(nc), dlt = cm - mean;
+        mean += dlt * static_cast<float>(nc) / tot;
+        m2 += cq + dlt * dlt * cnt * static_cast<float>(nc) / tot;
+        cnt = tot;
+        slab_store_f32(wstage + c * kSlabBytes, lane, t);      // row tile stays resident for the normalise passes
+        if (p.ln_mode == 1) {                                  // x itself is an output: store it now
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) { tma_store_2d(&tmOutF, smem_u32(wstage + c * kSlabBytes), c0, row0); bulk_commit(); }
         }
-      } else if (n_ok) {
-        if (p.out_f32 != nullptr) {
-          float* op = p.out_f32 + static_cast<size_t>(row0) * p.ld_out + n;
-#pragma unroll
-          for (int r = 0; r < 32; ++r) if (r < rows_valid) op[static_cast<size_t>(r) * p.ld_out] = t[r];
-        }
-        if (out_act != nullptr) {
-          T* op = out_act + static_cast<size_t>(row0) * p.ld_act + n;
-#pragma unroll
-          for (int r = 0; r < 32; ++r) if (r < rows_valid) op[static_cast<size_t>(r) * p.ld_act] = Tr::to(t[r]);
+      } else {
+        if (c > 0) { if (lane == 0) bulk_wait_read0(); __syncwarp(); }   // the previous chunk's stores have drained the slabs
+        if (p.has_out_f32) slab_store_f32(wstage, lane, t);
+        if (p.has_out_act) slab_store_act<T>(slabA, lane, t);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.has_out_f32) tma_store_2d(&tmOutF, smem_u32(wstage), out_col0 + c0, row0);
+          if (p.has_out_act) tma_store_2d(&tmOutA, smem_u32(slabA), out_col0 + c0, row0);
+          bulk_commit();
         }
       }
     }
     if constexpr (kLN) {
-      // ---- fused LayerNorm(s) over the rows this warp owns (every column of a row is in this CTA) ----
       const float inv_n = 1.0f / static_cast<float>(p.N);
-      float mean, rstd;                                    // of row `lane` (thread = row orientation)
-      auto row_stats = [&]() {                             // two-pass (mean, then centred squares) like nn.LayerNorm
-        __syncwarp();
-        const float* tr = tile + lane * tile_pitch;
-        float s = 0.f;
-        for (int n = 0; n < p.N; ++n) s += tr[n];
-        mean = s * inv_n;
-        float sq = 0.f;
-        for (int n = 0; n < p.N; ++n) { const float dlt = tr[n] - mean; sq = fmaf(dlt, dlt, sq); }
-        rstd = rsqrtf(sq * inv_n + p.ln_eps);
-        __syncwarp();
-      };
-      row_stats();
-      const float* g_fin = p.ln1_g; const float* b_fin = p.ln1_b;
-      if (p.ln_mode == 2) {                                // block norm in place, then the next module's LayerNorm
-        for (int c0 = 0; c0 < p.N; c0 += 32) {
-          const int n = c0 + lane;
-          if (n < p.N) {
-            const float g = __ldg(p.ln1_g + n), b = __ldg(p.ln1_b + n);
+      float rstd = rsqrtf(m2 * inv_n + p.ln_eps);
+      const float* gfin = sg1; const float* bfin = sb1;
+      bool affine = true;
+      if (p.ln_mode == 2) {            // block norm in place (fp32 output), then the next module's LayerNorm on top of it
+        float mean2 = 0.f, m22 = 0.f, cnt2 = 0.f;
+        for (int c = 0; c < n_chunks; ++c) {
+          const int c0 = c * 32, nc = min(32, p.N - c0);
+          float t[32];
+          slab_load_f32(wstage + c * kSlabBytes, lane, t);
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-              const float m_r = __shfl_sync(0xffffffffu, mean, r), rs_r = __shfl_sync(0xffffffffu, rstd, r);
-              tile[r * tile_pitch + n] = (tile[r * tile_pitch + n] - m_r) * rs_r * g + b;
-            }
-          } else {
-#pragma unroll
-            for (int r = 0; r < 32; ++r) { __shfl_sync(0xffffffffu, mean, r); __shfl_sync(0xffffffffu, rstd, r); }
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 g4 = *reinterpret_cast<const float4*>(sg1 + c0 + 4 * j4), b4 = *reinterpret_cast<const float4*>(sb1 + c0 + 4 * j4);
+            t[4 * j4] = (t[4 * j4] - mean) * rstd * g4.x + b4.x; t[4 * j4 + 1] = (t[4 * j4 + 1] - mean) * rstd * g4.y + b4.y;
+            t[4 * j4 + 2] = (t[4 * j4 + 2] - mean) * rstd * g4.z + b4.z; t[4 * j4 + 3] = (t[4 * j4 + 3] - mean) * rstd * g4.w + b4.w;
           }
-        }
-        g_fin = p.ln2_g; b_fin = p.ln2_b;
-        if (g_fin != nullptr) row_stats(); else __syncwarp();
-      }
-      T* ln_out = reinterpret_cast<T*>(p.ln_out);
-      T* copy_out = reinterpret_cast<T*>(p.copy_out);
-      for (int c0 = 0; c0 < p.N; c0 += 32) {
-        const int n = c0 + lane;
-        const bool n_ok = n < p.N;
-        const float g = (g_fin != nullptr && n_ok) ? __ldg(g_fin + n) : 1.f, b = (g_fin != nullptr && n_ok) ? __ldg(b_fin + n) : 0.f;
+          float cs = 0.f;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          const float m_r = __shfl_sync(0xffffffffu, mean, r), rs_r = __shfl_sync(0xffffffffu, rstd, r);
-          if (n_ok && r < rows_valid) {
-            const int m = row0 + r;
-            const float x = tile[r * tile_pitch + n];
-            p.out_f32[static_cast<size_t>(m) * p.ld_out + n] = x;
-            if (ln_out != nullptr) ln_out[static_cast<size_t>(m) * p.ld_ln + n] = Tr::to(g_fin != nullptr ? (x - m_r) * rs_r * g + b : x);
-            if (copy_out != nullptr) {
-              const int seq = m / p.frames_per_seq, tt = m - seq * p.frames_per_seq;
-              if (tt % p.copy_stride == 0)
-                copy_out[(static_cast<size_t>(seq) * p.frames_out_per_seq + tt / p.copy_stride) * p.N + n] = Tr::to(x);
+          for (int j = 0; j < 32; ++j) cs += (j < nc) ? t[j] : 0.f;
+          const float cm = cs / static_cast<float>(nc);
+          float cq = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const float dlt = t[j] - cm; cq += (j < nc) ? dlt * dlt : 0.f; }
+          const float tot = cnt2 + static_cast<float>(nc), dlt = cm - mean2;
+          mean2 += dlt * static_cast<float>(nc) / tot;
+          m22 += cq + dlt * dlt * cnt2 * static_cast<float>(nc) / tot;
+          cnt2 = tot;
+          slab_store_f32(wstage + c * kSlabBytes, lane, t);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) { tma_store_2d(&tmOutF, smem_u32(wstage + c * kSlabBytes), c0, row0); bulk_commit(); }
+        }
+        mean = mean2; rstd = rsqrtf(m22 * inv_n + p.ln_eps);
+        gfin = sg2; bfin = sb2;
+        affine = p.ln2_g != nullptr;
+      }
+      const bool do_copy = p.copy_out != nullptr;
+      T* copy_row = nullptr;
+      if (do_copy) {
+        const int m = row0 + lane;
+        if (m < p.M) {
+          const int seq = m / p.frames_per_seq, tt = m - seq * p.frames_per_seq;
+          if (tt % p.copy_stride == 0)
+            copy_row = reinterpret_cast<T*>(p.copy_out) + (static_cast<size_t>(seq) * p.frames_out_per_seq + tt / p.copy_stride) * p.N;
+        }
+      }
+      if (p.has_ln_out || do_copy) {
+        for (int c = 0; c < n_chunks; ++c) {
+          const int c0 = c * 32, nc = min(32, p.N - c0);
+          float t[32];
+          slab_load_f32(wstage + c * kSlabBytes, lane, t);
+          if (copy_row != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < nc) copy_row[c0 + j] = Tr::to(t[j]);
+          }
+          if (p.has_ln_out) {
+            if (affine) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 g4 = *reinterpret_cast<const float4*>(gfin + c0 + 4 * j4), b4 = *reinterpret_cast<const float4*>(bfin + c0 + 4 * j4);
+                t[4 * j4] = (t[4 * j4] - mean) * rstd * g4.x + b4.x; t[4 * j4 + 1] = (t[4 * j4 + 1] - mean) * rstd * g4.y + b4.y;
+                t[4 * j4 + 2] = (t[4 * j4 + 2] - mean) * rstd * g4.z + b4.z; t[4 * j4 + 3] = (t[4 * j4 + 3] - mean) * rstd * g4.w + b4.w;
+              }
             }
+            if (c > 0) { if (lane == 0) bulk_wait_read0(); __syncwarp(); }
+            slab_store_act<T>(slabA, lane, t);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&tmLn, smem_u32(slabA), c0, row0); bulk_commit(); }
           }
         }
       }
     }
+    if (lane == 0) bulk_wait_all0();     // all bulk stores of this warp have completed before the CTA retires
   }
   tc_fence_before();
   __syncthreads();
@@ -291,28 +402,40 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2D K-major operand [rows, K] -> tensor map with a (128-byte x box_rows) box and 128B swizzle.
-static int make_operand_map(CUtensorMap* map, int precision, const void* ptr, int rows, int K, int box_rows) {
+// 2D row-major tensor [rows, cols] of `esize`-byte elements -> tensor map with a (box_cols x box_rows) box.
+static int make_map(CUtensorMap* map, bool is_f32, const void* ptr, int rows, int cols, int ld, int box_cols, int box_rows,
+                    CUtensorMapSwizzle swz) {
   EncodeTiledFn enc = get_encode_fn();
   EC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
-  const int esize = precision == EC_PREC_TF32 ? 4 : 2;
-  const size_t pitch = static_cast<size_t>(K) * esize;
-  EC_REQUIRE(pitch % 16 == 0, "GEMM operand row pitch (K * element size) must be a multiple of 16 bytes");
-  EC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "GEMM operand must be 16-byte aligned");
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  const int esize = is_f32 ? 4 : 2;
+  const size_t pitch = static_cast<size_t>(ld) * esize;
+  EC_REQUIRE(pitch % 16 == 0, "tensor row pitch must be a multiple of 16 bytes for TMA (got " + std::to_string(pitch) + ")");
+  EC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "tensor base must be 16-byte aligned for TMA");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch)};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esize), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, precision == EC_PREC_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   EC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
   return EC_OK;
 }
+// K-major GEMM operand [rows, K]: (128-byte x box_rows) box, 128B swizzle.
+static int make_operand_map(CUtensorMap* map, int precision, const void* ptr, int rows, int K, int box_rows) {
+  const bool f32 = precision == EC_PREC_TF32;
+  return make_map(map, f32, ptr, rows, K, K, f32 ? 32 : 64, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+// 32 x 32 epilogue slab of an [M, cols] output / residual tensor.
+static int make_slab_map(CUtensorMap* map, bool is_f32, const void* ptr, int rows, int cols, int ld) {
+  return make_map(map, is_f32, ptr, rows, cols, ld, 32, 32, is_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+}
 
+// Output tiles are stored in 32-column slabs, so tile boundaries inside a row must be multiples of 32.
 static int pick_block_n(int N) {
+  if (N <= 256) return round_up(N, 16);
   const int tiles = cdiv(N, 256);
-  return round_up(cdiv(N, tiles), 16);
+  return std::min(256, round_up(cdiv(N, tiles), 32));
 }
 
 template <typename T, bool kLN>
@@ -322,18 +445,23 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   GemmDev p{};
   p.M = a.M; p.N = a.N; p.K = a.K;
   int tiles_n;
+  const int out_cols = a.glu_nb > 0 ? a.glu_channels : a.N;
   if (a.glu_nb > 0) {
     EC_REQUIRE(a.glu_nb % 8 == 0 && 2 * a.glu_nb <= 256 && (2 * a.glu_nb) % 16 == 0, "invalid GLU tile width");
     p.block_n = 2 * a.glu_nb;
     EC_REQUIRE(a.N % p.block_n == 0, "GLU weight rows must be a whole number of tiles");
     tiles_n = a.N / p.block_n;
+    EC_REQUIRE(tiles_n == 1 || a.glu_nb % 32 == 0, "multi-tile GLU needs a tile width that is a multiple of 32");
   } else {
     p.block_n = pick_block_n(a.N);
     tiles_n = cdiv(a.N, p.block_n);
   }
   p.num_k_blocks = cdiv(a.K, Tr::kBlockK);
+  p.has_res = a.residual != nullptr; p.has_out_f32 = a.out_f32 != nullptr; p.has_out_act = a.out_act != nullptr;
   const int stage_bytes = kATileBytes + p.block_n * 128;
-  const int fixed = kStagingBytes + (2 * kMaxStages + 2) * 8 + 1024;
+  const int n_chunks = cdiv(std::min(a.glu_nb > 0 ? a.glu_nb : p.block_n, out_cols), 32);
+  p.warp_stage_bytes = (kLN ? n_chunks + 1 : 2) * kSlabBytes;
+  const int fixed = (p.has_res ? kResRingBytes : 0) + kVecBytes + kNumBars * 8 + 16 + 1024;
   // up to 148 CTAs: one CTA per SM anyway -> deep ring (hides the TMA->MMA->refill round trip); otherwise 2 CTAs per SM
   const int ctas = cdiv(a.M, kBlockM) * tiles_n;
   const int budget = (ctas <= 148 || kLN) ? 208 * 1024 : 113 * 1024;
@@ -350,32 +478,36 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   p.tmem_cols = cols;
   p.bias = a.bias; p.alpha = a.alpha; p.act = a.act;
   p.glu_nb = a.glu_nb; p.glu_channels = a.glu_channels;
-  p.residual = a.residual; p.ld_res = a.ld_res;
-  p.out_f32 = a.out_f32; p.ld_out = a.ld_out;
-  p.out_act = a.out_act; p.ld_act = a.ld_act;
   p.round_out = a.round_out;
   EC_REQUIRE(a.out_f32 != nullptr || a.out_act != nullptr, "GEMM needs at least one output");
   EC_REQUIRE(a.glu_nb == 0 || a.bias != nullptr, "GLU GEMM needs a bias");
+  EC_REQUIRE(a.residual == nullptr || a.ld_res == out_cols, "residual must be dense [M, N]");
   if (kLN) {
     EC_REQUIRE(a.ln_mode == 1 || a.ln_mode == 2, "bad LayerNorm mode");
-    EC_REQUIRE(tiles_n == 1 && a.glu_nb == 0 && a.act == GEMM_ACT_NONE, "fused LayerNorm needs the whole row in one plain tile (N <= 256)");
-    EC_REQUIRE(a.out_f32 != nullptr && a.ld_out == a.N, "fused LayerNorm normalises the fp32 output in place");
+    EC_REQUIRE(tiles_n == 1 && a.glu_nb == 0 && a.act == GEMM_ACT_NONE && a.N <= 256, "fused LayerNorm needs the whole row in one plain tile (N <= 256)");
+    EC_REQUIRE(a.out_f32 != nullptr && a.ld_out == a.N && a.out_act == nullptr, "fused LayerNorm writes the fp32 output and ln_out only");
     EC_REQUIRE(a.ln1_g != nullptr && a.ln1_b != nullptr, "missing LayerNorm parameters");
     p.ln_mode = a.ln_mode; p.ln1_g = a.ln1_g; p.ln1_b = a.ln1_b; p.ln2_g = a.ln2_g; p.ln2_b = a.ln2_b; p.ln_eps = a.ln_eps;
-    p.ln_out = a.ln_out; p.ld_ln = a.N;
+    p.has_ln_out = a.ln_out != nullptr;
     p.copy_out = a.copy_out; p.copy_stride = a.copy_stride > 0 ? a.copy_stride : 1;
     p.frames_per_seq = a.frames_per_seq > 0 ? a.frames_per_seq : a.M; p.frames_out_per_seq = a.frames_out_per_seq;
     EC_REQUIRE(a.copy_out == nullptr || a.ln_mode == 1, "the strided copy is only available with a single LayerNorm");
   }
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmRes, tmOutF, tmOutA, tmLn;
   EC_TRY(make_operand_map(&tmA, precision, a.A, a.M, a.K, kBlockM));
   EC_TRY(make_operand_map(&tmB, precision, a.W, a.N, a.K, p.block_n));
+  const bool act_f32 = precision == EC_PREC_TF32;
+  tmRes = tmA; tmOutF = tmA; tmOutA = tmA; tmLn = tmA;       // placeholders for unused maps
+  if (a.residual != nullptr) EC_TRY(make_slab_map(&tmRes, true, a.residual, a.M, out_cols, a.ld_res));
+  if (a.out_f32 != nullptr) EC_TRY(make_slab_map(&tmOutF, true, a.out_f32, a.M, out_cols, a.ld_out));
+  if (a.out_act != nullptr) EC_TRY(make_slab_map(&tmOutA, act_f32, a.out_act, a.M, out_cols, a.ld_act));
+  if (kLN && a.ln_out != nullptr) EC_TRY(make_slab_map(&tmLn, act_f32, a.ln_out, a.M, a.N, a.N));
 
-  size_t pipe_bytes = static_cast<size_t>(stages) * stage_bytes;
-  if (kLN) pipe_bytes = std::max(pipe_bytes, static_cast<size_t>(kBlockM) * (a.N | 1) * sizeof(float));   // row tile aliases the stages
+  size_t pipe_bytes = std::max(static_cast<size_t>(stages) * stage_bytes, static_cast<size_t>(4) * p.warp_stage_bytes);
   p.pipe_bytes = static_cast<int>(pipe_bytes);
   const size_t smem = pipe_bytes + fixed;
+  EC_REQUIRE(smem <= 227 * 1024, "GEMM tile does not fit in shared memory");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -383,7 +515,7 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   });
   EC_CUDA(attr_err);
   dim3 grid(cdiv(a.M, kBlockM), tiles_n);
-  EC_TRY(launch_pdl(gemm_tc_kernel<T, kLN>, grid, dim3(192), smem, stream, tmA, tmB, p));
+  EC_TRY(launch_pdl(gemm_tc_kernel<T, kLN>, grid, dim3(192), smem, stream, tmA, tmB, tmRes, tmOutF, tmOutA, tmLn, p));
   return EC_OK;
 }
 
