@@ -318,10 +318,11 @@ static int launch_attn_t(const AttnDev& p, cudaStream_t stream) {
 }
 
 int launch_relpos_attention(int precision, const AttnArgs& a, cudaStream_t stream) {
+  if (precision == EC_PREC_BF16) return launch_relpos_attention_bf16(a, stream);
   EC_REQUIRE(a.G >= 1 && a.G % 2 == 1, "attention group size must be odd");
   EC_REQUIRE((a.G * a.D) % a.H == 0, "G*D must be divisible by H");
   AttnDev p{};
-  p.qkv = a.qkv; p.E = a.E; p.u = a.u; p.v = a.v; p.x_len = a.x_len;
+  p.qkv = reinterpret_cast<const float*>(a.qkv); p.E = reinterpret_cast<const float*>(a.E); p.u = a.u; p.v = a.v; p.x_len = a.x_len;
   p.B = a.B; p.T = a.T; p.D = a.D; p.H = a.H; p.G = a.G;
   p.d = (a.G * a.D) / a.H;
   const int P = (a.G - a.T % a.G) % a.G;
@@ -329,7 +330,7 @@ int launch_relpos_attention(int precision, const AttnArgs& a, cudaStream_t strea
   p.out = a.out; p.ld_out = a.ld_out;
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(p.d));
   if (precision == EC_PREC_TF32) return launch_attn_t<float>(p, stream);
-  if (precision == EC_PREC_BF16) return launch_attn_t<__nv_bfloat16>(p, stream);
+  if (precision == EC_PREC_BF16) return launch_relpos_attention_bf16(a, stream);     // bf16 q|k|v / E, bf16 tensor-core path
   EC_FAIL("unknown precision");
 }
 

@@ -91,6 +91,84 @@ __global__ void __launch_bounds__(256) ctc_alpha_kernel(const float* __restrict_
   }
 }
 
+// Warp-per-utterance variant for 2U+1 <= 32*kCtcNS: every lane keeps kCtcNS consecutive extended-label states in
+// registers, neighbours s-1 / s-2 come from the lane's own registers or two shuffles, the emission log-probs of the next
+// frame are prefetched while the current frame is combined; no block-level barrier in the T-step recursion.
+__device__ __forceinline__ float lse3_fast(float a, float b, float c) {
+  const float m = fmaxf(a, fmaxf(b, c));
+  if (m == -INFINITY) return -INFINITY;
+  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+}
+template <int kCtcNS>
+__global__ void __launch_bounds__(32) ctc_alpha_warp_kernel(const float* __restrict__ logits, const float* __restrict__ lse, int T, int V,
+                                                            const int* __restrict__ logits_len, const long long* __restrict__ targets,
+                                                            int target_stride, const long long* __restrict__ target_len,
+                                                            float* __restrict__ loss_per_utt) {
+  grid_dependency_wait();
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int U = static_cast<int>(target_len[b]);
+  const int S = 2 * U + 1;
+  int Tb = logits_len[b];
+  if (Tb > T) Tb = T;
+  if (Tb <= 0) { if (lane == 0) loss_per_utt[b] = INFINITY; return; }
+  const long long* y = targets + static_cast<size_t>(b) * target_stride;
+  int ext[kCtcNS]; bool skip[kCtcNS];
+#pragma unroll
+  for (int k = 0; k < kCtcNS; ++k) {
+    const int s = lane * kCtcNS + k;
+    ext[k] = (s < S && (s & 1)) ? static_cast<int>(y[s >> 1]) : 0;
+    const int e2 = (s >= 2 && s < S && (s & 1)) ? static_cast<int>(y[(s - 2) >> 1]) : 0;
+    skip[k] = s >= 2 && s < S && ext[k] != 0 && ext[k] != e2;
+  }
+  const float* lg = logits + static_cast<size_t>(b) * T * V;
+  const float* ls = lse + static_cast<size_t>(b) * T;
+  float a[kCtcNS], nxt[kCtcNS];
+#pragma unroll
+  for (int k = 0; k < kCtcNS; ++k) {
+    const int s = lane * kCtcNS + k;
+    a[k] = s < 2 && s < S ? lg[ext[k]] - ls[0] : -INFINITY;
+  }
+  if (Tb > 1) {
+#pragma unroll
+    for (int k = 0; k < kCtcNS; ++k) nxt[k] = lg[static_cast<size_t>(V) + ext[k]] - ls[1];
+  }
+  for (int t = 1; t < Tb; ++t) {
+    float cur[kCtcNS];
+#pragma unroll
+    for (int k = 0; k < kCtcNS; ++k) cur[k] = nxt[k];
+    if (t + 1 < Tb) {
+      const float* lgt = lg + static_cast<size_t>(t + 1) * V;
+      const float l1 = ls[t + 1];
+#pragma unroll
+      for (int k = 0; k < kCtcNS; ++k) nxt[k] = lgt[ext[k]] - l1;
+    }
+    // previous lane's last two states
+    float pm1 = __shfl_up_sync(0xffffffffu, a[kCtcNS - 1], 1), pm2 = __shfl_up_sync(0xffffffffu, a[kCtcNS - 2], 1);
+    if (lane == 0) { pm1 = -INFINITY; pm2 = -INFINITY; }
+    float na[kCtcNS];
+#pragma unroll
+    for (int k = 0; k < kCtcNS; ++k) {
+      const float x1 = k >= 1 ? a[k - 1] : pm1;
+      const float x2 = skip[k] ? (k >= 2 ? a[k - 2] : (k == 1 ? pm1 : pm2)) : -INFINITY;
+      const float acc = lse3_fast(a[k], x1, x2);
+      na[k] = (acc == -INFINITY || lane * kCtcNS + k >= S) ? -INFINITY : acc + cur[k];
+    }
+#pragma unroll
+    for (int k = 0; k < kCtcNS; ++k) a[k] = na[k];
+  }
+  // read-out: states S-1 and S-2
+  float e1 = -INFINITY, e2 = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < kCtcNS; ++k) {
+    const int s = lane * kCtcNS + k;
+    if (s == S - 1) e1 = a[k];
+    if (s == S - 2) e2 = a[k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { e1 = fmaxf(e1, __shfl_xor_sync(0xffffffffu, e1, o)); e2 = fmaxf(e2, __shfl_xor_sync(0xffffffffu, e2, o)); }
+  if (lane == 0) loss_per_utt[b] = -lse3(e1, e2, -INFINITY);
+}
+
 __global__ void mean_kernel(const float* x, int n, float* out) {
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += 32) s += x[i];
@@ -104,7 +182,16 @@ int launch_ctc_loss(const float* logits, const float* lse, int B, int T, int V, 
   EC_REQUIRE(B > 0 && target_stride >= 0, "bad CTC shapes");
   const size_t smem = sizeof(float) * 3 * (2 * static_cast<size_t>(target_stride) + 1);
   EC_REQUIRE(smem <= 48 * 1024, "CTC target too long for the shared-memory alpha buffers");
-  ctc_alpha_kernel<<<B, 256, smem, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, loss_per_utt);
+  const int s_max = 2 * target_stride + 1;
+  if (s_max <= 64) {
+    ctc_alpha_warp_kernel<2><<<B, 32, 0, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, loss_per_utt);
+  } else if (s_max <= 128) {
+    ctc_alpha_warp_kernel<4><<<B, 32, 0, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, loss_per_utt);
+  } else if (s_max <= 256) {
+    ctc_alpha_warp_kernel<8><<<B, 32, 0, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, loss_per_utt);
+  } else {
+    ctc_alpha_kernel<<<B, 256, smem, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, loss_per_utt);
+  }
   EC_CUDA(cudaGetLastError());
   if (loss_mean != nullptr) {
     mean_kernel<<<1, 32, 0, stream>>>(loss_per_utt, B, loss_mean);

@@ -93,6 +93,7 @@ struct GemmArgs {
   void* copy_out; int copy_stride, frames_per_seq, frames_out_per_seq;
 };
 int launch_gemm(int precision, const GemmArgs& a, cudaStream_t stream);
+int gemm_timeline(int enable, unsigned long long* out12);
 
 struct LayerNormArgs {
   const float* x; int rows, dim;
@@ -104,14 +105,15 @@ struct LayerNormArgs {
 int launch_layernorm(int precision, const LayerNormArgs& a, cudaStream_t stream);
 
 struct AttnArgs {
-  const float* qkv;      // [B*T, 3D] fp32: q | k | v (biases already added)
-  const float* E;        // [2*Tp - G, D] fp32 projected relative sinusoid rows
+  const void* qkv;       // [B*T, 3D] q | k | v (biases already added): fp32 TF32-rounded (EC_PREC_TF32) or bf16 (EC_PREC_BF16)
+  const void* E;         // [2*Tp - G, D] projected relative sinusoid rows, same type as qkv
   const float* u; const float* v;   // [D]
   const int* x_len;      // [B] valid frames at this stage, or nullptr
   int B, T, D, H, G;
   void* out; int ld_out; // [B*T, D] activation type
 };
 int launch_relpos_attention(int precision, const AttnArgs& a, cudaStream_t stream);
+int launch_relpos_attention_bf16(const AttnArgs& a, cudaStream_t stream);
 
 struct DwConvArgs {
   const void* x;         // [B, T, C] activation type (GLU output)

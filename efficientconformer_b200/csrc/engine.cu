@@ -416,10 +416,12 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
     std::swap(x, x_alt);
     // MHSA: x2 = x1 + Wo attn(LN(x1))                   [fused: epilogue emits xn = LN_conv(x2) and the strided copy xs]
     if (!fuse) EC_TRY(lnorm(e, st, x, M, D, b.att_ln_w, b.att_ln_b, ws.xn, nullptr));
-    EC_TRY(gemm(e, st, PC_QKV, ws.xn, b.wqkv, M, 3 * D, D, b.bqkv, 1.f, GEMM_ACT_NONE, nullptr, ws.qkv, nullptr, 0, 0, nullptr, 1));
+    // q|k|v and E feed the attention kernel: TF32-rounded fp32 in parity mode, bf16 in fast mode
+    const bool a16 = prec == EC_PREC_BF16;
+    EC_TRY(gemm(e, st, PC_QKV, ws.xn, b.wqkv, M, 3 * D, D, b.bqkv, 1.f, GEMM_ACT_NONE, nullptr, a16 ? nullptr : ws.qkv, a16 ? ws.qkv : nullptr, 0, 0, nullptr, 1));
     const int G = bc.group_size, P = (G - T % G) % G, e_rows = 2 * (T + P) - G;
     EC_REQUIRE(relpos[i] != nullptr, "missing relative position table");
-    EC_TRY(gemm(e, st, PC_POS, relpos[i], b.wpos, e_rows, D, D, b.bpos, 1.f, GEMM_ACT_NONE, nullptr, ws.ebuf, nullptr, 0, 0, nullptr, 1));
+    EC_TRY(gemm(e, st, PC_POS, relpos[i], b.wpos, e_rows, D, D, b.bpos, 1.f, GEMM_ACT_NONE, nullptr, a16 ? nullptr : ws.ebuf, a16 ? ws.ebuf : nullptr, 0, 0, nullptr, 1));
     {
       AttnArgs aa{ws.qkv, ws.ebuf, b.u, b.v, lens, B, T, D, bc.num_heads, G, ws.o, D};
       const double Tg = static_cast<double>(T + P) / G, dh = static_cast<double>(G) * D / bc.num_heads;
@@ -488,6 +490,7 @@ const char* ec_profile_category_name(int cat) { return (cat >= 0 && cat < PC_COU
 int ec_engine_set_profiling(ec_engine* e, int enabled) { e->prof_enabled = enabled != 0; return EC_OK; }
 /* option 0: fuse LayerNorm into the GEMM epilogues (default 1).  Global option via ec_set_pdl: programmatic dependent launch. */
 int ec_engine_set_fuse_ln(ec_engine* e, int enabled) { e->fuse_ln = enabled != 0; return EC_OK; }
+int ec_debug_gemm_timeline(int enable, unsigned long long* out12) { return gemm_timeline(enable, out12); }
 int ec_set_pdl(int enabled) { g_pdl = enabled != 0 ? 1 : 0; return EC_OK; }
 int ec_engine_last_launches(const ec_engine* e) { return e->last_launches; }
 /* sums the CUDA-event durations of the last (eager, profiled) forward per category; synchronises the recorded events */
@@ -576,7 +579,7 @@ int ec_op_fold_bn(const float* w, const float* b, const float* g, const float* b
                   int taps, float* w_out, float* b_out, void* stream) {
   return launch_fold_bn(w, b, g, beta, rm, rv, eps, C, taps, w_out, b_out, reinterpret_cast<cudaStream_t>(stream));
 }
-int ec_op_relpos_attention(int precision, const float* qkv, const float* E, const float* u, const float* v, const int32_t* x_len,
+int ec_op_relpos_attention(int precision, const void* qkv, const void* E, const float* u, const float* v, const int32_t* x_len,
                            int batch, int t, int dim, int heads, int group, void* out, void* stream) {
   AttnArgs a{qkv, E, u, v, x_len, batch, t, dim, heads, group, out, dim};
   return launch_relpos_attention(precision, a, reinterpret_cast<cudaStream_t>(stream));

@@ -41,8 +41,16 @@ struct GemmDev {
   const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
   float ln_eps;
   int has_ln_out;
+  int dbg;
   void* copy_out; int copy_stride, frames_per_seq, frames_out_per_seq;   // strided compaction of `out` (LN mode 1), activation type
 };
+
+// Optional in-kernel timeline (SM clock stamps of CTA (0,0)), enabled through ec_debug_gemm_timeline for latency studies.
+__device__ unsigned long long g_gemm_timeline[16];
+static int g_timeline_enabled = 0;
+__device__ __forceinline__ void stamp(int enabled, int slot) {
+  if (enabled && blockIdx.x == 0 && blockIdx.y == 0) g_gemm_timeline[slot] = clock64();
+}
 
 constexpr int kBlockM = 128;
 constexpr int kATileBytes = kBlockM * 128;
@@ -128,6 +136,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto res_bar = [&](int q, int s) { return bars_addr + 8u * (2 * kMaxStages + 1 + 2 * q + s); };
   volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(bars + kNumBars);
 
+  if (threadIdx.x == 0) stamp(p.dbg, 0);
   const int m0 = blockIdx.x * kBlockM;
   const int tile_n = blockIdx.y;
   const int w_row0 = tile_n * p.block_n;   // first W row (and, for plain GEMMs, first output column) of this tile
@@ -147,9 +156,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  if (threadIdx.x == 0) stamp(p.dbg, 1);
   // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on we read its output.
   grid_dependency_wait();
   grid_launch_dependents();
+  if (threadIdx.x == 0) stamp(p.dbg, 2);
 
   if (warp_idx == 0) {
     if (lane == 0) {
@@ -162,6 +173,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t a_dst = base + s * stage_bytes;
         tma_load_2d(a_dst, &tmA, full_bar(s), kb * Tr::kBlockK, m0);
         tma_load_2d(a_dst + kATileBytes, &tmB, full_bar(s), kb * Tr::kBlockK, w_row0);
+        if (kb == 0) stamp(p.dbg, 3);
       }
     }
   } else if (warp_idx == 1) {
@@ -172,6 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = (kb / p.stages) & 1;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
+        if (kb == 0) stamp(p.dbg, 4);
         const uint32_t a_src = base + s * stage_bytes;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {   // 4 x 32-byte K slices inside the 128-byte swizzle row
@@ -182,6 +195,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_commit(empty_bar(s));       // frees the smem slot when these MMAs retire
       }
       tc_commit(tmem_full_bar);        // accumulator complete
+      stamp(p.dbg, 5);
     }
   } else {
     // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp_idx % 4); thread = output row ----------------
@@ -223,8 +237,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* wstage = base_ptr + q * p.warp_stage_bytes;     // aliases the operand ring: only touched after tmem_full
     uint8_t* slabA = wstage + (kLN ? n_chunks : 1) * kSlabBytes;
     float mean = 0.f, m2 = 0.f, cnt = 0.f;                   // running LayerNorm statistics of this thread's row
+    if (et == 0) stamp(p.dbg, 6);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (et == 0) stamp(p.dbg, 7);
     for (int c = 0; c < n_chunks; ++c) {
       const int c0 = c * 32;
       uint32_t v[32];
@@ -301,6 +317,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    if (et == 0) stamp(p.dbg, 8);
     if constexpr (kLN) {
       const float inv_n = 1.0f / static_cast<float>(p.N);
       float rstd = rsqrtf(m2 * inv_n + p.ln_eps);
@@ -375,11 +392,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    if (et == 0) stamp(p.dbg, 9);
     if (lane == 0) bulk_wait_all0();     // all bulk stores of this warp have completed before the CTA retires
+    if (et == 0) stamp(p.dbg, 10);
   }
   tc_fence_before();
   __syncthreads();
   if (warp_idx == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (threadIdx.x == 32) stamp(p.dbg, 11);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -479,6 +499,7 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   p.bias = a.bias; p.alpha = a.alpha; p.act = a.act;
   p.glu_nb = a.glu_nb; p.glu_channels = a.glu_channels;
   p.round_out = a.round_out;
+  p.dbg = g_timeline_enabled;
   EC_REQUIRE(a.out_f32 != nullptr || a.out_act != nullptr, "GEMM needs at least one output");
   EC_REQUIRE(a.glu_nb == 0 || a.bias != nullptr, "GLU GEMM needs a bias");
   EC_REQUIRE(a.residual == nullptr || a.ld_res == out_cols, "residual must be dense [M, N]");
@@ -516,6 +537,15 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   EC_CUDA(attr_err);
   dim3 grid(cdiv(a.M, kBlockM), tiles_n);
   EC_TRY(launch_pdl(gemm_tc_kernel<T, kLN>, grid, dim3(192), smem, stream, tmA, tmB, tmRes, tmOutF, tmOutA, tmLn, p));
+  return EC_OK;
+}
+
+// Debug hook: enable/disable the timeline stamps and read the 12 stamps (SM cycles) of the last GEMM's CTA (0,0):
+// 0 start, 1 setup done, 2 dependency wait done, 3 first TMA issued, 4 first stage landed, 5 last MMA committed,
+// 6 epilogue ready, 7 accumulator complete, 8 chunk loop done, 9 LayerNorm passes done, 10 bulk stores complete, 11 end.
+int gemm_timeline(int enable, unsigned long long* out12) {
+  g_timeline_enabled = enable;
+  if (out12 != nullptr) EC_CUDA(cudaMemcpyFromSymbol(out12, g_gemm_timeline, 12 * sizeof(unsigned long long)));
   return EC_OK;
 }
 

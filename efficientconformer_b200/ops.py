@@ -84,13 +84,15 @@ def fold_bn(w, b, g, beta, rm, rv, eps=1e-5):
 
 
 def relpos_attention(qkv, E, u, v, x_len, heads, group, precision):
-    """qkv [B,T,3D] fp32, E [2Tp-G, D] fp32, x_len int32 [B] or None -> [B,T,D] activation type."""
+    """qkv [B,T,3D], E [2Tp-G, D] (cast here to the activation type the kernel expects: TF32-rounded fp32 or bf16),
+    x_len int32 [B] or None -> [B,T,D] activation type."""
     pr = _p(precision)
     B, T, D3 = qkv.shape
     D = D3 // 3
     out = torch.empty(B, T, D, dtype=act_dtype(pr), device=qkv.device)
     xl = x_len.to(torch.int32).contiguous() if x_len is not None else None
-    check(lib().ec_op_relpos_attention(pr, ptr(qkv.float().contiguous()), ptr(E.float().contiguous()), ptr(u.float().contiguous()),
+    qkv, E = cast(qkv, pr), cast(E, pr)
+    check(lib().ec_op_relpos_attention(pr, ptr(qkv), ptr(E), ptr(u.float().contiguous()),
                                        ptr(v.float().contiguous()), ptr(xl), B, T, D, heads, group, ptr(out), stream_ptr()))
     return out
 

@@ -114,6 +114,8 @@ int ec_engine_profile_read(ec_engine* e, double* ms, double* flops, double* byte
  * launch every kernel with programmatic stream serialization so its prologue overlaps the predecessor's tail. */
 int ec_engine_set_fuse_ln(ec_engine* e, int enabled);
 int ec_set_pdl(int enabled);
+/* Debug: enable in-kernel SM-clock stamps in the GEMM and read the 12 stamps of the last GEMM's CTA (0,0) (synchronises). */
+int ec_debug_gemm_timeline(int enable, unsigned long long* out12);
 
 /* CTC head.  logits [B, T, V] fp32, logits_len [B] int64, targets [B, target_stride] int64 (blank = 0), target_len [B] int64.
  * scratch: at least B*T*(sizeof(float)+sizeof(int)) + B*sizeof(int) bytes.  loss_per_utt [B], loss_mean [1] fp32. */
@@ -147,7 +149,8 @@ int ec_op_glu_scratch_rows(int channels);
 /* eval BatchNorm folded into conv taps: w_out [C, taps], b_out [C] */
 int ec_op_fold_bn(const float* w, const float* b, const float* g, const float* beta, const float* rm, const float* rv, float eps,
                   int C, int taps, float* w_out, float* b_out, void* stream);
-int ec_op_relpos_attention(int precision, const float* qkv, const float* E, const float* u, const float* v,
+/* qkv [B*T, 3D] and E [2Tp-G, D]: fp32 already rounded to TF32 for EC_PREC_TF32, bf16 for EC_PREC_BF16 (what the QKV / pos GEMM epilogues emit) */
+int ec_op_relpos_attention(int precision, const void* qkv, const void* E, const float* u, const float* v,
                            const int32_t* x_len, int batch, int t, int dim, int heads, int group, void* out, void* stream);
 int ec_op_dwconv_bn_swish(int precision, const void* x, const float* w_folded, const float* b_folded, int batch, int t,
                           int channels, int k, int stride, void* y, void* stream);

@@ -206,9 +206,9 @@ def _attention_reference(qkv, E, u, v, x_len, H, G):
 def test_relpos_attention(ops, prec, B, T, D, H, G):
     g = torch.Generator(device="cpu").manual_seed(T * 3 + D)
     # contract: q|k|v and E arrive TF32-rounded (the producing GEMM epilogues round their fp32 output, round_out)
-    qkv = tf32_round(torch.randn(B, T, 3 * D, generator=g)).to(DEV)
+    qkv = rnd(prec, torch.randn(B, T, 3 * D, generator=g)).to(DEV)
     Tp = T + (-T) % G
-    E = tf32_round(torch.randn(2 * Tp - G, D, generator=g)).to(DEV)
+    E = rnd(prec, torch.randn(2 * Tp - G, D, generator=g)).to(DEV)
     u, v = (0.3 * torch.randn(D, generator=g)).to(DEV), (0.3 * torch.randn(D, generator=g)).to(DEV)
     x_len = torch.tensor([T] + [max(1, (2 * T) // 3)] * (B - 1), device=DEV)
     for xl in (x_len, None):
@@ -216,7 +216,7 @@ def test_relpos_attention(ops, prec, B, T, D, H, G):
         ref = _attention_reference(qkv, E, u, v, xl, H, G)
         assert out.shape == ref.shape
         err = rel_l2(out.float(), ref)
-        assert err < (2e-3 if prec == "tf32" else 5e-3), (err, xl is None)
+        assert err < (2e-3 if prec == "tf32" else 1e-2), (err, xl is None)      # bf16 path also rounds qu/qv, P and the output to bf16
 
 
 def test_ctc_loss_and_greedy_on_device(golden_dir):
