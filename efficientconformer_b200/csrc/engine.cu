@@ -70,6 +70,9 @@ struct ec_engine {
   size_t events_used = 0;
   int last_launches = 0;
   bool fuse_ln = true;     // LayerNorms in the epilogue of the producing GEMM (needs dim <= 256)
+  // the positional projections E_i = pos_layer_i(R) depend on weights only: they run on a forked stream, off the critical path
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace ec {
@@ -140,6 +143,7 @@ static void compute_shapes(const ec_config& c, int t_mel, Shapes* s) {
 
 struct Workspace {
   int* lens; void* sub_a; float *xa, *xb; void *xn, *xs, *h; float* qkv; float* ebuf; void *o, *gl, *hc; float* r;
+  size_t e_stride;   // bytes between the per-block E buffers
   size_t bytes;
 };
 static void layout_workspace(const ec_engine* e, int B, int t_mel, void* base, Workspace* ws) {
@@ -168,7 +172,8 @@ static void layout_workspace(const ec_engine* e, int B, int t_mel, void* base, W
   ws->xs = a.take(std::max<size_t>(mx_xs, 1) * es);
   ws->h = a.take(mx_h * es);
   ws->qkv = reinterpret_cast<float*>(a.take(mx_qkv * 4));
-  ws->ebuf = reinterpret_cast<float*>(a.take(mx_e * 4));
+  ws->e_stride = align_up(mx_e * 4, 256);
+  ws->ebuf = reinterpret_cast<float*>(a.take(ws->e_stride * c.num_blocks));
   ws->o = a.take(mx_x * es);
   ws->gl = a.take(mx_g * es);
   ws->hc = a.take(mx_hc * es);
@@ -270,6 +275,9 @@ int ec_engine_create(const ec_config* cfg, int precision, ec_engine** out) {
 void ec_engine_destroy(ec_engine* e) {
   if (e == nullptr) return;
   for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->side) cudaStreamDestroy(e->side);
   delete e;
 }
 size_t ec_engine_weight_bytes(const ec_engine* e) { return e->weight_bytes; }
@@ -379,6 +387,26 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
   for (int i = 0; i < c.num_blocks; ++i) bs.s[i] = c.blocks[i].conv_stride;
   { ProfScope ps(e, st, PC_MISC, 0, 0); EC_TRY(launch_stage_lengths(x_len, B, t_mel, bs, ws.lens, st)); }
 
+  // ---- fork: all positional projections (weights x constant tables) on the side stream ----
+  if (e->side == nullptr) {
+    EC_CUDA(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+    EC_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    EC_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  }
+  EC_CUDA(cudaEventRecord(e->ev_fork, st));
+  EC_CUDA(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+  for (int i = 0; i < c.num_blocks; ++i) {
+    const ec_block_cfg& bc = c.blocks[i];
+    const int D = bc.dim_model, T = sh.t_in[i], G = bc.group_size, P = (G - T % G) % G, e_rows = 2 * (T + P) - G;
+    EC_REQUIRE(relpos[i] != nullptr, "missing relative position table");
+    float* eb = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws.ebuf) + i * ws.e_stride);
+    const bool a16 = prec == EC_PREC_BF16;
+    EC_TRY(gemm(e, e->side, PC_POS, relpos[i], w.blk[i].wpos, e_rows, D, D, w.blk[i].bpos, 1.f, GEMM_ACT_NONE, nullptr, a16 ? nullptr : eb,
+                a16 ? eb : nullptr, 0, 0, nullptr, 1));
+  }
+  EC_CUDA(cudaEventRecord(e->ev_join, e->side));
+  bool joined = false;
+
   // ---- front end: Conv2d+BN+Swish producer, then Linear (K = C*F/2) ----
   const int feat = c.sub_filters * (c.n_mels / 2);
   {
@@ -420,10 +448,10 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
     const bool a16 = prec == EC_PREC_BF16;
     EC_TRY(gemm(e, st, PC_QKV, ws.xn, b.wqkv, M, 3 * D, D, b.bqkv, 1.f, GEMM_ACT_NONE, nullptr, a16 ? nullptr : ws.qkv, a16 ? ws.qkv : nullptr, 0, 0, nullptr, 1));
     const int G = bc.group_size, P = (G - T % G) % G, e_rows = 2 * (T + P) - G;
-    EC_REQUIRE(relpos[i] != nullptr, "missing relative position table");
-    EC_TRY(gemm(e, st, PC_POS, relpos[i], b.wpos, e_rows, D, D, b.bpos, 1.f, GEMM_ACT_NONE, nullptr, a16 ? nullptr : ws.ebuf, a16 ? ws.ebuf : nullptr, 0, 0, nullptr, 1));
+    if (!joined) { EC_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0)); joined = true; }     // join: E_i of every block is ready
     {
-      AttnArgs aa{ws.qkv, ws.ebuf, b.u, b.v, lens, B, T, D, bc.num_heads, G, ws.o, D};
+      const float* eb = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(ws.ebuf) + i * ws.e_stride);
+      AttnArgs aa{ws.qkv, eb, b.u, b.v, lens, B, T, D, bc.num_heads, G, ws.o, D};
       const double Tg = static_cast<double>(T + P) / G, dh = static_cast<double>(G) * D / bc.num_heads;
       ProfScope ps(e, st, PC_ATTN, B * bc.num_heads * (4.0 * Tg * Tg * dh + 2.0 * Tg * (2 * Tg - 1) * dh),
                    4.0 * M * 3 * D + 4.0 * e_rows * D + es * M * D);

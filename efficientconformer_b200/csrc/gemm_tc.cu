@@ -62,6 +62,48 @@ constexpr int kMaxStages = 8;
 constexpr int kNumBars = 2 * kMaxStages + 1 + 8;
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// x * sigmoid(x).  Parity (TF32) mode: exp + reciprocal.  bf16 mode: 0.5x + 0.5x*tanh(0.5x) with the hardware tanh
+// (1 MUFU instead of 2; its 2^-11 relative error is below the bf16 rounding that follows).
+template <typename T>
+__device__ __forceinline__ float swish_fn(float x) {
+  if constexpr (sizeof(T) == 4) {
+    return x * fast_sigmoid(x);
+  } else {
+    const float h = 0.5f * x;
+    float th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+    return fmaf(h, th, h);
+  }
+}
+template <typename T>
+__device__ __forceinline__ float sigmoid_fn(float x) {
+  if constexpr (sizeof(T) == 4) {
+    return fast_sigmoid(x);
+  } else {
+    float th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * x));
+    return fmaf(0.5f, th, 0.5f);
+  }
+}
+// Mean / centred sum of squares of the first nc (<= 32) values of t, four independent accumulation chains.
+__device__ __forceinline__ void chunk_stats(const float (&t)[32], int nc, float& cm, float& cq) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    s0 += (j < nc) ? t[j] : 0.f; s1 += (j + 1 < nc) ? t[j + 1] : 0.f;
+    s2 += (j + 2 < nc) ? t[j + 2] : 0.f; s3 += (j + 3 < nc) ? t[j + 3] : 0.f;
+  }
+  cm = ((s0 + s1) + (s2 + s3)) / static_cast<float>(nc);
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float d0 = t[j] - cm, d1 = t[j + 1] - cm, d2 = t[j + 2] - cm, d3 = t[j + 3] - cm;
+    q0 = fmaf((j < nc) ? d0 : 0.f, d0, q0); q1 = fmaf((j + 1 < nc) ? d1 : 0.f, d1, q1);
+    q2 = fmaf((j + 2 < nc) ? d2 : 0.f, d2, q2); q3 = fmaf((j + 3 < nc) ? d3 : 0.f, d3, q3);
+  }
+  cq = (q0 + q1) + (q2 + q3);
+}
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // ---- TMA store / bulk-group helpers -------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src, int c0, int c1) {
@@ -235,17 +277,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (n_chunks > 1) issue_res(1);
     }
     uint8_t* wstage = base_ptr + q * p.warp_stage_bytes;     // aliases the operand ring: only touched after tmem_full
-    uint8_t* slabA = wstage + (kLN ? n_chunks : 1) * kSlabBytes;
+    // plain: [F0 | F1 | A0 | A1] double-buffered output slabs; kLN: [x slabs (n_chunks) | A0 | A1]
+    uint8_t* slabA = wstage + (kLN ? n_chunks : 2) * kSlabBytes;
     float mean = 0.f, m2 = 0.f, cnt = 0.f;                   // running LayerNorm statistics of this thread's row
     if (et == 0) stamp(p.dbg, 6);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (et == 0) stamp(p.dbg, 7);
+    const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t v[32];
+    tmem_ld_32x32(tbase, v);                                 // software pipeline: the next chunk's accumulator load is in flight
     for (int c = 0; c < n_chunks; ++c) {
       const int c0 = c * 32;
-      uint32_t v[32];
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
-      tmem_ld_32x32(taddr, v);
+      const uint32_t taddr = tbase + static_cast<uint32_t>(c0);
       tmem_ld_wait();
       float t[32];
 #pragma unroll
@@ -260,13 +304,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 b4 = *reinterpret_cast<const float4*>(sbias + p.glu_nb + c0 + 4 * j4);
-          t[4 * j4] *= fast_sigmoid(__uint_as_float(v[4 * j4]) + b4.x); t[4 * j4 + 1] *= fast_sigmoid(__uint_as_float(v[4 * j4 + 1]) + b4.y);
-          t[4 * j4 + 2] *= fast_sigmoid(__uint_as_float(v[4 * j4 + 2]) + b4.z); t[4 * j4 + 3] *= fast_sigmoid(__uint_as_float(v[4 * j4 + 3]) + b4.w);
+          t[4 * j4] *= sigmoid_fn<T>(__uint_as_float(v[4 * j4]) + b4.x); t[4 * j4 + 1] *= sigmoid_fn<T>(__uint_as_float(v[4 * j4 + 1]) + b4.y);
+          t[4 * j4 + 2] *= sigmoid_fn<T>(__uint_as_float(v[4 * j4 + 2]) + b4.z); t[4 * j4 + 3] *= sigmoid_fn<T>(__uint_as_float(v[4 * j4 + 3]) + b4.w);
         }
       }
+      if (c + 1 < n_chunks) tmem_ld_32x32(taddr + 32u, v);   // v is consumed: prefetch the next chunk while this one is finished
       if (p.act == GEMM_ACT_SWISH) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) t[j] *= fast_sigmoid(t[j]);
+        for (int j = 0; j < 32; ++j) t[j] = swish_fn<T>(t[j]);
       }
       if (p.has_res) {
         mbar_wait(res_bar(q, c & 1), (c >> 1) & 1);
@@ -276,7 +321,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < 32; ++j) t[j] = fmaf(p.alpha, t[j], rr[j]);
         __syncwarp();
         if (lane == 0 && c + 2 < n_chunks) issue_res(c + 2);
-      } else {
+      } else if (p.alpha != 1.0f) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) t[j] *= p.alpha;
       }
@@ -287,13 +332,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if constexpr (kLN) {
         // chunk statistics (two-pass inside the chunk), merged into the running row statistics (Chan et al.)
         const int nc = min(32, p.N - c0);
-        float cs = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) cs += (j < nc) ? t[j] : 0.f;
-        const float cm = cs / static_cast<float>(nc);
-        float cq = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { const float dlt = t[j] - cm; cq += (j < nc) ? dlt * dlt : 0.f; }
+        float cm, cq;
+        chunk_stats(t, nc, cm, cq);
         const float tot = cnt + static_cast<float>(nc), dlt = cm - mean;
         mean += dlt * static_cast<float>(nc) / tot;
         m2 += cq + dlt * dlt * cnt * static_cast<float>(nc) / tot;
@@ -305,14 +345,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) { tma_store_2d(&tmOutF, smem_u32(wstage + c * kSlabBytes), c0, row0); bulk_commit(); }
         }
       } else {
-        if (c > 0) { if (lane == 0) bulk_wait_read0(); __syncwarp(); }   // the previous chunk's stores have drained the slabs
-        if (p.has_out_f32) slab_store_f32(wstage, lane, t);
-        if (p.has_out_act) slab_store_act<T>(slabA, lane, t);
+        if (c > 1) { if (lane == 0) bulk_wait_read1(); __syncwarp(); }   // the stores issued two chunks ago have drained this buffer
+        uint8_t* sf = wstage + (c & 1) * kSlabBytes;
+        uint8_t* sa = slabA + (c & 1) * kSlabBytes;
+        if (p.has_out_f32) slab_store_f32(sf, lane, t);
+        if (p.has_out_act) slab_store_act<T>(sa, lane, t);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (p.has_out_f32) tma_store_2d(&tmOutF, smem_u32(wstage), out_col0 + c0, row0);
-          if (p.has_out_act) tma_store_2d(&tmOutA, smem_u32(slabA), out_col0 + c0, row0);
+          if (p.has_out_f32) tma_store_2d(&tmOutF, smem_u32(sf), out_col0 + c0, row0);
+          if (p.has_out_act) tma_store_2d(&tmOutA, smem_u32(sa), out_col0 + c0, row0);
           bulk_commit();
         }
       }
@@ -335,13 +377,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             t[4 * j4] = (t[4 * j4] - mean) * rstd * g4.x + b4.x; t[4 * j4 + 1] = (t[4 * j4 + 1] - mean) * rstd * g4.y + b4.y;
             t[4 * j4 + 2] = (t[4 * j4 + 2] - mean) * rstd * g4.z + b4.z; t[4 * j4 + 3] = (t[4 * j4 + 3] - mean) * rstd * g4.w + b4.w;
           }
-          float cs = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) cs += (j < nc) ? t[j] : 0.f;
-          const float cm = cs / static_cast<float>(nc);
-          float cq = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { const float dlt = t[j] - cm; cq += (j < nc) ? dlt * dlt : 0.f; }
+          float cm, cq;
+          chunk_stats(t, nc, cm, cq);
           const float tot = cnt2 + static_cast<float>(nc), dlt = cm - mean2;
           mean2 += dlt * static_cast<float>(nc) / tot;
           m22 += cq + dlt * dlt * cnt2 * static_cast<float>(nc) / tot;
@@ -383,11 +420,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 t[4 * j4 + 2] = (t[4 * j4 + 2] - mean) * rstd * g4.z + b4.z; t[4 * j4 + 3] = (t[4 * j4 + 3] - mean) * rstd * g4.w + b4.w;
               }
             }
-            if (c > 0) { if (lane == 0) bulk_wait_read0(); __syncwarp(); }
-            slab_store_act<T>(slabA, lane, t);
+            if (c > 1) { if (lane == 0) bulk_wait_read1(); __syncwarp(); }
+            uint8_t* sa = slabA + (c & 1) * kSlabBytes;
+            slab_store_act<T>(sa, lane, t);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) { tma_store_2d(&tmLn, smem_u32(slabA), c0, row0); bulk_commit(); }
+            if (lane == 0) { tma_store_2d(&tmLn, smem_u32(sa), c0, row0); bulk_commit(); }
           }
         }
       }
@@ -480,7 +518,7 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   p.has_res = a.residual != nullptr; p.has_out_f32 = a.out_f32 != nullptr; p.has_out_act = a.out_act != nullptr;
   const int stage_bytes = kATileBytes + p.block_n * 128;
   const int n_chunks = cdiv(std::min(a.glu_nb > 0 ? a.glu_nb : p.block_n, out_cols), 32);
-  p.warp_stage_bytes = (kLN ? n_chunks + 1 : 2) * kSlabBytes;
+  p.warp_stage_bytes = (kLN ? n_chunks + 2 : 4) * kSlabBytes;
   const int fixed = (p.has_res ? kResRingBytes : 0) + kVecBytes + kNumBars * 8 + 16 + 1024;
   // up to 148 CTAs: one CTA per SM anyway -> deep ring (hides the TMA->MMA->refill round trip); otherwise 2 CTAs per SM
   const int ctas = cdiv(a.M, kBlockM) * tiles_n;
