@@ -19,6 +19,7 @@
 // (only 16-byte row pitches).  Operand type float => kind::tf32, __nv_bfloat16 => kind::f16.
 #include "ec_common.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 namespace ec {
@@ -29,6 +30,8 @@ struct GemmDev {
   int num_k_blocks, stages;
   int pipe_bytes;    // operand ring bytes (epilogue staging aliases it after the mainloop)
   int warp_stage_bytes;
+  int nbuf;          // output slab buffers per warp (2, 4 or 8): chunk c uses buffer c % nbuf
+  int epi_batch;     // 1: one proxy fence + all TMA stores after the chunk loop (needs n_chunks <= nbuf)
   int tmem_cols;
   const float* bias;
   float alpha;
@@ -103,7 +106,12 @@ __device__ __forceinline__ void chunk_stats(const float (&t)[32], int nc, float&
   }
   cq = (q0 + q1) + (q2 + q3);
 }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// wait until at most `pending` (1, 3 or 7) of this thread's bulk-store groups have not finished reading shared memory
+__device__ __forceinline__ void bulk_wait_read(int pending) {
+  if (pending >= 7) asm volatile("cp.async.bulk.wait_group.read 7;" ::: "memory");
+  else if (pending >= 3) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+  else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
 
 // ---- TMA store / bulk-group helpers -------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src, int c0, int c1) {
@@ -277,8 +285,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (n_chunks > 1) issue_res(1);
     }
     uint8_t* wstage = base_ptr + q * p.warp_stage_bytes;     // aliases the operand ring: only touched after tmem_full
-    // plain: [F0 | F1 | A0 | A1] double-buffered output slabs; kLN: [x slabs (n_chunks) | A0 | A1]
-    uint8_t* slabA = wstage + (kLN ? n_chunks : 2) * kSlabBytes;
+    // plain: [F slabs (nbuf, if fp32 output) | A slabs (nbuf)]; kLN: [x slabs (n_chunks) | A slabs (n_chunks)]
+    constexpr int kASlab = sizeof(T) == 4 ? kSlabBytes : kSlabBytes / 2;
+    const int nbuf = p.nbuf;
+    uint8_t* slabA = wstage + (kLN ? n_chunks : (p.has_out_f32 ? nbuf : 0)) * kSlabBytes;
+    const bool batch = p.epi_batch != 0;
     float mean = 0.f, m2 = 0.f, cnt = 0.f;                   // running LayerNorm statistics of this thread's row
     if (et == 0) stamp(p.dbg, 6);
     mbar_wait(tmem_full_bar, 0);
@@ -339,24 +350,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         m2 += cq + dlt * dlt * cnt * static_cast<float>(nc) / tot;
         cnt = tot;
         slab_store_f32(wstage + c * kSlabBytes, lane, t);      // row tile stays resident for the normalise passes
-        if (p.ln_mode == 1) {                                  // x itself is an output: store it now
+        if (p.ln_mode == 1 && !batch) {                        // x itself is an output: store it now
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) { tma_store_2d(&tmOutF, smem_u32(wstage + c * kSlabBytes), c0, row0); bulk_commit(); }
         }
       } else {
-        if (c > 1) { if (lane == 0) bulk_wait_read1(); __syncwarp(); }   // the stores issued two chunks ago have drained this buffer
-        uint8_t* sf = wstage + (c & 1) * kSlabBytes;
-        uint8_t* sa = slabA + (c & 1) * kSlabBytes;
+        const int buf = c & (nbuf - 1);
+        if (c >= nbuf) { if (lane == 0) bulk_wait_read(nbuf - 1); __syncwarp(); }   // the stores issued nbuf chunks ago have drained this buffer
+        uint8_t* sf = wstage + buf * kSlabBytes;
+        uint8_t* sa = slabA + buf * kASlab;
         if (p.has_out_f32) slab_store_f32(sf, lane, t);
         if (p.has_out_act) slab_store_act<T>(sa, lane, t);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (p.has_out_f32) tma_store_2d(&tmOutF, smem_u32(sf), out_col0 + c0, row0);
-          if (p.has_out_act) tma_store_2d(&tmOutA, smem_u32(sa), out_col0 + c0, row0);
-          bulk_commit();
+        if (!batch) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.has_out_f32) tma_store_2d(&tmOutF, smem_u32(sf), out_col0 + c0, row0);
+            if (p.has_out_act) tma_store_2d(&tmOutA, smem_u32(sa), out_col0 + c0, row0);
+            bulk_commit();
+          }
         }
+      }
+    }
+    if (batch && (!kLN || p.ln_mode == 1)) {                 // one fence, then every slab of this warp in one burst
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        for (int c = 0; c < n_chunks; ++c) {
+          if (kLN || p.has_out_f32) tma_store_2d(&tmOutF, smem_u32(wstage + c * kSlabBytes), out_col0 + c * 32, row0);
+          if (!kLN && p.has_out_act) tma_store_2d(&tmOutA, smem_u32(slabA + c * kASlab), out_col0 + c * 32, row0);
+        }
+        bulk_commit();
       }
     }
     if (et == 0) stamp(p.dbg, 8);
@@ -384,9 +409,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           m22 += cq + dlt * dlt * cnt2 * static_cast<float>(nc) / tot;
           cnt2 = tot;
           slab_store_f32(wstage + c * kSlabBytes, lane, t);
+          if (!batch) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&tmOutF, smem_u32(wstage + c * kSlabBytes), c0, row0); bulk_commit(); }
+          }
+        }
+        if (batch) {
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) { tma_store_2d(&tmOutF, smem_u32(wstage + c * kSlabBytes), c0, row0); bulk_commit(); }
+          if (lane == 0) {
+            for (int c = 0; c < n_chunks; ++c) tma_store_2d(&tmOutF, smem_u32(wstage + c * kSlabBytes), c * 32, row0);
+            bulk_commit();
+          }
         }
         mean = mean2; rstd = rsqrtf(m22 * inv_n + p.ln_eps);
         gfin = sg2; bfin = sb2;
@@ -420,12 +455,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 t[4 * j4 + 2] = (t[4 * j4 + 2] - mean) * rstd * g4.z + b4.z; t[4 * j4 + 3] = (t[4 * j4 + 3] - mean) * rstd * g4.w + b4.w;
               }
             }
-            if (c > 1) { if (lane == 0) bulk_wait_read1(); __syncwarp(); }
-            uint8_t* sa = slabA + (c & 1) * kSlabBytes;
+            if (c >= nbuf) { if (lane == 0) bulk_wait_read(nbuf - 1); __syncwarp(); }
+            uint8_t* sa = slabA + (c & (nbuf - 1)) * kASlab;   // normally one slab per chunk (nbuf >= n_chunks): no waits
             slab_store_act<T>(sa, lane, t);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) { tma_store_2d(&tmLn, smem_u32(sa), c0, row0); bulk_commit(); }
+            if (!batch) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) { tma_store_2d(&tmLn, smem_u32(sa), c0, row0); bulk_commit(); }
+            }
+          }
+        }
+        if (batch && p.has_ln_out) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            for (int c = 0; c < n_chunks; ++c) tma_store_2d(&tmLn, smem_u32(slabA + c * kASlab), c * 32, row0);
+            bulk_commit();
           }
         }
       }
@@ -518,7 +563,25 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   p.has_res = a.residual != nullptr; p.has_out_f32 = a.out_f32 != nullptr; p.has_out_act = a.out_act != nullptr;
   const int stage_bytes = kATileBytes + p.block_n * 128;
   const int n_chunks = cdiv(std::min(a.glu_nb > 0 ? a.glu_nb : p.block_n, out_cols), 32);
-  p.warp_stage_bytes = (kLN ? n_chunks + 2 : 4) * kSlabBytes;
+  const int a_slab = precision == EC_PREC_TF32 ? kSlabBytes : kSlabBytes / 2;
+  static const int epi_batch_env = [] { const char* e = getenv("EFFCONF_EPI_BATCH"); return (e != nullptr && e[0] == '1') ? 1 : 0; }();
+  const int per_chunk = (p.has_out_f32 ? kSlabBytes : 0) + (p.has_out_act ? a_slab : 0);
+  if (kLN) {
+    // x slabs are persistent (one per chunk); ln_out slabs: one per chunk when that fits, else a small ring
+    int na = 2;
+    while (na < n_chunks && na < 8) na <<= 1;
+    const int fixed_ln = (p.has_res ? kResRingBytes : 0) + kVecBytes + kNumBars * 8 + 16 + 1024;
+    while (na > 2 && 4 * (n_chunks * kSlabBytes + na * a_slab) + fixed_ln > 227 * 1024) na >>= 1;
+    p.nbuf = na;
+    p.warp_stage_bytes = n_chunks * kSlabBytes + na * a_slab;
+    p.epi_batch = (epi_batch_env && na >= n_chunks) ? 1 : 0;
+  } else {
+    int nbuf = 2;
+    while (nbuf < n_chunks && nbuf < 8) nbuf <<= 1;
+    p.nbuf = nbuf;                                          // reduced below if the staging would not fit
+    p.warp_stage_bytes = nbuf * per_chunk;
+    p.epi_batch = 0;
+  }
   const int fixed = (p.has_res ? kResRingBytes : 0) + kVecBytes + kNumBars * 8 + 16 + 1024;
   // up to 148 CTAs: one CTA per SM anyway -> deep ring (hides the TMA->MMA->refill round trip); otherwise 2 CTAs per SM
   const int ctas = cdiv(a.M, kBlockM) * tiles_n;
@@ -563,6 +626,13 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   if (a.out_act != nullptr) EC_TRY(make_slab_map(&tmOutA, act_f32, a.out_act, a.M, out_cols, a.ld_act));
   if (kLN && a.ln_out != nullptr) EC_TRY(make_slab_map(&tmLn, act_f32, a.ln_out, a.M, a.N, a.N));
 
+  if (!kLN) {
+    // staging aliases the operand ring; 1-CTA/SM launches may grow it up to the budget, 2-CTA/SM launches shrink nbuf instead
+    const size_t avail = (ctas <= 148) ? static_cast<size_t>(budget - fixed) : static_cast<size_t>(stages) * stage_bytes;
+    while (p.nbuf > 2 && static_cast<size_t>(4) * p.nbuf * per_chunk > avail) p.nbuf >>= 1;
+    p.warp_stage_bytes = p.nbuf * per_chunk;
+    p.epi_batch = (epi_batch_env && n_chunks <= p.nbuf) ? 1 : 0;
+  }
   size_t pipe_bytes = std::max(static_cast<size_t>(stages) * stage_bytes, static_cast<size_t>(4) * p.warp_stage_bytes);
   p.pipe_bytes = static_cast<int>(pipe_bytes);
   const size_t smem = pipe_bytes + fixed;
