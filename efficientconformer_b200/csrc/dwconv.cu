@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(1024) dwconv_bn_swish_kernel(const T* __restri
 #pragma unroll
   for (int r = 0; r < kDwR; ++r) {
     const int to = to0 + run0 + r;
-    if (to < T_out) yb[static_cast<size_t>(to) * C + c] = Tr::to(swishf_(acc[r]));
+    if (to < T_out) yb[static_cast<size_t>(to) * C + c] = Tr::to(swish_fn<T>(acc[r]));
   }
 }
 

@@ -30,7 +30,8 @@ struct GemmDev {
   int num_k_blocks, stages;
   int pipe_bytes;    // operand ring bytes (epilogue staging aliases it after the mainloop)
   int warp_stage_bytes;
-  int nbuf;          // output slab buffers per warp (2, 4 or 8): chunk c uses buffer c % nbuf
+  int nbuf;          // output slab buffers per warp (1, 2, 4 or 8): the warp's i-th chunk uses buffer i % nbuf
+  int res_depth;     // residual TMA ring depth per warp (1 or 2)
   int epi_batch;     // 1: one proxy fence + all TMA stores after the chunk loop (needs n_chunks <= nbuf)
   int tmem_cols;
   const float* bias;
@@ -58,36 +59,11 @@ __device__ __forceinline__ void stamp(int enabled, int slot) {
 constexpr int kBlockM = 128;
 constexpr int kATileBytes = kBlockM * 128;
 constexpr int kSlabBytes = 4096;             // 32 rows x 128 B
-constexpr int kResRingBytes = 4 * 2 * kSlabBytes;
 constexpr int kVecFloats = 288;              // bias / LayerNorm vectors in smem (256 + one chunk of slack)
-constexpr int kVecBytes = 5 * kVecFloats * 4;
+constexpr int kVecBytes = 5 * kVecFloats * 4 + 2 * 2 * 4 * 32 * 3 * 4;   // + LayerNorm statistics exchange [stage][half][quarter][lane][3]
 constexpr int kMaxStages = 8;
-constexpr int kNumBars = 2 * kMaxStages + 1 + 8;
+constexpr int kNumBars = 2 * kMaxStages + 1 + 16;
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-// x * sigmoid(x).  Parity (TF32) mode: exp + reciprocal.  bf16 mode: 0.5x + 0.5x*tanh(0.5x) with the hardware tanh
-// (1 MUFU instead of 2; its 2^-11 relative error is below the bf16 rounding that follows).
-template <typename T>
-__device__ __forceinline__ float swish_fn(float x) {
-  if constexpr (sizeof(T) == 4) {
-    return x * fast_sigmoid(x);
-  } else {
-    const float h = 0.5f * x;
-    float th;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
-    return fmaf(h, th, h);
-  }
-}
-template <typename T>
-__device__ __forceinline__ float sigmoid_fn(float x) {
-  if constexpr (sizeof(T) == 4) {
-    return fast_sigmoid(x);
-  } else {
-    float th;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * x));
-    return fmaf(0.5f, th, 0.5f);
-  }
-}
 // Mean / centred sum of squares of the first nc (<= 32) values of t, four independent accumulation chains.
 __device__ __forceinline__ void chunk_stats(const float (&t)[32], int nc, float& cm, float& cq) {
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -160,8 +136,10 @@ __device__ __forceinline__ void slab_store_act(uint8_t* slab, int row, const flo
   }
 }
 
+// kLN kernels run one CTA per SM, so they use 8 epilogue warps: warps q and q+4 share TMEM lane quarter q and take the
+// even / odd 32-column chunks of the same 32 rows; their LayerNorm statistics are merged through shared memory.
 template <typename T, bool kLN>
-__global__ void __launch_bounds__(192, kLN ? 1 : 2)
+__global__ void __launch_bounds__(kLN ? 320 : 192, kLN ? 1 : 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmOutF,
                const __grid_constant__ CUtensorMap tmOutA, const __grid_constant__ CUtensorMap tmLn, const GemmDev p) {
@@ -174,7 +152,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stage_bytes = kATileBytes + p.block_n * 128;
-  const int res_bytes = p.has_res ? kResRingBytes : 0;
+  constexpr int kEpiWarps = kLN ? 8 : 4, kHalves = kLN ? 2 : 1;
+  const int res_bytes = p.has_res ? kEpiWarps * p.res_depth * kSlabBytes : 0;
   uint8_t* res_ring = base_ptr + p.pipe_bytes;
   float* vecs = reinterpret_cast<float*>(base_ptr + p.pipe_bytes + res_bytes);          // bias | ln1_g | ln1_b | ln2_g | ln2_b
   uint64_t* bars = reinterpret_cast<uint64_t*>(base_ptr + p.pipe_bytes + res_bytes + kVecBytes);
@@ -183,7 +162,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto full_bar = [&](int s) { return bars_addr + 8u * s; };
   auto empty_bar = [&](int s) { return bars_addr + 8u * (kMaxStages + s); };
   const uint32_t tmem_full_bar = bars_addr + 8u * (2 * kMaxStages);
-  auto res_bar = [&](int q, int s) { return bars_addr + 8u * (2 * kMaxStages + 1 + 2 * q + s); };
+  auto res_bar = [&](int ew, int s) { return bars_addr + 8u * (2 * kMaxStages + 1 + 2 * ew + s); };
   volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(bars + kNumBars);
 
   if (threadIdx.x == 0) stamp(p.dbg, 0);
@@ -196,7 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(tmem_full_bar, 1);
-    for (int i = 0; i < 8; ++i) mbar_init(res_bar(i >> 1, i & 1), 1);
+    for (int i = 0; i < 16; ++i) mbar_init(res_bar(i >> 1, i & 1), 1);
     fence_barrier_init();
   }
   if (warp_idx == 1) {
@@ -250,7 +229,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp_idx % 4); thread = output row ----------------
     const int q = warp_idx & 3;
-    const int et = (warp_idx - 2) * 32 + lane;               // 0..127 among the epilogue threads
+    const int ew = warp_idx - 2;                             // epilogue warp index
+    const int half = ew >> 2;                                // which chunk parity this warp owns (kLN only)
+    const int et = ew * 32 + lane;                           // index among the epilogue threads
     const bool glu = p.glu_nb > 0;
     const int cols = glu ? p.glu_nb : p.block_n;             // logical output columns of this tile (multiple of 32 unless last tile)
     const int out_col0 = glu ? tile_n * p.glu_nb : w_row0;
@@ -259,7 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* sbias = vecs;
     float *sg1 = vecs + kVecFloats, *sb1 = vecs + 2 * kVecFloats, *sg2 = vecs + 3 * kVecFloats, *sb2 = vecs + 4 * kVecFloats;
     // ---- per-column vectors -> smem (zero beyond the valid range) ----
-    for (int i = et; i < kVecFloats; i += 128) {
+    for (int i = et; i < kVecFloats; i += 32 * kEpiWarps) {
       float bv = 0.f;
       if (p.bias != nullptr) {
         if (glu) { if (i < 2 * p.glu_nb) bv = __ldg(p.bias + w_row0 + i); }
@@ -272,23 +253,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         sg2[i] = (ok && p.ln2_g != nullptr) ? __ldg(p.ln2_g + i) : 0.f; sb2[i] = (ok && p.ln2_g != nullptr) ? __ldg(p.ln2_b + i) : 0.f;
       }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");           // epilogue warps only
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");      // epilogue warps only
     // ---- residual slabs: 2-deep TMA ring per warp ----
     const int n_chunks = (min(cols, n_limit - out_col0) + 31) / 32;
-    uint8_t* my_res = res_ring + q * 2 * kSlabBytes;
-    auto issue_res = [&](int c) {
-      mbar_arrive_expect_tx(res_bar(q, c & 1), kSlabBytes);
-      tma_load_2d(smem_u32(my_res + (c & 1) * kSlabBytes), &tmRes, res_bar(q, c & 1), out_col0 + c * 32, row0);
+    // this warp's i-th chunk is column chunk c = half + i * kHalves
+    const int my_chunks = (n_chunks - half + kHalves - 1) / kHalves;
+    uint8_t* my_res = res_ring + ew * p.res_depth * kSlabBytes;
+    const int rmask = p.res_depth - 1;
+    auto issue_res = [&](int i) {
+      mbar_arrive_expect_tx(res_bar(ew, i & rmask), kSlabBytes);
+      tma_load_2d(smem_u32(my_res + (i & rmask) * kSlabBytes), &tmRes, res_bar(ew, i & rmask), out_col0 + (half + i * kHalves) * 32, row0);
     };
     if (p.has_res && lane == 0) {
-      issue_res(0);
-      if (n_chunks > 1) issue_res(1);
+      if (my_chunks > 0) issue_res(0);
+      if (my_chunks > 1 && p.res_depth > 1) issue_res(1);
     }
     uint8_t* wstage = base_ptr + q * p.warp_stage_bytes;     // aliases the operand ring: only touched after tmem_full
     // plain: [F slabs (nbuf, if fp32 output) | A slabs (nbuf)]; kLN: [x slabs (n_chunks) | A slabs (n_chunks)]
     constexpr int kASlab = sizeof(T) == 4 ? kSlabBytes : kSlabBytes / 2;
     const int nbuf = p.nbuf;
-    uint8_t* slabA = wstage + (kLN ? n_chunks : (p.has_out_f32 ? nbuf : 0)) * kSlabBytes;
+    uint8_t* slabA = wstage + (kLN ? n_chunks : (p.has_out_f32 ? nbuf : 0)) * kSlabBytes + (kLN ? half * nbuf * kASlab : 0);
+    float* stat_x = vecs + 5 * kVecFloats;                   // [stage 2][half 2][quarter 4][lane 32][3]
     const bool batch = p.epi_batch != 0;
     float mean = 0.f, m2 = 0.f, cnt = 0.f;                   // running LayerNorm statistics of this thread's row
     if (et == 0) stamp(p.dbg, 6);
@@ -297,8 +282,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (et == 0) stamp(p.dbg, 7);
     const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t v[32];
-    tmem_ld_32x32(tbase, v);                                 // software pipeline: the next chunk's accumulator load is in flight
-    for (int c = 0; c < n_chunks; ++c) {
+    if (my_chunks > 0) tmem_ld_32x32(tbase + 32u * half, v);  // software pipeline: the next chunk's accumulator load is in flight
+    for (int i = 0; i < my_chunks; ++i) {
+      const int c = half + i * kHalves;
       const int c0 = c * 32;
       const uint32_t taddr = tbase + static_cast<uint32_t>(c0);
       tmem_ld_wait();
@@ -319,19 +305,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           t[4 * j4 + 2] *= sigmoid_fn<T>(__uint_as_float(v[4 * j4 + 2]) + b4.z); t[4 * j4 + 3] *= sigmoid_fn<T>(__uint_as_float(v[4 * j4 + 3]) + b4.w);
         }
       }
-      if (c + 1 < n_chunks) tmem_ld_32x32(taddr + 32u, v);   // v is consumed: prefetch the next chunk while this one is finished
+      if (i + 1 < my_chunks) tmem_ld_32x32(taddr + 32u * kHalves, v);   // v is consumed: prefetch this warp's next chunk
       if (p.act == GEMM_ACT_SWISH) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) t[j] = swish_fn<T>(t[j]);
       }
       if (p.has_res) {
-        mbar_wait(res_bar(q, c & 1), (c >> 1) & 1);
+        mbar_wait(res_bar(ew, i & rmask), (i / p.res_depth) & 1);
         float rr[32];
-        slab_load_f32(my_res + (c & 1) * kSlabBytes, lane, rr);
+        slab_load_f32(my_res + (i & rmask) * kSlabBytes, lane, rr);
 #pragma unroll
         for (int j = 0; j < 32; ++j) t[j] = fmaf(p.alpha, t[j], rr[j]);
         __syncwarp();
-        if (lane == 0 && c + 2 < n_chunks) issue_res(c + 2);
+        if (lane == 0 && i + p.res_depth < my_chunks) issue_res(i + p.res_depth);
       } else if (p.alpha != 1.0f) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) t[j] *= p.alpha;
@@ -356,8 +342,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) { tma_store_2d(&tmOutF, smem_u32(wstage + c * kSlabBytes), c0, row0); bulk_commit(); }
         }
       } else {
-        const int buf = c & (nbuf - 1);
-        if (c >= nbuf) { if (lane == 0) bulk_wait_read(nbuf - 1); __syncwarp(); }   // the stores issued nbuf chunks ago have drained this buffer
+        const int buf = i & (nbuf - 1);
+        if (i >= nbuf) { if (lane == 0) bulk_wait_read(nbuf - 1); __syncwarp(); }   // the stores issued nbuf chunks ago have drained this buffer
         uint8_t* sf = wstage + buf * kSlabBytes;
         uint8_t* sa = slabA + buf * kASlab;
         if (p.has_out_f32) slab_store_f32(sf, lane, t);
@@ -377,7 +363,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        for (int c = 0; c < n_chunks; ++c) {
+        for (int c = half; c < n_chunks; c += kHalves) {
           if (kLN || p.has_out_f32) tma_store_2d(&tmOutF, smem_u32(wstage + c * kSlabBytes), out_col0 + c * 32, row0);
           if (!kLN && p.has_out_act) tma_store_2d(&tmOutA, smem_u32(slabA + c * kASlab), out_col0 + c * 32, row0);
         }
@@ -387,12 +373,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (et == 0) stamp(p.dbg, 8);
     if constexpr (kLN) {
       const float inv_n = 1.0f / static_cast<float>(p.N);
+      // merge the (count, mean, M2) of the two warps that share these 32 rows (fixed order -> both get identical results)
+      auto merge_pair = [&](int stage, float& mean_, float& m2_, float cnt_) {
+        float* mine = stat_x + (((stage * 2 + half) * 4 + q) * 32 + lane) * 3;
+        const float* other = stat_x + (((stage * 2 + (half ^ 1)) * 4 + q) * 32 + lane) * 3;
+        mine[0] = cnt_; mine[1] = mean_; mine[2] = m2_;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        const float oc = other[0], om = other[1], o2 = other[2];
+        const float c0_ = half == 0 ? cnt_ : oc, m0_ = half == 0 ? mean_ : om, q0_ = half == 0 ? m2_ : o2;
+        const float c1_ = half == 0 ? oc : cnt_, m1_ = half == 0 ? om : mean_, q1_ = half == 0 ? o2 : m2_;
+        const float tot = c0_ + c1_, dl = m1_ - m0_;
+        mean_ = c1_ > 0.f ? m0_ + dl * c1_ / tot : m0_;
+        m2_ = c1_ > 0.f ? q0_ + q1_ + dl * dl * c0_ * c1_ / tot : q0_;
+      };
+      merge_pair(0, mean, m2, cnt);
       float rstd = rsqrtf(m2 * inv_n + p.ln_eps);
       const float* gfin = sg1; const float* bfin = sb1;
       bool affine = true;
       if (p.ln_mode == 2) {            // block norm in place (fp32 output), then the next module's LayerNorm on top of it
         float mean2 = 0.f, m22 = 0.f, cnt2 = 0.f;
-        for (int c = 0; c < n_chunks; ++c) {
+        for (int c = half; c < n_chunks; c += kHalves) {
           const int c0 = c * 32, nc = min(32, p.N - c0);
           float t[32];
           slab_load_f32(wstage + c * kSlabBytes, lane, t);
@@ -419,10 +419,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            for (int c = 0; c < n_chunks; ++c) tma_store_2d(&tmOutF, smem_u32(wstage + c * kSlabBytes), c * 32, row0);
+            for (int c = half; c < n_chunks; c += kHalves) tma_store_2d(&tmOutF, smem_u32(wstage + c * kSlabBytes), c * 32, row0);
             bulk_commit();
           }
         }
+        if (p.ln2_g != nullptr) merge_pair(1, mean2, m22, cnt2);
         mean = mean2; rstd = rsqrtf(m22 * inv_n + p.ln_eps);
         gfin = sg2; bfin = sb2;
         affine = p.ln2_g != nullptr;
@@ -438,7 +439,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       if (p.has_ln_out || do_copy) {
-        for (int c = 0; c < n_chunks; ++c) {
+        for (int c = half, i = 0; c < n_chunks; c += kHalves, ++i) {
           const int c0 = c * 32, nc = min(32, p.N - c0);
           float t[32];
           slab_load_f32(wstage + c * kSlabBytes, lane, t);
@@ -455,8 +456,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 t[4 * j4 + 2] = (t[4 * j4 + 2] - mean) * rstd * g4.z + b4.z; t[4 * j4 + 3] = (t[4 * j4 + 3] - mean) * rstd * g4.w + b4.w;
               }
             }
-            if (c >= nbuf) { if (lane == 0) bulk_wait_read(nbuf - 1); __syncwarp(); }
-            uint8_t* sa = slabA + (c & (nbuf - 1)) * kASlab;   // normally one slab per chunk (nbuf >= n_chunks): no waits
+            if (i >= nbuf) { if (lane == 0) { if (nbuf > 1) bulk_wait_read(nbuf - 1); else bulk_wait_read0(); } __syncwarp(); }
+            uint8_t* sa = slabA + (i & (nbuf - 1)) * kASlab;   // normally one slab per owned chunk: no waits
             slab_store_act<T>(sa, lane, t);
             if (!batch) {
               fence_proxy_async_smem();
@@ -469,7 +470,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            for (int c = 0; c < n_chunks; ++c) tma_store_2d(&tmLn, smem_u32(slabA + c * kASlab), c * 32, row0);
+            for (int c = half, i = 0; c < n_chunks; c += kHalves, ++i) tma_store_2d(&tmLn, smem_u32(slabA + i * kASlab), c * 32, row0);
             bulk_commit();
           }
         }
@@ -566,15 +567,22 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   const int a_slab = precision == EC_PREC_TF32 ? kSlabBytes : kSlabBytes / 2;
   static const int epi_batch_env = [] { const char* e = getenv("EFFCONF_EPI_BATCH"); return (e != nullptr && e[0] == '1') ? 1 : 0; }();
   const int per_chunk = (p.has_out_f32 ? kSlabBytes : 0) + (p.has_out_act ? a_slab : 0);
+  p.res_depth = 2;
   if (kLN) {
-    // x slabs are persistent (one per chunk); ln_out slabs: one per chunk when that fits, else a small ring
-    int na = 2;
-    while (na < n_chunks && na < 8) na <<= 1;
-    const int fixed_ln = (p.has_res ? kResRingBytes : 0) + kVecBytes + kNumBars * 8 + 16 + 1024;
-    while (na > 2 && 4 * (n_chunks * kSlabBytes + na * a_slab) + fixed_ln > 227 * 1024) na >>= 1;
+    // per row quarter: persistent x slabs (one per chunk) + ln_out slabs for each of the two warps of the pair
+    // (one per owned chunk when that fits, else a smaller ring); the residual ring shrinks to depth 1 last
+    const int own = cdiv(n_chunks, 2);
+    int na = 1;
+    while (na < own && na < 4) na <<= 1;
+    auto total = [&](int na_, int depth) {
+      return 4 * (n_chunks * kSlabBytes + 2 * na_ * a_slab) + (p.has_res ? 8 * depth * kSlabBytes : 0) + kVecBytes + kNumBars * 8 + 16 + 1024;
+    };
+    while (na > 1 && total(na, 2) > 227 * 1024) na >>= 1;
+    if (total(na, 2) > 227 * 1024) p.res_depth = 1;
+    EC_REQUIRE(total(na, p.res_depth) <= 227 * 1024, "fused LayerNorm tile does not fit in shared memory");
     p.nbuf = na;
-    p.warp_stage_bytes = n_chunks * kSlabBytes + na * a_slab;
-    p.epi_batch = (epi_batch_env && na >= n_chunks) ? 1 : 0;
+    p.warp_stage_bytes = n_chunks * kSlabBytes + 2 * na * a_slab;
+    p.epi_batch = (epi_batch_env && na >= own) ? 1 : 0;
   } else {
     int nbuf = 2;
     while (nbuf < n_chunks && nbuf < 8) nbuf <<= 1;
@@ -582,10 +590,10 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
     p.warp_stage_bytes = nbuf * per_chunk;
     p.epi_batch = 0;
   }
-  const int fixed = (p.has_res ? kResRingBytes : 0) + kVecBytes + kNumBars * 8 + 16 + 1024;
+  const int fixed = (p.has_res ? (kLN ? 8 : 4) * p.res_depth * kSlabBytes : 0) + kVecBytes + kNumBars * 8 + 16 + 1024;
   // up to 148 CTAs: one CTA per SM anyway -> deep ring (hides the TMA->MMA->refill round trip); otherwise 2 CTAs per SM
   const int ctas = cdiv(a.M, kBlockM) * tiles_n;
-  const int budget = (ctas <= 148 || kLN) ? 208 * 1024 : 113 * 1024;
+  const int budget = (ctas <= 148 || kLN) ? 224 * 1024 : 113 * 1024;
   int stages = (budget - fixed) / stage_bytes;
   if (stages < 2) stages = 2;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -644,7 +652,7 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   });
   EC_CUDA(attr_err);
   dim3 grid(cdiv(a.M, kBlockM), tiles_n);
-  EC_TRY(launch_pdl(gemm_tc_kernel<T, kLN>, grid, dim3(192), smem, stream, tmA, tmB, tmRes, tmOutF, tmOutA, tmLn, p));
+  EC_TRY(launch_pdl(gemm_tc_kernel<T, kLN>, grid, dim3(kLN ? 320 : 192), smem, stream, tmA, tmB, tmRes, tmOutF, tmOutA, tmLn, p));
   return EC_OK;
 }
 
