@@ -175,11 +175,6 @@ def run_ours(args, rank, world, local_rank):
         logits, out_len, _ = model.forward_mel(mel_d, len_d)
         return ctc_loss(logits, out_len, y_d, yl_d)[0]
 
-    def step_e2e():
-        m = mel_h.to(dev, non_blocking=True); l = len_h.to(dev, non_blocking=True)
-        logits, out_len, _ = model.forward_mel(m, l)
-        return float(ctc_loss(logits, out_len, y_d, yl_d)[0].item())
-
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
@@ -206,12 +201,45 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms)
     # ---- end to end through the public API with host buffers ----
-    for _ in range(3):
-        step_e2e()
+    # Every step copies its own inputs from pinned host memory (copy stream), runs ModelCTC.forward_mel + ctc_loss and reads
+    # the loss back to the host.  The copy of step k+1 and the read-back of step k-1 overlap the compute of step k (a 2-deep
+    # input pipeline, what a DataLoader with pinned memory does); all K copies, K computes and K read-backs are inside the
+    # timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+
+    def e2e_loop(n_steps):
+        cur = torch.cuda.current_stream()
+        bufs, ready, done = [None, None], [torch.cuda.Event(), torch.cuda.Event()], [torch.cuda.Event(), torch.cuda.Event()]
+        losses = []
+
+        def stage(k):
+            with torch.cuda.stream(copy_stream):
+                if bufs[k & 1] is not None:
+                    copy_stream.wait_event(done[k & 1])                   # the compute that used this buffer has finished
+                bufs[k & 1] = (mel_h.to(dev, non_blocking=True), len_h.to(dev, non_blocking=True))
+                ready[k & 1].record(copy_stream)
+        stage(0)
+        for k in range(n_steps):
+            if k + 1 < n_steps:
+                stage(k + 1)
+            cur.wait_event(ready[k & 1])
+            m, l = bufs[k & 1]
+            logits, out_len, _ = model.forward_mel(m, l)
+            loss = ctc_loss(logits, out_len, y_d, yl_d)[0]
+            loss_host[k & 1].copy_(loss, non_blocking=True)               # D2H of the step's result
+            done[k & 1].record(cur)
+            if k >= 1:
+                done[(k - 1) & 1].synchronize()
+                losses.append(float(loss_host[(k - 1) & 1]))
+        done[(n_steps - 1) & 1].synchronize()
+        losses.append(float(loss_host[(n_steps - 1) & 1]))
+        return losses
+
+    e2e_loop(3)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
+    e2e_losses = e2e_loop(args.steps)
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     barrier()
@@ -278,7 +306,8 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic", "config": workload_config(args, B, "gpu"),
         "e2e": {"value": frames_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": mel_h.numel() * 4 + len_h.numel() * 8, "d2h_bytes_per_step": 4,
-                "ms_per_step": 1e3 * e2e_s / args.steps, "timing": "wall clock around K API calls, synchronised both sides"},
+                "ms_per_step": 1e3 * e2e_s / args.steps,
+                "timing": "wall clock around K API calls, synchronised both sides; 2-deep pinned-memory input pipeline on a copy stream"},
         "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
         "clocks": clocks, "roofline": roofline, "rooflines_other": extra_rooflines, "kernels": kernels,
         "step_ms_min_med_max": [round(min(step_ms), 4), round(statistics.median(step_ms), 4), round(max(step_ms), 4)],
