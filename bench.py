@@ -43,6 +43,24 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_gemm_traffic(precision):
+    """Average DRAM bytes (read + write) per GEMM launch from the committed `ncu --set full` capture of block 0
+    (profiles/, produced by tools/summarize_ncu.py); None when no capture exists for this precision."""
+    path = os.path.join(ROOT, "profiles", f"r1_ncu_full_block0_{precision}_summary.json")
+    if not os.path.exists(path):
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, n = 0.0, 0
+    for k in json.load(open(path))["kernels"]:
+        if not k["kernel"].startswith("gemm_tc_kernel"):
+            continue
+        for key in ("dram_read", "dram_write"):
+            val, unit = k[key].split()
+            tot += float(val) * scale[unit]
+        n += 1
+    return {"bytes_per_launch": round(tot / n), "launches_sampled": n, "source": os.path.relpath(path, ROOT)} if n else None
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -283,7 +301,7 @@ def run_ours(args, rank, world, local_rank):
     fwd_profiled_ms = sum(k["ms"] for k in kernels)
     achieved = gemm_fl / gemm_ms / 1e9 if gemm_ms > 0 else 0.0
     roofline = {"kernel": "gemm_tc_kernel (tcgen05, all GEMM launches of one forward)", "bound": "tensor", "achieved": round(achieved, 2),
-                "peak": tensor_peak, "unit": "TFLOP/s", "frac": round(achieved / tensor_peak, 4), "traffic": None,
+                "peak": tensor_peak, "unit": "TFLOP/s", "frac": round(achieved / tensor_peak, 4), "traffic": ncu_gemm_traffic(args.precision),
                 "peak_source": pk["source"] + (" bf16 cuBLAS burst" if args.precision == "bf16" else " bf16 cuBLAS burst / 2 (tf32 operands)"),
                 "launches_per_forward": gemm_n, "avg_launch_us": round(1e3 * gemm_ms / max(gemm_n, 1), 2),
                 "share_of_forward": round(gemm_ms / fwd_profiled_ms, 3) if fwd_profiled_ms else None}
