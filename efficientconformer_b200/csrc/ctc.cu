@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(32) ctc_alpha_warp_kernel(const float* __restr
                                                             const int* __restrict__ logits_len, const long long* __restrict__ targets,
                                                             int target_stride, const long long* __restrict__ target_len,
                                                             float* __restrict__ loss_per_utt) {
+  extern __shared__ float lp_sm[];                 // [Tb][32*kCtcNS] emission log-probs of the extended labels, gathered up front
+  constexpr int SP = 32 * kCtcNS;
   grid_dependency_wait();
   const int b = blockIdx.x, lane = threadIdx.x;
   const int U = static_cast<int>(target_len[b]);
@@ -112,37 +114,43 @@ __global__ void __launch_bounds__(32) ctc_alpha_warp_kernel(const float* __restr
   if (Tb > T) Tb = T;
   if (Tb <= 0) { if (lane == 0) loss_per_utt[b] = INFINITY; return; }
   const long long* y = targets + static_cast<size_t>(b) * target_stride;
-  int ext[kCtcNS]; bool skip[kCtcNS];
-#pragma unroll
-  for (int k = 0; k < kCtcNS; ++k) {
-    const int s = lane * kCtcNS + k;
-    ext[k] = (s < S && (s & 1)) ? static_cast<int>(y[s >> 1]) : 0;
-    const int e2 = (s >= 2 && s < S && (s & 1)) ? static_cast<int>(y[(s - 2) >> 1]) : 0;
-    skip[k] = s >= 2 && s < S && ext[k] != 0 && ext[k] != e2;
-  }
   const float* lg = logits + static_cast<size_t>(b) * T * V;
   const float* ls = lse + static_cast<size_t>(b) * T;
-  float a[kCtcNS], nxt[kCtcNS];
+  // gather phase: T*S independent loads (the recursion below then only touches shared memory); state s lives at column
+  // (s % kCtcNS) * 32 + s / kCtcNS so that a lane's kCtcNS states are conflict-free
+  {
+    int ge[kCtcNS];
+#pragma unroll
+    for (int k = 0; k < kCtcNS; ++k) { const int s = k * 32 + lane; ge[k] = (s < S && (s & 1)) ? static_cast<int>(y[s >> 1]) : 0; }
+    for (int t = 0; t < Tb; ++t) {
+      const float* lgt = lg + static_cast<size_t>(t) * V;
+      const float l1 = ls[t];
+#pragma unroll
+      for (int k = 0; k < kCtcNS; ++k) {
+        const int s = k * 32 + lane;                 // coalesced over s for the store
+        lp_sm[t * SP + (s % kCtcNS) * 32 + s / kCtcNS] = lgt[ge[k]] - l1;
+      }
+    }
+  }
+  __syncwarp();
+  bool skip[kCtcNS];
 #pragma unroll
   for (int k = 0; k < kCtcNS; ++k) {
     const int s = lane * kCtcNS + k;
-    a[k] = s < 2 && s < S ? lg[ext[k]] - ls[0] : -INFINITY;
+    const int e = (s < S && (s & 1)) ? static_cast<int>(y[s >> 1]) : 0;
+    const int e2 = (s >= 2 && s < S && (s & 1)) ? static_cast<int>(y[(s - 2) >> 1]) : 0;
+    skip[k] = s >= 2 && s < S && e != 0 && e != e2;
   }
-  if (Tb > 1) {
+  float a[kCtcNS];
 #pragma unroll
-    for (int k = 0; k < kCtcNS; ++k) nxt[k] = lg[static_cast<size_t>(V) + ext[k]] - ls[1];
+  for (int k = 0; k < kCtcNS; ++k) {
+    const int s = lane * kCtcNS + k;
+    a[k] = (s < 2 && s < S) ? lp_sm[k * 32 + lane] : -INFINITY;
   }
   for (int t = 1; t < Tb; ++t) {
     float cur[kCtcNS];
 #pragma unroll
-    for (int k = 0; k < kCtcNS; ++k) cur[k] = nxt[k];
-    if (t + 1 < Tb) {
-      const float* lgt = lg + static_cast<size_t>(t + 1) * V;
-      const float l1 = ls[t + 1];
-#pragma unroll
-      for (int k = 0; k < kCtcNS; ++k) nxt[k] = lgt[ext[k]] - l1;
-    }
-    // previous lane's last two states
+    for (int k = 0; k < kCtcNS; ++k) cur[k] = lp_sm[t * SP + k * 32 + lane];
     float pm1 = __shfl_up_sync(0xffffffffu, a[kCtcNS - 1], 1), pm2 = __shfl_up_sync(0xffffffffu, a[kCtcNS - 2], 1);
     if (lane == 0) { pm1 = -INFINITY; pm2 = -INFINITY; }
     float na[kCtcNS];
@@ -156,7 +164,6 @@ __global__ void __launch_bounds__(32) ctc_alpha_warp_kernel(const float* __restr
 #pragma unroll
     for (int k = 0; k < kCtcNS; ++k) a[k] = na[k];
   }
-  // read-out: states S-1 and S-2
   float e1 = -INFINITY, e2 = -INFINITY;
 #pragma unroll
   for (int k = 0; k < kCtcNS; ++k) {
@@ -183,15 +190,23 @@ int launch_ctc_loss(const float* logits, const float* lse, int B, int T, int V, 
   const size_t smem = sizeof(float) * 3 * (2 * static_cast<size_t>(target_stride) + 1);
   EC_REQUIRE(smem <= 48 * 1024, "CTC target too long for the shared-memory alpha buffers");
   const int s_max = 2 * target_stride + 1;
-  if (s_max <= 64) {
-    ctc_alpha_warp_kernel<2><<<B, 32, 0, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, loss_per_utt);
-  } else if (s_max <= 128) {
-    ctc_alpha_warp_kernel<4><<<B, 32, 0, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, loss_per_utt);
-  } else if (s_max <= 256) {
-    ctc_alpha_warp_kernel<8><<<B, 32, 0, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, loss_per_utt);
-  } else {
-    ctc_alpha_kernel<<<B, 256, smem, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, loss_per_utt);
+  // warp kernel: emissions of one utterance gathered into shared memory ([T][32*NS] floats)
+#define EC_CTC_WARP(NS)                                                                                                     \
+  {                                                                                                                        \
+    const size_t sm = static_cast<size_t>(T) * 32 * NS * sizeof(float);                                                     \
+    if (sm <= 200 * 1024) {                                                                                                \
+      static cudaError_t attr = cudaFuncSetAttribute(ctc_alpha_warp_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+      EC_CUDA(attr);                                                                                                       \
+      ctc_alpha_warp_kernel<NS><<<B, 32, sm, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, loss_per_utt); \
+      launched = true;                                                                                                     \
+    }                                                                                                                      \
   }
+  bool launched = false;
+  if (s_max <= 64) EC_CTC_WARP(2)
+  else if (s_max <= 128) EC_CTC_WARP(4)
+  else if (s_max <= 256) EC_CTC_WARP(8)
+#undef EC_CTC_WARP
+  if (!launched) ctc_alpha_kernel<<<B, 256, smem, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, loss_per_utt);
   EC_CUDA(cudaGetLastError());
   if (loss_mean != nullptr) {
     mean_kernel<<<1, 32, 0, stream>>>(loss_per_utt, B, loss_mean);
