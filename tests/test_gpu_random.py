@@ -76,7 +76,7 @@ def test_random_gemm_layernorm_shapes(ops, prec):
 def test_random_attention_shapes(ops, prec):
     rng = random.Random(7)
     for trial in range(14):
-        D, H, G = rng.choice([(120, 4, 3), (168, 4, 1), (240, 4, 1), (180, 4, 3), (256, 4, 1)])
+        D, H, G = rng.choice([(120, 4, 3), (168, 4, 1), (240, 4, 1), (100, 4, 3), (256, 4, 1)])
         T = rng.choice([1, 2, 3, 5, 63, 64, 65, 128, 191, 192, 193, 400])
         B = rng.choice([1, 2, 3])
         g = torch.Generator().manual_seed(500 + trial)
