@@ -318,7 +318,7 @@ static int launch_attn_t(const AttnDev& p, cudaStream_t stream) {
 }
 
 int launch_relpos_attention(int precision, const AttnArgs& a, cudaStream_t stream) {
-  if (precision == EC_PREC_BF16) return launch_relpos_attention_bf16(a, stream);
+  if (precision == EC_PREC_BF16 && !a.in_f32) return launch_relpos_attention_bf16(a, stream);
   EC_REQUIRE(a.G >= 1 && a.G % 2 == 1, "attention group size must be odd");
   EC_REQUIRE((a.G * a.D) % a.H == 0, "G*D must be divisible by H");
   AttnDev p{};
@@ -330,7 +330,7 @@ int launch_relpos_attention(int precision, const AttnArgs& a, cudaStream_t strea
   p.out = a.out; p.ld_out = a.ld_out;
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(p.d));
   if (precision == EC_PREC_TF32) return launch_attn_t<float>(p, stream);
-  if (precision == EC_PREC_BF16) return launch_relpos_attention_bf16(a, stream);     // bf16 q|k|v / E, bf16 tensor-core path
+  if (precision == EC_PREC_BF16) return launch_attn_t<__nv_bfloat16>(p, stream);     // fp32 inputs, TF32 math, bf16 output (odd head dims)
   EC_FAIL("unknown precision");
 }
 

@@ -135,6 +135,7 @@ struct AttnArgs {
   const int* x_len;      // [B] valid frames at this stage, or nullptr
   int B, T, D, H, G;
   void* out; int ld_out; // [B*T, D] activation type
+  int in_f32;            // EC_PREC_BF16 only: q|k|v / E are fp32 (odd head dims fall back to the TF32 kernel with bf16 output)
 };
 int launch_relpos_attention(int precision, const AttnArgs& a, cudaStream_t stream);
 int launch_relpos_attention_bf16(const AttnArgs& a, cudaStream_t stream);

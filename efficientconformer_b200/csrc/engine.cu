@@ -400,7 +400,7 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
     const int D = bc.dim_model, T = sh.t_in[i], G = bc.group_size, P = (G - T % G) % G, e_rows = 2 * (T + P) - G;
     EC_REQUIRE(relpos[i] != nullptr, "missing relative position table");
     float* eb = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws.ebuf) + i * ws.e_stride);
-    const bool a16 = prec == EC_PREC_BF16;
+    const bool a16 = prec == EC_PREC_BF16 && ((G * D) / bc.num_heads) % 2 == 0 && D % 2 == 0;
     EC_TRY(gemm(e, e->side, PC_POS, relpos[i], w.blk[i].wpos, e_rows, D, D, w.blk[i].bpos, 1.f, GEMM_ACT_NONE, nullptr, a16 ? nullptr : eb,
                 a16 ? eb : nullptr, 0, 0, nullptr, 1));
   }
@@ -445,13 +445,13 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
     // MHSA: x2 = x1 + Wo attn(LN(x1))                   [fused: epilogue emits xn = LN_conv(x2) and the strided copy xs]
     if (!fuse) EC_TRY(lnorm(e, st, x, M, D, b.att_ln_w, b.att_ln_b, ws.xn, nullptr));
     // q|k|v and E feed the attention kernel: TF32-rounded fp32 in parity mode, bf16 in fast mode
-    const bool a16 = prec == EC_PREC_BF16;
+    const bool a16 = prec == EC_PREC_BF16 && ((bc.group_size * D) / bc.num_heads) % 2 == 0 && D % 2 == 0;
     EC_TRY(gemm(e, st, PC_QKV, ws.xn, b.wqkv, M, 3 * D, D, b.bqkv, 1.f, GEMM_ACT_NONE, nullptr, a16 ? nullptr : ws.qkv, a16 ? ws.qkv : nullptr, 0, 0, nullptr, 1));
     const int G = bc.group_size, P = (G - T % G) % G, e_rows = 2 * (T + P) - G;
     if (!joined) { EC_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0)); joined = true; }     // join: E_i of every block is ready
     {
       const float* eb = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(ws.ebuf) + i * ws.e_stride);
-      AttnArgs aa{ws.qkv, eb, b.u, b.v, lens, B, T, D, bc.num_heads, G, ws.o, D};
+      AttnArgs aa{ws.qkv, eb, b.u, b.v, lens, B, T, D, bc.num_heads, G, ws.o, D, (prec == EC_PREC_BF16 && !a16) ? 1 : 0};
       const double Tg = static_cast<double>(T + P) / G, dh = static_cast<double>(G) * D / bc.num_heads;
       ProfScope ps(e, st, PC_ATTN, B * bc.num_heads * (4.0 * Tg * Tg * dh + 2.0 * Tg * (2 * Tg - 1) * dh),
                    4.0 * M * 3 * D + 4.0 * e_rows * D + es * M * D);
@@ -609,7 +609,7 @@ int ec_op_fold_bn(const float* w, const float* b, const float* g, const float* b
 }
 int ec_op_relpos_attention(int precision, const void* qkv, const void* E, const float* u, const float* v, const int32_t* x_len,
                            int batch, int t, int dim, int heads, int group, void* out, void* stream) {
-  AttnArgs a{qkv, E, u, v, x_len, batch, t, dim, heads, group, out, dim};
+  AttnArgs a{qkv, E, u, v, x_len, batch, t, dim, heads, group, out, dim, 0};
   return launch_relpos_attention(precision, a, reinterpret_cast<cudaStream_t>(stream));
 }
 int ec_op_dwconv_bn_swish(int precision, const void* x, const float* w_folded, const float* b_folded, int batch, int t, int channels,

@@ -235,6 +235,28 @@ def test_execution_options_do_not_change_results(sd, fuse_ln, pdl):
     assert rel_l2(ref_gpu, ref) < TOL_TF32
 
 
+def test_other_config_transducer_small_encoder():
+    """A second shipped encoder config (EfficientConformerTransducerSmall: dims [100,140,200], head dims 75/35/50 -- odd, not
+    multiples of 8) through the same engine in parity mode, against the oracle with seeded weights."""
+    from efficientconformer_b200 import ConformerEncoder
+    from oracle import conformer_oracle as O
+    p2 = dict(P, dim_model=[100, 140, 200], subsampling_filters=[100])
+    sd2 = seeded_state_dict(p2, None, seed=5)
+    enc = ConformerEncoder(p2, precision="tf32")
+    enc.load_state_dict(sd2, strict=False)
+    enc = enc.to(DEV).eval()
+    mel = synthetic_mel(3, 257, seed=13)
+    mel_len = torch.tensor([257, 200, 31])
+    x, x_len, _ = enc.forward_mel(mel.to(DEV), mel_len.to(DEV))
+    ref, ref_len = O.encoder_forward_mel(sd2, p2, mel, mel_len)
+    assert torch.equal(x_len.cpu(), ref_len)
+    assert rel_l2(x, ref) < TOL_TF32
+    with pytest.raises(RuntimeError, match="16 bytes"):          # bf16 rows of 100 elements are not TMA-addressable: loud, no fallback
+        enc16 = ConformerEncoder(p2, precision="bf16")
+        enc16.load_state_dict(sd2, strict=False)
+        enc16.to(DEV).eval().forward_mel(mel.to(DEV), mel_len.to(DEV))
+
+
 def test_no_fallback_paths(sd):
     from efficientconformer_b200 import ConformerEncoder
     enc = ConformerEncoder(P)

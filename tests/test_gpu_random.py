@@ -79,6 +79,8 @@ def test_random_attention_shapes(ops, prec):
         D, H, G = rng.choice([(120, 4, 3), (168, 4, 1), (240, 4, 1), (100, 4, 3), (256, 4, 1)])
         T = rng.choice([1, 2, 3, 5, 63, 64, 65, 128, 191, 192, 193, 400])
         B = rng.choice([1, 2, 3])
+        if prec == "bf16" and ((G * D) // H) % 2:
+            continue                                      # odd head dims take the TF32 kernel inside the engine
         g = torch.Generator().manual_seed(500 + trial)
         qkv = rnd(prec, torch.randn(B, T, 3 * D, generator=g)).to(DEV)
         Tp = T + (-T) % G
