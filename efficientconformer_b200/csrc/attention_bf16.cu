@@ -69,26 +69,32 @@ __global__ void __launch_bounds__(128, 2) relpos_attn_bf16_kernel(const AttnDevB
   __syncthreads();
   const int xl = p.x_len != nullptr ? p.x_len[b] : T;
   const __nv_bfloat16* qkv_b = p.qkv + static_cast<size_t>(b) * T * row3;
-  const bool wide = (d % 4 == 0) && (D % 4 == 0);    // 8-byte copies (4 features) stay inside a frame and aligned
-  const int step = wide ? 2 : 1;                     // pairs per copy
-  const int cbytes = wide ? 8 : 4;
+  // Staging map: every thread owns ONE feature pair (column) and walks the rows, so the (frame offset, channel) lookup, the
+  // u / v biases and all column predicates are loop invariants; per copy only the row address and bounds change.
+  constexpr int RPP = 128 / PR;                      // rows covered per pass by the PR*RPP active threads
+  const bool stager = tid < PR * RPP;
+  const int pr = tid % PR, rsub = tid / PR;
+  const int2 te = tab[pr];
+  const bool col_ok = stager && te.x >= 0;
 
-  // ---- stage Qu / Qv = bf16(q + u), bf16(q + v) ----
-  for (int idx = tid; idx < kBM * PR; idx += 128) {
-    const int r = idx / PR, pr = idx % PR;
-    const int i = i0 + r;
-    const int2 e = tab[pr];
-    float2 q = make_float2(0.f, 0.f);
-    uint32_t qu = 0, qv = 0;
-    if (e.x >= 0 && i < Tg) {
-      const int frame = i * G + e.x;
-      if (frame < T) q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qkv_b + frame * row3 + e.y));
-      const float2 uu = __ldg(reinterpret_cast<const float2*>(p.u + e.y)), vv = __ldg(reinterpret_cast<const float2*>(p.v + e.y));
-      qu = pack_bf16(q.x + uu.x, q.y + uu.y);
-      qv = pack_bf16(q.x + vv.x, q.y + vv.y);
+  // ---- stage Qu / Qv = bf16(q + u), bf16(q + v): independent loads, 4 rows in flight ----
+  if (stager) {
+    float2 uu = make_float2(0.f, 0.f), vv = uu;
+    if (col_ok) { uu = __ldg(reinterpret_cast<const float2*>(p.u + te.y)); vv = __ldg(reinterpret_cast<const float2*>(p.v + te.y)); }
+#pragma unroll 4
+    for (int r = rsub; r < kBM; r += RPP) {
+      const int i = i0 + r;
+      uint32_t qu = 0, qv = 0;
+      if (col_ok && i < Tg) {
+        const int frame = i * G + te.x;
+        float2 q = make_float2(0.f, 0.f);
+        if (frame < T) q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qkv_b + frame * row3 + te.y));
+        qu = pack_bf16(q.x + uu.x, q.y + uu.y);
+        qv = pack_bf16(q.x + vv.x, q.y + vv.y);
+      }
+      *reinterpret_cast<uint32_t*>(Qu + r * STR + 2 * pr) = qu;
+      *reinterpret_cast<uint32_t*>(Qv + r * STR + 2 * pr) = qv;
     }
-    *reinterpret_cast<uint32_t*>(Qu + r * STR + 2 * pr) = qu;
-    *reinterpret_cast<uint32_t*>(Qv + r * STR + 2 * pr) = qv;
   }
 
   float o[2 * KT][4];
@@ -102,24 +108,21 @@ __global__ void __launch_bounds__(128, 2) relpos_attn_bf16_kernel(const AttnDevB
   for (int j0 = 0; j0 < Tg; j0 += kBN) {
     __syncthreads();
     const int ebase = Tg - 1 + j0 - i0 - (kBM - 1);
-    for (int idx = tid * step; idx < kBN * PR; idx += 128 * step) {
-      const int r = idx / PR, pr = idx % PR;
-      const int j = j0 + r;
-      const int2 e = tab[pr];
-      const __nv_bfloat16* src = qkv_b;
-      uint32_t bytes = 0;
-      if (e.x >= 0 && j < Tg) {
-        const int frame = j * G + e.x;
-        if (frame < T) { src = qkv_b + frame * row3 + D + e.y; bytes = cbytes; }
+    if (stager) {
+      const __nv_bfloat16* kcol = qkv_b + D + te.y;
+      for (int r = rsub; r < kBN; r += RPP) {
+        const int j = j0 + r, frame = j * G + te.x;
+        const bool ok = col_ok && j < Tg && frame < T;
+        const __nv_bfloat16* src = ok ? kcol + frame * row3 : qkv_b;
+        cp_async_b(smem_u32(Ks + r * STR + 2 * pr), src, ok ? 4u : 0u, 4);
+        cp_async_b(smem_u32(Vs + r * STR + 2 * pr), src + D, ok ? 4u : 0u, 4);
       }
-      cp_async_b(smem_u32(Ks + r * STR + 2 * pr), src, bytes, cbytes);
-      cp_async_b(smem_u32(Vs + r * STR + 2 * pr), src + D, bytes, cbytes);
-    }
-    for (int idx = tid * step; idx < 128 * PR; idx += 128 * step) {
-      const int r = idx / PR, pr = idx % PR;
-      const int ee = ebase + r;
-      const bool ok = 2 * pr < d && ee >= 0 && ee <= 2 * Tg - 2;
-      cp_async_b(smem_u32(Es + r * STR + 2 * pr), ok ? p.E + ee * e_row + f0 + 2 * pr : p.E, ok ? cbytes : 0u, cbytes);
+      const __nv_bfloat16* ecol = p.E + f0 + 2 * pr;
+      for (int r = rsub; r < 128; r += RPP) {
+        const int ee = ebase + r;
+        const bool ok = col_ok && ee >= 0 && ee <= 2 * Tg - 2;
+        cp_async_b(smem_u32(Es + r * STR + 2 * pr), ok ? ecol + ee * e_row : p.E, ok ? 4u : 0u, 4);
+      }
     }
     cp_async_wait_all_b();
     __syncthreads();
