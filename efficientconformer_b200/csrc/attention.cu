@@ -78,23 +78,30 @@ __global__ void __launch_bounds__(128) relpos_attn_kernel(const AttnDev p) {
   };
 
   // ---- stage Qu / Qv (q + u, q + v rounded to tf32): 8-byte loads, 8 pairs in flight per thread ----
+  // vec2 staging map: every thread owns one feature pair (column) and walks the rows -> lookups and biases are loop invariant
+  constexpr int PRc = DP / 2, RPP = 128 / PRc;
+  const bool stager = tid < PRc * RPP;
+  const int prc = tid % PRc, rsub = tid / PRc, cc = 2 * prc;
+  int cfoff = 0, cch = 0;
+  if (cc < d) locate(cc, cfoff, cch);
+  const bool col_ok = stager && cc < d;
   if (vec2) {
-    constexpr int PR = DP / 2;
+    if (stager) {
+      float2 uu = make_float2(0.f, 0.f), vv = uu;
+      if (col_ok) { uu = __ldg(reinterpret_cast<const float2*>(p.u + cch)); vv = __ldg(reinterpret_cast<const float2*>(p.v + cch)); }
 #pragma unroll 4
-    for (int idx = tid; idx < kAttBM * PR; idx += 128) {
-      const int r = idx / PR, c = (idx % PR) * 2;
-      const int i = i0 + r;
-      float2 qu = make_float2(0.f, 0.f), qv = qu;
-      if (c < d && i < Tg) {
-        int foff, ch; locate(c, foff, ch);
-        const int frame = i * G + foff;
-        float2 q = make_float2(0.f, 0.f);                       // appended pad frames are exact zeros
-        if (frame < T) q = __ldg(reinterpret_cast<const float2*>(qkv_b + frame * row3 + ch));
-        const float2 uu = __ldg(reinterpret_cast<const float2*>(p.u + ch)), vv = __ldg(reinterpret_cast<const float2*>(p.v + ch));
-        qu = make_float2(q.x + uu.x, q.y + uu.y); qv = make_float2(q.x + vv.x, q.y + vv.y);
+      for (int r = rsub; r < kAttBM; r += RPP) {
+        const int i = i0 + r;
+        float2 qu = make_float2(0.f, 0.f), qv = qu;
+        if (col_ok && i < Tg) {
+          const int frame = i * G + cfoff;
+          float2 q = make_float2(0.f, 0.f);                     // appended pad frames are exact zeros
+          if (frame < T) q = __ldg(reinterpret_cast<const float2*>(qkv_b + frame * row3 + cch));
+          qu = make_float2(q.x + uu.x, q.y + uu.y); qv = make_float2(q.x + vv.x, q.y + vv.y);
+        }
+        *reinterpret_cast<float2*>(Qu + r * STR + cc) = make_float2(round_tf32(qu.x), round_tf32(qu.y));
+        *reinterpret_cast<float2*>(Qv + r * STR + cc) = make_float2(round_tf32(qv.x), round_tf32(qv.y));
       }
-      *reinterpret_cast<float2*>(Qu + r * STR + c) = make_float2(round_tf32(qu.x), round_tf32(qu.y));
-      *reinterpret_cast<float2*>(Qv + r * STR + c) = make_float2(round_tf32(qv.x), round_tf32(qv.y));
     }
   } else {
     for (int idx = tid; idx < kAttBM * DP; idx += 128) {
@@ -127,25 +134,21 @@ __global__ void __launch_bounds__(128) relpos_attn_kernel(const AttnDev p) {
     // K / V / E arrive already rounded to TF32 by the producing GEMM epilogues (round_out), so no register pass is needed.
     const int ebase = Tg - 1 + j0 - i0 - (kAttBM - 1);
     if (vec2) {
-      constexpr int PR = DP / 2;
-      for (int idx = tid; idx < kAttBN * PR; idx += 128) {
-        const int r = idx / PR, c = (idx % PR) * 2;
-        const int j = j0 + r;
-        const float* src = qkv_b;
-        uint32_t bytes = 0;
-        if (c < d && j < Tg) {
-          int foff, ch; locate(c, foff, ch);
-          const int frame = j * G + foff;
-          if (frame < T) { src = qkv_b + frame * row3 + D + ch; bytes = 8; }
+      if (stager) {
+        const float* kcol = qkv_b + D + cch;
+        for (int r = rsub; r < kAttBN; r += RPP) {
+          const int j = j0 + r, frame = j * G + cfoff;
+          const bool ok = col_ok && j < Tg && frame < T;
+          const float* src = ok ? kcol + frame * row3 : qkv_b;
+          cp_async_8(smem_u32(Ks + r * STR + cc), src, ok ? 8u : 0u);
+          cp_async_8(smem_u32(Vs + r * STR + cc), src + D, ok ? 8u : 0u);
         }
-        cp_async_8(smem_u32(Ks + r * STR + c), src, bytes);
-        cp_async_8(smem_u32(Vs + r * STR + c), src + D, bytes);
-      }
-      for (int idx = tid; idx < 128 * PR; idx += 128) {
-        const int r = idx / PR, c = (idx % PR) * 2;
-        const int e = ebase + r;
-        const bool ok = c < d && e >= 0 && e <= 2 * Tg - 2;
-        cp_async_8(smem_u32(Es + r * STR + c), ok ? p.E + e * e_row + f0 + c : p.E, ok ? 8u : 0u);
+        const float* ecol = p.E + f0 + cc;
+        for (int r = rsub; r < 128; r += RPP) {
+          const int e = ebase + r;
+          const bool ok = col_ok && e >= 0 && e <= 2 * Tg - 2;
+          cp_async_8(smem_u32(Es + r * STR + cc), ok ? ecol + e * e_row : p.E, ok ? 8u : 0u);
+        }
       }
     } else {
       for (int idx = tid; idx < kAttBN * DP; idx += 128) {
