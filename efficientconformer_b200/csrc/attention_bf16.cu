@@ -77,26 +77,6 @@ __global__ void __launch_bounds__(128, 2) relpos_attn_bf16_kernel(const AttnDevB
   const int2 te = tab[pr];
   const bool col_ok = stager && te.x >= 0;
 
-  // ---- stage Qu / Qv = bf16(q + u), bf16(q + v): independent loads, 4 rows in flight ----
-  if (stager) {
-    float2 uu = make_float2(0.f, 0.f), vv = uu;
-    if (col_ok) { uu = __ldg(reinterpret_cast<const float2*>(p.u + te.y)); vv = __ldg(reinterpret_cast<const float2*>(p.v + te.y)); }
-#pragma unroll 4
-    for (int r = rsub; r < kBM; r += RPP) {
-      const int i = i0 + r;
-      uint32_t qu = 0, qv = 0;
-      if (col_ok && i < Tg) {
-        const int frame = i * G + te.x;
-        float2 q = make_float2(0.f, 0.f);
-        if (frame < T) q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qkv_b + frame * row3 + te.y));
-        qu = pack_bf16(q.x + uu.x, q.y + uu.y);
-        qv = pack_bf16(q.x + vv.x, q.y + vv.y);
-      }
-      *reinterpret_cast<uint32_t*>(Qu + r * STR + 2 * pr) = qu;
-      *reinterpret_cast<uint32_t*>(Qv + r * STR + 2 * pr) = qv;
-    }
-  }
-
   float o[2 * KT][4];
 #pragma unroll
   for (int n = 0; n < 2 * KT; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
@@ -105,17 +85,16 @@ __global__ void __launch_bounds__(128, 2) relpos_attn_bf16_kernel(const AttnDevB
   const int eo = (3 - w) * 16;
   const size_t e_row = static_cast<size_t>(G) * D;
 
-  for (int j0 = 0; j0 < Tg; j0 += kBN) {
-    __syncthreads();
-    const int ebase = Tg - 1 + j0 - i0 - (kBM - 1);
+  // Copy schedule (no second buffer): K and the E band of tile j+1 are fetched while tile j does softmax and P.V; V of tile j
+  // is fetched while tile j does its two score products.  Every cp.async batch therefore has a compute phase to hide behind.
+  auto issue_ke = [&](int j0) {
     if (stager) {
+      const int ebase = Tg - 1 + j0 - i0 - (kBM - 1);
       const __nv_bfloat16* kcol = qkv_b + D + te.y;
       for (int r = rsub; r < kBN; r += RPP) {
         const int j = j0 + r, frame = j * G + te.x;
         const bool ok = col_ok && j < Tg && frame < T;
-        const __nv_bfloat16* src = ok ? kcol + frame * row3 : qkv_b;
-        cp_async_b(smem_u32(Ks + r * STR + 2 * pr), src, ok ? 4u : 0u, 4);
-        cp_async_b(smem_u32(Vs + r * STR + 2 * pr), src + D, ok ? 4u : 0u, 4);
+        cp_async_b(smem_u32(Ks + r * STR + 2 * pr), ok ? kcol + frame * row3 : qkv_b, ok ? 4u : 0u, 4);
       }
       const __nv_bfloat16* ecol = p.E + f0 + 2 * pr;
       for (int r = rsub; r < 128; r += RPP) {
@@ -124,8 +103,53 @@ __global__ void __launch_bounds__(128, 2) relpos_attn_bf16_kernel(const AttnDevB
         cp_async_b(smem_u32(Es + r * STR + 2 * pr), ok ? ecol + ee * e_row : p.E, ok ? 4u : 0u, 4);
       }
     }
-    cp_async_wait_all_b();
-    __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto issue_v = [&](int j0) {
+    if (stager) {
+      const __nv_bfloat16* vcol = qkv_b + 2 * D + te.y;
+      for (int r = rsub; r < kBN; r += RPP) {
+        const int j = j0 + r, frame = j * G + te.x;
+        const bool ok = col_ok && j < Tg && frame < T;
+        cp_async_b(smem_u32(Vs + r * STR + 2 * pr), ok ? vcol + frame * row3 : qkv_b, ok ? 4u : 0u, 4);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue_ke(0);
+
+  // ---- stage Qu / Qv = bf16(q + u), bf16(q + v): all of a thread's rows are loaded before the first use ----
+  if (stager) {
+    constexpr int NR = (kBM + RPP - 1) / RPP;
+    float2 uu = make_float2(0.f, 0.f), vv = uu;
+    if (col_ok) { uu = __ldg(reinterpret_cast<const float2*>(p.u + te.y)); vv = __ldg(reinterpret_cast<const float2*>(p.v + te.y)); }
+    uint32_t qraw[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      const int i = i0 + rsub + k * RPP, frame = i * G + te.x;
+      qraw[k] = 0u;
+      if (col_ok && rsub + k * RPP < kBM && i < Tg && frame < T) qraw[k] = __ldg(reinterpret_cast<const uint32_t*>(qkv_b + frame * row3 + te.y));
+    }
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      const int r = rsub + k * RPP, i = i0 + r;
+      if (r < kBM) {
+        uint32_t qu = 0, qv = 0;
+        if (col_ok && i < Tg) {
+          const float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qraw[k]));
+          qu = pack_bf16(q.x + uu.x, q.y + uu.y);
+          qv = pack_bf16(q.x + vv.x, q.y + vv.y);
+        }
+        *reinterpret_cast<uint32_t*>(Qu + r * STR + 2 * pr) = qu;
+        *reinterpret_cast<uint32_t*>(Qv + r * STR + 2 * pr) = qv;
+      }
+    }
+  }
+
+  for (int j0 = 0; j0 < Tg; j0 += kBN) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                 // K / E of this tile (and Q on the first pass) visible; P.V of the last tile done
+    issue_v(j0);
 
     // ---- G = Qv_w . Eband_w^T (16 x 80) -> per-warp fp32 strip ----
     {
@@ -150,8 +174,6 @@ __global__ void __launch_bounds__(128, 2) relpos_attn_bf16_kernel(const AttnDevB
         g0[8 * kBGStride] = acc[n][2]; g0[8 * kBGStride + 1] = acc[n][3];
       }
     }
-    __syncwarp();
-
     // ---- S = Qu_w . K^T (16 x 64) ----
     float s[kBN / 8][4];
 #pragma unroll
@@ -167,6 +189,9 @@ __global__ void __launch_bounds__(128, 2) relpos_attn_bf16_kernel(const AttnDevB
         mma_bf16(s[n], a0, a1, a2, a3, *reinterpret_cast<const uint32_t*>(kb), *reinterpret_cast<const uint32_t*>(kb + 8));
       }
     }
+    __syncthreads();                                 // every warp is done with K and the E band
+    if (j0 + kBN < Tg) issue_ke(j0 + kBN);
+    else asm volatile("cp.async.commit_group;" ::: "memory");      // keeps the group count uniform for the wait below
     // ---- relative shift, scale, key mask ----
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
@@ -205,6 +230,8 @@ __global__ void __launch_bounds__(128, 2) relpos_attn_bf16_kernel(const AttnDevB
     }
 #pragma unroll
     for (int n = 0; n < 2 * KT; ++n) { o[n][0] *= corr[0]; o[n][1] *= corr[0]; o[n][2] *= corr[1]; o[n][3] *= corr[1]; }
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();                                 // V of this tile visible
     // ---- O += P . V : P accumulators of two adjacent key n-tiles form one 16-key A fragment; V^T via ldmatrix.trans ----
 #pragma unroll
     for (int kt2 = 0; kt2 < kBN / 16; ++kt2) {
