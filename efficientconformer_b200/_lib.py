@@ -62,11 +62,15 @@ _SIGNATURES = {
     "ec_engine_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                          C.POINTER(C.c_int32)]),
     "ec_engine_set_fuse_ln": (C.c_int, [C.c_void_p, C.c_int]),
+    "ec_engine_set_fuse_ffn": (C.c_int, [C.c_void_p, C.c_int]),
     "ec_set_pdl": (C.c_int, [C.c_int]),
     "ec_debug_gemm_timeline": (C.c_int, [C.c_int, C.POINTER(C.c_ulonglong)]),
+    "ec_debug_ffn_timeline": (C.c_int, [C.c_int, C.POINTER(C.c_ulonglong)]),
     "ec_op_gemm_ln": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                 C.c_int, C.c_void_p]),
+    "ec_op_ffn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                            C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
     "ec_ctc_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "ec_ctc_loss": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -2,7 +2,8 @@
 //
 // Same algorithm and indexing as attention.cu (reference models/attentions.py:549-620, 645-718; closed form in SURVEY.md
 // section 8 row a9) with bf16 q|k|v and E produced directly by the QKV / pos GEMM epilogues:
-//   * all operand tiles live in shared memory as bf16 (half the footprint of the TF32 kernel -> 2 CTAs per SM),
+//   * K / V / E-band tiles live in shared memory as bf16, the query tile in registers (A fragments) -> 3-4 CTAs per SM, which
+//     is what lets the 384 / 512 CTA grids of the first two stages run as a single wave,
 //   * mma.sync m16n8k16 bf16 with fp32 accumulation; fp32 online softmax; P is re-packed from the accumulator layout
 //     straight into A fragments; V^T fragments come from ldmatrix.trans,
 //   * K / V / E staging with cp.async (4- or 8-byte copies, zero fill) driven by a per-head (frame offset, channel)
@@ -40,17 +41,22 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 constexpr int kBM = 64, kBN = 64, kBGW = 80, kBGStride = 81;
 
+constexpr int attn_ctas_per_sm(int KT) { return KT <= 3 ? 4 : 3; }
+
 template <int KT, typename OutT>     // KT = k-tiles of 16 covering the head dim
-__global__ void __launch_bounds__(128, 2) relpos_attn_bf16_kernel(const AttnDevB p) {
+__global__ void __launch_bounds__(128, attn_ctas_per_sm(KT)) relpos_attn_bf16_kernel(const AttnDevB p) {
   constexpr int DP = KT * 16, STR = DP + 8;          // bf16 elements; row pitch 2*STR bytes keeps 32-bit fragment loads conflict-free
   constexpr int PR = DP / 2;                         // bf16 pairs per row
   extern __shared__ __align__(16) uint8_t smb[];
-  __nv_bfloat16* Qu = reinterpret_cast<__nv_bfloat16*>(smb);
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smb);
+  __nv_bfloat16* Es = Ks + kBN * STR;
+  __nv_bfloat16* Vs = Es + 128 * STR;
+  float* Gs = reinterpret_cast<float*>(Vs + kBN * STR);
+  // The query tile only passes through shared memory once (gather + bias add), then lives in A fragments for the whole key
+  // loop; its staging area aliases V and the score strip, which are first written after the fragments have been read.
+  __nv_bfloat16* Qu = Vs;
   __nv_bfloat16* Qv = Qu + kBM * STR;
-  __nv_bfloat16* Ks = Qv + kBM * STR;
-  __nv_bfloat16* Vs = Ks + kBN * STR;
-  __nv_bfloat16* Es = Vs + kBN * STR;
-  float* Gs = reinterpret_cast<float*>(Es + 128 * STR);
+  static_assert(sizeof(__nv_bfloat16) * kBM * STR <= sizeof(float) * 4 * 16 * kBGStride, "Q staging must fit in V + strip");
   int2* tab = reinterpret_cast<int2*>(Gs + 4 * 16 * kBGStride);     // [PR] (frame offset, channel) of feature pair c
 
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -146,6 +152,18 @@ __global__ void __launch_bounds__(128, 2) relpos_attn_bf16_kernel(const AttnDevB
     }
   }
 
+  __syncthreads();
+  uint32_t qu[KT][4], qv[KT][4];
+#pragma unroll
+  for (int kt = 0; kt < KT; ++kt) {
+    const __nv_bfloat16* qa = Qu + (w * 16 + g) * STR + kt * 16 + 2 * t;
+    const __nv_bfloat16* qb = Qv + (w * 16 + g) * STR + kt * 16 + 2 * t;
+    qu[kt][0] = *reinterpret_cast<const uint32_t*>(qa); qu[kt][1] = *reinterpret_cast<const uint32_t*>(qa + 8 * STR);
+    qu[kt][2] = *reinterpret_cast<const uint32_t*>(qa + 8); qu[kt][3] = *reinterpret_cast<const uint32_t*>(qa + 8 * STR + 8);
+    qv[kt][0] = *reinterpret_cast<const uint32_t*>(qb); qv[kt][1] = *reinterpret_cast<const uint32_t*>(qb + 8 * STR);
+    qv[kt][2] = *reinterpret_cast<const uint32_t*>(qb + 8); qv[kt][3] = *reinterpret_cast<const uint32_t*>(qb + 8 * STR + 8);
+  }
+
   for (int j0 = 0; j0 < Tg; j0 += kBN) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();                                 // K / E of this tile (and Q on the first pass) visible; P.V of the last tile done
@@ -158,9 +176,7 @@ __global__ void __launch_bounds__(128, 2) relpos_attn_bf16_kernel(const AttnDevB
       for (int n = 0; n < kBGW / 8; ++n) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f; }
 #pragma unroll
       for (int kt = 0; kt < KT; ++kt) {
-        const __nv_bfloat16* qa = Qv + (w * 16 + g) * STR + kt * 16 + 2 * t;
-        const uint32_t a0 = *reinterpret_cast<const uint32_t*>(qa), a1 = *reinterpret_cast<const uint32_t*>(qa + 8 * STR);
-        const uint32_t a2 = *reinterpret_cast<const uint32_t*>(qa + 8), a3 = *reinterpret_cast<const uint32_t*>(qa + 8 * STR + 8);
+        const uint32_t a0 = qv[kt][0], a1 = qv[kt][1], a2 = qv[kt][2], a3 = qv[kt][3];
 #pragma unroll
         for (int n = 0; n < kBGW / 8; ++n) {
           const __nv_bfloat16* eb = Es + (eo + n * 8 + g) * STR + kt * 16 + 2 * t;
@@ -180,9 +196,7 @@ __global__ void __launch_bounds__(128, 2) relpos_attn_bf16_kernel(const AttnDevB
     for (int n = 0; n < kBN / 8; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; }
 #pragma unroll
     for (int kt = 0; kt < KT; ++kt) {
-      const __nv_bfloat16* qa = Qu + (w * 16 + g) * STR + kt * 16 + 2 * t;
-      const uint32_t a0 = *reinterpret_cast<const uint32_t*>(qa), a1 = *reinterpret_cast<const uint32_t*>(qa + 8 * STR);
-      const uint32_t a2 = *reinterpret_cast<const uint32_t*>(qa + 8), a3 = *reinterpret_cast<const uint32_t*>(qa + 8 * STR + 8);
+      const uint32_t a0 = qu[kt][0], a1 = qu[kt][1], a2 = qu[kt][2], a3 = qu[kt][3];
 #pragma unroll
       for (int n = 0; n < kBN / 8; ++n) {
         const __nv_bfloat16* kb = Ks + (n * 8 + g) * STR + kt * 16 + 2 * t;
@@ -279,7 +293,7 @@ __global__ void __launch_bounds__(128, 2) relpos_attn_bf16_kernel(const AttnDevB
 template <int KT, typename OutT>
 static int launch_inst(const AttnDevB& p, cudaStream_t stream) {
   constexpr int STR = KT * 16 + 8;
-  const size_t smem = sizeof(__nv_bfloat16) * (static_cast<size_t>(kBM) * STR * 2 + kBN * STR * 2 + 128 * STR) +
+  const size_t smem = sizeof(__nv_bfloat16) * (static_cast<size_t>(kBN) * STR * 2 + 128 * STR) +
                       sizeof(float) * 4 * 16 * kBGStride + sizeof(int2) * (KT * 8) + 16;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;

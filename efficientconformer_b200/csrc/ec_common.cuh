@@ -49,6 +49,21 @@ int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cud
   return EC_OK;
 }
 
+// Same, as thread-block clusters of `cluster_x` CTAs along x.
+template <typename... KArgs, typename... Args>
+int launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  EC_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+  return EC_OK;
+}
+
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int round_up(int a, int b) { return cdiv(a, b) * b; }
 inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
@@ -118,6 +133,24 @@ struct GemmArgs {
 };
 int launch_gemm(int precision, const GemmArgs& a, cudaStream_t stream);
 int gemm_timeline(int enable, unsigned long long* out12);
+
+// Fused feed-forward module (bf16 operands): out = residual + 0.5 * (Swish(x_act W1^T + b1) W2^T + b2), then
+// mode 1: ln_out = LN1(out);  mode 2: out <- LN1(out), ln_out = LN2(out) (plain rounded copy when ln2_g == nullptr).
+struct FfnArgs {
+  const void* x_act;     // [M, D] bf16 (LayerNorm output of the module)
+  const void* w1;        // [hidden, D] bf16
+  const void* w2;        // [D, hidden] bf16
+  const float *b1, *b2;
+  int M, D, hidden;
+  const float* residual; // [M, D] fp32
+  float* out_f32;        // [M, D] fp32
+  int ln_mode; const float *ln1_g, *ln1_b, *ln2_g, *ln2_b; float ln_eps;
+  void* ln_out;          // [M, D] bf16 (may alias x_act)
+  int cluster;           // CTAs per row tile (1, 2, 4); 0 = choose
+};
+int launch_ffn_fused(const FfnArgs& a, cudaStream_t stream);
+int ffn_timeline(int enable, unsigned long long* out192);
+bool ffn_fused_fits(int M, int D, int hidden);   // shape supported by the fused kernel
 
 struct LayerNormArgs {
   const float* x; int rows, dim;

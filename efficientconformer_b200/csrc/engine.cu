@@ -49,10 +49,10 @@ struct Weights {
 namespace ec {
 // kernel categories of one forward (profiling / launch accounting)
 enum ProfCat { PC_SUBSAMPLE = 0, PC_LIN, PC_LAYERNORM, PC_FFN_W1, PC_FFN_W2, PC_QKV, PC_POS, PC_ATTN, PC_OUT, PC_PW1_GLU, PC_DWCONV,
-               PC_RES, PC_PW2, PC_FC, PC_MISC, PC_COUNT };
+               PC_RES, PC_PW2, PC_FC, PC_MISC, PC_FFN_FUSED, PC_COUNT };
 static const char* kProfNames[PC_COUNT] = {"subsample_conv", "gemm_sub_linear", "layernorm", "gemm_ffn_w1_swish", "gemm_ffn_w2_res",
                                            "gemm_qkv", "gemm_pos", "relpos_attention", "gemm_att_out_res", "gemm_pw1_glu",
-                                           "dwconv_bn_swish", "gemm_conv_res", "gemm_pw2_res", "gemm_fc", "misc"};
+                                           "dwconv_bn_swish", "gemm_conv_res", "gemm_pw2_res", "gemm_fc", "misc", "ffn_fused"};
 struct ProfEntry { int cat; double flops, bytes; cudaEvent_t e0, e1; };
 }  // namespace ec
 
@@ -69,6 +69,7 @@ struct ec_engine {
   std::vector<cudaEvent_t> event_pool;
   size_t events_used = 0;
   int last_launches = 0;
+  bool fuse_ffn = true;    // bf16 mode: whole feed-forward module in one cluster kernel (needs fuse_ln)
   bool fuse_ln = true;     // LayerNorms in the epilogue of the producing GEMM (needs dim <= 256)
   // the positional projections E_i = pos_layer_i(R) depend on weights only: they run on a forked stream, off the critical path
   cudaStream_t side = nullptr;
@@ -222,6 +223,18 @@ static int gemm(ec_engine* e, cudaStream_t st, int cat, const void* A, const voi
                        ((out_f32 ? 4 : 0) + (out_act ? e->esize : 0) + (residual ? 4 : 0));
   ProfScope ps(e, st, cat, flops, bytes);
   return launch_gemm(e->precision, g, st);
+}
+// whole feed-forward module in one launch (bf16 mode)
+static int ffn_fused(ec_engine* e, cudaStream_t st, const void* x_act, const void* w1, const float* b1, const void* w2, const float* b2,
+                     int M, int D, int hidden, const float* residual, float* out_f32, const LnFuse& ln) {
+  FfnArgs f{};
+  f.x_act = x_act; f.w1 = w1; f.b1 = b1; f.w2 = w2; f.b2 = b2; f.M = M; f.D = D; f.hidden = hidden;
+  f.residual = residual; f.out_f32 = out_f32;
+  f.ln_mode = ln.mode; f.ln1_g = ln.g1; f.ln1_b = ln.b1; f.ln2_g = ln.g2; f.ln2_b = ln.b2; f.ln_eps = 1e-6f; f.ln_out = ln.y;
+  const double flops = 4.0 * M * D * hidden;
+  const double bytes = 2.0 * (static_cast<double>(M) * D + 2.0 * D * hidden) + static_cast<double>(M) * D * (4 + 4 + (ln.y ? 2 : 0));
+  ProfScope ps(e, st, PC_FFN_FUSED, flops, bytes);
+  return launch_ffn_fused(f, st);
 }
 static int lnorm(ec_engine* e, cudaStream_t st, const float* x, int rows, int dim, const float* g, const float* b, void* y_act,
                  float* y_f32, void* copy_out = nullptr, int copy_stride = 1, int fps = 0, int fops = 0) {
@@ -418,6 +431,10 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
   float* x = ws.xa; float* x_alt = ws.xb;
   bool fuse = e->fuse_ln;
   for (int i = 0; i < c.num_blocks; ++i) fuse = fuse && c.blocks[i].dim_model <= 256 && c.blocks[i].dim_expand <= 256;
+  bool fuse_ffn = fuse && e->fuse_ffn && prec == EC_PREC_BF16;
+  for (int i = 0; i < c.num_blocks && fuse_ffn; ++i)
+    fuse_ffn = ffn_fused_fits(B * sh.t_in[i], c.blocks[i].dim_model, c.blocks[i].ff_ratio * c.blocks[i].dim_model) &&
+               ffn_fused_fits(B * sh.t_out[i], c.blocks[i].dim_expand, c.blocks[i].ff_ratio * c.blocks[i].dim_expand);
   {
     LnFuse ln;   // fused: xn = LN_ffn1(x0) for block 0
     if (fuse) { ln.mode = 1; ln.g1 = w.blk[0].ffn1.ln_w; ln.b1 = w.blk[0].ffn1.ln_b; ln.y = ws.xn; }
@@ -435,8 +452,12 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
     const bool last = i == c.num_blocks - 1;
     // FFN1: x1 = x + 0.5 * W2 swish(W1 LN(x))          [fused: epilogue also emits xn = LN_att(x1)]
     if (!fuse) EC_TRY(lnorm(e, st, x, M, D, b.ffn1.ln_w, b.ffn1.ln_b, ws.xn, nullptr));
-    EC_TRY(gemm(e, st, PC_FFN_W1, ws.xn, b.ffn1.w1, M, Fr * D, D, b.ffn1.b1, 1.f, GEMM_ACT_SWISH, nullptr, nullptr, ws.h));
-    {
+    if (fuse_ffn) {
+      LnFuse ln;
+      ln.mode = 1; ln.g1 = b.att_ln_w; ln.b1 = b.att_ln_b; ln.y = ws.xn;
+      EC_TRY(ffn_fused(e, st, ws.xn, b.ffn1.w1, b.ffn1.b1, b.ffn1.w2, b.ffn1.b2, M, D, Fr * D, x, x_alt, ln));
+    } else {
+      EC_TRY(gemm(e, st, PC_FFN_W1, ws.xn, b.ffn1.w1, M, Fr * D, D, b.ffn1.b1, 1.f, GEMM_ACT_SWISH, nullptr, nullptr, ws.h));
       LnFuse ln;
       if (fuse) { ln.mode = 1; ln.g1 = b.att_ln_w; ln.b1 = b.att_ln_b; ln.y = ws.xn; }
       EC_TRY(gemm(e, st, PC_FFN_W2, ws.h, b.ffn1.w2, M, D, Fr * D, b.ffn1.b2, 0.5f, GEMM_ACT_NONE, x, x_alt, nullptr, 0, 0, &ln));
@@ -487,14 +508,15 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
     std::swap(x, x_alt);
     // FFN2 + block LayerNorm        [fused: epilogue normalises in place (block norm) and emits the next GEMM's operand]
     if (!fuse) EC_TRY(lnorm(e, st, x, Mo, De, b.ffn2.ln_w, b.ffn2.ln_b, ws.xn, nullptr));
-    EC_TRY(gemm(e, st, PC_FFN_W1, ws.xn, b.ffn2.w1, Mo, Fr * De, De, b.ffn2.b1, 1.f, GEMM_ACT_SWISH, nullptr, nullptr, ws.h));
+    if (!fuse_ffn) EC_TRY(gemm(e, st, PC_FFN_W1, ws.xn, b.ffn2.w1, Mo, Fr * De, De, b.ffn2.b1, 1.f, GEMM_ACT_SWISH, nullptr, nullptr, ws.h));
     float* y = (last && out_x != nullptr) ? out_x : x_alt;
     if (fuse) {
       LnFuse ln;
       ln.mode = 2; ln.g1 = b.norm_w; ln.b1 = b.norm_b;
       if (!last) { ln.g2 = w.blk[i + 1].ffn1.ln_w; ln.b2 = w.blk[i + 1].ffn1.ln_b; ln.y = ws.xn; }
       else { ln.g2 = nullptr; ln.b2 = nullptr; ln.y = logits != nullptr ? ws.xn : nullptr; }     // fc operand = rounded copy of the block output
-      EC_TRY(gemm(e, st, PC_FFN_W2, ws.h, b.ffn2.w2, Mo, De, Fr * De, b.ffn2.b2, 0.5f, GEMM_ACT_NONE, x, y, nullptr, 0, 0, &ln));
+      if (fuse_ffn) EC_TRY(ffn_fused(e, st, ws.xn, b.ffn2.w1, b.ffn2.b1, b.ffn2.w2, b.ffn2.b2, Mo, De, Fr * De, x, y, ln));
+      else EC_TRY(gemm(e, st, PC_FFN_W2, ws.h, b.ffn2.w2, Mo, De, Fr * De, b.ffn2.b2, 0.5f, GEMM_ACT_NONE, x, y, nullptr, 0, 0, &ln));
       if (!(last && out_x != nullptr)) x_alt = x, x = y;
     } else {
       EC_TRY(gemm(e, st, PC_FFN_W2, ws.h, b.ffn2.w2, Mo, De, Fr * De, b.ffn2.b2, 0.5f, GEMM_ACT_NONE, x, x_alt, nullptr));
@@ -518,7 +540,9 @@ const char* ec_profile_category_name(int cat) { return (cat >= 0 && cat < PC_COU
 int ec_engine_set_profiling(ec_engine* e, int enabled) { e->prof_enabled = enabled != 0; return EC_OK; }
 /* option 0: fuse LayerNorm into the GEMM epilogues (default 1).  Global option via ec_set_pdl: programmatic dependent launch. */
 int ec_engine_set_fuse_ln(ec_engine* e, int enabled) { e->fuse_ln = enabled != 0; return EC_OK; }
+int ec_engine_set_fuse_ffn(ec_engine* e, int enabled) { e->fuse_ffn = enabled != 0; return EC_OK; }
 int ec_debug_gemm_timeline(int enable, unsigned long long* out12) { return gemm_timeline(enable, out12); }
+int ec_debug_ffn_timeline(int enable, unsigned long long* out192) { return ffn_timeline(enable, out192); }
 int ec_set_pdl(int enabled) { g_pdl = enabled != 0 ? 1 : 0; return EC_OK; }
 int ec_engine_last_launches(const ec_engine* e) { return e->last_launches; }
 /* sums the CUDA-event durations of the last (eager, profiled) forward per category; synchronises the recorded events */
@@ -591,6 +615,15 @@ int ec_op_gemm_ln(int precision, const void* A, const void* W, int M, int N, int
   g.ln_mode = ln_mode; g.ln1_g = g1; g.ln1_b = b1; g.ln2_g = g2; g.ln2_b = b2; g.ln_eps = eps; g.ln_out = ln_out;
   g.copy_out = copy_out; g.copy_stride = copy_stride; g.frames_per_seq = frames_per_seq; g.frames_out_per_seq = frames_out_per_seq;
   return launch_gemm(precision, g, reinterpret_cast<cudaStream_t>(stream));
+}
+int ec_op_ffn(const void* x_act, const void* w1, const float* b1, const void* w2, const float* b2, int M, int D, int hidden,
+              const float* residual, float* out_f32, int ln_mode, const float* g1, const float* be1, const float* g2, const float* be2,
+              float eps, void* ln_out, int cluster, void* stream) {
+  FfnArgs f{};
+  f.x_act = x_act; f.w1 = w1; f.b1 = b1; f.w2 = w2; f.b2 = b2; f.M = M; f.D = D; f.hidden = hidden;
+  f.residual = residual; f.out_f32 = out_f32; f.ln_mode = ln_mode; f.ln1_g = g1; f.ln1_b = be1; f.ln2_g = g2; f.ln2_b = be2;
+  f.ln_eps = eps; f.ln_out = ln_out; f.cluster = cluster;
+  return launch_ffn_fused(f, reinterpret_cast<cudaStream_t>(stream));
 }
 int ec_op_pointwise_glu(int precision, const void* A, const float* w_raw, const float* b_raw, int M, int channels, int K, void* w_scratch,
                         float* b_scratch, void* out_act, void* stream_) {

@@ -18,6 +18,7 @@
 // K and N tails are zero-filled by TMA out-of-bounds handling, so D, 4D, head dims etc. need no host-side padding
 // (only 16-byte row pitches).  Operand type float => kind::tf32, __nv_bfloat16 => kind::f16.
 #include "ec_common.cuh"
+#include "ec_tma.cuh"
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
@@ -56,85 +57,10 @@ __device__ __forceinline__ void stamp(int enabled, int slot) {
   if (enabled && blockIdx.x == 0 && blockIdx.y == 0) g_gemm_timeline[slot] = clock64();
 }
 
-constexpr int kBlockM = 128;
-constexpr int kATileBytes = kBlockM * 128;
-constexpr int kSlabBytes = 4096;             // 32 rows x 128 B
 constexpr int kVecFloats = 288;              // bias / LayerNorm vectors in smem (256 + one chunk of slack)
 constexpr int kVecBytes = 5 * kVecFloats * 4 + 2 * 2 * 4 * 32 * 3 * 4;   // + LayerNorm statistics exchange [stage][half][quarter][lane][3]
 constexpr int kMaxStages = 8;
 constexpr int kNumBars = 2 * kMaxStages + 1 + 16;
-
-// Mean / centred sum of squares of the first nc (<= 32) values of t, four independent accumulation chains.
-__device__ __forceinline__ void chunk_stats(const float (&t)[32], int nc, float& cm, float& cq) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    s0 += (j < nc) ? t[j] : 0.f; s1 += (j + 1 < nc) ? t[j + 1] : 0.f;
-    s2 += (j + 2 < nc) ? t[j + 2] : 0.f; s3 += (j + 3 < nc) ? t[j + 3] : 0.f;
-  }
-  cm = ((s0 + s1) + (s2 + s3)) / static_cast<float>(nc);
-  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-#pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    const float d0 = t[j] - cm, d1 = t[j + 1] - cm, d2 = t[j + 2] - cm, d3 = t[j + 3] - cm;
-    q0 = fmaf((j < nc) ? d0 : 0.f, d0, q0); q1 = fmaf((j + 1 < nc) ? d1 : 0.f, d1, q1);
-    q2 = fmaf((j + 2 < nc) ? d2 : 0.f, d2, q2); q3 = fmaf((j + 3 < nc) ? d3 : 0.f, d3, q3);
-  }
-  cq = (q0 + q1) + (q2 + q3);
-}
-// wait until at most `pending` (1, 3 or 7) of this thread's bulk-store groups have not finished reading shared memory
-__device__ __forceinline__ void bulk_wait_read(int pending) {
-  if (pending >= 7) asm volatile("cp.async.bulk.wait_group.read 7;" ::: "memory");
-  else if (pending >= 3) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
-  else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-}
-
-// ---- TMA store / bulk-group helpers -------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-// 32 x 32 slab layouts written by thread = row (lane), matching the TMA swizzle modes:
-//   fp32: 128-byte rows, 16-byte chunk j4 in [0,8) XOR (row & 7)          (CU_TENSOR_MAP_SWIZZLE_128B)
-//   bf16:  64-byte rows, 16-byte chunk j8 in [0,4) XOR ((row >> 1) & 3)   (CU_TENSOR_MAP_SWIZZLE_64B)
-__device__ __forceinline__ uint32_t slab_f32_off(int row, int j4) { return row * 128 + ((j4 ^ (row & 7)) << 4); }
-__device__ __forceinline__ uint32_t slab_b16_off(int row, int j8) { return row * 64 + ((j8 ^ ((row >> 1) & 3)) << 4); }
-
-__device__ __forceinline__ void slab_store_f32(uint8_t* slab, int row, const float (&t)[32]) {
-#pragma unroll
-  for (int j4 = 0; j4 < 8; ++j4)
-    *reinterpret_cast<float4*>(slab + slab_f32_off(row, j4)) = make_float4(t[4 * j4], t[4 * j4 + 1], t[4 * j4 + 2], t[4 * j4 + 3]);
-}
-__device__ __forceinline__ void slab_load_f32(const uint8_t* slab, int row, float (&t)[32]) {
-#pragma unroll
-  for (int j4 = 0; j4 < 8; ++j4) {
-    const float4 x = *reinterpret_cast<const float4*>(slab + slab_f32_off(row, j4));
-    t[4 * j4] = x.x; t[4 * j4 + 1] = x.y; t[4 * j4 + 2] = x.z; t[4 * j4 + 3] = x.w;
-  }
-}
-template <typename T>
-__device__ __forceinline__ void slab_store_act(uint8_t* slab, int row, const float (&t)[32]) {
-  if constexpr (sizeof(T) == 4) {
-    float r[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) r[j] = round_tf32(t[j]);
-    slab_store_f32(slab, row, r);
-  } else {
-#pragma unroll
-    for (int j8 = 0; j8 < 4; ++j8) {
-      uint4 pk;
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(t[8 * j8], t[8 * j8 + 1]), h1 = __floats2bfloat162_rn(t[8 * j8 + 2], t[8 * j8 + 3]);
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(t[8 * j8 + 4], t[8 * j8 + 5]), h3 = __floats2bfloat162_rn(t[8 * j8 + 6], t[8 * j8 + 7]);
-      pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-      pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-      *reinterpret_cast<uint4*>(slab + slab_b16_off(row, j8)) = pk;
-    }
-  }
-}
 
 // kLN kernels run one CTA per SM, so they use 8 epilogue warps: warps q and q+4 share TMEM lane quarter q and take the
 // even / odd 32-column chunks of the same 32 rows; their LayerNorm statistics are merged through shared memory.
@@ -191,40 +117,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   grid_launch_dependents();
   if (threadIdx.x == 0) stamp(p.dbg, 2);
 
+  // Producer and MMA loops run warp-uniform; only the TMA / tcgen05 instructions sit under elect_one() (a lane-0 branch makes
+  // the compiler wrap every uniform-datapath instruction in an ELECT/BRA loop, which doubles the issue time per MMA).
   if (warp_idx == 0) {
-    if (lane == 0) {
-      const uint32_t tx = static_cast<uint32_t>(stage_bytes);
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (kb / p.stages) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
+    const uint32_t tx = static_cast<uint32_t>(stage_bytes);
+    int s = 0; uint32_t ph = 1;
+    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      mbar_wait(empty_bar(s), ph);
+      if (elect_one()) {
         mbar_arrive_expect_tx(full_bar(s), tx);
         const uint32_t a_dst = base + s * stage_bytes;
         tma_load_2d(a_dst, &tmA, full_bar(s), kb * Tr::kBlockK, m0);
         tma_load_2d(a_dst + kATileBytes, &tmB, full_bar(s), kb * Tr::kBlockK, w_row0);
         if (kb == 0) stamp(p.dbg, 3);
       }
+      __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1; }
     }
   } else if (warp_idx == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(Tr::kTf32 ? 2u : 1u, kBlockM, p.block_n);
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (kb / p.stages) & 1;
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
+    const uint32_t idesc = make_idesc(Tr::kTf32 ? 2u : 1u, kBlockM, p.block_n);
+    int s = 0; uint32_t ph = 0;
+    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      const uint64_t da = make_smem_desc_sw128(base + s * stage_bytes);
+      const uint64_t db = make_smem_desc_sw128(base + s * stage_bytes + kATileBytes);
+      if (elect_one()) {
         if (kb == 0) stamp(p.dbg, 4);
-        const uint32_t a_src = base + s * stage_bytes;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {   // 4 x 32-byte K slices inside the 128-byte swizzle row
-          const uint64_t da = make_smem_desc_sw128(a_src + k * 32);
-          const uint64_t db = make_smem_desc_sw128(a_src + kATileBytes + k * 32);
-          tc_mma<Tr::kTf32>(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-        }
-        tc_commit(empty_bar(s));       // frees the smem slot when these MMAs retire
+        for (int k = 0; k < 4; ++k)     // 4 x 32-byte K slices inside the 128-byte swizzle row: start address advances by 32 B
+          tc_mma<Tr::kTf32>(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        tc_commit(empty_bar(s));         // frees the smem slot when these MMAs retire
+        if (kb == p.num_k_blocks - 1) { tc_commit(tmem_full_bar); stamp(p.dbg, 5); }   // accumulator complete
       }
-      tc_commit(tmem_full_bar);        // accumulator complete
-      stamp(p.dbg, 5);
+      __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1; }
     }
   } else {
     // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp_idx % 4); thread = output row ----------------
@@ -477,7 +404,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (et == 0) stamp(p.dbg, 9);
-    if (lane == 0) bulk_wait_all0();     // all bulk stores of this warp have completed before the CTA retires
+    if (lane == 0) bulk_wait_read0();    // the slabs have been read (shared memory may be released); the writes themselves
+                                         // complete before the grid does
     if (et == 0) stamp(p.dbg, 10);
   }
   tc_fence_before();
@@ -489,52 +417,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
-// 2D row-major tensor [rows, cols] of `esize`-byte elements -> tensor map with a (box_cols x box_rows) box.
-static int make_map(CUtensorMap* map, bool is_f32, const void* ptr, int rows, int cols, int ld, int box_cols, int box_rows,
-                    CUtensorMapSwizzle swz) {
-  EncodeTiledFn enc = get_encode_fn();
-  EC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
-  const int esize = is_f32 ? 4 : 2;
-  const size_t pitch = static_cast<size_t>(ld) * esize;
-  EC_REQUIRE(pitch % 16 == 0, "tensor row pitch must be a multiple of 16 bytes for TMA (got " + std::to_string(pitch) + ")");
-  EC_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "tensor base must be 16-byte aligned for TMA");
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch)};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
-                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  EC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
-  return EC_OK;
-}
-// K-major GEMM operand [rows, K]: (128-byte x box_rows) box, 128B swizzle.
-static int make_operand_map(CUtensorMap* map, int precision, const void* ptr, int rows, int K, int box_rows) {
-  const bool f32 = precision == EC_PREC_TF32;
-  return make_map(map, f32, ptr, rows, K, K, f32 ? 32 : 64, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
-}
-// 32 x 32 epilogue slab of an [M, cols] output / residual tensor.
-static int make_slab_map(CUtensorMap* map, bool is_f32, const void* ptr, int rows, int cols, int ld) {
-  return make_map(map, is_f32, ptr, rows, cols, ld, 32, 32, is_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
-}
-
 // Output tiles are stored in 32-column slabs, so tile boundaries inside a row must be multiples of 32.
 static int pick_block_n(int N) {
   if (N <= 256) return round_up(N, 16);

@@ -58,6 +58,20 @@ def gemm_ln(a_act, w_act, bias, precision, g1, b1, g2=None, b2=None, mode=1, alp
     return of, ya, cp
 
 
+def ffn_fused(x_act, w1, b1, w2, b2, residual, g1, be1, g2=None, be2=None, mode=1, eps=1e-6, cluster=0, want_ln=True):
+    """Fused feed-forward module (bf16 operands).  Returns (out_f32, ln_out bf16 or None)."""
+    M, D = x_act.shape
+    hidden = w1.shape[0]
+    for t in (x_act, w1, w2):
+        if t.dtype != torch.bfloat16:
+            raise ValueError("ffn_fused takes bf16 operands")
+    of = torch.empty(M, D, dtype=torch.float32, device=x_act.device)
+    ya = torch.empty(M, D, dtype=torch.bfloat16, device=x_act.device) if want_ln else None
+    check(lib().ec_op_ffn(ptr(x_act), ptr(w1), ptr(b1), ptr(w2), ptr(b2), M, D, hidden, ptr(residual), ptr(of), mode, ptr(g1), ptr(be1),
+                          ptr(g2), ptr(be2), eps, ptr(ya), cluster, stream_ptr()))
+    return of, ya
+
+
 def pointwise_glu(a_act, w_raw, b_raw, precision):
     pr = _p(precision)
     M, K = a_act.shape

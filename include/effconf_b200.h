@@ -113,9 +113,14 @@ int ec_engine_profile_read(ec_engine* e, double* ms, double* flops, double* byte
  * GEMM instead of as separate kernels (needs model dims <= 256).  pdl (process wide, default 1, env EFFCONF_PDL=0 disables):
  * launch every kernel with programmatic stream serialization so its prologue overlaps the predecessor's tail. */
 int ec_engine_set_fuse_ln(ec_engine* e, int enabled);
+/* fuse_ffn (per engine, default 1; EC_PREC_BF16 with fuse_ln only): each feed-forward module runs as ONE cluster kernel
+ * (W1 -> Swish -> W2 -> half-step residual -> LayerNorm) whose hidden activation never leaves the SM. */
+int ec_engine_set_fuse_ffn(ec_engine* e, int enabled);
 int ec_set_pdl(int enabled);
 /* Debug: enable in-kernel SM-clock stamps in the GEMM and read the 12 stamps of the last GEMM's CTA (0,0) (synchronises). */
 int ec_debug_gemm_timeline(int enable, unsigned long long* out12);
+/* Same for the fused feed-forward kernel: 192 stamp slots of CTA 0 (see ffn_fused.cu). */
+int ec_debug_ffn_timeline(int enable, unsigned long long* out192);
 
 /* CTC head.  logits [B, T, V] fp32, logits_len [B] int64, targets [B, target_stride] int64 (blank = 0), target_len [B] int64.
  * scratch: at least B*T*(sizeof(float)+sizeof(int)) + B*sizeof(int) bytes.  loss_per_utt [B], loss_mean [1] fp32. */
@@ -141,6 +146,12 @@ int ec_op_gemm_ln(int precision, const void* A, const void* W, int M, int N, int
                   const float* residual, float* out_f32, int ln_mode, const float* g1, const float* b1, const float* g2,
                   const float* b2, float eps, void* ln_out, void* copy_out, int copy_stride, int frames_per_seq,
                   int frames_out_per_seq, void* stream);
+/* Fused feed-forward module (EC_PREC_BF16 operands; reference models/modules.py:367-398 + the half-step residual of
+ * models/blocks.py:123-150): out_f32 = residual + 0.5*(Swish(x_act W1^T + b1) W2^T + b2); LayerNorm modes as ec_op_gemm_ln.
+ * x_act [M,D], w1 [hidden,D], w2 [D,hidden] bf16; D <= 256.  cluster: CTAs per 128-row tile splitting the hidden dim (0 = auto). */
+int ec_op_ffn(const void* x_act, const void* w1, const float* b1, const void* w2, const float* b2, int M, int D, int hidden,
+              const float* residual, float* out_f32, int ln_mode, const float* g1, const float* be1, const float* g2,
+              const float* be2, float eps, void* ln_out, int cluster, void* stream);
 /* pointwise Conv1d(K -> 2*channels) + GLU: out[m, c] = (A w_c + b_c) * sigmoid(A w_{C+c} + b_{C+c}).  w_raw [2C, K], b_raw [2C] fp32
  * (reference layout); w_scratch / b_scratch hold ec_op_glu_scratch_rows(channels) rows of the interleaved copy. */
 int ec_op_pointwise_glu(int precision, const void* A, const float* w_raw, const float* b_raw, int M, int channels, int K,

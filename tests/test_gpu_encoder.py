@@ -235,6 +235,31 @@ def test_execution_options_do_not_change_results(sd, fuse_ln, pdl):
     assert rel_l2(ref_gpu, ref) < TOL_TF32
 
 
+def test_fused_ffn_matches_unfused_bf16(sd):
+    """Fast mode: the fused feed-forward cluster kernel (default) and the W1 / W2 GEMM pair compute the same module; both stay
+    at the bf16 operand-noise level against the oracle (TOL_BF16), and agree with each other at that level."""
+    from oracle import conformer_oracle as O
+    from efficientconformer_b200 import _lib
+    mel = synthetic_mel(4, 500, seed=91)
+    mel_len = torch.tensor([500, 431, 200, 64])
+    L = _lib.lib()
+    outs = []
+    for fuse_ffn in (1, 0):
+        m = make_model(sd, "bf16")
+        m.forward_mel(mel.to(DEV), mel_len.to(DEV))
+        eng = m.encoder._engines[_lib.PREC_BF16][0]
+        L.ec_engine_set_fuse_ffn(eng, fuse_ffn)
+        m.encoder._plans.clear()
+        lg, ol, _ = m.forward_mel(mel.to(DEV), mel_len.to(DEV))
+        launches = L.ec_engine_last_launches(eng)
+        outs.append((lg, launches))
+    assert outs[0][1] == outs[1][1] - 30, "the fused path replaces 2 launches by 1 for each of the 30 feed-forward modules"
+    ref, _ = O.model_ctc_forward_mel(sd, P, mel, mel_len)
+    assert rel_l2(outs[0][0], ref) < TOL_BF16
+    assert rel_l2(outs[1][0], ref) < TOL_BF16
+    assert rel_l2(outs[0][0], outs[1][0]) < TOL_BF16
+
+
 def test_other_config_transducer_small_encoder():
     """A second shipped encoder config (EfficientConformerTransducerSmall: dims [100,140,200], head dims 75/35/50 -- odd, not
     multiples of 8) through the same engine in parity mode, against the oracle with seeded weights."""

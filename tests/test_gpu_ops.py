@@ -105,6 +105,55 @@ def test_gemm_fused_layernorm(ops, prec, M, N, K, fps, stride):
     assert torch.equal(y3.float().cpu(), rnd(prec, out3.cpu()))
 
 
+@pytest.mark.parametrize("M,D,hidden,clusters", [(16000, 120, 480, (0, 1, 2)), (8000, 168, 672, (0, 2)), (4000, 240, 960, (0, 2, 4)),
+                                                 (999, 120, 480, (0, 2)), (37, 256, 1024, (0, 2, 4)), (130, 64, 256, (0, 1, 2, 4)),
+                                                 (300, 16, 64, (0, 1))])
+def test_ffn_fused(ops, M, D, hidden, clusters):
+    """Fused feed-forward cluster kernel vs the module's formula (reference models/modules.py:367-398, blocks.py:123-150)."""
+    g = torch.Generator(device="cpu").manual_seed(M + D + hidden)
+    x = torch.randn(M, D, generator=g).to(DEV)
+    w1 = (torch.randn(hidden, D, generator=g) / math.sqrt(D)).to(DEV)
+    w2 = (torch.randn(D, hidden, generator=g) / math.sqrt(hidden)).to(DEV)
+    b1, b2 = (0.3 * torch.randn(hidden, generator=g)).to(DEV), (0.3 * torch.randn(D, generator=g)).to(DEV)
+    res = (torch.randn(M, D, generator=g) * 2 + 0.3).to(DEV)
+    g1, be1 = (1 + 0.1 * torch.randn(D, generator=g)).to(DEV), (0.1 * torch.randn(D, generator=g)).to(DEV)
+    g2, be2 = (1 + 0.1 * torch.randn(D, generator=g)).to(DEV), (0.1 * torch.randn(D, generator=g)).to(DEV)
+    xa, w1a, w2a = ops.cast(x, "bf16"), ops.cast(w1, "bf16"), ops.cast(w2, "bf16")
+    h = xa.double() @ w1a.double().t() + b1.double()
+    h = (h * torch.sigmoid(h)).float().bfloat16().double()          # the hidden activation is a bf16 operand of the second product
+    delta_ref = 0.5 * (h @ w2a.double().t() + b2.double())
+    x_ref = res.double() + delta_ref
+    ln = lambda t, gg, bb: torch.nn.functional.layer_norm(t, (D,), gg.double(), bb.double(), 1e-6)
+    y_ref = ln(x_ref, g1, be1)
+    first = None
+    for cs in clusters:
+        out, y = ops.ffn_fused(xa, w1a, b1, w2a, b2, res, g1, be1, mode=1, cluster=cs)
+        assert rel_l2(out.double() - res.double(), delta_ref) < 6e-3, f"ffn delta, cluster {cs}"
+        assert rel_l2(out, x_ref) < 2e-3
+        assert rel_l2(y.float(), y_ref) < 5e-3
+        out2, y2 = ops.ffn_fused(xa, w1a, b1, w2a, b2, res, g1, be1, g2, be2, mode=2, cluster=cs)
+        assert rel_l2(out2, y_ref) < 2e-3
+        assert rel_l2(y2.float(), ln(y_ref, g2, be2)) < 5e-3
+        out3, y3 = ops.ffn_fused(xa, w1a, b1, w2a, b2, res, g1, be1, None, None, mode=2, cluster=cs)
+        assert torch.equal(out3, out2)
+        assert torch.equal(y3.float().cpu(), rnd("bf16", out3.cpu()))
+        out4, y4 = ops.ffn_fused(xa, w1a, b1, w2a, b2, res, g1, be1, None, None, mode=2, cluster=cs, want_ln=False)
+        assert y4 is None and torch.equal(out4, out2)
+        # in-place operand / LayerNorm output buffer, as the engine uses it
+        xin = xa.clone()
+        M_, D_ = xin.shape
+        from efficientconformer_b200 import _lib
+        of = torch.empty(M_, D_, dtype=torch.float32, device=DEV)
+        _lib.check(_lib.lib().ec_op_ffn(xin.data_ptr(), w1a.data_ptr(), b1.data_ptr(), w2a.data_ptr(), b2.data_ptr(), M_, D_, hidden,
+                                        res.data_ptr(), of.data_ptr(), 1, g1.data_ptr(), be1.data_ptr(), None, None, 1e-6, xin.data_ptr(),
+                                        cs, torch.cuda.current_stream().cuda_stream))
+        assert torch.equal(of, out) and torch.equal(xin, y)
+        if first is None:
+            first = out
+        else:     # the split over the cluster changes the summation order of the second product only
+            assert rel_l2(out, first) < 1e-5
+
+
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])
 @pytest.mark.parametrize("M,C,K", [(256, 120, 120), (1000, 168, 120), (517, 240, 168), (64, 8, 16), (300, 360, 360)])
 def test_pointwise_glu(ops, prec, M, C, K):
