@@ -321,7 +321,11 @@ static int launch_attn_t(const AttnDev& p, cudaStream_t stream) {
 }
 
 int launch_relpos_attention(int precision, const AttnArgs& a, cudaStream_t stream) {
-  if (precision == EC_PREC_BF16 && !a.in_f32) return launch_relpos_attention_bf16(a, stream);
+  if (precision == EC_PREC_BF16 && !a.in_f32) {
+    bool launched = false;                           // TMA-staged kernel when the head layout fits its panel scheme
+    EC_TRY(try_launch_relpos_attention_tma(a, stream, &launched));
+    return launched ? EC_OK : launch_relpos_attention_bf16(a, stream);
+  }
   EC_REQUIRE(a.G >= 1 && a.G % 2 == 1, "attention group size must be odd");
   EC_REQUIRE((a.G * a.D) % a.H == 0, "G*D must be divisible by H");
   AttnDev p{};

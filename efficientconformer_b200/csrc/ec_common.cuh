@@ -172,6 +172,7 @@ struct AttnArgs {
 };
 int launch_relpos_attention(int precision, const AttnArgs& a, cudaStream_t stream);
 int launch_relpos_attention_bf16(const AttnArgs& a, cudaStream_t stream);
+int try_launch_relpos_attention_tma(const AttnArgs& a, cudaStream_t stream, bool* launched);
 
 struct DwConvArgs {
   const void* x;         // [B, T, C] activation type (GLU output)
