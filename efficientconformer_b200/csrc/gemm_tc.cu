@@ -7,10 +7,12 @@
 // the subsampling Linear and the CTC fc head -- and, through the fused epilogue, the five nn.LayerNorm(eps=1e-6) of a
 // block (reference models/modules.py:386,433,511; models/blocks.py:96,135).
 //
-// One CTA = one 128 x BLOCK_N output tile over the whole K.  Warp roles (192 threads):
+// One CTA = one 128 x BLOCK_N output tile over the whole K.  Warp roles (2 + 16 warps; 2 + 8 in the fused-LayerNorm variant):
 //   warp 0    TMA producer : cp.async.bulk.tensor loads of the A (128 x 128B) and W (BLOCK_N x 128B) k-slices, 128B swizzle
 //   warp 1    MMA issuer   : allocates TMEM, one thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 32B), fp32 accumulator in TMEM
-//   warps 2-5 epilogue     : thread = output row.  Per 32-column chunk: tcgen05.ld -> bias (smem broadcast) / Swish / GLU /
+//   warps 2-.. epilogue    : four (two) warps per TMEM lane quarter share its 32 rows and interleave the 32-column chunks: the
+//                            per-row work is a dependent chain, so the epilogue is latency bound per warp, not throughput bound.
+//                            thread = output row.  Per 32-column chunk: tcgen05.ld -> bias (smem broadcast) / Swish / GLU /
 //                            alpha / residual (TMA-prefetched swizzled slab) in registers -> swizzled smem slab (conflict-free
 //                            16-byte stores) -> TMA bulk tensor store (coalesced, clips the M / N tails).  LayerNorm row
 //                            statistics are per-thread (chunk-wise Chan/Welford merge, no shuffles); the fp32 row tile stays
@@ -60,12 +62,12 @@ __device__ __forceinline__ void stamp(int enabled, int slot) {
 constexpr int kVecFloats = 288;              // bias / LayerNorm vectors in smem (256 + one chunk of slack)
 constexpr int kVecBytes = 5 * kVecFloats * 4 + 2 * 2 * 4 * 32 * 3 * 4;   // + LayerNorm statistics exchange [stage][half][quarter][lane][3]
 constexpr int kMaxStages = 8;
-constexpr int kNumBars = 2 * kMaxStages + 1 + 16;
+constexpr int kNumBars = 2 * kMaxStages + 1 + 32;
 
 // kLN kernels run one CTA per SM, so they use 8 epilogue warps: warps q and q+4 share TMEM lane quarter q and take the
 // even / odd 32-column chunks of the same 32 rows; their LayerNorm statistics are merged through shared memory.
 template <typename T, bool kLN>
-__global__ void __launch_bounds__(kLN ? 320 : 192, kLN ? 1 : 2)
+__global__ void __launch_bounds__(kLN ? 320 : 576, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmOutF,
                const __grid_constant__ CUtensorMap tmOutA, const __grid_constant__ CUtensorMap tmLn, const GemmDev p) {
@@ -78,7 +80,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stage_bytes = kATileBytes + p.block_n * 128;
-  constexpr int kEpiWarps = kLN ? 8 : 4, kHalves = kLN ? 2 : 1;
+  constexpr int kEpiWarps = kLN ? 8 : 16, kHalves = kEpiWarps / 4;       // warps per lane quarter = chunk interleave factor
   const int res_bytes = p.has_res ? kEpiWarps * p.res_depth * kSlabBytes : 0;
   uint8_t* res_ring = base_ptr + p.pipe_bytes;
   float* vecs = reinterpret_cast<float*>(base_ptr + p.pipe_bytes + res_bytes);          // bias | ln1_g | ln1_b | ln2_g | ln2_b
@@ -101,7 +103,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(tmem_full_bar, 1);
-    for (int i = 0; i < 16; ++i) mbar_init(res_bar(i >> 1, i & 1), 1);
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(res_bar(i >> 1, i & 1), 1);
     fence_barrier_init();
   }
   if (warp_idx == 1) {
@@ -195,7 +197,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (my_chunks > 0) issue_res(0);
       if (my_chunks > 1 && p.res_depth > 1) issue_res(1);
     }
-    uint8_t* wstage = base_ptr + q * p.warp_stage_bytes;     // aliases the operand ring: only touched after tmem_full
+    uint8_t* wstage = base_ptr + (kLN ? q : ew) * p.warp_stage_bytes;     // aliases the operand ring: only touched after tmem_full
     // plain: [F slabs (nbuf, if fp32 output) | A slabs (nbuf)]; kLN: [x slabs (n_chunks) | A slabs (n_chunks)]
     constexpr int kASlab = sizeof(T) == 4 ? kSlabBytes : kSlabBytes / 2;
     const int nbuf = p.nbuf;
@@ -270,7 +272,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else {
         const int buf = i & (nbuf - 1);
-        if (i >= nbuf) { if (lane == 0) bulk_wait_read(nbuf - 1); __syncwarp(); }   // the stores issued nbuf chunks ago have drained this buffer
+        if (i >= nbuf) {                                   // the stores issued nbuf chunks ago have drained this buffer
+          if (lane == 0) { if (nbuf > 1) bulk_wait_read(nbuf - 1); else bulk_wait_read0(); }
+          __syncwarp();
+        }
         uint8_t* sf = wstage + buf * kSlabBytes;
         uint8_t* sa = slabA + buf * kASlab;
         if (p.has_out_f32) slab_store_f32(sf, lane, t);
@@ -466,16 +471,14 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
     p.warp_stage_bytes = n_chunks * kSlabBytes + 2 * na * a_slab;
     p.epi_batch = (epi_batch_env && na >= own) ? 1 : 0;
   } else {
-    int nbuf = 2;
-    while (nbuf < n_chunks && nbuf < 8) nbuf <<= 1;
-    p.nbuf = nbuf;                                          // reduced below if the staging would not fit
-    p.warp_stage_bytes = nbuf * per_chunk;
+    p.nbuf = 2;                                             // each of the 16 epilogue warps owns at most ceil(n_chunks / 4) chunks
+    p.warp_stage_bytes = p.nbuf * per_chunk;
     p.epi_batch = 0;
+    p.res_depth = 1;
   }
-  const int fixed = (p.has_res ? (kLN ? 8 : 4) * p.res_depth * kSlabBytes : 0) + kVecBytes + kNumBars * 8 + 16 + 1024;
-  // up to 148 CTAs: one CTA per SM anyway -> deep ring (hides the TMA->MMA->refill round trip); otherwise 2 CTAs per SM
-  const int ctas = cdiv(a.M, kBlockM) * tiles_n;
-  const int budget = (ctas <= 148 || kLN) ? 224 * 1024 : 113 * 1024;
+  const int fixed = (p.has_res ? (kLN ? 8 : 16) * p.res_depth * kSlabBytes : 0) + kVecBytes + kNumBars * 8 + 16 + 1024;
+  // one CTA per SM (thread count): a deep ring hides the TMA->MMA->refill round trip
+  const int budget = 224 * 1024;
   int stages = (budget - fixed) / stage_bytes;
   if (stages < 2) stages = 2;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -517,13 +520,10 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   if (kLN && a.ln_out != nullptr) EC_TRY(make_slab_map(&tmLn, act_f32, a.ln_out, a.M, a.N, a.N));
 
   if (!kLN) {
-    // staging aliases the operand ring; 1-CTA/SM launches may grow it up to the budget, 2-CTA/SM launches shrink nbuf instead
-    const size_t avail = (ctas <= 148) ? static_cast<size_t>(budget - fixed) : static_cast<size_t>(stages) * stage_bytes;
-    while (p.nbuf > 2 && static_cast<size_t>(4) * p.nbuf * per_chunk > avail) p.nbuf >>= 1;
-    p.warp_stage_bytes = p.nbuf * per_chunk;
-    p.epi_batch = (epi_batch_env && n_chunks <= p.nbuf) ? 1 : 0;
+    if (static_cast<size_t>(16) * p.nbuf * per_chunk + fixed > 227 * 1024) { p.nbuf = 1; p.warp_stage_bytes = per_chunk; }
+    p.epi_batch = (epi_batch_env && cdiv(n_chunks, 4) <= p.nbuf) ? 1 : 0;   // staging (16 warps) aliases the operand ring
   }
-  size_t pipe_bytes = std::max(static_cast<size_t>(stages) * stage_bytes, static_cast<size_t>(4) * p.warp_stage_bytes);
+  size_t pipe_bytes = std::max(static_cast<size_t>(stages) * stage_bytes, static_cast<size_t>(kLN ? 4 : 16) * p.warp_stage_bytes);
   p.pipe_bytes = static_cast<int>(pipe_bytes);
   const size_t smem = pipe_bytes + fixed;
   EC_REQUIRE(smem <= 227 * 1024, "GEMM tile does not fit in shared memory");
@@ -534,7 +534,7 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   });
   EC_CUDA(attr_err);
   dim3 grid(cdiv(a.M, kBlockM), tiles_n);
-  EC_TRY(launch_pdl(gemm_tc_kernel<T, kLN>, grid, dim3(kLN ? 320 : 192), smem, stream, tmA, tmB, tmRes, tmOutF, tmOutA, tmLn, p));
+  EC_TRY(launch_pdl(gemm_tc_kernel<T, kLN>, grid, dim3(kLN ? 320 : 576), smem, stream, tmA, tmB, tmRes, tmOutF, tmOutA, tmLn, p));
   return EC_OK;
 }
 
