@@ -60,14 +60,14 @@ __device__ __forceinline__ void stamp(int enabled, int slot) {
 }
 
 constexpr int kVecFloats = 288;              // bias / LayerNorm vectors in smem (256 + one chunk of slack)
-constexpr int kVecBytes = 5 * kVecFloats * 4 + 2 * 2 * 4 * 32 * 3 * 4;   // + LayerNorm statistics exchange [stage][half][quarter][lane][3]
+constexpr int kVecBytes = 5 * kVecFloats * 4 + 2 * 4 * 4 * 32 * 3 * 4;   // + LayerNorm statistics exchange [stage][sub][quarter][lane][3]
 constexpr int kMaxStages = 8;
 constexpr int kNumBars = 2 * kMaxStages + 1 + 32;
 
-// kLN kernels run one CTA per SM, so they use 8 epilogue warps: warps q and q+4 share TMEM lane quarter q and take the
-// even / odd 32-column chunks of the same 32 rows; their LayerNorm statistics are merged through shared memory.
+// 16 epilogue warps: the four warps (q, sub) of TMEM lane quarter q share its 32 rows and take the 32-column chunks sub,
+// sub + 4, ...; the LayerNorm statistics of a row are merged through shared memory in a fixed order.
 template <typename T, bool kLN>
-__global__ void __launch_bounds__(kLN ? 320 : 576, 1)
+__global__ void __launch_bounds__(576, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmOutF,
                const __grid_constant__ CUtensorMap tmOutA, const __grid_constant__ CUtensorMap tmLn, const GemmDev p) {
@@ -80,8 +80,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stage_bytes = kATileBytes + p.block_n * 128;
-  constexpr int kEpiWarps = kLN ? 8 : 16, kHalves = kEpiWarps / 4;       // warps per lane quarter = chunk interleave factor
-  const int res_bytes = p.has_res ? kEpiWarps * p.res_depth * kSlabBytes : 0;
+  constexpr int kEpiWarps = 16, kHalves = kEpiWarps / 4;                 // warps per lane quarter = chunk interleave factor
+  const int res_bytes = p.has_res ? kEpiWarps * p.res_depth * kSlabBytes : 0;     // res_depth 0: residual lands in the x slabs
   uint8_t* res_ring = base_ptr + p.pipe_bytes;
   float* vecs = reinterpret_cast<float*>(base_ptr + p.pipe_bytes + res_bytes);          // bias | ln1_g | ln1_b | ln2_g | ln2_b
   uint64_t* bars = reinterpret_cast<uint64_t*>(base_ptr + p.pipe_bytes + res_bytes + kVecBytes);
@@ -187,28 +187,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n_chunks = (min(cols, n_limit - out_col0) + 31) / 32;
     // this warp's i-th chunk is column chunk c = half + i * kHalves
     const int my_chunks = (n_chunks - half + kHalves - 1) / kHalves;
+    uint8_t* wstage = base_ptr + (kLN ? q : ew) * p.warp_stage_bytes;     // aliases the operand ring: only touched after tmem_full
+    // residual: a per-warp TMA ring prefetched during the mainloop, or (res_depth 0, fused LayerNorm with a wide row) straight
+    // into the resident x slab of the chunk once the operand ring is drained
+    const bool res_direct = kLN && p.res_depth == 0;
+    const int rdepth = res_direct ? 2 : p.res_depth;       // a warp owns at most two chunks in the direct mode
     uint8_t* my_res = res_ring + ew * p.res_depth * kSlabBytes;
-    const int rmask = p.res_depth - 1;
+    const int rmask = rdepth - 1;
+    auto res_slab = [&](int i) { return res_direct ? wstage + (half + i * kHalves) * kSlabBytes : my_res + (i & rmask) * kSlabBytes; };
     auto issue_res = [&](int i) {
       mbar_arrive_expect_tx(res_bar(ew, i & rmask), kSlabBytes);
-      tma_load_2d(smem_u32(my_res + (i & rmask) * kSlabBytes), &tmRes, res_bar(ew, i & rmask), out_col0 + (half + i * kHalves) * 32, row0);
+      tma_load_2d(smem_u32(res_slab(i)), &tmRes, res_bar(ew, i & rmask), out_col0 + (half + i * kHalves) * 32, row0);
     };
-    if (p.has_res && lane == 0) {
+    if (p.has_res && !res_direct && lane == 0) {
       if (my_chunks > 0) issue_res(0);
-      if (my_chunks > 1 && p.res_depth > 1) issue_res(1);
+      if (my_chunks > 1 && rdepth > 1) issue_res(1);
     }
-    uint8_t* wstage = base_ptr + (kLN ? q : ew) * p.warp_stage_bytes;     // aliases the operand ring: only touched after tmem_full
     // plain: [F slabs (nbuf, if fp32 output) | A slabs (nbuf)]; kLN: [x slabs (n_chunks) | A slabs (n_chunks)]
     constexpr int kASlab = sizeof(T) == 4 ? kSlabBytes : kSlabBytes / 2;
     const int nbuf = p.nbuf;
     uint8_t* slabA = wstage + (kLN ? n_chunks : (p.has_out_f32 ? nbuf : 0)) * kSlabBytes + (kLN ? half * nbuf * kASlab : 0);
-    float* stat_x = vecs + 5 * kVecFloats;                   // [stage 2][half 2][quarter 4][lane 32][3]
+    float* stat_x = vecs + 5 * kVecFloats;                   // [stage 2][sub 4][quarter 4][lane 32][3]
     const bool batch = p.epi_batch != 0;
     float mean = 0.f, m2 = 0.f, cnt = 0.f;                   // running LayerNorm statistics of this thread's row
     if (et == 0) stamp(p.dbg, 6);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (et == 0) stamp(p.dbg, 7);
+    if (p.has_res && res_direct && lane == 0) {
+      if (my_chunks > 0) issue_res(0);
+      if (my_chunks > 1) issue_res(1);
+    }
     const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t v[32];
     if (my_chunks > 0) tmem_ld_32x32(tbase + 32u * half, v);  // software pipeline: the next chunk's accumulator load is in flight
@@ -240,13 +249,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < 32; ++j) t[j] = swish_fn<T>(t[j]);
       }
       if (p.has_res) {
-        mbar_wait(res_bar(ew, i & rmask), (i / p.res_depth) & 1);
+        mbar_wait(res_bar(ew, i & rmask), (i / rdepth) & 1);
         float rr[32];
-        slab_load_f32(my_res + (i & rmask) * kSlabBytes, lane, rr);
+        slab_load_f32(res_slab(i), lane, rr);
 #pragma unroll
         for (int j = 0; j < 32; ++j) t[j] = fmaf(p.alpha, t[j], rr[j]);
         __syncwarp();
-        if (lane == 0 && i + p.res_depth < my_chunks) issue_res(i + p.res_depth);
+        if (lane == 0 && !res_direct && i + rdepth < my_chunks) issue_res(i + rdepth);
       } else if (p.alpha != 1.0f) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) t[j] *= p.alpha;
@@ -305,18 +314,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (et == 0) stamp(p.dbg, 8);
     if constexpr (kLN) {
       const float inv_n = 1.0f / static_cast<float>(p.N);
-      // merge the (count, mean, M2) of the two warps that share these 32 rows (fixed order -> both get identical results)
+      // merge the (count, mean, M2) of the four warps that share these 32 rows (fixed order -> all get identical results)
       auto merge_pair = [&](int stage, float& mean_, float& m2_, float cnt_) {
-        float* mine = stat_x + (((stage * 2 + half) * 4 + q) * 32 + lane) * 3;
-        const float* other = stat_x + (((stage * 2 + (half ^ 1)) * 4 + q) * 32 + lane) * 3;
+        float* mine = stat_x + (((stage * 4 + half) * 4 + q) * 32 + lane) * 3;
         mine[0] = cnt_; mine[1] = mean_; mine[2] = m2_;
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
-        const float oc = other[0], om = other[1], o2 = other[2];
-        const float c0_ = half == 0 ? cnt_ : oc, m0_ = half == 0 ? mean_ : om, q0_ = half == 0 ? m2_ : o2;
-        const float c1_ = half == 0 ? oc : cnt_, m1_ = half == 0 ? om : mean_, q1_ = half == 0 ? o2 : m2_;
-        const float tot = c0_ + c1_, dl = m1_ - m0_;
-        mean_ = c1_ > 0.f ? m0_ + dl * c1_ / tot : m0_;
-        m2_ = c1_ > 0.f ? q0_ + q1_ + dl * dl * c0_ * c1_ / tot : q0_;
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+        float ct = 0.f, mu = 0.f, qq = 0.f;
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {
+          const float* o = stat_x + (((stage * 4 + hh) * 4 + q) * 32 + lane) * 3;
+          const float oc = o[0], om = o[1], o2 = o[2];
+          if (oc > 0.f) {
+            const float tot = ct + oc, w_ = __fdividef(oc, tot), dl = om - mu;
+            mu = fmaf(dl, w_, mu);
+            qq += o2 + dl * dl * ct * w_;
+            ct = tot;
+          }
+        }
+        mean_ = mu; m2_ = qq;
       };
       merge_pair(0, mean, m2, cnt);
       float rstd = rsqrtf(m2 * inv_n + p.ln_eps);
@@ -454,21 +469,23 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   const int a_slab = precision == EC_PREC_TF32 ? kSlabBytes : kSlabBytes / 2;
   static const int epi_batch_env = [] { const char* e = getenv("EFFCONF_EPI_BATCH"); return (e != nullptr && e[0] == '1') ? 1 : 0; }();
   const int per_chunk = (p.has_out_f32 ? kSlabBytes : 0) + (p.has_out_act ? a_slab : 0);
-  p.res_depth = 2;
+  p.res_depth = 1;
   if (kLN) {
-    // per row quarter: persistent x slabs (one per chunk) + ln_out slabs for each of the two warps of the pair
-    // (one per owned chunk when that fits, else a smaller ring); the residual ring shrinks to depth 1 last
-    const int own = cdiv(n_chunks, 2);
-    int na = 1;
-    while (na < own && na < 4) na <<= 1;
+    // per row quarter: persistent x slabs (one per chunk) + ln_out slabs for each of its four warps (one per owned chunk when
+    // that fits, else one); the residual ring (depth 1, prefetched during the mainloop) is dropped for wide rows, whose residual
+    // then lands in the x slabs once the operand ring is drained
+    const int own = cdiv(n_chunks, 4);
+    EC_REQUIRE(own <= 2, "fused LayerNorm row too wide");
+    int na = own;
     auto total = [&](int na_, int depth) {
-      return 4 * (n_chunks * kSlabBytes + 2 * na_ * a_slab) + (p.has_res ? 8 * depth * kSlabBytes : 0) + kVecBytes + kNumBars * 8 + 16 + 1024;
+      return 4 * (n_chunks * kSlabBytes + 4 * na_ * a_slab) + (p.has_res ? 16 * depth * kSlabBytes : 0) + kVecBytes + kNumBars * 8 + 16 + 1024;
     };
-    while (na > 1 && total(na, 2) > 227 * 1024) na >>= 1;
-    if (total(na, 2) > 227 * 1024) p.res_depth = 1;
+    p.res_depth = 1;
+    if (total(na, 1) > 227 * 1024) p.res_depth = 0;
+    if (total(na, p.res_depth) > 227 * 1024) na = 1;
     EC_REQUIRE(total(na, p.res_depth) <= 227 * 1024, "fused LayerNorm tile does not fit in shared memory");
     p.nbuf = na;
-    p.warp_stage_bytes = n_chunks * kSlabBytes + 2 * na * a_slab;
+    p.warp_stage_bytes = n_chunks * kSlabBytes + 4 * na * a_slab;
     p.epi_batch = (epi_batch_env && na >= own) ? 1 : 0;
   } else {
     p.nbuf = 2;                                             // each of the 16 epilogue warps owns at most ceil(n_chunks / 4) chunks
@@ -476,7 +493,7 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
     p.epi_batch = 0;
     p.res_depth = 1;
   }
-  const int fixed = (p.has_res ? (kLN ? 8 : 16) * p.res_depth * kSlabBytes : 0) + kVecBytes + kNumBars * 8 + 16 + 1024;
+  const int fixed = (p.has_res ? 16 * p.res_depth * kSlabBytes : 0) + kVecBytes + kNumBars * 8 + 16 + 1024;
   // one CTA per SM (thread count): a deep ring hides the TMA->MMA->refill round trip
   const int budget = 224 * 1024;
   int stages = (budget - fixed) / stage_bytes;
@@ -534,7 +551,7 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   });
   EC_CUDA(attr_err);
   dim3 grid(cdiv(a.M, kBlockM), tiles_n);
-  EC_TRY(launch_pdl(gemm_tc_kernel<T, kLN>, grid, dim3(kLN ? 320 : 576), smem, stream, tmA, tmB, tmRes, tmOutF, tmOutA, tmLn, p));
+  EC_TRY(launch_pdl(gemm_tc_kernel<T, kLN>, grid, dim3(576), smem, stream, tmA, tmB, tmRes, tmOutF, tmOutA, tmLn, p));
   return EC_OK;
 }
 
