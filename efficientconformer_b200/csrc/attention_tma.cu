@@ -79,7 +79,7 @@ relpos_attn_tma_kernel(const __grid_constant__ CUtensorMap tmKV0, const __grid_c
 
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * kTM;
-  const int D = p.D, G = p.G, d = p.d, Tg = p.Tg, T = p.T;
+  const int D = p.D, G = p.G, Tg = p.Tg, T = p.T;
   const size_t row3 = static_cast<size_t>(3) * D;
   const AttnPanels& hp = p.pan[h];
   for (int pr = tid; pr < PR; pr += 128) {           // input independent: built before the dependency wait

@@ -10,23 +10,28 @@ constexpr int kBlockM = 128;
 constexpr int kATileBytes = kBlockM * 128;
 constexpr int kSlabBytes = 4096;             // 32 rows x 128 B
 
-// Mean / centred sum of squares of the first nc (<= 32) values of t, four independent accumulation chains.
+// Mean / centred sum of squares of the first nc (<= 32) values of t; the caller guarantees t[j] == 0 for j >= nc, so the sums
+// run over all 32 registers without per-element predicates and the zero tail is taken out in closed form
+// (sum over the tail of (0 - mean)^2 = (32 - nc) mean^2).  Four independent accumulation chains.
 __device__ __forceinline__ void chunk_stats(const float (&t)[32], int nc, float& cm, float& cq) {
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    s0 += (j < nc) ? t[j] : 0.f; s1 += (j + 1 < nc) ? t[j + 1] : 0.f;
-    s2 += (j + 2 < nc) ? t[j + 2] : 0.f; s3 += (j + 3 < nc) ? t[j + 3] : 0.f;
-  }
-  cm = ((s0 + s1) + (s2 + s3)) / static_cast<float>(nc);
+  for (int j = 0; j < 32; j += 4) { s0 += t[j]; s1 += t[j + 1]; s2 += t[j + 2]; s3 += t[j + 3]; }
+  cm = __fdividef((s0 + s1) + (s2 + s3), static_cast<float>(nc));
   float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const float d0 = t[j] - cm, d1 = t[j + 1] - cm, d2 = t[j + 2] - cm, d3 = t[j + 3] - cm;
-    q0 = fmaf((j < nc) ? d0 : 0.f, d0, q0); q1 = fmaf((j + 1 < nc) ? d1 : 0.f, d1, q1);
-    q2 = fmaf((j + 2 < nc) ? d2 : 0.f, d2, q2); q3 = fmaf((j + 3 < nc) ? d3 : 0.f, d3, q3);
+    q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
   }
-  cq = (q0 + q1) + (q2 + q3);
+  cq = fmaf(-static_cast<float>(32 - nc) * cm, cm, (q0 + q1) + (q2 + q3));
+}
+// Chan et al. merge of a chunk (nc values, mean cm, centred squares cq) into running (cnt, mean, m2).
+__device__ __forceinline__ void stats_merge(float& cnt, float& mean, float& m2, float nc, float cm, float cq) {
+  const float tot = cnt + nc, w = __fdividef(nc, tot), dlt = cm - mean;
+  mean = fmaf(dlt, w, mean);
+  m2 += fmaf(dlt * dlt, cnt * w, cq);
+  cnt = tot;
 }
 // wait until at most `pending` (1, 3 or 7) of this thread's bulk-store groups have not finished reading shared memory
 __device__ __forceinline__ void bulk_wait_read(int pending) {

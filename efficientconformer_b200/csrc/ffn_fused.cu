@@ -377,7 +377,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       float rr[32];
       slab_load_f32(xt_slab, lane, rr);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) t[j] = (j < nc) ? fmaf(0.5f, t[j] + sb2[c0 + j], rr[j]) : 0.f;
+      for (int j = 0; j < 32; ++j) t[j] = fmaf(0.5f, t[j] + sb2[c0 + j], rr[j]);
+      if (nc < 32) {                   // accumulator columns beyond the row are stale tensor memory: zero them
+#pragma unroll
+        for (int j = 0; j < 32; ++j) t[j] = (j < nc) ? t[j] : 0.f;
+      }
     }
     float cm, cq;
     chunk_stats(t, nc, cm, cq);
@@ -400,7 +404,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   if (mine) {
     merge_stats(0, mean, rstd);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) t[j] = (j < nc) ? (t[j] - mean) * rstd * sg1[c0 + j] + sbb1[c0 + j] : 0.f;
+    for (int j = 0; j < 32; ++j) t[j] = (t[j] - mean) * rstd * sg1[c0 + j] + sbb1[c0 + j];     // gamma = beta = 0 beyond the row
     if (p.ln_mode == 2) {                // block norm replaces x; it is the fp32 output
       slab_store_f32(xt_slab, lane, t);
       if (second) {
@@ -428,7 +432,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       merge_stats(1, mean, rstd);
       if (p.has_ln_out) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) t[j] = (j < nc) ? (t[j] - mean) * rstd * sg2[c0 + j] + sbb2[c0 + j] : 0.f;
+        for (int j = 0; j < 32; ++j) t[j] = (t[j] - mean) * rstd * sg2[c0 + j] + sbb2[c0 + j];
         slab_store_act<T>(ln_slab, lane, t);
         fence_proxy_async_smem();
         __syncwarp();

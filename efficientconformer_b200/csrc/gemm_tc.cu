@@ -161,7 +161,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ew = warp_idx - 2;                             // epilogue warp index
     const int half = ew >> 2;                                // which chunk parity this warp owns (kLN only)
     const int et = ew * 32 + lane;                           // index among the epilogue threads
-    const bool glu = p.glu_nb > 0;
+    const bool glu = !kLN && p.glu_nb > 0;                   // (the fused-LayerNorm variant is plain: no GLU, no activation)
     const int cols = glu ? p.glu_nb : p.block_n;             // logical output columns of this tile (multiple of 32 unless last tile)
     const int out_col0 = glu ? tile_n * p.glu_nb : w_row0;
     const int n_limit = glu ? p.glu_channels : p.N;
@@ -244,7 +244,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       if (i + 1 < my_chunks) tmem_ld_32x32(taddr + 32u * kHalves, v);   // v is consumed: prefetch this warp's next chunk
-      if (p.act == GEMM_ACT_SWISH) {
+      if (!kLN && p.act == GEMM_ACT_SWISH) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) t[j] = swish_fn<T>(t[j]);
       }
@@ -267,12 +267,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if constexpr (kLN) {
         // chunk statistics (two-pass inside the chunk), merged into the running row statistics (Chan et al.)
         const int nc = min(32, p.N - c0);
+        if (nc < 32) {                   // accumulator columns beyond the UMMA N are stale tensor memory: zero the tail
+#pragma unroll
+          for (int j = 0; j < 32; ++j) t[j] = (j < nc) ? t[j] : 0.f;
+        }
         float cm, cq;
         chunk_stats(t, nc, cm, cq);
-        const float tot = cnt + static_cast<float>(nc), dlt = cm - mean;
-        mean += dlt * static_cast<float>(nc) / tot;
-        m2 += cq + dlt * dlt * cnt * static_cast<float>(nc) / tot;
-        cnt = tot;
+        stats_merge(cnt, mean, m2, static_cast<float>(nc), cm, cq);
         slab_store_f32(wstage + c * kSlabBytes, lane, t);      // row tile stays resident for the normalise passes
         if (p.ln_mode == 1 && !batch) {                        // x itself is an output: store it now
           fence_proxy_async_smem();
@@ -351,10 +352,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           float cm, cq;
           chunk_stats(t, nc, cm, cq);
-          const float tot = cnt2 + static_cast<float>(nc), dlt = cm - mean2;
-          mean2 += dlt * static_cast<float>(nc) / tot;
-          m22 += cq + dlt * dlt * cnt2 * static_cast<float>(nc) / tot;
-          cnt2 = tot;
+          stats_merge(cnt2, mean2, m22, static_cast<float>(nc), cm, cq);
           slab_store_f32(wstage + c * kSlabBytes, lane, t);
           if (!batch) {
             fence_proxy_async_smem();

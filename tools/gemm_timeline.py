@@ -41,3 +41,9 @@ for prec in ("bf16", "tf32"):
     run(f"{prec} W2 16000x120x480 +res f32", lambda: ops.gemm(a480, w120, b120, prec, alpha=0.5, residual=res))
     run(f"{prec} W2 16000x120x480 +res LN1", lambda: ops.gemm_ln(a480, w120, b120, prec, g1, b1, mode=1, alpha=0.5, residual=res))
     run(f"{prec} W2 16000x120x480 +res LN2", lambda: ops.gemm_ln(a480, w120, b120, prec, g1, b1, g1, b1, mode=2, alpha=0.5, residual=res))
+    run(f"{prec} att-out 16000x120x120 +res LN1", lambda: ops.gemm_ln(a120, wsq, b120, prec, g1, b1, mode=1, alpha=1.0, residual=res))
+    a240 = ops.cast(torch.randn(4000, 240, device=dev), prec); w240 = ops.cast(torch.randn(240, 240, device=dev), prec)
+    b240 = torch.randn(240, device=dev); res240 = torch.randn(4000, 240, device=dev); g240, z240 = torch.ones(240, device=dev), torch.zeros(240, device=dev)
+    run(f"{prec} att-out 4000x240x240 +res LN1", lambda: ops.gemm_ln(a240, w240, b240, prec, g240, z240, mode=1, alpha=1.0, residual=res240))
+    w720 = ops.cast(torch.randn(720, 240, device=dev), prec); b720 = torch.randn(720, device=dev)
+    run(f"{prec} qkv 4000x720x240 ->act", lambda: ops.gemm(a240, w720, b720, prec, want_f32=False, want_act=True))
