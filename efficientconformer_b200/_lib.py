@@ -23,7 +23,7 @@ class BlockCfg(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("n_mels", C.c_int32), ("sub_filters", C.c_int32), ("num_blocks", C.c_int32), ("vocab", C.c_int32),
-                ("blocks", BlockCfg * EC_MAX_BLOCKS)]
+                ("sub_layers", C.c_int32), ("sub_filters2", C.c_int32), ("blocks", BlockCfg * EC_MAX_BLOCKS)]
 
 
 class FfnRaw(C.Structure):
@@ -39,6 +39,7 @@ class BlockRaw(C.Structure):
 
 class RawWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("sub_conv_w", "sub_conv_b", "sub_bn_w", "sub_bn_b", "sub_bn_rm", "sub_bn_rv",
+                                          "sub2_conv_w", "sub2_conv_b", "sub2_bn_w", "sub2_bn_b", "sub2_bn_rm", "sub2_bn_rv",
                                           "lin_w", "lin_b", "fc_w", "fc_b")] + [("blocks", BlockRaw * EC_MAX_BLOCKS)]
 
 

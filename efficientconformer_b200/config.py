@@ -21,6 +21,41 @@ CTC_SMALL_ENCODER_PARAMS = {
 CTC_SMALL_VOCAB = 256
 
 
+def _variant(**over):
+    p = dict(CTC_SMALL_ENCODER_PARAMS)
+    p.update(over)
+    return p
+
+
+def _conformer(num_blocks, dim, heads, **over):
+    """The non-progressive Conformer family (reference configs/Conformer*.json): two Conv2d subsampling layers (1/4 frame rate),
+    constant width, depthwise k = 31, no strided / expand blocks, ungrouped relative attention."""
+    p = _variant(num_blocks=num_blocks, dim_model=dim, num_heads=heads, kernel_size=31, subsampling_layers=2,
+                 subsampling_filters=[dim, dim], **over)
+    for k in ("conv_stride", "att_stride", "strided_blocks", "expand_blocks", "att_group_size"):
+        del p[k]
+    return p
+
+
+# encoder_params of every shipped ASR config (reference configs/*.json), keyed by the config file name; value = (params, vocab)
+SHIPPED_ENCODER_PARAMS = {
+    "EfficientConformerCTCSmall": (CTC_SMALL_ENCODER_PARAMS, 256),
+    "EfficientConformerCTCMedium": (_variant(num_blocks=16, dim_model=[180, 256, 360], strided_blocks=[4, 10], expand_blocks=[4, 10],
+                                             subsampling_filters=[180]), 256),
+    "EfficientConformerCTCLarge": (_variant(num_blocks=16, dim_model=[360, 512, 720], num_heads=8, strided_blocks=[4, 10],
+                                            expand_blocks=[4, 10], subsampling_filters=[360], mT=10), 256),
+    "EfficientConformerTransducerSmall": (_variant(dim_model=[100, 140, 200], subsampling_filters=[100], mT=10), 1000),
+    "EfficientConformerTransducerMedium": (_variant(dim_model=[180, 256, 360], subsampling_filters=[180], mT=10), 1000),
+    "EfficientConformerTransducerLarge": (_variant(dim_model=[360, 512, 720], num_heads=8, subsampling_filters=[360], mT=10), 1000),
+    "ConformerCTCSmall": (_conformer(16, 176, 4), 256),
+    "ConformerCTCMedium": (_conformer(18, 256, 4), 256),
+    "ConformerCTCLarge": (_conformer(18, 512, 8, mT=10), 256),
+    "ConformerTransducerSmall": (_conformer(16, 144, 6, mT=10), 1000),
+    "ConformerTransducerMedium": (_conformer(16, 256, 4, mT=10), 1000),
+    "ConformerTransducerLarge": (_conformer(17, 512, 8, mT=10), 1000),
+}
+
+
 @dataclass
 class BlockSpec:
     dim_model: int      # D  : width of FFN1 + attention

@@ -46,18 +46,21 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-constexpr int kAttBM = 64, kAttBN = 64, kGW = 80, kGStride = 81;
+constexpr int kAttBM = 64;
 
-template <int DPT, typename OutT>
+// BN = keys per tile: 64, or 32 for the widest heads (d = 135 of the Medium / Large grouped blocks) whose 64-key tiles do not fit
+// in shared memory.  The staged E band has kAttBM + BN rows, the per-warp score strip is 16 x (BN + 16).
+template <int DPT, typename OutT, int BN>
 __global__ void __launch_bounds__(128) relpos_attn_kernel(const AttnDev p) {
   constexpr int DP = DPT * 8, STR = DP + 4;
+  constexpr int kAttBN = BN, kGW = BN + 16, kGStride = kGW + 1, kBand = kAttBM + BN;
   extern __shared__ float sm[];
   float* Qu = sm;
   float* Qv = Qu + kAttBM * STR;
   float* Ks = Qv + kAttBM * STR;
   float* Vs = Ks + kAttBN * STR;
   float* Es = Vs + kAttBN * STR;
-  float* Gs = Es + 128 * STR;
+  float* Gs = Es + kBand * STR;
 
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * kAttBM;
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(128) relpos_attn_kernel(const AttnDev p) {
           cp_async_8(smem_u32(Vs + r * STR + cc), src + D, ok ? 8u : 0u);
         }
         const float* ecol = p.E + f0 + cc;
-        for (int r = rsub; r < 128; r += RPP) {
+        for (int r = rsub; r < kBand; r += RPP) {
           const int e = ebase + r;
           const bool ok = col_ok && e >= 0 && e <= 2 * Tg - 2;
           cp_async_8(smem_u32(Es + r * STR + cc), ok ? ecol + e * e_row : p.E, ok ? 8u : 0u);
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(128) relpos_attn_kernel(const AttnDev p) {
         cp_async_4(smem_u32(Ks + r * STR + c), src, bytes);
         cp_async_4(smem_u32(Vs + r * STR + c), src + D, bytes);
       }
-      for (int idx = tid; idx < 128 * DP; idx += 128) {
+      for (int idx = tid; idx < kBand * DP; idx += 128) {
         const int r = idx / DP, c = idx % DP;
         const int e = ebase + r;
         const bool ok = c < d && e >= 0 && e <= 2 * Tg - 2;
@@ -292,16 +295,17 @@ __global__ void __launch_bounds__(128) relpos_attn_kernel(const AttnDev p) {
 template <int DPT, typename OutT>
 static int launch_attn_inst(const AttnDev& p, cudaStream_t stream) {
   constexpr int STR = DPT * 8 + 4;
-  const size_t smem = sizeof(float) * (static_cast<size_t>(kAttBM) * STR * 2 + kAttBN * STR * 2 + 128 * STR + 4 * 16 * kGStride);
+  constexpr int BN = DPT > 16 ? 32 : 64;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(kAttBM) * STR * 2 + BN * STR * 2 + (kAttBM + BN) * STR + 4 * 16 * (BN + 17));
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(relpos_attn_kernel<DPT, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(relpos_attn_kernel<DPT, OutT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   EC_CUDA(attr_err);
   EC_REQUIRE(smem <= 227 * 1024, "attention tile does not fit in shared memory");
   dim3 grid(cdiv(p.Tg, kAttBM), p.H, p.B);
-  return launch_pdl(relpos_attn_kernel<DPT, OutT>, grid, dim3(128), smem, stream, p);
+  return launch_pdl(relpos_attn_kernel<DPT, OutT, BN>, grid, dim3(128), smem, stream, p);
 }
 
 template <typename T>

@@ -5,7 +5,8 @@
 // on channels-last activations (the GLU output of the pw1 GEMM epilogue), with NO length masking (padded frames
 // are computed densely like the reference).  Bandwidth-bound: each input element is read from global once per CTA
 // (16-byte vector loads into shared memory, halo included), each thread then slides a register window over time for
-// one channel, so shared memory is read ~(R*s+K-1)/R times per output; the output is written once.
+// one channel, so shared memory is read ~(R*s+K-1)/R times per output; the output is written once.  Models wider than
+// 256 channels (Medium / Large: up to 720) are tiled along the channel dim (grid.z), 256 channels per CTA.
 #include "ec_common.cuh"
 
 namespace ec {
@@ -13,10 +14,11 @@ namespace ec {
 constexpr int kDwR = 16;        // outputs per thread (register run along time)
 constexpr int kDwRuns = 4;      // runs per CTA  -> 64 output frames per CTA
 constexpr int kDwMaxK = 31;
+constexpr int kDwMaxTile = 256;  // channels per CTA
 
 template <typename T, int STRIDE, int K>
 __global__ void __launch_bounds__(1024) dwconv_bn_swish_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                                               int T_in, int T_out, int C, T* __restrict__ y) {
+                                                               int T_in, int T_out, int C, int CT, T* __restrict__ y) {
   using Tr = ActTraits<T>;
   extern __shared__ __align__(16) uint8_t dw_smem[];
   T* tile = reinterpret_cast<T*>(dw_smem);
@@ -29,50 +31,52 @@ __global__ void __launch_bounds__(1024) dwconv_bn_swish_kernel(const T* __restri
   const int ti0 = to0 * STRIDE - pad;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
 
-  // ---- global -> shared, 16-byte vectors; the (rows x C) slab is contiguous in memory (channels-last) ----
+  // ---- global -> shared, 16-byte vectors; a CTA stages the (rows x cw) slab of its channel tile [c0, c0 + cw) ----
   constexpr int VEC = 16 / sizeof(T);
-  const T* xb = x + static_cast<size_t>(b) * T_in * C;
-  const int total = rows * C;
-  if (C % VEC == 0) {
-    for (int i = tid * VEC; i < total; i += nthr * VEC) {
-      const int r = i / C;
+  const int c0 = blockIdx.z * CT, cw = min(CT, C - c0);
+  const T* xb = x + static_cast<size_t>(b) * T_in * C + c0;
+  if (C % VEC == 0 && CT % VEC == 0) {
+    const int nv = cw / VEC, total = rows * nv;          // cw is a multiple of VEC because C and CT are
+    for (int i = tid; i < total; i += nthr) {
+      const int r = i / nv, v = i - r * nv;
       const int tt = ti0 + r;
       uint4 val = make_uint4(0, 0, 0, 0);
-      if (tt >= 0 && tt < T_in) val = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(tt) * C + (i - r * C));
-      *reinterpret_cast<uint4*>(tile + i) = val;
+      if (tt >= 0 && tt < T_in) val = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(tt) * C + v * VEC);
+      *reinterpret_cast<uint4*>(tile + r * cw + v * VEC) = val;
     }
   } else {
+    const int total = rows * cw;
     for (int i = tid; i < total; i += nthr) {
-      const int r = i / C;
+      const int r = i / cw;
       const int tt = ti0 + r;
-      tile[i] = (tt >= 0 && tt < T_in) ? xb[static_cast<size_t>(tt) * C + (i - r * C)] : Tr::to(0.f);
+      tile[i] = (tt >= 0 && tt < T_in) ? xb[static_cast<size_t>(tt) * C + (i - r * cw)] : Tr::to(0.f);
     }
   }
   __syncthreads();
 
   const int c = threadIdx.x;
-  if (c >= C) return;
+  if (c >= cw) return;
   float wk[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) wk[k] = __ldg(w + c * K + k);
-  const float bc = __ldg(bias + c);
+  for (int k = 0; k < K; ++k) wk[k] = __ldg(w + (c0 + c) * K + k);
+  const float bc = __ldg(bias + c0 + c);
   const int run0 = threadIdx.y * kDwR;                  // first local output of this thread
   float acc[kDwR];
 #pragma unroll
   for (int r = 0; r < kDwR; ++r) acc[r] = bc;
   // input-stationary sweep: every staged input frame is read once and scattered into the outputs it feeds
   constexpr int in_rows = (kDwR - 1) * STRIDE + K;
-  const T* col = tile + static_cast<size_t>(run0 * STRIDE) * C + c;
+  const T* col = tile + static_cast<size_t>(run0 * STRIDE) * cw + c;
 #pragma unroll
   for (int i = 0; i < in_rows; ++i) {
-    const float v = Tr::from(col[static_cast<size_t>(i) * C]);
+    const float v = Tr::from(col[static_cast<size_t>(i) * cw]);
 #pragma unroll
     for (int r = 0; r < kDwR; ++r) {
       const int k = i - r * STRIDE;            // compile-time after full unrolling
       if (k >= 0 && k < K) acc[r] = fmaf(v, wk[k], acc[r]);
     }
   }
-  T* yb = y + static_cast<size_t>(b) * T_out * C;
+  T* yb = y + static_cast<size_t>(b) * T_out * C + c0;
 #pragma unroll
   for (int r = 0; r < kDwR; ++r) {
     const int to = to0 + run0 + r;
@@ -84,20 +88,21 @@ template <typename T>
 static int launch_dw_t(const DwConvArgs& a, cudaStream_t stream) {
   EC_REQUIRE(a.k % 2 == 1 && a.k <= kDwMaxK, "depthwise kernel size must be odd and <= 31");
   EC_REQUIRE(a.stride == 1 || a.stride == 2, "depthwise stride must be 1 or 2");
-  EC_REQUIRE(a.C <= 256, "depthwise conv supports up to 256 channels per CTA row");   // TODO(large models): channel tiling
   const int T_out = (a.T - 1) / a.stride + 1;
-  const int cx = round_up(a.C, 32);
+  const int CT = a.C <= kDwMaxTile ? a.C : kDwMaxTile;   // channel tile of a CTA (wide models: several tiles along grid.z)
+  const int cx = round_up(CT, 32);
   dim3 block(cx, kDwRuns);
-  dim3 grid(cdiv(T_out, kDwR * kDwRuns), a.B);
+  dim3 grid(cdiv(T_out, kDwR * kDwRuns), a.B, cdiv(a.C, CT));
   const int rows = (kDwR * kDwRuns - 1) * a.stride + a.k;
-  const size_t smem = align_up(static_cast<size_t>(rows) * a.C * sizeof(T), 16);
+  const size_t smem = align_up(static_cast<size_t>(rows) * CT * sizeof(T), 16);
+  EC_REQUIRE(smem <= 200 * 1024, "depthwise slab does not fit in shared memory");
   const T* x = reinterpret_cast<const T*>(a.x);
   T* y = reinterpret_cast<T*>(a.y);
 #define EC_DW_CASE(S, KK)                                                                                              \
   if (a.stride == S && a.k == KK) {                                                                                    \
     static cudaError_t e = cudaFuncSetAttribute(dwconv_bn_swish_kernel<T, S, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
     EC_CUDA(e);                                                                                                        \
-    return launch_pdl(dwconv_bn_swish_kernel<T, S, KK>, grid, block, smem, stream, x, a.w, a.b, a.T, T_out, a.C, y);   \
+    return launch_pdl(dwconv_bn_swish_kernel<T, S, KK>, grid, block, smem, stream, x, a.w, a.b, a.T, T_out, a.C, CT, y); \
   }
   EC_DW_CASE(1, 15) EC_DW_CASE(2, 15) EC_DW_CASE(1, 31) EC_DW_CASE(2, 31)
 #undef EC_DW_CASE

@@ -191,13 +191,19 @@ struct SubsampleArgs {
   void* y;               // [B, T_out, C*F/2] activation type, feature = c*(F/2) + f
 };
 int launch_subsample_conv(int precision, const SubsampleArgs& a, cudaStream_t stream);
+// two-layer front end: channels-last layer 0 (y = [B, T_out, F/2, C]), im2col for the 3x3/s2 layer 1, weight preparation
+int launch_subsample_conv_cl(int precision, const SubsampleArgs& a, cudaStream_t stream);
+int launch_im2col_3x3s2(int precision, const void* y0, int B, int T1, int F1, int C, void* A, cudaStream_t stream);
+int launch_conv2_weight_prep(int precision, const float* w, const float* b, const float* g, const float* beta, const float* rm,
+                             const float* rv, float eps, int C2, int C, void* w_out, float* b_out, cudaStream_t stream);
+int launch_linear_weight_permute(int precision, const float* w, int D, int C, int Fq, void* out, cudaStream_t stream);
 
 int launch_cast_rows(int precision, const float* src, void* dst, size_t n, cudaStream_t stream);   // fp32 -> activation type
 int launch_fold_bn(const float* w, const float* b, const float* g, const float* beta, const float* rm, const float* rv,
                    float eps, int C, int taps, float* w_out, float* b_out, cudaStream_t stream);
 int launch_glu_interleave(int precision, const float* w, const float* b, int channels, int K, int nb, int tiles,
                           void* w_out, float* b_out, cudaStream_t stream);
-struct BlockStrides { int n; int s[EC_MAX_BLOCKS]; };
+struct BlockStrides { int n; int sub_layers; int s[EC_MAX_BLOCKS]; };
 int launch_stage_lengths(const long long* x_len, int B, int t_mel, const BlockStrides& st, int* out, cudaStream_t stream);
 int launch_i64_to_i32(const long long* src, int n, int* dst, int clamp_max, cudaStream_t stream);
 int launch_i32_to_i64(const int* src, int n, long long* dst, cudaStream_t stream);

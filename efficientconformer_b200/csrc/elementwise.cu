@@ -164,7 +164,7 @@ __global__ void stage_lengths_kernel(const long long* x_len, int B, int t_mel, B
   if (b >= B) return;
   long long l = x_len != nullptr ? x_len[b] : t_mel;
   if (l > t_mel) l = t_mel;
-  l = l > 0 ? (l - 1) / 2 + 1 : 0;
+  for (int i = 0; i < st.sub_layers; ++i) l = l > 0 ? (l - 1) / 2 + 1 : 0;   // one halving per Conv2d subsampling layer
   out[b] = static_cast<int>(l);
   for (int i = 0; i < st.n; ++i) {
     if (l > 0) l = (l - 1) / st.s[i] + 1;

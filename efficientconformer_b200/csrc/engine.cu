@@ -40,7 +40,7 @@ struct BlockW {
   int glu_nb, glu_tiles;
 };
 struct Weights {
-  float *sub_w, *sub_b; void* lin_w; float* lin_b; void* fc_w; float* fc_b;
+  float *sub_w, *sub_b; void* sub2_w; float* sub2_b; void* lin_w; float* lin_b; void* fc_w; float* fc_b;
   BlockW blk[EC_MAX_BLOCKS];
 };
 
@@ -49,10 +49,11 @@ struct Weights {
 namespace ec {
 // kernel categories of one forward (profiling / launch accounting)
 enum ProfCat { PC_SUBSAMPLE = 0, PC_LIN, PC_LAYERNORM, PC_FFN_W1, PC_FFN_W2, PC_QKV, PC_POS, PC_ATTN, PC_OUT, PC_PW1_GLU, PC_DWCONV,
-               PC_RES, PC_PW2, PC_FC, PC_MISC, PC_FFN_FUSED, PC_COUNT };
+               PC_RES, PC_PW2, PC_FC, PC_MISC, PC_FFN_FUSED, PC_IM2COL, PC_SUB_CONV2, PC_COUNT };
 static const char* kProfNames[PC_COUNT] = {"subsample_conv", "gemm_sub_linear", "layernorm", "gemm_ffn_w1_swish", "gemm_ffn_w2_res",
                                            "gemm_qkv", "gemm_pos", "relpos_attention", "gemm_att_out_res", "gemm_pw1_glu",
-                                           "dwconv_bn_swish", "gemm_conv_res", "gemm_pw2_res", "gemm_fc", "misc", "ffn_fused"};
+                                           "dwconv_bn_swish", "gemm_conv_res", "gemm_pw2_res", "gemm_fc", "misc", "ffn_fused", "im2col_3x3s2",
+                                           "gemm_sub_conv2_swish"};
 struct ProfEntry { int cat; double flops, bytes; cudaEvent_t e0, e1; };
 }  // namespace ec
 
@@ -85,6 +86,11 @@ static void pick_glu(int channels, int* nb, int* tiles) {
   *nb = *tiles == 1 ? round_up(channels, 8) : round_up(cdiv(channels, *tiles), 32);
 }
 
+// width of the Linear that follows the Conv2d subsampling: C_last * n_mels / 2^layers (reference models/encoders.py:71)
+static int sub_features(const ec_config& c) {
+  return c.sub_layers == 2 ? c.sub_filters2 * (c.n_mels / 4) : c.sub_filters * (c.n_mels / 2);
+}
+
 // Lays the prepared-weights arena out (dry run when arena == nullptr); fills e->w with pointers.
 static size_t layout_weights(ec_engine* e, void* arena) {
   Arena a(arena);
@@ -93,9 +99,11 @@ static size_t layout_weights(ec_engine* e, void* arena) {
   Weights& w = e->w;
   auto f32 = [&](size_t n) { return reinterpret_cast<float*>(a.take(n * 4)); };
   auto act = [&](size_t n) { return a.take(n * es); };
-  const int C = c.sub_filters, F2 = c.n_mels / 2, D0 = c.blocks[0].dim_model;
+  const int C = c.sub_filters, D0 = c.blocks[0].dim_model;
   w.sub_w = f32(C * 9); w.sub_b = f32(C);
-  w.lin_w = act(static_cast<size_t>(D0) * C * F2); w.lin_b = f32(D0);
+  if (c.sub_layers == 2) { w.sub2_w = act(static_cast<size_t>(c.sub_filters2) * 9 * C); w.sub2_b = f32(c.sub_filters2); }
+  else { w.sub2_w = nullptr; w.sub2_b = nullptr; }
+  w.lin_w = act(static_cast<size_t>(D0) * sub_features(c)); w.lin_b = f32(D0);
   for (int i = 0; i < c.num_blocks; ++i) {
     const ec_block_cfg& bc = c.blocks[i];
     const int D = bc.dim_model, De = bc.dim_expand, Fr = bc.ff_ratio;
@@ -127,12 +135,15 @@ static size_t layout_weights(ec_engine* e, void* arena) {
 }
 
 struct Shapes {   // per-block frame counts for one (batch, t_mel)
+  int t_sub1;                     // frames after the first Conv2d subsampling layer
   int t0;                         // frames after subsampling
   int t_in[EC_MAX_BLOCKS], t_out[EC_MAX_BLOCKS];
   int t_final;
 };
 static void compute_shapes(const ec_config& c, int t_mel, Shapes* s) {
   int t = (t_mel - 1) / 2 + 1;
+  s->t_sub1 = t;
+  if (c.sub_layers == 2) t = (t - 1) / 2 + 1;
   s->t0 = t;
   for (int i = 0; i < c.num_blocks; ++i) {
     s->t_in[i] = t;
@@ -143,7 +154,7 @@ static void compute_shapes(const ec_config& c, int t_mel, Shapes* s) {
 }
 
 struct Workspace {
-  int* lens; void* sub_a; float *xa, *xb; void *xn, *xs, *h; float* qkv; float* ebuf; void *o, *gl, *hc; float* r;
+  int* lens; void* sub_a; void *sub_y0, *sub_col; float *xa, *xb; void *xn, *xs, *h; float* qkv; float* ebuf; void *o, *gl, *hc; float* r;
   size_t e_stride;   // bytes between the per-block E buffers
   size_t bytes;
 };
@@ -166,7 +177,11 @@ static void layout_workspace(const ec_engine* e, int B, int t_mel, void* base, W
   }
   Arena a(base);
   ws->lens = reinterpret_cast<int*>(a.take(sizeof(int) * (c.num_blocks + 1) * B));
-  ws->sub_a = a.take(static_cast<size_t>(B) * sh.t0 * c.sub_filters * (c.n_mels / 2) * es);
+  ws->sub_a = a.take(static_cast<size_t>(B) * sh.t0 * sub_features(c) * es);       // operand of the subsampling Linear
+  if (c.sub_layers == 2) {   // channels-last layer-0 map and the im2col operand of the layer-1 GEMM
+    ws->sub_y0 = a.take(static_cast<size_t>(B) * sh.t_sub1 * (c.n_mels / 2) * c.sub_filters * es);
+    ws->sub_col = a.take(static_cast<size_t>(B) * sh.t0 * (c.n_mels / 4) * 9 * c.sub_filters * es);
+  } else { ws->sub_y0 = nullptr; ws->sub_col = nullptr; }
   ws->xa = reinterpret_cast<float*>(a.take(mx_x * 4));
   ws->xb = reinterpret_cast<float*>(a.take(mx_x * 4));
   ws->xn = a.take(mx_x * es);
@@ -270,6 +285,9 @@ int ec_engine_create(const ec_config* cfg, int precision, ec_engine** out) {
   EC_REQUIRE(precision == EC_PREC_TF32 || precision == EC_PREC_BF16, "unknown precision");
   EC_REQUIRE(cfg->num_blocks >= 1 && cfg->num_blocks <= EC_MAX_BLOCKS, "num_blocks out of range");
   EC_REQUIRE(cfg->n_mels > 0 && cfg->n_mels % 2 == 0 && cfg->sub_filters > 0, "bad front-end config");
+  EC_REQUIRE(cfg->sub_layers >= 0 && cfg->sub_layers <= 2, "1 or 2 Conv2d subsampling layers are supported");
+  if (cfg->sub_layers == 2)
+    EC_REQUIRE(cfg->n_mels % 4 == 0 && cfg->sub_filters % 8 == 0 && cfg->sub_filters2 > 0, "two-layer subsampling needs n_mels % 4 == 0 and filters % 8 == 0");
   for (int i = 0; i < cfg->num_blocks; ++i) {
     const ec_block_cfg& b = cfg->blocks[i];
     EC_REQUIRE(b.dim_model > 0 && b.dim_expand > 0 && b.num_heads > 0 && b.ff_ratio > 0, "bad block dims");
@@ -280,7 +298,8 @@ int ec_engine_create(const ec_config* cfg, int precision, ec_engine** out) {
     if (i > 0) EC_REQUIRE(cfg->blocks[i - 1].dim_expand == b.dim_model, "block dims do not chain");
   }
   ec_engine* e = new ec_engine();
-  e->cfg = *cfg; e->precision = precision; e->esize = precision == EC_PREC_TF32 ? 4 : 2; e->prepared = false;
+  e->cfg = *cfg; if (e->cfg.sub_layers == 0) e->cfg.sub_layers = 1;
+  e->precision = precision; e->esize = precision == EC_PREC_TF32 ? 4 : 2; e->prepared = false;
   e->weight_bytes = layout_weights(e, nullptr);
   *out = e;
   return EC_OK;
@@ -330,10 +349,19 @@ int ec_engine_prepare(ec_engine* e, const ec_raw_weights* raw, void* arena, void
     EC_REQUIRE(src != nullptr, "missing raw weight pointer");
     return launch_cast_rows(prec, src, dst, n, st);
   };
-  const int C = c.sub_filters, F2 = c.n_mels / 2, D0 = c.blocks[0].dim_model;
+  const int C = c.sub_filters, D0 = c.blocks[0].dim_model;
   EC_REQUIRE(raw->sub_conv_w && raw->sub_conv_b && raw->sub_bn_w && raw->sub_bn_b && raw->sub_bn_rm && raw->sub_bn_rv, "missing subsampling weights");
   EC_TRY(launch_fold_bn(raw->sub_conv_w, raw->sub_conv_b, raw->sub_bn_w, raw->sub_bn_b, raw->sub_bn_rm, raw->sub_bn_rv, 1e-5f, C, 9, w.sub_w, w.sub_b, st));
-  EC_TRY(cast(w.lin_w, raw->lin_w, static_cast<size_t>(D0) * C * F2));
+  if (c.sub_layers == 2) {
+    EC_REQUIRE(raw->sub2_conv_w && raw->sub2_conv_b && raw->sub2_bn_w && raw->sub2_bn_b && raw->sub2_bn_rm && raw->sub2_bn_rv,
+               "missing weights of the second subsampling layer");
+    EC_TRY(launch_conv2_weight_prep(prec, raw->sub2_conv_w, raw->sub2_conv_b, raw->sub2_bn_w, raw->sub2_bn_b, raw->sub2_bn_rm, raw->sub2_bn_rv,
+                                    1e-5f, c.sub_filters2, C, w.sub2_w, w.sub2_b, st));
+    EC_REQUIRE(raw->lin_w != nullptr, "missing raw weight pointer");
+    EC_TRY(launch_linear_weight_permute(prec, raw->lin_w, D0, c.sub_filters2, c.n_mels / 4, w.lin_w, st));
+  } else {
+    EC_TRY(cast(w.lin_w, raw->lin_w, static_cast<size_t>(D0) * sub_features(c)));
+  }
   EC_TRY(cp(w.lin_b, raw->lin_b, D0));
   for (int i = 0; i < c.num_blocks; ++i) {
     const ec_block_cfg& bc = c.blocks[i];
@@ -396,7 +424,7 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
   }
   const double es = static_cast<double>(e->esize);
 
-  BlockStrides bs{}; bs.n = c.num_blocks;
+  BlockStrides bs{}; bs.n = c.num_blocks; bs.sub_layers = c.sub_layers;
   for (int i = 0; i < c.num_blocks; ++i) bs.s[i] = c.blocks[i].conv_stride;
   { ProfScope ps(e, st, PC_MISC, 0, 0); EC_TRY(launch_stage_lengths(x_len, B, t_mel, bs, ws.lens, st)); }
 
@@ -420,25 +448,53 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
   EC_CUDA(cudaEventRecord(e->ev_join, e->side));
   bool joined = false;
 
-  // ---- front end: Conv2d+BN+Swish producer, then Linear (K = C*F/2) ----
-  const int feat = c.sub_filters * (c.n_mels / 2);
-  {
+  // ---- front end: Conv2d+BN+Swish producer(s), then Linear (K = C_last * F / 2^layers) ----
+  const int feat = sub_features(c);
+  if (c.sub_layers == 2) {
+    // layer 0 channels-last -> im2col -> layer 1 on the tensor cores (Swish in the epilogue); see subsample.cu
+    const int C = c.sub_filters, C2 = c.sub_filters2, F1 = c.n_mels / 2, F2 = c.n_mels / 4, T1 = sh.t_sub1, T2 = sh.t0;
+    {
+      SubsampleArgs sa{mel, w.sub_w, w.sub_b, B, c.n_mels, t_mel, C, ws.sub_y0};
+      ProfScope ps(e, st, PC_SUBSAMPLE, 18.0 * B * T1 * F1 * C, 4.0 * B * c.n_mels * t_mel + es * B * T1 * F1 * C);
+      EC_TRY(launch_subsample_conv_cl(prec, sa, st));
+    }
+    {
+      ProfScope ps(e, st, PC_IM2COL, 0, es * (static_cast<double>(B) * T1 * F1 * C + static_cast<double>(B) * T2 * F2 * 9 * C));
+      EC_TRY(launch_im2col_3x3s2(prec, ws.sub_y0, B, T1, F1, C, ws.sub_col, st));
+    }
+    EC_TRY(gemm(e, st, PC_SUB_CONV2, ws.sub_col, w.sub2_w, B * T2 * F2, C2, 9 * C, w.sub2_b, 1.f, GEMM_ACT_SWISH, nullptr, nullptr, ws.sub_a));
+  } else {
     SubsampleArgs sa{mel, w.sub_w, w.sub_b, B, c.n_mels, t_mel, c.sub_filters, ws.sub_a};
     ProfScope ps(e, st, PC_SUBSAMPLE, 18.0 * B * sh.t0 * feat, 4.0 * B * c.n_mels * t_mel + es * B * sh.t0 * feat);
     EC_TRY(launch_subsample_conv(prec, sa, st));
   }
   const int D0 = c.blocks[0].dim_model;
   float* x = ws.xa; float* x_alt = ws.xb;
-  bool fuse = e->fuse_ln;
-  for (int i = 0; i < c.num_blocks; ++i) fuse = fuse && c.blocks[i].dim_model <= 256 && c.blocks[i].dim_expand <= 256;
-  bool fuse_ffn = fuse && e->fuse_ffn && prec == EC_PREC_BF16;
-  for (int i = 0; i < c.num_blocks && fuse_ffn; ++i)
-    fuse_ffn = ffn_fused_fits(B * sh.t_in[i], c.blocks[i].dim_model, c.blocks[i].ff_ratio * c.blocks[i].dim_model) &&
-               ffn_fused_fits(B * sh.t_out[i], c.blocks[i].dim_expand, c.blocks[i].ff_ratio * c.blocks[i].dim_expand);
+
+  // GEMM followed by the LayerNorm(s) the next module needs: in the GEMM's own epilogue when the row fits one tile (N <= 256) and
+  // fuse_ln is on, else as separate row kernels with identical semantics (LnFuse modes 1 / 2 of GemmArgs).
+  auto gemm_ln = [&](int cat, const void* A, const void* W, int M, int N, int K, const float* bias, float alpha, const float* residual,
+                     float* out_f32, const LnFuse& ln) -> int {
+    if (e->fuse_ln && N <= 256) return gemm(e, st, cat, A, W, M, N, K, bias, alpha, GEMM_ACT_NONE, residual, out_f32, nullptr, 0, 0, &ln);
+    EC_TRY(gemm(e, st, cat, A, W, M, N, K, bias, alpha, GEMM_ACT_NONE, residual, out_f32, nullptr));
+    if (ln.mode == 1) return lnorm(e, st, out_f32, M, N, ln.g1, ln.b1, ln.y, nullptr, ln.copy_out, ln.copy_stride, ln.fps, ln.fops);
+    // mode 2: out <- LN1(out) in place (a warp holds its whole row in registers before it writes), then y = LN2(out) or its rounded copy
+    if (ln.g2 == nullptr) return lnorm(e, st, out_f32, M, N, ln.g1, ln.b1, ln.y, out_f32);
+    EC_TRY(lnorm(e, st, out_f32, M, N, ln.g1, ln.b1, nullptr, out_f32));
+    return lnorm(e, st, out_f32, M, N, ln.g2, ln.b2, ln.y, nullptr);
+  };
+  // whole feed-forward module: one cluster kernel when the shape fits (bf16 mode), else W1 GEMM (+Swish) and W2 GEMM (+residual, LN)
+  auto ffn = [&](const FfnW& f, int M, int D, int hidden, const float* residual, float* out_f32, const LnFuse& ln) -> int {
+    if (e->fuse_ln && e->fuse_ffn && prec == EC_PREC_BF16 && ffn_fused_fits(M, D, hidden))
+      return ffn_fused(e, st, ws.xn, f.w1, f.b1, f.w2, f.b2, M, D, hidden, residual, out_f32, ln);
+    EC_TRY(gemm(e, st, PC_FFN_W1, ws.xn, f.w1, M, hidden, D, f.b1, 1.f, GEMM_ACT_SWISH, nullptr, nullptr, ws.h));
+    return gemm_ln(PC_FFN_W2, ws.h, f.w2, M, D, hidden, f.b2, 0.5f, residual, out_f32, ln);
+  };
+
   {
-    LnFuse ln;   // fused: xn = LN_ffn1(x0) for block 0
-    if (fuse) { ln.mode = 1; ln.g1 = w.blk[0].ffn1.ln_w; ln.b1 = w.blk[0].ffn1.ln_b; ln.y = ws.xn; }
-    EC_TRY(gemm(e, st, PC_LIN, ws.sub_a, w.lin_w, B * sh.t0, D0, feat, w.lin_b, 1.f, GEMM_ACT_NONE, nullptr, x, nullptr, 0, 0, &ln));
+    LnFuse ln;   // x0 = Linear(sub), xn = LN_ffn1(x0) for block 0
+    ln.mode = 1; ln.g1 = w.blk[0].ffn1.ln_w; ln.b1 = w.blk[0].ffn1.ln_b; ln.y = ws.xn;
+    EC_TRY(gemm_ln(PC_LIN, ws.sub_a, w.lin_w, B * sh.t0, D0, feat, w.lin_b, 1.f, nullptr, x, ln));
   }
 
   for (int i = 0; i < c.num_blocks; ++i) {
@@ -450,21 +506,14 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
     const int* lens = ws.lens + static_cast<size_t>(i) * B;
     const bool proj = D != De;
     const bool last = i == c.num_blocks - 1;
-    // FFN1: x1 = x + 0.5 * W2 swish(W1 LN(x))          [fused: epilogue also emits xn = LN_att(x1)]
-    if (!fuse) EC_TRY(lnorm(e, st, x, M, D, b.ffn1.ln_w, b.ffn1.ln_b, ws.xn, nullptr));
-    if (fuse_ffn) {
+    // FFN1: x1 = x + 0.5 * W2 swish(W1 LN(x)); also emits xn = LN_att(x1)
+    {
       LnFuse ln;
       ln.mode = 1; ln.g1 = b.att_ln_w; ln.b1 = b.att_ln_b; ln.y = ws.xn;
-      EC_TRY(ffn_fused(e, st, ws.xn, b.ffn1.w1, b.ffn1.b1, b.ffn1.w2, b.ffn1.b2, M, D, Fr * D, x, x_alt, ln));
-    } else {
-      EC_TRY(gemm(e, st, PC_FFN_W1, ws.xn, b.ffn1.w1, M, Fr * D, D, b.ffn1.b1, 1.f, GEMM_ACT_SWISH, nullptr, nullptr, ws.h));
-      LnFuse ln;
-      if (fuse) { ln.mode = 1; ln.g1 = b.att_ln_w; ln.b1 = b.att_ln_b; ln.y = ws.xn; }
-      EC_TRY(gemm(e, st, PC_FFN_W2, ws.h, b.ffn1.w2, M, D, Fr * D, b.ffn1.b2, 0.5f, GEMM_ACT_NONE, x, x_alt, nullptr, 0, 0, &ln));
+      EC_TRY(ffn(b.ffn1, M, D, Fr * D, x, x_alt, ln));
     }
     std::swap(x, x_alt);
-    // MHSA: x2 = x1 + Wo attn(LN(x1))                   [fused: epilogue emits xn = LN_conv(x2) and the strided copy xs]
-    if (!fuse) EC_TRY(lnorm(e, st, x, M, D, b.att_ln_w, b.att_ln_b, ws.xn, nullptr));
+    // MHSA: x2 = x1 + Wo attn(LN(x1)); also emits xn = LN_conv(x2) and the strided copy xs (conv_res operand)
     // q|k|v and E feed the attention kernel: TF32-rounded fp32 in parity mode, bf16 in fast mode
     const bool a16 = prec == EC_PREC_BF16 && ((bc.group_size * D) / bc.num_heads) % 2 == 0 && D % 2 == 0;
     EC_TRY(gemm(e, st, PC_QKV, ws.xn, b.wqkv, M, 3 * D, D, b.bqkv, 1.f, GEMM_ACT_NONE, nullptr, a16 ? nullptr : ws.qkv, a16 ? ws.qkv : nullptr, 0, 0, nullptr, 1));
@@ -480,15 +529,12 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
     }
     {
       LnFuse ln;
-      if (fuse) {
-        ln.mode = 1; ln.g1 = b.conv_ln_w; ln.b1 = b.conv_ln_b; ln.y = ws.xn;
-        if (proj) { ln.copy_out = ws.xs; ln.copy_stride = bc.conv_stride; ln.fps = T; ln.fops = To; }
-      }
-      EC_TRY(gemm(e, st, PC_OUT, ws.o, b.wo, M, D, D, b.bo, 1.f, GEMM_ACT_NONE, x, x_alt, nullptr, 0, 0, &ln));
+      ln.mode = 1; ln.g1 = b.conv_ln_w; ln.b1 = b.conv_ln_b; ln.y = ws.xn;
+      if (proj) { ln.copy_out = ws.xs; ln.copy_stride = bc.conv_stride; ln.fps = T; ln.fops = To; }
+      EC_TRY(gemm_ln(PC_OUT, ws.o, b.wo, M, D, D, b.bo, 1.f, x, x_alt, ln));
     }
     std::swap(x, x_alt);
-    // Conv module: x3 = conv_res(x2) + pw2 swish(bn(dw(glu(pw1 LN(x2)))))     [fused: epilogue emits xn = LN_ffn2(x3)]
-    if (!fuse) EC_TRY(lnorm(e, st, x, M, D, b.conv_ln_w, b.conv_ln_b, ws.xn, nullptr, proj ? ws.xs : nullptr, bc.conv_stride, T, To));
+    // Conv module: x3 = conv_res(x2) + pw2 swish(bn(dw(glu(pw1 LN(x2))))); also emits xn = LN_ffn2(x3)
     EC_TRY(gemm(e, st, PC_PW1_GLU, ws.xn, b.pw1, M, b.glu_tiles * 2 * b.glu_nb, D, b.pw1_b, 1.f, GEMM_ACT_NONE, nullptr, nullptr, ws.gl, b.glu_nb, De));
     {
       DwConvArgs da{ws.gl, b.dw_w, b.dw_b, B, T, De, bc.kernel_size, bc.conv_stride, ws.hc};
@@ -502,28 +548,20 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
     }
     {
       LnFuse ln;
-      if (fuse) { ln.mode = 1; ln.g1 = b.ffn2.ln_w; ln.b1 = b.ffn2.ln_b; ln.y = ws.xn; }
-      EC_TRY(gemm(e, st, PC_PW2, ws.hc, b.pw2, Mo, De, De, b.pw2_b, 1.f, GEMM_ACT_NONE, res, x_alt, nullptr, 0, 0, &ln));
+      ln.mode = 1; ln.g1 = b.ffn2.ln_w; ln.b1 = b.ffn2.ln_b; ln.y = ws.xn;
+      EC_TRY(gemm_ln(PC_PW2, ws.hc, b.pw2, Mo, De, De, b.pw2_b, 1.f, res, x_alt, ln));
     }
     std::swap(x, x_alt);
-    // FFN2 + block LayerNorm        [fused: epilogue normalises in place (block norm) and emits the next GEMM's operand]
-    if (!fuse) EC_TRY(lnorm(e, st, x, Mo, De, b.ffn2.ln_w, b.ffn2.ln_b, ws.xn, nullptr));
-    if (!fuse_ffn) EC_TRY(gemm(e, st, PC_FFN_W1, ws.xn, b.ffn2.w1, Mo, Fr * De, De, b.ffn2.b1, 1.f, GEMM_ACT_SWISH, nullptr, nullptr, ws.h));
-    float* y = (last && out_x != nullptr) ? out_x : x_alt;
-    if (fuse) {
+    // FFN2 + block LayerNorm: normalises in place (block norm) and emits the next GEMM's operand
+    // (LN_ffn1 of the next block, or the rounded block output for the fc head)
+    {
+      float* y = (last && out_x != nullptr) ? out_x : x_alt;
       LnFuse ln;
       ln.mode = 2; ln.g1 = b.norm_w; ln.b1 = b.norm_b;
       if (!last) { ln.g2 = w.blk[i + 1].ffn1.ln_w; ln.b2 = w.blk[i + 1].ffn1.ln_b; ln.y = ws.xn; }
-      else { ln.g2 = nullptr; ln.b2 = nullptr; ln.y = logits != nullptr ? ws.xn : nullptr; }     // fc operand = rounded copy of the block output
-      if (fuse_ffn) EC_TRY(ffn_fused(e, st, ws.xn, b.ffn2.w1, b.ffn2.b1, b.ffn2.w2, b.ffn2.b2, Mo, De, Fr * De, x, y, ln));
-      else EC_TRY(gemm(e, st, PC_FFN_W2, ws.h, b.ffn2.w2, Mo, De, Fr * De, b.ffn2.b2, 0.5f, GEMM_ACT_NONE, x, y, nullptr, 0, 0, &ln));
+      else { ln.g2 = nullptr; ln.b2 = nullptr; ln.y = logits != nullptr ? ws.xn : nullptr; }
+      EC_TRY(ffn(b.ffn2, Mo, De, Fr * De, x, y, ln));
       if (!(last && out_x != nullptr)) x_alt = x, x = y;
-    } else {
-      EC_TRY(gemm(e, st, PC_FFN_W2, ws.h, b.ffn2.w2, Mo, De, Fr * De, b.ffn2.b2, 0.5f, GEMM_ACT_NONE, x, x_alt, nullptr));
-      std::swap(x, x_alt);
-      y = (last && out_x != nullptr) ? out_x : x_alt;
-      EC_TRY(lnorm(e, st, x, Mo, De, b.norm_w, b.norm_b, (last && logits != nullptr) ? ws.xn : nullptr, y));
-      if (!(last && out_x != nullptr)) std::swap(x, x_alt);
     }
   }
   if (logits != nullptr) {

@@ -107,12 +107,13 @@ class _PreprocessingHolder(nn.Module):
         return x, x_len
 
 
-class _SubsamplingHolder(nn.Module):      # reference models/modules.py:201-230 (single Conv2d layer)
+class _SubsamplingHolder(nn.Module):      # reference models/modules.py:201-230 (one or two strided Conv2d layers)
     def __init__(self, params):
         super().__init__()
-        C_out, ks = params["subsampling_filters"][0], params["subsampling_kernel_size"]
-        self.layers = nn.ModuleList([nn.Sequential(nn.Conv2d(1, C_out, ks, stride=2, padding=(ks - 1) // 2),
-                                                   nn.BatchNorm2d(C_out), nn.Identity())])
+        filters, ks = params["subsampling_filters"], params["subsampling_kernel_size"]
+        self.layers = nn.ModuleList([nn.Sequential(
+            nn.Conv2d(1 if l == 0 else filters[l - 1], filters[l], ks, stride=2, padding=(ks - 1) // 2),
+            nn.BatchNorm2d(filters[l]), nn.Identity()) for l in range(params["subsampling_layers"])])
 
 
 def relative_sinusoid_rows(t_pad: int, dim: int, group: int, max_len: int) -> torch.Tensor:
@@ -142,8 +143,9 @@ class ConformerEncoder(nn.Module):
 
     def __init__(self, params, precision: str = "auto", use_cuda_graph: bool = True):
         super().__init__()
-        if params.get("subsampling_module") != "Conv2d" or params.get("subsampling_layers") != 1:
-            raise NotImplementedError("this round supports the Efficient Conformer front end: one Conv2d subsampling layer")
+        if params.get("subsampling_module") != "Conv2d" or params.get("subsampling_layers") not in (1, 2) \
+                or params.get("subsampling_kernel_size") != 3:
+            raise NotImplementedError("supported front ends: one (Efficient Conformer) or two (Conformer) 3x3 Conv2d subsampling layers")
         if params.get("subsampling_norm") != "batch" or params.get("subsampling_act") != "swish":
             raise NotImplementedError("only subsampling_norm=batch / subsampling_act=swish (all shipped configs)")
         self.params = dict(params)
@@ -182,6 +184,8 @@ class ConformerEncoder(nn.Module):
         cfg = _lib.Config()
         cfg.n_mels = self.params["n_mels"]
         cfg.sub_filters = self.params["subsampling_filters"][0]
+        cfg.sub_layers = self.params["subsampling_layers"]
+        cfg.sub_filters2 = self.params["subsampling_filters"][1] if cfg.sub_layers == 2 else 0
         cfg.num_blocks = len(self.specs)
         cfg.vocab = self._head.out_features if self._head is not None else 0
         for i, s in enumerate(self.specs):
@@ -201,6 +205,10 @@ class ConformerEncoder(nn.Module):
         sub = self.subsampling_module.layers[0]
         raw.sub_conv_w, raw.sub_conv_b = p(sub[0].weight), p(sub[0].bias)
         raw.sub_bn_w, raw.sub_bn_b, raw.sub_bn_rm, raw.sub_bn_rv = p(sub[1].weight), p(sub[1].bias), p(sub[1].running_mean), p(sub[1].running_var)
+        if len(self.subsampling_module.layers) == 2:
+            sub = self.subsampling_module.layers[1]
+            raw.sub2_conv_w, raw.sub2_conv_b = p(sub[0].weight), p(sub[0].bias)
+            raw.sub2_bn_w, raw.sub2_bn_b, raw.sub2_bn_rm, raw.sub2_bn_rv = p(sub[1].weight), p(sub[1].bias), p(sub[1].running_mean), p(sub[1].running_var)
         raw.lin_w, raw.lin_b = p(self.linear.weight), p(self.linear.bias)
         if self._head is not None:
             raw.fc_w, raw.fc_b = p(self._head.weight), p(self._head.bias)

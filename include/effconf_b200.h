@@ -48,10 +48,12 @@ typedef struct ec_block_cfg {
 } ec_block_cfg;
 
 typedef struct ec_config {
-  int32_t n_mels;      /* 80 */
-  int32_t sub_filters; /* C of the single Conv2d subsampling layer */
+  int32_t n_mels;       /* 80 */
+  int32_t sub_filters;  /* C of the first Conv2d subsampling layer (1 -> C) */
   int32_t num_blocks;
-  int32_t vocab;       /* fc rows; 0 = encoder only */
+  int32_t vocab;        /* fc rows; 0 = encoder only */
+  int32_t sub_layers;   /* Conv2d subsampling layers: 1 (Efficient Conformer family) or 2 (Conformer family); 0 reads as 1 */
+  int32_t sub_filters2; /* C of the second layer (C -> C2) when sub_layers == 2 */
   ec_block_cfg blocks[EC_MAX_BLOCKS];
 } ec_config;
 
@@ -66,6 +68,8 @@ typedef struct ec_block_raw {
 } ec_block_raw;
 typedef struct ec_raw_weights {
   const float *sub_conv_w, *sub_conv_b, *sub_bn_w, *sub_bn_b, *sub_bn_rm, *sub_bn_rv;
+  /* second subsampling layer, Conv2d(C, C2, 3, stride 2) weight [C2, C, 3, 3] (NULL when sub_layers == 1) */
+  const float *sub2_conv_w, *sub2_conv_b, *sub2_bn_w, *sub2_bn_b, *sub2_bn_rm, *sub2_bn_rv;
   const float *lin_w, *lin_b;
   const float *fc_w, *fc_b; /* NULL when vocab == 0 */
   ec_block_raw blocks[EC_MAX_BLOCKS];

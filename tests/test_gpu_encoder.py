@@ -282,6 +282,43 @@ def test_other_config_transducer_small_encoder():
         enc16.to(DEV).eval().forward_mel(mel.to(DEV), mel_len.to(DEV))
 
 
+OTHER_CASES = ["EfficientConformerCTCLarge", "EfficientConformerCTCMedium", "EfficientConformerTransducerMedium",
+               "EfficientConformerTransducerLarge", "ConformerCTCLarge", "ConformerCTCLarge@long", "ConformerCTCMedium",
+               "ConformerCTCSmall", "ConformerTransducerSmall", "ConformerTransducerLarge"]
+
+
+@pytest.mark.parametrize("precision,tol", [("tf32", TOL_TF32), ("bf16", TOL_BF16)])
+@pytest.mark.parametrize("case", OTHER_CASES)
+def test_other_shipped_configs_against_reference_golden(golden_dir, case, precision, tol):
+    """BASELINE.json configs 3 (EfficientConformerCTCLarge), 4 (TransducerMedium encoder) and 5 (ConformerCTCLarge: two Conv2d
+    subsampling layers, k = 31, ungrouped attention) plus the remaining shipped families through the same engine, against
+    outputs of the real reference (tests/golden/make_golden_configs.py)."""
+    from efficientconformer_b200 import ConformerEncoder, ModelCTC
+    from efficientconformer_b200.config import SHIPPED_ENCODER_PARAMS
+    g = torch.load(os.path.join(golden_dir, "other_configs.pt"))[case]
+    params, vocab = SHIPPED_ENCODER_PARAMS[case.split("@")[0]]
+    dims = params["dim_model"] if isinstance(params["dim_model"], list) else [params["dim_model"]]
+    if precision == "bf16" and any(d % 8 for d in dims):
+        pytest.skip("bf16 rows of this width are not 16-byte multiples (TMA); the engine refuses loudly (tested elsewhere)")
+    mel = synthetic_mel(g["batch"], g["t_mel"], seed=g["mel_seed"]).to(DEV)
+    mel_len = g["mel_len"].to(DEV)
+    if "logits" in g:
+        sd2 = seeded_state_dict(params, vocab, seed=g["weights_seed"], prefix_encoder="encoder.")
+        m = ModelCTC(params, {"vocab_size": vocab}, precision=precision)
+        m.load_state_dict(sd2, strict=False)
+        out, out_len, _ = m.to(DEV).eval().forward_mel(mel, mel_len)
+        ref = g["logits"]
+    else:
+        sd2 = seeded_state_dict(params, None, seed=g["weights_seed"])
+        enc = ConformerEncoder(params, precision=precision)
+        enc.load_state_dict(sd2, strict=False)
+        out, out_len, _ = enc.to(DEV).eval().forward_mel(mel, mel_len)
+        ref = g["x"]
+    assert torch.equal(out_len.cpu(), g["out_len"])
+    assert torch.isfinite(out).all()
+    assert rel_l2(out, ref) < tol, (case, precision, rel_l2(out, ref))
+
+
 def test_no_fallback_paths(sd):
     from efficientconformer_b200 import ConformerEncoder
     enc = ConformerEncoder(P)

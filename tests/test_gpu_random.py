@@ -75,8 +75,11 @@ def test_random_gemm_layernorm_shapes(ops, prec):
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])
 def test_random_attention_shapes(ops, prec):
     rng = random.Random(7)
-    for trial in range(14):
-        D, H, G = rng.choice([(120, 4, 3), (168, 4, 1), (240, 4, 1), (100, 4, 3), (256, 4, 1)])
+    for trial in range(22):
+        # (D, H, G): the head layouts of every shipped config family (head dims 90/42/60/75/64, then 135/44/24/64/90 of the
+        # Medium / Large / Conformer families)
+        D, H, G = rng.choice([(120, 4, 3), (168, 4, 1), (240, 4, 1), (100, 4, 3), (256, 4, 1)]) if trial < 14 else \
+            rng.choice([(360, 8, 3), (180, 4, 3), (176, 4, 1), (144, 6, 1), (512, 8, 1), (720, 8, 1)])
         T = rng.choice([1, 2, 3, 5, 63, 64, 65, 128, 191, 192, 193, 400])
         B = rng.choice([1, 2, 3])
         if prec == "bf16" and ((G * D) // H) % 2:
@@ -95,8 +98,8 @@ def test_random_attention_shapes(ops, prec):
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])
 def test_random_dwconv_shapes(ops, prec):
     rng = random.Random(3)
-    for trial in range(12):
-        C = rng.choice([8, 120, 168, 176, 240, 256])
+    for trial in range(18):
+        C = rng.choice([8, 120, 168, 176, 240, 256]) if trial < 12 else rng.choice([360, 512, 720, 260])   # > 256: channel tiles
         k = rng.choice([15, 31])
         stride = rng.choice([1, 2])
         T = rng.choice([1, 2, 13, 64, 65, 127, 500])

@@ -136,3 +136,37 @@ def test_operand_rounding_emulation_predicts_tf32_within_gate(sd, golden_dir):
     print("emulated rel-L2: tf32 %.2e  bf16 %.2e" % (et, eb))
     assert et < 1e-3
     assert eb > et
+
+
+# ---- the other shipped configs (BASELINE.json configs 3-5 and the rest of reference configs/*.json) ----------------------
+OTHER_CASES = ["EfficientConformerCTCLarge", "EfficientConformerCTCMedium", "EfficientConformerTransducerMedium",
+               "EfficientConformerTransducerLarge", "ConformerCTCLarge", "ConformerCTCLarge@long", "ConformerCTCMedium",
+               "ConformerCTCSmall", "ConformerTransducerSmall", "ConformerTransducerLarge"]
+
+
+def test_shipped_config_table_matches_reference(golden_dir):
+    from efficientconformer_b200.config import SHIPPED_ENCODER_PARAMS
+    layouts = json.load(open(os.path.join(golden_dir, "state_dict_layouts.json")))
+    for name, entry in layouts.items():
+        assert SHIPPED_ENCODER_PARAMS[name] == (entry["encoder_params"], entry["vocab_size"]), name
+    assert len(SHIPPED_ENCODER_PARAMS) == 12
+
+
+@pytest.mark.parametrize("case", OTHER_CASES)
+def test_other_configs_against_reference_golden(golden_dir, case):
+    """Two-layer Conv2d front end, k = 31, widths up to 720, head dims 24 ... 135, T' up to 250: the oracle reproduces the
+    real reference's outputs for every shipped encoder family (fp32 vs fp32)."""
+    from efficientconformer_b200.config import SHIPPED_ENCODER_PARAMS
+    g = torch.load(os.path.join(golden_dir, "other_configs.pt"))[case]
+    params, vocab = SHIPPED_ENCODER_PARAMS[case.split("@")[0]]
+    mel = synthetic_mel(g["batch"], g["t_mel"], seed=g["mel_seed"])
+    if "logits" in g:
+        sd2 = seeded_state_dict(params, vocab, seed=g["weights_seed"], prefix_encoder="encoder.")
+        out, out_len = O.model_ctc_forward_mel(sd2, params, mel, g["mel_len"])
+        ref = g["logits"]
+    else:
+        sd2 = seeded_state_dict(params, None, seed=g["weights_seed"])
+        out, out_len = O.encoder_forward_mel(sd2, params, mel, g["mel_len"])
+        ref = g["x"]
+    assert torch.equal(out_len, g["out_len"])
+    assert rel_l2(out, ref) < 2e-5
