@@ -43,8 +43,8 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def ncu_gemm_traffic(precision):
-    """Average DRAM bytes (read + write) per GEMM launch from the committed `ncu --set full` capture of block 0
+def ncu_traffic(precision, kernel_prefix="gemm_tc_kernel"):
+    """Average DRAM bytes (read + write) per launch of one kernel from the committed `ncu --set full` capture of block 0
     (profiles/, produced by tools/summarize_ncu.py); None when no capture exists for this precision."""
     path = os.path.join(ROOT, "profiles", f"r1_ncu_full_block0_{precision}_summary.json")
     if not os.path.exists(path):
@@ -52,7 +52,7 @@ def ncu_gemm_traffic(precision):
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tot, n = 0.0, 0
     for k in json.load(open(path))["kernels"]:
-        if not k["kernel"].startswith("gemm_tc_kernel"):
+        if not k["kernel"].startswith(kernel_prefix):
             continue
         for key in ("dram_read", "dram_write"):
             val, unit = k[key].split()
@@ -289,24 +289,36 @@ def run_ours(args, rank, world, local_rank):
     pk = peaks()
     tensor_peak = pk["bf16_tflops"] * (1.0 if args.precision == "bf16" else 0.5)     # kind::tf32 runs at half the bf16 rate
     kernels = []
-    gemm_ms = gemm_fl = gemm_n = 0
+    # kernel classes = device functions: every gemm_* category is one gemm_tc_kernel, the fused FFN and attention are their own
+    classes = {"gemm_tc_kernel": [0.0, 0.0, 0], "ffn_fused_kernel": [0.0, 0.0, 0], "relpos_attn_kernel": [0.0, 0.0, 0]}
     for name, (ms_, fl_, by_, n_) in acc.items():
         if n_ == 0:
             continue
         ent = {"kernel": name, "launches": n_, "ms": round(ms_, 4), "tflops": round(fl_ / ms_ / 1e9, 2) if ms_ > 0 else None,
                "gbs": round(by_ / ms_ / 1e6, 1) if ms_ > 0 else None}
         kernels.append(ent)
-        if name.startswith("gemm_"):
-            gemm_ms += ms_; gemm_fl += fl_; gemm_n += n_
+        cls = "gemm_tc_kernel" if name.startswith("gemm_") else "ffn_fused_kernel" if name == "ffn_fused" else \
+            "relpos_attn_kernel" if name == "relpos_attention" else None
+        if cls:
+            c = classes[cls]; c[0] += ms_; c[1] += fl_; c[2] += n_
     fwd_profiled_ms = sum(k["ms"] for k in kernels)
-    achieved = gemm_fl / gemm_ms / 1e9 if gemm_ms > 0 else 0.0
-    roofline = {"kernel": "gemm_tc_kernel (tcgen05, all GEMM launches of one forward)", "bound": "tensor", "achieved": round(achieved, 2),
-                "peak": tensor_peak, "unit": "TFLOP/s", "frac": round(achieved / tensor_peak, 4), "traffic": ncu_gemm_traffic(args.precision),
+    desc = {"gemm_tc_kernel": "gemm_tc_kernel (tcgen05 + TMA, every Linear / pointwise conv launch of one forward)",
+            "ffn_fused_kernel": "ffn_fused_kernel (tcgen05 + TMA cluster kernel: W1 -> Swish -> W2 -> residual -> LayerNorm, 30 launches per forward)",
+            "relpos_attn_kernel": "relpos_attn kernels (mma.sync bf16/tf32, TMA-staged)"}
+
+    def tensor_roofline(cls):
+        ms_, fl_, n_ = classes[cls]
+        ach = fl_ / ms_ / 1e9 if ms_ > 0 else 0.0
+        return {"kernel": desc[cls], "bound": "tensor", "achieved": round(ach, 2), "peak": tensor_peak, "unit": "TFLOP/s",
+                "frac": round(ach / tensor_peak, 4), "traffic": ncu_traffic(args.precision, cls.replace("relpos_attn_kernel", "relpos_attn")),
                 "peak_source": pk["source"] + (" bf16 cuBLAS burst" if args.precision == "bf16" else " bf16 cuBLAS burst / 2 (tf32 operands)"),
-                "launches_per_forward": gemm_n, "avg_launch_us": round(1e3 * gemm_ms / max(gemm_n, 1), 2),
-                "share_of_forward": round(gemm_ms / fwd_profiled_ms, 3) if fwd_profiled_ms else None}
+                "launches_per_forward": n_, "avg_launch_us": round(1e3 * ms_ / max(n_, 1), 2),
+                "share_of_forward": round(ms_ / fwd_profiled_ms, 3) if fwd_profiled_ms else None,
+                "timing": "CUDA events around every launch of an eager forward on the launching stream (serialised: no PDL overlap)"}
+    dominant = max(classes, key=lambda c: classes[c][0])
+    roofline = tensor_roofline(dominant)
+    extra_rooflines = [tensor_roofline(c) for c in classes if c != dominant and classes[c][2] > 0]
     dw = acc.get("dwconv_bn_swish")
-    extra_rooflines = []
     if dw and dw[0] > 0:
         gbs = dw[2] / dw[0] / 1e6
         extra_rooflines.append({"kernel": "dwconv_bn_swish", "bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",

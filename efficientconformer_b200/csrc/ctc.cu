@@ -99,8 +99,9 @@ __device__ __forceinline__ float lse3_fast(float a, float b, float c) {
   if (m == -INFINITY) return -INFINITY;
   return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
 }
+constexpr int kCtcGatherThreads = 256;   // the whole CTA gathers emissions; warp 0 then runs the recursion
 template <int kCtcNS>
-__global__ void __launch_bounds__(32) ctc_alpha_warp_kernel(const float* __restrict__ logits, const float* __restrict__ lse, int T, int V,
+__global__ void __launch_bounds__(kCtcGatherThreads) ctc_alpha_warp_kernel(const float* __restrict__ logits, const float* __restrict__ lse, int T, int V,
                                                             const int* __restrict__ logits_len, const long long* __restrict__ targets,
                                                             int target_stride, const long long* __restrict__ target_len,
                                                             float* __restrict__ loss_per_utt) {
@@ -112,27 +113,23 @@ __global__ void __launch_bounds__(32) ctc_alpha_warp_kernel(const float* __restr
   const int S = 2 * U + 1;
   int Tb = logits_len[b];
   if (Tb > T) Tb = T;
-  if (Tb <= 0) { if (lane == 0) loss_per_utt[b] = INFINITY; return; }
+  if (Tb <= 0) { if (threadIdx.x == 0) loss_per_utt[b] = INFINITY; return; }
   const long long* y = targets + static_cast<size_t>(b) * target_stride;
   const float* lg = logits + static_cast<size_t>(b) * T * V;
   const float* ls = lse + static_cast<size_t>(b) * T;
-  // gather phase: T*S independent loads (the recursion below then only touches shared memory); state s lives at column
-  // (s % kCtcNS) * 32 + s / kCtcNS so that a lane's kCtcNS states are conflict-free
+  // gather phase: T*S independent loads spread over the whole CTA (the recursion below is one warp and only touches shared
+  // memory); state s lives at column (s % kCtcNS) * 32 + s / kCtcNS so that a lane's kCtcNS states are conflict-free
   {
-    int ge[kCtcNS];
-#pragma unroll
-    for (int k = 0; k < kCtcNS; ++k) { const int s = k * 32 + lane; ge[k] = (s < S && (s & 1)) ? static_cast<int>(y[s >> 1]) : 0; }
-    for (int t = 0; t < Tb; ++t) {
-      const float* lgt = lg + static_cast<size_t>(t) * V;
-      const float l1 = ls[t];
-#pragma unroll
-      for (int k = 0; k < kCtcNS; ++k) {
-        const int s = k * 32 + lane;                 // coalesced over s for the store
-        lp_sm[t * SP + (s % kCtcNS) * 32 + s / kCtcNS] = lgt[ge[k]] - l1;
-      }
+    __shared__ int lab[SP];
+    for (int s = threadIdx.x; s < SP; s += blockDim.x) lab[s] = (s < S && (s & 1)) ? static_cast<int>(y[s >> 1]) : 0;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < Tb * SP; idx += blockDim.x) {
+      const int t = idx / SP, s = idx - t * SP;
+      lp_sm[t * SP + (s % kCtcNS) * 32 + s / kCtcNS] = __ldg(lg + static_cast<size_t>(t) * V + lab[s]) - __ldg(ls + t);
     }
   }
-  __syncwarp();
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
   bool skip[kCtcNS];
 #pragma unroll
   for (int k = 0; k < kCtcNS; ++k) {
@@ -197,7 +194,7 @@ int launch_ctc_loss(const float* logits, const float* lse, int B, int T, int V, 
     if (sm <= 200 * 1024) {                                                                                                \
       static cudaError_t attr = cudaFuncSetAttribute(ctc_alpha_warp_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
       EC_CUDA(attr);                                                                                                       \
-      ctc_alpha_warp_kernel<NS><<<B, 32, sm, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, loss_per_utt); \
+      ctc_alpha_warp_kernel<NS><<<B, kCtcGatherThreads, sm, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, loss_per_utt); \
       launched = true;                                                                                                     \
     }                                                                                                                      \
   }

@@ -70,6 +70,7 @@ struct ec_engine {
   std::vector<cudaEvent_t> event_pool;
   size_t events_used = 0;
   int last_launches = 0;
+  unsigned skip_mask = 0;  // debug (ec_engine_set_skip_mask): kernel categories NOT launched -- marginal-cost studies only, results are garbage
   bool fuse_ffn = true;    // bf16 mode: whole feed-forward module in one cluster kernel (needs fuse_ln)
   bool fuse_ln = true;     // LayerNorms in the epilogue of the producing GEMM (needs dim <= 256)
   // the positional projections E_i = pos_layer_i(R) depend on weights only: they run on a forked stream, off the critical path
@@ -236,6 +237,7 @@ static int gemm(ec_engine* e, cudaStream_t st, int cat, const void* A, const voi
   const double flops = 2.0 * M * n_real * K;
   const double bytes = (static_cast<double>(M) * K + n_real * K) * e->esize + static_cast<double>(M) * ncols *
                        ((out_f32 ? 4 : 0) + (out_act ? e->esize : 0) + (residual ? 4 : 0));
+  if (e->skip_mask >> cat & 1u) return EC_OK;
   ProfScope ps(e, st, cat, flops, bytes);
   return launch_gemm(e->precision, g, st);
 }
@@ -248,6 +250,7 @@ static int ffn_fused(ec_engine* e, cudaStream_t st, const void* x_act, const voi
   f.ln_mode = ln.mode; f.ln1_g = ln.g1; f.ln1_b = ln.b1; f.ln2_g = ln.g2; f.ln2_b = ln.b2; f.ln_eps = 1e-6f; f.ln_out = ln.y;
   const double flops = 4.0 * M * D * hidden;
   const double bytes = 2.0 * (static_cast<double>(M) * D + 2.0 * D * hidden) + static_cast<double>(M) * D * (4 + 4 + (ln.y ? 2 : 0));
+  if (e->skip_mask >> PC_FFN_FUSED & 1u) return EC_OK;
   ProfScope ps(e, st, PC_FFN_FUSED, flops, bytes);
   return launch_ffn_fused(f, st);
 }
@@ -466,7 +469,7 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
   } else {
     SubsampleArgs sa{mel, w.sub_w, w.sub_b, B, c.n_mels, t_mel, c.sub_filters, ws.sub_a};
     ProfScope ps(e, st, PC_SUBSAMPLE, 18.0 * B * sh.t0 * feat, 4.0 * B * c.n_mels * t_mel + es * B * sh.t0 * feat);
-    EC_TRY(launch_subsample_conv(prec, sa, st));
+    if (!(e->skip_mask >> PC_SUBSAMPLE & 1u)) EC_TRY(launch_subsample_conv(prec, sa, st));
   }
   const int D0 = c.blocks[0].dim_model;
   float* x = ws.xa; float* x_alt = ws.xb;
@@ -525,7 +528,7 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
       const double Tg = static_cast<double>(T + P) / G, dh = static_cast<double>(G) * D / bc.num_heads;
       ProfScope ps(e, st, PC_ATTN, B * bc.num_heads * (4.0 * Tg * Tg * dh + 2.0 * Tg * (2 * Tg - 1) * dh),
                    4.0 * M * 3 * D + 4.0 * e_rows * D + es * M * D);
-      EC_TRY(launch_relpos_attention(prec, aa, st));
+      if (!(e->skip_mask >> PC_ATTN & 1u)) EC_TRY(launch_relpos_attention(prec, aa, st));
     }
     {
       LnFuse ln;
@@ -539,7 +542,7 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
     {
       DwConvArgs da{ws.gl, b.dw_w, b.dw_b, B, T, De, bc.kernel_size, bc.conv_stride, ws.hc};
       ProfScope ps(e, st, PC_DWCONV, 2.0 * Mo * De * bc.kernel_size, es * (static_cast<double>(M) * De + static_cast<double>(Mo) * De));
-      EC_TRY(launch_dwconv_bn_swish(prec, da, st));
+      if (!(e->skip_mask >> PC_DWCONV & 1u)) EC_TRY(launch_dwconv_bn_swish(prec, da, st));
     }
     const float* res = x;
     if (proj) {
@@ -579,6 +582,7 @@ int ec_engine_set_profiling(ec_engine* e, int enabled) { e->prof_enabled = enabl
 /* option 0: fuse LayerNorm into the GEMM epilogues (default 1).  Global option via ec_set_pdl: programmatic dependent launch. */
 int ec_engine_set_fuse_ln(ec_engine* e, int enabled) { e->fuse_ln = enabled != 0; return EC_OK; }
 int ec_engine_set_fuse_ffn(ec_engine* e, int enabled) { e->fuse_ffn = enabled != 0; return EC_OK; }
+int ec_engine_set_skip_mask(ec_engine* e, unsigned mask) { e->skip_mask = mask; return EC_OK; }
 int ec_debug_gemm_timeline(int enable, unsigned long long* out12) { return gemm_timeline(enable, out12); }
 int ec_debug_ffn_timeline(int enable, unsigned long long* out192) { return ffn_timeline(enable, out192); }
 int ec_set_pdl(int enabled) { g_pdl = enabled != 0 ? 1 : 0; return EC_OK; }

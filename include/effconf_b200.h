@@ -121,6 +121,9 @@ int ec_engine_set_fuse_ln(ec_engine* e, int enabled);
  * (W1 -> Swish -> W2 -> half-step residual -> LayerNorm) whose hidden activation never leaves the SM. */
 int ec_engine_set_fuse_ffn(ec_engine* e, int enabled);
 int ec_set_pdl(int enabled);
+/* Debug / measurement only: bit c set = the kernels of profile category c are NOT launched (outputs are garbage).  Used by
+ * tools/marginal_cost.py to measure what each kernel category really costs inside the replayed CUDA graph (PDL overlap included). */
+int ec_engine_set_skip_mask(ec_engine* e, unsigned mask);
 /* Debug: enable in-kernel SM-clock stamps in the GEMM and read the 12 stamps of the last GEMM's CTA (0,0) (synchronises). */
 int ec_debug_gemm_timeline(int enable, unsigned long long* out12);
 /* Same for the fused feed-forward kernel: 192 stamp slots of CTA 0 (see ffn_fused.cu). */
