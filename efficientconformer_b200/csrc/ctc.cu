@@ -94,11 +94,20 @@ __global__ void __launch_bounds__(256) ctc_alpha_kernel(const float* __restrict_
 // Warp-per-utterance variant for 2U+1 <= 32*kCtcNS: every lane keeps kCtcNS consecutive extended-label states in
 // registers, neighbours s-1 / s-2 come from the lane's own registers or two shuffles, the emission log-probs of the next
 // frame are prefetched while the current frame is combined; no block-level barrier in the T-step recursion.
-__device__ __forceinline__ float lse3_fast(float a, float b, float c) {
-  const float m = fmaxf(a, fmaxf(b, c));
-  if (m == -INFINITY) return -INFINITY;
-  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+// log2-domain logsumexp of three values, branch free (an all -inf triple gives ex2 -> 0 and lg2(0) = -inf by itself), so the
+// kCtcNS independent states of a lane interleave in the instruction stream instead of serialising behind a divergent early return
+__device__ __forceinline__ float lse3_log2(float a, float b, float c) {
+  // min/max network: m = largest, (o1, o2) = the other two; the largest contributes ex2(0) = 1, so only two ex2 are needed
+  const float hi = fmaxf(a, b), o2 = fminf(a, b);
+  const float m = fmaxf(hi, c), o1 = fminf(hi, c);
+  const float ms = (m == -INFINITY) ? 0.f : m;
+  float e1, e2, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(o1 - ms));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(o2 - ms));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((m == -INFINITY ? 0.f : 1.f) + e1 + e2));
+  return ms + r;
 }
+constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kCtcGatherThreads = 256;   // the whole CTA gathers emissions; warp 0 then runs the recursion
 template <int kCtcNS>
 __global__ void __launch_bounds__(kCtcGatherThreads) ctc_alpha_warp_kernel(const float* __restrict__ logits, const float* __restrict__ lse, int T, int V,
@@ -125,7 +134,7 @@ __global__ void __launch_bounds__(kCtcGatherThreads) ctc_alpha_warp_kernel(const
     __syncthreads();
     for (int idx = threadIdx.x; idx < Tb * SP; idx += blockDim.x) {
       const int t = idx / SP, s = idx - t * SP;
-      lp_sm[t * SP + (s % kCtcNS) * 32 + s / kCtcNS] = __ldg(lg + static_cast<size_t>(t) * V + lab[s]) - __ldg(ls + t);
+      lp_sm[t * SP + (s % kCtcNS) * 32 + s / kCtcNS] = kLog2e * (__ldg(lg + static_cast<size_t>(t) * V + lab[s]) - __ldg(ls + t));
     }
   }
   __syncthreads();
@@ -144,10 +153,15 @@ __global__ void __launch_bounds__(kCtcGatherThreads) ctc_alpha_warp_kernel(const
     const int s = lane * kCtcNS + k;
     a[k] = (s < 2 && s < S) ? lp_sm[k * 32 + lane] : -INFINITY;
   }
-  for (int t = 1; t < Tb; ++t) {
-    float cur[kCtcNS];
+  // the recursion runs in the log2 domain (emissions were scaled by log2(e) in the gather): ex2 / lg2 are single MUFU operations
+  float cur[kCtcNS];
 #pragma unroll
-    for (int k = 0; k < kCtcNS; ++k) cur[k] = lp_sm[t * SP + k * 32 + lane];
+  for (int k = 0; k < kCtcNS; ++k) cur[k] = Tb > 1 ? lp_sm[SP + k * 32 + lane] : 0.f;
+  for (int t = 1; t < Tb; ++t) {
+    float nxt[kCtcNS];                                  // next frame's emissions: independent of the recursion, issued first
+    const int tn = t + 1 < Tb ? t + 1 : t;
+#pragma unroll
+    for (int k = 0; k < kCtcNS; ++k) nxt[k] = lp_sm[tn * SP + k * 32 + lane];
     float pm1 = __shfl_up_sync(0xffffffffu, a[kCtcNS - 1], 1), pm2 = __shfl_up_sync(0xffffffffu, a[kCtcNS - 2], 1);
     if (lane == 0) { pm1 = -INFINITY; pm2 = -INFINITY; }
     float na[kCtcNS];
@@ -155,11 +169,11 @@ __global__ void __launch_bounds__(kCtcGatherThreads) ctc_alpha_warp_kernel(const
     for (int k = 0; k < kCtcNS; ++k) {
       const float x1 = k >= 1 ? a[k - 1] : pm1;
       const float x2 = skip[k] ? (k >= 2 ? a[k - 2] : (k == 1 ? pm1 : pm2)) : -INFINITY;
-      const float acc = lse3_fast(a[k], x1, x2);
-      na[k] = (acc == -INFINITY || lane * kCtcNS + k >= S) ? -INFINITY : acc + cur[k];
+      const float acc = lse3_log2(a[k], x1, x2);
+      na[k] = (lane * kCtcNS + k >= S) ? -INFINITY : acc + cur[k];       // -inf + finite stays -inf
     }
 #pragma unroll
-    for (int k = 0; k < kCtcNS; ++k) a[k] = na[k];
+    for (int k = 0; k < kCtcNS; ++k) { a[k] = na[k]; cur[k] = nxt[k]; }
   }
   float e1 = -INFINITY, e2 = -INFINITY;
 #pragma unroll
@@ -170,7 +184,7 @@ __global__ void __launch_bounds__(kCtcGatherThreads) ctc_alpha_warp_kernel(const
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { e1 = fmaxf(e1, __shfl_xor_sync(0xffffffffu, e1, o)); e2 = fmaxf(e2, __shfl_xor_sync(0xffffffffu, e2, o)); }
-  if (lane == 0) loss_per_utt[b] = -lse3(e1, e2, -INFINITY);
+  if (lane == 0) loss_per_utt[b] = -lse3_log2(e1, e2, -INFINITY) * 0.6931471805599453f;
 }
 
 __global__ void mean_kernel(const float* x, int n, float* out) {
@@ -179,6 +193,12 @@ __global__ void mean_kernel(const float* x, int n, float* out) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (threadIdx.x == 0) *out = s / n;
+}
+
+int launch_mean(const float* x, int n, float* out, cudaStream_t stream) {
+  mean_kernel<<<1, 32, 0, stream>>>(x, n, out);
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
 }
 
 int launch_ctc_loss(const float* logits, const float* lse, int B, int T, int V, const int* logits_len, const long long* targets,
@@ -200,7 +220,9 @@ int launch_ctc_loss(const float* logits, const float* lse, int B, int T, int V, 
   }
   bool launched = false;
   if (s_max <= 64) EC_CTC_WARP(2)
+  else if (s_max <= 96) EC_CTC_WARP(3)
   else if (s_max <= 128) EC_CTC_WARP(4)
+  else if (s_max <= 192) EC_CTC_WARP(6)
   else if (s_max <= 256) EC_CTC_WARP(8)
 #undef EC_CTC_WARP
   if (!launched) ctc_alpha_kernel<<<B, 256, smem, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, loss_per_utt);

@@ -211,6 +211,12 @@ int launch_i32_to_i64(const int* src, int n, long long* dst, cudaStream_t stream
 int launch_logsoftmax_argmax(const float* logits, int rows, int V, float* lse, int* argmax, cudaStream_t stream);
 int launch_ctc_loss(const float* logits, const float* lse, int B, int T, int V, const int* logits_len, const long long* targets,
                     int target_stride, const long long* target_len, float* loss_per_utt, float* loss_mean, cudaStream_t stream);
+int launch_mean(const float* x, int n, float* out, cudaStream_t stream);
+// backward of the CTC loss (ctc_grad.cu): per-utterance losses and d(mean loss)/d(logits) * (grad_scale * B)
+size_t ctc_grad_work_bytes(int B, int T, int target_stride);
+int launch_ctc_grad(const float* logits, const float* lse, int B, int T, int V, const int* logits_len, const long long* targets,
+                    int target_stride, const long long* target_len, float* work, float grad_scale, float* loss_per_utt, float* grad,
+                    cudaStream_t stream);
 int launch_greedy_collapse(const int* argmax, int B, int T, const int* logits_len, int* ids, int* counts, cudaStream_t stream);
 
 }  // namespace ec

@@ -620,6 +620,22 @@ int ec_ctc_loss(const float* logits, int B, int T, int V, const long long* logit
   EC_TRY(launch_logsoftmax_argmax(logits, B * T, V, lse, amax, st));
   return launch_ctc_loss(logits, lse, B, T, V, len32, targets, target_stride, target_len, loss_per_utt, loss_mean, st);
 }
+size_t ec_ctc_grad_work_bytes(int batch, int t, int target_stride) { return ctc_grad_work_bytes(batch, t, target_stride); }
+int ec_ctc_loss_grad(const float* logits, int B, int T, int V, const long long* logits_len, const long long* targets, int target_stride,
+                     const long long* target_len, void* scratch, void* work, float* loss_per_utt, float* loss_mean, float* grad_logits,
+                     void* stream_) {
+  EC_REQUIRE(logits && logits_len && targets && target_len && scratch && work && loss_per_utt && grad_logits, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  float* lse; int* amax; int* len32;
+  ctc_scratch(scratch, B, T, &lse, &amax, &len32);
+  EC_TRY(launch_i64_to_i32(logits_len, B, len32, T, st));
+  EC_TRY(launch_logsoftmax_argmax(logits, B * T, V, lse, amax, st));
+  // gradient of the MEAN over the batch (reference models/losses.py:71): every utterance's gradient is scaled by 1 / B
+  EC_TRY(launch_ctc_grad(logits, lse, B, T, V, len32, targets, target_stride, target_len, reinterpret_cast<float*>(work), 1.f / B,
+                         loss_per_utt, grad_logits, st));
+  if (loss_mean != nullptr) EC_TRY(launch_mean(loss_per_utt, B, loss_mean, st));
+  return EC_OK;
+}
 int ec_ctc_greedy(const float* logits, int B, int T, int V, const long long* logits_len, void* scratch, int32_t* ids, int32_t* counts,
                   void* stream_) {
   EC_REQUIRE(logits && logits_len && scratch && ids && counts, "null argument");

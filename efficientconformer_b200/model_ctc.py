@@ -15,11 +15,14 @@ from .encoders import ConformerEncoder
 
 class LossCTC(nn.Module):
     """reference models/losses.py:48-71: log_softmax -> CTCLoss(blank=0, reduction='none', zero_infinity=False) -> mean,
-    on device in one call (no autograd graph: forward value only in this round)."""
+    on device in one call.  When the logits require grad the loss carries an autograd node whose backward is the CUDA
+    alpha-beta kernel (ec_ctc_loss_grad): `loss.backward()` fills `logits.grad` like the reference's criterion does."""
 
     def forward(self, batch, pred):
         _, y, _, y_len = batch
         logits, f_len, _ = pred
+        if torch.is_grad_enabled() and logits.requires_grad:
+            return _CTCLossFn.apply(logits, f_len, y, y_len)
         return ctc_loss(logits, f_len, y, y_len)[0]
 
 
@@ -44,6 +47,45 @@ def ctc_loss(logits, logits_len, targets, target_len):
         _lib.check(_lib.lib().ec_ctc_loss(_lib.ptr(logits), B, T, V, _lib.ptr(logits_len), _lib.ptr(targets), targets.shape[1],
                                           _lib.ptr(target_len), _lib.ptr(scratch), _lib.ptr(per), _lib.ptr(mean), _lib.stream_ptr()))
     return mean, per
+
+
+def ctc_loss_and_grad(logits, logits_len, targets, target_len):
+    """Returns (mean loss (), per-utterance losses (B,), d mean / d logits (B, T, V)), fp32 CUDA tensors (ec_ctc_loss_grad)."""
+    if not logits.is_cuda:
+        raise RuntimeError("effconf_b200 CTC loss runs on CUDA only")
+    logits = logits.detach().float().contiguous()
+    B, T, V = logits.shape
+    dev = logits.device
+    logits_len = logits_len.to(dev, torch.int64).contiguous()
+    targets = targets.to(dev, torch.int64).contiguous()
+    target_len = target_len.to(dev, torch.int64).contiguous()
+    per = torch.empty(B, dtype=torch.float32, device=dev)
+    mean = torch.empty((), dtype=torch.float32, device=dev)
+    grad = torch.empty(B, T, V, dtype=torch.float32, device=dev)
+    scratch = _scratch(B, T, V, dev)
+    L = _lib.lib()
+    work = torch.empty(L.ec_ctc_grad_work_bytes(B, T, targets.shape[1]), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.ec_ctc_loss_grad(_lib.ptr(logits), B, T, V, _lib.ptr(logits_len), _lib.ptr(targets), targets.shape[1],
+                                      _lib.ptr(target_len), _lib.ptr(scratch), _lib.ptr(work), _lib.ptr(per), _lib.ptr(mean),
+                                      _lib.ptr(grad), _lib.stream_ptr()))
+    return mean, per, grad
+
+
+class _CTCLossFn(torch.autograd.Function):
+    """autograd node of LossCTC: forward and gradient come from one kernel sequence (the gradient is kept for backward)."""
+
+    @staticmethod
+    def forward(ctx, logits, logits_len, targets, target_len):
+        mean, _, grad = ctc_loss_and_grad(logits, logits_len, targets, target_len)
+        ctx.save_for_backward(grad)
+        ctx.in_dtype = logits.dtype
+        return mean
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (grad,) = ctx.saved_tensors
+        return (grad * grad_out).to(ctx.in_dtype), None, None, None
 
 
 def greedy_ids(logits, logits_len):

@@ -136,6 +136,13 @@ int ec_ctc_loss(const float* logits, int batch, int t, int vocab, const long lon
                 int target_stride, const long long* target_len, void* scratch, float* loss_per_utt, float* loss_mean,
                 void* stream);
 /* ids [B, T] int32 (collapsed token ids, zero padded), counts [B] int32 */
+/* Backward of ec_ctc_loss (first kernel of the training backward pass): also writes grad_logits [B, T, V] fp32 =
+ * d(mean_b nll_b) / d logits = (softmax - posterior occupancy of the class) / B for t < logits_len[b], 0 for padded frames
+ * (what autograd gives for LossCTC.forward, reference models/losses.py:56-71).  work: ec_ctc_grad_work_bytes() device bytes. */
+size_t ec_ctc_grad_work_bytes(int batch, int t, int target_stride);
+int ec_ctc_loss_grad(const float* logits, int batch, int t, int vocab, const long long* logits_len, const long long* targets,
+                     int target_stride, const long long* target_len, void* scratch, void* work, float* loss_per_utt,
+                     float* loss_mean, float* grad_logits, void* stream);
 int ec_ctc_greedy(const float* logits, int batch, int t, int vocab, const long long* logits_len, void* scratch,
                   int32_t* ids, int32_t* counts, void* stream);
 

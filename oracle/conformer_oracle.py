@@ -67,10 +67,33 @@ def layer_norm(x, w, b, eps=1e-6):  # nn.LayerNorm(dim, eps=1e-6): reference mod
     return (x - mu) / torch.sqrt(var + eps) * w + b
 
 
+def batch_norm(x, sd, p, dims, bn=None, eps=1e-5, momentum=0.1):
+    """nn.BatchNorm1d / BatchNorm2d over the channel dim of `x` (channel = the dim not in `dims` besides broadcasting).
+
+    Eval mode (bn is None): running statistics (reference models/modules.py:228,517 under model.eval()).
+    Train mode (bn = {"updates": {}}): statistics of the whole batch INCLUDING padded frames (SURVEY.md section 8 row a11:
+    the reference never masks), biased variance for the normalisation, running statistics updated with momentum 0.1 and
+    the unbiased variance (torch.nn.modules.batchnorm semantics); the new running statistics are collected in bn["updates"]."""
+    g, b = sd[f"{p}.weight"].to(x.dtype), sd[f"{p}.bias"].to(x.dtype)
+    rm, rv = sd[f"{p}.running_mean"].to(x.dtype), sd[f"{p}.running_var"].to(x.dtype)
+    shape = [1] * x.dim()
+    cdim = [d for d in range(x.dim()) if d not in dims][0]
+    shape[cdim] = -1
+    if bn is None:
+        mean, var = rm, rv
+    else:
+        mean = x.mean(dim=dims)
+        var = ((x - mean.view(shape)) ** 2).mean(dim=dims)
+        n = x.numel() // x.shape[cdim]
+        bn["updates"][f"{p}.running_mean"] = ((1 - momentum) * rm + momentum * mean).detach()
+        bn["updates"][f"{p}.running_var"] = ((1 - momentum) * rv + momentum * var * n / max(n - 1, 1)).detach()
+    return (x - mean.view(shape)) / torch.sqrt(var.view(shape) + eps) * g.view(shape) + b.view(shape)
+
+
 # ----------------------------------------------------------------------------------------------------------
 # front end
 # ----------------------------------------------------------------------------------------------------------
-def conv2d_subsampling(sd, params, mel, x_len, nm=EXACT, prefix=""):
+def conv2d_subsampling(sd, params, mel, x_len, nm=EXACT, prefix="", bn=None):
     """reference models/modules.py:232-249 (Conv2dSubsampling.forward), eval-mode BatchNorm2d.
 
     mel (B, n_mels, T) -> (B, C*n_mels/2^L, T') with feature index c*F' + f; x_len -> (x_len-1)//2+1 per layer."""
@@ -79,9 +102,7 @@ def conv2d_subsampling(sd, params, mel, x_len, nm=EXACT, prefix=""):
         p = f"{prefix}subsampling_module.layers.{l}"
         ks = params["subsampling_kernel_size"]
         x = F.conv2d(x, sd[f"{p}.0.weight"].to(x.dtype), sd[f"{p}.0.bias"].to(x.dtype), stride=2, padding=(ks - 1) // 2)
-        rm, rv = sd[f"{p}.1.running_mean"].to(x.dtype), sd[f"{p}.1.running_var"].to(x.dtype)
-        g, b = sd[f"{p}.1.weight"].to(x.dtype), sd[f"{p}.1.bias"].to(x.dtype)
-        x = (x - rm[None, :, None, None]) / torch.sqrt(rv[None, :, None, None] + 1e-5) * g[None, :, None, None] + b[None, :, None, None]
+        x = batch_norm(x, sd, f"{p}.1", (0, 2, 3), bn)
         x = swish(x)
         if x_len is not None:
             x_len = torch.div(x_len - 1, 2, rounding_mode="floor") + 1
@@ -159,7 +180,7 @@ def relpos_attention(sd, p, x, x_len, spec, nm=EXACT):
     return nm.linear(o, c("output_layer.weight"), c("output_layer.bias")), w
 
 
-def conv_module(sd, p, x, spec, nm=EXACT):
+def conv_module(sd, p, x, spec, nm=EXACT, bn=None):
     """reference models/modules.py:507-525 (ConvolutionModule) with Conv1d 'same' pre-padding
     (models/layers.py:99-100,131-136), Glu (activations.py:37-39), eval-mode BatchNorm1d (eps 1e-5)."""
     c = lambda k: sd[f"{p}.layers.{k}"].to(x.dtype)
@@ -176,12 +197,12 @@ def conv_module(sd, p, x, spec, nm=EXACT):
     for kk in range(ks):                                        # out[t,c] = b_c + sum_k w[c,k] * in[t*s + k - pad, c]
         out = out + hp[:, kk: kk + (To - 1) * st + 1: st, :] * w[:, kk]
     out = out + c("4.bias")
-    out = (out - c("5.running_mean")) / torch.sqrt(c("5.running_var") + 1e-5) * c("5.weight") + c("5.bias")
+    out = batch_norm(out, sd, f"{p}.layers.5", (0, 1), bn)
     out = swish(out)
     return nm.linear(out, c("7.weight")[:, :, 0], c("7.bias"))
 
 
-def conformer_block(sd, p, x, x_len, spec, nm=EXACT, taps=None):
+def conformer_block(sd, p, x, x_len, spec, nm=EXACT, taps=None, bn=None):
     """reference models/blocks.py:119-137."""
     x = x + 0.5 * feed_forward(sd, f"{p}.feed_forward_module1", x, nm)
     m = f"{p}.multi_head_self_attention_module"
@@ -190,7 +211,7 @@ def conformer_block(sd, p, x, x_len, spec, nm=EXACT, taps=None):
     x = x + att                                                 # att_res = Identity (att_stride == 1)
     if taps is not None:
         taps[f"{p}.after_mhsa"] = x
-    cm = conv_module(sd, f"{p}.convolution_module", x, spec, nm)
+    cm = conv_module(sd, f"{p}.convolution_module", x, spec, nm, bn)
     if spec.has_conv_res_proj:                                  # blocks.py:105-109: strided pointwise conv on the block input
         res = nm.linear(x[:, ::spec.conv_stride], sd[f"{p}.conv_res.1.weight"].to(x.dtype)[:, :, 0], sd[f"{p}.conv_res.1.bias"].to(x.dtype))
     elif spec.conv_stride > 1:                                  # blocks.py:110-113: MaxPool1d(kernel 1, stride s)
@@ -208,17 +229,19 @@ def conformer_block(sd, p, x, x_len, spec, nm=EXACT, taps=None):
 # ----------------------------------------------------------------------------------------------------------
 # encoder / CTC model
 # ----------------------------------------------------------------------------------------------------------
-def encoder_forward_mel(sd, params, mel, x_len, nm=EXACT, taps=None, prefix=""):
-    """reference models/encoders.py:106-142 from the mel spectrogram on (eval mode: no SpecAugment / dropout).
+def encoder_forward_mel(sd, params, mel, x_len, nm=EXACT, taps=None, prefix="", bn=None):
+    """reference models/encoders.py:106-142 from the mel spectrogram on (no SpecAugment / dropout: Pdrop = 0 semantics).
 
-    mel (B, n_mels, T), x_len (B,) in mel frames or None.  Returns (x (B,T_out,D_last), x_len_out)."""
+    mel (B, n_mels, T), x_len (B,) in mel frames or None.  Returns (x (B,T_out,D_last), x_len_out).
+    bn = None: eval-mode BatchNorm; bn = {"updates": {}}: train-mode batch statistics (see batch_norm).  Every operation is a
+    differentiable torch op, so torch.autograd over this function is the oracle of the backward pass as well."""
     sdp = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)} if prefix else sd
-    x, x_len = conv2d_subsampling(sdp, params, mel, x_len, nm)
+    x, x_len = conv2d_subsampling(sdp, params, mel, x_len, nm, bn=bn)
     x = nm.linear(x.transpose(1, 2), sdp["linear.weight"].to(mel.dtype), sdp["linear.bias"].to(mel.dtype))
     if taps is not None:
         taps["linear"] = x
     for i, spec in enumerate(resolve_blocks(params)):
-        x, _ = conformer_block(sdp, f"blocks.{i}", x, x_len, spec, nm, taps)
+        x, _ = conformer_block(sdp, f"blocks.{i}", x, x_len, spec, nm, taps, bn)
         if taps is not None:
             taps[f"blocks.{i}"] = x
         if spec.conv_stride > 1 and x_len is not None:
@@ -245,11 +268,22 @@ def audio_to_mel(sd, params, audio, audio_len, prefix=""):
     return mel, audio_len
 
 
-def model_ctc_forward_mel(sd, params, mel, x_len, nm=EXACT, taps=None):
-    """reference models/model_ctc.py:57-68 from the mel spectrogram on; `sd` uses `encoder.` / `fc.` prefixes."""
-    x, x_len = encoder_forward_mel(sd, params, mel, x_len, nm, taps, prefix="encoder.")
+def model_ctc_forward_mel(sd, params, mel, x_len, nm=EXACT, taps=None, bn=None):
+    """reference models/model_ctc.py:57-68 from the mel spectrogram on; `sd` uses `encoder.` / `fc.` prefixes.
+    Keys collected in bn["updates"] are relative to the encoder (no `encoder.` prefix)."""
+    x, x_len = encoder_forward_mel(sd, params, mel, x_len, nm, taps, prefix="encoder.", bn=bn)
     logits = nm.linear(x, sd["fc.weight"].to(x.dtype), sd["fc.bias"].to(x.dtype))
     return logits, x_len
+
+
+def _lse0(stacked):
+    """logsumexp over dim 0 that is differentiable when every entry is -inf (torch.logsumexp back-propagates NaN there):
+    value -inf, zero gradient."""
+    m = stacked.max(dim=0).values
+    dead = torch.isinf(m) & (m < 0)
+    m_safe = torch.where(dead, torch.zeros_like(m), m).detach()
+    tot = torch.exp(stacked - m_safe).sum(dim=0)
+    return torch.where(dead, torch.full_like(m, float("-inf")), m_safe + torch.log(tot.clamp_min(1e-300)))
 
 
 def ctc_loss(logits, logits_len, targets, target_len):
@@ -285,12 +319,12 @@ def ctc_loss(logits, logits_len, targets, target_len):
         a1 = torch.cat([pad1, alpha[:, :-1]], dim=1)
         a2 = torch.cat([pad2, alpha[:, :-2]], dim=1) if S > 2 else torch.full_like(alpha, neg_inf)
         a2 = torch.where(allow_skip, a2, torch.full_like(a2, neg_inf))
-        new = torch.logsumexp(torch.stack([alpha, a1, a2]), dim=0) + lp_ext[:, t]
+        new = _lse0(torch.stack([alpha, a1, a2])) + lp_ext[:, t]
         alpha = torch.where((t < logits_len)[:, None], new, alpha)
     last = 2 * target_len                                        # index S_b - 1
     end1 = alpha.gather(1, last[:, None])[:, 0]
     end2 = torch.where(last > 0, alpha.gather(1, (last - 1).clamp(min=0)[:, None])[:, 0], torch.full_like(end1, neg_inf))
-    losses = -torch.logsumexp(torch.stack([end1, end2]), dim=0)
+    losses = -_lse0(torch.stack([end1, end2]))
     losses = torch.where(logits_len > 0, losses, torch.full_like(losses, float("inf")))
     return losses.mean().to(logits.dtype), losses.to(logits.dtype)
 

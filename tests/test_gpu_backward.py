@@ -1,0 +1,75 @@
+"""Parity of the backward kernels (training step) on the B200, each through the C ABI against
+torch.autograd over the CPU oracle's restatement of the same forward op (the oracle's autograd is pinned against the real
+reference's loss.backward() in tests/test_oracle_golden.py::test_training_step_loss_gradients_and_running_stats)."""
+import os
+import random
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _oracle_ctc_grad(logits, ll, y, yl):
+    from oracle import conformer_oracle as O
+    lg = logits.double().clone().requires_grad_(True)
+    loss, per = O.ctc_loss(lg, ll, y, yl)
+    loss.backward()
+    return loss.detach(), per.detach(), lg.grad
+
+
+def test_ctc_gradient_known_answers(golden_dir):
+    """The reference's CTC known answers (repeated labels, ragged lengths): loss and d loss / d logits."""
+    from efficientconformer_b200.model_ctc import ctc_loss_and_grad
+    g = torch.load(os.path.join(golden_dir, "ctc_loss_small.pt"))
+    mean, per, grad = ctc_loss_and_grad(g["logits"].to(DEV), g["logits_len"], g["targets"], g["target_len"])
+    ref_mean, ref_per, ref_grad = _oracle_ctc_grad(g["logits"], g["logits_len"], g["targets"], g["target_len"])
+    assert torch.allclose(per.cpu(), g["loss_per_utt"], rtol=2e-5, atol=1e-4)
+    assert rel_l2(grad, ref_grad) < 2e-5
+    for b in range(g["logits"].shape[0]):                       # padded frames get exactly zero gradient
+        assert float(grad[b, int(g["logits_len"][b]):].abs().max() if int(g["logits_len"][b]) < grad.shape[1] else 0.0) == 0.0
+    # every frame's gradient sums to zero over the classes (softmax minus a distribution), up to fp32 rounding
+    assert float(grad.sum(-1).abs().max()) < 1e-5
+
+
+def test_ctc_gradient_random_shapes():
+    """Seeded sweep: T up to 250, U up to 100 (1..7 extended states per lane), repeats, single-label and U = T/2 cases,
+    peaky logits; plus the autograd node used by LossCTC."""
+    from efficientconformer_b200.model_ctc import ctc_loss_and_grad, LossCTC
+    rng = random.Random(11)
+    for trial in range(10):
+        B = rng.choice([1, 3, 8])
+        T = rng.choice([1, 2, 17, 63, 125, 200, 250])
+        V = rng.choice([5, 32, 256])
+        g = torch.Generator().manual_seed(900 + trial)
+        scale = rng.choice([1.0, 4.0, 12.0])
+        logits = scale * torch.randn(B, T, V, generator=g)
+        ll = torch.tensor([rng.randint(1, T) for _ in range(B)])
+        ll[0] = T
+        Umax = max(1, min(100, T // 2))
+        yl = torch.tensor([rng.randint(1, max(1, min(Umax, int(ll[b]) // 2))) for b in range(B)])
+        y = torch.randint(1, min(V, 4) if trial % 3 == 0 else V, (B, int(yl.max())), generator=g)   # small alphabets force repeats
+        mean, per, grad = ctc_loss_and_grad(logits.to(DEV), ll, y, yl)
+        ref_mean, ref_per, ref_grad = _oracle_ctc_grad(logits, ll, y, yl)
+        finite = torch.isfinite(ref_per)
+        assert torch.equal(torch.isfinite(per.cpu()), finite), (trial, per, ref_per)
+        assert torch.allclose(per.cpu()[finite], ref_per.float()[finite], rtol=1e-4, atol=1e-3), (trial, per, ref_per)
+        if bool(finite.all()):
+            # fp32 log-domain recursion (like torch's own CUDA CTC): with peaky logits log p(l|x) reaches -1e4 and one fp32 ulp of
+            # alpha + beta is ~1e-3 in the exponent of the occupancy -> the north-star tolerance (1e-3) for the stress cases
+            tol = 1e-4 if scale == 1.0 else 1.5e-3
+            assert rel_l2(grad, ref_grad) < tol, (trial, B, T, V, scale, rel_l2(grad, ref_grad))
+    # autograd node: loss.backward() through LossCTC fills logits.grad
+    logits = torch.randn(2, 40, 16, generator=torch.Generator().manual_seed(5)).to(DEV).requires_grad_(True)
+    ll, yl = torch.tensor([40, 31]), torch.tensor([7, 5])
+    y = torch.randint(1, 16, (2, 7), generator=torch.Generator().manual_seed(6))
+    loss = LossCTC()((None, y, None, yl), (logits, ll, None))
+    (3.0 * loss).backward()
+    _, _, ref_grad = _oracle_ctc_grad(logits.detach().cpu(), ll, y, yl)
+    assert rel_l2(logits.grad, 3.0 * ref_grad) < 1e-4

@@ -170,3 +170,35 @@ def test_other_configs_against_reference_golden(golden_dir, case):
         ref = g["x"]
     assert torch.equal(out_len, g["out_len"])
     assert rel_l2(out, ref) < 2e-5
+
+
+# ---- training step: the oracle's train-mode forward + autograd against the real reference ----
+def test_training_step_loss_gradients_and_running_stats(sd, golden_dir):
+    """Train-mode BatchNorm (batch statistics incl. padded frames, running-stat update), Pdrop = 0: CTC loss, the gradient of
+    every parameter and the updated running statistics equal the reference's loss.backward() (fp32 vs fp32)."""
+    g = torch.load(os.path.join(golden_dir, "ctc_small_train_b2_t500.pt"))
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+    bn = {"updates": {}}
+    mel = synthetic_mel(2, 500, seed=g["mel_seed"])
+    logits, out_len = O.model_ctc_forward_mel(leaf, P, mel, g["mel_len"], bn=bn)
+    assert rel_l2(logits.detach(), g["logits"]) < 2e-5
+    loss, _ = O.ctc_loss(logits, out_len, g["targets"], g["target_len"])
+    assert abs(float(loss) - float(g["loss"])) / abs(float(g["loss"])) < 1e-5
+    loss.backward()
+    worst = 0.0
+    # gradients that are zero in exact arithmetic (biases in front of BatchNorm, key / positional biases under the softmax's
+    # shift invariance) are fp32 noise of magnitude ~1e-6 in the reference: compared against an absolute floor
+    floor = 1e-4 * sorted(g["grad_norms"].values())[len(g["grad_norms"]) // 2]
+    for k, ref_norm in g["grad_norms"].items():
+        gn = float(leaf[k].grad.double().norm())
+        assert gn == gn, k
+        if ref_norm < floor:
+            assert gn < floor, k
+            continue
+        worst = max(worst, abs(gn - ref_norm) / ref_norm)
+    assert worst < 2e-3, worst                      # fp32 reference backward (op order differs); norms of all 582 gradients
+    for k, ref in g["grads"].items():
+        if g["grad_norms"][k] >= floor:
+            assert rel_l2(leaf[k].grad, ref) < 2e-3, k
+    for k, ref in g["running_stats"].items():
+        assert rel_l2(bn["updates"][k[len("encoder."):]], ref) < 1e-5, k
