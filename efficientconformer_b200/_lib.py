@@ -76,6 +76,14 @@ _SIGNATURES = {
     "ec_ctc_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "ec_ctc_loss": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ec_op_layernorm_bwd_work_bytes": (C.c_size_t, [C.c_int]),
+    "ec_op_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ec_op_colsum_work_bytes": (C.c_size_t, [C.c_int]),
+    "ec_op_colsum": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ec_op_transpose_cast": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ec_op_swish_bwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "ec_op_glu_bwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
     "ec_ctc_grad_work_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "ec_ctc_loss_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1,0 +1,234 @@
+// Row / element kernels of the training backward pass, bandwidth bound:
+//   LayerNorm backward          (nn.LayerNorm(eps=1e-6): reference models/modules.py:386,433,511; blocks.py:96)
+//   column sums (bias gradients of every Linear / pointwise conv: reference models/layers.py:67,136)
+//   transposed operand-type copies (W^T for the data-gradient GEMMs, which reuse the forward tcgen05 GEMM: dX = dY . W)
+//   Swish / GLU backward         (reference models/activations.py:28-29, 37-39)
+// Every reduction has a fixed order (per-CTA partials + a second pass), so gradients are bit-reproducible.
+#include "ec_common.cuh"
+#include <algorithm>
+
+namespace ec {
+
+constexpr int kBwdCtas = 296;     // 2 per SM: row-strided persistent CTAs for the column reductions
+
+// ---------------------------------------------------------------------------------------------------------------
+// LayerNorm backward.  y = (x - mu) * rstd * gamma + beta  (statistics recomputed from x: cheaper than storing them).
+//   g = dy * gamma;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat));  dgamma = sum_rows dy * xhat;  dbeta = sum_rows dy
+// One warp per row, the row in registers (dim <= 32 * NPL); a CTA walks rows blockIdx.x*8 + warp, + 8*gridDim.x, ...;
+// per-lane column partials stay in registers over the whole walk, are merged across the 8 warps in shared memory and
+// written as per-CTA partial rows; ln_bwd_reduce_kernel adds the partial rows in CTA order.
+// ---------------------------------------------------------------------------------------------------------------
+template <int NPL>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int rows, int dim,
+                                                            const float* __restrict__ gamma, float eps, float* __restrict__ dx,
+                                                            int accumulate, float* __restrict__ partial /* [gridDim.x][2][dim] */) {
+  __shared__ float red[8][32 * NPL];        // cross-warp merge buffer, used for dgamma then dbeta
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float gm[NPL], pg[NPL], pb[NPL];
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const int c = lane + 32 * i;
+    gm[i] = c < dim ? __ldg(gamma + c) : 0.f;
+    pg[i] = 0.f; pb[i] = 0.f;
+  }
+  const float inv_dim = 1.f / dim;
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += 8 * gridDim.x) {
+    const float* xr = x + static_cast<size_t>(row) * dim;
+    const float* dr = dy + static_cast<size_t>(row) * dim;
+    float v[NPL], d[NPL];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < dim ? xr[c] : 0.f;
+      d[i] = c < dim ? dr[c] : 0.f;
+      sum += v[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mu = sum * inv_dim;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int c = lane + 32 * i;
+      const float t = c < dim ? v[i] - mu : 0.f;
+      sq += t * t;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * inv_dim + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int c = lane + 32 * i;
+      const float xh = c < dim ? (v[i] - mu) * rstd : 0.f;
+      const float g = d[i] * gm[i];
+      s1 += g; s2 += g * xh;
+      pg[i] += d[i] * xh; pb[i] += d[i];
+      v[i] = xh; d[i] = g;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    const float m1 = s1 * inv_dim, m2 = s2 * inv_dim;
+    float* out = dx + static_cast<size_t>(row) * dim;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int c = lane + 32 * i;
+      if (c < dim) {
+        const float r = rstd * (d[i] - m1 - v[i] * m2);
+        out[c] = accumulate ? out[c] + r : r;
+      }
+    }
+  }
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    if (which) __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) red[warp][lane + 32 * i] = which ? pb[i] : pg[i];
+    __syncthreads();
+    for (int col = threadIdx.x; col < 32 * NPL; col += 256) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][col];
+      if (col < dim) partial[(static_cast<size_t>(blockIdx.x) * 2 + which) * dim + col] = s;
+    }
+  }
+}
+
+// out[j][c] = sum over the n_partial partial rows, in order (j = 0 .. n_out-1 stacked outputs of width dim)
+__global__ void partial_reduce_kernel(const float* __restrict__ partial, int n_partial, int n_out, int dim, float* __restrict__ out0,
+                                      float* __restrict__ out1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out * dim) return;
+  const int j = i / dim, c = i - j * dim;
+  float s = 0.f;
+  for (int p = 0; p < n_partial; ++p) s += partial[(static_cast<size_t>(p) * n_out + j) * dim + c];
+  (j == 0 ? out0 : out1)[c] = s;
+}
+
+size_t layernorm_bwd_work_bytes(int dim) { return align_up(static_cast<size_t>(kBwdCtas) * 2 * dim * sizeof(float), 256); }
+
+int launch_layernorm_bwd(const float* x, const float* dy, int rows, int dim, const float* gamma, float eps, float* dx, int accumulate,
+                         float* dgamma, float* dbeta, float* work, cudaStream_t stream) {
+  EC_REQUIRE(rows > 0 && dim > 0 && dim <= 1024, "LayerNorm backward: bad shape (dim <= 1024)");
+  EC_REQUIRE(x && dy && gamma && dx && dgamma && dbeta && work, "null argument");
+  const int ctas = std::min(kBwdCtas, cdiv(rows, 8));
+  if (dim <= 128) layernorm_bwd_kernel<4><<<ctas, 256, 0, stream>>>(x, dy, rows, dim, gamma, eps, dx, accumulate, work);
+  else if (dim <= 256) layernorm_bwd_kernel<8><<<ctas, 256, 0, stream>>>(x, dy, rows, dim, gamma, eps, dx, accumulate, work);
+  else if (dim <= 512) layernorm_bwd_kernel<16><<<ctas, 256, 0, stream>>>(x, dy, rows, dim, gamma, eps, dx, accumulate, work);
+  else layernorm_bwd_kernel<32><<<ctas, 256, 0, stream>>>(x, dy, rows, dim, gamma, eps, dx, accumulate, work);
+  EC_CUDA(cudaGetLastError());
+  partial_reduce_kernel<<<cdiv(2 * dim, 256), 256, 0, stream>>>(work, ctas, 2, dim, dgamma, dbeta);
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Column sums of a [rows, cols] matrix (fp32 or activation type): the bias gradient of a Linear / pointwise conv.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ m, int rows, int cols, float* __restrict__ partial) {
+  // thread = column (blockIdx.y tiles the columns by 256), CTA blockIdx.x walks rows blockIdx.x, + gridDim.x, ...: coalesced rows
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) s += ActTraits<T>::from(m[static_cast<size_t>(r) * cols + c]);
+  partial[static_cast<size_t>(blockIdx.x) * cols + c] = s;
+}
+
+
+size_t colsum_work_bytes(int cols) { return align_up(static_cast<size_t>(kBwdCtas) * cols * sizeof(float), 256); }
+
+int launch_colsum(int precision, const void* m, int is_f32, int rows, int cols, float* out, float* work, cudaStream_t stream) {
+  EC_REQUIRE(rows > 0 && cols > 0 && m && out && work, "column sum: bad arguments");
+  const int ctas = std::min(kBwdCtas, rows);
+  dim3 grid(ctas, cdiv(cols, 256));
+  if (is_f32 || precision == EC_PREC_TF32) colsum_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(m), rows, cols, work);
+  else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(m), rows, cols, work);
+  EC_CUDA(cudaGetLastError());
+  partial_reduce_kernel<<<cdiv(cols, 256), 256, 0, stream>>>(work, ctas, 1, cols, out, out);
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dst[c][r] = to_act(src[r][c]): operand-type transposed copy of an fp32 matrix (W^T for the data-gradient GEMMs).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __restrict__ src, int rows, int cols, T* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? src[static_cast<size_t>(r) * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < cols && r < rows) dst[static_cast<size_t>(c) * rows + r] = ActTraits<T>::to(tile[tx][i]);
+  }
+}
+
+int launch_transpose_cast(int precision, const float* src, int rows, int cols, void* dst, cudaStream_t stream) {
+  EC_REQUIRE(rows > 0 && cols > 0 && src && dst, "transpose: bad arguments");
+  dim3 grid(cdiv(cols, 32), cdiv(rows, 32));
+  if (precision == EC_PREC_TF32) transpose_cast_kernel<float><<<grid, 256, 0, stream>>>(src, rows, cols, reinterpret_cast<float*>(dst));
+  else if (precision == EC_PREC_BF16)
+    transpose_cast_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(src, rows, cols, reinterpret_cast<__nv_bfloat16*>(dst));
+  else EC_FAIL("unknown precision");
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Swish backward:  y = z * sigmoid(z)  ->  dz = dy * (s + z * s * (1 - s)),  s = sigmoid(z).       (z = pre-activation, saved)
+// GLU backward:    y = a * sigmoid(g)  ->  da = dy * s,  dg = dy * a * s * (1 - s);  zg = [a | g] rows of width 2C, out [da | dg].
+// Inputs fp32 or activation type for z / zg; dy fp32; outputs in the activation type (operands of the next gradient GEMM).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) swish_bwd_kernel(const T* __restrict__ z, const float* __restrict__ dy, size_t n, T* __restrict__ dz) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float zz = ActTraits<T>::from(z[i]);
+    const float s = 1.f / (1.f + __expf(-zz));
+    dz[i] = ActTraits<T>::to(dy[i] * (s + zz * s * (1.f - s)));
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) glu_bwd_kernel(const T* __restrict__ zg, const float* __restrict__ dy, size_t rows, int C,
+                                                      T* __restrict__ dzg) {
+  const size_t n = rows * C;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const size_t r = i / C; const int c = static_cast<int>(i - r * C);
+    const float a = ActTraits<T>::from(zg[r * 2 * C + c]), g = ActTraits<T>::from(zg[r * 2 * C + C + c]);
+    const float s = 1.f / (1.f + __expf(-g));
+    const float d = dy[i];
+    dzg[r * 2 * C + c] = ActTraits<T>::to(d * s);
+    dzg[r * 2 * C + C + c] = ActTraits<T>::to(d * a * s * (1.f - s));
+  }
+}
+
+int launch_swish_bwd(int precision, const void* z, const float* dy, size_t n, void* dz, cudaStream_t stream) {
+  EC_REQUIRE(z && dy && dz && n > 0, "swish backward: bad arguments");
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
+  if (precision == EC_PREC_TF32) swish_bwd_kernel<float><<<blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(z), dy, n, reinterpret_cast<float*>(dz));
+  else if (precision == EC_PREC_BF16)
+    swish_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(z), dy, n, reinterpret_cast<__nv_bfloat16*>(dz));
+  else EC_FAIL("unknown precision");
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+int launch_glu_bwd(int precision, const void* zg, const float* dy, size_t rows, int C, void* dzg, cudaStream_t stream) {
+  EC_REQUIRE(zg && dy && dzg && rows > 0 && C > 0, "GLU backward: bad arguments");
+  const int blocks = static_cast<int>(std::min<size_t>((rows * C + 255) / 256, 148 * 16));
+  if (precision == EC_PREC_TF32) glu_bwd_kernel<float><<<blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(zg), dy, rows, C, reinterpret_cast<float*>(dzg));
+  else if (precision == EC_PREC_BF16)
+    glu_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(zg), dy, rows, C, reinterpret_cast<__nv_bfloat16*>(dzg));
+  else EC_FAIL("unknown precision");
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+
+}  // namespace ec

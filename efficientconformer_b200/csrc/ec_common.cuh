@@ -217,6 +217,15 @@ size_t ctc_grad_work_bytes(int B, int T, int target_stride);
 int launch_ctc_grad(const float* logits, const float* lse, int B, int T, int V, const int* logits_len, const long long* targets,
                     int target_stride, const long long* target_len, float* work, float grad_scale, float* loss_per_utt, float* grad,
                     cudaStream_t stream);
+// row / element kernels of the backward pass (backward_rows.cu)
+size_t layernorm_bwd_work_bytes(int dim);
+int launch_layernorm_bwd(const float* x, const float* dy, int rows, int dim, const float* gamma, float eps, float* dx, int accumulate,
+                         float* dgamma, float* dbeta, float* work, cudaStream_t stream);
+size_t colsum_work_bytes(int cols);
+int launch_colsum(int precision, const void* m, int is_f32, int rows, int cols, float* out, float* work, cudaStream_t stream);
+int launch_transpose_cast(int precision, const float* src, int rows, int cols, void* dst, cudaStream_t stream);
+int launch_swish_bwd(int precision, const void* z, const float* dy, size_t n, void* dz, cudaStream_t stream);
+int launch_glu_bwd(int precision, const void* zg, const float* dy, size_t rows, int C, void* dzg, cudaStream_t stream);
 int launch_greedy_collapse(const int* argmax, int B, int T, const int* logits_len, int* ids, int* counts, cudaStream_t stream);
 
 }  // namespace ec

@@ -647,6 +647,27 @@ int ec_ctc_greedy(const float* logits, int B, int T, int V, const long long* log
   return launch_greedy_collapse(amax, B, T, len32, ids, counts, st);
 }
 
+// ---------------------------------------------------------------- backward operators (training step)
+size_t ec_op_layernorm_bwd_work_bytes(int dim) { return layernorm_bwd_work_bytes(dim); }
+int ec_op_layernorm_bwd(const float* x, const float* dy, int rows, int dim, const float* gamma, float eps, float* dx, int accumulate,
+                        float* dgamma, float* dbeta, void* work, void* stream) {
+  return launch_layernorm_bwd(x, dy, rows, dim, gamma, eps, dx, accumulate, dgamma, dbeta, reinterpret_cast<float*>(work),
+                              reinterpret_cast<cudaStream_t>(stream));
+}
+size_t ec_op_colsum_work_bytes(int cols) { return colsum_work_bytes(cols); }
+int ec_op_colsum(int precision, const void* m, int is_f32, int rows, int cols, float* out, void* work, void* stream) {
+  return launch_colsum(precision, m, is_f32, rows, cols, out, reinterpret_cast<float*>(work), reinterpret_cast<cudaStream_t>(stream));
+}
+int ec_op_transpose_cast(int precision, const float* src, int rows, int cols, void* dst, void* stream) {
+  return launch_transpose_cast(precision, src, rows, cols, dst, reinterpret_cast<cudaStream_t>(stream));
+}
+int ec_op_swish_bwd(int precision, const void* z, const float* dy, size_t n, void* dz, void* stream) {
+  return launch_swish_bwd(precision, z, dy, n, dz, reinterpret_cast<cudaStream_t>(stream));
+}
+int ec_op_glu_bwd(int precision, const void* zg, const float* dy, size_t rows, int channels, void* dzg, void* stream) {
+  return launch_glu_bwd(precision, zg, dy, rows, channels, dzg, reinterpret_cast<cudaStream_t>(stream));
+}
+
 // ---------------------------------------------------------------- single-operator entry points
 int ec_op_cast(int precision, const float* src, void* dst, size_t n, void* stream) {
   return launch_cast_rows(precision, src, dst, n, reinterpret_cast<cudaStream_t>(stream));

@@ -129,3 +129,63 @@ def subsample_conv(mel, w_folded, b_folded, precision):
     y = torch.empty(B, To, Cc * (F // 2), dtype=act_dtype(pr), device=mel.device)
     check(lib().ec_op_subsample_conv(pr, ptr(mel.float().contiguous()), ptr(w_folded), ptr(b_folded), B, F, T, Cc, ptr(y), stream_ptr()))
     return y
+
+
+# ---- backward operators (training step) --------------------------------------------------------------------------------
+def layernorm_bwd(x, dy, gamma, eps=1e-6, dx_accum=None):
+    """x, dy [rows, dim] fp32 -> (dx, dgamma, dbeta).  dx_accum: fp32 tensor the x-gradient is ADDED to (residual branch)."""
+    x, dy = x.float().contiguous(), dy.float().contiguous()
+    rows, dim = x.numel() // x.shape[-1], x.shape[-1]
+    dx = dx_accum if dx_accum is not None else torch.empty_like(x)
+    dg = torch.empty(dim, dtype=torch.float32, device=x.device)
+    db = torch.empty(dim, dtype=torch.float32, device=x.device)
+    work = torch.empty(lib().ec_op_layernorm_bwd_work_bytes(dim), dtype=torch.uint8, device=x.device)
+    check(lib().ec_op_layernorm_bwd(ptr(x), ptr(dy), rows, dim, ptr(gamma.float().contiguous()), eps, ptr(dx), 1 if dx_accum is not None else 0,
+                                    ptr(dg), ptr(db), ptr(work), stream_ptr()))
+    return dx, dg, db
+
+
+def colsum(m, precision):
+    """Column sums (bias gradient) of a 2-D fp32 or activation-type matrix."""
+    pr = _p(precision)
+    m = m.contiguous()
+    rows, cols = m.shape
+    out = torch.empty(cols, dtype=torch.float32, device=m.device)
+    work = torch.empty(lib().ec_op_colsum_work_bytes(cols), dtype=torch.uint8, device=m.device)
+    check(lib().ec_op_colsum(pr, ptr(m), 1 if m.dtype == torch.float32 else 0, rows, cols, ptr(out), ptr(work), stream_ptr()))
+    return out
+
+
+def transpose_cast(w, precision):
+    """fp32 [rows, cols] -> activation-type [cols, rows]."""
+    pr = _p(precision)
+    w = w.float().contiguous()
+    rows, cols = w.shape
+    out = torch.empty(cols, rows, dtype=act_dtype(pr), device=w.device)
+    check(lib().ec_op_transpose_cast(pr, ptr(w), rows, cols, ptr(out), stream_ptr()))
+    return out
+
+
+def linear_dgrad(dy_act, w_fp32, precision, residual=None):
+    """dX = dY . W  (+ residual): the forward tcgen05 GEMM on the transposed weight copy.  dy_act [M, N] activation type,
+    w_fp32 [N, K] fp32 (the nn.Linear weight) -> dX [M, K] fp32."""
+    wt = transpose_cast(w_fp32, precision)                      # [K, N] = the "weight" of a GEMM that reduces over N
+    return gemm(dy_act, wt, None, precision, residual=residual)[0]
+
+
+def swish_bwd(z_act, dy, precision):
+    pr = _p(precision)
+    z_act, dy = z_act.contiguous(), dy.float().contiguous()
+    out = torch.empty_like(z_act)
+    check(lib().ec_op_swish_bwd(pr, ptr(z_act), ptr(dy), z_act.numel(), ptr(out), stream_ptr()))
+    return out
+
+
+def glu_bwd(zg_act, dy, precision):
+    """zg_act [rows, 2C] = [a | g] (pre-GLU pointwise output), dy [rows, C] fp32 -> [da | dg] [rows, 2C] activation type."""
+    pr = _p(precision)
+    zg_act, dy = zg_act.contiguous(), dy.float().contiguous()
+    rows, C2 = zg_act.shape
+    out = torch.empty_like(zg_act)
+    check(lib().ec_op_glu_bwd(pr, ptr(zg_act), ptr(dy), rows, C2 // 2, ptr(out), stream_ptr()))
+    return out

@@ -136,6 +136,22 @@ int ec_ctc_loss(const float* logits, int batch, int t, int vocab, const long lon
                 int target_stride, const long long* target_len, void* scratch, float* loss_per_utt, float* loss_mean,
                 void* stream);
 /* ids [B, T] int32 (collapsed token ids, zero padded), counts [B] int32 */
+/* ---- backward operators (training step; each is tested against autograd over the CPU oracle, tests/test_gpu_backward.py) ----
+ * ec_op_layernorm_bwd : x, dy [rows, dim] fp32, gamma [dim] -> dx [rows, dim] (accumulate != 0: dx += ...: the LayerNorm sits on
+ *                       a residual branch), dgamma / dbeta [dim].  Row statistics are recomputed from x.  nn.LayerNorm(eps) backward.
+ * ec_op_colsum        : out[c] = sum_r m[r, c]  (bias gradient of a Linear / pointwise conv); m fp32 (is_f32) or activation type.
+ * ec_op_transpose_cast: dst [cols, rows] activation type = transpose of src [rows, cols] fp32.  The data gradient of a Linear,
+ *                       dX = dY . W, is ec_op_gemm(A = dY, W = transpose_cast(W)) on the same tcgen05 kernel as the forward.
+ * ec_op_swish_bwd     : dz = dy * d/dz (z sigmoid z);   ec_op_glu_bwd: zg = [a | g] (rows x 2C), dy (rows x C) -> [da | dg].
+ * Reductions use per-CTA partials added in a fixed order: bit-reproducible. */
+size_t ec_op_layernorm_bwd_work_bytes(int dim);
+int ec_op_layernorm_bwd(const float* x, const float* dy, int rows, int dim, const float* gamma, float eps, float* dx, int accumulate,
+                        float* dgamma, float* dbeta, void* work, void* stream);
+size_t ec_op_colsum_work_bytes(int cols);
+int ec_op_colsum(int precision, const void* m, int is_f32, int rows, int cols, float* out, void* work, void* stream);
+int ec_op_transpose_cast(int precision, const float* src, int rows, int cols, void* dst, void* stream);
+int ec_op_swish_bwd(int precision, const void* z, const float* dy, size_t n, void* dz, void* stream);
+int ec_op_glu_bwd(int precision, const void* zg, const float* dy, size_t rows, int channels, void* dzg, void* stream);
 /* Backward of ec_ctc_loss (first kernel of the training backward pass): also writes grad_logits [B, T, V] fp32 =
  * d(mean_b nll_b) / d logits = (softmax - posterior occupancy of the class) / B for t < logits_len[b], 0 for padded frames
  * (what autograd gives for LossCTC.forward, reference models/losses.py:56-71).  work: ec_ctc_grad_work_bytes() device bytes. */

@@ -73,3 +73,64 @@ def test_ctc_gradient_random_shapes():
     (3.0 * loss).backward()
     _, _, ref_grad = _oracle_ctc_grad(logits.detach().cpu(), ll, y, yl)
     assert rel_l2(logits.grad, 3.0 * ref_grad) < 1e-4
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from efficientconformer_b200 import ops as o
+    return o
+
+
+def test_layernorm_backward(ops):
+    rng = random.Random(21)
+    for trial in range(8):
+        rows = rng.choice([1, 7, 64, 1000, 4001, 16000])
+        dim = rng.choice([100, 120, 168, 240, 256, 360, 512, 720])
+        g = torch.Generator().manual_seed(700 + trial)
+        x = (2.0 * torch.randn(rows, dim, generator=g) + 0.7)
+        dy = torch.randn(rows, dim, generator=g)
+        gamma = 1 + 0.2 * torch.randn(dim, generator=g)
+        beta = 0.1 * torch.randn(dim, generator=g)
+        xr = x.double().requires_grad_(True); gr = gamma.double().requires_grad_(True); br = beta.double().requires_grad_(True)
+        torch.nn.functional.layer_norm(xr, (dim,), gr, br, 1e-6).backward(dy.double())
+        dx, dg, db = ops.layernorm_bwd(x.to(DEV), dy.to(DEV), gamma.to(DEV))
+        assert rel_l2(dx, xr.grad) < 2e-5, (trial, rows, dim)
+        assert rel_l2(dg, gr.grad) < 2e-5 and rel_l2(db, br.grad) < 2e-5, (trial, rows, dim)
+        # residual-branch accumulation and bit reproducibility
+        acc = torch.randn(rows, dim, generator=g).to(DEV)
+        ref_acc = acc.double().cpu() + xr.grad
+        dx2, dg2, db2 = ops.layernorm_bwd(x.to(DEV), dy.to(DEV), gamma.to(DEV), dx_accum=acc)
+        assert rel_l2(dx2, ref_acc) < 2e-5
+        assert torch.equal(dg, dg2) and torch.equal(db, db2)
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+def test_linear_data_gradient_bias_gradient_and_activations(ops, prec):
+    """dX = dY . W on the forward tcgen05 kernel with the transposed weight copy; bias gradient = column sums;
+    Swish / GLU backward."""
+    tol = 1e-3 if prec == "tf32" else 8e-3
+    rng = random.Random(31)
+    for trial in range(6):
+        M = rng.choice([5, 128, 1000, 4000, 16000])
+        N, K = rng.choice([(480, 120), (120, 480), (360, 120), (240, 240), (256, 240), (2880, 720)])
+        g = torch.Generator().manual_seed(800 + trial)
+        dy = torch.randn(M, N, generator=g)
+        w = torch.randn(N, K, generator=g) / N ** 0.5
+        res = torch.randn(M, K, generator=g)
+        dy_act = ops.cast(dy.to(DEV), prec)
+        dx = ops.linear_dgrad(dy_act, w.to(DEV), prec, residual=res.to(DEV))
+        ref = dy_act.double().cpu() @ w.double() + res.double()
+        assert rel_l2(dx, ref) < tol, (trial, M, N, K)
+        bsum = ops.colsum(dy_act, prec)
+        assert rel_l2(bsum, dy_act.double().cpu().sum(0)) < 1e-5
+        assert rel_l2(ops.colsum(dy.to(DEV), prec), dy.double().sum(0)) < 1e-5
+        # activations
+        z = ops.cast((2 * torch.randn(M, N, generator=g)).to(DEV), prec)
+        zr = z.double().cpu().requires_grad_(True)
+        (zr * torch.sigmoid(zr)).backward(dy.double())
+        assert rel_l2(ops.swish_bwd(z, dy.to(DEV), prec), zr.grad) < (2e-5 if prec == "tf32" else 4e-3) + (5e-4 if prec == "tf32" else 0)
+        C = N // 2
+        zg = ops.cast((2 * torch.randn(M, 2 * C, generator=g)).to(DEV), prec)
+        zgr = zg.double().cpu().requires_grad_(True)
+        (zgr[:, :C] * torch.sigmoid(zgr[:, C:])).backward(dy[:, :C].double())
+        assert rel_l2(ops.glu_bwd(zg, dy[:, :C].contiguous().to(DEV), prec), zgr.grad) < (6e-4 if prec == "tf32" else 4e-3)
