@@ -226,6 +226,10 @@ int launch_colsum(int precision, const void* m, int is_f32, int rows, int cols, 
 int launch_transpose_cast(int precision, const float* src, int rows, int cols, void* dst, cudaStream_t stream);
 int launch_swish_bwd(int precision, const void* z, const float* dy, size_t n, void* dz, cudaStream_t stream);
 int launch_glu_bwd(int precision, const void* zg, const float* dy, size_t rows, int C, void* dzg, cudaStream_t stream);
+// weight gradient dW[N,K] = dY[M,N]^T . X[M,K] on tcgen05 with MN-major operands (wgrad_tc.cu)
+size_t wgrad_work_bytes(int precision, int M, int N, int K);
+int launch_wgrad(int precision, const void* dy, const void* x, int M, int N, int K, float* dw, int accumulate, float* work,
+                 cudaStream_t stream);
 int launch_greedy_collapse(const int* argmax, int B, int T, const int* logits_len, int* ids, int* counts, cudaStream_t stream);
 
 }  // namespace ec

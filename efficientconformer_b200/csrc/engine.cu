@@ -654,6 +654,10 @@ int ec_op_layernorm_bwd(const float* x, const float* dy, int rows, int dim, cons
   return launch_layernorm_bwd(x, dy, rows, dim, gamma, eps, dx, accumulate, dgamma, dbeta, reinterpret_cast<float*>(work),
                               reinterpret_cast<cudaStream_t>(stream));
 }
+size_t ec_op_wgrad_work_bytes(int precision, int M, int N, int K) { return wgrad_work_bytes(precision, M, N, K); }
+int ec_op_wgrad(int precision, const void* dy, const void* x, int M, int N, int K, float* dw, int accumulate, void* work, void* stream) {
+  return launch_wgrad(precision, dy, x, M, N, K, dw, accumulate, reinterpret_cast<float*>(work), reinterpret_cast<cudaStream_t>(stream));
+}
 size_t ec_op_colsum_work_bytes(int cols) { return colsum_work_bytes(cols); }
 int ec_op_colsum(int precision, const void* m, int is_f32, int rows, int cols, float* out, void* work, void* stream) {
   return launch_colsum(precision, m, is_f32, rows, cols, out, reinterpret_cast<float*>(work), reinterpret_cast<cudaStream_t>(stream));

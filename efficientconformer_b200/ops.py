@@ -189,3 +189,15 @@ def glu_bwd(zg_act, dy, precision):
     out = torch.empty_like(zg_act)
     check(lib().ec_op_glu_bwd(pr, ptr(zg_act), ptr(dy), rows, C2 // 2, ptr(out), stream_ptr()))
     return out
+
+
+def linear_wgrad(dy_act, x_act, precision, dw_accum=None):
+    """dW [N, K] fp32 (+)= dY[M, N]^T . X[M, K] (both activation type): tcgen05 with MN-major operands."""
+    pr = _p(precision)
+    dy_act, x_act = dy_act.contiguous(), x_act.contiguous()
+    M, N = dy_act.shape
+    K = x_act.shape[1]
+    dw = dw_accum if dw_accum is not None else torch.empty(N, K, dtype=torch.float32, device=dy_act.device)
+    work = torch.empty(lib().ec_op_wgrad_work_bytes(pr, M, N, K), dtype=torch.uint8, device=dy_act.device)
+    check(lib().ec_op_wgrad(pr, ptr(dy_act), ptr(x_act), M, N, K, ptr(dw), 1 if dw_accum is not None else 0, ptr(work), stream_ptr()))
+    return dw

@@ -143,7 +143,11 @@ int ec_ctc_loss(const float* logits, int batch, int t, int vocab, const long lon
  * ec_op_transpose_cast: dst [cols, rows] activation type = transpose of src [rows, cols] fp32.  The data gradient of a Linear,
  *                       dX = dY . W, is ec_op_gemm(A = dY, W = transpose_cast(W)) on the same tcgen05 kernel as the forward.
  * ec_op_swish_bwd     : dz = dy * d/dz (z sigmoid z);   ec_op_glu_bwd: zg = [a | g] (rows x 2C), dy (rows x C) -> [da | dg].
- * Reductions use per-CTA partials added in a fixed order: bit-reproducible. */
+ * Reductions use per-CTA partials added in a fixed order: bit-reproducible.
+ * ec_op_wgrad         : dW [N, K] fp32 (+)= dY[M, N]^T . X[M, K], both activation type, on tcgen05 with MN-major operands (no
+ *                       transposed copies), split over M with a fixed-order reduction of the partial tiles. */
+size_t ec_op_wgrad_work_bytes(int precision, int M, int N, int K);
+int ec_op_wgrad(int precision, const void* dy, const void* x, int M, int N, int K, float* dw, int accumulate, void* work, void* stream);
 size_t ec_op_layernorm_bwd_work_bytes(int dim);
 int ec_op_layernorm_bwd(const float* x, const float* dy, int rows, int dim, const float* gamma, float eps, float* dx, int accumulate,
                         float* dgamma, float* dbeta, void* work, void* stream);

@@ -134,3 +134,23 @@ def test_linear_data_gradient_bias_gradient_and_activations(ops, prec):
         zgr = zg.double().cpu().requires_grad_(True)
         (zgr[:, :C] * torch.sigmoid(zgr[:, C:])).backward(dy[:, :C].double())
         assert rel_l2(ops.glu_bwd(zg, dy[:, :C].contiguous().to(DEV), prec), zgr.grad) < (6e-4 if prec == "tf32" else 4e-3)
+
+
+@pytest.mark.parametrize("prec", ["bf16", "tf32"])
+def test_linear_weight_gradient_tcgen05(ops, prec):
+    """dW = dY^T . X with MN-major tcgen05 operands and split-M reduction, against fp64 on the same rounded operands."""
+    rng = random.Random(41)
+    shapes = [(16000, 480, 120), (16000, 120, 480), (8000, 504, 168), (4000, 240, 960), (4000, 256, 240), (1000, 120, 4800),
+              (77, 120, 120), (1, 360, 120), (130, 2880, 720), (16000, 360, 120)]
+    for trial, (M, N, K) in enumerate(shapes):
+        g = torch.Generator().manual_seed(1000 + trial)
+        dy = ops.cast(torch.randn(M, N, generator=g).to(DEV), prec)
+        x = ops.cast(torch.randn(M, K, generator=g).to(DEV), prec)
+        dw = ops.linear_wgrad(dy, x, prec)
+        ref = dy.double().cpu().t() @ x.double().cpu()
+        assert rel_l2(dw, ref) < 2e-5, (prec, M, N, K, rel_l2(dw, ref))
+        acc = torch.randn(N, K, generator=g).to(DEV)
+        ref2 = acc.double().cpu() + ref
+        dw2 = ops.linear_wgrad(dy, x, prec, dw_accum=acc)
+        assert rel_l2(dw2, ref2) < 2e-5
+        assert torch.equal(ops.linear_wgrad(dy, x, prec), dw)                # fixed-order reduction: bit reproducible
