@@ -1,0 +1,294 @@
+// Training-mode kernels of the convolution module's depthwise stage:
+//   depthwise Conv1d (k taps, stride s, 'same' zero halo) -> BatchNorm1d with BATCH statistics over all B*T_out frames, padded
+//   frames included (the reference never masks) -> Swish             (reference models/modules.py:515-517, models/layers.py:96-136)
+// and their backward.  Channels-last activations [B, T, C]; all kernels are bandwidth bound; every reduction over frames uses
+// per-CTA partials added in a fixed order (bit-reproducible).  Between the statistics and the normalisation the host may
+// merge the per-rank (count, mean, M2) statistics across ranks (SyncBatchNorm of the reference's distribute_strategy, models/model_ctc.py:73).
+//
+//   forward :  dwconv_raw        y = b + sum_k w[c,k] x[t*s + k - pad]            (fp32) + per-channel mean / centred sum of squares
+//              bn_swish_fwd      h = swish((y - mean) * rstd * gamma + beta)      (activation type)
+//              bn_running_update running statistics, momentum 0.1, unbiased variance
+//   backward:  bn_swish_bwd_stats  dz = dh * swish'(z);  sum dz, sum dz * xhat    (= dbeta, dgamma)
+//              bn_swish_bwd_apply  dy = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat))
+//              dwconv_bwd_data     dx[ti] = sum_k w[c,k] dy[(ti + pad - k) / s]   (terms with a whole, in-range quotient)
+//              dwconv_bwd_weight   dw[c,k] = sum_{b,t} dy[t] x[t*s + k - pad],  db[c] = sum dy
+#include "ec_common.cuh"
+#include <algorithm>
+
+namespace ec {
+
+namespace {
+constexpr int kCtas = 296;
+constexpr int kMaxTaps = 31;
+
+// rows [r0, r1) of this CTA for a row-strided split of `rows` over gridDim.x CTAs (contiguous ranges: coalesced, deterministic)
+__device__ __forceinline__ void cta_rows(size_t rows, size_t& r0, size_t& r1) {
+  const size_t per = (rows + gridDim.x - 1) / gridDim.x;
+  r0 = min(rows, per * blockIdx.x); r1 = min(rows, r0 + per);
+}
+}  // namespace
+
+// ---- forward: raw depthwise conv + statistics ------------------------------------------------------------------------------
+// thread = channel (blockIdx.y tiles channels by 128), CTA = a contiguous range of output frames (flattened b*T_out + t)
+template <typename T>
+__global__ void __launch_bounds__(128) dwconv_raw_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                         int B, int T_in, int T_out, int C, int K, int stride, float* __restrict__ y,
+                                                         float* __restrict__ partial /* [gridDim.x][2][C] */) {
+  const int c = blockIdx.y * 128 + threadIdx.x;
+  if (c >= C) return;
+  float wk[kMaxTaps];
+#pragma unroll
+  for (int k = 0; k < kMaxTaps; ++k) wk[k] = k < K ? w[c * K + k] : 0.f;
+  const float bc = bias[c];
+  const int pad = (K - 1) / 2;
+  size_t r0, r1; cta_rows(static_cast<size_t>(B) * T_out, r0, r1);
+  float s1 = 0.f, s2 = 0.f;
+  for (size_t r = r0; r < r1; ++r) {
+    const int b = static_cast<int>(r / T_out), t = static_cast<int>(r - static_cast<size_t>(b) * T_out);
+    const T* xb = x + static_cast<size_t>(b) * T_in * C + c;
+    float acc = bc;
+#pragma unroll
+    for (int k = 0; k < kMaxTaps; ++k) {
+      const int ti = t * stride + k - pad;
+      if (k < K && ti >= 0 && ti < T_in) acc = fmaf(wk[k], ActTraits<T>::from(xb[static_cast<size_t>(ti) * C]), acc);
+    }
+    y[r * C + c] = acc;
+    s1 += acc;
+  }
+  // second pass over this thread's own outputs: centred sum of squares about the local mean (sum of squares minus mean^2 loses
+  // every digit when |mean| >> std, e.g. a tiny tap vector next to a large bias)
+  const float lm = r1 > r0 ? s1 / static_cast<float>(r1 - r0) : 0.f;
+  for (size_t r = r0; r < r1; ++r) { const float d = y[r * C + c] - lm; s2 = fmaf(d, d, s2); }
+  partial[(static_cast<size_t>(blockIdx.x) * 2) * C + c] = lm;
+  partial[(static_cast<size_t>(blockIdx.x) * 2 + 1) * C + c] = s2;
+}
+
+// (mean, M2) of the CTA row ranges merged in CTA order with Chan's update, in double: stats[0][c] = mean, stats[1][c] = M2
+__global__ void bn_stats_merge_kernel(const float* __restrict__ partial, int n_partial, size_t rows, int C, float* __restrict__ stats) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const size_t per = (rows + n_partial - 1) / n_partial;
+  double n = 0.0, mean = 0.0, m2 = 0.0;
+  for (int p = 0; p < n_partial; ++p) {
+    const size_t r0 = min(rows, per * p), r1 = min(rows, r0 + per);
+    const double nb = static_cast<double>(r1 - r0);
+    if (nb == 0.0) continue;
+    const double mb = partial[(static_cast<size_t>(p) * 2) * C + c], qb = partial[(static_cast<size_t>(p) * 2 + 1) * C + c];
+    const double tot = n + nb, dl = mb - mean;
+    mean += dl * nb / tot;
+    m2 += qb + dl * dl * n * nb / tot;
+    n = tot;
+  }
+  stats[c] = static_cast<float>(mean);
+  stats[C + c] = static_cast<float>(m2);
+}
+
+// out[j][c] = sum_p partial[p][j][c] in CTA order
+__global__ void conv_partial_reduce_kernel(const float* __restrict__ partial, int n_partial, int n_out, int dim, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out * dim) return;
+  float s = 0.f;
+  for (int p = 0; p < n_partial; ++p) s += partial[static_cast<size_t>(p) * n_out * dim + i];
+  out[i] = s;
+}
+
+// stats [2][C] (mean, centred sum of squares M2) over `count` frames -> mean / rstd (biased variance) and the running-statistics update
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, int C, float count, float eps, float momentum, float* __restrict__ mean,
+                                   float* __restrict__ rstd, float* __restrict__ running_mean, float* __restrict__ running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float m = sums[c];
+  const float var = fmaxf(sums[C + c] / count, 0.f);
+  mean[c] = m;
+  rstd[c] = rsqrtf(var + eps);
+  if (running_mean != nullptr) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * (count > 1.f ? count / (count - 1.f) : 1.f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_swish_fwd_kernel(const float* __restrict__ y, size_t rows, int C, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, T* __restrict__ h) {
+  const size_t n = rows * C, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int c = static_cast<int>(i % C);
+    const float z = (y[i] - mean[c]) * rstd[c] * gamma[c] + beta[c];
+    h[i] = ActTraits<T>::to(z / (1.f + __expf(-z)));
+  }
+}
+
+// ---- backward ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float swish_grad(float z) { const float s = 1.f / (1.f + __expf(-z)); return s + z * s * (1.f - s); }
+
+// thread = channel; partial[cta][0][c] = sum dz, partial[cta][1][c] = sum dz * xhat
+__global__ void __launch_bounds__(128) bn_swish_bwd_stats_kernel(const float* __restrict__ y, const float* __restrict__ dh, size_t rows, int C,
+                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 float* __restrict__ partial) {
+  const int c = blockIdx.y * 128 + threadIdx.x;
+  if (c >= C) return;
+  const float mu = mean[c], rs = rstd[c], g = gamma[c], be = beta[c];
+  size_t r0, r1; cta_rows(rows, r0, r1);
+  float s1 = 0.f, s2 = 0.f;
+  for (size_t r = r0; r < r1; ++r) {
+    const float xh = (y[r * C + c] - mu) * rs;
+    const float dz = dh[r * C + c] * swish_grad(xh * g + be);
+    s1 += dz; s2 = fmaf(dz, xh, s2);
+  }
+  partial[(static_cast<size_t>(blockIdx.x) * 2) * C + c] = s1;
+  partial[(static_cast<size_t>(blockIdx.x) * 2 + 1) * C + c] = s2;
+}
+
+// dy = gamma * rstd * (dz - sum_dz / R - xhat * sum_dzx / R)   (R = frames the statistics were taken over, all ranks)
+__global__ void __launch_bounds__(256) bn_swish_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ dh, size_t rows, int C,
+                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 const float* __restrict__ sums /* [2][C] */, float count,
+                                                                 float* __restrict__ dy) {
+  const size_t n = rows * C, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const float inv = 1.f / count;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int c = static_cast<int>(i % C);
+    const float xh = (y[i] - mean[c]) * rstd[c];
+    const float dz = dh[i] * swish_grad(xh * gamma[c] + beta[c]);
+    dy[i] = gamma[c] * rstd[c] * (dz - sums[c] * inv - xh * sums[C + c] * inv);
+  }
+}
+
+// dx[b, ti, c] = sum_k w[c,k] * dy[b, to, c],  to = (ti + pad - k) / s when divisible and 0 <= to < T_out
+__global__ void __launch_bounds__(128) dwconv_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, int B, int T_in,
+                                                              int T_out, int C, int K, int stride, float* __restrict__ dx) {
+  const int c = blockIdx.y * 128 + threadIdx.x;
+  if (c >= C) return;
+  float wk[kMaxTaps];
+#pragma unroll
+  for (int k = 0; k < kMaxTaps; ++k) wk[k] = k < K ? w[c * K + k] : 0.f;
+  const int pad = (K - 1) / 2;
+  size_t r0, r1; cta_rows(static_cast<size_t>(B) * T_in, r0, r1);
+  for (size_t r = r0; r < r1; ++r) {
+    const int b = static_cast<int>(r / T_in), ti = static_cast<int>(r - static_cast<size_t>(b) * T_in);
+    const float* db = dy + static_cast<size_t>(b) * T_out * C + c;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxTaps; ++k) {
+      const int num = ti + pad - k;
+      if (k < K && num >= 0 && num % stride == 0) {
+        const int to = num / stride;
+        if (to < T_out) acc = fmaf(wk[k], db[static_cast<size_t>(to) * C], acc);
+      }
+    }
+    dx[r * C + c] = acc;
+  }
+}
+
+// partial[cta][c][k] = sum over this CTA's output frames of dy * x[t*s + k - pad];  partial[cta][c][K] = sum dy
+template <typename T>
+__global__ void __launch_bounds__(128) dwconv_bwd_weight_kernel(const float* __restrict__ dy, const T* __restrict__ x, int B, int T_in, int T_out,
+                                                                int C, int K, int stride, float* __restrict__ partial) {
+  const int c = blockIdx.y * 128 + threadIdx.x;
+  if (c >= C) return;
+  const int pad = (K - 1) / 2;
+  float acc[kMaxTaps + 1];
+#pragma unroll
+  for (int k = 0; k <= kMaxTaps; ++k) acc[k] = 0.f;
+  size_t r0, r1; cta_rows(static_cast<size_t>(B) * T_out, r0, r1);
+  for (size_t r = r0; r < r1; ++r) {
+    const int b = static_cast<int>(r / T_out), t = static_cast<int>(r - static_cast<size_t>(b) * T_out);
+    const T* xb = x + static_cast<size_t>(b) * T_in * C + c;
+    const float d = dy[r * C + c];
+    acc[kMaxTaps] += d;
+#pragma unroll
+    for (int k = 0; k < kMaxTaps; ++k) {
+      const int ti = t * stride + k - pad;
+      if (k < K && ti >= 0 && ti < T_in) acc[k] = fmaf(d, ActTraits<T>::from(xb[static_cast<size_t>(ti) * C]), acc[k]);
+    }
+  }
+  float* out = partial + (static_cast<size_t>(blockIdx.x) * C + c) * (K + 1);
+#pragma unroll
+  for (int k = 0; k < kMaxTaps; ++k) if (k < K) out[k] = acc[k];
+  out[K] = acc[kMaxTaps];
+}
+// dw[c][k] / db[c] from the partials, in CTA order
+__global__ void dwconv_wgrad_reduce_kernel(const float* __restrict__ partial, int n_partial, int C, int K, float* __restrict__ dw,
+                                           float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * (K + 1)) return;
+  float s = 0.f;
+  for (int p = 0; p < n_partial; ++p) s += partial[static_cast<size_t>(p) * C * (K + 1) + i];
+  const int c = i / (K + 1), k = i - c * (K + 1);
+  if (k < K) dw[c * K + k] = s; else db[c] = s;
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------------------
+size_t conv_train_work_bytes(int C, int K) { return align_up(static_cast<size_t>(kCtas) * C * std::max(K + 1, 2) * sizeof(float), 256); }
+
+static int ctas_for(size_t rows) { return static_cast<int>(std::min<size_t>(kCtas, std::max<size_t>(rows, 1))); }
+
+int launch_dwconv_raw(int precision, const void* x, const float* w, const float* bias, int B, int T, int C, int K, int stride, float* y,
+                      float* sums /* [2][C] */, float* work, cudaStream_t st) {
+  EC_REQUIRE(K % 2 == 1 && K <= kMaxTaps && (stride == 1 || stride == 2), "depthwise conv: odd k <= 31, stride 1 or 2");
+  const int T_out = (T - 1) / stride + 1;
+  const int ctas = ctas_for(static_cast<size_t>(B) * T_out);
+  dim3 grid(ctas, cdiv(C, 128));
+  if (precision == EC_PREC_TF32)
+    dwconv_raw_kernel<float><<<grid, 128, 0, st>>>(reinterpret_cast<const float*>(x), w, bias, B, T, T_out, C, K, stride, y, work);
+  else
+    dwconv_raw_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, bias, B, T, T_out, C, K, stride, y, work);
+  EC_CUDA(cudaGetLastError());
+  bn_stats_merge_kernel<<<cdiv(C, 128), 128, 0, st>>>(work, ctas, static_cast<size_t>(B) * T_out, C, sums);
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+int launch_bn_finalize(const float* sums, int C, float count, float eps, float momentum, float* mean, float* rstd, float* running_mean,
+                       float* running_var, cudaStream_t st) {
+  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(sums, C, count, eps, momentum, mean, rstd, running_mean, running_var);
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+int launch_bn_swish_fwd(int precision, const float* y, size_t rows, int C, const float* mean, const float* rstd, const float* gamma,
+                        const float* beta, void* h, cudaStream_t st) {
+  const int blocks = static_cast<int>(std::min<size_t>((rows * C + 255) / 256, 148 * 16));
+  if (precision == EC_PREC_TF32) bn_swish_fwd_kernel<float><<<blocks, 256, 0, st>>>(y, rows, C, mean, rstd, gamma, beta, reinterpret_cast<float*>(h));
+  else bn_swish_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(y, rows, C, mean, rstd, gamma, beta, reinterpret_cast<__nv_bfloat16*>(h));
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+int launch_bn_swish_bwd_stats(const float* y, const float* dh, size_t rows, int C, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, float* sums /* [2][C]: dbeta, dgamma */, float* work, cudaStream_t st) {
+  const int ctas = ctas_for(rows);
+  bn_swish_bwd_stats_kernel<<<dim3(ctas, cdiv(C, 128)), 128, 0, st>>>(y, dh, rows, C, mean, rstd, gamma, beta, work);
+  EC_CUDA(cudaGetLastError());
+  conv_partial_reduce_kernel<<<cdiv(2 * C, 256), 256, 0, st>>>(work, ctas, 2, C, sums);
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+int launch_bn_swish_bwd_apply(const float* y, const float* dh, size_t rows, int C, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, const float* sums, float count, float* dy, cudaStream_t st) {
+  const int blocks = static_cast<int>(std::min<size_t>((rows * C + 255) / 256, 148 * 16));
+  bn_swish_bwd_apply_kernel<<<blocks, 256, 0, st>>>(y, dh, rows, C, mean, rstd, gamma, beta, sums, count, dy);
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+int launch_dwconv_bwd(int precision, const float* dy, const void* x, const float* w, int B, int T, int C, int K, int stride, float* dx,
+                      float* dw, float* db, float* work, cudaStream_t st) {
+  EC_REQUIRE(K % 2 == 1 && K <= kMaxTaps && (stride == 1 || stride == 2), "depthwise conv: odd k <= 31, stride 1 or 2");
+  const int T_out = (T - 1) / stride + 1;
+  if (dx != nullptr) {
+    dwconv_bwd_data_kernel<<<dim3(ctas_for(static_cast<size_t>(B) * T), cdiv(C, 128)), 128, 0, st>>>(dy, w, B, T, T_out, C, K, stride, dx);
+    EC_CUDA(cudaGetLastError());
+  }
+  const int ctas = ctas_for(static_cast<size_t>(B) * T_out);
+  dim3 grid(ctas, cdiv(C, 128));
+  if (precision == EC_PREC_TF32)
+    dwconv_bwd_weight_kernel<float><<<grid, 128, 0, st>>>(dy, reinterpret_cast<const float*>(x), B, T, T_out, C, K, stride, work);
+  else
+    dwconv_bwd_weight_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(dy, reinterpret_cast<const __nv_bfloat16*>(x), B, T, T_out, C, K, stride, work);
+  EC_CUDA(cudaGetLastError());
+  dwconv_wgrad_reduce_kernel<<<cdiv(C * (K + 1), 256), 256, 0, st>>>(work, ctas, C, K, dw, db);
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+
+}  // namespace ec

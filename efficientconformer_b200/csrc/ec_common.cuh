@@ -230,6 +230,20 @@ int launch_glu_bwd(int precision, const void* zg, const float* dy, size_t rows, 
 size_t wgrad_work_bytes(int precision, int M, int N, int K);
 int launch_wgrad(int precision, const void* dy, const void* x, int M, int N, int K, float* dw, int accumulate, float* work,
                  cudaStream_t stream);
+// training-mode depthwise conv + BatchNorm (batch statistics) + Swish and their backward (conv_train.cu)
+size_t conv_train_work_bytes(int C, int K);
+int launch_dwconv_raw(int precision, const void* x, const float* w, const float* bias, int B, int T, int C, int K, int stride, float* y,
+                      float* sums, float* work, cudaStream_t st);
+int launch_bn_finalize(const float* sums, int C, float count, float eps, float momentum, float* mean, float* rstd, float* running_mean,
+                       float* running_var, cudaStream_t st);
+int launch_bn_swish_fwd(int precision, const float* y, size_t rows, int C, const float* mean, const float* rstd, const float* gamma,
+                        const float* beta, void* h, cudaStream_t st);
+int launch_bn_swish_bwd_stats(const float* y, const float* dh, size_t rows, int C, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, float* sums, float* work, cudaStream_t st);
+int launch_bn_swish_bwd_apply(const float* y, const float* dh, size_t rows, int C, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, const float* sums, float count, float* dy, cudaStream_t st);
+int launch_dwconv_bwd(int precision, const float* dy, const void* x, const float* w, int B, int T, int C, int K, int stride, float* dx,
+                      float* dw, float* db, float* work, cudaStream_t st);
 int launch_greedy_collapse(const int* argmax, int B, int T, const int* logits_len, int* ids, int* counts, cudaStream_t stream);
 
 }  // namespace ec

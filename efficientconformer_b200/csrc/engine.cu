@@ -654,6 +654,34 @@ int ec_op_layernorm_bwd(const float* x, const float* dy, int rows, int dim, cons
   return launch_layernorm_bwd(x, dy, rows, dim, gamma, eps, dx, accumulate, dgamma, dbeta, reinterpret_cast<float*>(work),
                               reinterpret_cast<cudaStream_t>(stream));
 }
+size_t ec_op_conv_train_work_bytes(int channels, int k) { return conv_train_work_bytes(channels, k); }
+int ec_op_dwconv_raw(int precision, const void* x, const float* w, const float* bias, int batch, int t, int channels, int k, int stride,
+                     float* y, float* sums, void* work, void* stream) {
+  return launch_dwconv_raw(precision, x, w, bias, batch, t, channels, k, stride, y, sums, reinterpret_cast<float*>(work),
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+int ec_op_bn_finalize(const float* sums, int channels, float count, float eps, float momentum, float* mean, float* rstd,
+                      float* running_mean, float* running_var, void* stream) {
+  return launch_bn_finalize(sums, channels, count, eps, momentum, mean, rstd, running_mean, running_var, reinterpret_cast<cudaStream_t>(stream));
+}
+int ec_op_bn_swish_fwd(int precision, const float* y, size_t rows, int channels, const float* mean, const float* rstd, const float* gamma,
+                       const float* beta, void* h, void* stream) {
+  return launch_bn_swish_fwd(precision, y, rows, channels, mean, rstd, gamma, beta, h, reinterpret_cast<cudaStream_t>(stream));
+}
+int ec_op_bn_swish_bwd_stats(const float* y, const float* dh, size_t rows, int channels, const float* mean, const float* rstd,
+                             const float* gamma, const float* beta, float* sums, void* work, void* stream) {
+  return launch_bn_swish_bwd_stats(y, dh, rows, channels, mean, rstd, gamma, beta, sums, reinterpret_cast<float*>(work),
+                                   reinterpret_cast<cudaStream_t>(stream));
+}
+int ec_op_bn_swish_bwd_apply(const float* y, const float* dh, size_t rows, int channels, const float* mean, const float* rstd,
+                             const float* gamma, const float* beta, const float* sums, float count, float* dy, void* stream) {
+  return launch_bn_swish_bwd_apply(y, dh, rows, channels, mean, rstd, gamma, beta, sums, count, dy, reinterpret_cast<cudaStream_t>(stream));
+}
+int ec_op_dwconv_bwd(int precision, const float* dy, const void* x, const float* w, int batch, int t, int channels, int k, int stride,
+                     float* dx, float* dw, float* db, void* work, void* stream) {
+  return launch_dwconv_bwd(precision, dy, x, w, batch, t, channels, k, stride, dx, dw, db, reinterpret_cast<float*>(work),
+                           reinterpret_cast<cudaStream_t>(stream));
+}
 size_t ec_op_wgrad_work_bytes(int precision, int M, int N, int K) { return wgrad_work_bytes(precision, M, N, K); }
 int ec_op_wgrad(int precision, const void* dy, const void* x, int M, int N, int K, float* dw, int accumulate, void* work, void* stream) {
   return launch_wgrad(precision, dy, x, M, N, K, dw, accumulate, reinterpret_cast<float*>(work), reinterpret_cast<cudaStream_t>(stream));

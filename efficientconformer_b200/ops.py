@@ -201,3 +201,57 @@ def linear_wgrad(dy_act, x_act, precision, dw_accum=None):
     work = torch.empty(lib().ec_op_wgrad_work_bytes(pr, M, N, K), dtype=torch.uint8, device=dy_act.device)
     check(lib().ec_op_wgrad(pr, ptr(dy_act), ptr(x_act), M, N, K, ptr(dw), 1 if dw_accum is not None else 0, ptr(work), stream_ptr()))
     return dw
+
+
+class DwConvTrain:
+    """Training-mode depthwise conv -> BatchNorm1d (batch statistics, running-stat update) -> Swish and its backward
+    (reference models/modules.py:515-517 under .train()).  `reduce_stats(stats, count)` may merge the [2, C] (mean, M2) forward
+    statistics / all-reduce the backward sums across ranks between the stages (SyncBatchNorm) and returns the global frame count."""
+
+    @staticmethod
+    def forward(x_act, w, b, gamma, beta, running_mean, running_var, stride, precision, eps=1e-5, momentum=0.1, reduce_stats=None):
+        pr = _p(precision)
+        L = lib()
+        B, T, Cc = x_act.shape
+        K = w.shape[-1]
+        To = (T - 1) // stride + 1
+        dev = x_act.device
+        w2, b2 = w.reshape(Cc, K).float().contiguous(), b.float().contiguous()
+        y = torch.empty(B, To, Cc, dtype=torch.float32, device=dev)
+        sums = torch.empty(2, Cc, dtype=torch.float32, device=dev)
+        work = torch.empty(L.ec_op_conv_train_work_bytes(Cc, K), dtype=torch.uint8, device=dev)
+        check(L.ec_op_dwconv_raw(pr, ptr(x_act.contiguous()), ptr(w2), ptr(b2), B, T, Cc, K, stride, ptr(y), ptr(sums), ptr(work), stream_ptr()))
+        count = float(B * To)
+        if reduce_stats is not None:
+            count = reduce_stats(sums, count)
+        mean = torch.empty(Cc, dtype=torch.float32, device=dev)
+        rstd = torch.empty(Cc, dtype=torch.float32, device=dev)
+        check(L.ec_op_bn_finalize(ptr(sums), Cc, count, eps, momentum, ptr(mean), ptr(rstd), ptr(running_mean), ptr(running_var), stream_ptr()))
+        h = torch.empty(B, To, Cc, dtype=act_dtype(pr), device=dev)
+        g, be = gamma.float().contiguous(), beta.float().contiguous()
+        check(L.ec_op_bn_swish_fwd(pr, ptr(y), B * To, Cc, ptr(mean), ptr(rstd), ptr(g), ptr(be), ptr(h), stream_ptr()))
+        return h, (x_act, w2, y, mean, rstd, g, be, count, stride, pr)
+
+    @staticmethod
+    def backward(dh, saved, reduce_stats=None):
+        """dh [B, T_out, C] fp32 -> (dx fp32 [B,T,C], dw [C,K], db [C], dgamma [C], dbeta [C])."""
+        x_act, w2, y, mean, rstd, g, be, count, stride, pr = saved
+        L = lib()
+        B, T, Cc = x_act.shape
+        K = w2.shape[1]
+        To = y.shape[1]
+        dev = y.device
+        dh = dh.float().contiguous()
+        work = torch.empty(L.ec_op_conv_train_work_bytes(Cc, K), dtype=torch.uint8, device=dev)
+        sums = torch.empty(2, Cc, dtype=torch.float32, device=dev)
+        check(L.ec_op_bn_swish_bwd_stats(ptr(y), ptr(dh), B * To, Cc, ptr(mean), ptr(rstd), ptr(g), ptr(be), ptr(sums), ptr(work), stream_ptr()))
+        dbeta, dgamma = sums[0].clone(), sums[1].clone()          # local sums are this rank's parameter gradients
+        if reduce_stats is not None:
+            reduce_stats(sums, count)
+        dy = torch.empty_like(y)
+        check(L.ec_op_bn_swish_bwd_apply(ptr(y), ptr(dh), B * To, Cc, ptr(mean), ptr(rstd), ptr(g), ptr(be), ptr(sums), count, ptr(dy), stream_ptr()))
+        dx = torch.empty(B, T, Cc, dtype=torch.float32, device=dev)
+        dw = torch.empty(Cc, K, dtype=torch.float32, device=dev)
+        db = torch.empty(Cc, dtype=torch.float32, device=dev)
+        check(L.ec_op_dwconv_bwd(pr, ptr(dy), ptr(x_act), ptr(w2), B, T, Cc, K, stride, ptr(dx), ptr(dw), ptr(db), ptr(work), stream_ptr()))
+        return dx, dw, db, dgamma, dbeta

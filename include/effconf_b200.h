@@ -146,6 +146,28 @@ int ec_ctc_loss(const float* logits, int batch, int t, int vocab, const long lon
  * Reductions use per-CTA partials added in a fixed order: bit-reproducible.
  * ec_op_wgrad         : dW [N, K] fp32 (+)= dY[M, N]^T . X[M, K], both activation type, on tcgen05 with MN-major operands (no
  *                       transposed copies), split over M with a fixed-order reduction of the partial tiles. */
+/* Training-mode depthwise stage of the convolution module (reference models/modules.py:515-517 under model.train()) and its
+ * backward, in stages so that the host can all-reduce the statistics across ranks between them (SyncBatchNorm):
+ *   ec_op_dwconv_raw        y [B, T_out, C] fp32 = depthwise conv (raw taps w [C, k], bias); stats [2][C] = mean, centred sum of squares
+ *                           M2 over the B*T_out frames (two-pass per CTA + Chan merge: robust when |mean| >> std)
+ *   ec_op_bn_finalize       mean / rstd (biased variance M2 / count) from the (merged) stats over `count` frames; running stats updated in place when given
+ *   ec_op_bn_swish_fwd      h = swish(BatchNorm(y))  (activation type)
+ *   ec_op_bn_swish_bwd_stats  sums [2][C] = dbeta, dgamma  (= sum dz, sum dz * xhat with dz = dh * swish'(z))
+ *   ec_op_bn_swish_bwd_apply  dy = gamma * rstd * (dz - sums[0] / count - xhat * sums[1] / count)
+ *   ec_op_dwconv_bwd        dx [B, T, C] (may be NULL), dw [C, k], db [C] from dy [B, T_out, C] and the saved conv input x */
+size_t ec_op_conv_train_work_bytes(int channels, int k);
+int ec_op_dwconv_raw(int precision, const void* x, const float* w, const float* bias, int batch, int t, int channels, int k, int stride,
+                     float* y, float* sums, void* work, void* stream);
+int ec_op_bn_finalize(const float* sums, int channels, float count, float eps, float momentum, float* mean, float* rstd,
+                      float* running_mean, float* running_var, void* stream);
+int ec_op_bn_swish_fwd(int precision, const float* y, size_t rows, int channels, const float* mean, const float* rstd, const float* gamma,
+                       const float* beta, void* h, void* stream);
+int ec_op_bn_swish_bwd_stats(const float* y, const float* dh, size_t rows, int channels, const float* mean, const float* rstd,
+                             const float* gamma, const float* beta, float* sums, void* work, void* stream);
+int ec_op_bn_swish_bwd_apply(const float* y, const float* dh, size_t rows, int channels, const float* mean, const float* rstd,
+                             const float* gamma, const float* beta, const float* sums, float count, float* dy, void* stream);
+int ec_op_dwconv_bwd(int precision, const float* dy, const void* x, const float* w, int batch, int t, int channels, int k, int stride,
+                     float* dx, float* dw, float* db, void* work, void* stream);
 size_t ec_op_wgrad_work_bytes(int precision, int M, int N, int K);
 int ec_op_wgrad(int precision, const void* dy, const void* x, int M, int N, int K, float* dw, int accumulate, void* work, void* stream);
 size_t ec_op_layernorm_bwd_work_bytes(int dim);

@@ -154,3 +154,48 @@ def test_linear_weight_gradient_tcgen05(ops, prec):
         dw2 = ops.linear_wgrad(dy, x, prec, dw_accum=acc)
         assert rel_l2(dw2, ref2) < 2e-5
         assert torch.equal(ops.linear_wgrad(dy, x, prec), dw)                # fixed-order reduction: bit reproducible
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+def test_dwconv_batchnorm_swish_training_forward_backward(ops, prec):
+    """Train-mode depthwise conv -> BatchNorm1d (batch statistics incl. padded frames, running-stat update) -> Swish, forward and
+    every gradient, against autograd over torch's own conv1d / batch_norm in fp64 on the same rounded input."""
+    import torch.nn.functional as F
+    rng = random.Random(51)
+    for trial in range(8):
+        C = rng.choice([8, 120, 168, 240, 360, 720])
+        k = rng.choice([15, 31])
+        stride = rng.choice([1, 2])
+        T = rng.choice([1, 2, 13, 64, 127, 500]) if trial else 500
+        B = rng.choice([1, 3, 32]) if T < 500 else 4
+        g = torch.Generator().manual_seed(1200 + trial)
+        x = ops.cast(torch.randn(B, T, C, generator=g).to(DEV), prec)
+        w = (torch.randn(C, 1, k, generator=g) / k ** 0.5)
+        b = 0.1 * torch.randn(C, generator=g)
+        gam, bet = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+        rm, rv = 0.1 * torch.randn(C, generator=g), 0.5 + torch.rand(C, generator=g)
+        To = (T - 1) // stride + 1
+        dh = torch.randn(B, To, C, generator=g)
+        # fp64 reference
+        xr = x.double().cpu().requires_grad_(True)
+        wr, br, gr, ber = [t.double().clone().requires_grad_(True) for t in (w, b, gam, bet)]
+        rm_r, rv_r = rm.double().clone(), rv.double().clone()
+        pad = (k - 1) // 2
+        conv = F.conv1d(F.pad(xr.transpose(1, 2), (pad, pad)), wr, br, stride=stride, groups=C)
+        if B * To > 1:
+            bn = F.batch_norm(conv, rm_r, rv_r, gr, ber, training=True, momentum=0.1, eps=1e-5)
+        else:
+            continue                                   # torch refuses a single value per channel in training mode
+        out = (bn * torch.sigmoid(bn)).transpose(1, 2)
+        out.backward(dh.double())
+        rm_d, rv_d = rm.clone().to(DEV), rv.clone().to(DEV)
+        h, saved = ops.DwConvTrain.forward(x, w.to(DEV), b.to(DEV), gam.to(DEV), bet.to(DEV), rm_d, rv_d, stride, prec)
+        tol_h = 5e-4 if prec == "tf32" else 5e-3
+        assert rel_l2(h.float(), out.detach()) < tol_h, (trial, B, T, C, k, stride)
+        assert rel_l2(rm_d, rm_r) < 1e-5 and rel_l2(rv_d, rv_r) < 1e-4
+        dx, dw, db, dgam, dbet = ops.DwConvTrain.backward(dh.to(DEV), saved)
+        case = (trial, B, T, C, k, stride)
+        assert rel_l2(dx, xr.grad) < 2e-4, case
+        assert rel_l2(dw, wr.grad[:, 0, :]) < 2e-4, case
+        assert rel_l2(dgam, gr.grad) < 2e-4 and rel_l2(dbet, ber.grad) < 2e-4, case
+        assert float(db.abs().max()) < 1e-3 * max(1.0, float(dbet.abs().max())), case     # exactly zero in exact arithmetic
