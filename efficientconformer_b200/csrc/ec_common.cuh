@@ -174,6 +174,11 @@ int launch_relpos_attention(int precision, const AttnArgs& a, cudaStream_t strea
 int launch_relpos_attention_bf16(const AttnArgs& a, cudaStream_t stream);
 int try_launch_relpos_attention_tma(const AttnArgs& a, cudaStream_t stream, bool* launched);
 
+// backward of the attention core (attention_bwd.cu): dqkv [B*T, 3D], dE [2Tp-G, D], du / dv [D], all fp32
+size_t attention_bwd_work_bytes(int B, int T, int D, int H, int G);
+int launch_relpos_attention_bwd(int precision, const AttnArgs& a, const float* dO, float* dqkv, float* dE, float* du, float* dv, void* work,
+                                cudaStream_t stream);
+
 struct DwConvArgs {
   const void* x;         // [B, T, C] activation type (GLU output)
   const float* w;        // [C, k] BatchNorm-folded depthwise taps

@@ -654,6 +654,15 @@ int ec_op_layernorm_bwd(const float* x, const float* dy, int rows, int dim, cons
   return launch_layernorm_bwd(x, dy, rows, dim, gamma, eps, dx, accumulate, dgamma, dbeta, reinterpret_cast<float*>(work),
                               reinterpret_cast<cudaStream_t>(stream));
 }
+size_t ec_op_relpos_attention_bwd_work_bytes(int batch, int t, int dim, int heads, int group) {
+  return attention_bwd_work_bytes(batch, t, dim, heads, group);
+}
+int ec_op_relpos_attention_bwd(int precision, const void* qkv, const void* E, const float* u, const float* v, const int32_t* x_len, int batch,
+                               int t, int dim, int heads, int group, const float* d_out, float* dqkv, float* dE, float* du, float* dv,
+                               void* work, void* stream) {
+  AttnArgs a{qkv, E, u, v, x_len, batch, t, dim, heads, group, nullptr, dim, 0};
+  return launch_relpos_attention_bwd(precision, a, d_out, dqkv, dE, du, dv, work, reinterpret_cast<cudaStream_t>(stream));
+}
 size_t ec_op_conv_train_work_bytes(int channels, int k) { return conv_train_work_bytes(channels, k); }
 int ec_op_dwconv_raw(int precision, const void* x, const float* w, const float* bias, int batch, int t, int channels, int k, int stride,
                      float* y, float* sums, void* work, void* stream) {

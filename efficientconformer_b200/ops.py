@@ -255,3 +255,22 @@ class DwConvTrain:
         db = torch.empty(Cc, dtype=torch.float32, device=dev)
         check(L.ec_op_dwconv_bwd(pr, ptr(dy), ptr(x_act), ptr(w2), B, T, Cc, K, stride, ptr(dx), ptr(dw), ptr(db), ptr(work), stream_ptr()))
         return dx, dw, db, dgamma, dbeta
+
+
+def relpos_attention_bwd(qkv_act, E_act, u, v, x_len, heads, group, d_out, precision):
+    """Gradients of relpos_attention: qkv_act [B,T,3D], E_act [2Tp-G, D] (activation type), d_out [B,T,D] fp32
+    -> (dqkv [B,T,3D], dE [2Tp-G, D], du [D], dv [D]) fp32."""
+    pr = _p(precision)
+    B, T, D3 = qkv_act.shape
+    D = D3 // 3
+    dev = qkv_act.device
+    xl = x_len.to(torch.int32).contiguous() if x_len is not None else None
+    dqkv = torch.empty(B, T, D3, dtype=torch.float32, device=dev)
+    dE = torch.empty(E_act.shape, dtype=torch.float32, device=dev)
+    du = torch.empty(D, dtype=torch.float32, device=dev)
+    dv = torch.empty(D, dtype=torch.float32, device=dev)
+    work = torch.empty(lib().ec_op_relpos_attention_bwd_work_bytes(B, T, D, heads, group), dtype=torch.uint8, device=dev)
+    check(lib().ec_op_relpos_attention_bwd(pr, ptr(qkv_act.contiguous()), ptr(E_act.contiguous()), ptr(u.float().contiguous()),
+                                           ptr(v.float().contiguous()), ptr(xl), B, T, D, heads, group, ptr(d_out.float().contiguous()),
+                                           ptr(dqkv), ptr(dE), ptr(du), ptr(dv), ptr(work), stream_ptr()))
+    return dqkv, dE, du, dv

@@ -146,6 +146,13 @@ int ec_ctc_loss(const float* logits, int batch, int t, int vocab, const long lon
  * Reductions use per-CTA partials added in a fixed order: bit-reproducible.
  * ec_op_wgrad         : dW [N, K] fp32 (+)= dY[M, N]^T . X[M, K], both activation type, on tcgen05 with MN-major operands (no
  *                       transposed copies), split over M with a fixed-order reduction of the partial tiles. */
+/* Backward of ec_op_relpos_attention (same operand conventions: qkv [B*T, 3D] and E [2Tp-G, D] in the activation type):
+ * d_out [B*T, D] fp32 = gradient of the attention output -> dqkv [B*T, 3D], dE [2Tp-G, D] (summed over the batch), du, dv [D], fp32.
+ * First implementation on the CUDA cores with P and dS materialised in `work`; no atomics, bit-reproducible. */
+size_t ec_op_relpos_attention_bwd_work_bytes(int batch, int t, int dim, int heads, int group);
+int ec_op_relpos_attention_bwd(int precision, const void* qkv, const void* E, const float* u, const float* v, const int32_t* x_len, int batch,
+                               int t, int dim, int heads, int group, const float* d_out, float* dqkv, float* dE, float* du, float* dv,
+                               void* work, void* stream);
 /* Training-mode depthwise stage of the convolution module (reference models/modules.py:515-517 under model.train()) and its
  * backward, in stages so that the host can all-reduce the statistics across ranks between them (SyncBatchNorm):
  *   ec_op_dwconv_raw        y [B, T_out, C] fp32 = depthwise conv (raw taps w [C, k], bias); stats [2][C] = mean, centred sum of squares

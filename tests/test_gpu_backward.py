@@ -199,3 +199,35 @@ def test_dwconv_batchnorm_swish_training_forward_backward(ops, prec):
         assert rel_l2(dw, wr.grad[:, 0, :]) < 2e-4, case
         assert rel_l2(dgam, gr.grad) < 2e-4 and rel_l2(dbet, ber.grad) < 2e-4, case
         assert float(db.abs().max()) < 1e-3 * max(1.0, float(dbet.abs().max())), case     # exactly zero in exact arithmetic
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+def test_relpos_attention_backward(ops, prec):
+    """Gradients of the (grouped) relative-position attention core w.r.t. q|k|v, the projected positional rows E and the u / v
+    biases, against autograd over the fp64 closed form on the same rounded operands: every shipped
+    head layout, padded groups (T % G != 0), ragged key masks."""
+    from test_gpu_ops import _attention_reference
+    rng = random.Random(61)
+    layouts = [(120, 4, 3), (168, 4, 1), (240, 4, 1), (360, 8, 3), (176, 4, 1), (144, 6, 1), (100, 4, 3), (512, 8, 1)]
+    for trial in range(10):
+        D, H, G = layouts[trial % len(layouts)]
+        T = rng.choice([1, 2, 5, 17, 64, 125, 250, 251, 500])
+        B = rng.choice([1, 2, 3])
+        if prec == "bf16" and D % 8:
+            continue
+        g = torch.Generator().manual_seed(1500 + trial)
+        qkv = ops.cast(torch.randn(B, T, 3 * D, generator=g).to(DEV), prec)
+        Tp = T + (-T) % G
+        E = ops.cast(torch.randn(2 * Tp - G, D, generator=g).to(DEV), prec)
+        u, v = 0.3 * torch.randn(D, generator=g), 0.3 * torch.randn(D, generator=g)
+        x_len = torch.tensor([rng.randint(1, T) for _ in range(B)])
+        x_len[0] = T
+        d_out = torch.randn(B, T, D, generator=g)
+        qr, Er = qkv.double().cpu().requires_grad_(True), E.double().cpu().requires_grad_(True)
+        ur, vr = u.double().requires_grad_(True), v.double().requires_grad_(True)
+        _attention_reference(qr, Er, ur, vr, x_len, H, G).backward(d_out.double())
+        dqkv, dE, du, dv = ops.relpos_attention_bwd(qkv, E, u.to(DEV), v.to(DEV), x_len.to(DEV), H, G, d_out.to(DEV), prec)
+        case = (prec, trial, B, T, D, H, G)
+        assert rel_l2(dqkv, qr.grad) < 2e-5, (case, rel_l2(dqkv, qr.grad))
+        assert rel_l2(dE, Er.grad) < 2e-5, (case, rel_l2(dE, Er.grad))
+        assert rel_l2(du, ur.grad) < 2e-5 and rel_l2(dv, vr.grad) < 2e-5, case
