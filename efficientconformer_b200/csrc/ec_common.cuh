@@ -249,6 +249,20 @@ int launch_bn_swish_bwd_apply(const float* y, const float* dh, size_t rows, int 
                               const float* beta, const float* sums, float count, float* dy, cudaStream_t st);
 int launch_dwconv_bwd(int precision, const float* dy, const void* x, const float* w, int B, int T, int C, int K, int stride, float* dx,
                       float* dw, float* db, float* work, cudaStream_t st);
+// training forward / backward helpers (train_misc.cu, subsample.cu)
+int launch_subsample_conv_raw(const SubsampleArgs& a, cudaStream_t stream);
+int launch_cast_scaled(int precision, const float* src, float scale, size_t n, void* dst, cudaStream_t st);
+int launch_swish_fwd(int precision, const void* z, size_t n, void* h, cudaStream_t st);
+int launch_glu_fwd(int precision, const void* zg, size_t rows, int C, void* out, cudaStream_t st);
+int launch_strided_rows(int precision, const float* x, int B, int T_in, int D, int stride, void* out, cudaStream_t st);
+int launch_strided_rows_bwd(const float* d, int B, int T_in, int D, int stride, float* dx, cudaStream_t st);
+size_t col_stats_work_bytes(int cols);
+int launch_col_stats(const float* y, size_t rows, int cols, float* stats, float* work, cudaStream_t st);
+int launch_group_stats_merge(const float* col_stats, int C, int group, size_t rows, float* ch_stats, cudaStream_t st);
+int launch_group_expand(const float* in, int n_vec, int C, int group, float* out, cudaStream_t st);
+int launch_group_sum(const float* in, int n_vec, int C, int group, float* out, cudaStream_t st);
+size_t subsample_wgrad_work_bytes(int C, int F);
+int launch_subsample_wgrad(const float* dy, const float* mel, int B, int F, int T, int C, float* dw, float* db, float* work, cudaStream_t st);
 int launch_greedy_collapse(const int* argmax, int B, int T, const int* logits_len, int* ids, int* counts, cudaStream_t stream);
 
 }  // namespace ec

@@ -654,6 +654,43 @@ int ec_op_layernorm_bwd(const float* x, const float* dy, int rows, int dim, cons
   return launch_layernorm_bwd(x, dy, rows, dim, gamma, eps, dx, accumulate, dgamma, dbeta, reinterpret_cast<float*>(work),
                               reinterpret_cast<cudaStream_t>(stream));
 }
+#define EC_ST(s) reinterpret_cast<cudaStream_t>(s)
+int ec_op_cast_scaled(int precision, const float* src, float scale, size_t n, void* dst, void* stream) {
+  return launch_cast_scaled(precision, src, scale, n, dst, EC_ST(stream));
+}
+int ec_op_swish_fwd(int precision, const void* z, size_t n, void* h, void* stream) { return launch_swish_fwd(precision, z, n, h, EC_ST(stream)); }
+int ec_op_glu_fwd(int precision, const void* zg, size_t rows, int channels, void* out, void* stream) {
+  return launch_glu_fwd(precision, zg, rows, channels, out, EC_ST(stream));
+}
+int ec_op_strided_rows(int precision, const float* x, int batch, int t, int dim, int stride, void* out, void* stream) {
+  return launch_strided_rows(precision, x, batch, t, dim, stride, out, EC_ST(stream));
+}
+int ec_op_strided_rows_bwd(const float* d, int batch, int t, int dim, int stride, float* dx, void* stream) {
+  return launch_strided_rows_bwd(d, batch, t, dim, stride, dx, EC_ST(stream));
+}
+int ec_op_subsample_conv_raw(const float* mel, const float* w, const float* b, int batch, int n_mels, int t, int channels, float* y, void* stream) {
+  SubsampleArgs a{mel, w, b, batch, n_mels, t, channels, y};
+  return launch_subsample_conv_raw(a, EC_ST(stream));
+}
+size_t ec_op_col_stats_work_bytes(int cols) { return col_stats_work_bytes(cols); }
+int ec_op_col_stats(const float* y, size_t rows, int cols, float* stats, void* work, void* stream) {
+  return launch_col_stats(y, rows, cols, stats, reinterpret_cast<float*>(work), EC_ST(stream));
+}
+int ec_op_group_stats_merge(const float* col_stats, int channels, int group, size_t rows, float* ch_stats, void* stream) {
+  return launch_group_stats_merge(col_stats, channels, group, rows, ch_stats, EC_ST(stream));
+}
+int ec_op_group_expand(const float* in, int n_vec, int channels, int group, float* out, void* stream) {
+  return launch_group_expand(in, n_vec, channels, group, out, EC_ST(stream));
+}
+int ec_op_group_sum(const float* in, int n_vec, int channels, int group, float* out, void* stream) {
+  return launch_group_sum(in, n_vec, channels, group, out, EC_ST(stream));
+}
+size_t ec_op_subsample_wgrad_work_bytes(int channels, int n_mels) { return subsample_wgrad_work_bytes(channels, n_mels); }
+int ec_op_subsample_wgrad(const float* dy, const float* mel, int batch, int n_mels, int t, int channels, float* dw, float* db, void* work,
+                          void* stream) {
+  return launch_subsample_wgrad(dy, mel, batch, n_mels, t, channels, dw, db, reinterpret_cast<float*>(work), EC_ST(stream));
+}
+#undef EC_ST
 size_t ec_op_relpos_attention_bwd_work_bytes(int batch, int t, int dim, int heads, int group) {
   return attention_bwd_work_bytes(batch, t, dim, heads, group);
 }

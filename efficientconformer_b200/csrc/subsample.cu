@@ -13,7 +13,9 @@ namespace ec {
 
 constexpr int kSubTT = 8;
 
-template <typename T>
+// kRaw (training forward): plain convolution output in fp32, no BatchNorm fold, no Swish, no operand rounding -- the batch
+// statistics are taken over this tensor before the normalisation kernel runs.
+template <typename T, bool kRaw = false>
 __global__ void __launch_bounds__(512) subsample_conv_kernel(const float* __restrict__ mel, const float* __restrict__ w, const float* __restrict__ bias,
                                                              int F, int T_in, int T_out, int C, T* __restrict__ y) {
   using Tr = ActTraits<T>;
@@ -61,9 +63,12 @@ __global__ void __launch_bounds__(512) subsample_conv_kernel(const float* __rest
     a1 = fmaf(w0.x, pv[6], a1); a1 = fmaf(w0.y, pv[7], a1); a1 = fmaf(w0.z, pv[8], a1);
     a1 = fmaf(w0.w, pv[9], a1); a1 = fmaf(w1.x, pv[10], a1); a1 = fmaf(w1.y, pv[11], a1);
     a1 = fmaf(w1.z, pv[12], a1); a1 = fmaf(w1.w, pv[13], a1); a1 = fmaf(w2.x, pv[14], a1);
-    const float o0 = swish_fn<T>(a0), o1 = swish_fn<T>(a1);
+    const float o0 = kRaw ? a0 : swish_fn<T>(a0), o1 = kRaw ? a1 : swish_fn<T>(a1);
     T* dst = yo + static_cast<size_t>(c) * F2;
-    if (pair_ok) {
+    if constexpr (kRaw) {
+      dst[0] = o0;
+      if (f + 1 < F2) dst[1] = o1;
+    } else if (pair_ok) {
       if constexpr (sizeof(T) == 2) *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(o0, o1);
       else *reinterpret_cast<float2*>(dst) = make_float2(Tr::to(o0), Tr::to(o1));
     } else {
@@ -251,6 +256,19 @@ int launch_linear_weight_permute(int precision, const float* w, int D, int C, in
   return EC_OK;
 }
 
+// training forward: raw fp32 convolution (raw taps / bias), y [B, T_out, C*F/2]
+int launch_subsample_conv_raw(const SubsampleArgs& a, cudaStream_t stream) {
+  EC_REQUIRE(a.F % 2 == 0, "n_mels must be even");
+  const int T_out = (a.T - 1) / 2 + 1;
+  dim3 grid(cdiv(T_out, kSubTT), a.B);
+  dim3 block((a.F / 2 + 1) / 2, kSubTT);
+  EC_REQUIRE(block.x * block.y <= 512, "n_mels too large for the subsampling kernel");
+  const size_t smem = sizeof(float) * ((a.F + 3) * (2 * kSubTT + 2) + a.C * 12);
+  EC_REQUIRE(smem <= 48 * 1024, "subsampling patch does not fit in shared memory");
+  return launch_pdl(subsample_conv_kernel<float, true>, grid, block, smem, stream, a.mel, a.w, a.b, a.F, a.T, T_out, a.C,
+                    reinterpret_cast<float*>(a.y));
+}
+
 int launch_subsample_conv(int precision, const SubsampleArgs& a, cudaStream_t stream) {
   EC_REQUIRE(a.F % 2 == 0, "n_mels must be even");
   const int T_out = (a.T - 1) / 2 + 1;
@@ -260,10 +278,10 @@ int launch_subsample_conv(int precision, const SubsampleArgs& a, cudaStream_t st
   const size_t smem = sizeof(float) * ((a.F + 3) * (2 * kSubTT + 2) + a.C * 12);
   EC_REQUIRE(smem <= 48 * 1024, "subsampling patch does not fit in shared memory");
   if (precision == EC_PREC_TF32)
-    return launch_pdl(subsample_conv_kernel<float>, grid, block, smem, stream, a.mel, a.w, a.b, a.F, a.T, T_out, a.C,
+    return launch_pdl(subsample_conv_kernel<float, false>, grid, block, smem, stream, a.mel, a.w, a.b, a.F, a.T, T_out, a.C,
                       reinterpret_cast<float*>(a.y));
   if (precision == EC_PREC_BF16)
-    return launch_pdl(subsample_conv_kernel<__nv_bfloat16>, grid, block, smem, stream, a.mel, a.w, a.b, a.F, a.T, T_out, a.C,
+    return launch_pdl(subsample_conv_kernel<__nv_bfloat16, false>, grid, block, smem, stream, a.mel, a.w, a.b, a.F, a.T, T_out, a.C,
                       reinterpret_cast<__nv_bfloat16*>(a.y));
   EC_FAIL("unknown precision");
 }

@@ -274,3 +274,102 @@ def relpos_attention_bwd(qkv_act, E_act, u, v, x_len, heads, group, d_out, preci
                                            ptr(v.float().contiguous()), ptr(xl), B, T, D, heads, group, ptr(d_out.float().contiguous()),
                                            ptr(dqkv), ptr(dE), ptr(du), ptr(dv), ptr(work), stream_ptr()))
     return dqkv, dE, du, dv
+
+
+def cast_scaled(x, precision, scale):
+    pr = _p(precision)
+    x = x.float().contiguous()
+    out = torch.empty(x.shape, dtype=act_dtype(pr), device=x.device)
+    check(lib().ec_op_cast_scaled(pr, ptr(x), float(scale), x.numel(), ptr(out), stream_ptr()))
+    return out
+
+
+def swish_fwd(z_act, precision):
+    out = torch.empty_like(z_act)
+    check(lib().ec_op_swish_fwd(_p(precision), ptr(z_act.contiguous()), z_act.numel(), ptr(out), stream_ptr()))
+    return out
+
+
+def glu_fwd(zg_act, precision):
+    rows, C2 = zg_act.shape
+    out = torch.empty(rows, C2 // 2, dtype=zg_act.dtype, device=zg_act.device)
+    check(lib().ec_op_glu_fwd(_p(precision), ptr(zg_act.contiguous()), rows, C2 // 2, ptr(out), stream_ptr()))
+    return out
+
+
+def strided_rows(x, stride, precision):
+    """x [B, T, D] fp32 -> activation-type copy of frames 0, s, 2s, ... : [B, (T-1)//s+1, D]."""
+    pr = _p(precision)
+    B, T, D = x.shape
+    out = torch.empty(B, (T - 1) // stride + 1, D, dtype=act_dtype(pr), device=x.device)
+    check(lib().ec_op_strided_rows(pr, ptr(x.float().contiguous()), B, T, D, stride, ptr(out), stream_ptr()))
+    return out
+
+
+def strided_rows_bwd(d, dx, stride):
+    """dx [B, T, D] fp32 += scatter of d [B, T_out, D] to frames 0, s, 2s, ..."""
+    B, T, D = dx.shape
+    check(lib().ec_op_strided_rows_bwd(ptr(d.float().contiguous()), B, T, D, stride, ptr(dx), stream_ptr()))
+    return dx
+
+
+class SubsampleTrain:
+    """Training-mode Conv2d(1 -> C, 3x3, s2) -> BatchNorm2d (batch statistics over (b, f, t), running-stat update) -> Swish
+    (reference models/modules.py:226-249 under .train()), output in the layout of the following Linear ([B*T/2, C*F/2]),
+    and its backward (weight / bias / BatchNorm gradients; the mel input needs no gradient)."""
+
+    @staticmethod
+    def forward(mel, w, b, gamma, beta, running_mean, running_var, precision, eps=1e-5, momentum=0.1, reduce_stats=None):
+        pr = _p(precision)
+        L = lib()
+        B, F, T = mel.shape
+        Cc = w.shape[0]
+        F2, To = F // 2, (T - 1) // 2 + 1
+        cols, rows = Cc * F2, B * To
+        dev = mel.device
+        mel = mel.float().contiguous()
+        y = torch.empty(rows, cols, dtype=torch.float32, device=dev)
+        check(L.ec_op_subsample_conv_raw(ptr(mel), ptr(w.reshape(Cc, 9).float().contiguous()), ptr(b.float().contiguous()), B, F, T, Cc,
+                                         ptr(y), stream_ptr()))
+        col_stats = torch.empty(2, cols, dtype=torch.float32, device=dev)
+        work = torch.empty(L.ec_op_col_stats_work_bytes(cols), dtype=torch.uint8, device=dev)
+        check(L.ec_op_col_stats(ptr(y), rows, cols, ptr(col_stats), ptr(work), stream_ptr()))
+        stats = torch.empty(2, Cc, dtype=torch.float32, device=dev)
+        check(L.ec_op_group_stats_merge(ptr(col_stats), Cc, F2, rows, ptr(stats), stream_ptr()))
+        count = float(rows * F2)
+        if reduce_stats is not None:
+            count = reduce_stats(stats, count)
+        ch = torch.empty(4, Cc, dtype=torch.float32, device=dev)           # mean, rstd, gamma, beta per channel
+        ch[2].copy_(gamma); ch[3].copy_(beta)
+        check(L.ec_op_bn_finalize(ptr(stats), Cc, count, eps, momentum, ptr(ch[0]), ptr(ch[1]), ptr(running_mean), ptr(running_var), stream_ptr()))
+        colv = torch.empty(4, cols, dtype=torch.float32, device=dev)        # the same, expanded to the c*F2 + f columns
+        check(L.ec_op_group_expand(ptr(ch), 4, Cc, F2, ptr(colv), stream_ptr()))
+        a = torch.empty(rows, cols, dtype=act_dtype(pr), device=dev)
+        check(L.ec_op_bn_swish_fwd(pr, ptr(y), rows, cols, ptr(colv[0]), ptr(colv[1]), ptr(colv[2]), ptr(colv[3]), ptr(a), stream_ptr()))
+        return a, (mel, y, colv, count, Cc, F2, (B, F, T))
+
+    @staticmethod
+    def backward(da, saved, reduce_stats=None):
+        """da [B*T/2, C*F/2] fp32 -> (dw [C,1,3,3], db [C], dgamma [C], dbeta [C])."""
+        mel, y, colv, count, Cc, F2, (B, F, T) = saved
+        L = lib()
+        rows, cols = y.shape
+        dev = y.device
+        da = da.float().contiguous()
+        work = torch.empty(max(L.ec_op_conv_train_work_bytes(cols, 1), L.ec_op_subsample_wgrad_work_bytes(Cc, F)), dtype=torch.uint8, device=dev)
+        sums_col = torch.empty(2, cols, dtype=torch.float32, device=dev)
+        check(L.ec_op_bn_swish_bwd_stats(ptr(y), ptr(da), rows, cols, ptr(colv[0]), ptr(colv[1]), ptr(colv[2]), ptr(colv[3]), ptr(sums_col),
+                                         ptr(work), stream_ptr()))
+        sums = torch.empty(2, Cc, dtype=torch.float32, device=dev)
+        check(L.ec_op_group_sum(ptr(sums_col), 2, Cc, F2, ptr(sums), stream_ptr()))
+        dbeta, dgamma = sums[0].clone(), sums[1].clone()
+        if reduce_stats is not None:
+            reduce_stats(sums, count)
+        check(L.ec_op_group_expand(ptr(sums), 2, Cc, F2, ptr(sums_col), stream_ptr()))
+        dy = torch.empty_like(y)
+        check(L.ec_op_bn_swish_bwd_apply(ptr(y), ptr(da), rows, cols, ptr(colv[0]), ptr(colv[1]), ptr(colv[2]), ptr(colv[3]), ptr(sums_col),
+                                         count, ptr(dy), stream_ptr()))
+        dw = torch.empty(Cc, 1, 3, 3, dtype=torch.float32, device=dev)
+        db = torch.empty(Cc, dtype=torch.float32, device=dev)
+        check(L.ec_op_subsample_wgrad(ptr(dy), ptr(mel), B, F, T, Cc, ptr(dw), ptr(db), ptr(work), stream_ptr()))
+        return dw, db, dgamma, dbeta

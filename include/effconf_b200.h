@@ -146,6 +146,24 @@ int ec_ctc_loss(const float* logits, int batch, int t, int vocab, const long lon
  * Reductions use per-CTA partials added in a fixed order: bit-reproducible.
  * ec_op_wgrad         : dW [N, K] fp32 (+)= dY[M, N]^T . X[M, K], both activation type, on tcgen05 with MN-major operands (no
  *                       transposed copies), split over M with a fixed-order reduction of the partial tiles. */
+/* Training-forward element kernels (the pre-activation tensors are kept for the backward, so Swish / GLU run on their own), the
+ * strided frame copy feeding conv_res and its scatter-add backward, and the BatchNorm2d pieces of the Conv2d subsampling layer:
+ * raw fp32 convolution, per-column (mean, M2) statistics, merge / expand / sum between the F/2 columns of a channel and the
+ * channel (feature index c*F/2 + f), weight / bias gradient of the 3x3 stride-2 convolution. */
+int ec_op_cast_scaled(int precision, const float* src, float scale, size_t n, void* dst, void* stream); /* dst = act_type(scale * src) */
+int ec_op_swish_fwd(int precision, const void* z, size_t n, void* h, void* stream);
+int ec_op_glu_fwd(int precision, const void* zg, size_t rows, int channels, void* out, void* stream);
+int ec_op_strided_rows(int precision, const float* x, int batch, int t, int dim, int stride, void* out, void* stream);
+int ec_op_strided_rows_bwd(const float* d, int batch, int t, int dim, int stride, float* dx, void* stream);
+int ec_op_subsample_conv_raw(const float* mel, const float* w, const float* b, int batch, int n_mels, int t, int channels, float* y, void* stream);
+size_t ec_op_col_stats_work_bytes(int cols);
+int ec_op_col_stats(const float* y, size_t rows, int cols, float* stats, void* work, void* stream);
+int ec_op_group_stats_merge(const float* col_stats, int channels, int group, size_t rows, float* ch_stats, void* stream);
+int ec_op_group_expand(const float* in, int n_vec, int channels, int group, float* out, void* stream);
+int ec_op_group_sum(const float* in, int n_vec, int channels, int group, float* out, void* stream);
+size_t ec_op_subsample_wgrad_work_bytes(int channels, int n_mels);
+int ec_op_subsample_wgrad(const float* dy, const float* mel, int batch, int n_mels, int t, int channels, float* dw, float* db, void* work,
+                          void* stream);
 /* Backward of ec_op_relpos_attention (same operand conventions: qkv [B*T, 3D] and E [2Tp-G, D] in the activation type):
  * d_out [B*T, D] fp32 = gradient of the attention output -> dqkv [B*T, 3D], dE [2Tp-G, D] (summed over the batch), du, dv [D], fp32.
  * First implementation on the CUDA cores with P and dS materialised in `work`; no atomics, bit-reproducible. */

@@ -231,3 +231,39 @@ def test_relpos_attention_backward(ops, prec):
         assert rel_l2(dqkv, qr.grad) < 2e-5, (case, rel_l2(dqkv, qr.grad))
         assert rel_l2(dE, Er.grad) < 2e-5, (case, rel_l2(dE, Er.grad))
         assert rel_l2(du, ur.grad) < 2e-5 and rel_l2(dv, vr.grad) < 2e-5, case
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+def test_subsampling_conv2d_batchnorm2d_training_forward_backward(ops, prec):
+    """Train-mode Conv2d(1->C,3x3,s2) -> BatchNorm2d (batch statistics) -> Swish in the layout of the following Linear, and the
+    weight / bias / BatchNorm gradients, against fp64 autograd over torch's conv2d / batch_norm."""
+    import torch.nn.functional as F
+    rng = random.Random(71)
+    for trial in range(5):
+        C = rng.choice([8, 120, 180])
+        T = rng.choice([2, 7, 64, 101, 500])
+        B = rng.choice([1, 2, 4])
+        Fm = 80
+        g = torch.Generator().manual_seed(1700 + trial)
+        mel = torch.randn(B, Fm, T, generator=g)
+        w = torch.randn(C, 1, 3, 3, generator=g) / 3
+        b = 0.1 * torch.randn(C, generator=g)
+        gam, bet = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+        rm, rv = 0.1 * torch.randn(C, generator=g), 0.5 + torch.rand(C, generator=g)
+        To = (T - 1) // 2 + 1
+        da = torch.randn(B * To, C * (Fm // 2), generator=g)
+        wr, br, gr, ber = [t.double().clone().requires_grad_(True) for t in (w, b, gam, bet)]
+        rm_r, rv_r = rm.double().clone(), rv.double().clone()
+        conv = F.conv2d(mel.double().unsqueeze(1), wr, br, stride=2, padding=1)             # (B, C, F/2, T/2)
+        bn = F.batch_norm(conv, rm_r, rv_r, gr, ber, training=True, momentum=0.1, eps=1e-5)
+        out = (bn * torch.sigmoid(bn)).reshape(B, C * (Fm // 2), To).transpose(1, 2).reshape(B * To, -1)
+        out.backward(da.double())
+        rm_d, rv_d = rm.clone().to(DEV), rv.clone().to(DEV)
+        a, saved = ops.SubsampleTrain.forward(mel.to(DEV), w.to(DEV), b.to(DEV), gam.to(DEV), bet.to(DEV), rm_d, rv_d, prec)
+        case = (prec, trial, B, T, C)
+        assert rel_l2(a.float(), out.detach()) < (5e-4 if prec == "tf32" else 5e-3), case
+        assert rel_l2(rm_d, rm_r) < 1e-5 and rel_l2(rv_d, rv_r) < 1e-4, case
+        dw, db, dgam, dbet = ops.SubsampleTrain.backward(da.to(DEV), saved)
+        assert rel_l2(dw, wr.grad) < 2e-4, (case, rel_l2(dw, wr.grad))
+        assert rel_l2(dgam, gr.grad) < 2e-4 and rel_l2(dbet, ber.grad) < 2e-4, case
+        assert float(db.abs().max()) < 1e-3 * max(1.0, float(dbet.abs().max())), case
