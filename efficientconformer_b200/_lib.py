@@ -121,6 +121,15 @@ _SIGNATURES = {
     "ec_ctc_loss_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ec_ctc_greedy": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ec_op_dropout_advance": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ec_op_dropout": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_uint,
+                                C.c_void_p]),
+    "ec_op_dropout_residual": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_size_t, C.c_void_p, C.c_float, C.c_void_p, C.c_uint,
+                                         C.c_void_p]),
+    "ec_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                               C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "ec_op_stats_merge_ranks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ec_op_pack_flat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ec_op_cast": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ec_op_layernorm": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),

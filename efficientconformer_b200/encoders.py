@@ -7,9 +7,11 @@ The modules below are PARAMETER HOLDERS only: nothing here runs PyTorch math on 
 device pointers to the sm_100a CUDA library (efficientconformer_b200/csrc, C ABI in include/effconf_b200.h); the audio
 front end (STFT -> mel -> log, reference models/modules.py:87-106) stays host PyTorch/torchaudio as in the reference.
 
-Scope of this round: inference semantics (eval-mode BatchNorm, no dropout / SpecAugment) -- what `Model.evaluate`,
-`gready_search_decoding` and `eval_time_encoder` use.  A training-mode forward raises (backward kernels are SURVEY.md
-section 8f row 1).  There is no fallback path: without the CUDA library or on a non-sm_100 device, forward raises.
+`.eval()`: the fused inference engine (ec_engine_forward, CUDA-graph replay) -- what `Model.evaluate`, `gready_search_decoding`
+and `eval_time_encoder` use.  `.train()`: the training operator schedule of efficientconformer_b200/training.py (batch-statistics
+BatchNorm, dropout, one autograd node whose backward is the CUDA backward schedule); SpecAugment
+stays the reference's host PyTorch and is applied by the caller.  There is no fallback path: without the CUDA library or on a
+non-sm_100 device, forward raises.
 """
 import ctypes as C
 
@@ -308,8 +310,7 @@ class ConformerEncoder(nn.Module):
         """The hot path from the mel spectrogram on: mel (B, n_mels, T) fp32 CUDA, mel_len (B,) int64 or None.
         Returns (x (B,T_out,D_last) fp32, x_len_out, logits or None)."""
         if self.training:
-            raise NotImplementedError("training-mode forward (batch-statistics BatchNorm, dropout, SpecAugment) and backward are "
-                                      "not implemented yet (SURVEY.md section 8f row 1); call .eval() -- there is no PyTorch fallback path")
+            return self._forward_mel_train(mel, mel_len, want_logits)
         if not mel.is_cuda:
             raise RuntimeError("effconf_b200 runs on CUDA sm_100 only (the reference's --cpu path is the oracle's job)")
         if want_logits and self._head is None:
@@ -340,6 +341,43 @@ class ConformerEncoder(nn.Module):
             lg = (plan.logits.clone() if clone else plan.logits) if want_logits else None
             out_len = plan.out_len.clone() if has_len else None
         return x, out_len, lg
+
+    def training_path(self):
+        """The train-mode operator schedule (efficientconformer_b200/training.py) bound to this encoder's parameters."""
+        from .training import TrainingPath
+        tp = self.__dict__.get("_training_path")
+        if tp is None or tp.head is not self._head:
+            tp = TrainingPath(self, self._head, stats_reducer=self.__dict__.get("_stats_reducer"))
+            object.__setattr__(self, "_training_path", tp)
+        return tp
+
+    def set_stats_reducer(self, reducer):
+        """SyncBatchNorm: `reducer(stats, count)` merges BatchNorm statistics across ranks (efficientconformer_b200/distributed.py)."""
+        object.__setattr__(self, "_stats_reducer", reducer)
+        object.__setattr__(self, "_training_path", None)
+
+    def _forward_mel_train(self, mel, mel_len, want_logits):
+        """`.train()` semantics (batch-statistics BatchNorm with running-stat updates, dropout) -- reference models/encoders.py:106-142
+        under model.train().  With grad enabled the whole path is ONE autograd node whose backward is the CUDA backward schedule."""
+        from .training import EncoderTrainFn
+        if not mel.is_cuda:
+            raise RuntimeError("effconf_b200 runs on CUDA sm_100 only (the reference's --cpu path is the oracle's job)")
+        if want_logits and self._head is None:
+            raise RuntimeError("no fc head attached")
+        path = self.training_path()
+        prec = self._select_precision()
+        mel = mel.float().contiguous()
+        if mel_len is not None:
+            mel_len = mel_len.to(mel.device)
+        with torch.cuda.device(mel.device):
+            _lib.check(_lib.lib().ec_device_check())
+            plist = [p for _, p in path.param_list()]
+            if torch.is_grad_enabled() and any(p.requires_grad for p in plist):
+                x, logits, out_len = EncoderTrainFn.apply(path, mel, mel_len, prec, want_logits, *plist)
+            else:
+                with torch.no_grad():
+                    x, logits, out_len, _ = path.forward(mel, mel_len, prec, want_logits)
+        return x, out_len, logits
 
     def forward(self, x, x_len=None):
         """reference signature: x (B, L_audio) float, x_len (B,) long or None -> (x, x_len, attentions)."""

@@ -205,8 +205,9 @@ def linear_wgrad(dy_act, x_act, precision, dw_accum=None):
 
 class DwConvTrain:
     """Training-mode depthwise conv -> BatchNorm1d (batch statistics, running-stat update) -> Swish and its backward
-    (reference models/modules.py:515-517 under .train()).  `reduce_stats(stats, count)` may merge the [2, C] (mean, M2) forward
-    statistics / all-reduce the backward sums across ranks between the stages (SyncBatchNorm) and returns the global frame count."""
+    (reference models/modules.py:515-517 under .train()).  `reduce_stats` (SyncBatchNorm, efficientconformer_b200/distributed.py) merges the
+    [2, C] (mean, M2) forward statistics across ranks between the stages -- `forward_stats(stats, count)` returns the global frame
+    count -- and all-reduces the backward sums -- `backward_sums(sums)`."""
 
     @staticmethod
     def forward(x_act, w, b, gamma, beta, running_mean, running_var, stride, precision, eps=1e-5, momentum=0.1, reduce_stats=None):
@@ -223,7 +224,7 @@ class DwConvTrain:
         check(L.ec_op_dwconv_raw(pr, ptr(x_act.contiguous()), ptr(w2), ptr(b2), B, T, Cc, K, stride, ptr(y), ptr(sums), ptr(work), stream_ptr()))
         count = float(B * To)
         if reduce_stats is not None:
-            count = reduce_stats(sums, count)
+            count = reduce_stats.forward_stats(sums, count)
         mean = torch.empty(Cc, dtype=torch.float32, device=dev)
         rstd = torch.empty(Cc, dtype=torch.float32, device=dev)
         check(L.ec_op_bn_finalize(ptr(sums), Cc, count, eps, momentum, ptr(mean), ptr(rstd), ptr(running_mean), ptr(running_var), stream_ptr()))
@@ -247,7 +248,7 @@ class DwConvTrain:
         check(L.ec_op_bn_swish_bwd_stats(ptr(y), ptr(dh), B * To, Cc, ptr(mean), ptr(rstd), ptr(g), ptr(be), ptr(sums), ptr(work), stream_ptr()))
         dbeta, dgamma = sums[0].clone(), sums[1].clone()          # local sums are this rank's parameter gradients
         if reduce_stats is not None:
-            reduce_stats(sums, count)
+            reduce_stats.backward_sums(sums)
         dy = torch.empty_like(y)
         check(L.ec_op_bn_swish_bwd_apply(ptr(y), ptr(dh), B * To, Cc, ptr(mean), ptr(rstd), ptr(g), ptr(be), ptr(sums), count, ptr(dy), stream_ptr()))
         dx = torch.empty(B, T, Cc, dtype=torch.float32, device=dev)
@@ -338,7 +339,7 @@ class SubsampleTrain:
         check(L.ec_op_group_stats_merge(ptr(col_stats), Cc, F2, rows, ptr(stats), stream_ptr()))
         count = float(rows * F2)
         if reduce_stats is not None:
-            count = reduce_stats(stats, count)
+            count = reduce_stats.forward_stats(stats, count)
         ch = torch.empty(4, Cc, dtype=torch.float32, device=dev)           # mean, rstd, gamma, beta per channel
         ch[2].copy_(gamma); ch[3].copy_(beta)
         check(L.ec_op_bn_finalize(ptr(stats), Cc, count, eps, momentum, ptr(ch[0]), ptr(ch[1]), ptr(running_mean), ptr(running_var), stream_ptr()))
@@ -364,7 +365,7 @@ class SubsampleTrain:
         check(L.ec_op_group_sum(ptr(sums_col), 2, Cc, F2, ptr(sums), stream_ptr()))
         dbeta, dgamma = sums[0].clone(), sums[1].clone()
         if reduce_stats is not None:
-            reduce_stats(sums, count)
+            reduce_stats.backward_sums(sums)
         check(L.ec_op_group_expand(ptr(sums), 2, Cc, F2, ptr(sums_col), stream_ptr()))
         dy = torch.empty_like(y)
         check(L.ec_op_bn_swish_bwd_apply(ptr(y), ptr(da), rows, cols, ptr(colv[0]), ptr(colv[1]), ptr(colv[2]), ptr(colv[3]), ptr(sums_col),
@@ -373,3 +374,100 @@ class SubsampleTrain:
         db = torch.empty(Cc, dtype=torch.float32, device=dev)
         check(L.ec_op_subsample_wgrad(ptr(dy), ptr(mel), B, F, T, Cc, ptr(dw), ptr(db), ptr(work), stream_ptr()))
         return dw, db, dgamma, dbeta
+
+
+# ---- pieces the assembled training step needs (efficientconformer_b200/training.py) -----------------------------------------
+def relpos_attention_act(qkv_act, E_act, u, v, x_len, heads, group, precision):
+    """relpos_attention on operands that are already in the activation type (what the QKV / pos GEMM epilogues emit)."""
+    pr = _p(precision)
+    B, T, D3 = qkv_act.shape
+    D = D3 // 3
+    out = torch.empty(B, T, D, dtype=act_dtype(pr), device=qkv_act.device)
+    xl = x_len.to(torch.int32).contiguous() if x_len is not None else None
+    check(lib().ec_op_relpos_attention(pr, ptr(qkv_act.contiguous()), ptr(E_act.contiguous()), ptr(u.float().contiguous()),
+                                       ptr(v.float().contiguous()), ptr(xl), B, T, D, heads, group, ptr(out), stream_ptr()))
+    return out
+
+
+def concat_qkv(mhsa):
+    """fp32 staging copy [3D, D] of Wq | Wk | Wv and [3D] of the biases (device-to-device memcpys, no kernel): one GEMM computes q|k|v
+    and one transposed copy serves the data gradient."""
+    D = mhsa.query_layer.weight.shape[0]
+    dev = mhsa.query_layer.weight.device
+    w = torch.empty(3 * D, D, dtype=torch.float32, device=dev)
+    b = torch.empty(3 * D, dtype=torch.float32, device=dev)
+    for j, layer in enumerate((mhsa.query_layer, mhsa.key_layer, mhsa.value_layer)):
+        w[j * D:(j + 1) * D].copy_(layer.weight.detach())
+        b[j * D:(j + 1) * D].copy_(layer.bias.detach())
+    return w, b
+
+
+def own_f32(x):
+    """A private contiguous fp32 copy the backward may accumulate into."""
+    return x.detach().float().clone(memory_format=torch.contiguous_format)
+
+
+def zeros_f32(rows, cols, device):
+    return torch.zeros(rows, cols, dtype=torch.float32, device=device)      # a memset node
+
+
+def dropout_counter(device, seed):
+    """Device {seed, step} pair of the counter-based dropout (ec_op_dropout*)."""
+    t = torch.zeros(2, dtype=torch.int64, device=device)
+    t[0] = int(seed) & 0x7FFFFFFFFFFFFFFF
+    return t
+
+
+def dropout_advance(counter):
+    check(lib().ec_op_dropout_advance(ptr(counter), stream_ptr()))
+
+
+def _dropout(x, drop, site, precision, src_f32, dst_f32, scale=1.0):
+    pr = _p(precision)
+    x = x.contiguous()
+    dt = torch.float32 if dst_f32 else act_dtype(pr)
+    out = torch.empty(x.shape, dtype=dt, device=x.device)
+    check(lib().ec_op_dropout(pr, ptr(x), 1 if src_f32 else 0, float(scale), x.numel(), ptr(out), 1 if dst_f32 else 0, drop.p,
+                              ptr(drop.counter), site, stream_ptr()))
+    return out
+
+
+def dropout_f32(x, drop, site):
+    """fp32 -> fp32 (residual stream / gradients); identity when p == 0."""
+    if drop.p == 0.0:
+        return x
+    return _dropout(x.float(), drop, site, PRECISIONS["tf32"], True, True)
+
+
+def dropout_act(x_act, drop, site, precision):
+    if drop.p == 0.0:
+        return x_act
+    return _dropout(x_act, drop, site, precision, False, False)
+
+
+def dropout_cast_scaled(x, precision, scale, drop, site):
+    """fp32 gradient -> activation type, scaled, with the forward mask of `site` re-applied."""
+    if drop.p == 0.0:
+        return cast_scaled(x, precision, scale) if scale != 1.0 else cast(x, precision)
+    return _dropout(x.float(), drop, site, precision, True, False, scale)
+
+
+def dropout_residual(y, drop, site, alpha, residual):
+    y, residual = y.float().contiguous(), residual.float().contiguous()
+    out = torch.empty_like(y)
+    check(lib().ec_op_dropout_residual(ptr(y), ptr(residual), float(alpha), y.numel(), ptr(out), drop.p, ptr(drop.counter), site, stream_ptr()))
+    return out
+
+
+def stats_merge_ranks(gathered, counts, out):
+    """gathered [W, 2, C] fp32, counts [W] fp32 (device) -> out [2, C] (in place)."""
+    W, _, Cc = gathered.shape
+    check(lib().ec_op_stats_merge_ranks(ptr(gathered.contiguous()), ptr(counts), W, Cc, ptr(out), stream_ptr()))
+    return out
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, state, beta1, beta2, eps, weight_decay, grad_scale=1.0, schedule=0, K=0.0, dim=1.0,
+              warmup=1.0):
+    """One torch.optim.Adam step over flat fp32 arenas (ec_adam_step); `state` int32[4] device = {lr bits, t, s, 0}."""
+    check(lib().ec_adam_step(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), params.numel(), ptr(state), beta1, beta2, eps,
+                             weight_decay, grad_scale, schedule, K, dim, warmup, stream_ptr()))

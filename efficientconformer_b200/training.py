@@ -1,0 +1,359 @@
+"""Training step of the hot path (BASELINE.json configs[1]): the train-mode forward of
+`ConformerEncoder` (+ the CTC `fc` head) and its hand-scheduled backward, launched operator by operator through the C ABI.
+
+What the reference executes for this (reference models/model.py:239-259 -> models/model_ctc.py:57-68 ->
+models/encoders.py:106-142 -> models/blocks.py:119-137 under `.train()`, then `loss.backward()`):
+  * BatchNorm with BATCH statistics over every (padded) frame, running statistics updated (momentum 0.1, unbiased variance);
+  * dropout (p = encoder_params["Pdrop"]) after `encoder.linear`, twice per feed-forward module, after the attention
+    output projection and at the end of the convolution module (reference models/encoders.py:119, modules.py:389,391,486,521);
+  * autograd through all of it.
+Here the forward keeps an explicit tape (pre-activation tensors, LayerNorm inputs, GEMM operands in the activation type) and
+`backward` walks it in reverse with the backward operators of include/effconf_b200.h; residual-branch gradients are accumulated
+in place by the kernels (`accumulate` flags), not by framework adds.  Nothing here computes with PyTorch: tensors are only
+allocated (caching allocator) and handed to the library as pointers.  There is no fallback: without the CUDA library every
+operator raises.
+
+Autograd integration (the drop-in side): `EncoderTrainFn` is ONE autograd node for the whole path, so the reference trainer's
+`loss.backward()`, `GradScaler`, DDP gradient hooks and `optimizer.step()` work unchanged on the parameters of the holder modules.
+"""
+import torch
+
+from . import ops as _ops_module
+from . import _lib
+from .encoders import relative_sinusoid_rows
+
+_ops = _ops_module       # test seam: tests/test_train_glue_cpu.py swaps in a torch-CPU operator table to check the tape logic
+
+
+class DropoutState:
+    """Counter-based dropout: mask bit of element i of site s at step n = hash(seed, n, s, i) < keep.  The step counter lives on the
+    device so that a captured CUDA graph draws fresh masks on every replay; the backward recomputes the same bits from (site, i)."""
+
+    def __init__(self, p: float, device, seed: int = 0):
+        self.p = float(p)
+        self.seed = int(seed)
+        self.site = 0
+        self.counter = None
+        if self.p > 0.0:
+            self.counter = _ops.dropout_counter(device, seed)
+
+    def begin_step(self):
+        self.site = 0
+        if self.counter is not None:
+            _ops.dropout_advance(self.counter)
+
+    def next_site(self):
+        self.site += 1
+        return self.site
+
+
+def _bump_batches_tracked(bn):
+    """nn.BatchNorm*.num_batches_tracked += 1 in training mode (a state_dict entry of the reference)."""
+    if getattr(bn, "num_batches_tracked", None) is not None:
+        bn.num_batches_tracked.add_(1)
+
+
+def _len_after_stride(length, stride):
+    """reference models/modules.py:243, encoders.py:140: x_len = (x_len - 1) // s + 1 (B integers of length bookkeeping)."""
+    return torch.div(length - 1, stride, rounding_mode="floor") + 1
+
+
+def _w2(t):
+    """Conv1d(k=1) weights [N, K, 1] are used as [N, K] matrices."""
+    return t.reshape(t.shape[0], -1)
+
+
+class TrainingPath:
+    """Owns nothing but references to the parameter holders of a ConformerEncoder (+ optional fc head)."""
+
+    def __init__(self, encoder, head=None, stats_reducer=None, dropout_seed: int = 0):
+        if len(encoder.subsampling_module.layers) != 1:
+            raise NotImplementedError("training mode supports the one-layer Conv2d front end (Efficient Conformer family)")
+        self.encoder = encoder
+        self.head = head
+        self.specs = encoder.specs
+        self.stats_reducer = stats_reducer      # distributed.SyncBatchNormReducer (forward_stats / backward_sums) or None
+        self.p_drop = float(encoder.params.get("Pdrop", 0.0))
+        self.dropout_seed = dropout_seed
+        self._drop = None
+        self._tables = {}
+
+    # ---- helpers ------------------------------------------------------------------------------------------------------
+    def param_list(self):
+        """(name, Parameter) in a fixed order: encoder parameters, then the head's."""
+        named = [("encoder." + k, p) for k, p in self.encoder.named_parameters()]
+        if self.head is not None:
+            named += [("fc." + k, p) for k, p in self.head.named_parameters()]
+        return named
+
+    def _table(self, t_pad, spec, pr, device):
+        key = (t_pad, spec.dim_model, spec.group_size, spec.max_pos, pr, str(device))
+        tab = self._tables.get(key)
+        if tab is None:
+            tab = _ops.cast(relative_sinusoid_rows(t_pad, spec.dim_model, spec.group_size, spec.max_pos).to(device), pr)
+            self._tables[key] = tab
+        return tab
+
+    def _dropout_state(self, device):
+        if self._drop is None:
+            self._drop = DropoutState(self.p_drop, device, self.dropout_seed)
+        return self._drop
+
+    # ---- forward ------------------------------------------------------------------------------------------------------
+    def forward(self, mel, mel_len, precision, want_logits=True):
+        """mel (B, n_mels, T) fp32, mel_len (B,) integer tensor on the same device or None.
+        Returns (x (B, T_out, D_last) fp32, logits (B, T_out, V) fp32 or None, out_len or None, tape)."""
+        o = _ops
+        pr = _lib.PRECISIONS[precision] if isinstance(precision, str) else precision
+        enc = self.encoder
+        drop = self._dropout_state(mel.device)
+        drop.begin_step()
+        B, F, T = mel.shape
+        tape = {"pr": pr, "B": B, "blocks": []}
+
+        sub = enc.subsampling_module.layers[0]
+        a, sub_saved = o.SubsampleTrain.forward(mel, sub[0].weight, sub[0].bias, sub[1].weight, sub[1].bias, sub[1].running_mean,
+                                                sub[1].running_var, pr, reduce_stats=self.stats_reducer)
+        _bump_batches_tracked(sub[1])
+        T0 = (T - 1) // 2 + 1
+        cur_len = None
+        if mel_len is not None:
+            cur_len = _len_after_stride(mel_len, 2)
+        w_lin = o.cast(enc.linear.weight, pr)
+        x = o.gemm(a, w_lin, enc.linear.bias, pr)[0]                           # (B*T0, D0) fp32
+        site0 = drop.next_site()
+        x = o.dropout_f32(x, drop, site0)
+        tape["front"] = (a, sub_saved, w_lin, site0)
+
+        Tc = T0
+        n_blocks = len(self.specs)
+        x_act_last = None
+        for i, (spec, blk) in enumerate(zip(self.specs, enc.blocks)):
+            last = i == n_blocks - 1
+            x, Tn, bt, x_act = self._block_forward(blk, spec, x, B, Tc, cur_len, pr, drop, want_act_out=last and want_logits and self.head is not None)
+            tape["blocks"].append(bt)
+            if spec.conv_stride > 1 and cur_len is not None:
+                cur_len = _len_after_stride(cur_len, spec.conv_stride)
+            Tc = Tn
+            x_act_last = x_act
+        D_last = self.specs[-1].dim_expand
+        logits = None
+        if want_logits:
+            if self.head is None:
+                raise RuntimeError("no fc head attached")
+            w_fc = o.cast(self.head.weight, pr)
+            logits = o.gemm(x_act_last, w_fc, self.head.bias, pr)[0].view(B, Tc, -1)
+            tape["head"] = (x_act_last, w_fc)
+        tape["T_out"] = Tc
+        return x.view(B, Tc, D_last), logits, cur_len, tape
+
+    def _ffn_forward(self, holder, x, pr, drop, alpha=0.5):
+        """reference models/modules.py:378-395 + the half-step residual of models/blocks.py:122,132."""
+        o = _ops
+        L = holder.layers
+        h0 = o.layernorm(x, L[0].weight, L[0].bias, pr, want_f32=False, want_act=True)[0]
+        w1 = o.cast(L[1].weight, pr)
+        z = o.gemm(h0, w1, L[1].bias, pr, want_f32=False, want_act=True)[1]
+        s = o.swish_fwd(z, pr)
+        s1 = drop.next_site()
+        s = o.dropout_act(s, drop, s1, pr)
+        w2 = o.cast(L[4].weight, pr)
+        s2 = drop.next_site()
+        if drop.p > 0.0:
+            y = o.gemm(s, w2, L[4].bias, pr)[0]
+            out = o.dropout_residual(y, drop, s2, alpha, x)
+        else:
+            out = o.gemm(s, w2, L[4].bias, pr, alpha=alpha, residual=x)[0]
+        return out, (x, h0, z, s, s1, s2, alpha)
+
+    def _ffn_backward(self, holder, saved, d_out, pr, grads, prefix):
+        """d_out: gradient w.r.t. the module output (fp32, modified in place); returns the gradient w.r.t. its input x."""
+        o = _ops
+        x, h0, z, s, s1, s2, alpha = saved
+        L = holder.layers
+        drop = self._drop
+        dy = o.dropout_cast_scaled(d_out, pr, alpha, drop, s2)                 # d(W2 output) in the activation type
+        grads[f"{prefix}.layers.4.weight"] = o.linear_wgrad(dy, s, pr)
+        grads[f"{prefix}.layers.4.bias"] = o.colsum(dy, pr)
+        ds = o.linear_dgrad(dy, L[4].weight, pr)
+        ds = o.dropout_f32(ds, drop, s1)
+        dz = o.swish_bwd(z, ds, pr)
+        grads[f"{prefix}.layers.1.weight"] = o.linear_wgrad(dz, h0, pr)
+        grads[f"{prefix}.layers.1.bias"] = o.colsum(dz, pr)
+        dh0 = o.linear_dgrad(dz, L[1].weight, pr)
+        dx, dg, db = o.layernorm_bwd(x, dh0, L[0].weight, dx_accum=d_out)
+        grads[f"{prefix}.layers.0.weight"], grads[f"{prefix}.layers.0.bias"] = dg, db
+        return dx
+
+    def _block_forward(self, blk, spec, x, B, T, cur_len, pr, drop, want_act_out):
+        o = _ops
+        D, De, H, G, st = spec.dim_model, spec.dim_expand, spec.num_heads, spec.group_size, spec.conv_stride
+        if st > 1 and not spec.has_conv_res_proj:
+            raise NotImplementedError("strided block without channel expansion (MaxPool residual) is not used by any shipped config")
+        x1, ffn1 = self._ffn_forward(blk.feed_forward_module1, x, pr, drop)
+        # ---- attention module (reference models/modules.py:472-488, attentions.py:549-718)
+        m = blk.multi_head_self_attention_module
+        a_in = o.layernorm(x1, m.norm.weight, m.norm.bias, pr, want_f32=False, want_act=True)[0]
+        wqkv32, bqkv = o.concat_qkv(m.mhsa)
+        qkv = o.gemm(a_in, o.cast(wqkv32, pr), bqkv, pr, want_f32=False, want_act=True)[1]
+        t_pad = T + (-T) % G
+        R = self._table(t_pad, spec, pr, x.device)
+        wpos = o.cast(m.mhsa.pos_layer.weight, pr)
+        E = o.gemm(R, wpos, m.mhsa.pos_layer.bias, pr, want_f32=False, want_act=True)[1]
+        att = o.relpos_attention_act(qkv.view(B, T, 3 * D), E, m.mhsa.u, m.mhsa.v, cur_len, H, G, pr)
+        wo = o.cast(m.mhsa.output_layer.weight, pr)
+        s_att = drop.next_site()
+        if drop.p > 0.0:
+            y = o.gemm(att.view(B * T, D), wo, m.mhsa.output_layer.bias, pr)[0]
+            x2 = o.dropout_residual(y, drop, s_att, 1.0, x1)
+        else:
+            x2 = o.gemm(att.view(B * T, D), wo, m.mhsa.output_layer.bias, pr, residual=x1)[0]
+        # ---- convolution module (reference models/modules.py:507-525) + block residual (blocks.py:98-114,129)
+        Lc = blk.convolution_module.layers
+        c_in = o.layernorm(x2, Lc[0].weight, Lc[0].bias, pr, want_f32=False, want_act=True)[0]
+        wpw1 = o.cast(_w2(Lc[2].weight), pr)
+        zg = o.gemm(c_in, wpw1, Lc[2].bias, pr, want_f32=False, want_act=True)[1]
+        gl = o.glu_fwd(zg, pr)
+        h, dw_saved = o.DwConvTrain.forward(gl.view(B, T, De), Lc[4].weight, Lc[4].bias, Lc[5].weight, Lc[5].bias, Lc[5].running_mean,
+                                            Lc[5].running_var, st, pr, reduce_stats=self.stats_reducer)
+        _bump_batches_tracked(Lc[5])
+        To = (T - 1) // st + 1
+        xs = None
+        if spec.has_conv_res_proj:
+            xs = o.strided_rows(x2.view(B, T, D), st, pr).view(B * To, D)
+            wres = o.cast(_w2(blk.conv_res[1].weight), pr)
+            res = o.gemm(xs, wres, blk.conv_res[1].bias, pr)[0]
+        else:
+            res = x2
+        wpw2 = o.cast(_w2(Lc[7].weight), pr)
+        s_conv = drop.next_site()
+        if drop.p > 0.0:
+            y = o.gemm(h.view(B * To, De), wpw2, Lc[7].bias, pr)[0]
+            x3 = o.dropout_residual(y, drop, s_conv, 1.0, res)
+        else:
+            x3 = o.gemm(h.view(B * To, De), wpw2, Lc[7].bias, pr, residual=res)[0]
+        x4, ffn2 = self._ffn_forward(blk.feed_forward_module2, x3, pr, drop)
+        x_act, x5 = o.layernorm(x4, blk.norm.weight, blk.norm.bias, pr, want_f32=True, want_act=want_act_out)
+        tape = dict(ffn1=ffn1, x1=x1, a_in=a_in, qkv=qkv, wqkv32=wqkv32, E=E, R=R, att=att, cur_len=cur_len, s_att=s_att, x2=x2, c_in=c_in, zg=zg,
+                    h=h, dw_saved=dw_saved, xs=xs, s_conv=s_conv, ffn2=ffn2, x4=x4, T=T, To=To)
+        return x5, To, tape, x_act
+
+    # ---- backward -----------------------------------------------------------------------------------------------------
+    def backward(self, tape, d_x=None, d_logits=None):
+        """d_x (B, T_out, D_last) and / or d_logits (B, T_out, V) fp32 -> {parameter name: gradient} (fp32, reference names with
+        `encoder.` / `fc.` prefixes)."""
+        o = _ops
+        pr, B = tape["pr"], tape["B"]
+        enc = self.encoder
+        grads = {}
+        dx = None
+        if d_x is not None:
+            dx = o.own_f32(d_x).view(-1, d_x.shape[-1])
+        if d_logits is not None:
+            x_act, w_fc = tape["head"]
+            dl = o.cast(d_logits.reshape(-1, d_logits.shape[-1]), pr)
+            grads["fc.weight"] = o.linear_wgrad(dl, x_act, pr)
+            grads["fc.bias"] = o.colsum(dl, pr)
+            dx = o.linear_dgrad(dl, self.head.weight, pr, residual=dx)
+        if dx is None:
+            raise RuntimeError("backward needs a gradient for the encoder output or the logits")
+        for i in reversed(range(len(self.specs))):
+            dx = self._block_backward(enc.blocks[i], self.specs[i], tape["blocks"][i], dx, B, pr, grads, f"encoder.blocks.{i}")
+        a, sub_saved, w_lin, site0 = tape["front"]
+        d_act = o.dropout_cast_scaled(dx, pr, 1.0, self._drop, site0)
+        grads["encoder.linear.weight"] = o.linear_wgrad(d_act, a, pr)
+        grads["encoder.linear.bias"] = o.colsum(d_act, pr)
+        da = o.linear_dgrad(d_act, enc.linear.weight, pr)
+        dw, db, dgam, dbet = o.SubsampleTrain.backward(da, sub_saved, reduce_stats=self.stats_reducer)
+        p = "encoder.subsampling_module.layers.0"
+        grads[f"{p}.0.weight"], grads[f"{p}.0.bias"], grads[f"{p}.1.weight"], grads[f"{p}.1.bias"] = dw, db, dgam, dbet
+        return grads
+
+    def _block_backward(self, blk, spec, t, d_out, B, pr, grads, p):
+        o = _ops
+        D, De, H, G, st = spec.dim_model, spec.dim_expand, spec.num_heads, spec.group_size, spec.conv_stride
+        T, To = t["T"], t["To"]
+        drop = self._drop
+        # block LayerNorm (reference models/blocks.py:135)
+        dx4, dg, db = o.layernorm_bwd(t["x4"], d_out, blk.norm.weight)
+        grads[f"{p}.norm.weight"], grads[f"{p}.norm.bias"] = dg, db
+        dx3 = self._ffn_backward(blk.feed_forward_module2, t["ffn2"], dx4, pr, grads, f"{p}.feed_forward_module2")
+        # convolution module + residual
+        Lc = blk.convolution_module.layers
+        c = f"{p}.convolution_module.layers"
+        dy = o.dropout_cast_scaled(dx3, pr, 1.0, drop, t["s_conv"])            # gradient of the pw2 output (after its dropout)
+        h2 = t["h"].view(B * To, De)
+        grads[f"{c}.7.weight"] = o.linear_wgrad(dy, h2, pr).view(De, De, 1)
+        grads[f"{c}.7.bias"] = o.colsum(dy, pr)
+        dh = o.linear_dgrad(dy, _w2(Lc[7].weight), pr)
+        dgl, dw_dw, db_dw, dgam, dbet = o.DwConvTrain.backward(dh.view(B, To, De), t["dw_saved"], reduce_stats=self.stats_reducer)
+        grads[f"{c}.4.weight"], grads[f"{c}.4.bias"] = dw_dw.view(De, 1, -1), db_dw
+        grads[f"{c}.5.weight"], grads[f"{c}.5.bias"] = dgam, dbet
+        dzg = o.glu_bwd(t["zg"], dgl.view(B * T, De), pr)
+        grads[f"{c}.2.weight"] = o.linear_wgrad(dzg, t["c_in"], pr).view(2 * De, D, 1)
+        grads[f"{c}.2.bias"] = o.colsum(dzg, pr)
+        dc_in = o.linear_dgrad(dzg, _w2(Lc[2].weight), pr)
+        if spec.has_conv_res_proj:
+            # the residual branch sees the un-dropped gradient dx3
+            dres = o.cast(dx3, pr) if drop.p > 0.0 else dy
+            grads[f"{p}.conv_res.1.weight"] = o.linear_wgrad(dres, t["xs"], pr).view(De, D, 1)
+            grads[f"{p}.conv_res.1.bias"] = o.colsum(dres, pr)
+            dxs = o.linear_dgrad(dres, _w2(blk.conv_res[1].weight), pr)
+            acc = o.zeros_f32(B * T, D, dx3.device)
+            o.strided_rows_bwd(dxs.view(B, To, D), acc.view(B, T, D), st)
+        else:
+            acc = dx3                                                         # identity residual: gradient passes straight through
+        dx2, dg, db = o.layernorm_bwd(t["x2"], dc_in, Lc[0].weight, dx_accum=acc)
+        grads[f"{c}.0.weight"], grads[f"{c}.0.bias"] = dg, db
+        # attention module
+        m = blk.multi_head_self_attention_module
+        a = f"{p}.multi_head_self_attention_module"
+        do = o.dropout_cast_scaled(dx2, pr, 1.0, drop, t["s_att"])
+        att2 = t["att"].view(B * T, D)
+        grads[f"{a}.mhsa.output_layer.weight"] = o.linear_wgrad(do, att2, pr)
+        grads[f"{a}.mhsa.output_layer.bias"] = o.colsum(do, pr)
+        datt = o.linear_dgrad(do, m.mhsa.output_layer.weight, pr)
+        dqkv, dE, du, dv = o.relpos_attention_bwd(t["qkv"].view(B, T, 3 * D), t["E"], m.mhsa.u, m.mhsa.v, t["cur_len"], H, G,
+                                                  datt.view(B, T, D), pr)
+        grads[f"{a}.mhsa.u"], grads[f"{a}.mhsa.v"] = du, dv
+        dE_act = o.cast(dE, pr)
+        grads[f"{a}.mhsa.pos_layer.weight"] = o.linear_wgrad(dE_act, t["R"], pr)
+        grads[f"{a}.mhsa.pos_layer.bias"] = o.colsum(dE_act, pr)
+        dqkv_act = o.cast(dqkv.view(B * T, 3 * D), pr)
+        dwqkv = o.linear_wgrad(dqkv_act, t["a_in"], pr)                        # [3D, D]: rows q | k | v
+        dbqkv = o.colsum(dqkv_act, pr)
+        for j, nm in enumerate(("query", "key", "value")):
+            grads[f"{a}.mhsa.{nm}_layer.weight"] = dwqkv[j * D:(j + 1) * D]
+            grads[f"{a}.mhsa.{nm}_layer.bias"] = dbqkv[j * D:(j + 1) * D]
+        da_in = o.linear_dgrad(dqkv_act, t["wqkv32"], pr)
+        dx1, dg, db = o.layernorm_bwd(t["x1"], da_in, m.norm.weight, dx_accum=dx2)
+        grads[f"{a}.norm.weight"], grads[f"{a}.norm.bias"] = dg, db
+        return self._ffn_backward(blk.feed_forward_module1, t["ffn1"], dx1, pr, grads, f"{p}.feed_forward_module1")
+
+
+class EncoderTrainFn(torch.autograd.Function):
+    """One autograd node for the whole train-mode hot path: forward runs the CUDA operator sequence and keeps the tape; backward
+    runs the hand-scheduled CUDA backward and hands each parameter its gradient."""
+
+    @staticmethod
+    def forward(ctx, path, mel, mel_len, precision, want_logits, *params):
+        x, logits, out_len, tape = path.forward(mel, mel_len, precision, want_logits)
+        ctx.set_materialize_grads(False)             # an unused output (x when only the logits feed the loss) arrives as None
+        ctx.path, ctx.tape = path, tape
+        ctx.names = [n for n, _ in path.param_list()]
+        if out_len is not None:
+            ctx.mark_non_differentiable(out_len)
+        if logits is None:
+            return x, None, out_len
+        return x, logits, out_len
+
+    @staticmethod
+    def backward(ctx, d_x, d_logits, _d_len=None):
+        tape, ctx.tape = ctx.tape, None
+        if tape is None:
+            raise RuntimeError("the training tape of this forward has already been consumed (retain_graph is not supported)")
+        grads = ctx.path.backward(tape, d_x, d_logits)
+        out = []
+        for i, n in enumerate(ctx.names):
+            out.append(grads[n] if ctx.needs_input_grad[5 + i] else None)
+        return (None, None, None, None, None, *out)

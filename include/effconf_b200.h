@@ -213,6 +213,32 @@ int ec_ctc_loss_grad(const float* logits, int batch, int t, int vocab, const lon
 int ec_ctc_greedy(const float* logits, int batch, int t, int vocab, const long long* logits_len, void* scratch,
                   int32_t* ids, int32_t* counts, void* stream);
 
+/* ---- closing the training step (reference models/model.py:239-259: forward, loss.backward(), optimizer.step(), scheduler.step()) ----
+ * Dropout (reference nn.Dropout sites models/encoders.py:119, modules.py:389,391,486,521): counter-based masks.  `counter` is a
+ * device array {seed, step}; the keep bit of element i at `site` is a pure function of (seed, step, site, i), so the backward
+ * re-applies the same mask without storing it and a replayed CUDA graph draws fresh masks after ec_op_dropout_advance.
+ *   ec_op_dropout          dst = scale * keep / (1 - p) * src;  src fp32 (src_f32) or activation type, dst likewise (dst_f32)
+ *   ec_op_dropout_residual out = residual + alpha * keep / (1 - p) * y   (fp32)
+ * Adam (torch.optim.Adam semantics as the reference uses them, models/model.py:88-93: L2 weight decay added to the gradient, bias
+ * correction) over ONE flat fp32 arena; `state` is a device int[4] = {lr as float bits, adam step t, schedule step s, 0}.  After the
+ * update t += 1 and, with schedule == 1, the Transformer schedule of models/schedules.py:99-123 advances on device:
+ * s += 1, lr = K * dim^-0.5 * min(s^-0.5, s * warmup^-1.5).  grad_scale multiplies the gradient first (1 / world size after a SUM all-reduce).
+ * ec_op_stats_merge_ranks: SyncBatchNorm forward statistics -- gathered [world][2][C] (mean, centred sum of squares) and counts [world]
+ * (frames per rank, device) merged into out [2][C]. */
+int ec_op_dropout_advance(unsigned long long* counter, void* stream);
+int ec_op_dropout(int precision, const void* src, int src_f32, float scale, size_t n, void* dst, int dst_f32, float p,
+                  const unsigned long long* counter, unsigned site, void* stream);
+int ec_op_dropout_residual(const float* y, const float* residual, float alpha, size_t n, float* out, float p,
+                           const unsigned long long* counter, unsigned site, void* stream);
+int ec_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, int* state, float beta1, float beta2,
+                 float eps, float weight_decay, float grad_scale, int schedule, float sched_k, float sched_dim, float sched_warmup,
+                 void* stream);
+int ec_op_stats_merge_ranks(const float* gathered, const float* counts, int world, int channels, float* out, void* stream);
+/* gather n separately allocated fp32 tensors (device pointer table srcs[n], element offsets[n] into the arena, sizes[n]) into one
+ * flat arena: the gradient bucket that the data-parallel all-reduce (reference DistributedDataParallel, models/model_ctc.py:73-75)
+ * and ec_adam_step operate on. */
+int ec_op_pack_flat(const float* const* srcs, const long long* offsets, const long long* sizes, int n, float* arena, void* stream);
+
 /* ---- single-operator entry points (unit parity tests; same kernels the engine launches) ---------------------------- */
 int ec_op_cast(int precision, const float* src, void* dst, size_t n, void* stream);
 int ec_op_layernorm(int precision, const float* x, int rows, int dim, const float* gamma, const float* beta, float eps,

@@ -50,3 +50,53 @@ def test_two_rank_gloo_aggregation():
     assert all(r[2] == 2.0 for r in res)
     assert all(r[3] == float(sum(range(10))) for r in res)
     assert res[0][4] == res[1][4] == [[0, 7], [0], [1, 7], [1, 1]]
+
+
+def _syncbn_worker(rank, world, port, q):
+    """SyncBatchNorm exchange logic over gloo (the merge kernel is swapped for its torch-CPU restatement: no GPU here)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_ops_shim
+    from efficientconformer_b200 import distributed as D
+    D._ops = cpu_ops_shim
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(5)
+        full = 3.0 + 2.0 * torch.randn(70, 6, generator=g)              # 70 frames x 6 channels, |mean| > std
+        out = {}
+        for uniform, bounds in ((True, [(0, 35), (35, 70)]), (False, [(0, 50), (50, 70)])):
+            lo, hi = bounds[rank]
+            x = full[lo:hi]
+            stats = torch.stack([x.mean(0), ((x - x.mean(0)) ** 2).sum(0)])
+            red = D.SyncBatchNormReducer(None, "cpu", uniform=uniform)
+            n = red.forward_stats(stats, float(hi - lo))
+            sums = torch.stack([x.sum(0), (x * x).sum(0)])
+            red.backward_sums(sums)
+            out[uniform] = (n, stats, sums)
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sync_batchnorm_exchange():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_syncbn_worker, args=(r, 2, 29741, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(5)
+    full = 3.0 + 2.0 * torch.randn(70, 6, generator=g)
+    ref = torch.stack([full.mean(0), ((full - full.mean(0)) ** 2).sum(0)])
+    ref_sums = torch.stack([full.sum(0), (full * full).sum(0)])
+    for rank in (0, 1):
+        for uniform in (True, False):
+            n, stats, sums = res[rank][uniform]
+            assert n == 70.0
+            assert torch.allclose(stats, ref, rtol=1e-5, atol=1e-5), (rank, uniform)
+            assert torch.allclose(sums, ref_sums, rtol=1e-5)

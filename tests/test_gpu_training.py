@@ -1,0 +1,227 @@
+"""The ASSEMBLED training step on the B200 (BASELINE.json configs[1]) through the drop-in API:
+`ModelCTC(...).train()`, `forward`, `LossCTC`, `loss.backward()` -- against the REAL reference's loss.backward() (golden gradients
+of tests/golden/ctc_small_train_b2_t500.pt, produced by tests/golden/make_golden_train.py from /root/reference), plus the pieces
+that close the step: counter-based dropout, flat-arena Adam with the Transformer schedule (against torch.optim.Adam, the
+optimiser the reference constructs, models/model.py:88-93) and the graph-captured CTCTrainStep."""
+import math
+import os
+
+import pytest
+import torch
+
+from efficientconformer_b200.config import CTC_SMALL_ENCODER_PARAMS as P, CTC_SMALL_VOCAB as V
+from efficientconformer_b200.synthetic import seeded_state_dict, synthetic_mel, synthetic_targets
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _model(precision, pdrop=0.0, params=None, vocab=V, seed=0):
+    from efficientconformer_b200.model_ctc import ModelCTC
+    p = dict(params or P); p["Pdrop"] = pdrop
+    model = ModelCTC(p, {"vocab_size": vocab}, precision=precision)
+    model.load_state_dict(seeded_state_dict(params or P, vocab, seed=seed, prefix_encoder="encoder."), strict=False)
+    return model.to(DEV).train()
+
+
+# gradient tolerances (relative L2 per tensor / relative error of the gradient norm).  The reference is fp32; TF32 operand rounding
+# gives 7e-4 on the logits and accumulates through the 15-block backward; bf16 operands (the reference's own mixed-precision
+# training uses fp16 autocast) are one decimal looser.
+# Measured on the B200: tf32 logits 1.2e-3 / loss 8e-6 / worst gradient-norm error 9e-4 / worst tensor 2.1e-3;
+# bf16 1.0e-2 / 1e-5 / 1.3e-2 / 1.6e-2.  The gates below are ~3x those.
+TOL = {"tf32": dict(logits=2e-3, loss=1e-3, norm=3e-3, full=6e-3, stats=2e-4),
+       "bf16": dict(logits=1.5e-2, loss=1e-3, norm=4e-2, full=5e-2, stats=2e-3)}
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+def test_training_step_matches_reference_backward(prec, golden_dir):
+    g = torch.load(os.path.join(golden_dir, "ctc_small_train_b2_t500.pt"))
+    tol = TOL[prec]
+    model = _model(prec)
+    mel = synthetic_mel(2, 500, seed=g["mel_seed"]).to(DEV)
+    logits, out_len, _ = model.forward_mel(mel, g["mel_len"].to(DEV))
+    assert logits.requires_grad and logits.shape == g["logits"].shape
+    assert out_len.tolist() == [63, 48]
+    e_logits = rel_l2(logits.detach(), g["logits"])
+    loss = model.criterion((None, g["targets"].to(DEV), None, g["target_len"].to(DEV)), (logits, out_len, None))
+    e_loss = abs(float(loss) - float(g["loss"])) / abs(float(g["loss"]))
+    loss.backward()
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    assert set(grads) == set(g["grad_norms"])
+    floor = 1e-4 * sorted(g["grad_norms"].values())[len(g["grad_norms"]) // 2]
+    errs = []
+    for k, ref_norm in g["grad_norms"].items():
+        assert grads[k] is not None and grads[k].shape == dict(model.named_parameters())[k].shape, k
+        gn = float(grads[k].double().norm())
+        assert math.isfinite(gn), k
+        if ref_norm < floor:
+            # exactly zero in exact arithmetic (biases in front of BatchNorm, key / positional biases): rounding noise only
+            assert gn < 50 * floor, (k, gn, floor)
+            continue
+        errs.append((abs(gn - ref_norm) / ref_norm, k))
+    errs.sort(reverse=True)
+    full = sorted(((rel_l2(grads[k], ref), k) for k, ref in g["grads"].items() if g["grad_norms"][k] >= floor), reverse=True)
+    sd = model.state_dict()
+    e_stats = max(rel_l2(sd[k], ref) for k, ref in g["running_stats"].items())
+    print(f"\n[{prec}] logits {e_logits:.3e} loss {e_loss:.3e} worst grad-norm err {errs[0][0]:.3e} ({errs[0][1]}) "
+          f"median {errs[len(errs) // 2][0]:.3e}; worst full-tensor rel-L2 {full[0][0]:.3e} ({full[0][1]}); running stats {e_stats:.3e}")
+    assert e_logits < tol["logits"], e_logits
+    assert e_loss < tol["loss"], e_loss
+    assert errs[0][0] < tol["norm"], errs[:10]
+    assert full[0][0] < tol["full"], full[:10]
+    assert e_stats < tol["stats"], e_stats
+    assert int(sd["encoder.blocks.3.convolution_module.layers.5.num_batches_tracked"]) == 1
+
+
+def test_dropout_kernels_statistics_and_mask_consistency():
+    from efficientconformer_b200 import ops
+    from efficientconformer_b200.training import DropoutState
+    drop = DropoutState(0.1, DEV, seed=7)
+    drop.begin_step()
+    n = 1 << 20
+    x = torch.ones(n, device=DEV)
+    y = ops.dropout_f32(x, drop, 3)
+    keep = (y != 0)
+    frac = float(keep.float().mean())
+    assert abs(frac - 0.9) < 3e-3, frac
+    assert torch.allclose(y[keep], torch.full_like(y[keep], 65536.0 / round(0.9 * 65536)))
+    assert abs(float(y.mean()) - 1.0) < 4e-3                                  # unbiased
+    # the same (step, site) draws the same mask in every variant: forward on activations, gradient re-masking, fused residual
+    for prec in ("tf32", "bf16"):
+        ya = ops.dropout_act(ops.cast(x, prec), drop, 3, prec)
+        assert torch.equal(ya != 0, keep)
+        yg = ops.dropout_cast_scaled(x, prec, 0.5, drop, 3)
+        assert torch.equal(yg != 0, keep)
+        assert torch.allclose(yg.float(), 0.5 * y, rtol=1e-2)
+    r = torch.randn(n, device=DEV)
+    yr = ops.dropout_residual(x, drop, 3, 0.5, r)
+    assert torch.allclose(yr, r + 0.5 * y, rtol=1e-6, atol=1e-6)
+    # other site / next step: independent masks
+    y2 = ops.dropout_f32(x, drop, 4)
+    agree = float(((y2 != 0) == keep).float().mean())
+    assert abs(agree - (0.81 + 0.01)) < 5e-3, agree
+    drop.begin_step()
+    y3 = ops.dropout_f32(x, drop, 3)
+    assert abs(float(((y3 != 0) == keep).float().mean()) - 0.82) < 5e-3
+    # odd length (tail group) and no low-order structure along rows of width 120
+    z = ops.dropout_f32(torch.ones(1001 * 120 + 3, device=DEV), drop, 9)
+    assert z.shape[0] == 1001 * 120 + 3 and abs(float((z != 0).float().mean()) - 0.9) < 5e-3
+    cols = (z[:1001 * 120].view(1001, 120) != 0).float().mean(0)
+    assert float(cols.min()) > 0.85 and float(cols.max()) < 0.95
+
+
+def test_flat_adam_matches_torch_adam_with_transformer_schedule():
+    """ec_adam_step over a flat arena == torch.optim.Adam(lr=0 at first, then the reference's Transformer schedule,
+    models/schedules.py:99-123) on the same gradients (fp64 CPU reference)."""
+    from efficientconformer_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    n = 100003
+    p0 = torch.randn(n, generator=g)
+    tp = dict(beta1=0.9, beta2=0.98, eps=1e-9, weight_decay=1e-6, K=2.0, schedule_dim=240.0, warmup_steps=5.0)
+    ref_p = p0.double().clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref_p], lr=0.0, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6)
+    pad = (n + 63) // 64 * 64
+    p = torch.zeros(pad, device=DEV); p[:n] = p0.to(DEV)
+    m, v = torch.zeros(pad, device=DEV), torch.zeros(pad, device=DEV)
+    state = torch.zeros(4, dtype=torch.int32, device=DEV)
+    world = 2.0
+    model_step = -1
+    for it in range(8):
+        grad = torch.randn(n, generator=g) * (1.0 + it)
+        ref_p.grad = grad.double().clone()
+        opt.step()
+        model_step += 1; s = model_step + 1                                   # scheduler.step() AFTER optimizer.step()
+        opt.param_groups[0]["lr"] = 2.0 * 240.0 ** -0.5 * min(s ** -0.5, s * 5.0 ** -1.5)
+        gd = torch.zeros(pad, device=DEV); gd[:n] = (grad * world).to(DEV)    # a SUM all-reduce over 2 ranks; mean folded into Adam
+        ops.adam_step(p[:n], gd[:n], m[:n], v[:n], state, tp["beta1"], tp["beta2"], tp["eps"], tp["weight_decay"], grad_scale=1.0 / world,
+                      schedule=1, K=tp["K"], dim=tp["schedule_dim"], warmup=tp["warmup_steps"])
+        lr_dev = float(state[0:1].view(torch.float32).item())
+        assert abs(lr_dev - opt.param_groups[0]["lr"]) < 1e-6 * opt.param_groups[0]["lr"], (it, lr_dev)
+        assert int(state[1]) == it + 1 and int(state[2]) == it + 1
+        if it == 0:
+            assert torch.equal(p[:n].cpu(), p0)                               # first optimizer step runs with lr = 0 (reference quirk)
+    assert rel_l2(p[:n], ref_p.detach()) < 1e-6
+    assert float((p[:n].cpu().double() - ref_p.detach()).abs().max()) < 1e-5
+
+
+def _small_params():
+    p = dict(P)
+    p.update(num_blocks=3, strided_blocks=[1], expand_blocks=[1], dim_model=[64, 96], att_group_size=[3, 1], subsampling_filters=[16],
+             num_heads=4, kernel_size=15)
+    return p
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+def test_train_step_graph_replay_equals_autograd_plus_torch_adam(prec):
+    """CTCTrainStep (flat arenas, packed gradient bucket, device-side Adam + schedule, CUDA-graph replay) against the drop-in route
+    the reference trainer takes: forward -> LossCTC -> loss.backward() -> torch.optim.Adam.step() -> scheduler.step()."""
+    from efficientconformer_b200.trainer import CTCTrainStep
+    sp = _small_params()
+    tp = dict(optimizer="Adam", beta1=0.9, beta2=0.98, eps=1e-9, weight_decay=1e-6, lr_schedule="Transformer", schedule_dim=96,
+              warmup_steps=3, K=2)
+    B, T = 3, 161
+    mels = [synthetic_mel(B, T, seed=40 + i).to(DEV) for i in range(4)]
+    mel_len = torch.tensor([161, 120, 77], device=DEV)
+    out_len = ((((mel_len - 1) // 2 + 1) - 1) // 2 + 1)
+    y, yl = synthetic_targets(out_len.cpu(), 32, seed=4)
+    y, yl = y.to(DEV), yl.to(DEV)
+    # route A: autograd node + torch optimiser
+    a = _model(prec, 0.0, sp, vocab=32)
+    opt = torch.optim.Adam(a.parameters(), lr=0.0, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6)
+    losses_a, model_step = [], -1
+    for mel in mels:
+        logits, ol, _ = a.forward_mel(mel, mel_len)
+        loss = a.criterion((None, y, None, yl), (logits, ol, None))
+        loss.backward()
+        opt.step(); opt.zero_grad()
+        model_step += 1; s = model_step + 1
+        opt.param_groups[0]["lr"] = 2 * 96 ** -0.5 * min(s ** -0.5, s * 3 ** -1.5)
+        losses_a.append(float(loss))
+    # route B: native step, graph replay; route C: native step, eager
+    results = {}
+    for graph in (True, False):
+        b = _model(prec, 0.0, sp, vocab=32)
+        step = CTCTrainStep(b, tp, precision=prec, use_cuda_graph=graph)
+        losses_b = [float(step.step(mel, mel_len, y, yl)) for mel in mels]
+        assert step.steps_done() == len(mels)
+        results[graph] = (losses_b, {k: v.detach().clone() for k, v in b.state_dict().items()})
+    assert results[True][0] == results[False][0]                              # replay == eager, bit for bit
+    for k, v in results[True][1].items():
+        assert torch.equal(v, results[False][1][k]), k
+    sd_a = a.state_dict()
+    tol = 2e-3 if prec == "tf32" else 2e-2
+    for la, lb in zip(losses_a, results[True][0]):
+        assert abs(la - lb) < 1e-3 * abs(la), (losses_a, results[True][0])
+    assert losses_a[-1] != losses_a[0]
+    # parameters whose gradient is zero in exact arithmetic (conv biases in front of BatchNorm; key / positional biases under the
+    # softmax's shift invariance) receive pure rounding noise, which Adam normalises to +-lr steps: they are not comparable
+    noise = ("convolution_module.layers.4.bias", "subsampling_module.layers.0.0.bias", "key_layer.bias", "pos_layer.bias")
+    worst = max((rel_l2(results[True][1][k], sd_a[k]), k) for k in sd_a if sd_a[k].is_floating_point() and not k.endswith(noise))
+    print(f"\n[{prec}] losses {results[True][0]} | autograd+torch.optim {losses_a} | worst state rel-L2 {worst}")
+    assert worst[0] < tol, worst
+    for k in sd_a:
+        if k.endswith("num_batches_tracked"):
+            assert int(sd_a[k]) == int(results[True][1][k]) == len(mels), k
+
+
+def test_training_with_dropout_is_reproducible_and_finite():
+    from efficientconformer_b200.trainer import CTCTrainStep
+    sp = _small_params()
+    tp = dict(optimizer="Adam", beta1=0.9, beta2=0.98, eps=1e-9, weight_decay=1e-6, lr_schedule="Transformer", schedule_dim=96,
+              warmup_steps=3, K=2)
+    mel = synthetic_mel(4, 200, seed=9).to(DEV)
+    y, yl = synthetic_targets(torch.full((4,), 50), 32, seed=4)
+    runs = []
+    for seed in (1, 1, 2):
+        m = _model("bf16", 0.1, sp, vocab=32)
+        step = CTCTrainStep(m, tp, precision="bf16", use_cuda_graph=True, dropout_seed=seed)
+        runs.append([float(step.step(mel, None, y.to(DEV), yl.to(DEV))) for _ in range(4)])
+    assert all(math.isfinite(v) for r in runs for v in r)
+    assert runs[0] == runs[1]                                                 # same seed: same masks, forward and backward
+    assert runs[0] != runs[2]
+    assert len(set(runs[0])) == 4                                             # fresh masks every replay + parameters moving

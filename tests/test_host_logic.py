@@ -77,11 +77,15 @@ def test_relative_table_matches_oracle():
         assert torch.equal(relative_sinusoid_rows(tp, d, g, ml), oracle_rows(tp, d, g, ml))
 
 
-def test_product_fails_loudly_without_gpu_or_in_training_mode():
+def test_product_fails_loudly_without_gpu():
     from efficientconformer_b200 import ConformerEncoder
+    from efficientconformer_b200 import ops
     enc = ConformerEncoder(P)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):                     # neither mode has a CPU path
         enc.train().forward_mel(torch.zeros(1, 80, 16))
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):                    # the operators themselves reject host memory / a missing device
+            ops.cast(torch.zeros(4), "bf16")
     with pytest.raises(RuntimeError):
         enc.eval().forward_mel(torch.zeros(1, 80, 16))
     with pytest.raises(NotImplementedError):

@@ -1,0 +1,90 @@
+"""CPU check of the training step's TAPE LOGIC (efficientconformer_b200/training.py): the same forward / backward schedule the GPU
+runs, with the operator table swapped for exact torch-CPU restatements (tests/cpu_ops_shim.py), must reproduce the REAL reference's
+loss.backward() -- the golden gradients of tests/golden/ctc_small_train_b2_t500.pt (every parameter's gradient norm, full tensors
+for a subset, updated BatchNorm running statistics).  The CUDA operators themselves are held to autograd one by one in
+tests/test_gpu_backward.py, and the assembled step on the GPU in tests/test_gpu_training.py."""
+import os
+
+import pytest
+import torch
+
+from efficientconformer_b200.config import CTC_SMALL_ENCODER_PARAMS as P, CTC_SMALL_VOCAB as V
+from efficientconformer_b200.synthetic import seeded_state_dict, synthetic_mel
+from oracle import conformer_oracle as O
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.fixture()
+def cpu_ops(monkeypatch):
+    import cpu_ops_shim
+    from efficientconformer_b200 import training
+    monkeypatch.setattr(training, "_ops", cpu_ops_shim)
+    return training
+
+
+def test_training_tape_reproduces_reference_gradients(cpu_ops, golden_dir):
+    training = cpu_ops
+    from efficientconformer_b200.model_ctc import ModelCTC
+    g = torch.load(os.path.join(golden_dir, "ctc_small_train_b2_t500.pt"))
+    params = dict(P); params["Pdrop"] = 0.0
+    model = ModelCTC(params, {"vocab_size": V}, precision="tf32")
+    sd = seeded_state_dict(P, V, seed=0, prefix_encoder="encoder.")
+    model.load_state_dict(sd, strict=False)
+    model.train()
+    path = training.TrainingPath(model.encoder, model.fc)
+    mel = synthetic_mel(2, 500, seed=g["mel_seed"])
+    with torch.no_grad():
+        x, logits, out_len, tape = path.forward(mel, g["mel_len"], "tf32", want_logits=True)
+    assert rel_l2(logits, g["logits"]) < 2e-5
+    lg = logits.detach().double().requires_grad_(True)
+    loss, _ = O.ctc_loss(lg, out_len, g["targets"], g["target_len"])
+    assert abs(float(loss) - float(g["loss"])) / abs(float(g["loss"])) < 1e-5
+    loss.backward()
+    with torch.no_grad():
+        grads = path.backward(tape, None, lg.grad)
+    names = [n for n, _ in path.param_list()]
+    assert set(names) == set(g["grad_norms"]) and set(grads) == set(names)
+    shapes = dict(path.param_list())
+    floor = 1e-4 * sorted(g["grad_norms"].values())[len(g["grad_norms"]) // 2]
+    worst = 0.0
+    for k, ref_norm in g["grad_norms"].items():
+        assert tuple(grads[k].shape) == tuple(shapes[k].shape), k
+        gn = float(grads[k].double().norm())
+        if ref_norm < floor:
+            assert gn < floor, k
+            continue
+        worst = max(worst, abs(gn - ref_norm) / ref_norm)
+    assert worst < 2e-3, worst
+    for k, ref in g["grads"].items():
+        if g["grad_norms"][k] >= floor:
+            assert rel_l2(grads[k], ref) < 2e-3, k
+    new_sd = model.state_dict()
+    for k, ref in g["running_stats"].items():
+        assert rel_l2(new_sd[k], ref) < 1e-5, k
+    assert int(new_sd["encoder.subsampling_module.layers.0.1.num_batches_tracked"]) == 1
+
+
+def test_autograd_node_fills_parameter_grads(cpu_ops):
+    """EncoderTrainFn: loss.backward() through the single autograd node assigns .grad on every parameter (and only where
+    requires_grad), for the encoder-only output as well (Transducer-style callers)."""
+    training = cpu_ops
+    from efficientconformer_b200.encoders import ConformerEncoder
+    params = dict(P); params.update(Pdrop=0.0, num_blocks=2, strided_blocks=[1], expand_blocks=[1], dim_model=[24, 32], att_group_size=[3, 1],
+                                    subsampling_filters=[8], num_heads=4, kernel_size=7)
+    enc = ConformerEncoder(params).train()
+    path = training.TrainingPath(enc, None)
+    enc.blocks[0].feed_forward_module1.layers[1].weight.requires_grad_(False)
+    mel = synthetic_mel(2, 37, seed=3)
+    plist = [p for _, p in path.param_list()]
+    x, logits, out_len = training.EncoderTrainFn.apply(path, mel, torch.tensor([37, 20]), "tf32", False, *plist)
+    assert logits is None and x.shape == (2, 10, 32) and out_len.tolist() == [10, 5]
+    (x.double() ** 2).sum().backward()
+    for n, p in path.param_list():
+        if n == "encoder.blocks.0.feed_forward_module1.layers.1.weight":
+            assert p.grad is None
+        else:
+            assert p.grad is not None and p.grad.shape == p.shape and bool(torch.isfinite(p.grad).all()), n
