@@ -90,7 +90,7 @@ _SIGNATURES = {
     "ec_op_group_stats_merge": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]),
     "ec_op_group_expand": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ec_op_group_sum": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
-    "ec_op_subsample_wgrad_work_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "ec_op_subsample_wgrad_work_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ec_op_subsample_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p]),
     "ec_op_relpos_attention_bwd_work_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -12,6 +12,7 @@
 // on chip, flash style) is the planned successor.
 #include "ec_common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace ec {
 
@@ -335,13 +336,20 @@ static void bwd_layout(int B, int T, int D, int H, int G, size_t* off, size_t* t
 }
 size_t attention_bwd_work_bytes(int B, int T, int D, int H, int G) {
   size_t off[9], total; bwd_layout(B, T, D, H, G, off, &total);
-  return total;
+  return std::max(total, attention_bwd_tc_work_bytes(B, T, D, H, G));
+}
+static bool tc_path_enabled() {
+  static const bool on = [] { const char* e = getenv("EFFCONF_ATTN_BWD_TC"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 int launch_relpos_attention_bwd(int precision, const AttnArgs& a, const float* dO, float* dqkv, float* dE, float* du, float* dv, void* work,
                                 cudaStream_t stream) {
   EC_REQUIRE(a.G >= 1 && a.G % 2 == 1 && (a.G * a.D) % a.H == 0, "attention backward: bad head layout");
   EC_REQUIRE(dO && dqkv && dE && du && dv && work, "attention backward: null argument");
+  // bf16 operand mode: batched tensor-core GEMMs (attention_bwd_tc.cu); the CUDA-core kernels below are the TF32 parity path
+  if (precision == EC_PREC_BF16 && tc_path_enabled() && (a.T + a.G - 1) / a.G <= 1024)
+    return launch_relpos_attention_bwd_tc(a, dO, dqkv, dE, du, dv, work, stream);
   BwdDev p{};
   p.qkv = a.qkv; p.E = a.E; p.u = a.u; p.v = a.v; p.x_len = a.x_len; p.dO = dO;
   p.B = a.B; p.T = a.T; p.D = a.D; p.H = a.H; p.G = a.G;

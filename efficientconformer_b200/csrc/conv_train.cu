@@ -18,7 +18,7 @@
 namespace ec {
 
 namespace {
-constexpr int kCtas = 296;
+constexpr int kCtas = 1184;   // 8 per SM: these kernels are latency bound on one dependent load chain per thread
 constexpr int kMaxTaps = 31;
 
 // rows [r0, r1) of this CTA for a row-strided split of `rows` over gridDim.x CTAs (contiguous ranges: coalesced, deterministic)
@@ -63,33 +63,64 @@ __global__ void __launch_bounds__(128) dwconv_raw_kernel(const T* __restrict__ x
   partial[(static_cast<size_t>(blockIdx.x) * 2 + 1) * C + c] = s2;
 }
 
-// (mean, M2) of the CTA row ranges merged in CTA order with Chan's update, in double: stats[0][c] = mean, stats[1][c] = M2
-__global__ void bn_stats_merge_kernel(const float* __restrict__ partial, int n_partial, size_t rows, int C, float* __restrict__ stats) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// (mean, M2) of the CTA row ranges merged with Chan's update, in double: stats[0][c] = mean, stats[1][c] = M2.
+// Block = 32 channels x 8 lanes: lane ty merges the contiguous chunk ty of the partials in CTA order, then the 8 chunk results are
+// merged in lane order (fixed order: bit-reproducible; 8x shorter chain of dependent fp64 divisions than one thread per channel).
+__global__ void __launch_bounds__(256) bn_stats_merge_kernel(const float* __restrict__ partial, int n_partial, size_t rows, int C,
+                                                             float* __restrict__ stats) {
+  __shared__ double sn[8][33], smean[8][33], sm2[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   const size_t per = (rows + n_partial - 1) / n_partial;
+  const int chunk = (n_partial + 7) / 8, p0 = ty * chunk, p1 = min(n_partial, p0 + chunk);
   double n = 0.0, mean = 0.0, m2 = 0.0;
-  for (int p = 0; p < n_partial; ++p) {
-    const size_t r0 = min(rows, per * p), r1 = min(rows, r0 + per);
-    const double nb = static_cast<double>(r1 - r0);
-    if (nb == 0.0) continue;
-    const double mb = partial[(static_cast<size_t>(p) * 2) * C + c], qb = partial[(static_cast<size_t>(p) * 2 + 1) * C + c];
-    const double tot = n + nb, dl = mb - mean;
-    mean += dl * nb / tot;
-    m2 += qb + dl * dl * n * nb / tot;
-    n = tot;
+  if (c < C) {
+    for (int p = p0; p < p1; ++p) {
+      const size_t r0 = min(rows, per * p), r1 = min(rows, r0 + per);
+      const double nb = static_cast<double>(r1 - r0);
+      if (nb == 0.0) continue;
+      const double mb = partial[(static_cast<size_t>(p) * 2) * C + c], qb = partial[(static_cast<size_t>(p) * 2 + 1) * C + c];
+      const double tot = n + nb, dl = mb - mean;
+      mean += dl * nb / tot;
+      m2 += qb + dl * dl * n * nb / tot;
+      n = tot;
+    }
   }
-  stats[c] = static_cast<float>(mean);
-  stats[C + c] = static_cast<float>(m2);
+  sn[ty][tx] = n; smean[ty][tx] = mean; sm2[ty][tx] = m2;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    n = 0.0; mean = 0.0; m2 = 0.0;
+    for (int q = 0; q < 8; ++q) {
+      const double nb = sn[q][tx];
+      if (nb == 0.0) continue;
+      const double tot = n + nb, dl = smean[q][tx] - mean;
+      mean += dl * nb / tot;
+      m2 += sm2[q][tx] + dl * dl * n * nb / tot;
+      n = tot;
+    }
+    stats[c] = static_cast<float>(mean);
+    stats[C + c] = static_cast<float>(m2);
+  }
 }
 
-// out[j][c] = sum_p partial[p][j][c] in CTA order
-__global__ void conv_partial_reduce_kernel(const float* __restrict__ partial, int n_partial, int n_out, int dim, float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_out * dim) return;
+// out[j][c] = sum_p partial[p][j][c]: 32 outputs x 8 lanes per block, chunked in CTA order (fixed order)
+__global__ void __launch_bounds__(256) conv_partial_reduce_kernel(const float* __restrict__ partial, int n_partial, int n_out, int dim,
+                                                                  float* __restrict__ out) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + tx, n = n_out * dim;
+  const int per = (n_partial + 7) / 8, p0 = ty * per, p1 = min(n_partial, p0 + per);
   float s = 0.f;
-  for (int p = 0; p < n_partial; ++p) s += partial[static_cast<size_t>(p) * n_out * dim + i];
-  out[i] = s;
+  if (i < n)
+    for (int p = p0; p < p1; ++p) s += partial[static_cast<size_t>(p) * n + i];
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && i < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += sm[q][tx];
+    out[i] = t;
+  }
 }
 
 // stats [2][C] (mean, centred sum of squares M2) over `count` frames -> mean / rstd (biased variance) and the running-statistics update
@@ -237,7 +268,7 @@ int launch_dwconv_raw(int precision, const void* x, const float* w, const float*
   else
     dwconv_raw_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, bias, B, T, T_out, C, K, stride, y, work);
   EC_CUDA(cudaGetLastError());
-  bn_stats_merge_kernel<<<cdiv(C, 128), 128, 0, st>>>(work, ctas, static_cast<size_t>(B) * T_out, C, sums);
+  bn_stats_merge_kernel<<<cdiv(C, 32), 256, 0, st>>>(work, ctas, static_cast<size_t>(B) * T_out, C, sums);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -260,7 +291,7 @@ int launch_bn_swish_bwd_stats(const float* y, const float* dh, size_t rows, int 
   const int ctas = ctas_for(rows);
   bn_swish_bwd_stats_kernel<<<dim3(ctas, cdiv(C, 128)), 128, 0, st>>>(y, dh, rows, C, mean, rstd, gamma, beta, work);
   EC_CUDA(cudaGetLastError());
-  conv_partial_reduce_kernel<<<cdiv(2 * C, 256), 256, 0, st>>>(work, ctas, 2, C, sums);
+  conv_partial_reduce_kernel<<<cdiv(2 * C, 32), 256, 0, st>>>(work, ctas, 2, C, sums);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -276,7 +307,7 @@ int launch_dwconv_bwd(int precision, const float* dy, const void* x, const float
   EC_REQUIRE(K % 2 == 1 && K <= kMaxTaps && (stride == 1 || stride == 2), "depthwise conv: odd k <= 31, stride 1 or 2");
   const int T_out = (T - 1) / stride + 1;
   if (dx != nullptr) {
-    dwconv_bwd_data_kernel<<<dim3(ctas_for(static_cast<size_t>(B) * T), cdiv(C, 128)), 128, 0, st>>>(dy, w, B, T, T_out, C, K, stride, dx);
+    dwconv_bwd_data_kernel<<<dim3(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(B) * T, 148 * 32)), cdiv(C, 128)), 128, 0, st>>>(dy, w, B, T, T_out, C, K, stride, dx);
     EC_CUDA(cudaGetLastError());
   }
   const int ctas = ctas_for(static_cast<size_t>(B) * T_out);

@@ -176,6 +176,10 @@ int try_launch_relpos_attention_tma(const AttnArgs& a, cudaStream_t stream, bool
 
 // backward of the attention core (attention_bwd.cu): dqkv [B*T, 3D], dE [2Tp-G, D], du / dv [D], all fp32
 size_t attention_bwd_work_bytes(int B, int T, int D, int H, int G);
+size_t attention_bwd_tc_work_bytes(int B, int T, int D, int H, int G);
+struct AttnArgs;
+int launch_relpos_attention_bwd_tc(const AttnArgs& a, const float* dO, float* dqkv, float* dE, float* du, float* dv, void* work,
+                                   cudaStream_t stream);
 int launch_relpos_attention_bwd(int precision, const AttnArgs& a, const float* dO, float* dqkv, float* dE, float* du, float* dv, void* work,
                                 cudaStream_t stream);
 
@@ -261,7 +265,7 @@ int launch_col_stats(const float* y, size_t rows, int cols, float* stats, float*
 int launch_group_stats_merge(const float* col_stats, int C, int group, size_t rows, float* ch_stats, cudaStream_t st);
 int launch_group_expand(const float* in, int n_vec, int C, int group, float* out, cudaStream_t st);
 int launch_group_sum(const float* in, int n_vec, int C, int group, float* out, cudaStream_t st);
-size_t subsample_wgrad_work_bytes(int C, int F);
+size_t subsample_wgrad_work_bytes(int C, int F, int B, int T);
 int launch_subsample_wgrad(const float* dy, const float* mel, int B, int F, int T, int C, float* dw, float* db, float* work, cudaStream_t st);
 int launch_greedy_collapse(const int* argmax, int B, int T, const int* logits_len, int* ids, int* counts, cudaStream_t stream);
 

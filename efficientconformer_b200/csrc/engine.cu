@@ -685,7 +685,7 @@ int ec_op_group_expand(const float* in, int n_vec, int channels, int group, floa
 int ec_op_group_sum(const float* in, int n_vec, int channels, int group, float* out, void* stream) {
   return launch_group_sum(in, n_vec, channels, group, out, EC_ST(stream));
 }
-size_t ec_op_subsample_wgrad_work_bytes(int channels, int n_mels) { return subsample_wgrad_work_bytes(channels, n_mels); }
+size_t ec_op_subsample_wgrad_work_bytes(int channels, int n_mels, int batch, int t) { return subsample_wgrad_work_bytes(channels, n_mels, batch, t); }
 int ec_op_subsample_wgrad(const float* dy, const float* mel, int batch, int n_mels, int t, int channels, float* dw, float* db, void* work,
                           void* stream) {
   return launch_subsample_wgrad(dy, mel, batch, n_mels, t, channels, dw, db, reinterpret_cast<float*>(work), EC_ST(stream));

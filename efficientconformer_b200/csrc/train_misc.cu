@@ -183,10 +183,24 @@ int launch_group_sum(const float* in, int n_vec, int C, int group, float* out, c
 
 // ---- Conv2d(1 -> C, 3x3, stride 2, pad 1) weight / bias gradient ------------------------------------------------------------------
 // dy [B, T_out, C*F2] (feature c*F2 + f), mel [B, F, T]:  dw[c][kh*3+kw] = sum_{b,t,f} dy * mel[b, 2f-1+kh, 2t-1+kw],  db[c] = sum dy
-// thread = column (c, f); CTA = contiguous range of (b, t) rows; partial[cta][col][10]
-__global__ void __launch_bounds__(128) subsample_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ mel, int B, int F, int T_in,
+// Weight / bias gradient of Conv2d(1 -> C, 3x3, stride 2, pad 1):  dw[c, kh, kw] = sum_{b,t,f} dy[(b,t), c*F2+f] * mel[b, 2f-1+kh, 2t-1+kw].
+// Pre-pass: zero-bordered transposed copy melT[b, ti+1, fi+1] (coalesced along frequency, no bounds checks in the main loop).
+// Main kernel: thread = output column (c, f), CTA = row range; 9 + 1 accumulators; partial[cta][col][10]; then one block per channel
+// adds the partials of its F2 columns in a fixed order.
+__global__ void __launch_bounds__(256) subsample_melT_kernel(const float* __restrict__ mel, int B, int F, int T_in, float* __restrict__ melT) {
+  const int Fp = F + 2, Tp = T_in + 2;
+  const size_t n = static_cast<size_t>(B) * Tp * Fp, st = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += st) {
+    const int fp = static_cast<int>(i % Fp);
+    const size_t r = i / Fp;
+    const int tp = static_cast<int>(r % Tp), b = static_cast<int>(r / Tp);
+    const int fi = fp - 1, ti = tp - 1;
+    melT[i] = (fi >= 0 && fi < F && ti >= 0 && ti < T_in) ? mel[(static_cast<size_t>(b) * F + fi) * T_in + ti] : 0.f;
+  }
+}
+__global__ void __launch_bounds__(128) subsample_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ melT, int B, int F, int T_in,
                                                               int T_out, int C, float* __restrict__ partial) {
-  const int F2 = F / 2, cols = C * F2;
+  const int F2 = F / 2, cols = C * F2, Fp = F + 2, Tp = T_in + 2;
   const int col = blockIdx.y * 128 + threadIdx.x;
   if (col >= cols) return;
   const int f = col % F2;
@@ -197,39 +211,58 @@ __global__ void __launch_bounds__(128) subsample_wgrad_kernel(const float* __res
   for (size_t r = r0; r < r1; ++r) {
     const int b = static_cast<int>(r / T_out), t = static_cast<int>(r - static_cast<size_t>(b) * T_out);
     const float d = dy[r * cols + col];
-    const float* mb = mel + static_cast<size_t>(b) * F * T_in;
+    // rows 2t-1 .. 2t+1 of the input are rows 2t .. 2t+2 of the bordered copy (2t+2 <= T_in+1 always); same for the frequencies
+    const float* base = melT + (static_cast<size_t>(b) * Tp + 2 * t) * Fp + 2 * f;
     acc[9] += d;
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int fi = 2 * f - 1 + kh;
+    for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int ti = 2 * t - 1 + kw;
-        if (fi >= 0 && fi < F && ti >= 0 && ti < T_in) acc[kh * 3 + kw] = fmaf(d, mb[static_cast<size_t>(fi) * T_in + ti], acc[kh * 3 + kw]);
-      }
-    }
+      for (int kh = 0; kh < 3; ++kh) acc[kh * 3 + kw] = fmaf(d, base[kw * Fp + kh], acc[kh * 3 + kw]);
   }
   float* out = partial + (static_cast<size_t>(blockIdx.x) * cols + col) * 10;
 #pragma unroll
   for (int k = 0; k < 10; ++k) out[k] = acc[k];
 }
-__global__ void subsample_wgrad_reduce_kernel(const float* __restrict__ partial, int n_partial, int C, int F2, float* __restrict__ dw,
-                                              float* __restrict__ db) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C * 10) return;
-  const int c = i / 10, k = i - c * 10, cols = C * F2;
-  float s = 0.f;
-  for (int p = 0; p < n_partial; ++p)
-    for (int f = 0; f < F2; ++f) s += partial[(static_cast<size_t>(p) * cols + c * F2 + f) * 10 + k];
-  if (k < 9) dw[c * 9 + k] = s; else db[c] = s;
+// block = channel c: 256 threads stride over the (partial, f) pairs, then a fixed-order shared-memory tree per tap
+__global__ void __launch_bounds__(256) subsample_wgrad_reduce_kernel(const float* __restrict__ partial, int n_partial, int C, int F2,
+                                                                     float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float sm[256][11];
+  const int c = blockIdx.x, cols = C * F2, tid = threadIdx.x;
+  float acc[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) acc[k] = 0.f;
+  for (int idx = tid; idx < n_partial * F2; idx += 256) {
+    const int p = idx / F2, f = idx - p * F2;
+    const float* src = partial + (static_cast<size_t>(p) * cols + c * F2 + f) * 10;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[k] += src[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 10; ++k) sm[tid][k] = acc[k];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s)
+#pragma unroll
+      for (int k = 0; k < 10; ++k) sm[tid][k] += sm[tid + s][k];
+    __syncthreads();
+  }
+  if (tid < 9) dw[c * 9 + tid] = sm[0][tid];
+  if (tid == 9) db[c] = sm[0][9];
 }
-size_t subsample_wgrad_work_bytes(int C, int F) { return align_up(static_cast<size_t>(kCtas) * C * (F / 2) * 10 * sizeof(float), 256); }
+static constexpr int kWgCtas = 592;
+static size_t melT_bytes(int B, int F, int T) { return align_up(static_cast<size_t>(B) * (T + 2) * (F + 2) * sizeof(float), 256); }
+static size_t wg_partial_bytes(int C, int F) { return align_up(static_cast<size_t>(kWgCtas) * C * (F / 2) * 10 * sizeof(float), 256); }
+size_t subsample_wgrad_work_bytes(int C, int F, int B, int T) { return wg_partial_bytes(C, F) + melT_bytes(B, F, T); }
 int launch_subsample_wgrad(const float* dy, const float* mel, int B, int F, int T, int C, float* dw, float* db, float* work, cudaStream_t st) {
+  EC_REQUIRE(F % 2 == 0, "Conv2d subsampling weight gradient: even number of mel bins");
   const int T_out = (T - 1) / 2 + 1, cols = C * (F / 2);
-  const int ctas = static_cast<int>(std::min<size_t>(kCtas, static_cast<size_t>(B) * T_out));
-  subsample_wgrad_kernel<<<dim3(ctas, cdiv(cols, 128)), 128, 0, st>>>(dy, mel, B, F, T, T_out, C, work);
+  const int ctas = static_cast<int>(std::min<size_t>(kWgCtas, static_cast<size_t>(B) * T_out));
+  float* melT = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(work) + wg_partial_bytes(C, F));
+  subsample_melT_kernel<<<grid_for(static_cast<size_t>(B) * (T + 2) * (F + 2)), 256, 0, st>>>(mel, B, F, T, melT);
   EC_CUDA(cudaGetLastError());
-  subsample_wgrad_reduce_kernel<<<cdiv(C * 10, 128), 128, 0, st>>>(work, ctas, C, F / 2, dw, db);
+  subsample_wgrad_kernel<<<dim3(ctas, cdiv(cols, 128)), 128, 0, st>>>(dy, melT, B, F, T, T_out, C, work);
+  EC_CUDA(cudaGetLastError());
+  subsample_wgrad_reduce_kernel<<<C, 256, 0, st>>>(work, ctas, C, F / 2, dw, db);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }

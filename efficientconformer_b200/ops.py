@@ -357,7 +357,7 @@ class SubsampleTrain:
         rows, cols = y.shape
         dev = y.device
         da = da.float().contiguous()
-        work = torch.empty(max(L.ec_op_conv_train_work_bytes(cols, 1), L.ec_op_subsample_wgrad_work_bytes(Cc, F)), dtype=torch.uint8, device=dev)
+        work = torch.empty(max(L.ec_op_conv_train_work_bytes(cols, 1), L.ec_op_subsample_wgrad_work_bytes(Cc, F, B, T)), dtype=torch.uint8, device=dev)
         sums_col = torch.empty(2, cols, dtype=torch.float32, device=dev)
         check(L.ec_op_bn_swish_bwd_stats(ptr(y), ptr(da), rows, cols, ptr(colv[0]), ptr(colv[1]), ptr(colv[2]), ptr(colv[3]), ptr(sums_col),
                                          ptr(work), stream_ptr()))

@@ -161,7 +161,7 @@ int ec_op_col_stats(const float* y, size_t rows, int cols, float* stats, void* w
 int ec_op_group_stats_merge(const float* col_stats, int channels, int group, size_t rows, float* ch_stats, void* stream);
 int ec_op_group_expand(const float* in, int n_vec, int channels, int group, float* out, void* stream);
 int ec_op_group_sum(const float* in, int n_vec, int channels, int group, float* out, void* stream);
-size_t ec_op_subsample_wgrad_work_bytes(int channels, int n_mels);
+size_t ec_op_subsample_wgrad_work_bytes(int channels, int n_mels, int batch, int t);
 int ec_op_subsample_wgrad(const float* dy, const float* mel, int batch, int n_mels, int t, int channels, float* dw, float* db, void* work,
                           void* stream);
 /* Backward of ec_op_relpos_attention (same operand conventions: qkv [B*T, 3D] and E [2Tp-G, D] in the activation type):

@@ -228,9 +228,12 @@ def test_relpos_attention_backward(ops, prec):
         _attention_reference(qr, Er, ur, vr, x_len, H, G).backward(d_out.double())
         dqkv, dE, du, dv = ops.relpos_attention_bwd(qkv, E, u.to(DEV), v.to(DEV), x_len.to(DEV), H, G, d_out.to(DEV), prec)
         case = (prec, trial, B, T, D, H, G)
-        assert rel_l2(dqkv, qr.grad) < 2e-5, (case, rel_l2(dqkv, qr.grad))
-        assert rel_l2(dE, Er.grad) < 2e-5, (case, rel_l2(dE, Er.grad))
-        assert rel_l2(du, ur.grad) < 2e-5 and rel_l2(dv, vr.grad) < 2e-5, case
+        # tf32 mode: fp32 CUDA-core kernels (parity path).  bf16 mode: batched tensor-core GEMMs with bf16 Qu / Qv / P / dS operands
+        # (fp32 accumulation): the operand rounding (2^-9 relative per element) bounds the error, as in the forward kernel.
+        tol = 2e-5 if prec == "tf32" else 1.5e-2
+        errs = [rel_l2(dqkv, qr.grad), rel_l2(dE, Er.grad), rel_l2(du, ur.grad), rel_l2(dv, vr.grad)]
+        print(case, ["%.2e" % e for e in errs])
+        assert max(errs) < tol, (case, errs)
 
 
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])
