@@ -1,7 +1,12 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: EfficientConformerCTCSmall encoder forward + fc + CTC loss on synthetic 80-mel batches.
+"""Benchmark of the hot path on synthetic 80-mel batches of EfficientConformerCTCSmall.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|tf32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|tf32] [--mode train|forward]
+
+--mode train (default; BASELINE.json configs[1]): one optimisation step = train-mode forward (batch-statistics BatchNorm, dropout
+0.1) + CTC loss + backward + gradient all-reduce (N > 1) + Adam with the Transformer schedule, through
+efficientconformer_b200.trainer.CTCTrainStep (CUDA-graph replay).  --mode forward: inference forward + fc + CTC loss (the round-1
+forward numbers).  The remaining text describes the keys of the JSON line, which are the same in both modes.
 
 Prints ONE JSON line (rank 0).  metric = mel frames / second (BASELINE.json), whole job over all N GPUs.
   value     inputs already resident in HBM; every step timed by its own CUDA-event pair on the launching stream, L2 flushed
@@ -43,10 +48,10 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def ncu_traffic(precision, kernel_prefix="gemm_tc_kernel"):
+def ncu_traffic(precision, kernel_prefix="gemm_tc_kernel", stem="r1_ncu_full_block0"):
     """Average DRAM bytes (read + write) per launch of one kernel from the committed `ncu --set full` capture of block 0
     (profiles/, produced by tools/summarize_ncu.py); None when no capture exists for this precision."""
-    path = os.path.join(ROOT, "profiles", f"r1_ncu_full_block0_{precision}_summary.json")
+    path = os.path.join(ROOT, "profiles", f"{stem}_{precision}_summary.json")
     if not os.path.exists(path):
         return None
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -363,24 +368,322 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(out))
 
 
+# =====================================================================================================================
+# training step (BASELINE.json configs[1]; reference models/model.py:239-259)
+# =====================================================================================================================
+TRAINING_PARAMS = dict(optimizer="Adam", beta1=0.9, beta2=0.98, eps=1e-9, weight_decay=1e-6, lr_schedule="Transformer", schedule_dim=240,
+                       warmup_steps=10000, K=2)      # reference configs/EfficientConformerCTCSmall.json:53-69
+TRAIN_FLOP_PER_FRAME = {500: 6.148e6, 1000: 6.616e6, 1600: 7.198e6, 2000: 7.587e6}   # forward; training = 3x
+
+
+def train_workload_config(args, batch_per_gpu, world, where, extra=None):
+    cfg = {"workload": f"EfficientConformerCTCSmall CTC training step (train-mode forward, dropout {args.pdrop}, CTC loss, backward, Adam + Transformer "
+                       f"schedule), batch {batch_per_gpu}/GPU x 80-mel x {args.frames} frames, full-length utterances (BASELINE.json configs[1] at the "
+                       f"north_star target shape)",
+           "global_batch": batch_per_gpu * world, "frames": args.frames, "n_mels": 80, "weights": "seeded random init",
+           "l2": "256 MiB write between timed steps (L2 flush)" if where == "gpu" else "n/a (CPU)",
+           "parallelism": f"dp{world}: utterances sharded over ranks; SyncBatchNorm statistics + one flat gradient bucket all-reduced over NCCL"
+                          if world > 1 else "dp1"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def cpu_oracle_train_pass(leaf, opt, mel, mel_len, y, y_len, params):
+    """One training step of the CPU oracle: train-mode forward, CTC loss, autograd backward, torch.optim.Adam (the optimiser the
+    reference constructs, models/model.py:88-93).  Dropout is not applied (the oracle is deterministic; its cost is negligible)."""
+    from oracle import conformer_oracle as O           # checker / CPU baseline only (never the product path)
+    t0 = time.perf_counter()
+    bn = {"updates": {}}
+    logits, out_len = O.model_ctc_forward_mel(leaf, params, mel, mel_len, bn=bn)
+    loss, _ = O.ctc_loss(logits, out_len, y, y_len)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    with torch.no_grad():
+        for k, v in bn["updates"].items():
+            leaf["encoder." + k].copy_(v)
+    return time.perf_counter() - t0, float(loss.detach())
+
+
+def cpu_train_setup():
+    sd = seeded_state_dict(P, V, seed=0, prefix_encoder="encoder.")
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+    opt = torch.optim.Adam([v for v in leaf.values() if v.requires_grad], lr=1e-4, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6)
+    return sd, leaf, opt
+
+
+def run_reference_train(args, rank, world):
+    """Reference arm for the training step: the CPU implementation (oracle port + torch autograd + torch.optim.Adam) on the host cores."""
+    if rank != 0:
+        return
+    sd, leaf, opt = cpu_train_setup()
+    with torch.no_grad():
+        cores = best_cpu_threads(sd)
+    B = max(2, min(args.batch, 8)) if (args.steps + args.warmup) <= 12 else 4
+    mel = synthetic_mel(B, args.frames, seed=1)
+    mel_len = torch.full((B,), args.frames, dtype=torch.int64)
+    t_out = (((args.frames - 1) // 2 + 1 - 1) // 2 + 1 - 1) // 2 + 1
+    y, y_len = synthetic_targets(torch.full((B,), t_out), V, seed=4)
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_oracle_train_pass(leaf, opt, mel, mel_len, y, y_len, P)
+    times = [cpu_oracle_train_pass(leaf, opt, mel, mel_len, y, y_len, P)[0] for _ in range(args.steps)]
+    total = sum(times)
+    value = B * args.frames * args.steps / total
+    sample = (f"{args.steps} training steps of B={B} x 80 x {args.frames} (train-mode fwd + CTC + autograd backward + torch.optim.Adam), fp32, "
+              f"torch CPU {torch.get_num_threads()} threads (best of 8/16/32/64/all on a {os.cpu_count()}-core host)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": train_workload_config(args, B, 1, "cpu"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def count_launches(fn):
+    """Kernel launches of one eager call of fn(): (ours, library) -- `ours` are the kernels of libeffconf_b200.so (namespace ec::),
+    `library` whatever PyTorch / NCCL launched next to them (fills, index bookkeeping, collectives).  Memcpy / memset nodes excluded."""
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        ours = lib_k = 0
+        names = {}
+        for e in prof.events():
+            if e.device_type != torch.autograd.DeviceType.CUDA:
+                continue
+            n = e.name
+            if n.lower().startswith(("memcpy", "memset")):
+                continue
+            if "ec::" in n:
+                ours += 1
+            else:
+                lib_k += 1; names[n.split("<")[0][:60]] = names.get(n.split("<")[0][:60], 0) + 1
+        return ours, lib_k, names
+    except Exception as ex:                                          # profiler unavailable: report the committed ncu count
+        return None, None, {"error": repr(ex)}
+
+
+def run_train(args, rank, world, local_rank):
+    from efficientconformer_b200 import ModelCTC, _lib
+    from efficientconformer_b200.trainer import CTCTrainStep
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the single JSON line
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    B, T = args.batch, args.frames
+    params = dict(P); params["Pdrop"] = args.pdrop
+    sd = seeded_state_dict(P, V, seed=0, prefix_encoder="encoder.")
+
+    def make_step(graph):
+        model = ModelCTC(params, {"vocab_size": V}, precision=args.precision)
+        model.load_state_dict(sd, strict=False)
+        model = model.to(dev).train()
+        return CTCTrainStep(model, TRAINING_PARAMS, precision=args.precision, use_cuda_graph=graph, sync_bn=not args.no_sync_bn,
+                            dropout_seed=1234)
+    use_graph = not args.no_graph
+    step = make_step(use_graph)
+    mel_h = synthetic_mel(B, T, seed=1 + rank).pin_memory()
+    t_out = (((T - 1) // 2 + 1 - 1) // 2 + 1 - 1) // 2 + 1
+    y, y_len = synthetic_targets(torch.full((B,), t_out), V, seed=4 + rank)
+    y_h, yl_h = y.pin_memory(), y_len.pin_memory()
+    mel_d, y_d, yl_d = mel_h.to(dev), y_h.to(dev), yl_h.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    graph_note = "cuda graph replay" if use_graph else "eager launches"
+    try:
+        for _ in range(max(args.warmup, 3)):
+            step.step(mel_d, None, y_d, yl_d); flush.zero_()
+        torch.cuda.synchronize()
+    except Exception as ex:                              # e.g. a collective that cannot be captured: measure the eager step and say so
+        if not use_graph:
+            raise
+        graph_note = f"eager launches (graph capture failed: {type(ex).__name__})"
+        use_graph = False
+        step = make_step(False)
+        for _ in range(max(args.warmup, 3)):
+            step.step(mel_d, None, y_d, yl_d); flush.zero_()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    losses = []
+    for a, b in ev:
+        flush.zero_()
+        a.record(); loss = step.step(mel_d, None, y_d, yl_d); b.record()
+        losses.append(loss.clone())
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms)
+    losses = [float(l) for l in losses]
+
+    # ---- end to end: every step copies its batch (mel, targets, lengths) from pinned host memory, runs the step, reads the loss back ----
+    copy_stream = torch.cuda.Stream(device=dev)
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+
+    def e2e_loop(n_steps):
+        cur = torch.cuda.current_stream()
+        bufs, ready, done = [None, None], [torch.cuda.Event(), torch.cuda.Event()], [torch.cuda.Event(), torch.cuda.Event()]
+        out = []
+
+        def stage(k):
+            with torch.cuda.stream(copy_stream):
+                if bufs[k & 1] is not None:
+                    copy_stream.wait_event(done[k & 1])
+                bufs[k & 1] = (mel_h.to(dev, non_blocking=True), y_h.to(dev, non_blocking=True), yl_h.to(dev, non_blocking=True))
+                ready[k & 1].record(copy_stream)
+        stage(0)
+        for k in range(n_steps):
+            if k + 1 < n_steps:
+                stage(k + 1)
+            cur.wait_event(ready[k & 1])
+            m, yy, yl = bufs[k & 1]
+            ls = step.step(m, None, yy, yl)
+            loss_host[k & 1].copy_(ls, non_blocking=True)
+            done[k & 1].record(cur)
+            if k >= 1:
+                done[(k - 1) & 1].synchronize()
+                out.append(float(loss_host[(k - 1) & 1]))
+        done[(n_steps - 1) & 1].synchronize()
+        out.append(float(loss_host[(n_steps - 1) & 1]))
+        return out
+
+    e2e_loop(3)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_losses = e2e_loop(args.steps)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    barrier()
+    if dist is not None:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_s = float(e2e_s)
+
+    # ---- operator profile of eager steps: CUDA events around every operator entry point, launching stream (rank 0, no collectives) ----
+    prof_ops, ours_k, lib_k, lib_names = {}, None, None, {}
+    if world == 1:
+        estep = make_step(False)
+        for _ in range(2):
+            estep.step(mel_d, None, y_d, yl_d)
+        torch.cuda.synchronize()
+        reps = 3
+        with _lib.OpProfile() as prof:
+            for _ in range(reps):
+                estep.step(mel_d, None, y_d, yl_d)
+            summ = prof.summary()
+        for k, v in summ.items():
+            prof_ops[k] = {"calls": v["calls"] // reps, "ms": v["ms"] / reps, "flops": v["flops"] / reps}
+        ours_k, lib_k, lib_names = count_launches(lambda: estep.step(mel_d, None, y_d, yl_d))
+        del estep
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    pk = peaks()
+    tensor_peak = pk["bf16_tflops"] * (1.0 if args.precision == "bf16" else 0.5)
+    frames_total = world * B * T * args.steps
+    out = {
+        "metric": METRIC, "value": frames_total / (total_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic",
+        "config": train_workload_config(args, B, world, "gpu", {"launch": graph_note, "sync_bn": world > 1 and not args.no_sync_bn}),
+        "e2e": {"value": frames_total / e2e_s, "unit": UNIT,
+                "h2d_bytes_per_step": mel_h.numel() * 4 + y_h.numel() * 8 + yl_h.numel() * 8, "d2h_bytes_per_step": 4,
+                "ms_per_step": 1e3 * e2e_s / args.steps,
+                "timing": "wall clock around K CTCTrainStep.step calls with HOST batches (pinned mel / targets -> H2D on a copy stream, 2-deep "
+                          "pipeline, loss read back every step), synchronised both sides"},
+        "clocks": clocks,
+        "step_ms_min_med_max": [round(min(step_ms), 4), round(statistics.median(step_ms), 4), round(max(step_ms), 4)],
+        "loss_first_last": [losses[0], losses[-1]], "e2e_loss_last": e2e_losses[-1], "lr_after": step.lr(), "optimizer_steps": step.steps_done(),
+    }
+    if prof_ops:
+        tot_ms = sum(v["ms"] for v in prof_ops.values())
+        ops_sorted = sorted(prof_ops.items(), key=lambda kv: -kv[1]["ms"])
+        out["operators"] = [{"op": k, "calls": v["calls"], "ms": round(v["ms"], 4),
+                             "tflops": round(v["flops"] / v["ms"] / 1e9, 2) if v["flops"] else None} for k, v in ops_sorted]
+        tensor_ops = [(k, v) for k, v in ops_sorted if v["flops"] > 0]
+        k, v = tensor_ops[0]
+        desc = {"ec_op_wgrad": "ec_op_wgrad = wgrad_tc_kernel (tcgen05, MN-major operands, split-M) + fixed-order reduce: every weight gradient of one step",
+                "ec_op_gemm": "ec_op_gemm = gemm_tc_kernel (tcgen05 + TMA): every forward Linear / pointwise conv and every data-gradient GEMM of one step"}
+        ach = v["flops"] / v["ms"] / 1e9
+
+        def roof(k, v):
+            a = v["flops"] / v["ms"] / 1e9
+            kern = "wgrad_tc_kernel" if k == "ec_op_wgrad" else "gemm_tc_kernel"
+            return {"kernel": desc.get(k, k), "bound": "tensor", "achieved": round(a, 2), "peak": tensor_peak, "unit": "TFLOP/s",
+                    "frac": round(a / tensor_peak, 4), "traffic": ncu_traffic(args.precision, kern, "r2_ncu_full_train"),
+                    "peak_source": pk["source"] + (" bf16 cuBLAS burst" if args.precision == "bf16" else " bf16 cuBLAS burst / 2 (tf32 operands)"),
+                    "launches_per_step": v["calls"], "avg_launch_us": round(1e3 * v["ms"] / max(v["calls"], 1), 2),
+                    "share_of_step": round(v["ms"] / tot_ms, 3),
+                    "algorithmic_flops_per_step": v["flops"],
+                    "timing": "CUDA events around every operator call of an eager step on the launching stream (serialised), mean of 3 steps"}
+        out["roofline"] = roof(k, v)
+        out["rooflines_other"] = [roof(k2, v2) for k2, v2 in tensor_ops[1:]]
+        step_flops = 3.0 * TRAIN_FLOP_PER_FRAME.get(T, 6.616e6) * B * T
+        out["whole_step"] = {"algorithmic_tflop": round(step_flops / 1e12, 4), "achieved_tflops": round(step_flops / (total_ms / args.steps) / 1e9, 2),
+                             "frac_of_tensor_peak": round(step_flops / (total_ms / args.steps) / 1e9 / tensor_peak, 4),
+                             "note": "3 x forward FLOPs of SURVEY.md 8(d) per mel frame; the step is launch / latency bound, not math bound"}
+        out["eager_profiled_step_ms"] = round(tot_ms, 3)
+    launches = ours_k if ours_k is not None else 2048
+    out["gpu_launches"] = launches * args.steps
+    out["launches_per_step"] = launches
+    out["library_launches_per_step"] = {"count": lib_k, "kernels": lib_names}
+    if world == 1 and not args.no_cpu_baseline:
+        sd2, leaf, opt = cpu_train_setup()
+        with torch.no_grad():
+            best_cpu_threads(sd2)
+        Bs = 4
+        cm, cl = mel_h[:Bs].clone(), torch.full((Bs,), T, dtype=torch.int64)
+        cpu_oracle_train_pass(leaf, opt, cm, cl, y[:Bs], y_len[:Bs], P)
+        runs = [cpu_oracle_train_pass(leaf, opt, cm, cl, y[:Bs], y_len[:Bs], P)[0] for _ in range(3)]
+        sec = statistics.median(runs)
+        out["cpu_baseline"] = {"value": Bs * T / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"median of 3 training steps on the first {Bs} utterances of the same batch (oracle train-mode fwd + CTC + autograd "
+                                         f"backward + torch.optim.Adam), fp32 torch CPU, {torch.get_num_threads()} threads"}
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--frames", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="train", choices=["train", "forward"])
+    ap.add_argument("--pdrop", type=float, default=0.1, help="dropout probability of the training step (reference config: 0.1)")
+    ap.add_argument("--no-graph", action="store_true", help="training step: eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-sync-bn", action="store_true", help="N > 1: per-rank BatchNorm statistics (NOT the reference's SyncBatchNorm semantics)")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = (40 if args.mode == "train" else 100) if args.impl == "ours" else 3
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        (run_reference_train if args.mode == "train" else run_reference)(args, rank, world)
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a B200: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
-    run_ours(args, rank, world, local)
+    (run_train if args.mode == "train" else run_ours)(args, rank, world, local)
 
 
 if __name__ == "__main__":

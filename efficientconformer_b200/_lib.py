@@ -164,7 +164,61 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = handle
+    if _profile is not None:
+        return _ProfiledLib(_lib, _profile)
     return _lib
+
+
+class OpProfile:
+    """Measurement hook (bench.py, tools/): while active, every operator entry point (ec_op_*, ec_ctc_*, ec_adam_step) is bracketed by
+    a CUDA-event pair on the launching stream; `summary()` returns per-entry-point launch counts, device time and the algorithmic
+    FLOPs of the tensor-core operators (2*M*N*K from the call's own arguments).  Eager launches only (not under graph capture)."""
+    _GEMM_ARGS = {"ec_op_gemm": (3, 4, 5), "ec_op_wgrad": (3, 4, 5), "ec_op_gemm_ln": (3, 4, 5)}
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global _profile
+        _profile = self
+        return self
+
+    def __exit__(self, *exc):
+        global _profile
+        _profile = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, flops in self.records:
+            ent = out.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0})
+            ent["calls"] += 1; ent["ms"] += e0.elapsed_time(e1); ent["flops"] += flops
+        return out
+
+
+class _ProfiledLib:
+    def __init__(self, handle, prof):
+        self._h, self._p = handle, prof
+
+    def __getattr__(self, name):
+        fn = getattr(self._h, name)
+        if not (name.startswith(("ec_op_", "ec_ctc_", "ec_adam")) and not name.endswith(("_bytes", "_rows"))):
+            return fn
+        prof = self._p
+
+        def call(*args):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*args)
+            e1.record()
+            idx = OpProfile._GEMM_ARGS.get(name)
+            flops = 2.0 * args[idx[0]] * args[idx[1]] * args[idx[2]] if idx else 0.0
+            prof.records.append((name, e0, e1, flops))
+            return r
+        return call
+
+
+_profile = None
 
 
 def check(status: int):

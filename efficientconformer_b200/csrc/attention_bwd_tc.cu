@@ -274,30 +274,51 @@ __global__ void __launch_bounds__(256) tc_unpack_kernel(const TcDev p) {
     out[2 * p.D + ch] = p.dV[src];
   }
 }
-// column sums of dQu / dQv over the grouped rows of one (b, h): uv_part[bh][0 | 1][c]
-__global__ void __launch_bounds__(128) tc_uv_part_kernel(const TcDev p) {
-  const int bh = blockIdx.x;
-  for (int c = threadIdx.x; c < p.dp; c += blockDim.x) {
+// column sums of dQu / dQv over the grouped rows of one (b, h): uv_part[bh][0 | 1][c].  Block = 32 columns x 32 row lanes, lane ty
+// adds the contiguous row chunk ty, chunk sums added in lane order (fixed order).
+__global__ void __launch_bounds__(1024) tc_uv_part_kernel(const TcDev p) {
+  __shared__ float su_s[32][33], sv_s[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int bh = blockIdx.x, c = blockIdx.y * 32 + tx;
+  const int per = (p.Tg + 31) / 32, i0 = ty * per, i1 = min(p.Tg, i0 + per);
+  float su = 0.f, sv = 0.f;
+  if (c < p.dp) {
     const float* qu = p.dQu + static_cast<long long>(bh) * p.Tg * p.dp + c;
     const float* qv = p.dQv + static_cast<long long>(bh) * p.Tg * p.dp + c;
-    float su = 0.f, sv = 0.f;
-    for (int i = 0; i < p.Tg; ++i) { su += qu[static_cast<long long>(i) * p.dp]; sv += qv[static_cast<long long>(i) * p.dp]; }
+    for (int i = i0; i < i1; ++i) { su += qu[static_cast<long long>(i) * p.dp]; sv += qv[static_cast<long long>(i) * p.dp]; }
+  }
+  su_s[ty][tx] = su; sv_s[ty][tx] = sv;
+  __syncthreads();
+  if (ty == 0 && c < p.dp) {
+    su = 0.f; sv = 0.f;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) { su += su_s[q][tx]; sv += sv_s[q][tx]; }
     p.uv_part[(static_cast<long long>(bh) * 2) * p.dp + c] = su;
     p.uv_part[(static_cast<long long>(bh) * 2 + 1) * p.dp + c] = sv;
   }
 }
-// du[ch] = sum_b sum_fo part[b, h(fo, ch), c(fo, ch)]  (fixed order)
-__global__ void tc_uv_reduce_kernel(const TcDev p) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= p.D) return;
+// du[ch] = sum_b sum_fo part[b, h(fo, ch), c(fo, ch)]: 32 channels x 32 batch lanes per block (fixed order)
+__global__ void __launch_bounds__(1024) tc_uv_reduce_kernel(const TcDev p) {
+  __shared__ float su_s[32][33], sv_s[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + tx;
+  const int per = (p.B + 31) / 32, b0 = ty * per, b1 = min(p.B, b0 + per);
   float su = 0.f, sv = 0.f;
-  for (int b = 0; b < p.B; ++b)
-    for (int fo = 0; fo < p.G; ++fo) {
-      const int f = fo * p.D + ch, h = f / p.d, c = f - h * p.d;
-      const long long o = ((static_cast<long long>(b) * p.H + h) * 2) * p.dp + c;
-      su += p.uv_part[o]; sv += p.uv_part[o + p.dp];
-    }
-  p.du[ch] = su; p.dv[ch] = sv;
+  if (ch < p.D)
+    for (int b = b0; b < b1; ++b)
+      for (int fo = 0; fo < p.G; ++fo) {
+        const int f = fo * p.D + ch, h = f / p.d, c = f - h * p.d;
+        const long long o = ((static_cast<long long>(b) * p.H + h) * 2) * p.dp + c;
+        su += p.uv_part[o]; sv += p.uv_part[o + p.dp];
+      }
+  su_s[ty][tx] = su; sv_s[ty][tx] = sv;
+  __syncthreads();
+  if (ty == 0 && ch < p.D) {
+    su = 0.f; sv = 0.f;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) { su += su_s[q][tx]; sv += sv_s[q][tx]; }
+    p.du[ch] = su; p.dv[ch] = sv;
+  }
 }
 // dE[e, h*d + c] = sum_b dEp[b, h, e, c]
 __global__ void __launch_bounds__(128) tc_de_reduce_kernel(const TcDev p) {
@@ -391,9 +412,9 @@ int launch_relpos_attention_bwd_tc(const AttnArgs& a, const float* dO, float* dq
   EC_TRY((run_gemm<true, true>(BGemm{p.dRel, p.Qv, p.dEp, p.R, dp, Tg, p.Rp, dp, dp, sR * H, sR, sD * H, sD, sE * H, sE, H, 0}, BH, st)));
   tc_unpack_kernel<<<egrid(static_cast<long long>(a.B) * a.T * a.D), 256, 0, st>>>(p);
   EC_CUDA(cudaGetLastError());
-  tc_uv_part_kernel<<<BH, 128, 0, st>>>(p);
+  tc_uv_part_kernel<<<dim3(BH, cdiv(dp, 32)), 1024, 0, st>>>(p);
   EC_CUDA(cudaGetLastError());
-  tc_uv_reduce_kernel<<<cdiv(a.D, 128), 128, 0, st>>>(p);
+  tc_uv_reduce_kernel<<<cdiv(a.D, 32), 1024, 0, st>>>(p);
   EC_CUDA(cudaGetLastError());
   tc_de_reduce_kernel<<<dim3(p.R, H), 128, 0, st>>>(p);
   EC_CUDA(cudaGetLastError());

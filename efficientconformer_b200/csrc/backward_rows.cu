@@ -95,15 +95,15 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   }
 }
 
-// out[j][c] = sum over the n_partial partial rows (j = 0 .. n_out-1 stacked outputs of width dim).  Block = 32 columns x 8 row
-// lanes: lane ty adds the contiguous chunk ty of the partials in order, the 8 chunk sums are added in lane order: fixed order,
-// bit-reproducible, and an 8x shorter dependent chain than one thread per column.
-__global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __restrict__ partial, int n_partial, int n_out, int dim,
-                                                             float* __restrict__ out0, float* __restrict__ out1) {
-  __shared__ float sm[8][33];
+// out[j][c] = sum over the n_partial partial rows (j = 0 .. n_out-1 stacked outputs of width dim).  Block = 32 columns x 32 row
+// lanes: lane ty adds the contiguous chunk ty of the partials in order, the 32 chunk sums are added in lane order: fixed order,
+// bit-reproducible, and a 32x shorter dependent chain than one thread per column.
+__global__ void __launch_bounds__(1024) partial_reduce_kernel(const float* __restrict__ partial, int n_partial, int n_out, int dim,
+                                                              float* __restrict__ out0, float* __restrict__ out1) {
+  __shared__ float sm[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + tx, n = n_out * dim;
-  const int per = (n_partial + 7) / 8, p0 = ty * per, p1 = min(n_partial, p0 + per);
+  const int per = (n_partial + 31) / 32, p0 = ty * per, p1 = min(n_partial, p0 + per);
   float s = 0.f;
   if (i < n) {
     const int j = i / dim, c = i - j * dim;
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __rest
   if (ty == 0 && i < n) {
     float t = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) t += sm[q][tx];
+    for (int q = 0; q < 32; ++q) t += sm[q][tx];
     const int j = i / dim, c = i - j * dim;
     (j == 0 ? out0 : out1)[c] = t;
   }
@@ -132,7 +132,7 @@ int launch_layernorm_bwd(const float* x, const float* dy, int rows, int dim, con
   else if (dim <= 512) layernorm_bwd_kernel<16><<<ctas, 256, 0, stream>>>(x, dy, rows, dim, gamma, eps, dx, accumulate, work);
   else layernorm_bwd_kernel<32><<<ctas, 256, 0, stream>>>(x, dy, rows, dim, gamma, eps, dx, accumulate, work);
   EC_CUDA(cudaGetLastError());
-  partial_reduce_kernel<<<cdiv(2 * dim, 32), 256, 0, stream>>>(work, ctas, 2, dim, dgamma, dbeta);
+  partial_reduce_kernel<<<cdiv(2 * dim, 32), 1024, 0, stream>>>(work, ctas, 2, dim, dgamma, dbeta);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -160,7 +160,7 @@ int launch_colsum(int precision, const void* m, int is_f32, int rows, int cols, 
   if (is_f32 || precision == EC_PREC_TF32) colsum_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(m), rows, cols, work);
   else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(m), rows, cols, work);
   EC_CUDA(cudaGetLastError());
-  partial_reduce_kernel<<<cdiv(cols, 32), 256, 0, stream>>>(work, ctas, 1, cols, out, out);
+  partial_reduce_kernel<<<cdiv(cols, 32), 1024, 0, stream>>>(work, ctas, 1, cols, out, out);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }

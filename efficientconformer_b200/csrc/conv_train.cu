@@ -18,7 +18,7 @@
 namespace ec {
 
 namespace {
-constexpr int kCtas = 1184;   // 8 per SM: these kernels are latency bound on one dependent load chain per thread
+constexpr int kCtas = 888;      // 8 per SM: these kernels are latency bound on one dependent load chain per thread
 constexpr int kMaxTaps = 31;
 
 // rows [r0, r1) of this CTA for a row-strided split of `rows` over gridDim.x CTAs (contiguous ranges: coalesced, deterministic)
@@ -63,64 +63,69 @@ __global__ void __launch_bounds__(128) dwconv_raw_kernel(const T* __restrict__ x
   partial[(static_cast<size_t>(blockIdx.x) * 2 + 1) * C + c] = s2;
 }
 
-// (mean, M2) of the CTA row ranges merged with Chan's update, in double: stats[0][c] = mean, stats[1][c] = M2.
-// Block = 32 channels x 8 lanes: lane ty merges the contiguous chunk ty of the partials in CTA order, then the 8 chunk results are
-// merged in lane order (fixed order: bit-reproducible; 8x shorter chain of dependent fp64 divisions than one thread per channel).
-__global__ void __launch_bounds__(256) bn_stats_merge_kernel(const float* __restrict__ partial, int n_partial, size_t rows, int C,
-                                                             float* __restrict__ stats) {
-  __shared__ double sn[8][33], smean[8][33], sm2[8][33];
+// (mean, M2) of the CTA row ranges merged with Chan's update: stats[0][c] = mean, stats[1][c] = M2.
+// Block = 32 channels x 32 lanes: lane ty merges the contiguous chunk ty of the partials in CTA order, then the 32 chunk results
+// are merged in lane order in double (fixed order: bit-reproducible; the dependent chain is n_partial / 32 + 32 steps).
+__global__ void __launch_bounds__(1024) bn_stats_merge_kernel(const float* __restrict__ partial, int n_partial, size_t rows, int C,
+                                                              float* __restrict__ stats) {
+  __shared__ float sn[32][33], smean[32][33], sm2[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
   const size_t per = (rows + n_partial - 1) / n_partial;
-  const int chunk = (n_partial + 7) / 8, p0 = ty * chunk, p1 = min(n_partial, p0 + chunk);
-  double n = 0.0, mean = 0.0, m2 = 0.0;
+  const int chunk = (n_partial + 31) / 32, p0 = ty * chunk, p1 = min(n_partial, p0 + chunk);
+  float n = 0.f, mean = 0.f, m2 = 0.f;
   if (c < C) {
     for (int p = p0; p < p1; ++p) {
       const size_t r0 = min(rows, per * p), r1 = min(rows, r0 + per);
-      const double nb = static_cast<double>(r1 - r0);
-      if (nb == 0.0) continue;
-      const double mb = partial[(static_cast<size_t>(p) * 2) * C + c], qb = partial[(static_cast<size_t>(p) * 2 + 1) * C + c];
-      const double tot = n + nb, dl = mb - mean;
-      mean += dl * nb / tot;
-      m2 += qb + dl * dl * n * nb / tot;
+      const float nb = static_cast<float>(r1 - r0);
+      if (nb == 0.f) continue;
+      const float mb = partial[(static_cast<size_t>(p) * 2) * C + c], qb = partial[(static_cast<size_t>(p) * 2 + 1) * C + c];
+      const float tot = n + nb, dl = mb - mean, f = nb / tot;
+      mean = fmaf(dl, f, mean);
+      m2 += qb + dl * dl * n * f;
       n = tot;
     }
   }
   sn[ty][tx] = n; smean[ty][tx] = mean; sm2[ty][tx] = m2;
   __syncthreads();
   if (ty == 0 && c < C) {
-    n = 0.0; mean = 0.0; m2 = 0.0;
-    for (int q = 0; q < 8; ++q) {
+    double dn = 0.0, dmean = 0.0, dm2 = 0.0;
+    for (int q = 0; q < 32; ++q) {
       const double nb = sn[q][tx];
       if (nb == 0.0) continue;
-      const double tot = n + nb, dl = smean[q][tx] - mean;
-      mean += dl * nb / tot;
-      m2 += sm2[q][tx] + dl * dl * n * nb / tot;
-      n = tot;
+      const double tot = dn + nb, dl = static_cast<double>(smean[q][tx]) - dmean;
+      dmean += dl * nb / tot;
+      dm2 += static_cast<double>(sm2[q][tx]) + dl * dl * dn * nb / tot;
+      dn = tot;
     }
-    stats[c] = static_cast<float>(mean);
-    stats[C + c] = static_cast<float>(m2);
+    stats[c] = static_cast<float>(dmean);
+    stats[C + c] = static_cast<float>(dm2);
   }
 }
 
-// out[j][c] = sum_p partial[p][j][c]: 32 outputs x 8 lanes per block, chunked in CTA order (fixed order)
-__global__ void __launch_bounds__(256) conv_partial_reduce_kernel(const float* __restrict__ partial, int n_partial, int n_out, int dim,
-                                                                  float* __restrict__ out) {
-  __shared__ float sm[8][33];
+// out[i] = sum_p partial[p][i], i < n: block = 32 outputs x 32 lanes, lane ty adds chunk ty in CTA order, chunk sums added in lane order
+__device__ __forceinline__ float chunked_sum_32x32(const float* __restrict__ partial, int n_partial, size_t stride, int i, bool ok,
+                                                   float (*sm)[33]) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int i = blockIdx.x * 32 + tx, n = n_out * dim;
-  const int per = (n_partial + 7) / 8, p0 = ty * per, p1 = min(n_partial, p0 + per);
+  const int per = (n_partial + 31) / 32, p0 = ty * per, p1 = min(n_partial, p0 + per);
   float s = 0.f;
-  if (i < n)
-    for (int p = p0; p < p1; ++p) s += partial[static_cast<size_t>(p) * n + i];
+  if (ok)
+    for (int p = p0; p < p1; ++p) s += partial[static_cast<size_t>(p) * stride + i];
   sm[ty][tx] = s;
   __syncthreads();
-  if (ty == 0 && i < n) {
-    float t = 0.f;
+  float t = 0.f;
+  if (ty == 0) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) t += sm[q][tx];
-    out[i] = t;
+    for (int q = 0; q < 32; ++q) t += sm[q][tx];
   }
+  return t;
+}
+__global__ void __launch_bounds__(1024) conv_partial_reduce_kernel(const float* __restrict__ partial, int n_partial, int n_out, int dim,
+                                                                   float* __restrict__ out) {
+  __shared__ float sm[32][33];
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31), n = n_out * dim;
+  const float t = chunked_sum_32x32(partial, n_partial, static_cast<size_t>(n), i, i < n, sm);
+  if ((threadIdx.x >> 5) == 0 && i < n) out[i] = t;
 }
 
 // stats [2][C] (mean, centred sum of squares M2) over `count` frames -> mean / rstd (biased variance) and the running-statistics update
@@ -241,15 +246,16 @@ __global__ void __launch_bounds__(128) dwconv_bwd_weight_kernel(const float* __r
   for (int k = 0; k < kMaxTaps; ++k) if (k < K) out[k] = acc[k];
   out[K] = acc[kMaxTaps];
 }
-// dw[c][k] / db[c] from the partials, in CTA order
-__global__ void dwconv_wgrad_reduce_kernel(const float* __restrict__ partial, int n_partial, int C, int K, float* __restrict__ dw,
-                                           float* __restrict__ db) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C * (K + 1)) return;
-  float s = 0.f;
-  for (int p = 0; p < n_partial; ++p) s += partial[static_cast<size_t>(p) * C * (K + 1) + i];
-  const int c = i / (K + 1), k = i - c * (K + 1);
-  if (k < K) dw[c * K + k] = s; else db[c] = s;
+// dw[c][k] / db[c] from the partials (chunked fixed-order sum, see chunked_sum_32x32)
+__global__ void __launch_bounds__(1024) dwconv_wgrad_reduce_kernel(const float* __restrict__ partial, int n_partial, int C, int K,
+                                                                   float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float sm[32][33];
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31), n = C * (K + 1);
+  const float t = chunked_sum_32x32(partial, n_partial, static_cast<size_t>(n), i, i < n, sm);
+  if ((threadIdx.x >> 5) == 0 && i < n) {
+    const int c = i / (K + 1), k = i - c * (K + 1);
+    if (k < K) dw[c * K + k] = t; else db[c] = t;
+  }
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------------------
@@ -268,7 +274,7 @@ int launch_dwconv_raw(int precision, const void* x, const float* w, const float*
   else
     dwconv_raw_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, bias, B, T, T_out, C, K, stride, y, work);
   EC_CUDA(cudaGetLastError());
-  bn_stats_merge_kernel<<<cdiv(C, 32), 256, 0, st>>>(work, ctas, static_cast<size_t>(B) * T_out, C, sums);
+  bn_stats_merge_kernel<<<cdiv(C, 32), 1024, 0, st>>>(work, ctas, static_cast<size_t>(B) * T_out, C, sums);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -291,7 +297,7 @@ int launch_bn_swish_bwd_stats(const float* y, const float* dh, size_t rows, int 
   const int ctas = ctas_for(rows);
   bn_swish_bwd_stats_kernel<<<dim3(ctas, cdiv(C, 128)), 128, 0, st>>>(y, dh, rows, C, mean, rstd, gamma, beta, work);
   EC_CUDA(cudaGetLastError());
-  conv_partial_reduce_kernel<<<cdiv(2 * C, 32), 256, 0, st>>>(work, ctas, 2, C, sums);
+  conv_partial_reduce_kernel<<<cdiv(2 * C, 32), 1024, 0, st>>>(work, ctas, 2, C, sums);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -317,7 +323,7 @@ int launch_dwconv_bwd(int precision, const float* dy, const void* x, const float
   else
     dwconv_bwd_weight_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(dy, reinterpret_cast<const __nv_bfloat16*>(x), B, T, T_out, C, K, stride, work);
   EC_CUDA(cudaGetLastError());
-  dwconv_wgrad_reduce_kernel<<<cdiv(C * (K + 1), 256), 256, 0, st>>>(work, ctas, C, K, dw, db);
+  dwconv_wgrad_reduce_kernel<<<cdiv(C * (K + 1), 32), 1024, 0, st>>>(work, ctas, C, K, dw, db);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }

@@ -206,19 +206,19 @@ def test_train_step_graph_replay_equals_autograd_plus_torch_adam(prec):
         assert abs(la - lb) < 1e-3 * abs(la), (losses_a, results[True][0])
     sd_a, sd_b, mom = a.state_dict(), results[True][1], results[True][2]
     noise = ("convolution_module.layers.4.bias", "subsampling_module.layers.0.0.bias", "key_layer.bias", "pos_layer.bias", "pos_layer.weight")
-    worst_m, worst_v, worst_dir = 0.0, 0.0, 1.0
+    worst_m, worst_v, worst_dir = (0.0, ""), (0.0, ""), 1.0
     for n, p in a.named_parameters():
         if n.endswith(noise):
             continue
         st = opt.state[p]
-        worst_m = max(worst_m, rel_l2(mom[n][0], st["exp_avg"].reshape(-1)))
-        worst_v = max(worst_v, rel_l2(mom[n][1], st["exp_avg_sq"].reshape(-1)))
+        worst_m = max(worst_m, (rel_l2(mom[n][0], st["exp_avg"].reshape(-1)), n))
+        worst_v = max(worst_v, (rel_l2(mom[n][1], st["exp_avg_sq"].reshape(-1)), n))
         da, db = (sd_a[n] - init[n]).double().reshape(-1), (sd_b[n] - init[n]).double().reshape(-1)
         assert float(da.norm()) > 0 and float(db.norm()) > 0, n
         worst_dir = min(worst_dir, float(da @ db / (da.norm() * db.norm())))
-    print(f"\n[{prec}] losses {results[True][0]} | autograd+torch.optim {losses_a} | moments rel-L2 {worst_m:.2e} / {worst_v:.2e}, "
+    print(f"\n[{prec}] losses {results[True][0]} | autograd+torch.optim {losses_a} | moments rel-L2 {worst_m} / {worst_v}, "
           f"worst update cosine {worst_dir:.4f}")
-    assert worst_m < 2e-3 and worst_v < 4e-3, (worst_m, worst_v)
+    assert worst_m[0] < 2e-3 and worst_v[0] < 2e-3, (worst_m, worst_v)
     assert worst_dir > 0.98, worst_dir
     for k in sd_a:
         if k.endswith("num_batches_tracked"):
