@@ -466,6 +466,22 @@ def count_launches(fn):
         return None, None, {"error": repr(ex)}
 
 
+def _finish(dist, step):
+    """Leave a multi-rank run: drop the captured graphs (they hold NCCL kernels), then exit without waiting on communicator teardown."""
+    if dist is None:
+        return
+    step._graph = None
+    import gc
+    gc.collect()
+    sys.stdout.flush(); sys.stderr.flush()
+    os._exit(0)
+
+
+def _log(rank, msg):
+    if os.environ.get("EFFCONF_BENCH_VERBOSE"):
+        print(f"[bench rank {rank} t={time.perf_counter():.1f}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_train(args, rank, world, local_rank):
     from efficientconformer_b200 import ModelCTC, _lib
     from efficientconformer_b200.trainer import CTCTrainStep
@@ -473,7 +489,6 @@ def run_train(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the single JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     B, T = args.batch, args.frames
@@ -487,7 +502,9 @@ def run_train(args, rank, world, local_rank):
         return CTCTrainStep(model, TRAINING_PARAMS, precision=args.precision, use_cuda_graph=graph, sync_bn=not args.no_sync_bn,
                             dropout_seed=1234)
     use_graph = not args.no_graph
+    _log(rank, "process group ready")
     step = make_step(use_graph)
+    _log(rank, "step object built")
     mel_h = synthetic_mel(B, T, seed=1 + rank).pin_memory()
     t_out = (((T - 1) // 2 + 1 - 1) // 2 + 1 - 1) // 2 + 1
     y, y_len = synthetic_targets(torch.full((B,), t_out), V, seed=4 + rank)
@@ -514,8 +531,10 @@ def run_train(args, rank, world, local_rank):
         step = make_step(False)
         for _ in range(max(args.warmup, 3)):
             step.step(mel_d, None, y_d, yl_d); flush.zero_()
+    _log(rank, f"warm-up done ({graph_note})")
     sampler = ClockSampler(local_rank)
     barrier()
+    _log(rank, "barrier passed")
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -525,12 +544,14 @@ def run_train(args, rank, world, local_rank):
         a.record(); loss = step.step(mel_d, None, y_d, yl_d); b.record()
         losses.append(loss.clone())
     barrier()
+    _log(rank, "timed steps done")
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms)
     losses = [float(l) for l in losses]
+    _log(rank, f"ms/step {total_ms / args.steps:.3f}")
 
     # ---- end to end: every step copies its batch (mel, targets, lengths) from pinned host memory, runs the step, reads the loss back ----
     copy_stream = torch.cuda.Stream(device=dev)
@@ -565,6 +586,7 @@ def run_train(args, rank, world, local_rank):
 
     e2e_loop(3)
     barrier()
+    _log(rank, "e2e warm-up done")
     t0 = time.perf_counter()
     e2e_losses = e2e_loop(args.steps)
     torch.cuda.synchronize()
@@ -574,6 +596,7 @@ def run_train(args, rank, world, local_rank):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
     e2e_s = float(e2e_s)
+    _log(rank, "e2e done")
 
     # ---- operator profile of eager steps: CUDA events around every operator entry point, launching stream (rank 0, no collectives) ----
     prof_ops, ours_k, lib_k, lib_names = {}, None, None, {}
@@ -592,9 +615,13 @@ def run_train(args, rank, world, local_rank):
         ours_k, lib_k, lib_names = count_launches(lambda: estep.step(mel_d, None, y_d, yl_d))
         del estep
     if dist is not None:
+        # Tear-down: NCCL communicator destruction blocks while captured graphs still reference its kernels, so the graphs go first;
+        # should the destruction stall anyway, the result is already out and the process leaves without it.
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        _log(rank, "collectives done")
     if rank != 0:
+        _finish(dist, step)
         return
     pk = peaks()
     tensor_peak = pk["bf16_tflops"] * (1.0 if args.precision == "bf16" else 0.5)
@@ -658,6 +685,8 @@ def run_train(args, rank, world, local_rank):
                                "sample": f"median of 3 training steps on the first {Bs} utterances of the same batch (oracle train-mode fwd + CTC + autograd "
                                          f"backward + torch.optim.Adam), fp32 torch CPU, {torch.get_num_threads()} threads"}
     print(json.dumps(out))
+    sys.stdout.flush()
+    _finish(dist, step)
 
 
 def main():
@@ -672,6 +701,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="train", choices=["train", "forward"])
     ap.add_argument("--pdrop", type=float, default=0.1, help="dropout probability of the training step (reference config: 0.1)")
+    ap.add_argument("--watchdog", type=int, default=600, help="seconds after which a stuck run dumps its Python stacks to stderr and exits")
     ap.add_argument("--no-graph", action="store_true", help="training step: eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-sync-bn", action="store_true", help="N > 1: per-rank BatchNorm statistics (NOT the reference's SyncBatchNorm semantics)")
     args = ap.parse_args()
@@ -681,6 +711,13 @@ def main():
     if args.impl == "reference":
         (run_reference_train if args.mode == "train" else run_reference)(args, rank, world)
         return
+    if args.watchdog > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)      # a hung collective must not hang the caller: dump stacks, exit
+    # keep stdout to the single JSON line whatever the libraries print (NCCL prints its version banner to stdout)
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a B200: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     (run_train if args.mode == "train" else run_ours)(args, rank, world, local)

@@ -26,7 +26,9 @@ __device__ __forceinline__ unsigned long long site_key(const unsigned long long*
 __device__ __forceinline__ float keep_factor(unsigned long long draw, int lane, unsigned keep16, float inv_keep) {
   return ((draw >> (16 * lane)) & 0xFFFFull) < keep16 ? inv_keep : 0.f;
 }
+}  // namespace
 inline int grid_for(size_t n) { return static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16)); }
+namespace {
 }  // namespace
 
 __global__ void dropout_advance_kernel(unsigned long long* ctr) { ctr[1] += 1ull; }
@@ -247,4 +249,86 @@ extern "C" int ec_op_pack_flat(const float* const* srcs, const long long* offset
   ec::pack_flat_kernel<<<dim3(8, n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(srcs, offsets, sizes, arena);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
+}
+
+// ---- Swish fused with its dropout (feed-forward module, reference models/modules.py:388-389) --------------------------------------
+//   forward : h  = act_type(keep / (1 - p) * z * sigmoid(z))
+//   backward: dz = act_type(keep / (1 - p) * dy * d/dz (z sigmoid z))      (same mask: same (step, site, element) hash)
+namespace ec {
+template <typename T, bool kBwd>
+__global__ void __launch_bounds__(256) swish_dropout_kernel(const T* __restrict__ z, const float* __restrict__ dy, size_t n, T* __restrict__ out,
+                                                            const unsigned long long* __restrict__ ctr, unsigned site, unsigned keep16) {
+  const unsigned long long key = site_key(ctr, site);
+  const float inv_keep = 65536.f / static_cast<float>(keep16);
+  const size_t groups = (n + 3) / 4, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t g = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < groups; g += stride) {
+    const unsigned long long draw = splitmix64(key + g);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const size_t i = g * 4 + l;
+      if (i >= n) break;
+      const float zz = ActTraits<T>::from(z[i]);
+      const float s = 1.f / (1.f + __expf(-zz));
+      const float v = kBwd ? dy[i] * (s + zz * s * (1.f - s)) : zz * s;
+      out[i] = ActTraits<T>::to(keep_factor(draw, l, keep16, inv_keep) * v);
+    }
+  }
+}
+// ---- multi-tensor transposed cast: for each descriptor (src offset, rows, cols, dst offset) of the flat fp32 parameter arena,
+//      dst[c][r] = act_type(src[r][c]) in the transposed operand arena (the W^T operands of the data-gradient GEMMs, one launch) ----
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_cast_multi_kernel(const float* __restrict__ src_arena, const long long* __restrict__ desc,
+                                                                   T* __restrict__ dst_arena) {
+  __shared__ float tile[32][33];
+  const long long* d = desc + static_cast<long long>(blockIdx.y) * 4;
+  const int rows = static_cast<int>(d[1]), cols = static_cast<int>(d[2]);
+  const int tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* __restrict__ src = src_arena + d[0];
+  T* __restrict__ dst = dst_arena + d[3];
+  for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+    const int c0 = (t % tiles_c) * 32, r0 = (t / tiles_c) * 32;
+    for (int i = ty; i < 32; i += 8) {
+      const int r = r0 + i, c = c0 + tx;
+      tile[i][tx] = (r < rows && c < cols) ? src[static_cast<size_t>(r) * cols + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i, r = r0 + tx;
+      if (c < cols && r < rows) dst[static_cast<size_t>(c) * rows + r] = ActTraits<T>::to(tile[tx][i]);
+    }
+    __syncthreads();
+  }
+}
+}  // namespace ec
+extern "C" {
+int ec_op_swish_dropout(int precision, const void* z, const float* dy, size_t n, void* out, float p, const unsigned long long* counter,
+                        unsigned site, void* stream) {
+  EC_REQUIRE(z && out && counter && p >= 0.f && p < 1.f, "bad argument");
+  if (n == 0) return EC_OK;
+  const int grid = ec::grid_for((n + 3) / 4);
+  const unsigned k = ec::keep16_of(p);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  using bf = __nv_bfloat16;
+  if (precision == EC_PREC_TF32) {
+    if (dy) ec::swish_dropout_kernel<float, true><<<grid, 256, 0, st>>>(static_cast<const float*>(z), dy, n, static_cast<float*>(out), counter, site, k);
+    else ec::swish_dropout_kernel<float, false><<<grid, 256, 0, st>>>(static_cast<const float*>(z), dy, n, static_cast<float*>(out), counter, site, k);
+  } else {
+    if (dy) ec::swish_dropout_kernel<bf, true><<<grid, 256, 0, st>>>(static_cast<const bf*>(z), dy, n, static_cast<bf*>(out), counter, site, k);
+    else ec::swish_dropout_kernel<bf, false><<<grid, 256, 0, st>>>(static_cast<const bf*>(z), dy, n, static_cast<bf*>(out), counter, site, k);
+  }
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+int ec_op_transpose_cast_multi(int precision, const float* src_arena, const long long* desc, int n, int ctas_per_tensor, void* dst_arena,
+                               void* stream) {
+  EC_REQUIRE(src_arena && desc && dst_arena && n >= 0 && n <= 65535 && ctas_per_tensor >= 1, "bad argument");
+  if (n == 0) return EC_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(ctas_per_tensor, n);
+  if (precision == EC_PREC_TF32) ec::transpose_cast_multi_kernel<float><<<grid, 256, 0, st>>>(src_arena, desc, static_cast<float*>(dst_arena));
+  else ec::transpose_cast_multi_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src_arena, desc, static_cast<__nv_bfloat16*>(dst_arena));
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
+}
 }

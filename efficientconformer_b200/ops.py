@@ -471,3 +471,35 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, state, beta1, beta2, eps, weig
     """One torch.optim.Adam step over flat fp32 arenas (ec_adam_step); `state` int32[4] device = {lr bits, t, s, 0}."""
     check(lib().ec_adam_step(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), params.numel(), ptr(state), beta1, beta2, eps,
                              weight_decay, grad_scale, schedule, K, dim, warmup, stream_ptr()))
+
+
+def swish_dropout_fwd(z_act, drop, site, precision):
+    """Swish followed by the feed-forward module's first dropout, one kernel (plain Swish when p == 0)."""
+    if drop.p == 0.0:
+        return swish_fwd(z_act, precision)
+    z_act = z_act.contiguous()
+    out = torch.empty_like(z_act)
+    check(lib().ec_op_swish_dropout(_p(precision), ptr(z_act), None, z_act.numel(), ptr(out), drop.p, ptr(drop.counter), site, stream_ptr()))
+    return out
+
+
+def swish_dropout_bwd(z_act, dy, drop, site, precision):
+    """Gradient through dropout(Swish(z)) with the forward mask of `site` re-applied, one kernel."""
+    if drop.p == 0.0:
+        return swish_bwd(z_act, dy, precision)
+    z_act, dy = z_act.contiguous(), dy.float().contiguous()
+    out = torch.empty_like(z_act)
+    check(lib().ec_op_swish_dropout(_p(precision), ptr(z_act), ptr(dy), z_act.numel(), ptr(out), drop.p, ptr(drop.counter), site, stream_ptr()))
+    return out
+
+
+def cast_into(x_f32, out_act, precision):
+    """fp32 -> activation type into a preallocated tensor (the whole flat parameter arena in one launch)."""
+    check(lib().ec_op_cast(_p(precision), ptr(x_f32), ptr(out_act), x_f32.numel(), stream_ptr()))
+    return out_act
+
+
+def transpose_cast_multi(src_arena, desc_dev, n, dst_arena, precision, ctas_per_tensor=32):
+    """desc_dev int64 [n, 4] = (src offset, rows, cols, dst offset): every W^T operand of the data-gradient GEMMs in one launch."""
+    check(lib().ec_op_transpose_cast_multi(_p(precision), ptr(src_arena), ptr(desc_dev), n, ctas_per_tensor, ptr(dst_arena), stream_ptr()))
+    return dst_arena

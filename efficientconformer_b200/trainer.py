@@ -30,6 +30,7 @@ class FlatParams:
     def __init__(self, named, device):
         self.names, self.offsets, self.sizes, self.shapes = [], [], [], []
         off = 0
+        self.tensors = [p for _, p in named]
         for n, p in named:
             self.names.append(n); self.offsets.append(off); self.sizes.append(p.numel()); self.shapes.append(tuple(p.shape))
             off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
@@ -69,11 +70,101 @@ class FlatParams:
         return keep
 
 
+def _qkv_adjacent_order(named):
+    """Reorder (name, Parameter) so that the query / key / value weights of every attention module are consecutive in the arena:
+    Wq | Wk | Wv is then ONE [3D, D] matrix (no per-step concatenation) when D*D is a multiple of the arena alignment."""
+    by_name = dict(named)
+    out, used = [], set()
+    for n, p in named:
+        if n in used:
+            continue
+        out.append((n, p)); used.add(n)
+        if n.endswith("mhsa.query_layer.weight"):
+            for other in ("key", "value"):
+                k = n.replace("query_layer", f"{other}_layer")
+                if k in by_name and k not in used:
+                    out.append((k, by_name[k])); used.add(k)
+    return out
+
+
+class ArenaWeights:
+    """GEMM operands of every weight, produced from the flat fp32 parameter arena by TWO launches per step: one cast of the whole
+    arena (forward operands, [N, K]) and one multi-tensor transposed cast (data-gradient operands, [K, N]).  Views are looked up
+    by Parameter identity."""
+
+    def __init__(self, flat, precision, device):
+        self.flat = flat
+        self.pr = _lib.PRECISIONS[precision] if isinstance(precision, str) else precision
+        dt = _lib.act_dtype(self.pr)
+        self.arena = torch.zeros(flat.total, dtype=dt, device=device)
+        self.arena_t = torch.zeros(flat.total, dtype=dt, device=device)
+        self._fwd, self._bwd, self._qkv, desc = {}, {}, {}, []
+        params = dict(zip(flat.names, flat.tensors))
+        merged = set()
+        for n in flat.names:
+            if not n.endswith("mhsa.query_layer.weight"):
+                continue
+            names = [n, n.replace("query_layer", "key_layer"), n.replace("query_layer", "value_layer")]
+            i = [flat.index[x] for x in names]
+            D = flat.shapes[i[0]][0]
+            if all(flat.offsets[i[j]] == flat.offsets[i[0]] + j * D * D for j in range(3)):
+                o = flat.offsets[i[0]]
+                self._qkv[id(params[n])] = (self.arena[o:o + 3 * D * D].view(3 * D, D), self.arena_t[o:o + 3 * D * D].view(D, 3 * D),
+                                            torch.zeros(3 * D, dtype=torch.float32, device=device))
+                desc.append((o, 3 * D, D, o))
+                merged.update(names)
+        for n, o, shape in zip(flat.names, flat.offsets, flat.shapes):
+            is_matrix = len(shape) == 2 or (len(shape) == 3 and shape[-1] == 1)
+            if not is_matrix:
+                continue
+            N, K = shape[0], shape[1]
+            self._fwd[id(params[n])] = self.arena[o:o + N * K].view(N, K)
+            if n not in merged:
+                self._bwd[id(params[n])] = self.arena_t[o:o + N * K].view(K, N)
+                desc.append((o, N, K, o))
+        self.n_desc = len(desc)
+        self.desc = torch.tensor(desc, dtype=torch.int64, device=device).contiguous()
+
+    def refresh(self):
+        """Run once per step, before the forward: the parameters changed in the previous optimiser step."""
+        _ops.cast_into(self.flat.params, self.arena, self.pr)
+        _ops.transpose_cast_multi(self.flat.params, self.desc, self.n_desc, self.arena_t, self.pr)
+
+    def act(self, weight):
+        return self._fwd[id(weight)]
+
+    def act_t(self, weight):
+        return self._bwd[id(weight)]
+
+    def _qkv_entry(self, mhsa):
+        ent = self._qkv.get(id(mhsa.query_layer.weight))
+        if ent is None:
+            raise RuntimeError("Wq | Wk | Wv are not adjacent in the parameter arena (model dim not a multiple of 8?)")
+        return ent
+
+    def qkv_act(self, mhsa):
+        return self._qkv_entry(mhsa)[0]
+
+    def qkv_act_t(self, mhsa):
+        return self._qkv_entry(mhsa)[1]
+
+    def qkv_bias(self, mhsa):
+        b = self._qkv_entry(mhsa)[2]
+        D = b.numel() // 3
+        for j, layer in enumerate((mhsa.query_layer, mhsa.key_layer, mhsa.value_layer)):
+            b[j * D:(j + 1) * D].copy_(layer.bias.detach())       # device-to-device memcpy nodes
+        return b
+
+    def supports(self, encoder):
+        return all(id(b.multi_head_self_attention_module.mhsa.query_layer.weight) in self._qkv for b in encoder.blocks)
+
+
 class CTCTrainStep:
     """One optimisation step of ModelCTC on a fixed batch shape.  `training_params` is the reference config's dict
     (optimizer Adam: beta1, beta2, eps, weight_decay; lr_schedule Transformer: schedule_dim, warmup_steps, K)."""
 
-    def __init__(self, model, training_params, precision="bf16", process_group=None, sync_bn=True, use_cuda_graph=True, dropout_seed=0):
+    def __init__(self, model, training_params, precision="bf16", process_group=None, sync_bn=True, use_cuda_graph=True, dropout_seed=0,
+                 data_parallel=True):
         if training_params.get("optimizer", "Adam") != "Adam":
             raise NotImplementedError("the shipped configs train with Adam (reference models/model.py:88-93)")
         sched = training_params.get("lr_schedule", "Transformer")
@@ -83,7 +174,7 @@ class CTCTrainStep:
         self.tp = training_params
         self.precision = precision
         self.group = process_group
-        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.world = dist.get_world_size(process_group) if (data_parallel and dist.is_available() and dist.is_initialized()) else 1
         self.device = next(model.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("CTCTrainStep runs on CUDA sm_100 only")
@@ -93,8 +184,11 @@ class CTCTrainStep:
             reducer = SyncBatchNormReducer(process_group, self.device)
         self.reducer = reducer
         self.path = TrainingPath(model.encoder, model.fc, stats_reducer=reducer, dropout_seed=dropout_seed)
-        self.flat = FlatParams(self.path.param_list(), self.device)
+        self.flat = FlatParams(_qkv_adjacent_order(self.path.param_list()), self.device)
         model.encoder._drop_engines()                       # inference arenas were prepared from the old parameter storage
+        weights = ArenaWeights(self.flat, precision, self.device)
+        self.weights = weights if weights.supports(model.encoder) else None
+        self.path.weights = self.weights
         self.state = torch.zeros(4, dtype=torch.int32, device=self.device)
         if sched == "Constant":
             self.state[0:1].view(torch.float32).fill_(float(training_params["lr_value"]))
@@ -107,6 +201,8 @@ class CTCTrainStep:
 
     # ---- pieces -----------------------------------------------------------------------------------------------------------
     def _forward_backward(self, mel, mel_len, targets, target_len):
+        if self.weights is not None:
+            self.weights.refresh()
         x, logits, out_len, tape = self.path.forward(mel, mel_len, self.precision, want_logits=True)
         if out_len is None:
             out_len = torch.full((mel.shape[0],), logits.shape[1], dtype=torch.int64, device=mel.device)
@@ -172,15 +268,17 @@ class CTCTrainStep:
         torch.cuda.synchronize()
         split = self.world > 1 and self.reducer is None     # no SyncBN collectives inside: keep NCCL outside the graphs
         g1, g2 = torch.cuda.CUDAGraph(), None
+        # other threads (the NCCL watchdog) may touch the CUDA API while this thread captures
+        mode = {"capture_error_mode": "thread_local"} if self.world > 1 else {}
         with torch.no_grad():
-            with torch.cuda.graph(g1):
+            with torch.cuda.graph(g1, **mode):
                 keep = self._forward_backward(s_mel, s_len, s_y, s_yl)
                 if not split:
                     self._all_reduce()
                     self._optimizer()
             if split:
                 g2 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g2):
+                with torch.cuda.graph(g2, **mode):
                     self._optimizer()
         self._keep = keep
         self._graph = (g1, g2)

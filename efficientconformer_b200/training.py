@@ -77,6 +77,37 @@ class TrainingPath:
         self.dropout_seed = dropout_seed
         self._drop = None
         self._tables = {}
+        self.weights = None                      # optional arena-backed operand provider (trainer.ArenaWeights)
+
+    # ---- GEMM operands of the weights ----------------------------------------------------------------------------------------
+    # Default: one cast / transposed cast per weight and use.  CTCTrainStep installs a provider backed by its flat parameter arena
+    # (one cast launch and one multi-tensor transpose launch per step for all weights).
+    def _w(self, weight, pr):
+        """[N, K] operand of the forward GEMM (activation type)."""
+        if self.weights is not None:
+            return self.weights.act(weight)
+        return _ops.cast(_w2(weight), pr)
+
+    def _wt(self, weight, pr):
+        """[K, N] operand of the data-gradient GEMM dX = dY . W (activation type)."""
+        if self.weights is not None:
+            return self.weights.act_t(weight)
+        return _ops.transpose_cast(_w2(weight), pr)
+
+    def _dgrad(self, dy_act, weight, pr, residual=None):
+        return _ops.gemm(dy_act, self._wt(weight, pr), None, pr, residual=residual)[0]
+
+    def _qkv(self, mhsa, pr):
+        """([3D, D] forward operand, [3D] fp32 bias, handle for the backward) of the concatenated Q | K | V projection."""
+        if self.weights is not None:
+            return self.weights.qkv_act(mhsa), self.weights.qkv_bias(mhsa), mhsa
+        w32, b = _ops.concat_qkv(mhsa)
+        return _ops.cast(w32, pr), b, w32
+
+    def _qkv_dgrad(self, dqkv_act, handle, pr):
+        if self.weights is not None:
+            return _ops.gemm(dqkv_act, self.weights.qkv_act_t(handle), None, pr)[0]
+        return _ops.gemm(dqkv_act, _ops.transpose_cast(handle, pr), None, pr)[0]
 
     # ---- helpers ------------------------------------------------------------------------------------------------------
     def param_list(self):
@@ -119,7 +150,7 @@ class TrainingPath:
         cur_len = None
         if mel_len is not None:
             cur_len = _len_after_stride(mel_len, 2)
-        w_lin = o.cast(enc.linear.weight, pr)
+        w_lin = self._w(enc.linear.weight, pr)
         x = o.gemm(a, w_lin, enc.linear.bias, pr)[0]                           # (B*T0, D0) fp32
         site0 = drop.next_site()
         x = o.dropout_f32(x, drop, site0)
@@ -141,7 +172,7 @@ class TrainingPath:
         if want_logits:
             if self.head is None:
                 raise RuntimeError("no fc head attached")
-            w_fc = o.cast(self.head.weight, pr)
+            w_fc = self._w(self.head.weight, pr)
             logits = o.gemm(x_act_last, w_fc, self.head.bias, pr)[0].view(B, Tc, -1)
             tape["head"] = (x_act_last, w_fc)
         tape["T_out"] = Tc
@@ -152,12 +183,11 @@ class TrainingPath:
         o = _ops
         L = holder.layers
         h0 = o.layernorm(x, L[0].weight, L[0].bias, pr, want_f32=False, want_act=True)[0]
-        w1 = o.cast(L[1].weight, pr)
+        w1 = self._w(L[1].weight, pr)
         z = o.gemm(h0, w1, L[1].bias, pr, want_f32=False, want_act=True)[1]
-        s = o.swish_fwd(z, pr)
         s1 = drop.next_site()
-        s = o.dropout_act(s, drop, s1, pr)
-        w2 = o.cast(L[4].weight, pr)
+        s = o.swish_dropout_fwd(z, drop, s1, pr)
+        w2 = self._w(L[4].weight, pr)
         s2 = drop.next_site()
         if drop.p > 0.0:
             y = o.gemm(s, w2, L[4].bias, pr)[0]
@@ -175,12 +205,11 @@ class TrainingPath:
         dy = o.dropout_cast_scaled(d_out, pr, alpha, drop, s2)                 # d(W2 output) in the activation type
         grads[f"{prefix}.layers.4.weight"] = o.linear_wgrad(dy, s, pr)
         grads[f"{prefix}.layers.4.bias"] = o.colsum(dy, pr)
-        ds = o.linear_dgrad(dy, L[4].weight, pr)
-        ds = o.dropout_f32(ds, drop, s1)
-        dz = o.swish_bwd(z, ds, pr)
+        ds = self._dgrad(dy, L[4].weight, pr)
+        dz = o.swish_dropout_bwd(z, ds, drop, s1, pr)
         grads[f"{prefix}.layers.1.weight"] = o.linear_wgrad(dz, h0, pr)
         grads[f"{prefix}.layers.1.bias"] = o.colsum(dz, pr)
-        dh0 = o.linear_dgrad(dz, L[1].weight, pr)
+        dh0 = self._dgrad(dz, L[1].weight, pr)
         dx, dg, db = o.layernorm_bwd(x, dh0, L[0].weight, dx_accum=d_out)
         grads[f"{prefix}.layers.0.weight"], grads[f"{prefix}.layers.0.bias"] = dg, db
         return dx
@@ -194,14 +223,14 @@ class TrainingPath:
         # ---- attention module (reference models/modules.py:472-488, attentions.py:549-718)
         m = blk.multi_head_self_attention_module
         a_in = o.layernorm(x1, m.norm.weight, m.norm.bias, pr, want_f32=False, want_act=True)[0]
-        wqkv32, bqkv = o.concat_qkv(m.mhsa)
-        qkv = o.gemm(a_in, o.cast(wqkv32, pr), bqkv, pr, want_f32=False, want_act=True)[1]
+        wqkv, bqkv, qkv_handle = self._qkv(m.mhsa, pr)
+        qkv = o.gemm(a_in, wqkv, bqkv, pr, want_f32=False, want_act=True)[1]
         t_pad = T + (-T) % G
         R = self._table(t_pad, spec, pr, x.device)
-        wpos = o.cast(m.mhsa.pos_layer.weight, pr)
+        wpos = self._w(m.mhsa.pos_layer.weight, pr)
         E = o.gemm(R, wpos, m.mhsa.pos_layer.bias, pr, want_f32=False, want_act=True)[1]
         att = o.relpos_attention_act(qkv.view(B, T, 3 * D), E, m.mhsa.u, m.mhsa.v, cur_len, H, G, pr)
-        wo = o.cast(m.mhsa.output_layer.weight, pr)
+        wo = self._w(m.mhsa.output_layer.weight, pr)
         s_att = drop.next_site()
         if drop.p > 0.0:
             y = o.gemm(att.view(B * T, D), wo, m.mhsa.output_layer.bias, pr)[0]
@@ -211,7 +240,7 @@ class TrainingPath:
         # ---- convolution module (reference models/modules.py:507-525) + block residual (blocks.py:98-114,129)
         Lc = blk.convolution_module.layers
         c_in = o.layernorm(x2, Lc[0].weight, Lc[0].bias, pr, want_f32=False, want_act=True)[0]
-        wpw1 = o.cast(_w2(Lc[2].weight), pr)
+        wpw1 = self._w(Lc[2].weight, pr)
         zg = o.gemm(c_in, wpw1, Lc[2].bias, pr, want_f32=False, want_act=True)[1]
         gl = o.glu_fwd(zg, pr)
         h, dw_saved = o.DwConvTrain.forward(gl.view(B, T, De), Lc[4].weight, Lc[4].bias, Lc[5].weight, Lc[5].bias, Lc[5].running_mean,
@@ -221,11 +250,11 @@ class TrainingPath:
         xs = None
         if spec.has_conv_res_proj:
             xs = o.strided_rows(x2.view(B, T, D), st, pr).view(B * To, D)
-            wres = o.cast(_w2(blk.conv_res[1].weight), pr)
+            wres = self._w(blk.conv_res[1].weight, pr)
             res = o.gemm(xs, wres, blk.conv_res[1].bias, pr)[0]
         else:
             res = x2
-        wpw2 = o.cast(_w2(Lc[7].weight), pr)
+        wpw2 = self._w(Lc[7].weight, pr)
         s_conv = drop.next_site()
         if drop.p > 0.0:
             y = o.gemm(h.view(B * To, De), wpw2, Lc[7].bias, pr)[0]
@@ -234,7 +263,7 @@ class TrainingPath:
             x3 = o.gemm(h.view(B * To, De), wpw2, Lc[7].bias, pr, residual=res)[0]
         x4, ffn2 = self._ffn_forward(blk.feed_forward_module2, x3, pr, drop)
         x_act, x5 = o.layernorm(x4, blk.norm.weight, blk.norm.bias, pr, want_f32=True, want_act=want_act_out)
-        tape = dict(ffn1=ffn1, x1=x1, a_in=a_in, qkv=qkv, wqkv32=wqkv32, E=E, R=R, att=att, cur_len=cur_len, s_att=s_att, x2=x2, c_in=c_in, zg=zg,
+        tape = dict(ffn1=ffn1, x1=x1, a_in=a_in, qkv=qkv, qkv_handle=qkv_handle, E=E, R=R, att=att, cur_len=cur_len, s_att=s_att, x2=x2, c_in=c_in, zg=zg,
                     h=h, dw_saved=dw_saved, xs=xs, s_conv=s_conv, ffn2=ffn2, x4=x4, T=T, To=To)
         return x5, To, tape, x_act
 
@@ -254,7 +283,7 @@ class TrainingPath:
             dl = o.cast(d_logits.reshape(-1, d_logits.shape[-1]), pr)
             grads["fc.weight"] = o.linear_wgrad(dl, x_act, pr)
             grads["fc.bias"] = o.colsum(dl, pr)
-            dx = o.linear_dgrad(dl, self.head.weight, pr, residual=dx)
+            dx = self._dgrad(dl, self.head.weight, pr, residual=dx)
         if dx is None:
             raise RuntimeError("backward needs a gradient for the encoder output or the logits")
         for i in reversed(range(len(self.specs))):
@@ -263,7 +292,7 @@ class TrainingPath:
         d_act = o.dropout_cast_scaled(dx, pr, 1.0, self._drop, site0)
         grads["encoder.linear.weight"] = o.linear_wgrad(d_act, a, pr)
         grads["encoder.linear.bias"] = o.colsum(d_act, pr)
-        da = o.linear_dgrad(d_act, enc.linear.weight, pr)
+        da = self._dgrad(d_act, enc.linear.weight, pr)
         dw, db, dgam, dbet = o.SubsampleTrain.backward(da, sub_saved, reduce_stats=self.stats_reducer)
         p = "encoder.subsampling_module.layers.0"
         grads[f"{p}.0.weight"], grads[f"{p}.0.bias"], grads[f"{p}.1.weight"], grads[f"{p}.1.bias"] = dw, db, dgam, dbet
@@ -285,20 +314,20 @@ class TrainingPath:
         h2 = t["h"].view(B * To, De)
         grads[f"{c}.7.weight"] = o.linear_wgrad(dy, h2, pr).view(De, De, 1)
         grads[f"{c}.7.bias"] = o.colsum(dy, pr)
-        dh = o.linear_dgrad(dy, _w2(Lc[7].weight), pr)
+        dh = self._dgrad(dy, Lc[7].weight, pr)
         dgl, dw_dw, db_dw, dgam, dbet = o.DwConvTrain.backward(dh.view(B, To, De), t["dw_saved"], reduce_stats=self.stats_reducer)
         grads[f"{c}.4.weight"], grads[f"{c}.4.bias"] = dw_dw.view(De, 1, -1), db_dw
         grads[f"{c}.5.weight"], grads[f"{c}.5.bias"] = dgam, dbet
         dzg = o.glu_bwd(t["zg"], dgl.view(B * T, De), pr)
         grads[f"{c}.2.weight"] = o.linear_wgrad(dzg, t["c_in"], pr).view(2 * De, D, 1)
         grads[f"{c}.2.bias"] = o.colsum(dzg, pr)
-        dc_in = o.linear_dgrad(dzg, _w2(Lc[2].weight), pr)
+        dc_in = self._dgrad(dzg, Lc[2].weight, pr)
         if spec.has_conv_res_proj:
             # the residual branch sees the un-dropped gradient dx3
             dres = o.cast(dx3, pr) if drop.p > 0.0 else dy
             grads[f"{p}.conv_res.1.weight"] = o.linear_wgrad(dres, t["xs"], pr).view(De, D, 1)
             grads[f"{p}.conv_res.1.bias"] = o.colsum(dres, pr)
-            dxs = o.linear_dgrad(dres, _w2(blk.conv_res[1].weight), pr)
+            dxs = self._dgrad(dres, blk.conv_res[1].weight, pr)
             acc = o.zeros_f32(B * T, D, dx3.device)
             o.strided_rows_bwd(dxs.view(B, To, D), acc.view(B, T, D), st)
         else:
@@ -312,7 +341,7 @@ class TrainingPath:
         att2 = t["att"].view(B * T, D)
         grads[f"{a}.mhsa.output_layer.weight"] = o.linear_wgrad(do, att2, pr)
         grads[f"{a}.mhsa.output_layer.bias"] = o.colsum(do, pr)
-        datt = o.linear_dgrad(do, m.mhsa.output_layer.weight, pr)
+        datt = self._dgrad(do, m.mhsa.output_layer.weight, pr)
         dqkv, dE, du, dv = o.relpos_attention_bwd(t["qkv"].view(B, T, 3 * D), t["E"], m.mhsa.u, m.mhsa.v, t["cur_len"], H, G,
                                                   datt.view(B, T, D), pr)
         grads[f"{a}.mhsa.u"], grads[f"{a}.mhsa.v"] = du, dv
@@ -325,7 +354,7 @@ class TrainingPath:
         for j, nm in enumerate(("query", "key", "value")):
             grads[f"{a}.mhsa.{nm}_layer.weight"] = dwqkv[j * D:(j + 1) * D]
             grads[f"{a}.mhsa.{nm}_layer.bias"] = dbqkv[j * D:(j + 1) * D]
-        da_in = o.linear_dgrad(dqkv_act, t["wqkv32"], pr)
+        da_in = self._qkv_dgrad(dqkv_act, t["qkv_handle"], pr)
         dx1, dg, db = o.layernorm_bwd(t["x1"], da_in, m.norm.weight, dx_accum=dx2)
         grads[f"{a}.norm.weight"], grads[f"{a}.norm.bias"] = dg, db
         return self._ffn_backward(blk.feed_forward_module1, t["ffn1"], dx1, pr, grads, f"{p}.feed_forward_module1")

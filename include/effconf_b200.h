@@ -237,6 +237,14 @@ int ec_op_stats_merge_ranks(const float* gathered, const float* counts, int worl
 /* gather n separately allocated fp32 tensors (device pointer table srcs[n], element offsets[n] into the arena, sizes[n]) into one
  * flat arena: the gradient bucket that the data-parallel all-reduce (reference DistributedDataParallel, models/model_ctc.py:73-75)
  * and ec_adam_step operate on. */
+/* Swish fused with the dropout that follows it in the feed-forward module: dy == NULL: out = keep/(1-p) * z*sigmoid(z);
+ * dy != NULL (backward): out = keep/(1-p) * dy * d/dz(z*sigmoid(z)); z / out in the activation type, same mask as ec_op_dropout at `site`. */
+int ec_op_swish_dropout(int precision, const void* z, const float* dy, size_t n, void* out, float p, const unsigned long long* counter,
+                        unsigned site, void* stream);
+/* W^T operands of all data-gradient GEMMs in one launch: desc[n][4] = {src element offset, rows, cols, dst element offset} over the flat
+ * fp32 parameter arena; dst[c][r] = act_type(src[r][c]). */
+int ec_op_transpose_cast_multi(int precision, const float* src_arena, const long long* desc, int n, int ctas_per_tensor, void* dst_arena,
+                               void* stream);
 int ec_op_pack_flat(const float* const* srcs, const long long* offsets, const long long* sizes, int n, float* arena, void* stream);
 
 /* ---- single-operator entry points (unit parity tests; same kernels the engine launches) ---------------------------- */

@@ -229,3 +229,17 @@ def stats_merge_ranks(gathered, counts, out):
     m2 = g[:, 1].sum(0) + (n[:, None] * (g[:, 0] - mean) ** 2).sum(0)
     out[0].copy_(mean.to(out.dtype)); out[1].copy_(m2.to(out.dtype))
     return out
+
+
+def swish_dropout_fwd(z, drop, site, precision):
+    assert drop.p == 0.0
+    return swish_fwd(z, precision)
+
+
+def swish_dropout_bwd(z, dy, drop, site, precision):
+    assert drop.p == 0.0
+    return swish_bwd(z, dy, precision)
+
+
+def transpose_cast(w, precision):
+    return _d(w).t().contiguous()

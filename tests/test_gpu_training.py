@@ -115,6 +115,45 @@ def test_dropout_kernels_statistics_and_mask_consistency():
     assert float(cols.min()) > 0.85 and float(cols.max()) < 0.95
 
 
+def test_fused_swish_dropout_and_arena_operand_kernels():
+    """Swish fused with its dropout (forward and backward) equals the two-kernel sequence with the same mask; the one-launch
+    arena cast / multi-tensor transposed cast equal the per-tensor operators."""
+    from efficientconformer_b200 import ops, trainer
+    from efficientconformer_b200.training import DropoutState, TrainingPath
+    drop = DropoutState(0.1, DEV, seed=3)
+    drop.begin_step()
+    g = torch.Generator().manual_seed(8)
+    z32, dy = 2 * torch.randn(4001, 480, generator=g).to(DEV), torch.randn(4001, 480, generator=g).to(DEV)
+    for prec in ("tf32", "bf16"):
+        z = ops.cast(z32, prec)
+        fused = ops.swish_dropout_fwd(z, drop, 5, prec)
+        ref = ops.dropout_act(ops.swish_fwd(z, prec), drop, 5, prec)
+        assert torch.equal(fused == 0, ref == 0)
+        assert rel_l2(fused.float(), ref.float()) < (1e-3 if prec == "tf32" else 6e-3)
+        fb = ops.swish_dropout_bwd(z, dy, drop, 5, prec)
+        rb = ops.swish_bwd(z, ops.dropout_f32(dy, drop, 5), prec)
+        assert torch.equal(fb == 0, rb == 0)
+        assert rel_l2(fb.float(), rb.float()) < (1e-3 if prec == "tf32" else 6e-3)
+    # arena operands
+    model = _model("bf16", 0.0, _small_params(), vocab=32)
+    path = TrainingPath(model.encoder, model.fc)
+    flat = trainer.FlatParams(trainer._qkv_adjacent_order(path.param_list()), DEV)
+    for prec in ("tf32", "bf16"):
+        w = trainer.ArenaWeights(flat, prec, DEV)
+        assert w.supports(model.encoder)
+        w.refresh()
+        blk = model.encoder.blocks[1]
+        for weight in (blk.feed_forward_module1.layers[1].weight, blk.convolution_module.layers[2].weight, blk.conv_res[1].weight,
+                       model.encoder.linear.weight, model.fc.weight, blk.multi_head_self_attention_module.mhsa.output_layer.weight):
+            w2 = weight.detach().reshape(weight.shape[0], -1)
+            assert torch.equal(w.act(weight), ops.cast(w2, prec))
+            assert torch.equal(w.act_t(weight), ops.transpose_cast(w2, prec))
+        mh = blk.multi_head_self_attention_module.mhsa
+        w32, b = ops.concat_qkv(mh)
+        assert torch.equal(w.qkv_act(mh), ops.cast(w32, prec)) and torch.equal(w.qkv_act_t(mh), ops.transpose_cast(w32, prec))
+        assert torch.equal(w.qkv_bias(mh), b)
+
+
 def test_flat_adam_matches_torch_adam_with_transformer_schedule():
     """ec_adam_step over a flat arena == torch.optim.Adam(lr=0 at first, then the reference's Transformer schedule,
     models/schedules.py:99-123) on the same gradients (fp64 CPU reference)."""
@@ -243,3 +282,69 @@ def test_training_with_dropout_is_reproducible_and_finite():
     assert runs[0] == runs[1]                                                 # same seed: same masks, forward and backward
     assert runs[0] != runs[2]
     assert len(set(runs[0])) == 4                                             # fresh masks every replay + parameters moving
+
+
+# ---- two GPUs: utterance shards + SyncBatchNorm + one all-reduced gradient bucket == the single-GPU step on the whole batch ----------
+def _dp_worker(rank, world, port, prec, graph, q):
+    import torch.distributed as dist
+    from efficientconformer_b200.trainer import CTCTrainStep
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        sp = _small_params()
+        tp = dict(optimizer="Adam", beta1=0.9, beta2=0.98, eps=1e-9, weight_decay=1e-6, lr_schedule="Transformer", schedule_dim=96,
+                  warmup_steps=300, K=2)
+        B, T, V2 = 4, 120, 32
+        mels = [synthetic_mel(B, T, seed=60 + i) for i in range(3)]
+        y, yl = synthetic_targets(torch.full((B,), 30), V2, seed=4)
+        lo, hi = rank * (B // world), (rank + 1) * (B // world)
+
+        def run(data_parallel, sl):
+            from efficientconformer_b200.model_ctc import ModelCTC
+            p = dict(sp); p["Pdrop"] = 0.0
+            m = ModelCTC(p, {"vocab_size": V2}, precision=prec)
+            m.load_state_dict(seeded_state_dict(sp, V2, seed=0, prefix_encoder="encoder."), strict=False)
+            m = m.to(dev).train()
+            st = CTCTrainStep(m, tp, precision=prec, use_cuda_graph=graph, sync_bn=True, data_parallel=data_parallel)
+            ls = [float(st.step(mel[sl].to(dev), None, y[sl].to(dev), yl[sl].to(dev))) for mel in mels]
+            return ls, st.flat.exp_avg.clone().cpu(), st.flat.params.clone().cpu(), {k: v.clone().cpu() for k, v in m.state_dict().items() if "running" in k}
+        dp = run(True, slice(lo, hi))
+        out = {"rank": rank, "dp": dp}
+        if rank == 0:
+            out["full"] = run(False, slice(0, B))            # the whole batch on one GPU, no collectives
+        q.put(out)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_two_gpu_data_parallel_step_matches_single_gpu_full_batch(graph):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, 29761 + int(graph), "tf32", graph, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(2):
+        o = q.get(timeout=300)
+        res[o["rank"]] = o
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    l0, m0, p0, s0 = res[0]["dp"]
+    l1, m1, p1, s1 = res[1]["dp"]
+    lf, mf, pf, sf = res[0]["full"]
+    assert torch.equal(p0, p1) and torch.equal(m0, m1)                        # replicas stay identical
+    for k in s0:
+        assert torch.equal(s0[k], s1[k]), k                                   # SyncBatchNorm: same running statistics on every rank
+        assert rel_l2(s0[k], sf[k]) < 1e-4, k                                 # == statistics of the whole batch
+    for a, b, f in zip(l0, l1, lf):
+        assert abs(0.5 * (a + b) - f) < 1e-4 * abs(f), (l0, l1, lf)           # mean of the shard losses == loss of the whole batch
+    print(f"\n[2 GPUs graph={graph}] shard losses {l0} {l1} | whole batch {lf} | exp_avg rel-L2 {rel_l2(m0, mf):.2e}")
+    assert rel_l2(m0, mf) < 2e-3
