@@ -30,15 +30,15 @@ __device__ __forceinline__ void cta_rows(size_t rows, size_t& r0, size_t& r1) {
 
 // ---- forward: raw depthwise conv + statistics ------------------------------------------------------------------------------
 // thread = channel (blockIdx.y tiles channels by 128), CTA = a contiguous range of output frames (flattened b*T_out + t)
-template <typename T>
-__global__ void __launch_bounds__(128) dwconv_raw_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+template <typename T, int KT>
+__global__ void __launch_bounds__(128) dwconv_raw_kernel_(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                                          int B, int T_in, int T_out, int C, int K, int stride, float* __restrict__ y,
                                                          float* __restrict__ partial /* [gridDim.x][2][C] */) {
   const int c = blockIdx.y * 128 + threadIdx.x;
   if (c >= C) return;
-  float wk[kMaxTaps];
+  float wk[KT];
 #pragma unroll
-  for (int k = 0; k < kMaxTaps; ++k) wk[k] = k < K ? w[c * K + k] : 0.f;
+  for (int k = 0; k < KT; ++k) wk[k] = k < K ? w[c * K + k] : 0.f;
   const float bc = bias[c];
   const int pad = (K - 1) / 2;
   size_t r0, r1; cta_rows(static_cast<size_t>(B) * T_out, r0, r1);
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(128) dwconv_raw_kernel(const T* __restrict__ x
     const T* xb = x + static_cast<size_t>(b) * T_in * C + c;
     float acc = bc;
 #pragma unroll
-    for (int k = 0; k < kMaxTaps; ++k) {
+    for (int k = 0; k < KT; ++k) {
       const int ti = t * stride + k - pad;
       if (k < K && ti >= 0 && ti < T_in) acc = fmaf(wk[k], ActTraits<T>::from(xb[static_cast<size_t>(ti) * C]), acc);
     }
@@ -194,13 +194,14 @@ __global__ void __launch_bounds__(256) bn_swish_bwd_apply_kernel(const float* __
 }
 
 // dx[b, ti, c] = sum_k w[c,k] * dy[b, to, c],  to = (ti + pad - k) / s when divisible and 0 <= to < T_out
+template <int KT>
 __global__ void __launch_bounds__(128) dwconv_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, int B, int T_in,
                                                               int T_out, int C, int K, int stride, float* __restrict__ dx) {
   const int c = blockIdx.y * 128 + threadIdx.x;
   if (c >= C) return;
-  float wk[kMaxTaps];
+  float wk[KT];
 #pragma unroll
-  for (int k = 0; k < kMaxTaps; ++k) wk[k] = k < K ? w[c * K + k] : 0.f;
+  for (int k = 0; k < KT; ++k) wk[k] = k < K ? w[c * K + k] : 0.f;
   const int pad = (K - 1) / 2;
   size_t r0, r1; cta_rows(static_cast<size_t>(B) * T_in, r0, r1);
   for (size_t r = r0; r < r1; ++r) {
@@ -208,43 +209,43 @@ __global__ void __launch_bounds__(128) dwconv_bwd_data_kernel(const float* __res
     const float* db = dy + static_cast<size_t>(b) * T_out * C + c;
     float acc = 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxTaps; ++k) {
+    for (int k = 0; k < KT; ++k) {
       const int num = ti + pad - k;
-      if (k < K && num >= 0 && num % stride == 0) {
-        const int to = num / stride;
-        if (to < T_out) acc = fmaf(wk[k], db[static_cast<size_t>(to) * C], acc);
-      }
+      // stride is 1 or 2 (checked by the launcher): no integer division in the tap loop
+      const bool hit = k < K && num >= 0 && (stride == 1 || (num & 1) == 0);
+      const int to = stride == 1 ? num : (num >> 1);
+      if (hit && to < T_out) acc = fmaf(wk[k], db[static_cast<size_t>(to) * C], acc);
     }
     dx[r * C + c] = acc;
   }
 }
 
 // partial[cta][c][k] = sum over this CTA's output frames of dy * x[t*s + k - pad];  partial[cta][c][K] = sum dy
-template <typename T>
+template <typename T, int KT>
 __global__ void __launch_bounds__(128) dwconv_bwd_weight_kernel(const float* __restrict__ dy, const T* __restrict__ x, int B, int T_in, int T_out,
                                                                 int C, int K, int stride, float* __restrict__ partial) {
   const int c = blockIdx.y * 128 + threadIdx.x;
   if (c >= C) return;
   const int pad = (K - 1) / 2;
-  float acc[kMaxTaps + 1];
+  float acc[KT + 1];
 #pragma unroll
-  for (int k = 0; k <= kMaxTaps; ++k) acc[k] = 0.f;
+  for (int k = 0; k <= KT; ++k) acc[k] = 0.f;
   size_t r0, r1; cta_rows(static_cast<size_t>(B) * T_out, r0, r1);
   for (size_t r = r0; r < r1; ++r) {
     const int b = static_cast<int>(r / T_out), t = static_cast<int>(r - static_cast<size_t>(b) * T_out);
     const T* xb = x + static_cast<size_t>(b) * T_in * C + c;
     const float d = dy[r * C + c];
-    acc[kMaxTaps] += d;
+    acc[KT] += d;
 #pragma unroll
-    for (int k = 0; k < kMaxTaps; ++k) {
+    for (int k = 0; k < KT; ++k) {
       const int ti = t * stride + k - pad;
       if (k < K && ti >= 0 && ti < T_in) acc[k] = fmaf(d, ActTraits<T>::from(xb[static_cast<size_t>(ti) * C]), acc[k]);
     }
   }
   float* out = partial + (static_cast<size_t>(blockIdx.x) * C + c) * (K + 1);
 #pragma unroll
-  for (int k = 0; k < kMaxTaps; ++k) if (k < K) out[k] = acc[k];
-  out[K] = acc[kMaxTaps];
+  for (int k = 0; k < KT; ++k) if (k < K) out[k] = acc[k];
+  out[K] = acc[KT];
 }
 // dw[c][k] / db[c] from the partials (chunked fixed-order sum, see chunked_sum_32x32)
 __global__ void __launch_bounds__(1024) dwconv_wgrad_reduce_kernel(const float* __restrict__ partial, int n_partial, int C, int K,
@@ -269,10 +270,15 @@ int launch_dwconv_raw(int precision, const void* x, const float* w, const float*
   const int T_out = (T - 1) / stride + 1;
   const int ctas = ctas_for(static_cast<size_t>(B) * T_out);
   dim3 grid(ctas, cdiv(C, 128));
-  if (precision == EC_PREC_TF32)
-    dwconv_raw_kernel<float><<<grid, 128, 0, st>>>(reinterpret_cast<const float*>(x), w, bias, B, T, T_out, C, K, stride, y, work);
-  else
-    dwconv_raw_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, bias, B, T, T_out, C, K, stride, y, work);
+  const bool small = K <= 15;                                  // tap loops are fully unrolled: 15-tap (Efficient Conformer) or 31-tap instances
+  const float* xf = reinterpret_cast<const float*>(x); const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  if (precision == EC_PREC_TF32) {
+    if (small) dwconv_raw_kernel_<float, 15><<<grid, 128, 0, st>>>(xf, w, bias, B, T, T_out, C, K, stride, y, work);
+    else dwconv_raw_kernel_<float, 31><<<grid, 128, 0, st>>>(xf, w, bias, B, T, T_out, C, K, stride, y, work);
+  } else {
+    if (small) dwconv_raw_kernel_<__nv_bfloat16, 15><<<grid, 128, 0, st>>>(xb, w, bias, B, T, T_out, C, K, stride, y, work);
+    else dwconv_raw_kernel_<__nv_bfloat16, 31><<<grid, 128, 0, st>>>(xb, w, bias, B, T, T_out, C, K, stride, y, work);
+  }
   EC_CUDA(cudaGetLastError());
   bn_stats_merge_kernel<<<cdiv(C, 32), 1024, 0, st>>>(work, ctas, static_cast<size_t>(B) * T_out, C, sums);
   EC_CUDA(cudaGetLastError());
@@ -313,15 +319,21 @@ int launch_dwconv_bwd(int precision, const float* dy, const void* x, const float
   EC_REQUIRE(K % 2 == 1 && K <= kMaxTaps && (stride == 1 || stride == 2), "depthwise conv: odd k <= 31, stride 1 or 2");
   const int T_out = (T - 1) / stride + 1;
   if (dx != nullptr) {
-    dwconv_bwd_data_kernel<<<dim3(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(B) * T, 148 * 32)), cdiv(C, 128)), 128, 0, st>>>(dy, w, B, T, T_out, C, K, stride, dx);
+    const dim3 gd(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(B) * T, 148 * 32)), cdiv(C, 128));
+    if (K <= 15) dwconv_bwd_data_kernel<15><<<gd, 128, 0, st>>>(dy, w, B, T, T_out, C, K, stride, dx);
+    else dwconv_bwd_data_kernel<31><<<gd, 128, 0, st>>>(dy, w, B, T, T_out, C, K, stride, dx);
     EC_CUDA(cudaGetLastError());
   }
   const int ctas = ctas_for(static_cast<size_t>(B) * T_out);
   dim3 grid(ctas, cdiv(C, 128));
-  if (precision == EC_PREC_TF32)
-    dwconv_bwd_weight_kernel<float><<<grid, 128, 0, st>>>(dy, reinterpret_cast<const float*>(x), B, T, T_out, C, K, stride, work);
-  else
-    dwconv_bwd_weight_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(dy, reinterpret_cast<const __nv_bfloat16*>(x), B, T, T_out, C, K, stride, work);
+  const float* xf = reinterpret_cast<const float*>(x); const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  if (precision == EC_PREC_TF32) {
+    if (K <= 15) dwconv_bwd_weight_kernel<float, 15><<<grid, 128, 0, st>>>(dy, xf, B, T, T_out, C, K, stride, work);
+    else dwconv_bwd_weight_kernel<float, 31><<<grid, 128, 0, st>>>(dy, xf, B, T, T_out, C, K, stride, work);
+  } else {
+    if (K <= 15) dwconv_bwd_weight_kernel<__nv_bfloat16, 15><<<grid, 128, 0, st>>>(dy, xb, B, T, T_out, C, K, stride, work);
+    else dwconv_bwd_weight_kernel<__nv_bfloat16, 31><<<grid, 128, 0, st>>>(dy, xb, B, T, T_out, C, K, stride, work);
+  }
   EC_CUDA(cudaGetLastError());
   dwconv_wgrad_reduce_kernel<<<cdiv(C * (K + 1), 32), 1024, 0, st>>>(work, ctas, C, K, dw, db);
   EC_CUDA(cudaGetLastError());

@@ -322,7 +322,11 @@ def test_other_shipped_configs_against_reference_golden(golden_dir, case, precis
 def test_no_fallback_paths(sd):
     from efficientconformer_b200 import ConformerEncoder
     enc = ConformerEncoder(P)
-    with pytest.raises(NotImplementedError):
-        enc.train().to(DEV).forward_mel(torch.zeros(1, 80, 16, device=DEV))
     with pytest.raises(RuntimeError):
         enc.eval().forward_mel(torch.zeros(1, 80, 16))       # CPU tensor: no CPU path in the product
+    with pytest.raises(RuntimeError):
+        enc.train().forward_mel(torch.zeros(1, 80, 16))      # ... in either mode
+    from efficientconformer_b200.config import SHIPPED_ENCODER_PARAMS
+    two_layer = ConformerEncoder(SHIPPED_ENCODER_PARAMS["ConformerCTCSmall"][0]).to(DEV).train()
+    with pytest.raises(NotImplementedError):                 # unsupported training front end raises instead of computing something else
+        two_layer.forward_mel(torch.zeros(1, 80, 16, device=DEV))
