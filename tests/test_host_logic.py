@@ -99,3 +99,64 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src, f
+
+
+def test_flat_parameter_arena_and_operand_views_bookkeeping():
+    """Host side of the native training step (efficientconformer_b200/trainer.py), no GPU: the flat arena keeps every parameter's
+    values and state_dict name, Wq | Wk | Wv become one contiguous [3D, D] matrix, every GEMM weight gets a forward and a
+    transposed operand view at its own offset, and the descriptor table of the multi-tensor transpose covers them exactly once."""
+    from efficientconformer_b200.model_ctc import ModelCTC
+    from efficientconformer_b200 import trainer
+    from efficientconformer_b200.training import TrainingPath
+    torch.manual_seed(0)
+    m = ModelCTC(P, {"vocab_size": V})
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    path = TrainingPath(m.encoder, m.fc)
+    named = trainer._qkv_adjacent_order(path.param_list())
+    assert sorted(n for n, _ in named) == sorted(n for n, _ in path.param_list())
+    flat = trainer.FlatParams(named, "cpu")
+    after = m.state_dict()
+    assert list(after) == list(before) and all(torch.equal(after[k], before[k]) for k in before)      # same names, same values
+    assert flat.total % 64 == 0 and all(o % 64 == 0 for o in flat.offsets)
+    for n, p in named:                                                                             # parameters alias the arena
+        i = flat.index[n]
+        assert p.data_ptr() == flat.params[flat.offsets[i]:].data_ptr() and tuple(p.shape) == flat.shapes[i]
+    with torch.no_grad():
+        flat.params.add_(1.0)                                                                      # an optimiser step on the arena ...
+    assert torch.equal(m.state_dict()["fc.bias"], before["fc.bias"] + 1.0)                         # ... is visible through the modules
+    w = trainer.ArenaWeights(flat, "bf16", "cpu")
+    assert w.supports(m.encoder) and len(w._qkv) == len(m.encoder.blocks)
+    covered = torch.zeros(flat.total, dtype=torch.int32)
+    for o, rows, cols, dst in w.desc.tolist():
+        assert o == dst
+        covered[o:o + rows * cols] += 1
+    assert int(covered.max()) == 1                                                                 # no tensor transposed twice
+    blk = m.encoder.blocks[4]
+    mh = blk.multi_head_self_attention_module.mhsa
+    D = mh.query_layer.weight.shape[0]
+    assert w.qkv_act(mh).shape == (3 * D, D) and w.qkv_act_t(mh).shape == (D, 3 * D)
+    assert w.qkv_act(mh).data_ptr() == w.act(mh.query_layer.weight).data_ptr()
+    assert w.act(mh.key_layer.weight).data_ptr() == w.qkv_act(mh)[D:].data_ptr()
+    for weight in (blk.conv_res[1].weight, blk.convolution_module.layers[2].weight, m.encoder.linear.weight, m.fc.weight):
+        N, K = weight.shape[0], weight.numel() // weight.shape[0]
+        assert w.act(weight).shape == (N, K) and w.act_t(weight).shape == (K, N)
+    with pytest.raises(KeyError):
+        w.act(blk.convolution_module.layers[4].weight)                                             # the depthwise taps are not a GEMM operand
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours) in both modes on a tiny shape: one JSON line with
+    the contract keys."""
+    import subprocess
+    import sys
+    for mode in ("train", "forward"):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--mode", mode, "--steps", "1", "--warmup", "1",
+                            "--batch", "2", "--frames", "120"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+        assert len(lines) == 1
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and d["metric"] == "encoder_mel_frames_per_sec" and d["unit"] == "frames/s" and d["value"] > 0
+        assert d["higher_is_better"] is True and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+        assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        assert "workload" in d["config"] and d["steps"] == 1
