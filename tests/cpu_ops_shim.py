@@ -127,55 +127,89 @@ def relpos_attention_bwd(qkv_act, E_act, u, v, x_len, heads, group, d_out, preci
     return tuple(t.grad for t in leaves)
 
 
+class _StagedBatchNorm:
+    """Train-mode BatchNorm + Swish in the same STAGES as the CUDA operators (raw statistics -> optional cross-rank exchange ->
+    normalise; backward sums -> optional exchange -> apply), so that the SyncBatchNorm protocol of efficientconformer_b200/distributed.py
+    can be exercised end to end over gloo.  `y` is [rows, C] (channel last); without a reducer this equals F.batch_norm(training=True)."""
+
+    @staticmethod
+    def forward(y, gamma, beta, running_mean, running_var, eps, momentum, reduce_stats):
+        rows = y.shape[0]
+        mean = y.mean(0)
+        stats = torch.stack([mean, ((y - mean) ** 2).sum(0)]).to(torch.float32)       # the exchange runs on fp32 (mean, M2) pairs
+        count = float(rows)
+        if reduce_stats is not None:
+            count = reduce_stats.forward_stats(stats, count)
+            mean, m2 = stats[0].to(DT), stats[1].to(DT)
+        else:
+            mean, m2 = mean, ((y - mean) ** 2).sum(0)
+        var = m2 / count
+        rstd = 1.0 / torch.sqrt(var + eps)
+        running_mean.copy_(((1 - momentum) * _d(running_mean) + momentum * mean).to(running_mean.dtype))
+        running_var.copy_(((1 - momentum) * _d(running_var) + momentum * var * (count / max(count - 1.0, 1.0))).to(running_var.dtype))
+        xhat = (y - mean) * rstd
+        z = xhat * gamma + beta
+        return z * torch.sigmoid(z), (xhat, z, rstd, gamma, count)
+
+    @staticmethod
+    def backward(dh, saved, reduce_stats):
+        xhat, z, rstd, gamma, count = saved
+        s = torch.sigmoid(z)
+        dz = dh * (s + z * s * (1 - s))
+        sums = torch.stack([dz.sum(0), (dz * xhat).sum(0)]).to(torch.float32)
+        dbeta, dgamma = sums[0].to(DT).clone(), sums[1].to(DT).clone()                 # this rank's parameter gradients (local sums)
+        if reduce_stats is not None:
+            reduce_stats.backward_sums(sums)
+        g = sums.to(DT)
+        dy = gamma * rstd * (dz - g[0] / count - xhat * g[1] / count)
+        return dy, dgamma, dbeta
+
+
 class DwConvTrain:
     @staticmethod
     def forward(x_act, w, b, gamma, beta, running_mean, running_var, stride, precision, eps=1e-5, momentum=0.1, reduce_stats=None):
-        assert reduce_stats is None
-        leaves = [_d(t).clone().requires_grad_(True) for t in (x_act, w, b, gamma, beta)]
-        xr, wr, br, gr, ber = leaves
-        k = w.shape[-1]
-        C = w.shape[0]
-        rm, rv = _d(running_mean).clone(), _d(running_var).clone()
+        xr, wr, br = [_d(t).clone().requires_grad_(True) for t in (x_act, w, b)]
+        k, C = w.shape[-1], w.shape[0]
         with torch.enable_grad():
             conv = F.conv1d(F.pad(xr.transpose(1, 2), ((k - 1) // 2, (k - 1) // 2)), wr.reshape(C, 1, k), br, stride=stride, groups=C)
-            bn = F.batch_norm(conv, rm, rv, gr, ber, training=True, momentum=momentum, eps=eps)
-            out = (bn * torch.sigmoid(bn)).transpose(1, 2)
-        running_mean.copy_(rm.to(running_mean.dtype)); running_var.copy_(rv.to(running_var.dtype))
-        return out.detach().contiguous(), (leaves, out)
+            y = conv.transpose(1, 2)                                                  # [B, To, C]
+        B, To, _ = y.shape
+        h, bn_saved = _StagedBatchNorm.forward(y.detach().reshape(B * To, C), _d(gamma), _d(beta), running_mean, running_var, eps, momentum,
+                                               reduce_stats)
+        return h.reshape(B, To, C).contiguous(), ((xr, wr, br), y, bn_saved)
 
     @staticmethod
     def backward(dh, saved, reduce_stats=None):
-        leaves, out = saved
+        (xr, wr, br), y, bn_saved = saved
+        B, To, C = y.shape
+        dy, dgamma, dbeta = _StagedBatchNorm.backward(_d(dh).reshape(B * To, C), bn_saved, reduce_stats)
         with torch.enable_grad():
-            out.backward(_d(dh))
-        xr, wr, br, gr, ber = leaves
-        return xr.grad, wr.grad.reshape(wr.shape[0], -1), br.grad, gr.grad, ber.grad
+            y.backward(dy.reshape(B, To, C))
+        return xr.grad, wr.grad.reshape(C, -1), br.grad, dgamma, dbeta
 
 
 class SubsampleTrain:
     @staticmethod
     def forward(mel, w, b, gamma, beta, running_mean, running_var, precision, eps=1e-5, momentum=0.1, reduce_stats=None):
-        assert reduce_stats is None
-        leaves = [_d(t).clone().requires_grad_(True) for t in (w, b, gamma, beta)]
-        wr, br, gr, ber = leaves
+        wr, br = [_d(t).clone().requires_grad_(True) for t in (w, b)]
         B, Fm, T = mel.shape
         C = w.shape[0]
-        rm, rv = _d(running_mean).clone(), _d(running_var).clone()
         with torch.enable_grad():
-            conv = F.conv2d(_d(mel).unsqueeze(1), wr, br, stride=2, padding=1)
-            bn = F.batch_norm(conv, rm, rv, gr, ber, training=True, momentum=momentum, eps=eps)
-            To = conv.shape[-1]
-            out = (bn * torch.sigmoid(bn)).reshape(B, C * (Fm // 2), To).transpose(1, 2).reshape(B * To, -1)
-        running_mean.copy_(rm.to(running_mean.dtype)); running_var.copy_(rv.to(running_var.dtype))
-        return out.detach().contiguous(), (leaves, out)
+            conv = F.conv2d(_d(mel).unsqueeze(1), wr, br, stride=2, padding=1)       # [B, C, F/2, To]
+        F2, To = conv.shape[2], conv.shape[3]
+        y = conv.detach().permute(0, 2, 3, 1).reshape(B * F2 * To, C)                 # statistics over (b, f, t) per channel
+        h, bn_saved = _StagedBatchNorm.forward(y, _d(gamma), _d(beta), running_mean, running_var, eps, momentum, reduce_stats)
+        out = h.reshape(B, F2, To, C).permute(0, 2, 3, 1).reshape(B * To, C * F2)     # [(b, t), c * F2 + f]: layout of the following Linear
+        return out.contiguous(), ((wr, br), conv, bn_saved, (B, C, F2, To))
 
     @staticmethod
     def backward(da, saved, reduce_stats=None):
-        leaves, out = saved
+        (wr, br), conv, bn_saved, (B, C, F2, To) = saved
+        dh = _d(da).reshape(B, To, C, F2).permute(0, 3, 1, 2).reshape(B * F2 * To, C)
+        dy, dgamma, dbeta = _StagedBatchNorm.backward(dh, bn_saved, reduce_stats)
         with torch.enable_grad():
-            out.backward(_d(da))
-        wr, br, gr, ber = leaves
-        return wr.grad, br.grad, gr.grad, ber.grad
+            conv.backward(dy.reshape(B, F2, To, C).permute(0, 3, 1, 2))
+        return wr.grad, br.grad, dgamma, dbeta
 
 
 def strided_rows(x, stride, precision):

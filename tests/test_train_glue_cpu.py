@@ -88,3 +88,57 @@ def test_autograd_node_fills_parameter_grads(cpu_ops):
             assert p.grad is None
         else:
             assert p.grad is not None and p.grad.shape == p.shape and bool(torch.isfinite(p.grad).all()), n
+
+
+VARIANTS = {
+    # scaled-down relatives of the shipped Efficient Conformer configs (reference configs/EfficientConformer*.json): the block layout rules
+    # (strided / expand indices, grouped attention in stage 0, head counts, tap counts) are what the tape logic depends on, not the widths
+    "medium_like_three_stages": dict(num_blocks=6, strided_blocks=[1, 3], expand_blocks=[1, 3], dim_model=[16, 24, 32], num_heads=4,
+                                     att_group_size=[3, 1, 1], kernel_size=15, subsampling_filters=[8]),
+    "large_like_eight_heads_stride_first_block": dict(num_blocks=4, strided_blocks=[0, 2], expand_blocks=[0, 2], dim_model=[32, 48, 64], num_heads=8,
+                                                      att_group_size=[3, 1, 1], kernel_size=15, subsampling_filters=[6]),
+    "single_stage_no_stride_k31": dict(num_blocks=2, strided_blocks=[], expand_blocks=[], dim_model=[24], num_heads=4, att_group_size=[1],
+                                       kernel_size=31, subsampling_filters=[4]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(VARIANTS))
+def test_training_tape_equals_oracle_autograd_on_other_block_layouts(cpu_ops, name):
+    """Every parameter gradient of the training schedule equals torch autograd over the oracle's train-mode forward (itself pinned to
+    the reference's loss.backward() above) for other block layouts, ragged lengths included (x_len hitting the group-of-3 and
+    stride-2 boundaries); vocabulary 1000 as in the Transducer encoders' sibling CTC heads is irrelevant to the path, 64 is used."""
+    training = cpu_ops
+    from efficientconformer_b200.model_ctc import ModelCTC
+    from efficientconformer_b200.synthetic import synthetic_targets
+    params = dict(P); params.update(VARIANTS[name]); params["Pdrop"] = 0.0
+    Vv = 64
+    sd = seeded_state_dict(params, Vv, seed=3, prefix_encoder="encoder.")
+    model = ModelCTC(params, {"vocab_size": Vv})
+    model.load_state_dict(sd, strict=False)
+    model.train()
+    path = training.TrainingPath(model.encoder, model.fc)
+    mel = synthetic_mel(3, 131, seed=17)
+    mel_len = torch.tensor([131, 100, 58])
+    with torch.no_grad():
+        x, logits, out_len, tape = path.forward(mel, mel_len, "tf32", want_logits=True)
+    leaf = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.double() if v.is_floating_point() else v)
+            for k, v in sd.items()}
+    ref_logits, ref_len = O.model_ctc_forward_mel(leaf, params, mel.double(), mel_len, bn={"updates": {}})
+    assert torch.equal(out_len, ref_len)
+    assert rel_l2(logits, ref_logits.detach()) < 1e-9
+    y, yl = synthetic_targets(ref_len, Vv, seed=4)
+    ref_loss, _ = O.ctc_loss(ref_logits, ref_len, y, yl)
+    ref_loss.backward()
+    lg = logits.detach().double().requires_grad_(True)
+    loss, _ = O.ctc_loss(lg, out_len, y, yl)
+    loss.backward()
+    with torch.no_grad():
+        grads = path.backward(tape, None, lg.grad)
+    names = [n for n, _ in path.param_list()]
+    assert set(grads) == set(names)
+    scale = max(float(leaf[k].grad.norm()) for k in names)
+    for k in names:
+        ref = leaf[k].grad
+        assert tuple(grads[k].shape) == tuple(ref.shape), k
+        # the shim exchanges BatchNorm statistics as fp32 (mean, M2) pairs like the CUDA stages: 1e-7-level noise on exact-zero gradients
+        assert float((grads[k].double() - ref).norm()) < 1e-7 * scale + 1e-6 * float(ref.norm()), k
