@@ -381,6 +381,8 @@ def train_workload_config(args, batch_per_gpu, world, where, extra=None):
                        f"schedule), batch {batch_per_gpu}/GPU x 80-mel x {args.frames} frames, full-length utterances (BASELINE.json configs[1] at the "
                        f"north_star target shape)",
            "global_batch": batch_per_gpu * world, "frames": args.frames, "n_mels": 80, "weights": "seeded random init",
+           "optimizer": "Adam + Transformer schedule applied after EVERY batch (the reference config accumulates 2 micro-batches per optimiser "
+                        "step: this measures more optimiser work per frame, not less)",
            "l2": "256 MiB write between timed steps (L2 flush)" if where == "gpu" else "n/a (CPU)",
            "parallelism": f"dp{world}: utterances sharded over ranks; SyncBatchNorm statistics + one flat gradient bucket all-reduced over NCCL"
                           if world > 1 else "dp1"}

@@ -14,6 +14,7 @@
 #include "ec_common.cuh"
 #include "ec_tma.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace ec {
 
@@ -28,6 +29,7 @@ struct WgDev {
   int bn;                // UMMA N = weight columns per CTA (multiple of the box width, <= 256)
   int a_boxes, b_boxes;  // 128-byte column blocks of the dY / X tiles
   int rows_per_split, stages, tmem_cols;
+  int epi;               // 0: thread-per-row stores (measured default); 1: experimental coalesced epilogue through shared memory
   float* partial;        // [splits][N][K]
 };
 
@@ -133,11 +135,27 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0u;
       }
-      if (n < p.N) {
+      if (p.epi == 0) {
+        if (n < p.N) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int k = k0 + c0 + j;
-          if (k < p.K) out[k] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) {
+            const int k = k0 + c0 + j;
+            if (k < p.K) out[k] = __uint_as_float(v[j]);
+          }
+        }
+      } else {
+        // EXPERIMENTAL (EFFCONF_WGRAD_EPI=1, not yet measured): the 32 x 32 chunk of this warp is transposed through shared memory
+        // (the drained operand ring: every MMA has completed once acc_full fired and the producer issues no further loads), so that
+        // each store instruction writes 128 contiguous bytes of ONE weight row instead of 4 bytes of 32 different rows.
+        float* tile = reinterpret_cast<float*>(bp) + (warp - 2) * (32 * 33);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int k = k0 + c0 + lane;
+        for (int r = 0; r < 32; ++r) {
+          const int nr = n0 + q * 32 + r;
+          if (nr < p.N && k < p.K) p.partial[(static_cast<size_t>(blockIdx.z) * p.N + nr) * p.K + k] = tile[r * 33 + lane];
         }
       }
     }
@@ -204,6 +222,8 @@ static int launch_wgrad_t(int precision, const void* dy, const void* x, int M, i
   while (cols < p.bn) cols <<= 1;
   p.tmem_cols = cols;
   p.partial = work;
+  static const int epi_mode = [] { const char* e = getenv("EFFCONF_WGRAD_EPI"); return (e && e[0] == '1') ? 1 : 0; }();
+  p.epi = epi_mode;
   CUtensorMap tmDY, tmX;
   const bool f32 = precision == EC_PREC_TF32;
   EC_TRY(make_map(&tmDY, f32, dy, M, N, N, EB, kWgRows, CU_TENSOR_MAP_SWIZZLE_128B));

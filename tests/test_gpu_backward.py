@@ -270,3 +270,29 @@ def test_subsampling_conv2d_batchnorm2d_training_forward_backward(ops, prec):
         assert rel_l2(dw, wr.grad) < 2e-4, (case, rel_l2(dw, wr.grad))
         assert rel_l2(dgam, gr.grad) < 2e-4 and rel_l2(dbet, ber.grad) < 2e-4, case
         assert float(db.abs().max()) < 1e-3 * max(1.0, float(dbet.abs().max())), case
+
+
+@pytest.mark.skipif(os.environ.get("EFFCONF_TEST_EXPERIMENTAL") != "1", reason="experimental kernel switches are validated on demand "
+                    "(EFFCONF_TEST_EXPERIMENTAL=1): they are off by default and not part of the measured path")
+def test_experimental_coalesced_wgrad_epilogue_in_a_subprocess():
+    """EFFCONF_WGRAD_EPI=1 (wgrad_tc.cu: partial tile transposed through the drained operand ring, 128-byte row stores) must give
+    bit-identical weight gradients to the default thread-per-row epilogue.  The switch is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "from efficientconformer_b200 import ops\n"
+        "g = torch.Generator().manual_seed(1)\n"
+        "out = []\n"
+        "for (M, N, K) in [(16000, 480, 120), (8000, 504, 168), (249, 120, 120), (4000, 256, 240), (1000, 120, 4800)]:\n"
+        "    dy = ops.cast(torch.randn(M, N, generator=g).cuda(), 'bf16'); x = ops.cast(torch.randn(M, K, generator=g).cuda(), 'bf16')\n"
+        "    out.append(ops.linear_wgrad(dy, x, 'bf16').cpu())\n"
+        "torch.save(out, sys.argv[1])\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ("0", "1"):
+        path = f"/tmp/effconf_wgrad_epi_{mode}.pt"
+        env = dict(os.environ, EFFCONF_WGRAD_EPI=mode)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+        res[mode] = torch.load(path)
+    for a, b in zip(res["0"], res["1"]):
+        assert torch.equal(a, b)
