@@ -657,7 +657,7 @@ def run_train(args, rank, world, local_rank):
             a = v["flops"] / v["ms"] / 1e9
             kern = "wgrad_tc_kernel" if k == "ec_op_wgrad" else "gemm_tc_kernel"
             return {"kernel": desc.get(k, k), "bound": "tensor", "achieved": round(a, 2), "peak": tensor_peak, "unit": "TFLOP/s",
-                    "frac": round(a / tensor_peak, 4), "traffic": ncu_traffic(args.precision, kern, "r2_ncu_full_train"),
+                    "frac": round(a / tensor_peak, 4), "traffic": ncu_traffic(args.precision, kern, "r1_ncu_full_train"),
                     "peak_source": pk["source"] + (" bf16 cuBLAS burst" if args.precision == "bf16" else " bf16 cuBLAS burst / 2 (tf32 operands)"),
                     "launches_per_step": v["calls"], "avg_launch_us": round(1e3 * v["ms"] / max(v["calls"], 1), 2),
                     "share_of_step": round(v["ms"] / tot_ms, 3),
