@@ -2,7 +2,7 @@
 # One GPU-box visit for the training step: parity tests, bench lines (train + forward), ncu launch list and a full-set capture of the
 # dominant tensor-core kernels of one training step; everything lands in gpurun_out/.
 #   gpurun --timeout 1500 -- 'bash tools/gpu_round_train.sh [tag] [stages]'
-TAG=${1:-r2}
+TAG=${1:-r1t}
 STAGES=${2:-test,bench,launches,full}
 OUT=gpurun_out
 mkdir -p $OUT
