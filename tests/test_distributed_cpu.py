@@ -74,7 +74,7 @@ def _syncbn_worker(rank, world, port, q):
             n = red.forward_stats(stats, float(hi - lo))
             sums = torch.stack([x.sum(0), (x * x).sum(0)])
             red.backward_sums(sums)
-            out[uniform] = (n, stats, sums)
+            out[uniform] = (n, stats.numpy().copy(), sums.numpy().copy())      # by value: the worker may exit before the parent reads
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
@@ -97,6 +97,7 @@ def test_two_rank_sync_batchnorm_exchange():
     for rank in (0, 1):
         for uniform in (True, False):
             n, stats, sums = res[rank][uniform]
+            stats, sums = torch.from_numpy(stats), torch.from_numpy(sums)
             assert n == 70.0
             assert torch.allclose(stats, ref, rtol=1e-5, atol=1e-5), (rank, uniform)
             assert torch.allclose(sums, ref_sums, rtol=1e-5)
@@ -160,7 +161,7 @@ def _dp_worker(rank, world, port, q):
         loss, grads, stats = _dp_run(_dp_params(), mel[lo:hi], y[lo:hi], yl[lo:hi], D.SyncBatchNormReducer(None, "cpu", uniform=True))
         flat = torch.cat([grads[k].reshape(-1) for k in sorted(grads)])
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)                  # the one gradient bucket; the mean (1 / world) is folded into Adam
-        q.put((rank, loss, flat / world, stats))
+        q.put((rank, loss, (flat / world).numpy().copy(), {k: v.numpy().copy() for k, v in stats.items()}))   # by value
     finally:
         dist.destroy_process_group()
 
@@ -186,9 +187,10 @@ def test_two_rank_data_parallel_training_step_equals_whole_batch():
     loss, grads, stats = _dp_run(_dp_params(), mel, y, yl, None)
     ref = torch.cat([grads[k].reshape(-1) for k in sorted(grads)])
     assert abs(0.5 * (res[0][1] + res[1][1]) - loss) < 1e-6 * abs(loss)
-    assert torch.equal(res[0][2], res[1][2])                              # every rank ends with the same averaged gradient
-    err = float((res[0][2] - ref).norm() / ref.norm())
+    g0, g1 = torch.from_numpy(res[0][2]), torch.from_numpy(res[1][2])
+    assert torch.equal(g0, g1)                                            # every rank ends with the same averaged gradient
+    err = float((g0 - ref).norm() / ref.norm())
     assert err < 1e-5, err                                                # fp32 statistics exchange bounds the agreement
     for k, v in stats.items():
         for r in (0, 1):
-            assert torch.allclose(res[r][3][k], v, rtol=1e-5, atol=1e-6), (k, r)
+            assert torch.allclose(torch.from_numpy(res[r][3][k]), v, rtol=1e-5, atol=1e-6), (k, r)

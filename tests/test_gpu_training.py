@@ -309,7 +309,9 @@ def _dp_worker(rank, world, port, prec, graph, q):
             m = m.to(dev).train()
             st = CTCTrainStep(m, tp, precision=prec, use_cuda_graph=graph, sync_bn=True, data_parallel=data_parallel)
             ls = [float(st.step(mel[sl].to(dev), None, y[sl].to(dev), yl[sl].to(dev))) for mel in mels]
-            return ls, st.flat.exp_avg.clone().cpu(), st.flat.params.clone().cpu(), {k: v.clone().cpu() for k, v in m.state_dict().items() if "running" in k}
+            # numpy: pickled by value (tensors travel through a queue as shared-memory handles that die with the worker)
+            return ls, st.flat.exp_avg.cpu().numpy().copy(), st.flat.params.cpu().numpy().copy(), \
+                {k: v.cpu().numpy().copy() for k, v in m.state_dict().items() if "running" in k}
         dp = run(True, slice(lo, hi))
         out = {"rank": rank, "dp": dp}
         if rank == 0:
@@ -337,9 +339,11 @@ def test_two_gpu_data_parallel_step_matches_single_gpu_full_batch(graph):
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    l0, m0, p0, s0 = res[0]["dp"]
-    l1, m1, p1, s1 = res[1]["dp"]
-    lf, mf, pf, sf = res[0]["full"]
+    t = torch.from_numpy
+    unpack = lambda r: (r[0], t(r[1]), t(r[2]), {k: t(v) for k, v in r[3].items()})
+    l0, m0, p0, s0 = unpack(res[0]["dp"])
+    l1, m1, p1, s1 = unpack(res[1]["dp"])
+    lf, mf, pf, sf = unpack(res[0]["full"])
     assert torch.equal(p0, p1) and torch.equal(m0, m1)                        # replicas stay identical
     for k in s0:
         assert torch.equal(s0[k], s1[k]), k                                   # SyncBatchNorm: same running statistics on every rank
