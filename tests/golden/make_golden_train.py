@@ -39,8 +39,9 @@ FULL = ["fc.bias", "fc.weight", "encoder.linear.bias", "encoder.subsampling_modu
         "encoder.blocks.14.feed_forward_module2.layers.4.bias"]
 
 
-def main():
-    cfg = json.load(open(f"{REF}/configs/EfficientConformerCTCSmall.json"))
+def main(config="EfficientConformerCTCSmall", out_name="ctc_small_train_b2_t500.pt", B=2, T=500, lens=(500, 377), full_names=None):
+    full_names = FULL if full_names is None else full_names
+    cfg = json.load(open(f"{REF}/configs/{config}.json"))
     cfg["encoder_params"]["Pdrop"] = 0.0
     cwd = os.getcwd(); os.chdir(REF)
     try:
@@ -53,9 +54,8 @@ def main():
     miss = model.load_state_dict(sd, strict=False)
     assert all("preprocessing." in k for k in miss.missing_keys) and not miss.unexpected_keys
     model.train()
-    B, T = 2, 500
     mel = synthetic_mel(B, T, seed=1)
-    mel_len = torch.tensor([500, 377])
+    mel_len = torch.tensor(list(lens))
     enc = model.encoder
     h, l = enc.subsampling_module(mel, mel_len)
     mask = enc.padding_mask(h, l)
@@ -73,14 +73,20 @@ def main():
     for k, p in model.named_parameters():
         assert p.grad is not None, k
         norms[k] = float(p.grad.double().norm())
-        if k in FULL:
+        if k in full_names:
             full[k] = p.grad.clone()
     new_sd = model.state_dict()
     stats = {k: new_sd[k].clone() for k in new_sd if k.endswith("running_mean") or k.endswith("running_var")}
     torch.save({"mel_seed": 1, "mel_len": mel_len, "targets": y, "target_len": y_len, "loss": loss.detach(), "logits": logits.detach(),
-                "grad_norms": norms, "grads": full, "running_stats": stats}, f"{HERE}/ctc_small_train_b2_t500.pt")
-    print("loss", float(loss), "params", len(norms), "size KB", os.path.getsize(f"{HERE}/ctc_small_train_b2_t500.pt") // 1024)
+                "grad_norms": norms, "grads": full, "running_stats": stats, "config": config, "shape": (B, T)}, f"{HERE}/{out_name}")
+    print(config, "loss", float(loss), "params", len(norms), "size KB", os.path.getsize(f"{HERE}/{out_name}") // 1024)
 
 
 if __name__ == "__main__":
-    main()
+    if "--medium" in sys.argv:
+        # second shipped config (16 blocks, widths 180 / 256 / 360, strided blocks 4 and 10), lengths off the group-of-3 / stride-2 grid
+        main("EfficientConformerCTCMedium", "ctc_medium_train_b2_t250.pt", B=2, T=250, lens=(250, 163),
+             full_names=["fc.bias", "encoder.linear.bias", "encoder.blocks.10.conv_res.1.bias", "encoder.blocks.4.convolution_module.layers.5.weight",
+                         "encoder.blocks.0.multi_head_self_attention_module.mhsa.u", "encoder.blocks.15.norm.weight"])
+    else:
+        main()

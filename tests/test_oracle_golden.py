@@ -202,3 +202,30 @@ def test_training_step_loss_gradients_and_running_stats(sd, golden_dir):
             assert rel_l2(leaf[k].grad, ref) < 2e-3, k
     for k, ref in g["running_stats"].items():
         assert rel_l2(bn["updates"][k[len("encoder."):]], ref) < 1e-5, k
+
+
+def test_training_step_medium_config_loss_gradients_and_running_stats(golden_dir):
+    """The oracle's train-mode forward + autograd against the real reference's loss.backward() on the second shipped config
+    (EfficientConformerCTCMedium, B=2, 80x250, lengths 250 / 163): loss, all 620 gradient norms, running statistics."""
+    from efficientconformer_b200.config import SHIPPED_ENCODER_PARAMS
+    PM, VM = SHIPPED_ENCODER_PARAMS["EfficientConformerCTCMedium"]
+    g = torch.load(os.path.join(golden_dir, "ctc_medium_train_b2_t250.pt"))
+    sdm = seeded_state_dict(PM, VM, seed=0, prefix_encoder="encoder.")
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sdm.items()}
+    bn = {"updates": {}}
+    logits, out_len = O.model_ctc_forward_mel(leaf, PM, synthetic_mel(2, 250, seed=g["mel_seed"]), g["mel_len"], bn=bn)
+    assert rel_l2(logits.detach(), g["logits"]) < 2e-5
+    loss, _ = O.ctc_loss(logits, out_len, g["targets"], g["target_len"])
+    assert abs(float(loss.detach()) - float(g["loss"])) / abs(float(g["loss"])) < 1e-5
+    loss.backward()
+    floor = 1e-4 * sorted(g["grad_norms"].values())[len(g["grad_norms"]) // 2]
+    worst = 0.0
+    for k, ref_norm in g["grad_norms"].items():
+        gn = float(leaf[k].grad.double().norm())
+        if ref_norm < floor:
+            assert gn < floor, k
+            continue
+        worst = max(worst, abs(gn - ref_norm) / ref_norm)
+    assert worst < 2e-3, worst
+    for k, ref in g["running_stats"].items():
+        assert rel_l2(bn["updates"][k[len("encoder."):]], ref) < 1e-5, k

@@ -68,6 +68,48 @@ def test_training_tape_reproduces_reference_gradients(cpu_ops, golden_dir):
     assert int(new_sd["encoder.subsampling_module.layers.0.1.num_batches_tracked"]) == 1
 
 
+def test_training_tape_reproduces_reference_gradients_medium_config(cpu_ops, golden_dir):
+    """Same check against the REAL reference on the second shipped config (EfficientConformerCTCMedium: 16 blocks, widths 180 / 256 /
+    360, strided blocks 4 and 10; golden from tests/golden/make_golden_train.py --medium; lengths 250 / 163 sit off the group-of-3 and
+    stride-2 grids): loss, all 620 gradient norms, a subset of full gradients, running statistics."""
+    training = cpu_ops
+    from efficientconformer_b200.config import SHIPPED_ENCODER_PARAMS
+    from efficientconformer_b200.model_ctc import ModelCTC
+    g = torch.load(os.path.join(golden_dir, "ctc_medium_train_b2_t250.pt"))
+    PM, VM = SHIPPED_ENCODER_PARAMS["EfficientConformerCTCMedium"]
+    params = dict(PM); params["Pdrop"] = 0.0
+    model = ModelCTC(params, {"vocab_size": VM})
+    model.load_state_dict(seeded_state_dict(PM, VM, seed=0, prefix_encoder="encoder."), strict=False)
+    model.train()
+    path = training.TrainingPath(model.encoder, model.fc)
+    mel = synthetic_mel(2, 250, seed=g["mel_seed"])
+    with torch.no_grad():
+        x, logits, out_len, tape = path.forward(mel, g["mel_len"], "tf32", want_logits=True)
+    assert rel_l2(logits, g["logits"]) < 2e-5
+    lg = logits.detach().double().requires_grad_(True)
+    loss, _ = O.ctc_loss(lg, out_len, g["targets"], g["target_len"])
+    assert abs(float(loss.detach()) - float(g["loss"])) / abs(float(g["loss"])) < 1e-5
+    loss.backward()
+    with torch.no_grad():
+        grads = path.backward(tape, None, lg.grad)
+    assert set(grads) == set(g["grad_norms"])
+    floor = 1e-4 * sorted(g["grad_norms"].values())[len(g["grad_norms"]) // 2]
+    worst = 0.0
+    for k, ref_norm in g["grad_norms"].items():
+        gn = float(grads[k].double().norm())
+        if ref_norm < floor:
+            assert gn < floor, k
+            continue
+        worst = max(worst, abs(gn - ref_norm) / ref_norm)
+    assert worst < 2e-3, worst
+    for k, ref in g["grads"].items():
+        if g["grad_norms"][k] >= floor:
+            assert rel_l2(grads[k], ref) < 2e-3, k
+    new_sd = model.state_dict()
+    for k, ref in g["running_stats"].items():
+        assert rel_l2(new_sd[k], ref) < 1e-5, k
+
+
 def test_autograd_node_fills_parameter_grads(cpu_ops):
     """EncoderTrainFn: loss.backward() through the single autograd node assigns .grad on every parameter (and only where
     requires_grad), for the encoder-only output as well (Transducer-style callers)."""
