@@ -11,8 +11,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeffconf_b200.so")
 
 EC_MAX_BLOCKS = 32
-PREC_TF32, PREC_BF16 = 0, 1
-PRECISIONS = {"tf32": PREC_TF32, "bf16": PREC_BF16}
+PREC_TF32, PREC_BF16, PREC_BF16X2 = 0, 1, 2
+# "bf16x2": split mode, every operand element is a packed (hi, lo) bf16 pair = 16 significant bits (include/effconf_b200.h)
+PRECISIONS = {"tf32": PREC_TF32, "bf16": PREC_BF16, "bf16x2": PREC_BF16X2}
 _fp = C.POINTER(C.c_float)
 
 
@@ -132,7 +133,11 @@ _SIGNATURES = {
     "ec_op_swish_dropout": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_float, C.c_void_p, C.c_uint, C.c_void_p]),
     "ec_op_transpose_cast_multi": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ec_op_pack_flat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ec_op_pack_flat_acc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "ec_op_cast": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ec_weight_planes": (C.c_int, [C.c_int]),
+    "ec_op_cast_weight": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "ec_op_cast_multi": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ec_op_layernorm": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
     "ec_op_gemm": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_void_p,
@@ -240,4 +245,10 @@ def stream_ptr():
 
 
 def act_dtype(precision: int):
-    return torch.float32 if precision == PREC_TF32 else torch.bfloat16
+    """torch dtype that carries one activation element: fp32 words for TF32-rounded values and for the packed (hi, lo) pairs of the
+    split mode (view as int32 / use ops.unpack to look at the values), bf16 otherwise."""
+    return torch.bfloat16 if precision == PREC_BF16 else torch.float32
+
+
+def weight_planes(precision: int):
+    return 2 if precision == PREC_BF16X2 else 1

@@ -50,7 +50,11 @@ constexpr int kAttBM = 64;
 
 // BN = keys per tile: 64, or 32 for the widest heads (d = 135 of the Medium / Large grouped blocks) whose 64-key tiles do not fit
 // in shared memory.  The staged E band has kAttBM + BN rows, the per-warp score strip is 16 x (BN + 16).
-template <int DPT, typename OutT, int BN>
+// kPacked (split mode): q|k|v and E arrive as packed (hi, lo) bf16 pairs; they are unpacked (16 significant bits) and rounded to
+// TF32 while staging, so the contractions of the attention core run at TF32 precision like the parity mode.
+__device__ __forceinline__ float unpack_tf32(float w) { return round_tf32(split_unpack(__float_as_uint(w))); }
+
+template <int DPT, typename OutT, int BN, bool kPacked>
 __global__ void __launch_bounds__(128) relpos_attn_kernel(const AttnDev p) {
   constexpr int DP = DPT * 8, STR = DP + 4;
   constexpr int kAttBN = BN, kGW = BN + 16, kGStride = kGW + 1, kBand = kAttBM + BN;
@@ -100,6 +104,7 @@ __global__ void __launch_bounds__(128) relpos_attn_kernel(const AttnDev p) {
           const int frame = i * G + cfoff;
           float2 q = make_float2(0.f, 0.f);                     // appended pad frames are exact zeros
           if (frame < T) q = __ldg(reinterpret_cast<const float2*>(qkv_b + frame * row3 + cch));
+          if constexpr (kPacked) { q.x = split_unpack(__float_as_uint(q.x)); q.y = split_unpack(__float_as_uint(q.y)); }
           qu = make_float2(q.x + uu.x, q.y + uu.y); qv = make_float2(q.x + vv.x, q.y + vv.y);
         }
         *reinterpret_cast<float2*>(Qu + r * STR + cc) = make_float2(round_tf32(qu.x), round_tf32(qu.y));
@@ -114,7 +119,8 @@ __global__ void __launch_bounds__(128) relpos_attn_kernel(const AttnDev p) {
       if (c < d && i < Tg) {
         int foff, ch; locate(c, foff, ch);
         const int frame = i * G + foff;
-        const float q = frame < T ? __ldg(qkv_b + frame * row3 + ch) : 0.f;
+        float q = frame < T ? __ldg(qkv_b + frame * row3 + ch) : 0.f;
+        if constexpr (kPacked) q = split_unpack(__float_as_uint(q));
         qu = q + __ldg(p.u + ch);
         qv = q + __ldg(p.v + ch);
       }
@@ -175,6 +181,29 @@ __global__ void __launch_bounds__(128) relpos_attn_kernel(const AttnDev p) {
       }
     }
     cp_async_wait_all();
+    if constexpr (kPacked) {      // every thread converts, in place, exactly the words its own cp.async wrote (visible after the wait)
+      if (vec2) {
+        if (stager) {
+          for (int r = rsub; r < kAttBN; r += RPP) {
+            float2* k2 = reinterpret_cast<float2*>(Ks + r * STR + cc); float2* v2 = reinterpret_cast<float2*>(Vs + r * STR + cc);
+            *k2 = make_float2(unpack_tf32(k2->x), unpack_tf32(k2->y)); *v2 = make_float2(unpack_tf32(v2->x), unpack_tf32(v2->y));
+          }
+          for (int r = rsub; r < kBand; r += RPP) {
+            float2* e2 = reinterpret_cast<float2*>(Es + r * STR + cc);
+            *e2 = make_float2(unpack_tf32(e2->x), unpack_tf32(e2->y));
+          }
+        }
+      } else {
+        for (int idx = tid; idx < kAttBN * DP; idx += 128) {
+          const int r = idx / DP, c = idx % DP;
+          Ks[r * STR + c] = unpack_tf32(Ks[r * STR + c]); Vs[r * STR + c] = unpack_tf32(Vs[r * STR + c]);
+        }
+        for (int idx = tid; idx < kBand * DP; idx += 128) {
+          const int r = idx / DP, c = idx % DP;
+          Es[r * STR + c] = unpack_tf32(Es[r * STR + c]);
+        }
+      }
+    }
     __syncthreads();
 
     // ---- G = Qv_w . Eband_w^T  (16 x 80) -> per-warp smem strip ----
@@ -292,7 +321,7 @@ __global__ void __launch_bounds__(128) relpos_attn_kernel(const AttnDev p) {
   }
 }
 
-template <int DPT, typename OutT>
+template <int DPT, typename OutT, bool kPacked>
 static int launch_attn_inst(const AttnDev& p, cudaStream_t stream) {
   constexpr int STR = DPT * 8 + 4;
   constexpr int BN = DPT > 16 ? 32 : 64;
@@ -300,26 +329,26 @@ static int launch_attn_inst(const AttnDev& p, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(relpos_attn_kernel<DPT, OutT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(relpos_attn_kernel<DPT, OutT, BN, kPacked>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   EC_CUDA(attr_err);
   EC_REQUIRE(smem <= 227 * 1024, "attention tile does not fit in shared memory");
   dim3 grid(cdiv(p.Tg, kAttBM), p.H, p.B);
-  return launch_pdl(relpos_attn_kernel<DPT, OutT, BN>, grid, dim3(128), smem, stream, p);
+  return launch_pdl(relpos_attn_kernel<DPT, OutT, BN, kPacked>, grid, dim3(128), smem, stream, p);
 }
 
-template <typename T>
+template <typename T, bool kPacked = false>
 static int launch_attn_t(const AttnDev& p, cudaStream_t stream) {
   const int dpt = cdiv(p.d, 8);
   switch (dpt) {
-    case 3: return launch_attn_inst<3, T>(p, stream);
-    case 5: return launch_attn_inst<5, T>(p, stream);
-    case 6: return launch_attn_inst<6, T>(p, stream);
-    case 7: return launch_attn_inst<7, T>(p, stream);
-    case 8: return launch_attn_inst<8, T>(p, stream);
-    case 10: return launch_attn_inst<10, T>(p, stream);
-    case 12: return launch_attn_inst<12, T>(p, stream);
-    case 17: return launch_attn_inst<17, T>(p, stream);
+    case 3: return launch_attn_inst<3, T, kPacked>(p, stream);
+    case 5: return launch_attn_inst<5, T, kPacked>(p, stream);
+    case 6: return launch_attn_inst<6, T, kPacked>(p, stream);
+    case 7: return launch_attn_inst<7, T, kPacked>(p, stream);
+    case 8: return launch_attn_inst<8, T, kPacked>(p, stream);
+    case 10: return launch_attn_inst<10, T, kPacked>(p, stream);
+    case 12: return launch_attn_inst<12, T, kPacked>(p, stream);
+    case 17: return launch_attn_inst<17, T, kPacked>(p, stream);
     default: EC_FAIL("unsupported attention head dim " + std::to_string(p.d));
   }
 }
@@ -342,6 +371,7 @@ int launch_relpos_attention(int precision, const AttnArgs& a, cudaStream_t strea
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(p.d));
   if (precision == EC_PREC_TF32) return launch_attn_t<float>(p, stream);
   if (precision == EC_PREC_BF16) return launch_attn_t<__nv_bfloat16>(p, stream);     // fp32 inputs, TF32 math, bf16 output (odd head dims)
+  if (precision == EC_PREC_BF16X2) return launch_attn_t<SplitBf16, true>(p, stream);  // packed inputs and output, TF32 math
   EC_FAIL("unknown precision");
 }
 

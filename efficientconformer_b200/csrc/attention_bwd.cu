@@ -348,8 +348,10 @@ int launch_relpos_attention_bwd(int precision, const AttnArgs& a, const float* d
   EC_REQUIRE(a.G >= 1 && a.G % 2 == 1 && (a.G * a.D) % a.H == 0, "attention backward: bad head layout");
   EC_REQUIRE(dO && dqkv && dE && du && dv && work, "attention backward: null argument");
   // bf16 operand mode: batched tensor-core GEMMs (attention_bwd_tc.cu); the CUDA-core kernels below are the TF32 parity path
-  if (precision == EC_PREC_BF16 && tc_path_enabled() && (a.T + a.G - 1) / a.G <= 1024)
-    return launch_relpos_attention_bwd_tc(a, dO, dqkv, dE, du, dv, work, stream);
+  // (split mode: the packed operands are rounded to bf16 while packing -- the gradients of the attention core are bf16 grade)
+  if ((precision == EC_PREC_BF16 || precision == EC_PREC_BF16X2) && tc_path_enabled() && (a.T + a.G - 1) / a.G <= 1024)
+    return launch_relpos_attention_bwd_tc(precision, a, dO, dqkv, dE, du, dv, work, stream);
+  EC_REQUIRE(precision != EC_PREC_BF16X2, "attention backward: the split mode needs the tensor-core path (<= 1024 grouped frames)");
   BwdDev p{};
   p.qkv = a.qkv; p.E = a.E; p.u = a.u; p.v = a.v; p.x_len = a.x_len; p.dO = dO;
   p.B = a.B; p.T = a.T; p.D = a.D; p.H = a.H; p.G = a.G;

@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(128) bgemm_kernel(const BGemm g) {
 }
 
 struct TcDev {
-  const bf16* qkv; const bf16* E; const float* u; const float* v; const int* x_len; const float* dO;
+  const void* qkv; const void* E;            // activation type: bf16, or packed (hi, lo) pairs in split mode (rounded to bf16 while packing)
+  const float* u; const float* v; const int* x_len; const float* dO;
   int B, T, D, H, G, d, dp, Tg, Tp, R, Rp;
   float scale;
   bf16 *Qu, *Qv, *Kd, *Vd, *dOd, *Eh;        // [BH, Tg, dp] x5, [H, R, dp]
@@ -164,6 +165,7 @@ struct TcDev {
 };
 
 // ---- pack: dense per-head operands.  One thread per (bh, i, c) -------------------------------------------------------------
+template <typename TIn>
 __global__ void __launch_bounds__(256) tc_pack_kernel(const TcDev p) {
   const long long n = static_cast<long long>(p.B) * p.H * p.Tg * p.dp;
   const long long row3 = 3LL * p.D;
@@ -179,8 +181,8 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const TcDev p) {
       const int frame = i * p.G + fo;
       float q = 0.f;
       if (frame < p.T) {
-        const bf16* row = p.qkv + (static_cast<long long>(b) * p.T + frame) * row3;
-        q = __bfloat162float(row[ch]); k = __bfloat162float(row[p.D + ch]); v = __bfloat162float(row[2 * p.D + ch]);
+        const TIn* row = reinterpret_cast<const TIn*>(p.qkv) + (static_cast<long long>(b) * p.T + frame) * row3;
+        q = ActTraits<TIn>::from(row[ch]); k = ActTraits<TIn>::from(row[p.D + ch]); v = ActTraits<TIn>::from(row[2 * p.D + ch]);
         go = p.dO[(static_cast<long long>(b) * p.T + frame) * p.D + ch];
       }
       qu = q + p.u[ch]; qv = q + p.v[ch];
@@ -189,6 +191,7 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const TcDev p) {
     p.Kd[idx] = __float2bfloat16_rn(k); p.Vd[idx] = __float2bfloat16_rn(v); p.dOd[idx] = __float2bfloat16_rn(go);
   }
 }
+template <typename TIn>
 __global__ void __launch_bounds__(256) tc_pack_e_kernel(const TcDev p) {
   const long long n = static_cast<long long>(p.H) * p.R * p.dp;
   const long long e_row = static_cast<long long>(p.H) * p.d;            // = G * D
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(256) tc_pack_e_kernel(const TcDev p) {
     const int c = static_cast<int>(idx % p.dp);
     const long long r = idx / p.dp;
     const int e = static_cast<int>(r % p.R), h = static_cast<int>(r / p.R);
-    p.Eh[idx] = c < p.d ? p.E[e * e_row + h * p.d + c] : __float2bfloat16_rn(0.f);
+    p.Eh[idx] = __float2bfloat16_rn(c < p.d ? ActTraits<TIn>::from(reinterpret_cast<const TIn*>(p.E)[e * e_row + h * p.d + c]) : 0.f);
   }
 }
 
@@ -362,10 +365,10 @@ inline int egrid(long long n) { return static_cast<int>(std::min<long long>((n +
 
 size_t attention_bwd_tc_work_bytes(int B, int T, int D, int H, int G) { return tc_layout(B, T, D, H, G).total; }
 
-int launch_relpos_attention_bwd_tc(const AttnArgs& a, const float* dO, float* dqkv, float* dE, float* du, float* dv, void* work,
+int launch_relpos_attention_bwd_tc(int precision, const AttnArgs& a, const float* dO, float* dqkv, float* dE, float* du, float* dv, void* work,
                                    cudaStream_t st) {
   TcDev p{};
-  p.qkv = reinterpret_cast<const bf16*>(a.qkv); p.E = reinterpret_cast<const bf16*>(a.E); p.u = a.u; p.v = a.v; p.x_len = a.x_len; p.dO = dO;
+  p.qkv = a.qkv; p.E = a.E; p.u = a.u; p.v = a.v; p.x_len = a.x_len; p.dO = dO;
   p.B = a.B; p.T = a.T; p.D = a.D; p.H = a.H; p.G = a.G;
   p.d = (a.G * a.D) / a.H; p.dp = round_up(p.d, 16);
   const int Pad = (a.G - a.T % a.G) % a.G;
@@ -387,9 +390,13 @@ int launch_relpos_attention_bwd_tc(const AttnArgs& a, const float* dO, float* dq
   const long long sE = static_cast<long long>(p.R) * dp;
   const int H = a.H;
 
-  tc_pack_kernel<<<egrid(static_cast<long long>(BH) * Tg * dp), 256, 0, st>>>(p);
-  EC_CUDA(cudaGetLastError());
-  tc_pack_e_kernel<<<egrid(static_cast<long long>(H) * p.R * dp), 256, 0, st>>>(p);
+  if (precision == EC_PREC_BF16X2) {
+    tc_pack_kernel<SplitBf16><<<egrid(static_cast<long long>(BH) * Tg * dp), 256, 0, st>>>(p);
+    tc_pack_e_kernel<SplitBf16><<<egrid(static_cast<long long>(H) * p.R * dp), 256, 0, st>>>(p);
+  } else {
+    tc_pack_kernel<bf16><<<egrid(static_cast<long long>(BH) * Tg * dp), 256, 0, st>>>(p);
+    tc_pack_e_kernel<bf16><<<egrid(static_cast<long long>(H) * p.R * dp), 256, 0, st>>>(p);
+  }
   EC_CUDA(cudaGetLastError());
   // S1 = Qu K^T, Rel = Qv Eh^T, dP = dO V^T
   EC_TRY((run_gemm<false, false>(BGemm{p.Qu, p.Kd, p.S1, Tg, Tg, dp, dp, dp, p.Tp, sD * H, sD, sD * H, sD, sS * H, sS, H, 0}, BH, st)));

@@ -157,8 +157,8 @@ int launch_colsum(int precision, const void* m, int is_f32, int rows, int cols, 
   EC_REQUIRE(rows > 0 && cols > 0 && m && out && work, "column sum: bad arguments");
   const int ctas = std::min(kBwdCtas, rows);
   dim3 grid(ctas, cdiv(cols, 256));
-  if (is_f32 || precision == EC_PREC_TF32) colsum_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(m), rows, cols, work);
-  else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(m), rows, cols, work);
+  if (is_f32) precision = EC_PREC_TF32;
+  EC_DISPATCH_PREC(precision, (colsum_kernel<ActT><<<grid, 256, 0, stream>>>(reinterpret_cast<const ActT*>(m), rows, cols, work)));
   EC_CUDA(cudaGetLastError());
   partial_reduce_kernel<<<cdiv(cols, 32), 1024, 0, stream>>>(work, ctas, 1, cols, out, out);
   EC_CUDA(cudaGetLastError());
@@ -180,17 +180,19 @@ __global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __rest
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int c = c0 + i, r = r0 + tx;
-    if (c < cols && r < rows) dst[static_cast<size_t>(c) * rows + r] = ActTraits<T>::to(tile[tx][i]);
+    if (c < cols && r < rows) {
+      const T v = ActTraits<T>::to(tile[tx][i]);
+      dst[static_cast<size_t>(c) * rows + r] = v;
+      if constexpr (IsSplit<T>::value)      // swapped plane of the [2, cols, rows] weight operand
+        dst[static_cast<size_t>(cols) * rows + static_cast<size_t>(c) * rows + r] = SplitBf16{split_swap(v.bits)};
+    }
   }
 }
 
 int launch_transpose_cast(int precision, const float* src, int rows, int cols, void* dst, cudaStream_t stream) {
   EC_REQUIRE(rows > 0 && cols > 0 && src && dst, "transpose: bad arguments");
   dim3 grid(cdiv(cols, 32), cdiv(rows, 32));
-  if (precision == EC_PREC_TF32) transpose_cast_kernel<float><<<grid, 256, 0, stream>>>(src, rows, cols, reinterpret_cast<float*>(dst));
-  else if (precision == EC_PREC_BF16)
-    transpose_cast_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(src, rows, cols, reinterpret_cast<__nv_bfloat16*>(dst));
-  else EC_FAIL("unknown precision");
+  EC_DISPATCH_PREC(precision, (transpose_cast_kernel<ActT><<<grid, 256, 0, stream>>>(src, rows, cols, reinterpret_cast<ActT*>(dst))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -227,20 +229,14 @@ __global__ void __launch_bounds__(256) glu_bwd_kernel(const T* __restrict__ zg, 
 int launch_swish_bwd(int precision, const void* z, const float* dy, size_t n, void* dz, cudaStream_t stream) {
   EC_REQUIRE(z && dy && dz && n > 0, "swish backward: bad arguments");
   const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
-  if (precision == EC_PREC_TF32) swish_bwd_kernel<float><<<blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(z), dy, n, reinterpret_cast<float*>(dz));
-  else if (precision == EC_PREC_BF16)
-    swish_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(z), dy, n, reinterpret_cast<__nv_bfloat16*>(dz));
-  else EC_FAIL("unknown precision");
+  EC_DISPATCH_PREC(precision, (swish_bwd_kernel<ActT><<<blocks, 256, 0, stream>>>(reinterpret_cast<const ActT*>(z), dy, n, reinterpret_cast<ActT*>(dz))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
 int launch_glu_bwd(int precision, const void* zg, const float* dy, size_t rows, int C, void* dzg, cudaStream_t stream) {
   EC_REQUIRE(zg && dy && dzg && rows > 0 && C > 0, "GLU backward: bad arguments");
   const int blocks = static_cast<int>(std::min<size_t>((rows * C + 255) / 256, 148 * 16));
-  if (precision == EC_PREC_TF32) glu_bwd_kernel<float><<<blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(zg), dy, rows, C, reinterpret_cast<float*>(dzg));
-  else if (precision == EC_PREC_BF16)
-    glu_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(zg), dy, rows, C, reinterpret_cast<__nv_bfloat16*>(dzg));
-  else EC_FAIL("unknown precision");
+  EC_DISPATCH_PREC(precision, (glu_bwd_kernel<ActT><<<blocks, 256, 0, stream>>>(reinterpret_cast<const ActT*>(zg), dy, rows, C, reinterpret_cast<ActT*>(dzg))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }

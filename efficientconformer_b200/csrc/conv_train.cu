@@ -271,14 +271,8 @@ int launch_dwconv_raw(int precision, const void* x, const float* w, const float*
   const int ctas = ctas_for(static_cast<size_t>(B) * T_out);
   dim3 grid(ctas, cdiv(C, 128));
   const bool small = K <= 15;                                  // tap loops are fully unrolled: 15-tap (Efficient Conformer) or 31-tap instances
-  const float* xf = reinterpret_cast<const float*>(x); const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
-  if (precision == EC_PREC_TF32) {
-    if (small) dwconv_raw_kernel_<float, 15><<<grid, 128, 0, st>>>(xf, w, bias, B, T, T_out, C, K, stride, y, work);
-    else dwconv_raw_kernel_<float, 31><<<grid, 128, 0, st>>>(xf, w, bias, B, T, T_out, C, K, stride, y, work);
-  } else {
-    if (small) dwconv_raw_kernel_<__nv_bfloat16, 15><<<grid, 128, 0, st>>>(xb, w, bias, B, T, T_out, C, K, stride, y, work);
-    else dwconv_raw_kernel_<__nv_bfloat16, 31><<<grid, 128, 0, st>>>(xb, w, bias, B, T, T_out, C, K, stride, y, work);
-  }
+  if (small) EC_DISPATCH_PREC(precision, (dwconv_raw_kernel_<ActT, 15><<<grid, 128, 0, st>>>(reinterpret_cast<const ActT*>(x), w, bias, B, T, T_out, C, K, stride, y, work)));
+  else EC_DISPATCH_PREC(precision, (dwconv_raw_kernel_<ActT, 31><<<grid, 128, 0, st>>>(reinterpret_cast<const ActT*>(x), w, bias, B, T, T_out, C, K, stride, y, work)));
   EC_CUDA(cudaGetLastError());
   bn_stats_merge_kernel<<<cdiv(C, 32), 1024, 0, st>>>(work, ctas, static_cast<size_t>(B) * T_out, C, sums);
   EC_CUDA(cudaGetLastError());
@@ -293,8 +287,7 @@ int launch_bn_finalize(const float* sums, int C, float count, float eps, float m
 int launch_bn_swish_fwd(int precision, const float* y, size_t rows, int C, const float* mean, const float* rstd, const float* gamma,
                         const float* beta, void* h, cudaStream_t st) {
   const int blocks = static_cast<int>(std::min<size_t>((rows * C + 255) / 256, 148 * 16));
-  if (precision == EC_PREC_TF32) bn_swish_fwd_kernel<float><<<blocks, 256, 0, st>>>(y, rows, C, mean, rstd, gamma, beta, reinterpret_cast<float*>(h));
-  else bn_swish_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(y, rows, C, mean, rstd, gamma, beta, reinterpret_cast<__nv_bfloat16*>(h));
+  EC_DISPATCH_PREC(precision, (bn_swish_fwd_kernel<ActT><<<blocks, 256, 0, st>>>(y, rows, C, mean, rstd, gamma, beta, reinterpret_cast<ActT*>(h))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -326,14 +319,8 @@ int launch_dwconv_bwd(int precision, const float* dy, const void* x, const float
   }
   const int ctas = ctas_for(static_cast<size_t>(B) * T_out);
   dim3 grid(ctas, cdiv(C, 128));
-  const float* xf = reinterpret_cast<const float*>(x); const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
-  if (precision == EC_PREC_TF32) {
-    if (K <= 15) dwconv_bwd_weight_kernel<float, 15><<<grid, 128, 0, st>>>(dy, xf, B, T, T_out, C, K, stride, work);
-    else dwconv_bwd_weight_kernel<float, 31><<<grid, 128, 0, st>>>(dy, xf, B, T, T_out, C, K, stride, work);
-  } else {
-    if (K <= 15) dwconv_bwd_weight_kernel<__nv_bfloat16, 15><<<grid, 128, 0, st>>>(dy, xb, B, T, T_out, C, K, stride, work);
-    else dwconv_bwd_weight_kernel<__nv_bfloat16, 31><<<grid, 128, 0, st>>>(dy, xb, B, T, T_out, C, K, stride, work);
-  }
+  if (K <= 15) EC_DISPATCH_PREC(precision, (dwconv_bwd_weight_kernel<ActT, 15><<<grid, 128, 0, st>>>(dy, reinterpret_cast<const ActT*>(x), B, T, T_out, C, K, stride, work)));
+  else EC_DISPATCH_PREC(precision, (dwconv_bwd_weight_kernel<ActT, 31><<<grid, 128, 0, st>>>(dy, reinterpret_cast<const ActT*>(x), B, T, T_out, C, K, stride, work)));
   EC_CUDA(cudaGetLastError());
   dwconv_wgrad_reduce_kernel<<<cdiv(C * (K + 1), 32), 1024, 0, st>>>(work, ctas, C, K, dw, db);
   EC_CUDA(cudaGetLastError());

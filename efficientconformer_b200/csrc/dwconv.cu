@@ -110,9 +110,7 @@ static int launch_dw_t(const DwConvArgs& a, cudaStream_t stream) {
 }
 
 int launch_dwconv_bn_swish(int precision, const DwConvArgs& a, cudaStream_t stream) {
-  if (precision == EC_PREC_TF32) return launch_dw_t<float>(a, stream);
-  if (precision == EC_PREC_BF16) return launch_dw_t<__nv_bfloat16>(a, stream);
-  EC_FAIL("unknown precision");
+  EC_DISPATCH_PREC(precision, return launch_dw_t<ActT>(a, stream));
 }
 
 }  // namespace ec

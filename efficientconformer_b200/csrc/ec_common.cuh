@@ -76,6 +76,7 @@ template <> struct ActTraits<float> {
   static constexpr int kUmmaK = 8;
   __device__ static float to(float x) { return round_tf32(x); }
   __device__ static float from(float x) { return x; }
+  __device__ static float word(float x) { return round_tf32(x); }     // the stored 32-bit word, carried in a float register
 };
 template <> struct ActTraits<__nv_bfloat16> {
   static constexpr bool kTf32 = false;
@@ -84,6 +85,40 @@ template <> struct ActTraits<__nv_bfloat16> {
   __device__ static __nv_bfloat16 to(float x) { return __float2bfloat16_rn(x); }
   __device__ static float from(__nv_bfloat16 x) { return __bfloat162float(x); }
 };
+
+// Split mode (EC_PREC_BF16X2): one element = the pair hi = bf16(x), lo = bf16(x - hi) in one 32-bit word (low half hi), 16
+// significant bits.  Same 4-byte footprint, TMA boxes, slab layouts and workspace sizes as the TF32 mode; the tensor core reads a
+// row of K packed elements as 2K bf16 values (kind::f16) against the two planes of the weight operand (see effconf_b200.h).
+struct SplitBf16 { uint32_t bits; };
+__device__ __forceinline__ uint32_t split_pack(float x) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  return static_cast<uint32_t>(__bfloat16_as_ushort(h)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l)) << 16);
+}
+__device__ __forceinline__ float split_unpack(uint32_t b) { return __uint_as_float(b << 16) + __uint_as_float(b & 0xffff0000u); }
+__device__ __forceinline__ uint32_t split_swap(uint32_t b) { return __byte_perm(b, 0, 0x1032); }
+template <> struct ActTraits<SplitBf16> {
+  static constexpr bool kTf32 = false;
+  static constexpr int kBlockK = 32;  // packed elements per 128-byte swizzle row (= 64 bf16 values)
+  static constexpr int kUmmaK = 16;
+  __device__ static SplitBf16 to(float x) { return SplitBf16{split_pack(x)}; }
+  __device__ static float word(float x) { return __uint_as_float(split_pack(x)); }
+  __device__ static float from(SplitBf16 x) { return split_unpack(x.bits); }
+};
+template <typename T> struct IsSplit { static constexpr bool value = false; };
+template <> struct IsSplit<SplitBf16> { static constexpr bool value = true; };
+// bytes of one activation element / factor of the weight operand ([2, N, K] in split mode)
+inline size_t act_esize(int precision) { return precision == EC_PREC_BF16 ? 2 : 4; }
+inline size_t weight_planes(int precision) { return precision == EC_PREC_BF16X2 ? 2 : 1; }
+
+// `body` sees the activation storage type of `precision` as ActT
+#define EC_DISPATCH_PREC(precision, ...)                                                  \
+  do {                                                                                    \
+    if ((precision) == EC_PREC_TF32) { using ActT = float; __VA_ARGS__; }                    \
+    else if ((precision) == EC_PREC_BF16) { using ActT = __nv_bfloat16; __VA_ARGS__; }       \
+    else if ((precision) == EC_PREC_BF16X2) { using ActT = ::ec::SplitBf16; __VA_ARGS__; }   \
+    else EC_FAIL("unknown precision");                                                    \
+  } while (0)
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 // x * sigmoid(x).  Parity (TF32) mode: exp + reciprocal.  bf16 mode: 0.5x + 0.5x*tanh(0.5x) with the hardware tanh
@@ -114,7 +149,8 @@ enum GemmAct { GEMM_ACT_NONE = 0, GEMM_ACT_SWISH = 1 };
 
 struct GemmArgs {
   const void* A;        // [M, K] row-major, activation type
-  const void* W;        // [N, K] row-major (nn.Linear layout), activation type
+  const void* W;        // [N, K] row-major (nn.Linear layout), activation type; split mode: plane 0 of the [2, N, K] operand
+  size_t w_twin_bytes;  // split mode: byte distance from W to its swapped plane (0: N*K*4, i.e. a contiguous [2, N, K])
   int M, N, K;
   const float* bias;    // [N] (GLU: prepared interleaved order) or nullptr
   float alpha;          // out = alpha * act(acc + bias) + residual
@@ -178,7 +214,7 @@ int try_launch_relpos_attention_tma(const AttnArgs& a, cudaStream_t stream, bool
 size_t attention_bwd_work_bytes(int B, int T, int D, int H, int G);
 size_t attention_bwd_tc_work_bytes(int B, int T, int D, int H, int G);
 struct AttnArgs;
-int launch_relpos_attention_bwd_tc(const AttnArgs& a, const float* dO, float* dqkv, float* dE, float* du, float* dv, void* work,
+int launch_relpos_attention_bwd_tc(int precision, const AttnArgs& a, const float* dO, float* dqkv, float* dE, float* du, float* dv, void* work,
                                    cudaStream_t stream);
 int launch_relpos_attention_bwd(int precision, const AttnArgs& a, const float* dO, float* dqkv, float* dE, float* du, float* dv, void* work,
                                 cudaStream_t stream);
@@ -208,6 +244,8 @@ int launch_conv2_weight_prep(int precision, const float* w, const float* b, cons
 int launch_linear_weight_permute(int precision, const float* w, int D, int C, int Fq, void* out, cudaStream_t stream);
 
 int launch_cast_rows(int precision, const float* src, void* dst, size_t n, cudaStream_t stream);   // fp32 -> activation type
+// weight operand: cast + (split mode) the swapped plane at dst + twin_elems elements
+int launch_cast_weight(int precision, const float* src, void* dst, size_t n, size_t twin_elems, cudaStream_t stream);
 int launch_fold_bn(const float* w, const float* b, const float* g, const float* beta, const float* rm, const float* rv,
                    float eps, int C, int taps, float* w_out, float* b_out, cudaStream_t stream);
 int launch_glu_interleave(int precision, const float* w, const float* b, int channels, int K, int nb, int tiles,

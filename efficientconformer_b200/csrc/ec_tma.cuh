@@ -69,7 +69,12 @@ __device__ __forceinline__ void slab_load_f32(const uint8_t* slab, int row, floa
 }
 template <typename T>
 __device__ __forceinline__ void slab_store_act(uint8_t* slab, int row, const float (&t)[32]) {
-  if constexpr (sizeof(T) == 4) {
+  if constexpr (IsSplit<T>::value) {
+    float r[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(split_pack(t[j]));
+    slab_store_f32(slab, row, r);
+  } else if constexpr (sizeof(T) == 4) {
     float r[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) r[j] = round_tf32(t[j]);
@@ -128,7 +133,7 @@ inline int make_map(CUtensorMap* map, bool is_f32, const void* ptr, int rows, in
 }
 // K-major GEMM operand [rows, K]: (128-byte x box_rows) box, 128B swizzle.
 inline int make_operand_map(CUtensorMap* map, int precision, const void* ptr, int rows, int K, int box_rows) {
-  const bool f32 = precision == EC_PREC_TF32;
+  const bool f32 = precision != EC_PREC_BF16;      // split mode: 4-byte packed pairs move like fp32 words
   return make_map(map, f32, ptr, rows, K, K, f32 ? 32 : 64, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 // 32 x 32 epilogue slab of an [M, cols] output / residual tensor.

@@ -76,9 +76,7 @@ static int launch_layernorm_t(const LayerNormArgs& a, cudaStream_t stream) {
 }
 
 int launch_layernorm(int precision, const LayerNormArgs& a, cudaStream_t stream) {
-  if (precision == EC_PREC_TF32) return launch_layernorm_t<float>(a, stream);
-  if (precision == EC_PREC_BF16) return launch_layernorm_t<__nv_bfloat16>(a, stream);
-  EC_FAIL("unknown precision");
+  EC_DISPATCH_PREC(precision, return launch_layernorm_t<ActT>(a, stream));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -94,9 +92,26 @@ int launch_cast_rows(int precision, const float* src, void* dst, size_t n, cudaS
   if (n == 0) return EC_OK;
   const int threads = 256;
   const int blocks = static_cast<int>(std::min<size_t>((n + threads - 1) / threads, 148 * 8));
-  if (precision == EC_PREC_TF32) cast_kernel<float><<<blocks, threads, 0, stream>>>(src, reinterpret_cast<float*>(dst), n);
-  else if (precision == EC_PREC_BF16) cast_kernel<__nv_bfloat16><<<blocks, threads, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
-  else EC_FAIL("unknown precision");
+  EC_DISPATCH_PREC(precision, (cast_kernel<ActT><<<blocks, threads, 0, stream>>>(src, reinterpret_cast<ActT*>(dst), n)));
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+
+// Weight operand of a GEMM: the activation-type cast and, in split mode, the second plane with the halves swapped at
+// dst + twin_elems (see effconf_b200.h, EC_PREC_BF16X2).
+__global__ void cast_weight_split_kernel(const float* __restrict__ src, uint32_t* __restrict__ dst, size_t n, size_t twin_elems) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t v = split_pack(src[i]);
+    dst[i] = v;
+    dst[twin_elems + i] = split_swap(v);
+  }
+}
+int launch_cast_weight(int precision, const float* src, void* dst, size_t n, size_t twin_elems, cudaStream_t stream) {
+  if (precision != EC_PREC_BF16X2) return launch_cast_rows(precision, src, dst, n, stream);
+  if (n == 0) return EC_OK;
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 8));
+  cast_weight_split_kernel<<<blocks, 256, 0, stream>>>(src, reinterpret_cast<uint32_t*>(dst), n, twin_elems);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -136,19 +151,19 @@ __global__ void glu_interleave_kernel(const float* __restrict__ w, const float* 
   const int ch = tile * nb + (gate ? r - nb : r);
   const bool valid = ch < C;
   const int src_row = gate ? C + ch : ch;
-  for (int k = threadIdx.x; k < K; k += blockDim.x)
-    w_out[static_cast<size_t>(row) * K + k] = ActTraits<T>::to(valid ? w[static_cast<size_t>(src_row) * K + k] : 0.f);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const T v = ActTraits<T>::to(valid ? w[static_cast<size_t>(src_row) * K + k] : 0.f);
+    w_out[static_cast<size_t>(row) * K + k] = v;
+    if constexpr (IsSplit<T>::value)     // swapped plane of the [2, rows, K] weight operand
+      w_out[(static_cast<size_t>(gridDim.x) + row) * K + k] = SplitBf16{split_swap(v.bits)};
+  }
   if (threadIdx.x == 0) b_out[row] = valid ? b[src_row] : 0.f;
 }
 
 int launch_glu_interleave(int precision, const float* w, const float* b, int channels, int K, int nb, int tiles,
                           void* w_out, float* b_out, cudaStream_t stream) {
   const int rows = tiles * 2 * nb;
-  if (precision == EC_PREC_TF32)
-    glu_interleave_kernel<float><<<rows, 128, 0, stream>>>(w, b, channels, K, nb, tiles, reinterpret_cast<float*>(w_out), b_out);
-  else if (precision == EC_PREC_BF16)
-    glu_interleave_kernel<__nv_bfloat16><<<rows, 128, 0, stream>>>(w, b, channels, K, nb, tiles, reinterpret_cast<__nv_bfloat16*>(w_out), b_out);
-  else EC_FAIL("unknown precision");
+  EC_DISPATCH_PREC(precision, (glu_interleave_kernel<ActT><<<rows, 128, 0, stream>>>(w, b, channels, K, nb, tiles, reinterpret_cast<ActT*>(w_out), b_out)));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }

@@ -99,7 +99,7 @@ static size_t layout_weights(ec_engine* e, void* arena) {
   const size_t es = e->esize;
   Weights& w = e->w;
   auto f32 = [&](size_t n) { return reinterpret_cast<float*>(a.take(n * 4)); };
-  auto act = [&](size_t n) { return a.take(n * es); };
+  auto act = [&](size_t n) { return a.take(n * es * weight_planes(e->precision)); };   // GEMM weight operand (split mode: two planes)
   const int C = c.sub_filters, D0 = c.blocks[0].dim_model;
   w.sub_w = f32(C * 9); w.sub_b = f32(C);
   if (c.sub_layers == 2) { w.sub2_w = act(static_cast<size_t>(c.sub_filters2) * 9 * C); w.sub2_b = f32(c.sub_filters2); }
@@ -285,7 +285,7 @@ int ec_device_check(void) {
 
 int ec_engine_create(const ec_config* cfg, int precision, ec_engine** out) {
   EC_REQUIRE(cfg != nullptr && out != nullptr, "null argument");
-  EC_REQUIRE(precision == EC_PREC_TF32 || precision == EC_PREC_BF16, "unknown precision");
+  EC_REQUIRE(precision == EC_PREC_TF32 || precision == EC_PREC_BF16 || precision == EC_PREC_BF16X2, "unknown precision");
   EC_REQUIRE(cfg->num_blocks >= 1 && cfg->num_blocks <= EC_MAX_BLOCKS, "num_blocks out of range");
   EC_REQUIRE(cfg->n_mels > 0 && cfg->n_mels % 2 == 0 && cfg->sub_filters > 0, "bad front-end config");
   EC_REQUIRE(cfg->sub_layers >= 0 && cfg->sub_layers <= 2, "1 or 2 Conv2d subsampling layers are supported");
@@ -302,7 +302,7 @@ int ec_engine_create(const ec_config* cfg, int precision, ec_engine** out) {
   }
   ec_engine* e = new ec_engine();
   e->cfg = *cfg; if (e->cfg.sub_layers == 0) e->cfg.sub_layers = 1;
-  e->precision = precision; e->esize = precision == EC_PREC_TF32 ? 4 : 2; e->prepared = false;
+  e->precision = precision; e->esize = act_esize(precision); e->prepared = false;
   e->weight_bytes = layout_weights(e, nullptr);
   *out = e;
   return EC_OK;
@@ -348,9 +348,10 @@ int ec_engine_prepare(ec_engine* e, const ec_raw_weights* raw, void* arena, void
     EC_CUDA(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, st));
     return EC_OK;
   };
-  auto cast = [&](void* dst, const float* src, size_t n) -> int {
+  // weight operand of a GEMM; twin = element distance to the swapped plane of the split mode (default: right behind the n elements)
+  auto cast = [&](void* dst, const float* src, size_t n, size_t twin = 0) -> int {
     EC_REQUIRE(src != nullptr, "missing raw weight pointer");
-    return launch_cast_rows(prec, src, dst, n, st);
+    return launch_cast_weight(prec, src, dst, n, twin != 0 ? twin : n, st);
   };
   const int C = c.sub_filters, D0 = c.blocks[0].dim_model;
   EC_REQUIRE(raw->sub_conv_w && raw->sub_conv_b && raw->sub_bn_w && raw->sub_bn_b && raw->sub_bn_rm && raw->sub_bn_rv, "missing subsampling weights");
@@ -382,7 +383,7 @@ int ec_engine_prepare(ec_engine* e, const ec_raw_weights* raw, void* arena, void
     EC_TRY(cp(b.u, r.u, D)); EC_TRY(cp(b.v, r.v, D));
     const size_t dd = static_cast<size_t>(D) * D;
     uint8_t* wqkv = reinterpret_cast<uint8_t*>(b.wqkv);
-    EC_TRY(cast(wqkv, r.wq, dd)); EC_TRY(cast(wqkv + dd * e->esize, r.wk, dd)); EC_TRY(cast(wqkv + 2 * dd * e->esize, r.wv, dd));
+    EC_TRY(cast(wqkv, r.wq, dd, 3 * dd)); EC_TRY(cast(wqkv + dd * e->esize, r.wk, dd, 3 * dd)); EC_TRY(cast(wqkv + 2 * dd * e->esize, r.wv, dd, 3 * dd));
     EC_TRY(cp(b.bqkv, r.bq, D)); EC_TRY(cp(b.bqkv + D, r.bk, D)); EC_TRY(cp(b.bqkv + 2 * D, r.bv, D));
     EC_TRY(cast(b.wo, r.wo, dd)); EC_TRY(cp(b.bo, r.bo, D));
     EC_TRY(cast(b.wpos, r.wpos, dd)); EC_TRY(cp(b.bpos, r.bpos, D));
@@ -444,7 +445,8 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
     const int D = bc.dim_model, T = sh.t_in[i], G = bc.group_size, P = (G - T % G) % G, e_rows = 2 * (T + P) - G;
     EC_REQUIRE(relpos[i] != nullptr, "missing relative position table");
     float* eb = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws.ebuf) + i * ws.e_stride);
-    const bool a16 = prec == EC_PREC_BF16 && ((G * D) / bc.num_heads) % 2 == 0 && D % 2 == 0;
+    // activation-type (bf16 / packed) E straight from the epilogue, else TF32-rounded fp32
+    const bool a16 = prec == EC_PREC_BF16X2 || (prec == EC_PREC_BF16 && ((G * D) / bc.num_heads) % 2 == 0 && D % 2 == 0);
     EC_TRY(gemm(e, e->side, PC_POS, relpos[i], w.blk[i].wpos, e_rows, D, D, w.blk[i].bpos, 1.f, GEMM_ACT_NONE, nullptr, a16 ? nullptr : eb,
                 a16 ? eb : nullptr, 0, 0, nullptr, 1));
   }
@@ -518,7 +520,7 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
     std::swap(x, x_alt);
     // MHSA: x2 = x1 + Wo attn(LN(x1)); also emits xn = LN_conv(x2) and the strided copy xs (conv_res operand)
     // q|k|v and E feed the attention kernel: TF32-rounded fp32 in parity mode, bf16 in fast mode
-    const bool a16 = prec == EC_PREC_BF16 && ((bc.group_size * D) / bc.num_heads) % 2 == 0 && D % 2 == 0;
+    const bool a16 = prec == EC_PREC_BF16X2 || (prec == EC_PREC_BF16 && ((bc.group_size * D) / bc.num_heads) % 2 == 0 && D % 2 == 0);
     EC_TRY(gemm(e, st, PC_QKV, ws.xn, b.wqkv, M, 3 * D, D, b.bqkv, 1.f, GEMM_ACT_NONE, nullptr, a16 ? nullptr : ws.qkv, a16 ? ws.qkv : nullptr, 0, 0, nullptr, 1));
     const int G = bc.group_size, P = (G - T % G) % G, e_rows = 2 * (T + P) - G;
     if (!joined) { EC_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0)); joined = true; }     // join: E_i of every block is ready
@@ -750,6 +752,10 @@ int ec_op_glu_bwd(int precision, const void* zg, const float* dy, size_t rows, i
 int ec_op_cast(int precision, const float* src, void* dst, size_t n, void* stream) {
   return launch_cast_rows(precision, src, dst, n, reinterpret_cast<cudaStream_t>(stream));
 }
+int ec_op_cast_weight(int precision, const float* src, size_t n, void* dst, void* stream) {
+  return launch_cast_weight(precision, src, dst, n, n, reinterpret_cast<cudaStream_t>(stream));
+}
+int ec_weight_planes(int precision) { return static_cast<int>(weight_planes(precision)); }
 int ec_op_layernorm(int precision, const float* x, int rows, int dim, const float* gamma, const float* beta, float eps, void* y_act,
                     float* y_f32, void* stream) {
   LayerNormArgs a{};

@@ -69,7 +69,7 @@ constexpr int kNumBars = 2 * kMaxStages + 1 + 32;
 template <typename T, bool kLN>
 __global__ void __launch_bounds__(576, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmOutF,
+               const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmOutF,
                const __grid_constant__ CUtensorMap tmOutA, const __grid_constant__ CUtensorMap tmLn, const GemmDev p) {
   using Tr = ActTraits<T>;
   extern __shared__ uint8_t smem_raw[];
@@ -79,7 +79,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int stage_bytes = kATileBytes + p.block_n * 128;
+  constexpr bool kSplit = IsSplit<T>::value;       // split mode: a second W tile (halves swapped) and a second MMA per k-slice
+  const int b_tile_bytes = p.block_n * 128;
+  const int stage_bytes = kATileBytes + (kSplit ? 2 : 1) * b_tile_bytes;
   constexpr int kEpiWarps = 16, kHalves = kEpiWarps / 4;                 // warps per lane quarter = chunk interleave factor
   const int res_bytes = p.has_res ? kEpiWarps * p.res_depth * kSlabBytes : 0;     // res_depth 0: residual lands in the x slabs
   uint8_t* res_ring = base_ptr + p.pipe_bytes;
@@ -131,6 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t a_dst = base + s * stage_bytes;
         tma_load_2d(a_dst, &tmA, full_bar(s), kb * Tr::kBlockK, m0);
         tma_load_2d(a_dst + kATileBytes, &tmB, full_bar(s), kb * Tr::kBlockK, w_row0);
+        if constexpr (kSplit) tma_load_2d(a_dst + kATileBytes + b_tile_bytes, &tmB2, full_bar(s), kb * Tr::kBlockK, w_row0);
         if (kb == 0) stamp(p.dbg, 3);
       }
       __syncwarp();
@@ -147,8 +150,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (elect_one()) {
         if (kb == 0) stamp(p.dbg, 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)     // 4 x 32-byte K slices inside the 128-byte swizzle row: start address advances by 32 B
+        for (int k = 0; k < 4; ++k) {   // 4 x 32-byte K slices inside the 128-byte swizzle row: start address advances by 32 B
           tc_mma<Tr::kTf32>(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          if constexpr (kSplit)         // [ah al] . [wl wh]: the cross terms, against the swapped plane of the weight operand
+            tc_mma<false>(tmem_base, da + 2 * k, make_smem_desc_sw128(base + s * stage_bytes + kATileBytes + b_tile_bytes) + 2 * k, idesc, 1u);
+        }
         tc_commit(empty_bar(s));         // frees the smem slot when these MMAs retire
         if (kb == p.num_k_blocks - 1) { tc_commit(tmem_full_bar); stamp(p.dbg, 5); }   // accumulator complete
       }
@@ -462,9 +468,9 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   }
   p.num_k_blocks = cdiv(a.K, Tr::kBlockK);
   p.has_res = a.residual != nullptr; p.has_out_f32 = a.out_f32 != nullptr; p.has_out_act = a.out_act != nullptr;
-  const int stage_bytes = kATileBytes + p.block_n * 128;
+  const int stage_bytes = kATileBytes + (IsSplit<T>::value ? 2 : 1) * p.block_n * 128;
   const int n_chunks = cdiv(std::min(a.glu_nb > 0 ? a.glu_nb : p.block_n, out_cols), 32);
-  const int a_slab = precision == EC_PREC_TF32 ? kSlabBytes : kSlabBytes / 2;
+  const int a_slab = sizeof(T) == 4 ? kSlabBytes : kSlabBytes / 2;
   static const int epi_batch_env = [] { const char* e = getenv("EFFCONF_EPI_BATCH"); return (e != nullptr && e[0] == '1') ? 1 : 0; }();
   const int per_chunk = (p.has_out_f32 ? kSlabBytes : 0) + (p.has_out_act ? a_slab : 0);
   p.res_depth = 1;
@@ -524,10 +530,15 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
     EC_REQUIRE(a.copy_out == nullptr || a.ln_mode == 1, "the strided copy is only available with a single LayerNorm");
   }
 
-  CUtensorMap tmA, tmB, tmRes, tmOutF, tmOutA, tmLn;
+  CUtensorMap tmA, tmB, tmB2, tmRes, tmOutF, tmOutA, tmLn;
   EC_TRY(make_operand_map(&tmA, precision, a.A, a.M, a.K, kBlockM));
   EC_TRY(make_operand_map(&tmB, precision, a.W, a.N, a.K, p.block_n));
-  const bool act_f32 = precision == EC_PREC_TF32;
+  tmB2 = tmB;
+  if (IsSplit<T>::value) {            // plane 1 of the [2, N, K] weight operand: (lo, hi)
+    const uint8_t* twin = reinterpret_cast<const uint8_t*>(a.W) + (a.w_twin_bytes != 0 ? a.w_twin_bytes : static_cast<size_t>(a.N) * a.K * 4);
+    EC_TRY(make_operand_map(&tmB2, precision, twin, a.N, a.K, p.block_n));
+  }
+  const bool act_f32 = sizeof(T) == 4;
   tmRes = tmA; tmOutF = tmA; tmOutA = tmA; tmLn = tmA;       // placeholders for unused maps
   if (a.residual != nullptr) EC_TRY(make_slab_map(&tmRes, true, a.residual, a.M, out_cols, a.ld_res));
   if (a.out_f32 != nullptr) EC_TRY(make_slab_map(&tmOutF, true, a.out_f32, a.M, out_cols, a.ld_out));
@@ -549,7 +560,7 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   });
   EC_CUDA(attr_err);
   dim3 grid(cdiv(a.M, kBlockM), tiles_n);
-  EC_TRY(launch_pdl(gemm_tc_kernel<T, kLN>, grid, dim3(576), smem, stream, tmA, tmB, tmRes, tmOutF, tmOutA, tmLn, p));
+  EC_TRY(launch_pdl(gemm_tc_kernel<T, kLN>, grid, dim3(576), smem, stream, tmA, tmB, tmB2, tmRes, tmOutF, tmOutA, tmLn, p));
   return EC_OK;
 }
 
@@ -566,6 +577,8 @@ int launch_gemm(int precision, const GemmArgs& a, cudaStream_t stream) {
   if (precision == EC_PREC_TF32) return a.ln_mode ? launch_gemm_t<float, true>(precision, a, stream) : launch_gemm_t<float, false>(precision, a, stream);
   if (precision == EC_PREC_BF16)
     return a.ln_mode ? launch_gemm_t<__nv_bfloat16, true>(precision, a, stream) : launch_gemm_t<__nv_bfloat16, false>(precision, a, stream);
+  if (precision == EC_PREC_BF16X2)
+    return a.ln_mode ? launch_gemm_t<SplitBf16, true>(precision, a, stream) : launch_gemm_t<SplitBf16, false>(precision, a, stream);
   EC_FAIL("unknown precision");
 }
 

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(512) subsample_conv_kernel(const float* __rest
       if (f + 1 < F2) dst[1] = o1;
     } else if (pair_ok) {
       if constexpr (sizeof(T) == 2) *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(o0, o1);
-      else *reinterpret_cast<float2*>(dst) = make_float2(Tr::to(o0), Tr::to(o1));
+      else *reinterpret_cast<float2*>(dst) = make_float2(Tr::word(o0), Tr::word(o1));
     } else {
       dst[0] = Tr::to(o0);
       if (f + 1 < F2) dst[1] = Tr::to(o1);
@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(256) subsample_conv_cl_kernel(const float* __r
       pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
       *reinterpret_cast<uint4*>(dst) = pk;
     } else {
-      *reinterpret_cast<float4*>(dst) = make_float4(Tr::to(o[0]), Tr::to(o[1]), Tr::to(o[2]), Tr::to(o[3]));
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(Tr::to(o[4]), Tr::to(o[5]), Tr::to(o[6]), Tr::to(o[7]));
+      *reinterpret_cast<float4*>(dst) = make_float4(Tr::word(o[0]), Tr::word(o[1]), Tr::word(o[2]), Tr::word(o[3]));
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(Tr::word(o[4]), Tr::word(o[5]), Tr::word(o[6]), Tr::word(o[7]));
     }
   }
 }
@@ -156,13 +156,8 @@ int launch_subsample_conv_cl(int precision, const SubsampleArgs& a, cudaStream_t
   dim3 block(cg, std::max(1, 256 / cg));
   const size_t smem = sizeof(float) * ((a.F + 2) * (2 * kSubTT + 2));
   EC_REQUIRE(smem <= 48 * 1024, "subsampling patch does not fit in shared memory");
-  if (precision == EC_PREC_TF32)
-    return launch_pdl(subsample_conv_cl_kernel<float>, grid, block, smem, stream, a.mel, a.w, a.b, a.F, a.T, T_out, a.C,
-                      reinterpret_cast<float*>(a.y));
-  if (precision == EC_PREC_BF16)
-    return launch_pdl(subsample_conv_cl_kernel<__nv_bfloat16>, grid, block, smem, stream, a.mel, a.w, a.b, a.F, a.T, T_out, a.C,
-                      reinterpret_cast<__nv_bfloat16*>(a.y));
-  EC_FAIL("unknown precision");
+  EC_DISPATCH_PREC(precision, return launch_pdl(subsample_conv_cl_kernel<ActT>, grid, block, smem, stream, a.mel, a.w, a.b, a.F, a.T, T_out, a.C,
+                                                reinterpret_cast<ActT*>(a.y)));
 }
 
 // im2col of a channels-last map for a 3x3 / stride 2 / pad 1 convolution: row (b, t2, f2), column (kh*3 + kw)*C + c holds
@@ -195,19 +190,12 @@ __global__ void __launch_bounds__(256) im2col_3x3s2_kernel(const T* __restrict__
 
 int launch_im2col_3x3s2(int precision, const void* y0, int B, int T1, int F1, int C, void* A, cudaStream_t stream) {
   const int T2 = (T1 - 1) / 2 + 1, F2 = (F1 - 1) / 2 + 1;
-  const size_t vecs = static_cast<size_t>(B) * T2 * F2 * 9 * (C / (precision == EC_PREC_TF32 ? 4 : 8));
+  const int vec = static_cast<int>(16 / act_esize(precision));
+  const size_t vecs = static_cast<size_t>(B) * T2 * F2 * 9 * (C / vec);
   const int blocks = static_cast<int>(std::min<size_t>((vecs + 255) / 256, 148 * 32));
-  if (precision == EC_PREC_TF32) {
-    EC_REQUIRE(C % 4 == 0, "im2col needs C % 4 == 0");
-    return launch_pdl(im2col_3x3s2_kernel<float>, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const float*>(y0), B, T1, F1, C, T2, F2,
-                      reinterpret_cast<float*>(A));
-  }
-  if (precision == EC_PREC_BF16) {
-    EC_REQUIRE(C % 8 == 0, "im2col needs C % 8 == 0");
-    return launch_pdl(im2col_3x3s2_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(y0), B, T1, F1,
-                      C, T2, F2, reinterpret_cast<__nv_bfloat16*>(A));
-  }
-  EC_FAIL("unknown precision");
+  EC_REQUIRE(C % vec == 0, "im2col needs whole 16-byte channel vectors");
+  EC_DISPATCH_PREC(precision, return launch_pdl(im2col_3x3s2_kernel<ActT>, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const ActT*>(y0), B, T1,
+                                                F1, C, T2, F2, reinterpret_cast<ActT*>(A)));
 }
 
 // Weight preparation of the second layer: eval BatchNorm2d folded into the taps and bias, K order (kh, kw, c_in).
@@ -219,18 +207,16 @@ __global__ void conv2_weight_prep_kernel(const float* __restrict__ w, const floa
   if (i >= static_cast<size_t>(C2) * 9 * C) return;
   const int co = static_cast<int>(i / (9 * C)), r = static_cast<int>(i % (9 * C)), k = r / C, ci = r % C;
   const float s = g[co] / sqrtf(rv[co] + eps);
-  w_out[i] = ActTraits<T>::to(w[(static_cast<size_t>(co) * C + ci) * 9 + k] * s);
+  const T v = ActTraits<T>::to(w[(static_cast<size_t>(co) * C + ci) * 9 + k] * s);
+  w_out[i] = v;
+  if constexpr (IsSplit<T>::value) w_out[static_cast<size_t>(C2) * 9 * C + i] = SplitBf16{split_swap(v.bits)};   // swapped plane
   if (r == 0) b_out[co] = (b[co] - rm[co]) * s + beta[co];
 }
 int launch_conv2_weight_prep(int precision, const float* w, const float* b, const float* g, const float* beta, const float* rm,
                              const float* rv, float eps, int C2, int C, void* w_out, float* b_out, cudaStream_t stream) {
   const size_t n = static_cast<size_t>(C2) * 9 * C;
   const int blocks = static_cast<int>((n + 255) / 256);
-  if (precision == EC_PREC_TF32)
-    conv2_weight_prep_kernel<float><<<blocks, 256, 0, stream>>>(w, b, g, beta, rm, rv, eps, C2, C, reinterpret_cast<float*>(w_out), b_out);
-  else if (precision == EC_PREC_BF16)
-    conv2_weight_prep_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(w, b, g, beta, rm, rv, eps, C2, C, reinterpret_cast<__nv_bfloat16*>(w_out), b_out);
-  else EC_FAIL("unknown precision");
+  EC_DISPATCH_PREC(precision, (conv2_weight_prep_kernel<ActT><<<blocks, 256, 0, stream>>>(w, b, g, beta, rm, rv, eps, C2, C, reinterpret_cast<ActT*>(w_out), b_out)));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -243,15 +229,14 @@ __global__ void linear_weight_permute_kernel(const float* __restrict__ w, int D,
   if (i >= D * K) return;
   const size_t d = i / K, r = i % K;
   const int f = static_cast<int>(r / C), c = static_cast<int>(r % C);
-  out[i] = ActTraits<T>::to(w[d * K + static_cast<size_t>(c) * Fq + f]);
+  const T v = ActTraits<T>::to(w[d * K + static_cast<size_t>(c) * Fq + f]);
+  out[i] = v;
+  if constexpr (IsSplit<T>::value) out[D * K + i] = SplitBf16{split_swap(v.bits)};   // swapped plane
 }
 int launch_linear_weight_permute(int precision, const float* w, int D, int C, int Fq, void* out, cudaStream_t stream) {
   const size_t n = static_cast<size_t>(D) * C * Fq;
   const int blocks = static_cast<int>((n + 255) / 256);
-  if (precision == EC_PREC_TF32) linear_weight_permute_kernel<float><<<blocks, 256, 0, stream>>>(w, D, C, Fq, reinterpret_cast<float*>(out));
-  else if (precision == EC_PREC_BF16)
-    linear_weight_permute_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(w, D, C, Fq, reinterpret_cast<__nv_bfloat16*>(out));
-  else EC_FAIL("unknown precision");
+  EC_DISPATCH_PREC(precision, (linear_weight_permute_kernel<ActT><<<blocks, 256, 0, stream>>>(w, D, C, Fq, reinterpret_cast<ActT*>(out))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -277,13 +262,8 @@ int launch_subsample_conv(int precision, const SubsampleArgs& a, cudaStream_t st
   EC_REQUIRE(block.x * block.y <= 512, "n_mels too large for the subsampling kernel");
   const size_t smem = sizeof(float) * ((a.F + 3) * (2 * kSubTT + 2) + a.C * 12);
   EC_REQUIRE(smem <= 48 * 1024, "subsampling patch does not fit in shared memory");
-  if (precision == EC_PREC_TF32)
-    return launch_pdl(subsample_conv_kernel<float, false>, grid, block, smem, stream, a.mel, a.w, a.b, a.F, a.T, T_out, a.C,
-                      reinterpret_cast<float*>(a.y));
-  if (precision == EC_PREC_BF16)
-    return launch_pdl(subsample_conv_kernel<__nv_bfloat16, false>, grid, block, smem, stream, a.mel, a.w, a.b, a.F, a.T, T_out, a.C,
-                      reinterpret_cast<__nv_bfloat16*>(a.y));
-  EC_FAIL("unknown precision");
+  EC_DISPATCH_PREC(precision, return launch_pdl(subsample_conv_kernel<ActT, false>, grid, block, smem, stream, a.mel, a.w, a.b, a.F, a.T, T_out,
+                                                a.C, reinterpret_cast<ActT*>(a.y)));
 }
 
 }  // namespace ec

@@ -65,30 +65,26 @@ __global__ void __launch_bounds__(256) cast_scaled_kernel(const float* __restric
 }
 static int grid_for(size_t n);
 int launch_cast_scaled(int precision, const float* src, float scale, size_t n, void* dst, cudaStream_t st) {
-  if (precision == EC_PREC_TF32) cast_scaled_kernel<float><<<grid_for(n), 256, 0, st>>>(src, scale, n, reinterpret_cast<float*>(dst));
-  else cast_scaled_kernel<__nv_bfloat16><<<grid_for(n), 256, 0, st>>>(src, scale, n, reinterpret_cast<__nv_bfloat16*>(dst));
+  EC_DISPATCH_PREC(precision, (cast_scaled_kernel<ActT><<<grid_for(n), 256, 0, st>>>(src, scale, n, reinterpret_cast<ActT*>(dst))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
 static int grid_for(size_t n) { return static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16)); }
 
 int launch_swish_fwd(int precision, const void* z, size_t n, void* h, cudaStream_t st) {
-  if (precision == EC_PREC_TF32) swish_fwd_kernel<float><<<grid_for(n), 256, 0, st>>>(reinterpret_cast<const float*>(z), n, reinterpret_cast<float*>(h));
-  else swish_fwd_kernel<__nv_bfloat16><<<grid_for(n), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(z), n, reinterpret_cast<__nv_bfloat16*>(h));
+  EC_DISPATCH_PREC(precision, (swish_fwd_kernel<ActT><<<grid_for(n), 256, 0, st>>>(reinterpret_cast<const ActT*>(z), n, reinterpret_cast<ActT*>(h))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
 int launch_glu_fwd(int precision, const void* zg, size_t rows, int C, void* out, cudaStream_t st) {
-  if (precision == EC_PREC_TF32) glu_fwd_kernel<float><<<grid_for(rows * C), 256, 0, st>>>(reinterpret_cast<const float*>(zg), rows, C, reinterpret_cast<float*>(out));
-  else glu_fwd_kernel<__nv_bfloat16><<<grid_for(rows * C), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(zg), rows, C, reinterpret_cast<__nv_bfloat16*>(out));
+  EC_DISPATCH_PREC(precision, (glu_fwd_kernel<ActT><<<grid_for(rows * C), 256, 0, st>>>(reinterpret_cast<const ActT*>(zg), rows, C, reinterpret_cast<ActT*>(out))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
 int launch_strided_rows(int precision, const float* x, int B, int T_in, int D, int stride, void* out, cudaStream_t st) {
   const int T_out = (T_in - 1) / stride + 1;
   const size_t n = static_cast<size_t>(B) * T_out * D;
-  if (precision == EC_PREC_TF32) strided_rows_kernel<float><<<grid_for(n), 256, 0, st>>>(x, B, T_in, T_out, D, stride, reinterpret_cast<float*>(out));
-  else strided_rows_kernel<__nv_bfloat16><<<grid_for(n), 256, 0, st>>>(x, B, T_in, T_out, D, stride, reinterpret_cast<__nv_bfloat16*>(out));
+  EC_DISPATCH_PREC(precision, (strided_rows_kernel<ActT><<<grid_for(n), 256, 0, st>>>(x, B, T_in, T_out, D, stride, reinterpret_cast<ActT*>(out))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }

@@ -38,6 +38,7 @@ template <typename TOut, bool kRound> __device__ __forceinline__ TOut drop_store
 template <> __device__ __forceinline__ float drop_store<float, false>(float x) { return x; }               // true fp32 (residual stream, gradients)
 template <> __device__ __forceinline__ float drop_store<float, true>(float x) { return round_tf32(x); }    // TF32-mode GEMM operand
 template <> __device__ __forceinline__ __nv_bfloat16 drop_store<__nv_bfloat16, true>(float x) { return __float2bfloat16_rn(x); }
+template <> __device__ __forceinline__ SplitBf16 drop_store<SplitBf16, true>(float x) { return SplitBf16{split_pack(x)}; }
 template <typename TIn, typename TOut, bool kRound>
 __global__ void __launch_bounds__(256) dropout_kernel(const TIn* __restrict__ src, float scale, size_t n, TOut* __restrict__ dst,
                                                       const unsigned long long* __restrict__ ctr, unsigned site, unsigned keep16) {
@@ -101,13 +102,17 @@ int launch_dropout(int precision, const void* src, int src_f32, float scale, siz
   const int grid = grid_for((n + 3) / 4);
   if (n == 0) return EC_OK;
   using bf = __nv_bfloat16;
-  const float* s32 = static_cast<const float*>(src); const bf* s16 = static_cast<const bf*>(src);
-  float* d32 = static_cast<float*>(dst); bf* d16 = static_cast<bf*>(dst);
+  const float* s32 = static_cast<const float*>(src); const bf* s16 = static_cast<const bf*>(src); const SplitBf16* sx = static_cast<const SplitBf16*>(src);
+  float* d32 = static_cast<float*>(dst); bf* d16 = static_cast<bf*>(dst); SplitBf16* dx = static_cast<SplitBf16*>(dst);
   if (dst_f32) {
     if (sf) dropout_kernel<float, float, false><<<grid, 256, 0, st>>>(s32, scale, n, d32, ctr, site, k);
+    else if (precision == EC_PREC_BF16X2) dropout_kernel<SplitBf16, float, false><<<grid, 256, 0, st>>>(sx, scale, n, d32, ctr, site, k);
     else dropout_kernel<bf, float, false><<<grid, 256, 0, st>>>(s16, scale, n, d32, ctr, site, k);
   } else if (precision == EC_PREC_TF32) {
     dropout_kernel<float, float, true><<<grid, 256, 0, st>>>(s32, scale, n, d32, ctr, site, k);
+  } else if (precision == EC_PREC_BF16X2) {
+    if (sf) dropout_kernel<float, SplitBf16, true><<<grid, 256, 0, st>>>(s32, scale, n, dx, ctr, site, k);
+    else dropout_kernel<SplitBf16, SplitBf16, true><<<grid, 256, 0, st>>>(sx, scale, n, dx, ctr, site, k);
   } else {
     if (sf) dropout_kernel<float, bf, true><<<grid, 256, 0, st>>>(s32, scale, n, d16, ctr, site, k);
     else dropout_kernel<bf, bf, true><<<grid, 256, 0, st>>>(s16, scale, n, d16, ctr, site, k);
@@ -234,21 +239,27 @@ int ec_op_stats_merge_ranks(const float* gathered, const float* counts, int worl
 
 // ---- pack: gather n separately allocated fp32 tensors into one flat arena (gradient bucket for the all-reduce / Adam) ----------
 namespace ec {
+template <bool kAcc>
 __global__ void __launch_bounds__(256) pack_flat_kernel(const float* const* __restrict__ srcs, const long long* __restrict__ offsets,
                                                         const long long* __restrict__ sizes, float* __restrict__ arena) {
   const float* __restrict__ src = srcs[blockIdx.y];
   float* __restrict__ dst = arena + offsets[blockIdx.y];
   const long long n = sizes[blockIdx.y];
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
-    dst[i] = src[i];
+    dst[i] = kAcc ? dst[i] + src[i] : src[i];
 }
 }  // namespace ec
-extern "C" int ec_op_pack_flat(const float* const* srcs, const long long* offsets, const long long* sizes, int n, float* arena, void* stream) {
+extern "C" int ec_op_pack_flat_acc(const float* const* srcs, const long long* offsets, const long long* sizes, int n, float* arena, int accumulate,
+                                   void* stream) {
   EC_REQUIRE(srcs && offsets && sizes && arena && n >= 0 && n <= 65535, "bad argument");
   if (n == 0) return EC_OK;
-  ec::pack_flat_kernel<<<dim3(8, n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(srcs, offsets, sizes, arena);
+  if (accumulate) ec::pack_flat_kernel<true><<<dim3(8, n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(srcs, offsets, sizes, arena);
+  else ec::pack_flat_kernel<false><<<dim3(8, n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(srcs, offsets, sizes, arena);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
+}
+extern "C" int ec_op_pack_flat(const float* const* srcs, const long long* offsets, const long long* sizes, int n, float* arena, void* stream) {
+  return ec_op_pack_flat_acc(srcs, offsets, sizes, n, arena, 0, stream);
 }
 
 // ---- Swish fused with its dropout (feed-forward module, reference models/modules.py:388-389) --------------------------------------
@@ -295,9 +306,29 @@ __global__ void __launch_bounds__(256) transpose_cast_multi_kernel(const float* 
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
       const int c = c0 + i, r = r0 + tx;
-      if (c < cols && r < rows) dst[static_cast<size_t>(c) * rows + r] = ActTraits<T>::to(tile[tx][i]);
+      if (c < cols && r < rows) {
+        const T v = ActTraits<T>::to(tile[tx][i]);
+        dst[static_cast<size_t>(c) * rows + r] = v;
+        if constexpr (IsSplit<T>::value)      // swapped plane right behind the [cols, rows] operand
+          dst[static_cast<size_t>(cols) * rows + static_cast<size_t>(c) * rows + r] = SplitBf16{split_swap(v.bits)};
+      }
     }
     __syncthreads();
+  }
+}
+// ---- multi-tensor weight cast: the [N, K] forward operands of all GEMM weights in one launch (same descriptors; split mode writes
+//      the swapped plane right behind each tensor, so the destination offsets are twice the source offsets there) ----
+template <typename T>
+__global__ void __launch_bounds__(256) cast_multi_kernel(const float* __restrict__ src_arena, const long long* __restrict__ desc,
+                                                         T* __restrict__ dst_arena) {
+  const long long* d = desc + static_cast<long long>(blockIdx.y) * 4;
+  const size_t n = static_cast<size_t>(d[1]) * static_cast<size_t>(d[2]);
+  const float* __restrict__ src = src_arena + d[0];
+  T* __restrict__ dst = dst_arena + d[3];
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const T v = ActTraits<T>::to(src[i]);
+    dst[i] = v;
+    if constexpr (IsSplit<T>::value) dst[n + i] = SplitBf16{split_swap(v.bits)};
   }
 }
 }  // namespace ec
@@ -309,14 +340,8 @@ int ec_op_swish_dropout(int precision, const void* z, const float* dy, size_t n,
   const int grid = ec::grid_for((n + 3) / 4);
   const unsigned k = ec::keep16_of(p);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  using bf = __nv_bfloat16;
-  if (precision == EC_PREC_TF32) {
-    if (dy) ec::swish_dropout_kernel<float, true><<<grid, 256, 0, st>>>(static_cast<const float*>(z), dy, n, static_cast<float*>(out), counter, site, k);
-    else ec::swish_dropout_kernel<float, false><<<grid, 256, 0, st>>>(static_cast<const float*>(z), dy, n, static_cast<float*>(out), counter, site, k);
-  } else {
-    if (dy) ec::swish_dropout_kernel<bf, true><<<grid, 256, 0, st>>>(static_cast<const bf*>(z), dy, n, static_cast<bf*>(out), counter, site, k);
-    else ec::swish_dropout_kernel<bf, false><<<grid, 256, 0, st>>>(static_cast<const bf*>(z), dy, n, static_cast<bf*>(out), counter, site, k);
-  }
+  if (dy) EC_DISPATCH_PREC(precision, (ec::swish_dropout_kernel<ActT, true><<<grid, 256, 0, st>>>(static_cast<const ActT*>(z), dy, n, static_cast<ActT*>(out), counter, site, k)));
+  else EC_DISPATCH_PREC(precision, (ec::swish_dropout_kernel<ActT, false><<<grid, 256, 0, st>>>(static_cast<const ActT*>(z), dy, n, static_cast<ActT*>(out), counter, site, k)));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -326,8 +351,16 @@ int ec_op_transpose_cast_multi(int precision, const float* src_arena, const long
   if (n == 0) return EC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(ctas_per_tensor, n);
-  if (precision == EC_PREC_TF32) ec::transpose_cast_multi_kernel<float><<<grid, 256, 0, st>>>(src_arena, desc, static_cast<float*>(dst_arena));
-  else ec::transpose_cast_multi_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src_arena, desc, static_cast<__nv_bfloat16*>(dst_arena));
+  EC_DISPATCH_PREC(precision, (ec::transpose_cast_multi_kernel<ActT><<<grid, 256, 0, st>>>(src_arena, desc, static_cast<ActT*>(dst_arena))));
+  EC_CUDA(cudaGetLastError());
+  return EC_OK;
+}
+int ec_op_cast_multi(int precision, const float* src_arena, const long long* desc, int n, int ctas_per_tensor, void* dst_arena, void* stream) {
+  EC_REQUIRE(src_arena && desc && dst_arena && n >= 0 && n <= 65535 && ctas_per_tensor >= 1, "bad argument");
+  if (n == 0) return EC_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(ctas_per_tensor, n);
+  EC_DISPATCH_PREC(precision, (ec::cast_multi_kernel<ActT><<<grid, 256, 0, st>>>(src_arena, desc, static_cast<ActT*>(dst_arena))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }

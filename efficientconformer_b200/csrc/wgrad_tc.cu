@@ -189,7 +189,7 @@ static size_t wgrad_partial_bytes(int M, int N, int K) {
 }
 size_t wgrad_work_bytes(int precision, int M, int N, int K) {
   size_t b = wgrad_partial_bytes(M, N, K);
-  if (precision == EC_PREC_TF32)   // bf16 hi / lo copies of both operands (see launch_wgrad)
+  if (precision == EC_PREC_TF32 || precision == EC_PREC_BF16X2)   // bf16 hi / lo copies of both operands (see launch_wgrad)
     b += 2 * (align_up(static_cast<size_t>(M) * N * 2, 256) + align_up(static_cast<size_t>(M) * K * 2, 256));
   return b;
 }
@@ -203,6 +203,17 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     hi[i] = h;
     lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// split mode: the packed (hi, lo) pairs are taken apart into the same two bf16 planes
+__global__ void __launch_bounds__(256) unpack_bf16_kernel(const uint32_t* __restrict__ src, size_t n, __nv_bfloat16* __restrict__ hi,
+                                                          __nv_bfloat16* __restrict__ lo) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t v = src[i];
+    hi[i] = __ushort_as_bfloat16(static_cast<unsigned short>(v & 0xffffu));
+    lo[i] = __ushort_as_bfloat16(static_cast<unsigned short>(v >> 16));
   }
 }
 
@@ -243,8 +254,8 @@ int launch_wgrad(int precision, const void* dy, const void* x, int M, int N, int
                  cudaStream_t stream) {
   EC_REQUIRE(M > 0 && N > 0 && K > 0 && dy && x && dw && work, "wgrad: bad arguments");
   if (precision == EC_PREC_BF16) return launch_wgrad_t<__nv_bfloat16>(precision, dy, x, M, N, K, dw, accumulate, work, stream);
-  if (precision == EC_PREC_TF32) {
-    // Parity mode.  The tensor core reads MN-major operands only for 16-bit types (kind::tf32 with a transposed operand produces
+  if (precision == EC_PREC_TF32 || precision == EC_PREC_BF16X2) {
+    // Parity / split modes.  The tensor core reads MN-major operands only for 16-bit types (kind::tf32 with a transposed operand produces
     // nothing -- measured), so the fp32 operands are split into bf16 hi + lo parts and the product is assembled from three bf16
     // passes, dY_hi^T X_hi + dY_hi^T X_lo + dY_lo^T X_hi: 16 significant operand bits, more than the 11 of TF32.
     uint8_t* wp = reinterpret_cast<uint8_t*>(work) + wgrad_partial_bytes(M, N, K);
@@ -253,8 +264,14 @@ int launch_wgrad(int precision, const void* dy, const void* x, int M, int N, int
     __nv_bfloat16* x_hi = reinterpret_cast<__nv_bfloat16*>(wp); wp += align_up(static_cast<size_t>(M) * K * 2, 256);
     __nv_bfloat16* x_lo = reinterpret_cast<__nv_bfloat16*>(wp);
     const size_t n1 = static_cast<size_t>(M) * N, n2 = static_cast<size_t>(M) * K;
-    split_bf16_kernel<<<static_cast<int>(std::min<size_t>((n1 + 255) / 256, 148 * 16)), 256, 0, stream>>>(reinterpret_cast<const float*>(dy), n1, dy_hi, dy_lo);
-    split_bf16_kernel<<<static_cast<int>(std::min<size_t>((n2 + 255) / 256, 148 * 16)), 256, 0, stream>>>(reinterpret_cast<const float*>(x), n2, x_hi, x_lo);
+    const int g1 = static_cast<int>(std::min<size_t>((n1 + 255) / 256, 148 * 16)), g2 = static_cast<int>(std::min<size_t>((n2 + 255) / 256, 148 * 16));
+    if (precision == EC_PREC_TF32) {
+      split_bf16_kernel<<<g1, 256, 0, stream>>>(reinterpret_cast<const float*>(dy), n1, dy_hi, dy_lo);
+      split_bf16_kernel<<<g2, 256, 0, stream>>>(reinterpret_cast<const float*>(x), n2, x_hi, x_lo);
+    } else {
+      unpack_bf16_kernel<<<g1, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(dy), n1, dy_hi, dy_lo);
+      unpack_bf16_kernel<<<g2, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(x), n2, x_hi, x_lo);
+    }
     EC_CUDA(cudaGetLastError());
     EC_TRY(launch_wgrad_t<__nv_bfloat16>(EC_PREC_BF16, dy_lo, x_hi, M, N, K, dw, accumulate, work, stream));   // small terms first
     EC_TRY(launch_wgrad_t<__nv_bfloat16>(EC_PREC_BF16, dy_hi, x_lo, M, N, K, dw, 1, work, stream));

@@ -157,12 +157,13 @@ class ConformerEncoder(nn.Module):
         feat = params["subsampling_filters"][-1] * params["n_mels"] // 2 ** params["subsampling_layers"]
         self.linear = nn.Linear(feat, self.specs[0].dim_model)
         self.blocks = nn.ModuleList([ConformerBlockHolder(s) for s in self.specs])
-        assert precision in ("auto", "tf32", "bf16")
+        assert precision in ("auto", "tf32", "bf16", "bf16x2")
         self.precision = precision
         self.use_cuda_graph = use_cuda_graph
         self._head = None            # optional (weight, bias) Parameters of the CTC fc layer, attached by ModelCTC
         self._engines = {}           # precision id -> [engine handle, arena tensor, weights fingerprint]
         self._plans = {}
+        self._weights_epoch = 0      # bumped by writers that bypass tensor._version (CTCTrainStep updates parameters through raw pointers)
 
     # ---- engine plumbing ------------------------------------------------------------------------------------------
     def attach_head(self, fc: nn.Linear):
@@ -236,11 +237,16 @@ class ConformerEncoder(nn.Module):
                 r.res_w, r.res_b = p(blk.conv_res[1].weight), p(blk.conv_res[1].bias)
         return raw, keep
 
+    def mark_weights_changed(self):
+        """Parameters / running statistics were updated in place by device code that does not bump tensor._version (the native training
+        step): the inference engines re-fold and re-cast their weights on the next eval-mode forward."""
+        self._weights_epoch += 1
+
     def _fingerprint(self):
         ts = list(self.parameters()) + [b for b in self.buffers()]
         if self._head is not None:
             ts += [self._head.weight, self._head.bias]
-        return tuple((t.data_ptr(), t._version) for t in ts)
+        return (self._weights_epoch,) + tuple((t.data_ptr(), t._version) for t in ts)
 
     def _engine(self, prec: int, device):
         L = _lib.lib()
@@ -303,7 +309,9 @@ class ConformerEncoder(nn.Module):
     def _select_precision(self):
         if self.precision != "auto":
             return _lib.PRECISIONS[self.precision]
-        return _lib.PREC_BF16 if torch.is_autocast_enabled() else _lib.PREC_TF32
+        # default: the split mode (packed bf16 hi/lo operands, 16 significant bits -- the mode that meets the 1e-3 parity gate);
+        # under torch.autocast the caller has asked for reduced precision: plain bf16 operands
+        return _lib.PREC_BF16 if torch.is_autocast_enabled() else _lib.PREC_BF16X2
 
     # ---- public API -----------------------------------------------------------------------------------------------
     def forward_mel(self, mel, mel_len=None, want_logits: bool = False, clone: bool = True):
@@ -366,6 +374,7 @@ class ConformerEncoder(nn.Module):
             raise RuntimeError("no fc head attached")
         path = self.training_path()
         prec = self._select_precision()
+        self.mark_weights_changed()          # BatchNorm running statistics are updated through raw pointers below
         mel = mel.float().contiguous()
         if mel_len is not None:
             mel_len = mel_len.to(mel.device)

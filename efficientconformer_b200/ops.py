@@ -3,7 +3,7 @@ Every function takes/returns CUDA tensors and launches on the current stream; no
 import torch
 
 from . import _lib
-from ._lib import lib, check, ptr, stream_ptr, act_dtype, PRECISIONS
+from ._lib import lib, check, ptr, stream_ptr, act_dtype, weight_planes, PRECISIONS, PREC_BF16X2
 
 
 def _p(precision):
@@ -19,6 +19,27 @@ def cast(x, precision):
     return out
 
 
+def cast_weight(w, precision):
+    """fp32 [N, K] -> GEMM weight operand.  Returns the [N, K] plane-0 view of a [planes, N, K] buffer: in the split mode the plane
+    with the swapped halves sits right behind it in the same storage (which the view keeps alive) -- the layout ec_op_gemm expects."""
+    pr = _p(precision)
+    w = w.float().contiguous()
+    out = torch.empty((weight_planes(pr),) + tuple(w.shape), dtype=act_dtype(pr), device=w.device)
+    check(lib().ec_op_cast_weight(pr, ptr(w), w.numel(), ptr(out), stream_ptr()))
+    return out[0]
+
+
+def unpack(x_act, precision):
+    """Values of an activation-type tensor as fp32 (tests / debugging): identity for TF32 words, hi + lo for split-mode pairs."""
+    pr = _p(precision)
+    if pr != PREC_BF16X2:
+        return x_act.float()
+    bits = x_act.contiguous().view(torch.int32)
+    hi = (bits << 16).view(torch.float32)
+    lo = (bits & -65536).view(torch.float32)
+    return hi + lo
+
+
 def layernorm(x, gamma, beta, precision, eps=1e-6, want_f32=True, want_act=True):
     pr = _p(precision)
     x = x.float().contiguous()
@@ -31,7 +52,7 @@ def layernorm(x, gamma, beta, precision, eps=1e-6, want_f32=True, want_act=True)
 
 
 def gemm(a_act, w_act, bias, precision, alpha=1.0, act=0, residual=None, want_f32=True, want_act=False):
-    """a_act [M,K], w_act [N,K] already in the activation type."""
+    """a_act [M,K] in the activation type, w_act [N,K] a weight operand (cast_weight / transpose_cast)."""
     pr = _p(precision)
     M, K = a_act.shape
     N = w_act.shape[0]
@@ -77,7 +98,7 @@ def pointwise_glu(a_act, w_raw, b_raw, precision):
     M, K = a_act.shape
     Cc = w_raw.shape[0] // 2
     rows = lib().ec_op_glu_scratch_rows(Cc)
-    ws = torch.empty(rows, K, dtype=act_dtype(pr), device=a_act.device)
+    ws = torch.empty(weight_planes(pr) * rows, K, dtype=act_dtype(pr), device=a_act.device)
     bs = torch.empty(rows, dtype=torch.float32, device=a_act.device)
     out = torch.empty(M, Cc, dtype=act_dtype(pr), device=a_act.device)
     w2 = w_raw.float().reshape(2 * Cc, K).contiguous()
@@ -157,13 +178,13 @@ def colsum(m, precision):
 
 
 def transpose_cast(w, precision):
-    """fp32 [rows, cols] -> activation-type [cols, rows]."""
+    """fp32 [rows, cols] -> weight operand [cols, rows] (plane-0 view of [planes, cols, rows], see cast_weight)."""
     pr = _p(precision)
     w = w.float().contiguous()
     rows, cols = w.shape
-    out = torch.empty(cols, rows, dtype=act_dtype(pr), device=w.device)
+    out = torch.empty(weight_planes(pr), cols, rows, dtype=act_dtype(pr), device=w.device)
     check(lib().ec_op_transpose_cast(pr, ptr(w), rows, cols, ptr(out), stream_ptr()))
-    return out
+    return out[0]
 
 
 def linear_dgrad(dy_act, w_fp32, precision, residual=None):
@@ -497,6 +518,12 @@ def cast_into(x_f32, out_act, precision):
     """fp32 -> activation type into a preallocated tensor (the whole flat parameter arena in one launch)."""
     check(lib().ec_op_cast(_p(precision), ptr(x_f32), ptr(out_act), x_f32.numel(), stream_ptr()))
     return out_act
+
+
+def cast_multi(src_arena, desc_dev, n, dst_arena, precision, ctas_per_tensor=16):
+    """desc_dev int64 [n, 4] = (src offset, rows, cols, dst offset): every forward weight operand in one launch."""
+    check(lib().ec_op_cast_multi(_p(precision), ptr(src_arena), ptr(desc_dev), n, ctas_per_tensor, ptr(dst_arena), stream_ptr()))
+    return dst_arena
 
 
 def transpose_cast_multi(src_arena, desc_dev, n, dst_arena, precision, ctas_per_tensor=32):

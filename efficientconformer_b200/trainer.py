@@ -47,26 +47,50 @@ class FlatParams:
         self.index = {n: i for i, n in enumerate(self.names)}
         self.offsets_dev = torch.tensor(self.offsets, dtype=torch.int64, device=device)
         self.sizes_dev = torch.tensor(self.sizes, dtype=torch.int64, device=device)
-        self._ptr_host = torch.empty(len(self.names), dtype=torch.int64).pin_memory() if torch.cuda.is_available() else \
-            torch.empty(len(self.names), dtype=torch.int64)
-        self._ptr_dev = torch.empty(len(self.names), dtype=torch.int64, device=device)
+        # gradient-pointer tables: a ring of (pinned host, device, event) slots, so that an eager step that runs ahead of the GPU never
+        # rewrites a table whose host-to-device copy has not executed yet
+        pin = torch.cuda.is_available()
+        self._slots = []
+        for _ in range(4):
+            host = torch.empty(len(self.names), dtype=torch.int64)
+            self._slots.append([host.pin_memory() if pin else host, torch.empty(len(self.names), dtype=torch.int64, device=device), None])
+        self._slot = 0
 
     def grad_view(self, name):
         i = self.index[name]
         return self.grads[self.offsets[i]:self.offsets[i] + self.sizes[i]].view(self.shapes[i])
 
-    def pack(self, grads):
-        """Gather the per-parameter gradient tensors (dict name -> contiguous fp32 tensor) into `self.grads`."""
+    def new_tables(self):
+        """A private (pinned host, device) pointer-table pair for ONE captured graph: its memcpy node re-reads the pinned table on every
+        replay, so the table must never be rewritten while the graph lives.  Allocate outside the capture."""
+        host = torch.empty(len(self.names), dtype=torch.int64)
+        return (host.pin_memory() if torch.cuda.is_available() else host, torch.empty(len(self.names), dtype=torch.int64, device=self.grads.device))
+
+    def pack(self, grads, accumulate=False, tables=None):
+        """Gather the per-parameter gradient tensors (dict name -> contiguous fp32 tensor) into `self.grads` (accumulate: add to it)."""
         keep = []
+        capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+        if capturing and tables is None:
+            raise RuntimeError("FlatParams.pack under CUDA-graph capture needs private pointer tables (new_tables())")
+        if tables is not None:
+            (host, dev), ev = tables, None
+        else:
+            host, dev, ev = self._slots[self._slot]
+            if ev is not None:
+                ev.synchronize()                  # the copy that last read this host table has executed
         for i, n in enumerate(self.names):
             g = grads[n]
             if g.dtype != torch.float32 or not g.is_contiguous():
                 g = g.float().contiguous(); keep.append(g)
             assert g.numel() == self.sizes[i], n
-            self._ptr_host[i] = g.data_ptr()
-        self._ptr_dev.copy_(self._ptr_host, non_blocking=True)
-        _lib.check(_lib.lib().ec_op_pack_flat(_lib.ptr(self._ptr_dev), _lib.ptr(self.offsets_dev), _lib.ptr(self.sizes_dev), len(self.names),
-                                              _lib.ptr(self.grads), _lib.stream_ptr()))
+            host[i] = g.data_ptr()
+        dev.copy_(host, non_blocking=True)
+        if torch.cuda.is_available() and tables is None:
+            ev = torch.cuda.Event(); ev.record()
+            self._slots[self._slot][2] = ev
+            self._slot = (self._slot + 1) % len(self._slots)
+        _lib.check(_lib.lib().ec_op_pack_flat_acc(_lib.ptr(dev), _lib.ptr(self.offsets_dev), _lib.ptr(self.sizes_dev), len(self.names),
+                                                  _lib.ptr(self.grads), 1 if accumulate else 0, _lib.stream_ptr()))
         return keep
 
 
@@ -96,9 +120,11 @@ class ArenaWeights:
         self.flat = flat
         self.pr = _lib.PRECISIONS[precision] if isinstance(precision, str) else precision
         dt = _lib.act_dtype(self.pr)
-        self.arena = torch.zeros(flat.total, dtype=dt, device=device)
-        self.arena_t = torch.zeros(flat.total, dtype=dt, device=device)
-        self._fwd, self._bwd, self._qkv, desc = {}, {}, {}, []
+        # split mode: every weight operand is [2, N, K] (second plane = swapped halves), so operand offsets are twice the fp32 ones
+        pl = self.planes = _lib.weight_planes(self.pr)
+        self.arena = torch.zeros(pl * flat.total, dtype=dt, device=device)
+        self.arena_t = torch.zeros(pl * flat.total, dtype=dt, device=device)
+        self._fwd, self._bwd, self._qkv, desc, desc_f = {}, {}, {}, [], []
         params = dict(zip(flat.names, flat.tensors))
         merged = set()
         for n in flat.names:
@@ -109,25 +135,34 @@ class ArenaWeights:
             D = flat.shapes[i[0]][0]
             if all(flat.offsets[i[j]] == flat.offsets[i[0]] + j * D * D for j in range(3)):
                 o = flat.offsets[i[0]]
-                self._qkv[id(params[n])] = (self.arena[o:o + 3 * D * D].view(3 * D, D), self.arena_t[o:o + 3 * D * D].view(D, 3 * D),
+                self._qkv[id(params[n])] = (self.arena[pl * o:pl * o + 3 * D * D].view(3 * D, D),
+                                            self.arena_t[pl * o:pl * o + 3 * D * D].view(D, 3 * D),
                                             torch.zeros(3 * D, dtype=torch.float32, device=device))
-                desc.append((o, 3 * D, D, o))
+                desc.append((o, 3 * D, D, pl * o))
+                desc_f.append((o, 3 * D, D, pl * o))
                 merged.update(names)
         for n, o, shape in zip(flat.names, flat.offsets, flat.shapes):
             is_matrix = len(shape) == 2 or (len(shape) == 3 and shape[-1] == 1)
             if not is_matrix:
                 continue
             N, K = shape[0], shape[1]
-            self._fwd[id(params[n])] = self.arena[o:o + N * K].view(N, K)
             if n not in merged:
-                self._bwd[id(params[n])] = self.arena_t[o:o + N * K].view(K, N)
-                desc.append((o, N, K, o))
+                self._fwd[id(params[n])] = self.arena[pl * o:pl * o + N * K].view(N, K)
+                self._bwd[id(params[n])] = self.arena_t[pl * o:pl * o + N * K].view(K, N)
+                desc.append((o, N, K, pl * o))
+                desc_f.append((o, N, K, pl * o))
+            elif pl == 1:
+                self._fwd[id(params[n])] = self.arena[o:o + N * K].view(N, K)
         self.n_desc = len(desc)
         self.desc = torch.tensor(desc, dtype=torch.int64, device=device).contiguous()
+        self.desc_f = torch.tensor(desc_f, dtype=torch.int64, device=device).contiguous()
 
     def refresh(self):
         """Run once per step, before the forward: the parameters changed in the previous optimiser step."""
-        _ops.cast_into(self.flat.params, self.arena, self.pr)
+        if self.planes == 1:
+            _ops.cast_into(self.flat.params, self.arena, self.pr)
+        else:
+            _ops.cast_multi(self.flat.params, self.desc_f, self.n_desc, self.arena, self.pr)
         _ops.transpose_cast_multi(self.flat.params, self.desc, self.n_desc, self.arena_t, self.pr)
 
     def act(self, weight):
@@ -160,11 +195,13 @@ class ArenaWeights:
 
 
 class CTCTrainStep:
-    """One optimisation step of ModelCTC on a fixed batch shape.  `training_params` is the reference config's dict
-    (optimizer Adam: beta1, beta2, eps, weight_decay; lr_schedule Transformer: schedule_dim, warmup_steps, K)."""
+    """The reference trainer's optimisation step for ModelCTC (reference models/model.py:239-259).  `training_params` is the reference
+    config's dict: optimizer Adam (beta1, beta2, eps, weight_decay), lr_schedule Transformer (schedule_dim, warmup_steps, K) or
+    Constant (lr_value), accumulated_steps (micro-batches per optimiser step, default 1).  One CUDA graph per (batch shape, role of the
+    micro-step) is captured on first use and replayed afterwards."""
 
-    def __init__(self, model, training_params, precision="bf16", process_group=None, sync_bn=True, use_cuda_graph=True, dropout_seed=0,
-                 data_parallel=True):
+    def __init__(self, model, training_params, precision="bf16x2", process_group=None, sync_bn=True, use_cuda_graph=True, dropout_seed=0,
+                 data_parallel=True, max_graphs=8):
         if training_params.get("optimizer", "Adam") != "Adam":
             raise NotImplementedError("the shipped configs train with Adam (reference models/model.py:88-93)")
         sched = training_params.get("lr_schedule", "Transformer")
@@ -178,6 +215,9 @@ class CTCTrainStep:
         self.device = next(model.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("CTCTrainStep runs on CUDA sm_100 only")
+        self.accum = int(training_params.get("accumulated_steps", 1))
+        if self.accum < 1:
+            raise ValueError("accumulated_steps must be >= 1")
         reducer = None
         if self.world > 1 and sync_bn:
             from .distributed import SyncBatchNormReducer
@@ -189,18 +229,34 @@ class CTCTrainStep:
         weights = ArenaWeights(self.flat, precision, self.device)
         self.weights = weights if weights.supports(model.encoder) else None
         self.path.weights = self.weights
+        # device state {lr bits, adam step t, schedule step s, 0}.  The reference's compile() ends with scheduler.step() ("Init LR",
+        # models/model.py:150): the n-th optimiser step runs with lr(s = n) and scheduler.model_step == n afterwards.
         self.state = torch.zeros(4, dtype=torch.int32, device=self.device)
-        if sched == "Constant":
-            self.state[0:1].view(torch.float32).fill_(float(training_params["lr_value"]))
         self.schedule = 1 if sched == "Transformer" else 0
+        self._set_schedule_step(0)
         self.use_cuda_graph = use_cuda_graph
-        self._graph = None
-        self._static = None
+        self.max_graphs = max_graphs
+        self._graphs = {}                                   # (shape key, accumulate, final) -> [graph(s), static inputs, keep-alive]
+        self._micro = 0                                     # micro-batches accumulated since the last optimiser step
         self.loss = torch.zeros((), dtype=torch.float32, device=self.device)
         self.launches_per_step = None
 
+    def _lr_of(self, s):
+        tp = self.tp
+        if not self.schedule:
+            return float(tp["lr_value"])
+        return float(tp["K"]) * float(tp["schedule_dim"]) ** -0.5 * min(s ** -0.5, s * float(tp["warmup_steps"]) ** -1.5)
+
+    def _set_schedule_step(self, model_step, adam_t=None):
+        """State after `model_step` optimiser steps: lr = lr(s = model_step + 1), as the reference's scheduler holds it."""
+        st = torch.zeros(4, dtype=torch.int32)
+        st[0:1].view(torch.float32).fill_(self._lr_of(model_step + 1))
+        st[1] = model_step if adam_t is None else adam_t
+        st[2] = model_step + 1
+        self.state.copy_(st)
+
     # ---- pieces -----------------------------------------------------------------------------------------------------------
-    def _forward_backward(self, mel, mel_len, targets, target_len):
+    def _forward_backward(self, mel, mel_len, targets, target_len, accumulate, tables=None):
         if self.weights is not None:
             self.weights.refresh()
         x, logits, out_len, tape = self.path.forward(mel, mel_len, self.precision, want_logits=True)
@@ -208,92 +264,157 @@ class CTCTrainStep:
             out_len = torch.full((mel.shape[0],), logits.shape[1], dtype=torch.int64, device=mel.device)
         mean, per, dlogits = ctc_loss_and_grad(logits, out_len, targets, target_len)
         grads = self.path.backward(tape, None, dlogits)
-        keep = self.flat.pack(grads)
+        keep = self.flat.pack(grads, accumulate=accumulate, tables=tables)
         self.loss.copy_(mean)
         return keep
 
     def _optimizer(self):
         tp = self.tp
+        # loss / accumulated_steps (reference models/model.py:245) and the data-parallel mean, folded into one gradient scale
         _ops.adam_step(self.flat.params, self.flat.grads, self.flat.exp_avg, self.flat.exp_avg_sq, self.state, float(tp["beta1"]),
-                       float(tp["beta2"]), float(tp["eps"]), float(tp["weight_decay"]), grad_scale=1.0 / self.world, schedule=self.schedule,
-                       K=float(tp.get("K", 0.0)), dim=float(tp.get("schedule_dim", 1.0)), warmup=float(tp.get("warmup_steps", 1.0)))
+                       float(tp["beta2"]), float(tp["eps"]), float(tp["weight_decay"]), grad_scale=1.0 / (self.world * self.accum),
+                       schedule=self.schedule, K=float(tp.get("K", 0.0)), dim=float(tp.get("schedule_dim", 1.0)),
+                       warmup=float(tp.get("warmup_steps", 1.0)))
 
     def _all_reduce(self):
         if self.world > 1:
             dist.all_reduce(self.flat.grads, op=dist.ReduceOp.SUM, group=self.group)     # ONE bucket; the mean is folded into Adam
 
-    def _step_eager(self, mel, mel_len, targets, target_len):
+    def _step_eager(self, mel, mel_len, targets, target_len, accumulate, final):
         with torch.no_grad():
-            keep = self._forward_backward(mel, mel_len, targets, target_len)
-            self._all_reduce()
-            self._optimizer()
+            keep = self._forward_backward(mel, mel_len, targets, target_len, accumulate)
+            if final:
+                self._all_reduce()
+                self._optimizer()
         del keep
 
     # ---- public -----------------------------------------------------------------------------------------------------------
     def step(self, mel, mel_len, targets, target_len):
         """mel (B, n_mels, T) fp32, mel_len (B,) int64 or None, targets (B, U) int64, target_len (B,) int64 -- CUDA tensors.
-        Returns the (device) mean CTC loss of this batch; parameters, Adam moments, BatchNorm running statistics and the
-        learning-rate schedule have advanced by one step."""
+        Returns the (device) mean CTC loss of this (micro-)batch.  With accumulated_steps == A every A-th call is an optimiser step:
+        parameters, Adam moments and the learning-rate schedule advance; BatchNorm running statistics advance on every call."""
         for t in (mel, targets, target_len):
             if not t.is_cuda:
                 raise RuntimeError("CTCTrainStep takes CUDA tensors (copy the batch with non_blocking H2D first)")
+        accumulate, final = self._micro > 0, self._micro + 1 == self.accum
+        self._micro = 0 if final else self._micro + 1
+        if final:
+            self.model.encoder.mark_weights_changed()       # the inference engines re-prepare their weights on the next eval forward
         if not self.use_cuda_graph:
-            self._step_eager(mel, mel_len, targets, target_len)
+            self._step_eager(mel, mel_len, targets, target_len, accumulate, final)
             return self.loss
-        key = (tuple(mel.shape), mel_len is not None, tuple(targets.shape))
-        if self._graph is None or self._static[0] != key:
-            self._capture(key, mel, mel_len, targets, target_len)
-        _, s_mel, s_len, s_y, s_yl = self._static
+        key = (tuple(mel.shape), mel_len is not None, tuple(targets.shape), accumulate, final)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= self.max_graphs:        # bounded cache: drop the least recently used graph
+                self._graphs.pop(next(iter(self._graphs)))
+            ent = self._capture(mel, mel_len, targets, target_len, accumulate, final)
+        else:
+            self._graphs.pop(key)                           # re-insert: most recently used last
+        self._graphs[key] = ent
+        (g1, g2), (s_mel, s_len, s_y, s_yl), _ = ent
         s_mel.copy_(mel, non_blocking=True)
         if s_len is not None:
             s_len.copy_(mel_len, non_blocking=True)
         s_y.copy_(targets, non_blocking=True); s_yl.copy_(target_len, non_blocking=True)
-        self._graph[0].replay()
-        if self._graph[1] is not None:                      # world > 1 with collectives kept outside the graph
+        g1.replay()
+        if g2 is not None:                                  # world > 1 with collectives kept outside the graph
             self._all_reduce()
-            self._graph[1].replay()
+            g2.replay()
         return self.loss
 
-    def _capture(self, key, mel, mel_len, targets, target_len):
+    def _capture(self, mel, mel_len, targets, target_len, accumulate, final):
         s_mel, s_y, s_yl = mel.clone(), targets.clone(), target_len.clone()
         s_len = mel_len.clone() if mel_len is not None else None
-        self._static = (key, s_mel, s_len, s_y, s_yl)
         # snapshot everything a step mutates: the warm-up step below must not count as a training step
-        snap = [t.clone() for t in (self.flat.params, self.flat.exp_avg, self.flat.exp_avg_sq, self.state)]
+        mutated = (self.flat.params, self.flat.grads, self.flat.exp_avg, self.flat.exp_avg_sq, self.state)
+        snap = [t.clone() for t in mutated]
         bufs = [b for b in self.model.buffers()]
         snap_b = [b.clone() for b in bufs]
         drop = self.path._dropout_state(self.device)
         snap_c = drop.counter.clone() if drop.counter is not None else None
-        self._step_eager(s_mel, s_len, s_y, s_yl)           # warm-up: kernel attributes, allocator pools, NCCL communicators
+        self._step_eager(s_mel, s_len, s_y, s_yl, accumulate, final)   # warm-up: kernel attributes, allocator pools, NCCL communicators
         torch.cuda.synchronize()
-        split = self.world > 1 and self.reducer is None     # no SyncBN collectives inside: keep NCCL outside the graphs
+        tables = self.flat.new_tables()
+        split = final and self.world > 1 and self.reducer is None      # no SyncBN collectives inside: keep NCCL outside the graphs
         g1, g2 = torch.cuda.CUDAGraph(), None
         # other threads (the NCCL watchdog) may touch the CUDA API while this thread captures
         mode = {"capture_error_mode": "thread_local"} if self.world > 1 else {}
         with torch.no_grad():
             with torch.cuda.graph(g1, **mode):
-                keep = self._forward_backward(s_mel, s_len, s_y, s_yl)
-                if not split:
+                keep = self._forward_backward(s_mel, s_len, s_y, s_yl, accumulate, tables=tables)
+                if final and not split:
                     self._all_reduce()
                     self._optimizer()
             if split:
                 g2 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g2, **mode):
                     self._optimizer()
-        self._keep = keep
-        self._graph = (g1, g2)
         with torch.no_grad():
-            for t, s in zip((self.flat.params, self.flat.exp_avg, self.flat.exp_avg_sq, self.state), snap):
-                t.copy_(s)
-            for b, s in zip(bufs, snap_b):
-                b.copy_(s)
+            for t, sn in zip(mutated, snap):
+                t.copy_(sn)
+            for b, sn in zip(bufs, snap_b):
+                b.copy_(sn)
             if snap_c is not None:
                 drop.counter.copy_(snap_c)
         torch.cuda.synchronize()
+        return [(g1, g2), (s_mel, s_len, s_y, s_yl), (keep, tables)]
+
+    def close(self):
+        """Drop the captured graphs (they hold NCCL kernels when world > 1): call before destroy_process_group()."""
+        torch.cuda.synchronize()
+        self._graphs.clear()
+
+    # ---- checkpointing (reference models/model.py:346-376 saves optimizer.state_dict() and scheduler.model_step) --------------------
+    def _torch_param_order(self):
+        return [n for n, _ in self.model.named_parameters()]
+
+    def state_dict(self):
+        """{"optimizer": a torch.optim.Adam state_dict over model.parameters() (same layout the reference saves), "model_step": int,
+        "dropout_counter": tensor or None}."""
+        names = self._torch_param_order()
+        t = int(self.state[1].item())
+        state = {}
+        for idx, n in enumerate(names):
+            i = self.flat.index[n]
+            o, sz, shape = self.flat.offsets[i], self.flat.sizes[i], self.flat.shapes[i]
+            state[idx] = {"step": torch.tensor(float(t)), "exp_avg": self.flat.exp_avg[o:o + sz].view(shape).clone(),
+                          "exp_avg_sq": self.flat.exp_avg_sq[o:o + sz].view(shape).clone()}
+        tp = self.tp
+        group = {"lr": self.lr(), "betas": (float(tp["beta1"]), float(tp["beta2"])), "eps": float(tp["eps"]),
+                 "weight_decay": float(tp["weight_decay"]), "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                 "differentiable": False, "fused": None, "params": list(range(len(names)))}
+        drop = self.path._dropout_state(self.device)
+        return {"optimizer": {"state": state if t > 0 else {}, "param_groups": [group]}, "model_step": self.steps_done(),
+                "dropout_counter": drop.counter.clone() if drop.counter is not None else None}
+
+    def load_state_dict(self, sd):
+        """Accepts state_dict() of this class or a checkpoint of the reference ({"optimizer_state_dict", "model_step"} entries map to
+        "optimizer" / "model_step")."""
+        opt = sd.get("optimizer", sd.get("optimizer_state_dict"))
+        names = self._torch_param_order()
+        t = 0
+        with torch.no_grad():
+            self.flat.exp_avg.zero_(); self.flat.exp_avg_sq.zero_()
+            for idx, st in (opt["state"] if opt is not None else {}).items():
+                i = self.flat.index[names[int(idx)]]
+                o, sz = self.flat.offsets[i], self.flat.sizes[i]
+                self.flat.exp_avg[o:o + sz].copy_(st["exp_avg"].reshape(-1))
+                self.flat.exp_avg_sq[o:o + sz].copy_(st["exp_avg_sq"].reshape(-1))
+                t = max(t, int(float(st["step"])))
+        model_step = int(sd.get("model_step", t))
+        self._set_schedule_step(model_step, adam_t=t)
+        ctr = sd.get("dropout_counter")
+        drop = self.path._dropout_state(self.device)
+        if ctr is not None and drop.counter is not None:
+            drop.counter.copy_(ctr)
+        self._micro = 0
 
     # ---- introspection ------------------------------------------------------------------------------------------------------
     def lr(self):
+        """Learning rate the NEXT optimiser step will use."""
         return float(self.state[0:1].view(torch.float32).item())
 
     def steps_done(self):
-        return int(self.state[1].item())
+        """Optimiser steps taken == the reference scheduler's model_step."""
+        return int(self.state[2].item()) - 1 if self.schedule else int(self.state[1].item())

@@ -86,7 +86,7 @@ class TrainingPath:
         """[N, K] operand of the forward GEMM (activation type)."""
         if self.weights is not None:
             return self.weights.act(weight)
-        return _ops.cast(_w2(weight), pr)
+        return _ops.cast_weight(_w2(weight), pr)
 
     def _wt(self, weight, pr):
         """[K, N] operand of the data-gradient GEMM dX = dY . W (activation type)."""
@@ -102,7 +102,7 @@ class TrainingPath:
         if self.weights is not None:
             return self.weights.qkv_act(mhsa), self.weights.qkv_bias(mhsa), mhsa
         w32, b = _ops.concat_qkv(mhsa)
-        return _ops.cast(w32, pr), b, w32
+        return _ops.cast_weight(w32, pr), b, w32
 
     def _qkv_dgrad(self, dqkv_act, handle, pr):
         if self.weights is not None:

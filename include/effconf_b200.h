@@ -35,6 +35,13 @@ extern "C" {
 /* numerics mode of the tensor-core operands (accumulation, residual stream, LayerNorm, softmax are always fp32) */
 #define EC_PREC_TF32 0 /* parity mode: operands rounded to TF32 (fp32 storage), tcgen05 kind::tf32 */
 #define EC_PREC_BF16 1 /* fast mode: bf16 operands and bf16 inter-kernel activations, tcgen05 kind::f16 */
+/* split mode (the default; meets the 1e-3 parity gate with ~50x margin): every operand element is the PAIR (hi, lo) of bf16
+ * values hi = bf16(x), lo = bf16(x - hi) packed in one 32-bit word (low half hi), i.e. 16 significant bits.  A row of K packed
+ * elements is read by the tensor core as 2K bf16 values; weights carry a second plane with the halves swapped, so that
+ *   [ah al] . [wh wl] + [ah al] . [wl wh] = (ah + al)(wh + wl)
+ * is assembled from two kind::f16 MMAs into the same fp32 TMEM accumulator.  Weight operands are therefore [2, N, K] (plane 0
+ * = (hi, lo), plane 1 = (lo, hi)); activations [M, K]. */
+#define EC_PREC_BF16X2 2
 
 typedef struct ec_block_cfg {
   int32_t dim_model;   /* D  */
@@ -245,10 +252,20 @@ int ec_op_swish_dropout(int precision, const void* z, const float* dy, size_t n,
  * fp32 parameter arena; dst[c][r] = act_type(src[r][c]). */
 int ec_op_transpose_cast_multi(int precision, const float* src_arena, const long long* desc, int n, int ctas_per_tensor, void* dst_arena,
                                void* stream);
+/* forward operands [N, K] of all GEMM weights in one launch (same descriptor table; dst offsets in activation-type elements) */
+int ec_op_cast_multi(int precision, const float* src_arena, const long long* desc, int n, int ctas_per_tensor, void* dst_arena, void* stream);
 int ec_op_pack_flat(const float* const* srcs, const long long* offsets, const long long* sizes, int n, float* arena, void* stream);
+/* accumulate != 0: arena += gathered gradients (gradient accumulation over micro-batches, reference models/model.py:245-259) */
+int ec_op_pack_flat_acc(const float* const* srcs, const long long* offsets, const long long* sizes, int n, float* arena, int accumulate,
+                        void* stream);
 
 /* ---- single-operator entry points (unit parity tests; same kernels the engine launches) ---------------------------- */
 int ec_op_cast(int precision, const float* src, void* dst, size_t n, void* stream);
+/* GEMM weight operand ("W" of ec_op_gemm and friends): ec_weight_planes(precision) planes of n = N*K activation-type elements; plane 0
+ * is ec_op_cast(src), plane 1 (EC_PREC_BF16X2 only) the same pairs with the halves swapped.  ec_op_transpose_cast, ec_op_cast_multi,
+ * ec_op_transpose_cast_multi and ec_op_pointwise_glu's scratch follow the same [planes, N, K] convention. */
+int ec_weight_planes(int precision);
+int ec_op_cast_weight(int precision, const float* src, size_t n, void* dst, void* stream);
 int ec_op_layernorm(int precision, const float* x, int rows, int dim, const float* gamma, const float* beta, float eps,
                     void* y_act /* activation type or NULL */, float* y_f32 /* or NULL */, void* stream);
 /* out = alpha * act(A @ W^T + bias) + residual.  A [M,K], W [N,K] in the activation type (use ec_op_cast).  act: 0 none, 1 swish. */

@@ -17,6 +17,10 @@ def cast(x, precision):
     return _d(x).clone()
 
 
+def cast_weight(x, precision):
+    return _d(x).clone()
+
+
 def cast_scaled(x, precision, scale):
     return _d(x) * scale
 

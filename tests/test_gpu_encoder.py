@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 TOL_TF32 = 1e-3
 TOL_BF16 = 1.5e-2
+PARITY = "bf16x2"      # the default operand mode (packed bf16 hi / lo pairs): the mode bench.py times and the north-star 1e-3 gate applies to
 
 
 def rel_l2(a, b):
@@ -42,7 +43,7 @@ def make_model(sd, precision, golden=None):
     return m.to(DEV).eval()
 
 
-@pytest.mark.parametrize("precision,tol", [("tf32", TOL_TF32), ("bf16", TOL_BF16)])
+@pytest.mark.parametrize("precision,tol", [("bf16x2", TOL_TF32), ("tf32", TOL_TF32), ("bf16", TOL_BF16)])
 def test_config1_against_reference_golden(sd, golden_dir, precision, tol):
     from efficientconformer_b200.model_ctc import ctc_loss, greedy_ids
     g = torch.load(os.path.join(golden_dir, "ctc_small_b2_t500.pt"))
@@ -57,10 +58,12 @@ def test_config1_against_reference_golden(sd, golden_dir, precision, tol):
     loss, per = ctc_loss(logits, out_len, g["targets"], g["target_len"])
     assert abs(float(loss) - float(g["loss"])) / abs(float(g["loss"])) < tol
     ids = greedy_ids(logits, out_len)
-    if precision == "tf32":
-        # ids must match wherever the reference's own top-2 margin exceeds the parity tolerance (random-init logits are near-tied)
+    if precision != "bf16":
+        # ids must match wherever the reference's own top-2 margin exceeds the parity tolerance (random-init logits are near-tied):
+        # 1e-3 * absmax in the default split mode, 4e-3 * absmax in the TF32 mode (whose own error is 7e-4)
         top2 = g["logits"].topk(2, dim=-1).values
-        safe = (top2[..., 0] - top2[..., 1]) > 4 * tol * g["logits"].abs().max()
+        safe = (top2[..., 0] - top2[..., 1]) > (1 if precision == "bf16x2" else 4) * tol * g["logits"].abs().max()
+        print(f"[{precision}] greedy ids compared on {int(safe.sum())} of {safe.numel()} frames")
         pred = logits.argmax(-1).cpu()
         assert torch.equal(pred[safe], g["logits"].argmax(-1)[safe])
         if bool(safe.all()):
@@ -69,7 +72,7 @@ def test_config1_against_reference_golden(sd, golden_dir, precision, tol):
 
 def test_audio_level_forward_matches_reference(sd, golden_dir):
     g = torch.load(os.path.join(golden_dir, "ctc_small_audio_b2_t200.pt"))
-    model = make_model(sd, "tf32")
+    model = make_model(sd, PARITY)
     audio = synthetic_audio(2, g["t_mel"], seed=g["audio_seed"]).to(DEV)
     logits, out_len, _ = model.forward((audio, None, g["audio_len"].to(DEV), None))
     assert torch.equal(out_len.cpu(), g["out_len"])
@@ -82,7 +85,7 @@ def test_encoder_only_and_no_lengths(sd):
     from efficientconformer_b200 import ConformerEncoder
     from oracle import conformer_oracle as O
     enc_sd = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
-    enc = ConformerEncoder(P, precision="tf32")
+    enc = ConformerEncoder(P, precision=PARITY)
     enc.load_state_dict(enc_sd, strict=False)
     enc = enc.to(DEV).eval()
     mel = synthetic_mel(2, 131, seed=11)
@@ -100,7 +103,7 @@ def test_ragged_batch_against_oracle(sd):
     mel = synthetic_mel(B, T, seed=21)
     mel_len = torch.tensor([1000, 900, 700, 445])
     ref, ref_len = O.model_ctc_forward_mel(sd, P, mel, mel_len)
-    model = make_model(sd, "tf32")
+    model = make_model(sd, PARITY)
     logits, out_len, _ = model.forward_mel(mel.to(DEV), mel_len.to(DEV))
     assert torch.equal(out_len.cpu(), ref_len)
     e = rel_l2(logits, ref)
@@ -112,7 +115,8 @@ def test_ragged_batch_against_oracle(sd):
     assert abs(float(loss) - float(ref_loss)) / abs(float(ref_loss)) < TOL_TF32
 
 
-def test_block_goldens_awkward_lengths(sd, golden_dir):
+@pytest.mark.parametrize("precision", ["bf16x2", "tf32"])
+def test_block_goldens_awkward_lengths(sd, golden_dir, precision):
     """Single-block engines on the reference's block outputs for T in {1,2,4,17,250,251,...} incl. stride-2 / expand blocks."""
     import ctypes as C
     from efficientconformer_b200 import ConformerEncoder
@@ -130,7 +134,7 @@ def test_block_goldens_awkward_lengths(sd, golden_dir):
         # the golden stores the reference block's output for a seeded block INPUT: compose the block from the C entry points
         gen = torch.Generator().manual_seed(100 * bi + Tq)
         x = torch.randn(2, Tq, spec.dim_model, generator=gen)
-        out = run_block_with_ops(ops, enc_sd, f"blocks.{bi}", x.to(DEV), e["x_len"].to(DEV), spec, "tf32")
+        out = run_block_with_ops(ops, enc_sd, f"blocks.{bi}", x.to(DEV), e["x_len"].to(DEV), spec, precision)
         err = rel_l2(out, e["block"])
         worst = max(worst, err)
         assert out.shape == e["block"].shape, key
@@ -149,20 +153,20 @@ def run_block_with_ops(ops, sd, p, x, x_len, spec, prec):
 
     def ffn(tag, xin, d):
         xn, _ = ops.layernorm(xin, c(f"{tag}.layers.0.weight"), c(f"{tag}.layers.0.bias"), prec, want_f32=False)
-        _, h = ops.gemm(xn, ops.cast(c(f"{tag}.layers.1.weight"), prec), c(f"{tag}.layers.1.bias"), prec, act=1, want_f32=False, want_act=True)
-        y, _ = ops.gemm(h, ops.cast(c(f"{tag}.layers.4.weight"), prec), c(f"{tag}.layers.4.bias"), prec, alpha=0.5, residual=xin)
+        _, h = ops.gemm(xn, ops.cast_weight(c(f"{tag}.layers.1.weight"), prec), c(f"{tag}.layers.1.bias"), prec, act=1, want_f32=False, want_act=True)
+        y, _ = ops.gemm(h, ops.cast_weight(c(f"{tag}.layers.4.weight"), prec), c(f"{tag}.layers.4.bias"), prec, alpha=0.5, residual=xin)
         return y
     x2 = ffn("feed_forward_module1", x2, D)
     m = "multi_head_self_attention_module"
     xn, _ = ops.layernorm(x2, c(f"{m}.norm.weight"), c(f"{m}.norm.bias"), prec, want_f32=False)
     wqkv = torch.cat([c(f"{m}.mhsa.{n}_layer.weight") for n in ("query", "key", "value")])
     bqkv = torch.cat([c(f"{m}.mhsa.{n}_layer.bias") for n in ("query", "key", "value")])
-    qkv, _ = ops.gemm(xn, ops.cast(wqkv, prec), bqkv, prec)
+    qkv, _ = ops.gemm(xn, ops.cast_weight(wqkv, prec), bqkv, prec)
     Tp = T + (-T) % G
     R = ops.cast(relative_sinusoid_rows(Tp, D, G, spec.max_pos).to(DEV), prec)
-    E, _ = ops.gemm(R, ops.cast(c(f"{m}.mhsa.pos_layer.weight"), prec), c(f"{m}.mhsa.pos_layer.bias"), prec)
+    E, _ = ops.gemm(R, ops.cast_weight(c(f"{m}.mhsa.pos_layer.weight"), prec), c(f"{m}.mhsa.pos_layer.bias"), prec)
     o = ops.relpos_attention(qkv.reshape(B, T, 3 * D), E, c(f"{m}.mhsa.u"), c(f"{m}.mhsa.v"), x_len, H, G, prec)
-    x2, _ = ops.gemm(o.reshape(B * T, D), ops.cast(c(f"{m}.mhsa.output_layer.weight"), prec), c(f"{m}.mhsa.output_layer.bias"), prec, residual=x2)
+    x2, _ = ops.gemm(o.reshape(B * T, D), ops.cast_weight(c(f"{m}.mhsa.output_layer.weight"), prec), c(f"{m}.mhsa.output_layer.bias"), prec, residual=x2)
     cm = "convolution_module.layers"
     xn, _ = ops.layernorm(x2, c(f"{cm}.0.weight"), c(f"{cm}.0.bias"), prec, want_f32=False)
     gl = ops.pointwise_glu(xn, c(f"{cm}.2.weight"), c(f"{cm}.2.bias"), prec)
@@ -171,10 +175,10 @@ def run_block_with_ops(ops, sd, p, x, x_len, spec, prec):
     To = hc.shape[1]
     if spec.dim_model != De:
         xs = ops.cast(x2.reshape(B, T, D)[:, ::spec.conv_stride].reshape(B * To, D), prec)
-        res, _ = ops.gemm(xs, ops.cast(c("conv_res.1.weight")[:, :, 0], prec), c("conv_res.1.bias"), prec)
+        res, _ = ops.gemm(xs, ops.cast_weight(c("conv_res.1.weight")[:, :, 0], prec), c("conv_res.1.bias"), prec)
     else:
         res = x2
-    x3, _ = ops.gemm(hc.reshape(B * To, De), ops.cast(c(f"{cm}.7.weight")[:, :, 0], prec), c(f"{cm}.7.bias"), prec, residual=res)
+    x3, _ = ops.gemm(hc.reshape(B * To, De), ops.cast_weight(c(f"{cm}.7.weight")[:, :, 0], prec), c(f"{cm}.7.bias"), prec, residual=res)
     x3 = ffn("feed_forward_module2", x3, De)
     _, y = ops.layernorm(x3, c("norm.weight"), c("norm.bias"), prec, want_act=False)
     return y.reshape(B, To, De)
@@ -186,7 +190,7 @@ def test_full_size_properties(sd):
     two runs are bit-identical; a B=4 slice agrees with the oracle."""
     from oracle import conformer_oracle as O
     B, T = 32, 1000
-    model = make_model(sd, "tf32")
+    model = make_model(sd, PARITY)
     mel = synthetic_mel(B, T, seed=31).to(DEV)
     mel_len = ragged_lengths(B, T, seed=3).to(DEV)
     lg1, len1, _ = model.forward_mel(mel, mel_len)
@@ -214,12 +218,12 @@ def test_execution_options_do_not_change_results(sd, fuse_ln, pdl):
     from efficientconformer_b200 import _lib
     mel = synthetic_mel(3, 333, seed=77)
     mel_len = torch.tensor([333, 200, 77])
-    base = make_model(sd, "tf32")
+    base = make_model(sd, PARITY)
     ref_gpu, _, _ = base.forward_mel(mel.to(DEV), mel_len.to(DEV))
     L = _lib.lib()
     try:
         L.ec_set_pdl(pdl)
-        m = make_model(sd, "tf32")
+        m = make_model(sd, PARITY)
         m.forward_mel(mel.to(DEV), mel_len.to(DEV))                       # creates the engine
         eng = m.encoder._engines[_lib.PREC_TF32][0]
         L.ec_engine_set_fuse_ln(eng, fuse_ln)
@@ -267,7 +271,7 @@ def test_other_config_transducer_small_encoder():
     from oracle import conformer_oracle as O
     p2 = dict(P, dim_model=[100, 140, 200], subsampling_filters=[100])
     sd2 = seeded_state_dict(p2, None, seed=5)
-    enc = ConformerEncoder(p2, precision="tf32")
+    enc = ConformerEncoder(p2, precision=PARITY)
     enc.load_state_dict(sd2, strict=False)
     enc = enc.to(DEV).eval()
     mel = synthetic_mel(3, 257, seed=13)
@@ -287,7 +291,7 @@ OTHER_CASES = ["EfficientConformerCTCLarge", "EfficientConformerCTCMedium", "Eff
                "ConformerCTCSmall", "ConformerTransducerSmall", "ConformerTransducerLarge"]
 
 
-@pytest.mark.parametrize("precision,tol", [("tf32", TOL_TF32), ("bf16", TOL_BF16)])
+@pytest.mark.parametrize("precision,tol", [("bf16x2", TOL_TF32), ("tf32", TOL_TF32), ("bf16", TOL_BF16)])
 @pytest.mark.parametrize("case", OTHER_CASES)
 def test_other_shipped_configs_against_reference_golden(golden_dir, case, precision, tol):
     """BASELINE.json configs 3 (EfficientConformerCTCLarge), 4 (TransducerMedium encoder) and 5 (ConformerCTCLarge: two Conv2d

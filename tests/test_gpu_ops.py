@@ -23,8 +23,19 @@ def tf32_round(x):
     return ((xi + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
+def split_round(x):
+    """hi + lo with hi = bf16(x), lo = bf16(x - hi): the value a split-mode (bf16x2) operand element carries."""
+    hi = x.float().to(torch.bfloat16).float()
+    return hi + (x.float() - hi).to(torch.bfloat16).float()
+
+
 def rnd(prec, x):
+    if prec == "bf16x2":
+        return split_round(x)
     return tf32_round(x) if prec == "tf32" else x.to(torch.bfloat16).float()
+
+
+PRECS = ["tf32", "bf16", "bf16x2"]
 
 
 @pytest.fixture(scope="module")
@@ -33,18 +44,21 @@ def ops():
     return o
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", PRECS)
 def test_cast_rounding(ops, prec):
     x = torch.randn(1000, 37, device=DEV) * 3
-    y = ops.cast(x, prec).float()
-    if prec == "tf32":
+    y = ops.unpack(ops.cast(x, prec), prec)
+    if prec == "bf16x2":
+        assert torch.equal(y.cpu(), split_round(x.cpu()))
+        assert rel_l2(y, x) < 2e-5            # 16 significant bits
+    elif prec == "tf32":
         # round-to-nearest (ties away) onto 10 mantissa bits
         assert torch.equal(y.cpu(), tf32_round(x.cpu()))
     else:
         assert torch.equal(y.cpu(), x.cpu().to(torch.bfloat16).float())
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 16, 64), (256, 240, 120), (16000, 480, 120), (8000, 168, 672), (4000, 256, 240),
                                    (999, 120, 120), (1, 120, 120), (130, 504, 168), (333, 960, 240), (700, 120, 4800), (77, 8, 40)])
 def test_gemm_exact_operands(ops, prec, M, N, K):
@@ -55,21 +69,21 @@ def test_gemm_exact_operands(ops, prec, M, N, K):
     w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
     bias = torch.randn(N, generator=g).to(DEV)
     res = torch.randn(M, N, generator=g).to(DEV)
-    aa, ww = ops.cast(a, prec), ops.cast(w, prec)
-    ref = aa.double() @ ww.double().t() + bias.double()
+    aa, ww = ops.cast(a, prec), ops.cast_weight(w, prec)
+    ref = ops.unpack(aa, prec).double() @ ops.unpack(ww, prec).double().t() + bias.double()
     out, _ = ops.gemm(aa, ww, bias, prec)
     tol = 2e-6 if K <= 1024 else 2e-5      # tensor-core fp32 accumulation over long K is slightly lossier than an IEEE fp32 chain
     assert rel_l2(out, ref) < tol, "plain"
     out2, out2a = ops.gemm(aa, ww, bias, prec, alpha=0.5, act=0, residual=res, want_act=True)
     ref2 = 0.5 * ref + res.double()
     assert rel_l2(out2, ref2) < tol, "residual"
-    assert torch.equal(out2a.float().cpu(), rnd(prec, out2.cpu())), "activation-type copy is the rounded fp32 output"
+    assert torch.equal(ops.unpack(out2a, prec).cpu(), rnd(prec, out2.cpu())), "activation-type copy is the rounded fp32 output"
     out3, _ = ops.gemm(aa, ww, bias, prec, act=1)
     ref3 = ref * torch.sigmoid(ref)
     assert rel_l2(out3, ref3) < 3 * tol, "swish"
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("M,N,K,fps,stride", [(16000, 120, 480, 500, 2), (8000, 168, 168, 250, 2), (4000, 240, 960, 125, 1), (999, 120, 4800, 333, 2),
                                               (37, 256, 64, 37, 1), (130, 8, 40, 13, 2)])
 def test_gemm_fused_layernorm(ops, prec, M, N, K, fps, stride):
@@ -82,27 +96,28 @@ def test_gemm_fused_layernorm(ops, prec, M, N, K, fps, stride):
     res = (torch.randn(M, N, generator=g) * 2 + 0.3).to(DEV)
     g1, b1 = (1 + 0.1 * torch.randn(N, generator=g)).to(DEV), (0.1 * torch.randn(N, generator=g)).to(DEV)
     g2, b2 = (1 + 0.1 * torch.randn(N, generator=g)).to(DEV), (0.1 * torch.randn(N, generator=g)).to(DEV)
-    aa, ww = ops.cast(a, prec), ops.cast(w, prec)
-    x_ref = 0.5 * (aa.double() @ ww.double().t() + bias.double()) + res.double()
+    aa, ww = ops.cast(a, prec), ops.cast_weight(w, prec)
+    x_ref = 0.5 * (ops.unpack(aa, prec).double() @ ops.unpack(ww, prec).double().t() + bias.double()) + res.double()
     ln = lambda x, gg, bb: torch.nn.functional.layer_norm(x, (N,), gg.double(), bb.double(), 1e-6)
     # mode 1: out = x, ln_out = LN1(x), strided compaction copy of x
     out, y, cp = ops.gemm_ln(aa, ww, bias, prec, g1, b1, mode=1, alpha=0.5, residual=res, copy_stride=stride, frames_per_seq=fps)
     tol = 2e-6 if K <= 1024 else 2e-5
     assert rel_l2(out, x_ref) < tol
     y_ref = ln(x_ref, g1, b1)
-    assert rel_l2(y.float(), y_ref) < (4e-4 if prec == "tf32" else 4e-3)          # + rounding to the activation type
-    assert rel_l2(y.float(), rnd(prec, y_ref.float().cpu())) < 2e-4 + (0 if prec == "tf32" else 2e-3)
+    y = ops.unpack(y, prec)
+    assert rel_l2(y, y_ref) < (4e-4 if prec != "bf16" else 4e-3)          # + rounding to the activation type
+    assert rel_l2(y, rnd(prec, y_ref.float().cpu())) < 2e-4 + (0 if prec != "bf16" else 2e-3)
     sel = x_ref.reshape(M // fps, fps, N)[:, ::stride].reshape(-1, N)
     assert cp.shape == sel.shape
-    assert rel_l2(cp.float(), sel) < (4e-4 if prec == "tf32" else 4e-3)
+    assert rel_l2(ops.unpack(cp, prec), sel) < (4e-4 if prec != "bf16" else 4e-3)
     # mode 2: out = LN1(x) in place, ln_out = LN2(out)
     out2, y2, _ = ops.gemm_ln(aa, ww, bias, prec, g1, b1, g2, b2, mode=2, alpha=0.5, residual=res)
     assert rel_l2(out2, y_ref) < 5e-6 + tol
-    assert rel_l2(y2.float(), ln(y_ref, g2, b2)) < (4e-4 if prec == "tf32" else 4e-3)
+    assert rel_l2(ops.unpack(y2, prec), ln(y_ref, g2, b2)) < (4e-4 if prec != "bf16" else 4e-3)
     # mode 2 with identity second stage: activation-type copy of the normalised output
     out3, y3, _ = ops.gemm_ln(aa, ww, bias, prec, g1, b1, None, None, mode=2, alpha=0.5, residual=res)
     assert torch.equal(out3, out2)
-    assert torch.equal(y3.float().cpu(), rnd(prec, out3.cpu()))
+    assert torch.equal(ops.unpack(y3, prec).cpu(), rnd(prec, out3.cpu()))
 
 
 @pytest.mark.parametrize("M,D,hidden,clusters", [(16000, 120, 480, (0, 1, 2)), (8000, 168, 672, (0, 2)), (4000, 240, 960, (0, 2, 4)),
@@ -154,7 +169,7 @@ def test_ffn_fused(ops, M, D, hidden, clusters):
             assert rel_l2(out, first) < 1e-5
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("M,C,K", [(256, 120, 120), (1000, 168, 120), (517, 240, 168), (64, 8, 16), (300, 360, 360)])
 def test_pointwise_glu(ops, prec, M, C, K):
     g = torch.Generator(device="cpu").manual_seed(C + K)
@@ -162,15 +177,16 @@ def test_pointwise_glu(ops, prec, M, C, K):
     w = (torch.randn(2 * C, K, 1, generator=g) / math.sqrt(K)).to(DEV)
     b = torch.randn(2 * C, generator=g).to(DEV)
     aa = ops.cast(a, prec)
-    h = aa.double() @ rnd(prec, w[:, :, 0].cpu()).to(DEV).double().t() + b.double()
+    h = ops.unpack(aa, prec).double() @ rnd(prec, w[:, :, 0].cpu()).to(DEV).double().t() + b.double()
     ref = h[:, :C] * torch.sigmoid(h[:, C:])
     out = ops.pointwise_glu(aa, w, b, prec)
-    tol = 2e-6 if prec == "tf32" else 4e-3     # output is rounded to the activation type
-    assert rel_l2(out.float(), ref) < (1e-3 if prec == "tf32" else 4e-3)
-    assert rel_l2(out.float(), rnd(prec, ref.float().cpu())) < 1e-4 + tol
+    tol = 2e-6 if prec != "bf16" else 4e-3     # output is rounded to the activation type
+    out = ops.unpack(out, prec)
+    assert rel_l2(out, ref) < (1e-3 if prec != "bf16" else 4e-3)
+    assert rel_l2(out, rnd(prec, ref.float().cpu())) < 1e-4 + tol
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("rows,dim", [(16000, 120), (1000, 168), (37, 240), (5, 1024), (3, 8)])
 def test_layernorm(ops, prec, rows, dim):
     g = torch.Generator(device="cpu").manual_seed(rows + dim)
@@ -180,10 +196,10 @@ def test_layernorm(ops, prec, rows, dim):
     ya, yf = ops.layernorm(x, gamma, beta, prec)
     ref = torch.nn.functional.layer_norm(x.double(), (dim,), gamma.double(), beta.double(), 1e-6)
     assert rel_l2(yf, ref) < 1e-6
-    assert torch.equal(ya.float().cpu(), rnd(prec, yf.cpu()))
+    assert torch.equal(ops.unpack(ya, prec).cpu(), rnd(prec, yf.cpu()))
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("B,T,C,k,stride", [(4, 500, 120, 15, 1), (3, 251, 168, 15, 2), (2, 250, 240, 15, 2), (2, 1, 120, 15, 1),
                                             (2, 7, 240, 15, 2), (1, 130, 256, 31, 1), (2, 65, 176, 31, 2)])
 def test_dwconv_bn_swish(ops, prec, B, T, C, k, stride):
@@ -195,16 +211,16 @@ def test_dwconv_bn_swish(ops, prec, B, T, C, k, stride):
     xa = ops.cast(x, prec)
     wf, bf = ops.fold_bn(w, b, gam, bet, rm, rv)
     y = ops.dwconv_bn_swish(xa, wf, bf, stride, prec)
-    xin = xa.double().transpose(1, 2)
+    xin = ops.unpack(xa, prec).double().transpose(1, 2)
     pad = (k - 1) // 2
     conv = torch.nn.functional.conv1d(torch.nn.functional.pad(xin, (pad, pad)), w.double(), b.double(), stride=stride, groups=C)
     bn = (conv - rm.double()[None, :, None]) / torch.sqrt(rv.double()[None, :, None] + 1e-5) * gam.double()[None, :, None] + bet.double()[None, :, None]
     ref = (bn * torch.sigmoid(bn)).transpose(1, 2)
     assert y.shape == ref.shape
-    assert rel_l2(y.float(), ref) < (5e-4 if prec == "tf32" else 4e-3)
+    assert rel_l2(ops.unpack(y, prec), ref) < (5e-4 if prec != "bf16" else 4e-3)
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("B,T", [(2, 101), (3, 64), (1, 1), (2, 2), (2, 33)])
 def test_subsample_conv(ops, prec, B, T):
     C, F = 120, 80
@@ -219,7 +235,7 @@ def test_subsample_conv(ops, prec, B, T):
     bn = torch.nn.functional.batch_norm(conv, rm.double(), rv.double(), gam.double(), bet.double(), False, 0.0, 1e-5)
     ref = (bn * torch.sigmoid(bn)).reshape(B, C * (F // 2), -1).transpose(1, 2)
     assert y.shape == ref.shape
-    assert rel_l2(y.float(), ref) < (5e-4 if prec == "tf32" else 4e-3)
+    assert rel_l2(ops.unpack(y, prec), ref) < (5e-4 if prec != "bf16" else 4e-3)
 
 
 def _attention_reference(qkv, E, u, v, x_len, H, G):
@@ -249,7 +265,7 @@ def _attention_reference(qkv, E, u, v, x_len, H, G):
     return (w @ vh).transpose(1, 2).reshape(B, Tg * G, D)[:, :T]
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("B,T,D,H,G", [(2, 500, 120, 4, 3), (2, 251, 120, 4, 3), (3, 250, 168, 4, 1), (2, 125, 240, 4, 1), (2, 1, 120, 4, 3),
                                        (2, 2, 120, 4, 3), (1, 64, 168, 4, 1), (2, 65, 240, 4, 1), (1, 700, 168, 4, 1), (2, 33, 120, 8, 3)])
 def test_relpos_attention(ops, prec, B, T, D, H, G):
@@ -266,8 +282,8 @@ def test_relpos_attention(ops, prec, B, T, D, H, G):
         out = ops.relpos_attention(qkv, E, u, v, xl, H, G, prec)
         ref = _attention_reference(qkv, E, u, v, xl, H, G)
         assert out.shape == ref.shape
-        err = rel_l2(out.float(), ref)
-        assert err < (2e-3 if prec == "tf32" else 1e-2), (err, xl is None)      # bf16 path also rounds qu/qv, P and the output to bf16
+        err = rel_l2(ops.unpack(out, prec), ref)
+        assert err < (2e-3 if prec != "bf16" else 1e-2), (err, xl is None)      # bf16 path also rounds qu/qv, P and the output to bf16
 
 
 def test_ctc_loss_and_greedy_on_device(golden_dir):
