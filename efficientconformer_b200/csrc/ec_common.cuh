@@ -275,7 +275,8 @@ int launch_swish_bwd(int precision, const void* z, const float* dy, size_t n, vo
 int launch_glu_bwd(int precision, const void* zg, const float* dy, size_t rows, int C, void* dzg, cudaStream_t stream);
 // weight gradient dW[N,K] = dY[M,N]^T . X[M,K] on tcgen05 with MN-major operands (wgrad_tc.cu)
 size_t wgrad_work_bytes(int precision, int M, int N, int K);
-int launch_wgrad(int precision, const void* dy, const void* x, int M, int N, int K, float* dw, int accumulate, float* work,
+// db (may be null): bias gradient [N] = column sums of dY, from the same kernel
+int launch_wgrad(int precision, const void* dy, const void* x, int M, int N, int K, float* dw, int accumulate, float* db, float* work,
                  cudaStream_t stream);
 // training-mode depthwise conv + BatchNorm (batch statistics) + Swish and their backward (conv_train.cu)
 size_t conv_train_work_bytes(int C, int K);

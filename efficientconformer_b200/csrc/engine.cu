@@ -732,7 +732,11 @@ int ec_op_dwconv_bwd(int precision, const float* dy, const void* x, const float*
 }
 size_t ec_op_wgrad_work_bytes(int precision, int M, int N, int K) { return wgrad_work_bytes(precision, M, N, K); }
 int ec_op_wgrad(int precision, const void* dy, const void* x, int M, int N, int K, float* dw, int accumulate, void* work, void* stream) {
-  return launch_wgrad(precision, dy, x, M, N, K, dw, accumulate, reinterpret_cast<float*>(work), reinterpret_cast<cudaStream_t>(stream));
+  return launch_wgrad(precision, dy, x, M, N, K, dw, accumulate, nullptr, reinterpret_cast<float*>(work), reinterpret_cast<cudaStream_t>(stream));
+}
+int ec_op_wgrad_bias(int precision, const void* dy, const void* x, int M, int N, int K, float* dw, int accumulate, float* db, void* work,
+                     void* stream) {
+  return launch_wgrad(precision, dy, x, M, N, K, dw, accumulate, db, reinterpret_cast<float*>(work), reinterpret_cast<cudaStream_t>(stream));
 }
 size_t ec_op_colsum_work_bytes(int cols) { return colsum_work_bytes(cols); }
 int ec_op_colsum(int precision, const void* m, int is_f32, int rows, int cols, float* out, void* work, void* stream) {

@@ -442,10 +442,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // host side
 // ------------------------------------------------------------------------------------------------------------------
 // Output tiles are stored in 32-column slabs, so tile boundaries inside a row must be multiples of 32.
-static int pick_block_n(int N) {
-  if (N <= 256) return round_up(N, 16);
-  const int tiles = cdiv(N, 256);
-  return std::min(256, round_up(cdiv(N, tiles), 32));
+static int pick_block_n(int N, int cap = 256) {
+  if (N <= cap) return round_up(N, 16);
+  const int tiles = cdiv(N, cap);
+  return std::min(cap, round_up(cdiv(N, tiles), 32));
 }
 
 template <typename T, bool kLN>
@@ -463,7 +463,9 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
     tiles_n = a.N / p.block_n;
     EC_REQUIRE(tiles_n == 1 || a.glu_nb % 32 == 0, "multi-tile GLU needs a tile width that is a multiple of 32");
   } else {
-    p.block_n = pick_block_n(a.N);
+    // split mode stages two W tiles per k-block: narrower plain tiles keep a 3-4 deep ring (the fused-LayerNorm variant needs the
+    // whole row in one tile and runs 2 stages for wide rows)
+    p.block_n = pick_block_n(a.N, (IsSplit<T>::value && !kLN) ? 128 : 256);
     tiles_n = cdiv(a.N, p.block_n);
   }
   p.num_k_blocks = cdiv(a.K, Tr::kBlockK);
@@ -497,9 +499,13 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
     p.epi_batch = 0;
     p.res_depth = 1;
   }
-  const int fixed = (p.has_res ? 16 * p.res_depth * kSlabBytes : 0) + kVecBytes + kNumBars * 8 + 16 + 1024;
+  int fixed = (p.has_res ? 16 * p.res_depth * kSlabBytes : 0) + kVecBytes + kNumBars * 8 + 16 + 1024;
   // one CTA per SM (thread count): a deep ring hides the TMA->MMA->refill round trip
   const int budget = 224 * 1024;
+  if (kLN && p.has_res && p.res_depth == 1 && (budget - fixed) / stage_bytes < 2) {   // wide split-mode rows: residual lands in the x slabs
+    p.res_depth = 0;
+    fixed = kVecBytes + kNumBars * 8 + 16 + 1024;
+  }
   int stages = (budget - fixed) / stage_bytes;
   if (stages < 2) stages = 2;
   if (stages > kMaxStages) stages = kMaxStages;

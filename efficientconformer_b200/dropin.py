@@ -1,17 +1,42 @@
-"""Drop the B200 encoder into an unmodified reference checkout.
+"""Drop the B200 hot path into an unmodified reference checkout.
 
     import efficientconformer_b200 as ec; ec.patch_reference()     # before `from functions import create_model`
     python main.py -c configs/EfficientConformerCTCSmall.json --mode validation-clean --gready   # unchanged CLI
 
-`models.model_ctc.ModelCTC.__init__` looks `ConformerEncoder` up in its own module namespace
-(reference models/model_ctc.py:28,43-44) and `models.transducer` does the same (models/transducer.py:59), so rebinding
-the name in those modules (and in models.encoders) is all that is needed."""
+What is rebound (everything else -- trainer, optimiser, schedules, data loading, tokenizer, beam search -- stays the reference's):
+
+  * `ConformerEncoder` in `models.encoders`, `models.model_ctc`, `models.transducer`: those modules look the class up in their own
+    namespace (reference models/model_ctc.py:28,43-44; models/transducer.py:59).  `.eval()` runs the fused inference engine,
+    `.train()` the CUDA training schedule behind ONE autograd node (SpecAugment inside, SyncBatchNorm holders detected), so the
+    reference's `loss.backward()`, `GradScaler`, `DistributedDataParallel` and `torch.optim` work unchanged.
+  * `LossCTC` in `models.losses` / `models.model_ctc` (reference models/losses.py:48-71): log-softmax + CTC alpha-beta + gradient on
+    the device in one call (`ec_ctc_loss_grad`) instead of `nn.CTCLoss`.
+  * `ModelCTC.gready_search_decoding` (reference models/model_ctc.py:99-136): argmax + collapse on the device (`ec_ctc_greedy`, one
+    device-to-host copy) instead of the reference's B * T' host synchronisations; the token ids handed to `tokenizer.decode` are
+    the same.
+
+The CTC `fc` layer stays the reference's own `nn.Linear` under the drop-in (the reference wraps it in its own DistributedDataParallel,
+models/model_ctc.py:75); the repo's `ModelCTC` runs it inside the engine."""
 import importlib
 import sys
 
 
-def patch_reference(modules=("models.encoders", "models.model_ctc", "models.transducer")):
+def _greedy_search_decoding(self, x, x_len):
+    """Replacement for reference ModelCTC.gready_search_decoding (models/model_ctc.py:99-136)."""
+    import torch
+    from .model_ctc import greedy_ids
+    logits, logits_len = self.encoder(x, x_len)[:2]
+    logits = self.fc(logits)
+    if logits_len is None:
+        logits_len = torch.full((logits.shape[0],), logits.shape[1], dtype=torch.int64, device=logits.device)
+    ids = greedy_ids(logits, logits_len)
+    return self.tokenizer.decode(ids) if getattr(self, "tokenizer", None) is not None else ids
+
+
+def patch_reference(modules=("models.encoders", "models.model_ctc", "models.transducer"), loss=True, greedy=True):
+    """Returns the list of rebound names ("module.attr")."""
     from .encoders import ConformerEncoder
+    from .model_ctc import LossCTC
     patched = []
     for name in modules:
         try:
@@ -20,5 +45,22 @@ def patch_reference(modules=("models.encoders", "models.model_ctc", "models.tran
             continue
         if hasattr(mod, "ConformerEncoder"):
             setattr(mod, "ConformerEncoder", ConformerEncoder)
-            patched.append(name)
+            patched.append(name + ".ConformerEncoder")
+    if loss:
+        for name in ("models.losses", "models.model_ctc"):
+            try:
+                mod = sys.modules.get(name) or importlib.import_module(name)
+            except Exception:
+                continue
+            if hasattr(mod, "LossCTC"):
+                setattr(mod, "LossCTC", LossCTC)
+                patched.append(name + ".LossCTC")
+    if greedy:
+        try:
+            mod = sys.modules.get("models.model_ctc") or importlib.import_module("models.model_ctc")
+            if hasattr(mod, "ModelCTC"):
+                mod.ModelCTC.gready_search_decoding = _greedy_search_decoding
+                patched.append("models.model_ctc.ModelCTC.gready_search_decoding")
+        except Exception:
+            pass
     return patched

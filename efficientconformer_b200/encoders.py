@@ -10,7 +10,7 @@ front end (STFT -> mel -> log, reference models/modules.py:87-106) stays host Py
 `.eval()`: the fused inference engine (ec_engine_forward, CUDA-graph replay) -- what `Model.evaluate`, `gready_search_decoding`
 and `eval_time_encoder` use.  `.train()`: the training operator schedule of efficientconformer_b200/training.py (batch-statistics
 BatchNorm, dropout, one autograd node whose backward is the CUDA backward schedule); SpecAugment
-stays the reference's host PyTorch and is applied by the caller.  There is no fallback path: without the CUDA library or on a
+stays host PyTorch (batched torch ops on the mel tensor) and is applied inside `forward` when training, as the reference does.  There is no fallback path: without the CUDA library or on a
 non-sm_100 device, forward raises.
 """
 import ctypes as C
@@ -109,6 +109,45 @@ class _PreprocessingHolder(nn.Module):
         return x, x_len
 
 
+class SpecAugment(nn.Module):
+    """Host-PyTorch SpecAugment with the reference's semantics (reference models/modules.py:108-151; SURVEY.md section 8 row a3: it stays
+    torch ops on the mel tensor, called inside the train-mode forward like reference models/encoders.py:103-104):
+      * mF frequency masks shared by the whole batch, width floor(U(0, F)), start floor(U(0, n_mels - width))
+        (torchaudio FrequencyMasking(F, iid_masks=False) -> mask_along_axis);
+      * per utterance b, mT time masks inside its valid frames [0, x_len[b]), width floor(U(0, int(pS * x_len[b]))),
+        start floor(U(0, x_len[b] - width)); masked cells are set to 0.
+    The reference loops over the batch with one host read of x_len[b] per utterance; here all B * mT masks are drawn and applied with
+    batched device ops (no host synchronisation).  Random streams differ from the reference's, the distribution is the same."""
+
+    def __init__(self, spec_augment, mF, F, mT, pS):
+        super().__init__()
+        self.spec_augment, self.mF, self.F, self.mT, self.pS = bool(spec_augment), int(mF), int(F), int(mT), float(pS)
+
+    def forward(self, x, x_len=None):
+        if not self.spec_augment:
+            return x
+        B, n_mels, T = x.shape
+        dev = x.device
+        keep = torch.ones(B, n_mels, T, dtype=torch.bool, device=dev)
+        if self.mF > 0:
+            value = torch.rand(self.mF, device=dev) * self.F
+            start = (torch.rand(self.mF, device=dev) * (n_mels - value)).long()
+            end = start + value.long()
+            f = torch.arange(n_mels, device=dev)[None, :]
+            fmask = ((f >= start[:, None]) & (f < end[:, None])).any(0)                     # (n_mels,)
+            keep &= ~fmask[None, :, None]
+        if self.mT > 0:
+            lens = (x_len.to(dev) if x_len is not None else torch.full((B,), T, device=dev)).to(torch.float32)
+            t_param = torch.floor(self.pS * lens)                                           # int(pS * x_len[b])
+            value = torch.rand(B, self.mT, device=dev) * t_param[:, None]
+            start = (torch.rand(B, self.mT, device=dev) * (lens[:, None] - value)).long()
+            end = start + value.long()
+            t = torch.arange(T, device=dev)[None, None, :]
+            tmask = ((t >= start[:, :, None]) & (t < end[:, :, None])).any(1)              # (B, T)
+            keep &= ~tmask[:, None, :]
+        return x * keep.to(x.dtype)
+
+
 class _SubsamplingHolder(nn.Module):      # reference models/modules.py:201-230 (one or two strided Conv2d layers)
     def __init__(self, params):
         super().__init__()
@@ -153,6 +192,8 @@ class ConformerEncoder(nn.Module):
         self.params = dict(params)
         self.specs = resolve_blocks(params)
         self.preprocessing = _PreprocessingHolder(params)
+        self.augment = SpecAugment(params.get("spec_augment", False), params.get("mF", 0), params.get("F", 0), params.get("mT", 0),
+                                   params.get("pS", 0.0))
         self.subsampling_module = _SubsamplingHolder(params)
         feat = params["subsampling_filters"][-1] * params["n_mels"] // 2 ** params["subsampling_layers"]
         self.linear = nn.Linear(feat, self.specs[0].dim_model)
@@ -350,12 +391,30 @@ class ConformerEncoder(nn.Module):
             out_len = plan.out_len.clone() if has_len else None
         return x, out_len, lg
 
-    def training_path(self):
+    def _sync_batchnorm_group(self):
+        """(found, process_group) of the first nn.SyncBatchNorm among the holders: the reference's distribute_strategy runs
+        SyncBatchNorm.convert_sync_batchnorm over the encoder (reference models/model_ctc.py:73), which swaps the BatchNorm holders."""
+        for m in self.modules():
+            if isinstance(m, nn.SyncBatchNorm):
+                return True, m.process_group
+        return False, None
+
+    def training_path(self, device=None):
         """The train-mode operator schedule (efficientconformer_b200/training.py) bound to this encoder's parameters."""
         from .training import TrainingPath
+        import torch.distributed as dist
+        reducer = self.__dict__.get("_stats_reducer")
+        has_sync, group = self._sync_batchnorm_group()
+        if reducer is None and has_sync and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            # never run local statistics silently under SyncBatchNorm holders: install the cross-rank exchange.  Ranks may hold
+            # different frame counts under the reference's DistributedSampler + collate_fn_pad, hence uniform=False.
+            from .distributed import SyncBatchNormReducer
+            reducer = SyncBatchNormReducer(group, device if device is not None else next(self.parameters()).device, uniform=False)
+            object.__setattr__(self, "_stats_reducer", reducer)
+            object.__setattr__(self, "_training_path", None)
         tp = self.__dict__.get("_training_path")
         if tp is None or tp.head is not self._head:
-            tp = TrainingPath(self, self._head, stats_reducer=self.__dict__.get("_stats_reducer"))
+            tp = TrainingPath(self, self._head, stats_reducer=reducer)
             object.__setattr__(self, "_training_path", tp)
         return tp
 
@@ -372,7 +431,7 @@ class ConformerEncoder(nn.Module):
             raise RuntimeError("effconf_b200 runs on CUDA sm_100 only (the reference's --cpu path is the oracle's job)")
         if want_logits and self._head is None:
             raise RuntimeError("no fc head attached")
-        path = self.training_path()
+        path = self.training_path(mel.device)
         prec = self._select_precision()
         self.mark_weights_changed()          # BatchNorm running statistics are updated through raw pointers below
         mel = mel.float().contiguous()
@@ -391,6 +450,8 @@ class ConformerEncoder(nn.Module):
     def forward(self, x, x_len=None):
         """reference signature: x (B, L_audio) float, x_len (B,) long or None -> (x, x_len, attentions)."""
         mel, mel_len = self.preprocessing(x.float(), x_len)
+        if self.training:                                   # reference models/encoders.py:103-104
+            mel = self.augment(mel, mel_len)
         out, out_len, _ = self.forward_mel(mel.contiguous(), mel_len)
         # the reference returns one (B,H,T',T') attention map per block that no caller reads; they are never materialised here
         return out, out_len, [None] * len(self.blocks)

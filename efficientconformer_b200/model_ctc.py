@@ -123,6 +123,8 @@ class ModelCTC(nn.Module):
     def forward(self, batch):
         x, _, x_len, _ = batch
         mel, mel_len = self.encoder.preprocessing(x.float(), x_len)
+        if self.training:                                   # reference models/encoders.py:103-104 (SpecAugment inside the train-mode forward)
+            mel = self.encoder.augment(mel, mel_len)
         return self.forward_mel(mel.contiguous(), mel_len)
 
     def forward_mel(self, mel, mel_len=None):

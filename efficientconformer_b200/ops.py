@@ -224,6 +224,19 @@ def linear_wgrad(dy_act, x_act, precision, dw_accum=None):
     return dw
 
 
+def linear_wgrad_bias(dy_act, x_act, precision):
+    """(dW [N, K], db [N]) fp32 of a Linear from ONE kernel: dW = dY^T . X on tcgen05, db = column sums of dY through a ones operand."""
+    pr = _p(precision)
+    dy_act, x_act = dy_act.contiguous(), x_act.contiguous()
+    M, N = dy_act.shape
+    K = x_act.shape[1]
+    dw = torch.empty(N, K, dtype=torch.float32, device=dy_act.device)
+    db = torch.empty(N, dtype=torch.float32, device=dy_act.device)
+    work = torch.empty(lib().ec_op_wgrad_work_bytes(pr, M, N, K), dtype=torch.uint8, device=dy_act.device)
+    check(lib().ec_op_wgrad_bias(pr, ptr(dy_act), ptr(x_act), M, N, K, ptr(dw), 0, ptr(db), ptr(work), stream_ptr()))
+    return dw, db
+
+
 class DwConvTrain:
     """Training-mode depthwise conv -> BatchNorm1d (batch statistics, running-stat update) -> Swish and its backward
     (reference models/modules.py:515-517 under .train()).  `reduce_stats` (SyncBatchNorm, efficientconformer_b200/distributed.py) merges the

@@ -203,12 +203,12 @@ class TrainingPath:
         L = holder.layers
         drop = self._drop
         dy = o.dropout_cast_scaled(d_out, pr, alpha, drop, s2)                 # d(W2 output) in the activation type
-        grads[f"{prefix}.layers.4.weight"] = o.linear_wgrad(dy, s, pr)
-        grads[f"{prefix}.layers.4.bias"] = o.colsum(dy, pr)
+        dw_, db_ = o.linear_wgrad_bias(dy, s, pr)
+        grads[f"{prefix}.layers.4.weight"], grads[f"{prefix}.layers.4.bias"] = dw_, db_
         ds = self._dgrad(dy, L[4].weight, pr)
         dz = o.swish_dropout_bwd(z, ds, drop, s1, pr)
-        grads[f"{prefix}.layers.1.weight"] = o.linear_wgrad(dz, h0, pr)
-        grads[f"{prefix}.layers.1.bias"] = o.colsum(dz, pr)
+        dw_, db_ = o.linear_wgrad_bias(dz, h0, pr)
+        grads[f"{prefix}.layers.1.weight"], grads[f"{prefix}.layers.1.bias"] = dw_, db_
         dh0 = self._dgrad(dz, L[1].weight, pr)
         dx, dg, db = o.layernorm_bwd(x, dh0, L[0].weight, dx_accum=d_out)
         grads[f"{prefix}.layers.0.weight"], grads[f"{prefix}.layers.0.bias"] = dg, db
@@ -281,8 +281,8 @@ class TrainingPath:
         if d_logits is not None:
             x_act, w_fc = tape["head"]
             dl = o.cast(d_logits.reshape(-1, d_logits.shape[-1]), pr)
-            grads["fc.weight"] = o.linear_wgrad(dl, x_act, pr)
-            grads["fc.bias"] = o.colsum(dl, pr)
+            dw_, db_ = o.linear_wgrad_bias(dl, x_act, pr)
+            grads["fc.weight"], grads["fc.bias"] = dw_, db_
             dx = self._dgrad(dl, self.head.weight, pr, residual=dx)
         if dx is None:
             raise RuntimeError("backward needs a gradient for the encoder output or the logits")
@@ -290,8 +290,8 @@ class TrainingPath:
             dx = self._block_backward(enc.blocks[i], self.specs[i], tape["blocks"][i], dx, B, pr, grads, f"encoder.blocks.{i}")
         a, sub_saved, w_lin, site0 = tape["front"]
         d_act = o.dropout_cast_scaled(dx, pr, 1.0, self._drop, site0)
-        grads["encoder.linear.weight"] = o.linear_wgrad(d_act, a, pr)
-        grads["encoder.linear.bias"] = o.colsum(d_act, pr)
+        dw_, db_ = o.linear_wgrad_bias(d_act, a, pr)
+        grads["encoder.linear.weight"], grads["encoder.linear.bias"] = dw_, db_
         da = self._dgrad(d_act, enc.linear.weight, pr)
         dw, db, dgam, dbet = o.SubsampleTrain.backward(da, sub_saved, reduce_stats=self.stats_reducer)
         p = "encoder.subsampling_module.layers.0"
@@ -312,21 +312,21 @@ class TrainingPath:
         c = f"{p}.convolution_module.layers"
         dy = o.dropout_cast_scaled(dx3, pr, 1.0, drop, t["s_conv"])            # gradient of the pw2 output (after its dropout)
         h2 = t["h"].view(B * To, De)
-        grads[f"{c}.7.weight"] = o.linear_wgrad(dy, h2, pr).view(De, De, 1)
-        grads[f"{c}.7.bias"] = o.colsum(dy, pr)
+        dw_, db_ = o.linear_wgrad_bias(dy, h2, pr)
+        grads[f"{c}.7.weight"], grads[f"{c}.7.bias"] = dw_.view(De, De, 1), db_
         dh = self._dgrad(dy, Lc[7].weight, pr)
         dgl, dw_dw, db_dw, dgam, dbet = o.DwConvTrain.backward(dh.view(B, To, De), t["dw_saved"], reduce_stats=self.stats_reducer)
         grads[f"{c}.4.weight"], grads[f"{c}.4.bias"] = dw_dw.view(De, 1, -1), db_dw
         grads[f"{c}.5.weight"], grads[f"{c}.5.bias"] = dgam, dbet
         dzg = o.glu_bwd(t["zg"], dgl.view(B * T, De), pr)
-        grads[f"{c}.2.weight"] = o.linear_wgrad(dzg, t["c_in"], pr).view(2 * De, D, 1)
-        grads[f"{c}.2.bias"] = o.colsum(dzg, pr)
+        dw_, db_ = o.linear_wgrad_bias(dzg, t["c_in"], pr)
+        grads[f"{c}.2.weight"], grads[f"{c}.2.bias"] = dw_.view(2 * De, D, 1), db_
         dc_in = self._dgrad(dzg, Lc[2].weight, pr)
         if spec.has_conv_res_proj:
             # the residual branch sees the un-dropped gradient dx3
             dres = o.cast(dx3, pr) if drop.p > 0.0 else dy
-            grads[f"{p}.conv_res.1.weight"] = o.linear_wgrad(dres, t["xs"], pr).view(De, D, 1)
-            grads[f"{p}.conv_res.1.bias"] = o.colsum(dres, pr)
+            dw_, db_ = o.linear_wgrad_bias(dres, t["xs"], pr)
+            grads[f"{p}.conv_res.1.weight"], grads[f"{p}.conv_res.1.bias"] = dw_.view(De, D, 1), db_
             dxs = self._dgrad(dres, blk.conv_res[1].weight, pr)
             acc = o.zeros_f32(B * T, D, dx3.device)
             o.strided_rows_bwd(dxs.view(B, To, D), acc.view(B, T, D), st)
@@ -339,18 +339,17 @@ class TrainingPath:
         a = f"{p}.multi_head_self_attention_module"
         do = o.dropout_cast_scaled(dx2, pr, 1.0, drop, t["s_att"])
         att2 = t["att"].view(B * T, D)
-        grads[f"{a}.mhsa.output_layer.weight"] = o.linear_wgrad(do, att2, pr)
-        grads[f"{a}.mhsa.output_layer.bias"] = o.colsum(do, pr)
+        dw_, db_ = o.linear_wgrad_bias(do, att2, pr)
+        grads[f"{a}.mhsa.output_layer.weight"], grads[f"{a}.mhsa.output_layer.bias"] = dw_, db_
         datt = self._dgrad(do, m.mhsa.output_layer.weight, pr)
         dqkv, dE, du, dv = o.relpos_attention_bwd(t["qkv"].view(B, T, 3 * D), t["E"], m.mhsa.u, m.mhsa.v, t["cur_len"], H, G,
                                                   datt.view(B, T, D), pr)
         grads[f"{a}.mhsa.u"], grads[f"{a}.mhsa.v"] = du, dv
         dE_act = o.cast(dE, pr)
-        grads[f"{a}.mhsa.pos_layer.weight"] = o.linear_wgrad(dE_act, t["R"], pr)
-        grads[f"{a}.mhsa.pos_layer.bias"] = o.colsum(dE_act, pr)
+        dw_, db_ = o.linear_wgrad_bias(dE_act, t["R"], pr)
+        grads[f"{a}.mhsa.pos_layer.weight"], grads[f"{a}.mhsa.pos_layer.bias"] = dw_, db_
         dqkv_act = o.cast(dqkv.view(B * T, 3 * D), pr)
-        dwqkv = o.linear_wgrad(dqkv_act, t["a_in"], pr)                        # [3D, D]: rows q | k | v
-        dbqkv = o.colsum(dqkv_act, pr)
+        dwqkv, dbqkv = o.linear_wgrad_bias(dqkv_act, t["a_in"], pr)            # [3D, D]: rows q | k | v
         for j, nm in enumerate(("query", "key", "value")):
             grads[f"{a}.mhsa.{nm}_layer.weight"] = dwqkv[j * D:(j + 1) * D]
             grads[f"{a}.mhsa.{nm}_layer.bias"] = dbqkv[j * D:(j + 1) * D]

@@ -202,6 +202,9 @@ int ec_op_dwconv_bwd(int precision, const float* dy, const void* x, const float*
                      float* dx, float* dw, float* db, void* work, void* stream);
 size_t ec_op_wgrad_work_bytes(int precision, int M, int N, int K);
 int ec_op_wgrad(int precision, const void* dy, const void* x, int M, int N, int K, float* dw, int accumulate, void* work, void* stream);
+/* same, plus the bias gradient db [N] = column sums of dY from the same kernel (a ones tile as a second MMA operand) */
+int ec_op_wgrad_bias(int precision, const void* dy, const void* x, int M, int N, int K, float* dw, int accumulate, float* db, void* work,
+                     void* stream);
 size_t ec_op_layernorm_bwd_work_bytes(int dim);
 int ec_op_layernorm_bwd(const float* x, const float* dy, int rows, int dim, const float* gamma, float eps, float* dx, int accumulate,
                         float* dgamma, float* dbeta, void* work, void* stream);

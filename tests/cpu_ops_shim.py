@@ -92,6 +92,10 @@ def linear_wgrad(dy_act, x_act, precision, dw_accum=None):
     return dw
 
 
+def linear_wgrad_bias(dy_act, x_act, precision):
+    return _d(dy_act).t() @ _d(x_act), _d(dy_act).sum(0)
+
+
 def _attention(qkv, E, u, v, x_len, H, G):
     """Closed form of SURVEY.md section 8 row a9 (same as tests/test_gpu_ops._attention_reference)."""
     B, T, D3 = qkv.shape

@@ -225,7 +225,7 @@ def test_execution_options_do_not_change_results(sd, fuse_ln, pdl):
         L.ec_set_pdl(pdl)
         m = make_model(sd, PARITY)
         m.forward_mel(mel.to(DEV), mel_len.to(DEV))                       # creates the engine
-        eng = m.encoder._engines[_lib.PREC_TF32][0]
+        eng = m.encoder._engines[_lib.PRECISIONS[PARITY]][0]
         L.ec_engine_set_fuse_ln(eng, fuse_ln)
         m.encoder._plans.clear()                                          # drop graphs captured with the old option
         lg, ol, _ = m.forward_mel(mel.to(DEV), mel_len.to(DEV))
