@@ -322,11 +322,11 @@ int launch_relpos_attention_bf16(const AttnArgs& a, cudaStream_t stream) {
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(p.d));
   const int kt = cdiv(p.d, 16);
   switch (kt) {
-    case 2: return launch_inst<2, __nv_bfloat16>(p, stream);
-    case 3: return launch_inst<3, __nv_bfloat16>(p, stream);
-    case 4: return launch_inst<4, __nv_bfloat16>(p, stream);
-    case 5: return launch_inst<5, __nv_bfloat16>(p, stream);
-    case 6: return launch_inst<6, __nv_bfloat16>(p, stream);
+    case 2: return a.in_bf16 ? launch_inst<2, SplitBf16>(p, stream) : launch_inst<2, __nv_bfloat16>(p, stream);
+    case 3: return a.in_bf16 ? launch_inst<3, SplitBf16>(p, stream) : launch_inst<3, __nv_bfloat16>(p, stream);
+    case 4: return a.in_bf16 ? launch_inst<4, SplitBf16>(p, stream) : launch_inst<4, __nv_bfloat16>(p, stream);
+    case 5: return a.in_bf16 ? launch_inst<5, SplitBf16>(p, stream) : launch_inst<5, __nv_bfloat16>(p, stream);
+    case 6: return a.in_bf16 ? launch_inst<6, SplitBf16>(p, stream) : launch_inst<6, __nv_bfloat16>(p, stream);
     default: EC_FAIL("unsupported attention head dim " + std::to_string(p.d) + " for the bf16 kernel");
   }
 }

@@ -390,7 +390,7 @@ int launch_relpos_attention_bwd_tc(int precision, const AttnArgs& a, const float
   const long long sE = static_cast<long long>(p.R) * dp;
   const int H = a.H;
 
-  if (precision == EC_PREC_BF16X2) {
+  if (precision == EC_PREC_BF16X2 && !a.in_bf16) {
     tc_pack_kernel<SplitBf16><<<egrid(static_cast<long long>(BH) * Tg * dp), 256, 0, st>>>(p);
     tc_pack_e_kernel<SplitBf16><<<egrid(static_cast<long long>(H) * p.R * dp), 256, 0, st>>>(p);
   } else {

@@ -332,7 +332,7 @@ static int make_strided_map(CUtensorMap* map, const void* ptr, int rows, int col
   return EC_OK;
 }
 
-template <int KT0, int KT1>
+template <int KT0, int KT1, typename OutT>
 static int launch_tma_inst(const AttnArgs& a, AttnDevT& p, cudaStream_t stream) {
   constexpr int KT = KT0 + KT1;
   CUtensorMap kv0, kv1, e0, e1;
@@ -348,11 +348,11 @@ static int launch_tma_inst(const AttnArgs& a, AttnDevT& p, cudaStream_t stream) 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(relpos_attn_tma_kernel<KT0, KT1, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(relpos_attn_tma_kernel<KT0, KT1, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   EC_CUDA(attr_err);
   dim3 grid(cdiv(p.Tg, kTM), p.H, p.B);
-  return launch_pdl(relpos_attn_tma_kernel<KT0, KT1, __nv_bfloat16>, grid, dim3(128), smem, stream, kv0, kv1, e0, e1, p);
+  return launch_pdl(relpos_attn_tma_kernel<KT0, KT1, OutT>, grid, dim3(128), smem, stream, kv0, kv1, e0, e1, p);
 }
 
 // Returns EC_OK after launching, or 1 (without setting an error) when the shape does not fit the panel scheme; the caller then
@@ -400,10 +400,10 @@ int try_launch_relpos_attention_tma(const AttnArgs& a, cudaStream_t stream, bool
     kt1 = std::max(kt1, np == 2 ? cdiv(pc[1].shift + pc[1].n, 16) : 0);
   }
   int rc;
-  if (kt1 == 0 && kt0 <= 2) rc = launch_tma_inst<2, 0>(a, p, stream);
-  else if (kt1 == 0 && kt0 == 3) rc = launch_tma_inst<3, 0>(a, p, stream);
-  else if (kt1 == 0 && kt0 == 4) rc = launch_tma_inst<4, 0>(a, p, stream);
-  else if (kt0 <= 4 && kt1 <= 2) rc = launch_tma_inst<4, 2>(a, p, stream);
+  if (kt1 == 0 && kt0 <= 2) rc = a.in_bf16 ? launch_tma_inst<2, 0, SplitBf16>(a, p, stream) : launch_tma_inst<2, 0, __nv_bfloat16>(a, p, stream);
+  else if (kt1 == 0 && kt0 == 3) rc = a.in_bf16 ? launch_tma_inst<3, 0, SplitBf16>(a, p, stream) : launch_tma_inst<3, 0, __nv_bfloat16>(a, p, stream);
+  else if (kt1 == 0 && kt0 == 4) rc = a.in_bf16 ? launch_tma_inst<4, 0, SplitBf16>(a, p, stream) : launch_tma_inst<4, 0, __nv_bfloat16>(a, p, stream);
+  else if (kt0 <= 4 && kt1 <= 2) rc = a.in_bf16 ? launch_tma_inst<4, 2, SplitBf16>(a, p, stream) : launch_tma_inst<4, 2, __nv_bfloat16>(a, p, stream);
   else return EC_OK;
   *launched = rc == EC_OK;
   return rc;

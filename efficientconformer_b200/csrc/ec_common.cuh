@@ -160,6 +160,7 @@ struct GemmArgs {
   const float* residual; int ld_res;   // fp32 [M, *] or nullptr
   float* out_f32; int ld_out;          // optional fp32 output
   void* out_act; int ld_act;           // optional activation-type output (rounded)
+  int act_bf16;                        // split mode only: out_act is written as PLAIN bf16 (q|k|v and E feed the bf16 attention kernels)
   int round_out;                       // round the fp32 output to TF32 (feeds the TF32 mma.sync attention)
   // fused LayerNorm epilogue (N <= 256, plain epilogue): mode 1: ln_out = LN1(out); mode 2: out <- LN1(out), ln_out = LN2(out)
   // (LN2 = identity copy when ln2_g == nullptr).  copy_out: activation-type copy of every copy_stride-th frame of `out` (mode 1).
@@ -205,7 +206,11 @@ struct AttnArgs {
   int B, T, D, H, G;
   void* out; int ld_out; // [B*T, D] activation type
   int in_f32;            // EC_PREC_BF16 only: q|k|v / E are fp32 (odd head dims fall back to the TF32 kernel with bf16 output)
+  int in_bf16;           // EC_PREC_BF16X2 only: q|k|v / E are plain bf16 (attn_operands_bf16(): the bf16 kernels apply), output packed
 };
+// Split mode: the attention core runs on bf16 q|k|v / E (its contribution to the logits error stays ~2e-4, measured) whenever the
+// bf16 kernels support the head layout; other layouts keep packed operands and the TF32 kernel.
+inline bool attn_operands_bf16(int D, int H, int G) { return D % 8 == 0 && ((G * D) / H) % 2 == 0; }
 int launch_relpos_attention(int precision, const AttnArgs& a, cudaStream_t stream);
 int launch_relpos_attention_bf16(const AttnArgs& a, cudaStream_t stream);
 int try_launch_relpos_attention_tma(const AttnArgs& a, cudaStream_t stream, bool* launched);

@@ -51,14 +51,26 @@ def layernorm(x, gamma, beta, precision, eps=1e-6, want_f32=True, want_act=True)
     return ya, yf
 
 
-def gemm(a_act, w_act, bias, precision, alpha=1.0, act=0, residual=None, want_f32=True, want_act=False):
-    """a_act [M,K] in the activation type, w_act [N,K] a weight operand (cast_weight / transpose_cast)."""
+def attn_operand_precision(precision, dim, heads, group):
+    """Precision id of the q|k|v / E operands of the attention core: the activation type, except in split mode where they are plain
+    bf16 whenever the bf16 attention kernels support the head layout (ec_attention_operands_bf16)."""
+    pr = _p(precision)
+    if pr == PREC_BF16X2 and lib().ec_attention_operands_bf16(pr, dim, heads, group):
+        return PRECISIONS["bf16"]
+    return pr
+
+
+def gemm(a_act, w_act, bias, precision, alpha=1.0, act=0, residual=None, want_f32=True, want_act=False, act_bf16=False):
+    """a_act [M,K] in the activation type, w_act [N,K] a weight operand (cast_weight / transpose_cast).
+    act_bf16 (split mode): the activation-type output is plain bf16 (attention operands)."""
     pr = _p(precision)
     M, K = a_act.shape
     N = w_act.shape[0]
+    act_bf16 = bool(act_bf16) and pr == PREC_BF16X2
     of = torch.empty(M, N, dtype=torch.float32, device=a_act.device) if want_f32 else None
-    oa = torch.empty(M, N, dtype=act_dtype(pr), device=a_act.device) if want_act else None
-    check(lib().ec_op_gemm(pr, ptr(a_act), ptr(w_act), M, N, K, ptr(bias), alpha, act, ptr(residual), ptr(of), ptr(oa), stream_ptr()))
+    oa = torch.empty(M, N, dtype=torch.bfloat16 if act_bf16 else act_dtype(pr), device=a_act.device) if want_act else None
+    check(lib().ec_op_gemm_ex(pr, ptr(a_act), ptr(w_act), M, N, K, ptr(bias), alpha, act, ptr(residual), ptr(of), ptr(oa),
+                              1 if act_bf16 else 0, stream_ptr()))
     return of, oa
 
 
@@ -126,7 +138,8 @@ def relpos_attention(qkv, E, u, v, x_len, heads, group, precision):
     D = D3 // 3
     out = torch.empty(B, T, D, dtype=act_dtype(pr), device=qkv.device)
     xl = x_len.to(torch.int32).contiguous() if x_len is not None else None
-    qkv, E = cast(qkv, pr), cast(E, pr)
+    opr = attn_operand_precision(pr, D, heads, group)
+    qkv, E = cast(qkv, opr), cast(E, opr)
     check(lib().ec_op_relpos_attention(pr, ptr(qkv), ptr(E), ptr(u.float().contiguous()),
                                        ptr(v.float().contiguous()), ptr(xl), B, T, D, heads, group, ptr(out), stream_ptr()))
     return out
@@ -166,14 +179,17 @@ def layernorm_bwd(x, dy, gamma, eps=1e-6, dx_accum=None):
     return dx, dg, db
 
 
-def colsum(m, precision):
-    """Column sums (bias gradient) of a 2-D fp32 or activation-type matrix."""
+def colsum(m, precision, is_f32=None):
+    """Column sums (bias gradient) of a 2-D fp32 or activation-type matrix.  fp32-typed tensors are plain fp32 values unless the
+    precision is the split mode, whose packed (hi, lo) words also travel as fp32-typed tensors: pass is_f32=True for true fp32 there."""
     pr = _p(precision)
     m = m.contiguous()
     rows, cols = m.shape
+    if is_f32 is None:
+        is_f32 = m.dtype == torch.float32 and pr != PREC_BF16X2
     out = torch.empty(cols, dtype=torch.float32, device=m.device)
     work = torch.empty(lib().ec_op_colsum_work_bytes(cols), dtype=torch.uint8, device=m.device)
-    check(lib().ec_op_colsum(pr, ptr(m), 1 if m.dtype == torch.float32 else 0, rows, cols, ptr(out), ptr(work), stream_ptr()))
+    check(lib().ec_op_colsum(pr, ptr(m), 1 if is_f32 else 0, rows, cols, ptr(out), ptr(work), stream_ptr()))
     return out
 
 

@@ -78,6 +78,11 @@ class TrainingPath:
         self._drop = None
         self._tables = {}
         self.weights = None                      # optional arena-backed operand provider (trainer.ArenaWeights)
+        # Weight gradients are off the critical path of the backward (only the optimiser reads them): they run on a forked side
+        # stream (event fork / join, capturable), overlapping the data-gradient chain on the main stream.
+        self.side_wgrad = True
+        self._side = None
+        self._side_keep = []
 
     # ---- GEMM operands of the weights ----------------------------------------------------------------------------------------
     # Default: one cast / transposed cast per weight and use.  CTCTrainStep installs a provider backed by its flat parameter arena
@@ -93,6 +98,24 @@ class TrainingPath:
         if self.weights is not None:
             return self.weights.act_t(weight)
         return _ops.transpose_cast(_w2(weight), pr)
+
+    def _wgrad(self, dy_act, x_act, pr):
+        """(dW, db) of a Linear on the side stream.  The operands are kept alive until the join at the end of backward()."""
+        if not self.side_wgrad or not dy_act.is_cuda:
+            return _ops.linear_wgrad_bias(dy_act, x_act, pr)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dy_act.device)
+        main = torch.cuda.current_stream(dy_act.device)
+        self._side.wait_stream(main)             # dy was produced on the main stream
+        with torch.cuda.stream(self._side):
+            out = _ops.linear_wgrad_bias(dy_act, x_act, pr)
+        self._side_keep.append((dy_act, x_act))
+        return out
+
+    def _join_side(self, device):
+        if self._side is not None and self._side_keep:
+            torch.cuda.current_stream(device).wait_stream(self._side)
+        self._side_keep = []
 
     def _dgrad(self, dy_act, weight, pr, residual=None):
         return _ops.gemm(dy_act, self._wt(weight, pr), None, pr, residual=residual)[0]
@@ -203,11 +226,11 @@ class TrainingPath:
         L = holder.layers
         drop = self._drop
         dy = o.dropout_cast_scaled(d_out, pr, alpha, drop, s2)                 # d(W2 output) in the activation type
-        dw_, db_ = o.linear_wgrad_bias(dy, s, pr)
+        dw_, db_ = self._wgrad(dy, s, pr)
         grads[f"{prefix}.layers.4.weight"], grads[f"{prefix}.layers.4.bias"] = dw_, db_
         ds = self._dgrad(dy, L[4].weight, pr)
         dz = o.swish_dropout_bwd(z, ds, drop, s1, pr)
-        dw_, db_ = o.linear_wgrad_bias(dz, h0, pr)
+        dw_, db_ = self._wgrad(dz, h0, pr)
         grads[f"{prefix}.layers.1.weight"], grads[f"{prefix}.layers.1.bias"] = dw_, db_
         dh0 = self._dgrad(dz, L[1].weight, pr)
         dx, dg, db = o.layernorm_bwd(x, dh0, L[0].weight, dx_accum=d_out)
@@ -224,11 +247,12 @@ class TrainingPath:
         m = blk.multi_head_self_attention_module
         a_in = o.layernorm(x1, m.norm.weight, m.norm.bias, pr, want_f32=False, want_act=True)[0]
         wqkv, bqkv, qkv_handle = self._qkv(m.mhsa, pr)
-        qkv = o.gemm(a_in, wqkv, bqkv, pr, want_f32=False, want_act=True)[1]
+        ab16 = o.attn_operand_precision(pr, D, H, G) != pr           # split mode: plain bf16 q|k|v and E for the attention core
+        qkv = o.gemm(a_in, wqkv, bqkv, pr, want_f32=False, want_act=True, act_bf16=ab16)[1]
         t_pad = T + (-T) % G
         R = self._table(t_pad, spec, pr, x.device)
         wpos = self._w(m.mhsa.pos_layer.weight, pr)
-        E = o.gemm(R, wpos, m.mhsa.pos_layer.bias, pr, want_f32=False, want_act=True)[1]
+        E = o.gemm(R, wpos, m.mhsa.pos_layer.bias, pr, want_f32=False, want_act=True, act_bf16=ab16)[1]
         att = o.relpos_attention_act(qkv.view(B, T, 3 * D), E, m.mhsa.u, m.mhsa.v, cur_len, H, G, pr)
         wo = self._w(m.mhsa.output_layer.weight, pr)
         s_att = drop.next_site()
@@ -281,7 +305,7 @@ class TrainingPath:
         if d_logits is not None:
             x_act, w_fc = tape["head"]
             dl = o.cast(d_logits.reshape(-1, d_logits.shape[-1]), pr)
-            dw_, db_ = o.linear_wgrad_bias(dl, x_act, pr)
+            dw_, db_ = self._wgrad(dl, x_act, pr)
             grads["fc.weight"], grads["fc.bias"] = dw_, db_
             dx = self._dgrad(dl, self.head.weight, pr, residual=dx)
         if dx is None:
@@ -290,12 +314,13 @@ class TrainingPath:
             dx = self._block_backward(enc.blocks[i], self.specs[i], tape["blocks"][i], dx, B, pr, grads, f"encoder.blocks.{i}")
         a, sub_saved, w_lin, site0 = tape["front"]
         d_act = o.dropout_cast_scaled(dx, pr, 1.0, self._drop, site0)
-        dw_, db_ = o.linear_wgrad_bias(d_act, a, pr)
+        dw_, db_ = self._wgrad(d_act, a, pr)
         grads["encoder.linear.weight"], grads["encoder.linear.bias"] = dw_, db_
         da = self._dgrad(d_act, enc.linear.weight, pr)
         dw, db, dgam, dbet = o.SubsampleTrain.backward(da, sub_saved, reduce_stats=self.stats_reducer)
         p = "encoder.subsampling_module.layers.0"
         grads[f"{p}.0.weight"], grads[f"{p}.0.bias"], grads[f"{p}.1.weight"], grads[f"{p}.1.bias"] = dw, db, dgam, dbet
+        self._join_side(da.device)               # every weight gradient is complete before the caller reads `grads`
         return grads
 
     def _block_backward(self, blk, spec, t, d_out, B, pr, grads, p):
@@ -312,20 +337,20 @@ class TrainingPath:
         c = f"{p}.convolution_module.layers"
         dy = o.dropout_cast_scaled(dx3, pr, 1.0, drop, t["s_conv"])            # gradient of the pw2 output (after its dropout)
         h2 = t["h"].view(B * To, De)
-        dw_, db_ = o.linear_wgrad_bias(dy, h2, pr)
+        dw_, db_ = self._wgrad(dy, h2, pr)
         grads[f"{c}.7.weight"], grads[f"{c}.7.bias"] = dw_.view(De, De, 1), db_
         dh = self._dgrad(dy, Lc[7].weight, pr)
         dgl, dw_dw, db_dw, dgam, dbet = o.DwConvTrain.backward(dh.view(B, To, De), t["dw_saved"], reduce_stats=self.stats_reducer)
         grads[f"{c}.4.weight"], grads[f"{c}.4.bias"] = dw_dw.view(De, 1, -1), db_dw
         grads[f"{c}.5.weight"], grads[f"{c}.5.bias"] = dgam, dbet
         dzg = o.glu_bwd(t["zg"], dgl.view(B * T, De), pr)
-        dw_, db_ = o.linear_wgrad_bias(dzg, t["c_in"], pr)
+        dw_, db_ = self._wgrad(dzg, t["c_in"], pr)
         grads[f"{c}.2.weight"], grads[f"{c}.2.bias"] = dw_.view(2 * De, D, 1), db_
         dc_in = self._dgrad(dzg, Lc[2].weight, pr)
         if spec.has_conv_res_proj:
             # the residual branch sees the un-dropped gradient dx3
             dres = o.cast(dx3, pr) if drop.p > 0.0 else dy
-            dw_, db_ = o.linear_wgrad_bias(dres, t["xs"], pr)
+            dw_, db_ = self._wgrad(dres, t["xs"], pr)
             grads[f"{p}.conv_res.1.weight"], grads[f"{p}.conv_res.1.bias"] = dw_.view(De, D, 1), db_
             dxs = self._dgrad(dres, blk.conv_res[1].weight, pr)
             acc = o.zeros_f32(B * T, D, dx3.device)
@@ -339,17 +364,17 @@ class TrainingPath:
         a = f"{p}.multi_head_self_attention_module"
         do = o.dropout_cast_scaled(dx2, pr, 1.0, drop, t["s_att"])
         att2 = t["att"].view(B * T, D)
-        dw_, db_ = o.linear_wgrad_bias(do, att2, pr)
+        dw_, db_ = self._wgrad(do, att2, pr)
         grads[f"{a}.mhsa.output_layer.weight"], grads[f"{a}.mhsa.output_layer.bias"] = dw_, db_
         datt = self._dgrad(do, m.mhsa.output_layer.weight, pr)
         dqkv, dE, du, dv = o.relpos_attention_bwd(t["qkv"].view(B, T, 3 * D), t["E"], m.mhsa.u, m.mhsa.v, t["cur_len"], H, G,
                                                   datt.view(B, T, D), pr)
         grads[f"{a}.mhsa.u"], grads[f"{a}.mhsa.v"] = du, dv
         dE_act = o.cast(dE, pr)
-        dw_, db_ = o.linear_wgrad_bias(dE_act, t["R"], pr)
+        dw_, db_ = self._wgrad(dE_act, t["R"], pr)
         grads[f"{a}.mhsa.pos_layer.weight"], grads[f"{a}.mhsa.pos_layer.bias"] = dw_, db_
         dqkv_act = o.cast(dqkv.view(B * T, 3 * D), pr)
-        dwqkv, dbqkv = o.linear_wgrad_bias(dqkv_act, t["a_in"], pr)            # [3D, D]: rows q | k | v
+        dwqkv, dbqkv = self._wgrad(dqkv_act, t["a_in"], pr)            # [3D, D]: rows q | k | v
         for j, nm in enumerate(("query", "key", "value")):
             grads[f"{a}.mhsa.{nm}_layer.weight"] = dwqkv[j * D:(j + 1) * D]
             grads[f"{a}.mhsa.{nm}_layer.bias"] = dbqkv[j * D:(j + 1) * D]

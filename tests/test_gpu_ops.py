@@ -73,6 +73,8 @@ def test_gemm_exact_operands(ops, prec, M, N, K):
     ref = ops.unpack(aa, prec).double() @ ops.unpack(ww, prec).double().t() + bias.double()
     out, _ = ops.gemm(aa, ww, bias, prec)
     tol = 2e-6 if K <= 1024 else 2e-5      # tensor-core fp32 accumulation over long K is slightly lossier than an IEEE fp32 chain
+    if prec == "bf16x2":
+        tol *= 2                           # four partial products per element pair are accumulated
     assert rel_l2(out, ref) < tol, "plain"
     out2, out2a = ops.gemm(aa, ww, bias, prec, alpha=0.5, act=0, residual=res, want_act=True)
     ref2 = 0.5 * ref + res.double()
@@ -283,7 +285,8 @@ def test_relpos_attention(ops, prec, B, T, D, H, G):
         ref = _attention_reference(qkv, E, u, v, xl, H, G)
         assert out.shape == ref.shape
         err = rel_l2(ops.unpack(out, prec), ref)
-        assert err < (2e-3 if prec != "bf16" else 1e-2), (err, xl is None)      # bf16 path also rounds qu/qv, P and the output to bf16
+        bf16_core = prec == "bf16" or ops.attn_operand_precision(prec, D, H, G) != ops.PRECISIONS[prec]
+        assert err < (1e-2 if bf16_core else 2e-3), (err, xl is None)      # bf16 path also rounds qu/qv, P and the output to bf16
 
 
 def test_ctc_loss_and_greedy_on_device(golden_dir):

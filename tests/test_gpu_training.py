@@ -272,7 +272,10 @@ def test_train_step_graph_replay_equals_autograd_plus_torch_adam(prec):
         print("   moment rel-L2 %.2e / %.2e  update cosine %.4f  %s" % row)
     print(f"\n[{prec}] losses {results[True][0]} | autograd+torch.optim {losses_a} | moments rel-L2 {worst_m} / {worst_v}, "
           f"worst update cosine {worst_dir:.4f}")
-    assert worst_m[0] < 2e-3 and worst_v[0] < 2e-3, (worst_m, worst_v)
+    # bf16x2: the attention backward rounds its operands to bf16, which amplifies the round-off difference between the two Adam
+    # implementations on the attention parameters (5e-3 measured on mhsa.v; everything else < 1e-3)
+    gate = 1e-2 if prec == "bf16x2" else 2e-3
+    assert worst_m[0] < gate and worst_v[0] < gate, (worst_m, worst_v)
     assert worst_dir > 0.98, worst_dir
     for k in sd_a:
         if k.endswith("num_batches_tracked"):
