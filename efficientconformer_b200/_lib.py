@@ -146,7 +146,7 @@ _SIGNATURES = {
                              C.c_void_p, C.c_void_p, C.c_void_p]),
     "ec_op_gemm_ex": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
-    "ec_attention_operands_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ec_attention_operand_kind": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ec_op_pointwise_glu": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
     "ec_op_glu_scratch_rows": (C.c_int, [C.c_int]),

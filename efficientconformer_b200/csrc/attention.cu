@@ -354,7 +354,7 @@ static int launch_attn_t(const AttnDev& p, cudaStream_t stream) {
 }
 
 int launch_relpos_attention(int precision, const AttnArgs& a, cudaStream_t stream) {
-  if ((precision == EC_PREC_BF16 && !a.in_f32) || (precision == EC_PREC_BF16X2 && a.in_bf16)) {
+  if ((precision == EC_PREC_BF16 && !a.in_f32) || (precision == EC_PREC_BF16X2 && a.in_f16)) {
     bool launched = false;                           // TMA-staged kernel when the head layout fits its panel scheme
     EC_TRY(try_launch_relpos_attention_tma(a, stream, &launched));
     return launched ? EC_OK : launch_relpos_attention_bf16(a, stream);

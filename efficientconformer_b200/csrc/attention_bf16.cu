@@ -25,18 +25,32 @@ __device__ __forceinline__ void cp_async_b(uint32_t dst, const void* src, uint32
   else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all_b() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+// kHalf: fp16 operands (split mode: 11 significant bits at the same MMA rate), else bf16
+template <bool kHalf>
 __device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  if constexpr (kHalf)
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  else
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
+template <bool kHalf>
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
+  if constexpr (kHalf) { __half2 h = __floats2half2_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&h); }
+  else { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&h); }
+}
+template <bool kHalf>
+__device__ __forceinline__ float2 unpack16x2(uint32_t w) {
+  if constexpr (kHalf) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  else return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
 }
 
 constexpr int kBM = 64, kBN = 64, kBGW = 80, kBGStride = 81;
@@ -47,6 +61,7 @@ template <int KT, typename OutT>     // KT = k-tiles of 16 covering the head dim
 __global__ void __launch_bounds__(128, attn_ctas_per_sm(KT)) relpos_attn_bf16_kernel(const AttnDevB p) {
   constexpr int DP = KT * 16, STR = DP + 8;          // bf16 elements; row pitch 2*STR bytes keeps 32-bit fragment loads conflict-free
   constexpr int PR = DP / 2;                         // bf16 pairs per row
+  constexpr bool kHalf = IsSplit<OutT>::value;       // split mode: fp16 operands in, packed (hi, lo) pairs out
   extern __shared__ __align__(16) uint8_t smb[];
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smb);
   __nv_bfloat16* Es = Ks + kBN * STR;
@@ -142,9 +157,9 @@ __global__ void __launch_bounds__(128, attn_ctas_per_sm(KT)) relpos_attn_bf16_ke
       if (r < kBM) {
         uint32_t qu = 0, qv = 0;
         if (col_ok && i < Tg) {
-          const float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qraw[k]));
-          qu = pack_bf16(q.x + uu.x, q.y + uu.y);
-          qv = pack_bf16(q.x + vv.x, q.y + vv.y);
+          const float2 q = unpack16x2<kHalf>(qraw[k]);
+          qu = pack_bf16<kHalf>(q.x + uu.x, q.y + uu.y);
+          qv = pack_bf16<kHalf>(q.x + vv.x, q.y + vv.y);
         }
         *reinterpret_cast<uint32_t*>(Qu + r * STR + 2 * pr) = qu;
         *reinterpret_cast<uint32_t*>(Qv + r * STR + 2 * pr) = qv;
@@ -180,7 +195,7 @@ __global__ void __launch_bounds__(128, attn_ctas_per_sm(KT)) relpos_attn_bf16_ke
 #pragma unroll
         for (int n = 0; n < kBGW / 8; ++n) {
           const __nv_bfloat16* eb = Es + (eo + n * 8 + g) * STR + kt * 16 + 2 * t;
-          mma_bf16(acc[n], a0, a1, a2, a3, *reinterpret_cast<const uint32_t*>(eb), *reinterpret_cast<const uint32_t*>(eb + 8));
+          mma_bf16<kHalf>(acc[n], a0, a1, a2, a3, *reinterpret_cast<const uint32_t*>(eb), *reinterpret_cast<const uint32_t*>(eb + 8));
         }
       }
 #pragma unroll
@@ -200,7 +215,7 @@ __global__ void __launch_bounds__(128, attn_ctas_per_sm(KT)) relpos_attn_bf16_ke
 #pragma unroll
       for (int n = 0; n < kBN / 8; ++n) {
         const __nv_bfloat16* kb = Ks + (n * 8 + g) * STR + kt * 16 + 2 * t;
-        mma_bf16(s[n], a0, a1, a2, a3, *reinterpret_cast<const uint32_t*>(kb), *reinterpret_cast<const uint32_t*>(kb + 8));
+        mma_bf16<kHalf>(s[n], a0, a1, a2, a3, *reinterpret_cast<const uint32_t*>(kb), *reinterpret_cast<const uint32_t*>(kb + 8));
       }
     }
     __syncthreads();                                 // every warp is done with K and the E band
@@ -249,16 +264,16 @@ __global__ void __launch_bounds__(128, attn_ctas_per_sm(KT)) relpos_attn_bf16_ke
     // ---- O += P . V : P accumulators of two adjacent key n-tiles form one 16-key A fragment; V^T via ldmatrix.trans ----
 #pragma unroll
     for (int kt2 = 0; kt2 < kBN / 16; ++kt2) {
-      const uint32_t a0 = pack_bf16(s[2 * kt2][0], s[2 * kt2][1]), a1 = pack_bf16(s[2 * kt2][2], s[2 * kt2][3]);
-      const uint32_t a2 = pack_bf16(s[2 * kt2 + 1][0], s[2 * kt2 + 1][1]), a3 = pack_bf16(s[2 * kt2 + 1][2], s[2 * kt2 + 1][3]);
+      const uint32_t a0 = pack_bf16<kHalf>(s[2 * kt2][0], s[2 * kt2][1]), a1 = pack_bf16<kHalf>(s[2 * kt2][2], s[2 * kt2][3]);
+      const uint32_t a2 = pack_bf16<kHalf>(s[2 * kt2 + 1][0], s[2 * kt2 + 1][1]), a3 = pack_bf16<kHalf>(s[2 * kt2 + 1][2], s[2 * kt2 + 1][3]);
       const int mi = lane >> 3, rr = lane & 7;
       const __nv_bfloat16* vrow = Vs + (kt2 * 16 + (mi & 1) * 8 + rr) * STR + (mi >> 1) * 8;
 #pragma unroll
       for (int np = 0; np < KT; ++np) {            // pairs of 8-wide dim tiles
         uint32_t b0, b1, b2, b3;
         ldmatrix_x4_trans(smem_u32(vrow + np * 16), b0, b1, b2, b3);
-        mma_bf16(o[2 * np], a0, a1, a2, a3, b0, b1);
-        mma_bf16(o[2 * np + 1], a0, a1, a2, a3, b2, b3);
+        mma_bf16<kHalf>(o[2 * np], a0, a1, a2, a3, b0, b1);
+        mma_bf16<kHalf>(o[2 * np + 1], a0, a1, a2, a3, b2, b3);
       }
     }
   }
@@ -322,11 +337,11 @@ int launch_relpos_attention_bf16(const AttnArgs& a, cudaStream_t stream) {
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(p.d));
   const int kt = cdiv(p.d, 16);
   switch (kt) {
-    case 2: return a.in_bf16 ? launch_inst<2, SplitBf16>(p, stream) : launch_inst<2, __nv_bfloat16>(p, stream);
-    case 3: return a.in_bf16 ? launch_inst<3, SplitBf16>(p, stream) : launch_inst<3, __nv_bfloat16>(p, stream);
-    case 4: return a.in_bf16 ? launch_inst<4, SplitBf16>(p, stream) : launch_inst<4, __nv_bfloat16>(p, stream);
-    case 5: return a.in_bf16 ? launch_inst<5, SplitBf16>(p, stream) : launch_inst<5, __nv_bfloat16>(p, stream);
-    case 6: return a.in_bf16 ? launch_inst<6, SplitBf16>(p, stream) : launch_inst<6, __nv_bfloat16>(p, stream);
+    case 2: return a.in_f16 ? launch_inst<2, SplitBf16>(p, stream) : launch_inst<2, __nv_bfloat16>(p, stream);
+    case 3: return a.in_f16 ? launch_inst<3, SplitBf16>(p, stream) : launch_inst<3, __nv_bfloat16>(p, stream);
+    case 4: return a.in_f16 ? launch_inst<4, SplitBf16>(p, stream) : launch_inst<4, __nv_bfloat16>(p, stream);
+    case 5: return a.in_f16 ? launch_inst<5, SplitBf16>(p, stream) : launch_inst<5, __nv_bfloat16>(p, stream);
+    case 6: return a.in_f16 ? launch_inst<6, SplitBf16>(p, stream) : launch_inst<6, __nv_bfloat16>(p, stream);
     default: EC_FAIL("unsupported attention head dim " + std::to_string(p.d) + " for the bf16 kernel");
   }
 }

@@ -390,9 +390,12 @@ int launch_relpos_attention_bwd_tc(int precision, const AttnArgs& a, const float
   const long long sE = static_cast<long long>(p.R) * dp;
   const int H = a.H;
 
-  if (precision == EC_PREC_BF16X2 && !a.in_bf16) {
+  if (precision == EC_PREC_BF16X2 && !a.in_f16) {
     tc_pack_kernel<SplitBf16><<<egrid(static_cast<long long>(BH) * Tg * dp), 256, 0, st>>>(p);
     tc_pack_e_kernel<SplitBf16><<<egrid(static_cast<long long>(H) * p.R * dp), 256, 0, st>>>(p);
+  } else if (precision == EC_PREC_BF16X2) {          // fp16 q|k|v / E from the forward; the backward GEMMs run on bf16 copies
+    tc_pack_kernel<__half><<<egrid(static_cast<long long>(BH) * Tg * dp), 256, 0, st>>>(p);
+    tc_pack_e_kernel<__half><<<egrid(static_cast<long long>(H) * p.R * dp), 256, 0, st>>>(p);
   } else {
     tc_pack_kernel<bf16><<<egrid(static_cast<long long>(BH) * Tg * dp), 256, 0, st>>>(p);
     tc_pack_e_kernel<bf16><<<egrid(static_cast<long long>(H) * p.R * dp), 256, 0, st>>>(p);

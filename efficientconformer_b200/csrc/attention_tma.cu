@@ -33,18 +33,32 @@ struct AttnDevT {
   AttnPanels pan[8];
 };
 
+// kHalf: fp16 operands (split mode: 11 significant bits at the same MMA rate), else bf16
+template <bool kHalf>
 __device__ __forceinline__ void mma_bf16_t(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  if constexpr (kHalf)
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  else
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
+template <bool kHalf>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
+  if constexpr (kHalf) { __half2 h = __floats2half2_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&h); }
+  else { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&h); }
+}
+template <bool kHalf>
+__device__ __forceinline__ float2 unpack16x2(uint32_t w) {
+  if constexpr (kHalf) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  else return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
 }
 
 constexpr int kTM = 64, kTN = 64, kTGW = 80, kTGStride = 81;
@@ -58,6 +72,7 @@ template <int KT0, int KT1, typename OutT>     // k-tiles of 16 features in pane
 __global__ void __launch_bounds__(128, tma_attn_ctas(KT0 + KT1))
 relpos_attn_tma_kernel(const __grid_constant__ CUtensorMap tmKV0, const __grid_constant__ CUtensorMap tmKV1,
                        const __grid_constant__ CUtensorMap tmE0, const __grid_constant__ CUtensorMap tmE1, const AttnDevT p) {
+  constexpr bool kHalf = IsSplit<OutT>::value;       // split mode: fp16 operands in, packed (hi, lo) pairs out
   constexpr int KT = KT0 + KT1, DP = KT * 16, PR = DP / 2, STRQ = DP + 8;
   constexpr int kK0 = kTN * 128, kK1 = KT1 ? kTN * 64 : 0;               // panel bytes of a 64-key tile
   constexpr int kE0 = 128 * 128, kE1 = KT1 ? 128 * 64 : 0;
@@ -154,9 +169,9 @@ relpos_attn_tma_kernel(const __grid_constant__ CUtensorMap tmKV0, const __grid_c
         if (r < kTM) {
           uint32_t qu = 0, qv = 0;
           if (col_ok && i < Tg) {
-            const float2 q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qraw[k]));
-            qu = pack2(q.x + uu.x, q.y + uu.y);
-            qv = pack2(q.x + vv.x, q.y + vv.y);
+            const float2 q = unpack16x2<kHalf>(qraw[k]);
+            qu = pack2<kHalf>(q.x + uu.x, q.y + uu.y);
+            qv = pack2<kHalf>(q.x + vv.x, q.y + vv.y);
           }
           *reinterpret_cast<uint32_t*>(Qu + r * STRQ + 2 * pr) = qu;
           *reinterpret_cast<uint32_t*>(Qv + r * STRQ + 2 * pr) = qv;
@@ -206,7 +221,7 @@ relpos_attn_tma_kernel(const __grid_constant__ CUtensorMap tmKV0, const __grid_c
 #pragma unroll
         for (int n = 0; n < kTGW / 8; ++n) {
           const int row = eo + n * 8 + g;
-          mma_bf16_t(acc[n], a0, a1, a2, a3, frag(oE0, oE1, row, kt, 0), frag(oE0, oE1, row, kt, 1));
+          mma_bf16_t<kHalf>(acc[n], a0, a1, a2, a3, frag(oE0, oE1, row, kt, 0), frag(oE0, oE1, row, kt, 1));
         }
       }
 #pragma unroll
@@ -226,7 +241,7 @@ relpos_attn_tma_kernel(const __grid_constant__ CUtensorMap tmKV0, const __grid_c
 #pragma unroll
       for (int n = 0; n < kTN / 8; ++n) {
         const int row = n * 8 + g;
-        mma_bf16_t(s[n], a0, a1, a2, a3, frag(oK0, oK1, row, kt, 0), frag(oK0, oK1, row, kt, 1));
+        mma_bf16_t<kHalf>(s[n], a0, a1, a2, a3, frag(oK0, oK1, row, kt, 0), frag(oK0, oK1, row, kt, 1));
       }
     }
     __syncthreads();                                 // every warp is done with K and the E band (and has written its strip)
@@ -274,8 +289,8 @@ relpos_attn_tma_kernel(const __grid_constant__ CUtensorMap tmKV0, const __grid_c
     // ---- O += P . V : P accumulators of two adjacent key n-tiles form one 16-key A fragment; V^T via ldmatrix.trans ----
 #pragma unroll
     for (int kt2 = 0; kt2 < kTN / 16; ++kt2) {
-      const uint32_t a0 = pack2(s[2 * kt2][0], s[2 * kt2][1]), a1 = pack2(s[2 * kt2][2], s[2 * kt2][3]);
-      const uint32_t a2 = pack2(s[2 * kt2 + 1][0], s[2 * kt2 + 1][1]), a3 = pack2(s[2 * kt2 + 1][2], s[2 * kt2 + 1][3]);
+      const uint32_t a0 = pack2<kHalf>(s[2 * kt2][0], s[2 * kt2][1]), a1 = pack2<kHalf>(s[2 * kt2][2], s[2 * kt2][3]);
+      const uint32_t a2 = pack2<kHalf>(s[2 * kt2 + 1][0], s[2 * kt2 + 1][1]), a3 = pack2<kHalf>(s[2 * kt2 + 1][2], s[2 * kt2 + 1][3]);
       const int mi = lane >> 3, rr = lane & 7;
       const int row = kt2 * 16 + (mi & 1) * 8 + rr;  // key row this lane addresses; (mi >> 1) selects the upper 8 features
 #pragma unroll
@@ -283,8 +298,8 @@ relpos_attn_tma_kernel(const __grid_constant__ CUtensorMap tmKV0, const __grid_c
         uint32_t b0, b1, b2, b3;
         const uint32_t addr = np < KT0 ? base + oV0 + p0_off(row, 2 * np + (mi >> 1)) : base + oV1 + p1_off(row, 2 * (np - KT0) + (mi >> 1));
         ldsm_x4_trans(addr, b0, b1, b2, b3);
-        mma_bf16_t(o[2 * np], a0, a1, a2, a3, b0, b1);
-        mma_bf16_t(o[2 * np + 1], a0, a1, a2, a3, b2, b3);
+        mma_bf16_t<kHalf>(o[2 * np], a0, a1, a2, a3, b0, b1);
+        mma_bf16_t<kHalf>(o[2 * np + 1], a0, a1, a2, a3, b2, b3);
       }
     }
   }
@@ -400,10 +415,10 @@ int try_launch_relpos_attention_tma(const AttnArgs& a, cudaStream_t stream, bool
     kt1 = std::max(kt1, np == 2 ? cdiv(pc[1].shift + pc[1].n, 16) : 0);
   }
   int rc;
-  if (kt1 == 0 && kt0 <= 2) rc = a.in_bf16 ? launch_tma_inst<2, 0, SplitBf16>(a, p, stream) : launch_tma_inst<2, 0, __nv_bfloat16>(a, p, stream);
-  else if (kt1 == 0 && kt0 == 3) rc = a.in_bf16 ? launch_tma_inst<3, 0, SplitBf16>(a, p, stream) : launch_tma_inst<3, 0, __nv_bfloat16>(a, p, stream);
-  else if (kt1 == 0 && kt0 == 4) rc = a.in_bf16 ? launch_tma_inst<4, 0, SplitBf16>(a, p, stream) : launch_tma_inst<4, 0, __nv_bfloat16>(a, p, stream);
-  else if (kt0 <= 4 && kt1 <= 2) rc = a.in_bf16 ? launch_tma_inst<4, 2, SplitBf16>(a, p, stream) : launch_tma_inst<4, 2, __nv_bfloat16>(a, p, stream);
+  if (kt1 == 0 && kt0 <= 2) rc = a.in_f16 ? launch_tma_inst<2, 0, SplitBf16>(a, p, stream) : launch_tma_inst<2, 0, __nv_bfloat16>(a, p, stream);
+  else if (kt1 == 0 && kt0 == 3) rc = a.in_f16 ? launch_tma_inst<3, 0, SplitBf16>(a, p, stream) : launch_tma_inst<3, 0, __nv_bfloat16>(a, p, stream);
+  else if (kt1 == 0 && kt0 == 4) rc = a.in_f16 ? launch_tma_inst<4, 0, SplitBf16>(a, p, stream) : launch_tma_inst<4, 0, __nv_bfloat16>(a, p, stream);
+  else if (kt0 <= 4 && kt1 <= 2) rc = a.in_f16 ? launch_tma_inst<4, 2, SplitBf16>(a, p, stream) : launch_tma_inst<4, 2, __nv_bfloat16>(a, p, stream);
   else return EC_OK;
   *launched = rc == EC_OK;
   return rc;

@@ -7,6 +7,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "ec_ptx.cuh"
 #include "../../include/effconf_b200.h"
 
@@ -105,6 +106,13 @@ template <> struct ActTraits<SplitBf16> {
   __device__ static float word(float x) { return __uint_as_float(split_pack(x)); }
   __device__ static float from(SplitBf16 x) { return split_unpack(x.bits); }
 };
+// fp16: the q|k|v / E operands of the attention core in split mode (11 significant bits = TF32 grade at the bf16 MMA rate; the values
+// are O(1) activations, far inside the fp16 range)
+template <> struct ActTraits<__half> {
+  static constexpr bool kTf32 = false;
+  __device__ static __half to(float x) { return __float2half_rn(x); }
+  __device__ static float from(__half x) { return __half2float(x); }
+};
 template <typename T> struct IsSplit { static constexpr bool value = false; };
 template <> struct IsSplit<SplitBf16> { static constexpr bool value = true; };
 // bytes of one activation element / factor of the weight operand ([2, N, K] in split mode)
@@ -160,7 +168,7 @@ struct GemmArgs {
   const float* residual; int ld_res;   // fp32 [M, *] or nullptr
   float* out_f32; int ld_out;          // optional fp32 output
   void* out_act; int ld_act;           // optional activation-type output (rounded)
-  int act_bf16;                        // split mode only: out_act is written as PLAIN bf16 (q|k|v and E feed the bf16 attention kernels)
+  int act_f16;                         // split mode only: out_act is written as PLAIN fp16 (q|k|v and E feed the 16-bit attention kernels)
   int round_out;                       // round the fp32 output to TF32 (feeds the TF32 mma.sync attention)
   // fused LayerNorm epilogue (N <= 256, plain epilogue): mode 1: ln_out = LN1(out); mode 2: out <- LN1(out), ln_out = LN2(out)
   // (LN2 = identity copy when ln2_g == nullptr).  copy_out: activation-type copy of every copy_stride-th frame of `out` (mode 1).
@@ -206,11 +214,11 @@ struct AttnArgs {
   int B, T, D, H, G;
   void* out; int ld_out; // [B*T, D] activation type
   int in_f32;            // EC_PREC_BF16 only: q|k|v / E are fp32 (odd head dims fall back to the TF32 kernel with bf16 output)
-  int in_bf16;           // EC_PREC_BF16X2 only: q|k|v / E are plain bf16 (attn_operands_bf16(): the bf16 kernels apply), output packed
+  int in_f16;            // EC_PREC_BF16X2 only: q|k|v / E are plain fp16 (attn_operands_f16(): the 16-bit kernels apply), output packed
 };
-// Split mode: the attention core runs on bf16 q|k|v / E (its contribution to the logits error stays ~2e-4, measured) whenever the
-// bf16 kernels support the head layout; other layouts keep packed operands and the TF32 kernel.
-inline bool attn_operands_bf16(int D, int H, int G) { return D % 8 == 0 && ((G * D) / H) % 2 == 0; }
+// Split mode: the attention core runs the 16-bit mma.sync kernels on FP16 q|k|v / E / P (11 significant bits: TF32-grade accuracy at
+// the bf16 rate) whenever those kernels support the head layout; other layouts keep packed operands and the TF32 kernel.
+inline bool attn_operands_f16(int D, int H, int G) { return D % 8 == 0 && ((G * D) / H) % 2 == 0; }
 int launch_relpos_attention(int precision, const AttnArgs& a, cudaStream_t stream);
 int launch_relpos_attention_bf16(const AttnArgs& a, cudaStream_t stream);
 int try_launch_relpos_attention_tma(const AttnArgs& a, cudaStream_t stream, bool* launched);

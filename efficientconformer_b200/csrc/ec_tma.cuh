@@ -3,6 +3,7 @@
 #pragma once
 #include "ec_common.cuh"
 #include <mutex>
+#include <type_traits>
 
 namespace ec {
 
@@ -79,6 +80,16 @@ __device__ __forceinline__ void slab_store_act(uint8_t* slab, int row, const flo
 #pragma unroll
     for (int j = 0; j < 32; ++j) r[j] = round_tf32(t[j]);
     slab_store_f32(slab, row, r);
+  } else if constexpr (sizeof(T) == 2 && !std::is_same<T, __nv_bfloat16>::value) {     // fp16
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+      uint4 pk;
+      __half2 h0 = __floats2half2_rn(t[8 * j8], t[8 * j8 + 1]), h1 = __floats2half2_rn(t[8 * j8 + 2], t[8 * j8 + 3]);
+      __half2 h2 = __floats2half2_rn(t[8 * j8 + 4], t[8 * j8 + 5]), h3 = __floats2half2_rn(t[8 * j8 + 6], t[8 * j8 + 7]);
+      pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(slab + slab_b16_off(row, j8)) = pk;
+    }
   } else {
 #pragma unroll
     for (int j8 = 0; j8 < 4; ++j8) {

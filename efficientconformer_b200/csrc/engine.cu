@@ -221,9 +221,9 @@ struct LnFuse {            // optional fused LayerNorm epilogue of a GEMM
 };
 static int gemm(ec_engine* e, cudaStream_t st, int cat, const void* A, const void* W, int M, int N, int K, const float* bias, float alpha,
                 int act, const float* residual, float* out_f32, void* out_act, int glu_nb = 0, int glu_channels = 0,
-                const LnFuse* ln = nullptr, int round_out = 0, int act_bf16 = 0) {
+                const LnFuse* ln = nullptr, int round_out = 0, int act_f16 = 0) {
   GemmArgs g{};
-  g.round_out = round_out; g.act_bf16 = act_bf16;
+  g.round_out = round_out; g.act_f16 = act_f16;
   if (ln != nullptr && ln->mode != 0) {
     g.ln_mode = ln->mode; g.ln1_g = ln->g1; g.ln1_b = ln->b1; g.ln2_g = ln->g2; g.ln2_b = ln->b2; g.ln_eps = 1e-6f; g.ln_out = ln->y;
     g.copy_out = ln->copy_out; g.copy_stride = ln->copy_stride; g.frames_per_seq = ln->fps; g.frames_out_per_seq = ln->fops;
@@ -447,9 +447,9 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
     float* eb = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws.ebuf) + i * ws.e_stride);
     // activation-type (bf16 / packed) E straight from the epilogue, else TF32-rounded fp32
     const bool a16 = prec == EC_PREC_BF16X2 || (prec == EC_PREC_BF16 && ((G * D) / bc.num_heads) % 2 == 0 && D % 2 == 0);
-    const int ab16 = (prec == EC_PREC_BF16X2 && attn_operands_bf16(D, bc.num_heads, G)) ? 1 : 0;      // split mode: plain bf16 E
+    const int af16 = (prec == EC_PREC_BF16X2 && attn_operands_f16(D, bc.num_heads, G)) ? 1 : 0;      // split mode: plain bf16 E
     EC_TRY(gemm(e, e->side, PC_POS, relpos[i], w.blk[i].wpos, e_rows, D, D, w.blk[i].bpos, 1.f, GEMM_ACT_NONE, nullptr, a16 ? nullptr : eb,
-                a16 ? eb : nullptr, 0, 0, nullptr, 1, ab16));
+                a16 ? eb : nullptr, 0, 0, nullptr, 1, af16));
   }
   EC_CUDA(cudaEventRecord(e->ev_join, e->side));
   bool joined = false;
@@ -522,13 +522,13 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
     // MHSA: x2 = x1 + Wo attn(LN(x1)); also emits xn = LN_conv(x2) and the strided copy xs (conv_res operand)
     // q|k|v and E feed the attention kernel: TF32-rounded fp32 in parity mode, bf16 in fast mode
     const bool a16 = prec == EC_PREC_BF16X2 || (prec == EC_PREC_BF16 && ((bc.group_size * D) / bc.num_heads) % 2 == 0 && D % 2 == 0);
-    const int ab16 = (prec == EC_PREC_BF16X2 && attn_operands_bf16(D, bc.num_heads, bc.group_size)) ? 1 : 0;   // split mode: plain bf16 q|k|v
-    EC_TRY(gemm(e, st, PC_QKV, ws.xn, b.wqkv, M, 3 * D, D, b.bqkv, 1.f, GEMM_ACT_NONE, nullptr, a16 ? nullptr : ws.qkv, a16 ? ws.qkv : nullptr, 0, 0, nullptr, 1, ab16));
+    const int af16 = (prec == EC_PREC_BF16X2 && attn_operands_f16(D, bc.num_heads, bc.group_size)) ? 1 : 0;   // split mode: plain bf16 q|k|v
+    EC_TRY(gemm(e, st, PC_QKV, ws.xn, b.wqkv, M, 3 * D, D, b.bqkv, 1.f, GEMM_ACT_NONE, nullptr, a16 ? nullptr : ws.qkv, a16 ? ws.qkv : nullptr, 0, 0, nullptr, 1, af16));
     const int G = bc.group_size, P = (G - T % G) % G, e_rows = 2 * (T + P) - G;
     if (!joined) { EC_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0)); joined = true; }     // join: E_i of every block is ready
     {
       const float* eb = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(ws.ebuf) + i * ws.e_stride);
-      AttnArgs aa{ws.qkv, eb, b.u, b.v, lens, B, T, D, bc.num_heads, G, ws.o, D, (prec == EC_PREC_BF16 && !a16) ? 1 : 0, ab16};
+      AttnArgs aa{ws.qkv, eb, b.u, b.v, lens, B, T, D, bc.num_heads, G, ws.o, D, (prec == EC_PREC_BF16 && !a16) ? 1 : 0, af16};
       const double Tg = static_cast<double>(T + P) / G, dh = static_cast<double>(G) * D / bc.num_heads;
       ProfScope ps(e, st, PC_ATTN, B * bc.num_heads * (4.0 * Tg * Tg * dh + 2.0 * Tg * (2 * Tg - 1) * dh),
                    4.0 * M * 3 * D + 4.0 * e_rows * D + es * M * D);
@@ -702,7 +702,7 @@ int ec_op_relpos_attention_bwd(int precision, const void* qkv, const void* E, co
                                int t, int dim, int heads, int group, const float* d_out, float* dqkv, float* dE, float* du, float* dv,
                                void* work, void* stream) {
   AttnArgs a{qkv, E, u, v, x_len, batch, t, dim, heads, group, nullptr, dim, 0,
-             (precision == EC_PREC_BF16X2 && attn_operands_bf16(dim, heads, group)) ? 1 : 0};
+             (precision == EC_PREC_BF16X2 && attn_operands_f16(dim, heads, group)) ? 1 : 0};
   return launch_relpos_attention_bwd(precision, a, d_out, dqkv, dE, du, dv, work, reinterpret_cast<cudaStream_t>(stream));
 }
 size_t ec_op_conv_train_work_bytes(int channels, int k) { return conv_train_work_bytes(channels, k); }
@@ -781,11 +781,11 @@ int ec_op_gemm_ex(int precision, const void* A, const void* W, int M, int N, int
   GemmArgs g{};
   g.A = A; g.W = W; g.M = M; g.N = N; g.K = K; g.bias = bias; g.alpha = alpha; g.act = act;
   g.residual = residual; g.ld_res = N; g.out_f32 = out_f32; g.ld_out = N; g.out_act = out_act; g.ld_act = N;
-  g.act_bf16 = (flags & 1) ? 1 : 0;
+  g.act_f16 = (flags & 1) ? 1 : 0;
   return launch_gemm(precision, g, reinterpret_cast<cudaStream_t>(stream));
 }
-int ec_attention_operands_bf16(int precision, int dim, int heads, int group) {
-  return precision == EC_PREC_BF16 ? 1 : (precision == EC_PREC_BF16X2 && attn_operands_bf16(dim, heads, group)) ? 1 : 0;
+int ec_attention_operand_kind(int precision, int dim, int heads, int group) {
+  return precision == EC_PREC_BF16 ? 1 : (precision == EC_PREC_BF16X2 && attn_operands_f16(dim, heads, group)) ? 2 : 0;
 }
 int ec_op_gemm_ln(int precision, const void* A, const void* W, int M, int N, int K, const float* bias, float alpha, const float* residual,
                   float* out_f32, int ln_mode, const float* g1, const float* b1, const float* g2, const float* b2, float eps, void* ln_out,
@@ -824,7 +824,7 @@ int ec_op_fold_bn(const float* w, const float* b, const float* g, const float* b
 int ec_op_relpos_attention(int precision, const void* qkv, const void* E, const float* u, const float* v, const int32_t* x_len,
                            int batch, int t, int dim, int heads, int group, void* out, void* stream) {
   AttnArgs a{qkv, E, u, v, x_len, batch, t, dim, heads, group, out, dim, 0,
-             (precision == EC_PREC_BF16X2 && attn_operands_bf16(dim, heads, group)) ? 1 : 0};
+             (precision == EC_PREC_BF16X2 && attn_operands_f16(dim, heads, group)) ? 1 : 0};
   return launch_relpos_attention(precision, a, reinterpret_cast<cudaStream_t>(stream));
 }
 int ec_op_dwconv_bn_swish(int precision, const void* x, const float* w_folded, const float* b_folded, int batch, int t, int channels,

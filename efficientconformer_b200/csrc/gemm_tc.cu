@@ -43,7 +43,7 @@ struct GemmDev {
   int glu_nb, glu_channels;
   int has_res, has_out_f32, has_out_act;
   int round_out;     // round the fp32 output to TF32 (it feeds a TF32 mma.sync consumer)
-  int act_bf16;      // split mode: the activation-type output is plain bf16 (64-byte slab rows)
+  int act_f16;       // split mode: the activation-type output is plain fp16 (64-byte slab rows)
   // fused LayerNorm (kLN instantiation only; requires a single N tile)
   int ln_mode;       // 1: y = LN1(out);  2: out <- LN1(out), y = LN2(out) (plain copy when ln2_g == nullptr)
   const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
@@ -297,7 +297,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* sa = slabA + buf * kASlab;
         if (p.has_out_f32) slab_store_f32(sf, lane, t);
         if (p.has_out_act) {
-          if (kSplit && p.act_bf16) slab_store_act<__nv_bfloat16>(sa, lane, t);
+          if (kSplit && p.act_f16) slab_store_act<__half>(sa, lane, t);
           else slab_store_act<T>(sa, lane, t);
         }
         if (!batch) {
@@ -524,8 +524,8 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   p.bias = a.bias; p.alpha = a.alpha; p.act = a.act;
   p.glu_nb = a.glu_nb; p.glu_channels = a.glu_channels;
   p.round_out = a.round_out;
-  p.act_bf16 = (IsSplit<T>::value && a.act_bf16) ? 1 : 0;
-  EC_REQUIRE(!a.act_bf16 || (IsSplit<T>::value && !kLN), "act_bf16 is an option of the plain split-mode GEMM");
+  p.act_f16 = (IsSplit<T>::value && a.act_f16) ? 1 : 0;
+  EC_REQUIRE(!a.act_f16 || (IsSplit<T>::value && !kLN), "act_f16 is an option of the plain split-mode GEMM");
   p.dbg = g_timeline_enabled;
   EC_REQUIRE(a.out_f32 != nullptr || a.out_act != nullptr, "GEMM needs at least one output");
   EC_REQUIRE(a.glu_nb == 0 || a.bias != nullptr, "GLU GEMM needs a bias");
@@ -554,7 +554,7 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   tmRes = tmA; tmOutF = tmA; tmOutA = tmA; tmLn = tmA;       // placeholders for unused maps
   if (a.residual != nullptr) EC_TRY(make_slab_map(&tmRes, true, a.residual, a.M, out_cols, a.ld_res));
   if (a.out_f32 != nullptr) EC_TRY(make_slab_map(&tmOutF, true, a.out_f32, a.M, out_cols, a.ld_out));
-  if (a.out_act != nullptr) EC_TRY(make_slab_map(&tmOutA, act_f32 && !p.act_bf16, a.out_act, a.M, out_cols, a.ld_act));
+  if (a.out_act != nullptr) EC_TRY(make_slab_map(&tmOutA, act_f32 && !p.act_f16, a.out_act, a.M, out_cols, a.ld_act));
   if (kLN && a.ln_out != nullptr) EC_TRY(make_slab_map(&tmLn, act_f32, a.ln_out, a.M, a.N, a.N));
 
   if (!kLN) {

@@ -51,26 +51,35 @@ def layernorm(x, gamma, beta, precision, eps=1e-6, want_f32=True, want_act=True)
     return ya, yf
 
 
-def attn_operand_precision(precision, dim, heads, group):
-    """Precision id of the q|k|v / E operands of the attention core: the activation type, except in split mode where they are plain
-    bf16 whenever the bf16 attention kernels support the head layout (ec_attention_operands_bf16)."""
-    pr = _p(precision)
-    if pr == PREC_BF16X2 and lib().ec_attention_operands_bf16(pr, dim, heads, group):
-        return PRECISIONS["bf16"]
-    return pr
+def attn_operands_f16(precision, dim, heads, group):
+    """True when the q|k|v / E operands of the attention core are plain fp16 tensors: split mode with a head layout the 16-bit
+    attention kernels support (ec_attention_operand_kind == 2); otherwise they are in the activation type."""
+    return lib().ec_attention_operand_kind(_p(precision), dim, heads, group) == 2
 
 
-def gemm(a_act, w_act, bias, precision, alpha=1.0, act=0, residual=None, want_f32=True, want_act=False, act_bf16=False):
+def cast_attn_operand(x, precision, dim, heads, group):
+    """fp32 -> the storage the attention entry points expect for q|k|v / E in this mode (tests)."""
+    if attn_operands_f16(precision, dim, heads, group):
+        return x.float().to(torch.float16).contiguous()
+    return cast(x, precision)
+
+
+def attn_operand_values(x, precision):
+    """fp32 values of an attention operand tensor (tests)."""
+    return x.float() if x.dtype == torch.float16 else unpack(x, precision)
+
+
+def gemm(a_act, w_act, bias, precision, alpha=1.0, act=0, residual=None, want_f32=True, want_act=False, act_f16=False):
     """a_act [M,K] in the activation type, w_act [N,K] a weight operand (cast_weight / transpose_cast).
-    act_bf16 (split mode): the activation-type output is plain bf16 (attention operands)."""
+    act_f16 (split mode): the activation-type output is plain fp16 (attention operands)."""
     pr = _p(precision)
     M, K = a_act.shape
     N = w_act.shape[0]
-    act_bf16 = bool(act_bf16) and pr == PREC_BF16X2
+    act_f16 = bool(act_f16) and pr == PREC_BF16X2
     of = torch.empty(M, N, dtype=torch.float32, device=a_act.device) if want_f32 else None
-    oa = torch.empty(M, N, dtype=torch.bfloat16 if act_bf16 else act_dtype(pr), device=a_act.device) if want_act else None
+    oa = torch.empty(M, N, dtype=torch.float16 if act_f16 else act_dtype(pr), device=a_act.device) if want_act else None
     check(lib().ec_op_gemm_ex(pr, ptr(a_act), ptr(w_act), M, N, K, ptr(bias), alpha, act, ptr(residual), ptr(of), ptr(oa),
-                              1 if act_bf16 else 0, stream_ptr()))
+                              1 if act_f16 else 0, stream_ptr()))
     return of, oa
 
 
@@ -138,8 +147,7 @@ def relpos_attention(qkv, E, u, v, x_len, heads, group, precision):
     D = D3 // 3
     out = torch.empty(B, T, D, dtype=act_dtype(pr), device=qkv.device)
     xl = x_len.to(torch.int32).contiguous() if x_len is not None else None
-    opr = attn_operand_precision(pr, D, heads, group)
-    qkv, E = cast(qkv, opr), cast(E, opr)
+    qkv, E = cast_attn_operand(qkv, pr, D, heads, group), cast_attn_operand(E, pr, D, heads, group)
     check(lib().ec_op_relpos_attention(pr, ptr(qkv), ptr(E), ptr(u.float().contiguous()),
                                        ptr(v.float().contiguous()), ptr(xl), B, T, D, heads, group, ptr(out), stream_ptr()))
     return out

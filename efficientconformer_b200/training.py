@@ -247,12 +247,12 @@ class TrainingPath:
         m = blk.multi_head_self_attention_module
         a_in = o.layernorm(x1, m.norm.weight, m.norm.bias, pr, want_f32=False, want_act=True)[0]
         wqkv, bqkv, qkv_handle = self._qkv(m.mhsa, pr)
-        ab16 = o.attn_operand_precision(pr, D, H, G) != pr           # split mode: plain bf16 q|k|v and E for the attention core
-        qkv = o.gemm(a_in, wqkv, bqkv, pr, want_f32=False, want_act=True, act_bf16=ab16)[1]
+        ab16 = o.attn_operands_f16(pr, D, H, G)                      # split mode: plain fp16 q|k|v and E for the attention core
+        qkv = o.gemm(a_in, wqkv, bqkv, pr, want_f32=False, want_act=True, act_f16=ab16)[1]
         t_pad = T + (-T) % G
         R = self._table(t_pad, spec, pr, x.device)
         wpos = self._w(m.mhsa.pos_layer.weight, pr)
-        E = o.gemm(R, wpos, m.mhsa.pos_layer.bias, pr, want_f32=False, want_act=True, act_bf16=ab16)[1]
+        E = o.gemm(R, wpos, m.mhsa.pos_layer.bias, pr, want_f32=False, want_act=True, act_f16=ab16)[1]
         att = o.relpos_attention_act(qkv.view(B, T, 3 * D), E, m.mhsa.u, m.mhsa.v, cur_len, H, G, pr)
         wo = self._w(m.mhsa.output_layer.weight, pr)
         s_att = drop.next_site()

@@ -274,12 +274,13 @@ int ec_op_layernorm(int precision, const float* x, int rows, int dim, const floa
 /* out = alpha * act(A @ W^T + bias) + residual.  A [M,K], W [N,K] in the activation type (use ec_op_cast).  act: 0 none, 1 swish. */
 int ec_op_gemm(int precision, const void* A, const void* W, int M, int N, int K, const float* bias, float alpha, int act,
                const float* residual, float* out_f32, void* out_act, void* stream);
-/* flags bit 0 (EC_PREC_BF16X2 only): out_act is written as PLAIN bf16 -- the q|k|v and E operands of the attention core in split mode */
+/* flags bit 0 (EC_PREC_BF16X2 only): out_act is written as PLAIN fp16 -- the q|k|v and E operands of the attention core in split mode */
 int ec_op_gemm_ex(int precision, const void* A, const void* W, int M, int N, int K, const float* bias, float alpha, int act,
                   const float* residual, float* out_f32, void* out_act, int flags, void* stream);
-/* 1 when ec_op_relpos_attention / _bwd read q|k|v and E as plain bf16 in this mode and head layout (EC_PREC_BF16: always for the
- * activation-type entry points; EC_PREC_BF16X2: when dim % 8 == 0 and the head dim G*dim/heads is even), 0: activation type */
-int ec_attention_operands_bf16(int precision, int dim, int heads, int group);
+/* Storage of the q|k|v and E operands that ec_op_relpos_attention / _bwd read in this mode and head layout: 0 = the activation type,
+ * 1 = bf16 (EC_PREC_BF16), 2 = fp16 (EC_PREC_BF16X2 when dim % 8 == 0 and the head dim G*dim/heads is even: the 16-bit mma.sync kernels
+ * then run on fp16 operands -- 11 significant bits, TF32-grade accuracy at the bf16 rate -- and write the packed output). */
+int ec_attention_operand_kind(int precision, int dim, int heads, int group);
 /* GEMM + fused LayerNorm epilogue (N <= 256): out_f32 = alpha*(A W^T + bias) + residual;
  * ln_mode 1: ln_out = LN(out; g1,b1) (activation type), optional copy_out = activation-type copy of every copy_stride-th frame of out;
  * ln_mode 2: out_f32 <- LN(out; g1,b1) in place, ln_out = LN(out_f32; g2,b2), or a plain activation-type copy when g2 == NULL. */
@@ -302,7 +303,7 @@ int ec_op_glu_scratch_rows(int channels);
 int ec_op_fold_bn(const float* w, const float* b, const float* g, const float* beta, const float* rm, const float* rv, float eps,
                   int C, int taps, float* w_out, float* b_out, void* stream);
 /* qkv [B*T, 3D] and E [2Tp-G, D]: fp32 already rounded to TF32 for EC_PREC_TF32, bf16 for EC_PREC_BF16 (what the QKV / pos GEMM epilogues
- * emit); EC_PREC_BF16X2: plain bf16 when ec_attention_operands_bf16() says so (ec_op_gemm_ex flag), packed pairs otherwise; out packed */
+ * emit); EC_PREC_BF16X2: plain fp16 when ec_attention_operand_kind() == 2 (ec_op_gemm_ex flag), packed pairs otherwise; out packed */
 int ec_op_relpos_attention(int precision, const void* qkv, const void* E, const float* u, const float* v,
                            const int32_t* x_len, int batch, int t, int dim, int heads, int group, void* out, void* stream);
 int ec_op_dwconv_bn_swish(int precision, const void* x, const float* w_folded, const float* b_folded, int batch, int t,

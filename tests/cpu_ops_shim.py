@@ -30,11 +30,11 @@ def layernorm(x, gamma, beta, precision, eps=1e-6, want_f32=True, want_act=True)
     return (y.clone() if want_act else None), (y if want_f32 else None)
 
 
-def attn_operand_precision(precision, dim, heads, group):
-    return precision
+def attn_operands_f16(precision, dim, heads, group):
+    return False
 
 
-def gemm(a_act, w_act, bias, precision, alpha=1.0, act=0, residual=None, want_f32=True, want_act=False, act_bf16=False):
+def gemm(a_act, w_act, bias, precision, alpha=1.0, act=0, residual=None, want_f32=True, want_act=False, act_f16=False):
     y = _d(a_act) @ _d(w_act).t()
     if bias is not None:
         y = y + _d(bias)

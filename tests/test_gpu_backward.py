@@ -222,15 +222,15 @@ def test_relpos_attention_backward(ops, prec):
         if prec == "bf16" and D % 8:
             continue
         g = torch.Generator().manual_seed(1500 + trial)
-        oprec = ops.attn_operand_precision(prec, D, H, G)       # split mode: plain bf16 operands where the bf16 kernels apply
-        qkv = ops.cast(torch.randn(B, T, 3 * D, generator=g).to(DEV), oprec)
+        # split mode: plain fp16 operands where the 16-bit kernels apply
+        qkv = ops.cast_attn_operand(torch.randn(B, T, 3 * D, generator=g).to(DEV), prec, D, H, G)
         Tp = T + (-T) % G
-        E = ops.cast(torch.randn(2 * Tp - G, D, generator=g).to(DEV), oprec)
+        E = ops.cast_attn_operand(torch.randn(2 * Tp - G, D, generator=g).to(DEV), prec, D, H, G)
         u, v = 0.3 * torch.randn(D, generator=g), 0.3 * torch.randn(D, generator=g)
         x_len = torch.tensor([rng.randint(1, T) for _ in range(B)])
         x_len[0] = T
         d_out = torch.randn(B, T, D, generator=g)
-        qr, Er = ops.unpack(qkv, oprec).double().cpu().requires_grad_(True), ops.unpack(E, oprec).double().cpu().requires_grad_(True)
+        qr, Er = ops.attn_operand_values(qkv, prec).double().cpu().requires_grad_(True), ops.attn_operand_values(E, prec).double().cpu().requires_grad_(True)
         ur, vr = u.double().requires_grad_(True), v.double().requires_grad_(True)
         _attention_reference(qr, Er, ur, vr, x_len, H, G).backward(d_out.double())
         dqkv, dE, du, dv = ops.relpos_attention_bwd(qkv, E, u.to(DEV), v.to(DEV), x_len.to(DEV), H, G, d_out.to(DEV), prec)
