@@ -160,3 +160,19 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert d["higher_is_better"] is True and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
         assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
         assert "workload" in d["config"] and d["steps"] == 1
+
+
+def test_bench_both_arms_describe_the_same_config():
+    """The driver compares the `config` objects of the two arms: for the same flags they must be identical."""
+    import argparse
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for mode in ("train", "forward"):
+        for n in (1, 8):
+            a = argparse.Namespace(config="EfficientConformerCTCSmall", batch=32, frames=1000, gpus=n, pdrop=0.1)
+            c1, c2 = bench.workload_config(a, mode), bench.workload_config(argparse.Namespace(**vars(a)), mode)
+            assert c1 == c2 and c1["global_batch"] == 32 * n and c1["frames"] == 1000 and "workload" in c1
+    assert abs(bench.flops_per_frame(*bench.SHIPPED_ENCODER_PARAMS["EfficientConformerCTCSmall"], 1000, 32) / 1e6 - 6.616) < 1e-3   # SURVEY.md 8(d)
+    assert abs(bench.flops_per_frame(*bench.SHIPPED_ENCODER_PARAMS["ConformerCTCLarge"], 4000, 8) / 1e6 - 99.888) < 1e-2
