@@ -401,10 +401,17 @@ int launch_relpos_attention_bwd_tc(int precision, const AttnArgs& a, const float
     tc_pack_e_kernel<bf16><<<egrid(static_cast<long long>(H) * p.R * dp), 256, 0, st>>>(p);
   }
   EC_CUDA(cudaGetLastError());
+  // Independent launches run as parallel branches (library-owned side streams, event fork / join: capturable); the critical path is
+  // pack -> max(S1, Rel, dP) -> rows -> max(dV, dK, dQu, dQv) -> unpack, the parameter-gradient tail (dE, du, dv) runs beside it.
+  SideStreams& ss = side_streams();
+  const bool par = side_streams_enabled() && ss.init();
+  cudaStream_t s1 = par ? ss.s[0] : st, s2 = par ? ss.s[1] : st, s3 = par ? ss.s[2] : st;
   // S1 = Qu K^T, Rel = Qv Eh^T, dP = dO V^T
-  EC_TRY((run_gemm<false, false>(BGemm{p.Qu, p.Kd, p.S1, Tg, Tg, dp, dp, dp, p.Tp, sD * H, sD, sD * H, sD, sS * H, sS, H, 0}, BH, st)));
+  if (par) EC_REQUIRE(ss.fork(st, 2), "side-stream fork failed");
   EC_TRY((run_gemm<false, false>(BGemm{p.Qv, p.Eh, p.Rel, Tg, p.R, dp, dp, dp, p.Rp, sD * H, sD, 0, sE, sR * H, sR, H, 0}, BH, st)));
-  EC_TRY((run_gemm<false, false>(BGemm{p.dOd, p.Vd, p.dP, Tg, Tg, dp, dp, dp, p.Tp, sD * H, sD, sD * H, sD, sS * H, sS, H, 0}, BH, st)));
+  EC_TRY((run_gemm<false, false>(BGemm{p.Qu, p.Kd, p.S1, Tg, Tg, dp, dp, dp, p.Tp, sD * H, sD, sD * H, sD, sS * H, sS, H, 0}, BH, s1)));
+  EC_TRY((run_gemm<false, false>(BGemm{p.dOd, p.Vd, p.dP, Tg, Tg, dp, dp, dp, p.Tp, sD * H, sD, sD * H, sD, sS * H, sS, H, 0}, BH, s2)));
+  if (par) EC_REQUIRE(ss.join(st, 2), "side-stream join failed");
   const long long rows = static_cast<long long>(BH) * Tg;
   const int rgrid = static_cast<int>((rows + 7) / 8);
   if (Tg <= 128) tc_rows_kernel<4><<<rgrid, 256, 0, st>>>(p);
@@ -412,22 +419,33 @@ int launch_relpos_attention_bwd_tc(int precision, const AttnArgs& a, const float
   else if (Tg <= 512) tc_rows_kernel<16><<<rgrid, 256, 0, st>>>(p);
   else tc_rows_kernel<32><<<rgrid, 256, 0, st>>>(p);
   EC_CUDA(cudaGetLastError());
-  // dV = P^T dO, dK = dS^T Qu  (contraction over the query rows: A stored [K = i, M = j])
-  EC_TRY((run_gemm<true, true>(BGemm{p.P, p.dOd, p.dV, Tg, dp, Tg, p.Tp, dp, dp, sS * H, sS, sD * H, sD, sD * H, sD, H, 0}, BH, st)));
-  EC_TRY((run_gemm<true, true>(BGemm{p.dS, p.Qu, p.dK, Tg, dp, Tg, p.Tp, dp, dp, sS * H, sS, sD * H, sD, sD * H, sD, H, 0}, BH, st)));
-  // dQu = dS K, dQv = dRel Eh
-  EC_TRY((run_gemm<false, true>(BGemm{p.dS, p.Kd, p.dQu, Tg, dp, Tg, p.Tp, dp, dp, sS * H, sS, sD * H, sD, sD * H, sD, H, 0}, BH, st)));
+  if (par) EC_REQUIRE(ss.fork(st, 3), "side-stream fork failed");
+  // dQv = dRel Eh (longest contraction: R) on the caller's stream; dV = P^T dO, dK = dS^T Qu (contraction over the query rows: A stored
+  // [K = i, M = j]) and dQu = dS K beside it
   EC_TRY((run_gemm<false, true>(BGemm{p.dRel, p.Eh, p.dQv, Tg, dp, p.R, p.Rp, dp, dp, sR * H, sR, 0, sE, sD * H, sD, H, 0}, BH, st)));
-  // dE_b = dRel^T Qv  (per (b, h) partials, reduced over b below)
-  EC_TRY((run_gemm<true, true>(BGemm{p.dRel, p.Qv, p.dEp, p.R, dp, Tg, p.Rp, dp, dp, sR * H, sR, sD * H, sD, sE * H, sE, H, 0}, BH, st)));
+  EC_TRY((run_gemm<true, true>(BGemm{p.P, p.dOd, p.dV, Tg, dp, Tg, p.Tp, dp, dp, sS * H, sS, sD * H, sD, sD * H, sD, H, 0}, BH, s1)));
+  EC_TRY((run_gemm<true, true>(BGemm{p.dS, p.Qu, p.dK, Tg, dp, Tg, p.Tp, dp, dp, sS * H, sS, sD * H, sD, sD * H, sD, H, 0}, BH, s2)));
+  EC_TRY((run_gemm<false, true>(BGemm{p.dS, p.Kd, p.dQu, Tg, dp, Tg, p.Tp, dp, dp, sS * H, sS, sD * H, sD, sD * H, sD, H, 0}, BH, s2)));
+  // parameter-gradient tail on the third branch: dE_b = dRel^T Qv (per (b, h) partials) reduced over b
+  EC_TRY((run_gemm<true, true>(BGemm{p.dRel, p.Qv, p.dEp, p.R, dp, Tg, p.Rp, dp, dp, sR * H, sR, sD * H, sD, sE * H, sE, H, 0}, BH, s3)));
+  tc_de_reduce_kernel<<<dim3(p.R, H), 128, 0, s3>>>(p);
+  EC_CUDA(cudaGetLastError());
+  if (par) EC_REQUIRE(ss.join(st, 2), "side-stream join failed");      // dV, dK, dQu, dQv complete
+  // du / dv from dQu / dQv: parameter gradients, beside the unpack
+  if (par) {
+    EC_CUDA(cudaEventRecord(ss.fork_ev, st));                          // (after the join: dQu / dQv are complete at this point of `st`)
+    EC_CUDA(cudaStreamWaitEvent(s1, ss.fork_ev, 0));
+  }
   tc_unpack_kernel<<<egrid(static_cast<long long>(a.B) * a.T * a.D), 256, 0, st>>>(p);
   EC_CUDA(cudaGetLastError());
-  tc_uv_part_kernel<<<dim3(BH, cdiv(dp, 32)), 1024, 0, st>>>(p);
+  tc_uv_part_kernel<<<dim3(BH, cdiv(dp, 32)), 1024, 0, s1>>>(p);
   EC_CUDA(cudaGetLastError());
-  tc_uv_reduce_kernel<<<cdiv(a.D, 32), 1024, 0, st>>>(p);
+  tc_uv_reduce_kernel<<<cdiv(a.D, 32), 1024, 0, s1>>>(p);
   EC_CUDA(cudaGetLastError());
-  tc_de_reduce_kernel<<<dim3(p.R, H), 128, 0, st>>>(p);
-  EC_CUDA(cudaGetLastError());
+  if (par) {
+    EC_CUDA(cudaEventRecord(ss.join_ev[0], s1)); EC_CUDA(cudaStreamWaitEvent(st, ss.join_ev[0], 0));
+    EC_CUDA(cudaEventRecord(ss.join_ev[2], s3)); EC_CUDA(cudaStreamWaitEvent(st, ss.join_ev[2], 0));
+  }
   return EC_OK;
 }
 

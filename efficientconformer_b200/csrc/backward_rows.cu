@@ -6,22 +6,33 @@
 // Every reduction has a fixed order (per-CTA partials + a second pass), so gradients are bit-reproducible.
 #include "ec_common.cuh"
 #include <algorithm>
+#include <type_traits>
 
 namespace ec {
 
-constexpr int kBwdCtas = 296;     // 2 per SM: row-strided persistent CTAs for the column reductions
+constexpr int kBwdCtas = 592;     // 4 per SM: row-strided persistent CTAs for the column reductions
 
 // ---------------------------------------------------------------------------------------------------------------
 // LayerNorm backward.  y = (x - mu) * rstd * gamma + beta  (statistics recomputed from x: cheaper than storing them).
 //   g = dy * gamma;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat));  dgamma = sum_rows dy * xhat;  dbeta = sum_rows dy
-// One warp per row, the row in registers (dim <= 32 * NPL); a CTA walks rows blockIdx.x*8 + warp, + 8*gridDim.x, ...;
-// per-lane column partials stay in registers over the whole walk, are merged across the 8 warps in shared memory and
-// written as per-CTA partial rows; ln_bwd_reduce_kernel adds the partial rows in CTA order.
+// One warp per row, the row in registers (dim <= 32 * NPL); a warp walks rows blockIdx.x*8 + warp, + 8*gridDim.x, ... TWO at a time
+// (both rows' loads are issued before the first reduction: the walk is latency bound); per-lane column partials stay in registers
+// over the whole walk, are merged across the 8 warps in shared memory and written as per-CTA partial rows; partial_reduce_kernel
+// adds the partial rows in CTA order.
+// Optional second output (TE != void): the x-gradient AFTER the residual accumulation, scaled, with the dropout mask of `site`
+// re-applied, in the activation type -- the operand of the next data-gradient / weight-gradient GEMM of the backward chain (what
+// ec_op_dropout computed from dx in a separate pass).
 // ---------------------------------------------------------------------------------------------------------------
-template <int NPL>
+struct LnEmit { void* out; float scale; const unsigned long long* ctr; unsigned site, keep16; };
+
+template <typename TE> __device__ __forceinline__ void emit_store(void* out, size_t i, float v) { reinterpret_cast<TE*>(out)[i] = ActTraits<TE>::to(v); }
+template <> __device__ __forceinline__ void emit_store<void>(void*, size_t, float) {}
+
+template <int NPL, typename TE>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int rows, int dim,
                                                             const float* __restrict__ gamma, float eps, float* __restrict__ dx,
-                                                            int accumulate, float* __restrict__ partial /* [gridDim.x][2][dim] */) {
+                                                            int accumulate, float* __restrict__ partial /* [gridDim.x][2][dim] */, const LnEmit em) {
+  constexpr bool kEmit = !std::is_same<TE, void>::value;
   __shared__ float red[8][32 * NPL];        // cross-warp merge buffer, used for dgamma then dbeta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float gm[NPL], pg[NPL], pb[NPL];
@@ -31,52 +42,78 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     gm[i] = c < dim ? __ldg(gamma + c) : 0.f;
     pg[i] = 0.f; pb[i] = 0.f;
   }
+  unsigned long long key = 0; float inv_keep = 0.f;
+  if (kEmit) {
+    inv_keep = em.scale;
+    if (em.ctr != nullptr) { key = site_key(em.ctr, em.site); inv_keep = em.scale * 65536.f / static_cast<float>(em.keep16); }
+  }
   const float inv_dim = 1.f / dim;
-  for (int row = blockIdx.x * 8 + warp; row < rows; row += 8 * gridDim.x) {
-    const float* xr = x + static_cast<size_t>(row) * dim;
-    const float* dr = dy + static_cast<size_t>(row) * dim;
-    float v[NPL], d[NPL];
-    float sum = 0.f;
+  const int step = 8 * gridDim.x;
+  for (int row0 = blockIdx.x * 8 + warp; row0 < rows; row0 += 2 * step) {
+    float v[2][NPL], d[2][NPL], a[2][NPL];
 #pragma unroll
-    for (int i = 0; i < NPL; ++i) {
-      const int c = lane + 32 * i;
-      v[i] = c < dim ? xr[c] : 0.f;
-      d[i] = c < dim ? dr[c] : 0.f;
-      sum += v[i];
+    for (int h = 0; h < 2; ++h) {
+      const int row = row0 + h * step;
+      const bool live = row < rows;
+      const float* xr = x + static_cast<size_t>(row) * dim;
+      const float* dr = dy + static_cast<size_t>(row) * dim;
+      const float* ar = dx + static_cast<size_t>(row) * dim;
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int c = lane + 32 * i;
+        const bool ok = live && c < dim;
+        v[h][i] = ok ? xr[c] : 0.f;
+        d[h][i] = ok ? dr[c] : 0.f;
+        a[h][i] = (ok && accumulate) ? ar[c] : 0.f;
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mu = sum * inv_dim;
-    float sq = 0.f;
+    for (int h = 0; h < 2; ++h) {
+      const int row = row0 + h * step;
+      if (row >= rows) break;
+      float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < NPL; ++i) {
-      const int c = lane + 32 * i;
-      const float t = c < dim ? v[i] - mu : 0.f;
-      sq += t * t;
-    }
+      for (int i = 0; i < NPL; ++i) sum += v[h][i];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    const float rstd = rsqrtf(sq * inv_dim + eps);
-    float s1 = 0.f, s2 = 0.f;
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mu = sum * inv_dim;
+      float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < NPL; ++i) {
-      const int c = lane + 32 * i;
-      const float xh = c < dim ? (v[i] - mu) * rstd : 0.f;
-      const float g = d[i] * gm[i];
-      s1 += g; s2 += g * xh;
-      pg[i] += d[i] * xh; pb[i] += d[i];
-      v[i] = xh; d[i] = g;
-    }
+      for (int i = 0; i < NPL; ++i) {
+        const int c = lane + 32 * i;
+        const float t = c < dim ? v[h][i] - mu : 0.f;
+        sq += t * t;
+      }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-    const float m1 = s1 * inv_dim, m2 = s2 * inv_dim;
-    float* out = dx + static_cast<size_t>(row) * dim;
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      const float rstd = rsqrtf(sq * inv_dim + eps);
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < NPL; ++i) {
-      const int c = lane + 32 * i;
-      if (c < dim) {
-        const float r = rstd * (d[i] - m1 - v[i] * m2);
-        out[c] = accumulate ? out[c] + r : r;
+      for (int i = 0; i < NPL; ++i) {
+        const int c = lane + 32 * i;
+        const float xh = c < dim ? (v[h][i] - mu) * rstd : 0.f;
+        const float g = d[h][i] * gm[i];
+        s1 += g; s2 += g * xh;
+        pg[i] += d[h][i] * xh; pb[i] += d[h][i];
+        v[h][i] = xh; d[h][i] = g;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+      const float m1 = s1 * inv_dim, m2 = s2 * inv_dim;
+      float* out = dx + static_cast<size_t>(row) * dim;
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int c = lane + 32 * i;
+        if (c < dim) {
+          const float r = a[h][i] + rstd * (d[h][i] - m1 - v[h][i] * m2);
+          out[c] = r;
+          if (kEmit) {
+            const size_t idx = static_cast<size_t>(row) * dim + c;
+            float f = inv_keep;
+            if (em.ctr != nullptr) f = keep_factor(splitmix64(key + (idx >> 2)), static_cast<int>(idx & 3), em.keep16, inv_keep);
+            emit_store<TE>(em.out, idx, f * r);
+          }
+        }
       }
     }
   }
@@ -122,15 +159,28 @@ __global__ void __launch_bounds__(1024) partial_reduce_kernel(const float* __res
 
 size_t layernorm_bwd_work_bytes(int dim) { return align_up(static_cast<size_t>(kBwdCtas) * 2 * dim * sizeof(float), 256); }
 
+template <typename TE>
+static void launch_ln_bwd_t(int ctas, const float* x, const float* dy, int rows, int dim, const float* gamma, float eps, float* dx, int accumulate,
+                            float* work, const LnEmit& em, cudaStream_t stream) {
+  if (dim <= 128) layernorm_bwd_kernel<4, TE><<<ctas, 256, 0, stream>>>(x, dy, rows, dim, gamma, eps, dx, accumulate, work, em);
+  else if (dim <= 256) layernorm_bwd_kernel<8, TE><<<ctas, 256, 0, stream>>>(x, dy, rows, dim, gamma, eps, dx, accumulate, work, em);
+  else if (dim <= 512) layernorm_bwd_kernel<16, TE><<<ctas, 256, 0, stream>>>(x, dy, rows, dim, gamma, eps, dx, accumulate, work, em);
+  else layernorm_bwd_kernel<32, TE><<<ctas, 256, 0, stream>>>(x, dy, rows, dim, gamma, eps, dx, accumulate, work, em);
+}
+
 int launch_layernorm_bwd(const float* x, const float* dy, int rows, int dim, const float* gamma, float eps, float* dx, int accumulate,
-                         float* dgamma, float* dbeta, float* work, cudaStream_t stream) {
+                         float* dgamma, float* dbeta, float* work, cudaStream_t stream, int emit_precision, void* emit_out, float emit_scale,
+                         const unsigned long long* drop_ctr, float drop_p, unsigned drop_site) {
   EC_REQUIRE(rows > 0 && dim > 0 && dim <= 1024, "LayerNorm backward: bad shape (dim <= 1024)");
   EC_REQUIRE(x && dy && gamma && dx && dgamma && dbeta && work, "null argument");
+  EC_REQUIRE(drop_ctr == nullptr || (drop_p >= 0.f && drop_p < 1.f && dim % 4 == 0), "bad dropout arguments (dim must be a multiple of 4)");
   const int ctas = std::min(kBwdCtas, cdiv(rows, 8));
-  if (dim <= 128) layernorm_bwd_kernel<4><<<ctas, 256, 0, stream>>>(x, dy, rows, dim, gamma, eps, dx, accumulate, work);
-  else if (dim <= 256) layernorm_bwd_kernel<8><<<ctas, 256, 0, stream>>>(x, dy, rows, dim, gamma, eps, dx, accumulate, work);
-  else if (dim <= 512) layernorm_bwd_kernel<16><<<ctas, 256, 0, stream>>>(x, dy, rows, dim, gamma, eps, dx, accumulate, work);
-  else layernorm_bwd_kernel<32><<<ctas, 256, 0, stream>>>(x, dy, rows, dim, gamma, eps, dx, accumulate, work);
+  LnEmit em{emit_out, emit_scale, drop_ctr, drop_site, drop_ctr != nullptr ? keep16_of(drop_p) : 65536u};
+  if (emit_out == nullptr) launch_ln_bwd_t<void>(ctas, x, dy, rows, dim, gamma, eps, dx, accumulate, work, em, stream);
+  else if (emit_precision == EC_PREC_TF32) launch_ln_bwd_t<float>(ctas, x, dy, rows, dim, gamma, eps, dx, accumulate, work, em, stream);
+  else if (emit_precision == EC_PREC_BF16) launch_ln_bwd_t<__nv_bfloat16>(ctas, x, dy, rows, dim, gamma, eps, dx, accumulate, work, em, stream);
+  else if (emit_precision == EC_PREC_BF16X2) launch_ln_bwd_t<SplitBf16>(ctas, x, dy, rows, dim, gamma, eps, dx, accumulate, work, em, stream);
+  else EC_FAIL("unknown precision");
   EC_CUDA(cudaGetLastError());
   partial_reduce_kernel<<<cdiv(2 * dim, 32), 1024, 0, stream>>>(work, ctas, 2, dim, dgamma, dbeta);
   EC_CUDA(cudaGetLastError());

@@ -18,68 +18,85 @@
 namespace ec {
 
 namespace {
-constexpr int kCtas = 888;      // 8 per SM: these kernels are latency bound on one dependent load chain per thread
+constexpr int kRun = 16;        // output frames per thread run (register sliding window over the taps)
+constexpr int kMaxRunCtas = 2048;
+constexpr int kColCtas = 592;   // 4 per SM: CTAs of the column-reduction kernels
 constexpr int kMaxTaps = 31;
-
-// rows [r0, r1) of this CTA for a row-strided split of `rows` over gridDim.x CTAs (contiguous ranges: coalesced, deterministic)
-__device__ __forceinline__ void cta_rows(size_t rows, size_t& r0, size_t& r1) {
-  const size_t per = (rows + gridDim.x - 1) / gridDim.x;
-  r0 = min(rows, per * blockIdx.x); r1 = min(rows, r0 + per);
-}
 }  // namespace
 
 // ---- forward: raw depthwise conv + statistics ------------------------------------------------------------------------------
-// thread = channel (blockIdx.y tiles channels by 128), CTA = a contiguous range of output frames (flattened b*T_out + t)
-template <typename T, int KT>
-__global__ void __launch_bounds__(128) dwconv_raw_kernel_(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                                         int B, int T_in, int T_out, int C, int K, int stride, float* __restrict__ y,
-                                                         float* __restrict__ partial /* [gridDim.x][2][C] */) {
+// thread = channel (coalesced 128-byte rows per warp), one RUN of kRun consecutive output frames of one sequence per iteration: the
+// (kRun-1)*S + K input frames of the run are loaded once into a register window and every output reads its taps from it (1 load per
+// output instead of K).  Per-thread statistics of its runs are exact two-pass (values are in registers), merged with Chan's update;
+// partial[cta] = (count, mean, M2) per channel.  kFlip: taps reversed, input fp32, no bias / statistics = the stride-1 data gradient.
+template <typename T, int KT, int S, bool kFlip>
+__global__ void __launch_bounds__(128) dwconv_run_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                         int B, int T_in, int T_out, int C, int K, float* __restrict__ y,
+                                                         float* __restrict__ partial /* [gridDim.x][3][C] or nullptr */) {
   const int c = blockIdx.y * 128 + threadIdx.x;
   if (c >= C) return;
   float wk[KT];
 #pragma unroll
-  for (int k = 0; k < KT; ++k) wk[k] = k < K ? w[c * K + k] : 0.f;
-  const float bc = bias[c];
+  for (int k = 0; k < KT; ++k) wk[k] = k < K ? w[c * K + (kFlip ? K - 1 - k : k)] : 0.f;
+  const float bc = (kFlip || bias == nullptr) ? 0.f : bias[c];
   const int pad = (K - 1) / 2;
-  size_t r0, r1; cta_rows(static_cast<size_t>(B) * T_out, r0, r1);
-  float s1 = 0.f, s2 = 0.f;
-  for (size_t r = r0; r < r1; ++r) {
-    const int b = static_cast<int>(r / T_out), t = static_cast<int>(r - static_cast<size_t>(b) * T_out);
+  const int runs_per_seq = (T_out + kRun - 1) / kRun;
+  const int n_runs = B * runs_per_seq;
+  constexpr int W = (kRun - 1) * S + KT;
+  float n_acc = 0.f, mean_acc = 0.f, m2_acc = 0.f;
+  for (int run = blockIdx.x; run < n_runs; run += gridDim.x) {
+    const int b = run / runs_per_seq, t0 = (run - b * runs_per_seq) * kRun;
     const T* xb = x + static_cast<size_t>(b) * T_in * C + c;
-    float acc = bc;
+    const int ti0 = t0 * S - pad;
+    float xin[W];
 #pragma unroll
-    for (int k = 0; k < KT; ++k) {
-      const int ti = t * stride + k - pad;
-      if (k < K && ti >= 0 && ti < T_in) acc = fmaf(wk[k], ActTraits<T>::from(xb[static_cast<size_t>(ti) * C]), acc);
+    for (int j = 0; j < W; ++j) {
+      const int ti = ti0 + j;
+      xin[j] = (ti >= 0 && ti < T_in) ? ActTraits<T>::from(xb[static_cast<size_t>(ti) * C]) : 0.f;
     }
-    y[r * C + c] = acc;
-    s1 += acc;
+    const int nv = min(kRun, T_out - t0);
+    float acc[kRun];
+    float s1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < kRun; ++r) {
+      float a = bc;
+#pragma unroll
+      for (int k = 0; k < KT; ++k) a = fmaf(wk[k], xin[r * S + k], a);
+      acc[r] = a;
+      if (r < nv) { y[(static_cast<size_t>(b) * T_out + t0 + r) * C + c] = a; s1 += a; }
+    }
+    if (!kFlip) {
+      const float lm = s1 / static_cast<float>(nv);
+      float s2 = 0.f;
+#pragma unroll
+      for (int r = 0; r < kRun; ++r) if (r < nv) { const float d = acc[r] - lm; s2 = fmaf(d, d, s2); }
+      const float nb = static_cast<float>(nv), tot = n_acc + nb, dl = lm - mean_acc, f = nb / tot;
+      mean_acc = fmaf(dl, f, mean_acc);
+      m2_acc += s2 + dl * dl * n_acc * f;
+      n_acc = tot;
+    }
   }
-  // second pass over this thread's own outputs: centred sum of squares about the local mean (sum of squares minus mean^2 loses
-  // every digit when |mean| >> std, e.g. a tiny tap vector next to a large bias)
-  const float lm = r1 > r0 ? s1 / static_cast<float>(r1 - r0) : 0.f;
-  for (size_t r = r0; r < r1; ++r) { const float d = y[r * C + c] - lm; s2 = fmaf(d, d, s2); }
-  partial[(static_cast<size_t>(blockIdx.x) * 2) * C + c] = lm;
-  partial[(static_cast<size_t>(blockIdx.x) * 2 + 1) * C + c] = s2;
+  if (!kFlip && partial != nullptr) {
+    float* o = partial + static_cast<size_t>(blockIdx.x) * 3 * C + c;
+    o[0] = n_acc; o[C] = mean_acc; o[2 * C] = m2_acc;
+  }
 }
 
-// (mean, M2) of the CTA row ranges merged with Chan's update: stats[0][c] = mean, stats[1][c] = M2.
+// (count, mean, M2) partials merged with Chan's update: stats[0][c] = mean, stats[1][c] = M2.
 // Block = 32 channels x 32 lanes: lane ty merges the contiguous chunk ty of the partials in CTA order, then the 32 chunk results
 // are merged in lane order in double (fixed order: bit-reproducible; the dependent chain is n_partial / 32 + 32 steps).
-__global__ void __launch_bounds__(1024) bn_stats_merge_kernel(const float* __restrict__ partial, int n_partial, size_t rows, int C,
-                                                              float* __restrict__ stats) {
+__global__ void __launch_bounds__(1024) bn_stats_merge_kernel(const float* __restrict__ partial, int n_partial, int C, float* __restrict__ stats) {
   __shared__ float sn[32][33], smean[32][33], sm2[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
-  const size_t per = (rows + n_partial - 1) / n_partial;
   const int chunk = (n_partial + 31) / 32, p0 = ty * chunk, p1 = min(n_partial, p0 + chunk);
   float n = 0.f, mean = 0.f, m2 = 0.f;
   if (c < C) {
     for (int p = p0; p < p1; ++p) {
-      const size_t r0 = min(rows, per * p), r1 = min(rows, r0 + per);
-      const float nb = static_cast<float>(r1 - r0);
+      const float* q = partial + static_cast<size_t>(p) * 3 * C + c;
+      const float nb = q[0];
       if (nb == 0.f) continue;
-      const float mb = partial[(static_cast<size_t>(p) * 2) * C + c], qb = partial[(static_cast<size_t>(p) * 2 + 1) * C + c];
+      const float mb = q[C], qb = q[2 * C];
       const float tot = n + nb, dl = mb - mean, f = nb / tot;
       mean = fmaf(dl, f, mean);
       m2 += qb + dl * dl * n * f;
@@ -143,38 +160,92 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, int C, float 
   }
 }
 
+// Element kernels over [rows, C] with per-channel parameters: a thread owns 4 consecutive channels (128-bit accesses; C % 4 == 0)
+template <typename T> __device__ __forceinline__ void store4(T* p, const float (&v)[4]);
+template <> __device__ __forceinline__ void store4<float>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]));
+}
+template <> __device__ __forceinline__ void store4<SplitBf16>(SplitBf16* p, const float (&v)[4]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(split_pack(v[0]), split_pack(v[1]), split_pack(v[2]), split_pack(v[3]));
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) bn_swish_fwd_kernel(const float* __restrict__ y, size_t rows, int C, const float* __restrict__ mean,
                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, T* __restrict__ h) {
-  const size_t n = rows * C, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int c = static_cast<int>(i % C);
-    const float z = (y[i] - mean[c]) * rstd[c] * gamma[c] + beta[c];
-    h[i] = ActTraits<T>::to(z / (1.f + __expf(-z)));
+  const size_t n4 = rows * C / 4, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t g = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < n4; g += stride) {
+    const int c = static_cast<int>((g * 4) % C);
+    const float4 yv = reinterpret_cast<const float4*>(y)[g];
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+    float z[4] = {(yv.x - mu.x) * rs.x * ga.x + be.x, (yv.y - mu.y) * rs.y * ga.y + be.y, (yv.z - mu.z) * rs.z * ga.z + be.z,
+                  (yv.w - mu.w) * rs.w * ga.w + be.w};
+#pragma unroll
+    for (int l = 0; l < 4; ++l) z[l] = z[l] / (1.f + __expf(-z[l]));
+    store4<T>(h + g * 4, z);
   }
 }
 
 // ---- backward ----------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float swish_grad(float z) { const float s = 1.f / (1.f + __expf(-z)); return s + z * s * (1.f - s); }
 
-// thread = channel; partial[cta][0][c] = sum dz, partial[cta][1][c] = sum dz * xhat
-__global__ void __launch_bounds__(128) bn_swish_bwd_stats_kernel(const float* __restrict__ y, const float* __restrict__ dh, size_t rows, int C,
+// Column sums of dz = dh * swish'(z) and dz * xhat.  Block = 32 channel quads x 8 row lanes; the CTA owns a contiguous row range and
+// its row lane ty the rows r0 + ty, r0 + ty + 8, ... (4 independent rows in flight per thread); lanes merged in shared memory in a fixed
+// order.  partial[cta.x][0][c] = sum dz, partial[cta.x][1][c] = sum dz * xhat.
+__global__ void __launch_bounds__(256) bn_swish_bwd_stats_kernel(const float* __restrict__ y, const float* __restrict__ dh, size_t rows, int C,
                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                  float* __restrict__ partial) {
-  const int c = blockIdx.y * 128 + threadIdx.x;
-  if (c >= C) return;
-  const float mu = mean[c], rs = rstd[c], g = gamma[c], be = beta[c];
-  size_t r0, r1; cta_rows(rows, r0, r1);
-  float s1 = 0.f, s2 = 0.f;
-  for (size_t r = r0; r < r1; ++r) {
-    const float xh = (y[r * C + c] - mu) * rs;
-    const float dz = dh[r * C + c] * swish_grad(xh * g + be);
-    s1 += dz; s2 = fmaf(dz, xh, s2);
+  __shared__ float sm[2][8][132];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.y * 128 + tx * 4;
+  const bool ok = c < C;
+  float4 mu = make_float4(0, 0, 0, 0), rs = mu, ga = mu, be = mu;
+  if (ok) {
+    mu = *reinterpret_cast<const float4*>(mean + c); rs = *reinterpret_cast<const float4*>(rstd + c);
+    ga = *reinterpret_cast<const float4*>(gamma + c); be = *reinterpret_cast<const float4*>(beta + c);
   }
-  partial[(static_cast<size_t>(blockIdx.x) * 2) * C + c] = s1;
-  partial[(static_cast<size_t>(blockIdx.x) * 2 + 1) * C + c] = s2;
+  const size_t per = (rows + gridDim.x - 1) / gridDim.x;
+  const size_t r0 = min(rows, per * blockIdx.x), r1 = min(rows, r0 + per);
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (ok) {
+    for (size_t r = r0 + ty; r < r1; r += 32) {
+      float4 yv[4], dv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const size_t rr = r + 8 * u;
+        if (rr < r1) { yv[u] = *reinterpret_cast<const float4*>(y + rr * C + c); dv[u] = *reinterpret_cast<const float4*>(dh + rr * C + c); }
+        else { yv[u] = mu; dv[u] = make_float4(0, 0, 0, 0); }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float xh[4] = {(yv[u].x - mu.x) * rs.x, (yv[u].y - mu.y) * rs.y, (yv[u].z - mu.z) * rs.z, (yv[u].w - mu.w) * rs.w};
+        const float dd[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+        const float gg[4] = {ga.x, ga.y, ga.z, ga.w}, bb[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          const float dz = dd[l] * swish_grad(xh[l] * gg[l] + bb[l]);
+          s1[l] += dz; s2[l] = fmaf(dz, xh[l], s2[l]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < 4; ++l) { sm[0][ty][tx * 4 + l] = s1[l]; sm[1][ty][tx * 4 + l] = s2[l]; }
+  __syncthreads();
+  {
+    const int which = threadIdx.x >> 7, col = threadIdx.x & 127;       // 256 threads = 2 outputs x 128 channels
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += sm[which][q][col];
+    const int cc = blockIdx.y * 128 + col;
+    if (cc < C) partial[(static_cast<size_t>(blockIdx.x) * 2 + which) * C + cc] = t;
+  }
 }
 
 // dy = gamma * rstd * (dz - sum_dz / R - xhat * sum_dzx / R)   (R = frames the statistics were taken over, all ranks)
@@ -183,17 +254,29 @@ __global__ void __launch_bounds__(256) bn_swish_bwd_apply_kernel(const float* __
                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                  const float* __restrict__ sums /* [2][C] */, float count,
                                                                  float* __restrict__ dy) {
-  const size_t n = rows * C, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t n4 = rows * C / 4, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   const float inv = 1.f / count;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int c = static_cast<int>(i % C);
-    const float xh = (y[i] - mean[c]) * rstd[c];
-    const float dz = dh[i] * swish_grad(xh * gamma[c] + beta[c]);
-    dy[i] = gamma[c] * rstd[c] * (dz - sums[c] * inv - xh * sums[C + c] * inv);
+  for (size_t g = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < n4; g += stride) {
+    const int c = static_cast<int>((g * 4) % C);
+    const float4 yv = reinterpret_cast<const float4*>(y)[g], dv = reinterpret_cast<const float4*>(dh)[g];
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+    const float4 sa = *reinterpret_cast<const float4*>(sums + c), sb = *reinterpret_cast<const float4*>(sums + C + c);
+    const float yy[4] = {yv.x, yv.y, yv.z, yv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w}, mm[4] = {mu.x, mu.y, mu.z, mu.w}, rr[4] = {rs.x, rs.y, rs.z, rs.w};
+    const float gg[4] = {ga.x, ga.y, ga.z, ga.w}, bb[4] = {be.x, be.y, be.z, be.w}, a1[4] = {sa.x, sa.y, sa.z, sa.w}, a2[4] = {sb.x, sb.y, sb.z, sb.w};
+    float o[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const float xh = (yy[l] - mm[l]) * rr[l];
+      const float dz = dd[l] * swish_grad(xh * gg[l] + bb[l]);
+      o[l] = gg[l] * rr[l] * (dz - a1[l] * inv - xh * a2[l] * inv);
+    }
+    reinterpret_cast<float4*>(dy)[g] = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
-// dx[b, ti, c] = sum_k w[c,k] * dy[b, to, c],  to = (ti + pad - k) / s when divisible and 0 <= to < T_out
+// dx[b, ti, c] = sum_k w[c,k] * dy[b, to, c],  to = (ti + pad - k) / s when divisible and 0 <= to < T_out  (strided blocks; the stride-1
+// data gradient is the forward run kernel with reversed taps)
 template <int KT>
 __global__ void __launch_bounds__(128) dwconv_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, int B, int T_in,
                                                               int T_out, int C, int K, int stride, float* __restrict__ dx) {
@@ -203,7 +286,9 @@ __global__ void __launch_bounds__(128) dwconv_bwd_data_kernel(const float* __res
 #pragma unroll
   for (int k = 0; k < KT; ++k) wk[k] = k < K ? w[c * K + k] : 0.f;
   const int pad = (K - 1) / 2;
-  size_t r0, r1; cta_rows(static_cast<size_t>(B) * T_in, r0, r1);
+  const size_t rows = static_cast<size_t>(B) * T_in;
+  const size_t per = (rows + gridDim.x - 1) / gridDim.x;
+  const size_t r0 = min(rows, per * blockIdx.x), r1 = min(rows, r0 + per);
   for (size_t r = r0; r < r1; ++r) {
     const int b = static_cast<int>(r / T_in), ti = static_cast<int>(r - static_cast<size_t>(b) * T_in);
     const float* db = dy + static_cast<size_t>(b) * T_out * C + c;
@@ -220,32 +305,58 @@ __global__ void __launch_bounds__(128) dwconv_bwd_data_kernel(const float* __res
   }
 }
 
-// partial[cta][c][k] = sum over this CTA's output frames of dy * x[t*s + k - pad];  partial[cta][c][K] = sum dy
-template <typename T, int KT>
-__global__ void __launch_bounds__(128) dwconv_bwd_weight_kernel(const float* __restrict__ dy, const T* __restrict__ x, int B, int T_in, int T_out,
-                                                                int C, int K, int stride, float* __restrict__ partial) {
-  const int c = blockIdx.y * 128 + threadIdx.x;
-  if (c >= C) return;
+// Weight / bias gradient of the depthwise conv.  Block = 128 channels x 4 run lanes; every thread walks runs of kRun output frames with
+// the same register window as the forward, accumulating its K tap gradients and the bias gradient in registers; the 4 run lanes are
+// merged in shared memory in a fixed order.  partial[cta][c][k] (k = K: sum dy).
+template <typename T, int KT, int S>
+__global__ void __launch_bounds__(512) dwconv_bwd_weight_kernel(const float* __restrict__ dy, const T* __restrict__ x, int B, int T_in, int T_out,
+                                                                int C, int K, float* __restrict__ partial) {
+  __shared__ float sm[3][KT + 1][128];
+  const int tx = threadIdx.x & 127, ty = threadIdx.x >> 7;
+  const int c = blockIdx.y * 128 + tx;
   const int pad = (K - 1) / 2;
+  const int runs_per_seq = (T_out + kRun - 1) / kRun;
+  const int n_runs = B * runs_per_seq;
+  constexpr int W = (kRun - 1) * S + KT;
   float acc[KT + 1];
 #pragma unroll
   for (int k = 0; k <= KT; ++k) acc[k] = 0.f;
-  size_t r0, r1; cta_rows(static_cast<size_t>(B) * T_out, r0, r1);
-  for (size_t r = r0; r < r1; ++r) {
-    const int b = static_cast<int>(r / T_out), t = static_cast<int>(r - static_cast<size_t>(b) * T_out);
-    const T* xb = x + static_cast<size_t>(b) * T_in * C + c;
-    const float d = dy[r * C + c];
-    acc[KT] += d;
+  if (c < C) {
+    for (int run = blockIdx.x * 4 + ty; run < n_runs; run += gridDim.x * 4) {
+      const int b = run / runs_per_seq, t0 = (run - b * runs_per_seq) * kRun;
+      const T* xb = x + static_cast<size_t>(b) * T_in * C + c;
+      const float* db = dy + (static_cast<size_t>(b) * T_out + t0) * C + c;
+      const int ti0 = t0 * S - pad;
+      const int nv = min(kRun, T_out - t0);
+      float xin[W], d[kRun];
 #pragma unroll
-    for (int k = 0; k < KT; ++k) {
-      const int ti = t * stride + k - pad;
-      if (k < K && ti >= 0 && ti < T_in) acc[k] = fmaf(d, ActTraits<T>::from(xb[static_cast<size_t>(ti) * C]), acc[k]);
+      for (int j = 0; j < W; ++j) {
+        const int ti = ti0 + j;
+        xin[j] = (ti >= 0 && ti < T_in) ? ActTraits<T>::from(xb[static_cast<size_t>(ti) * C]) : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < kRun; ++r) d[r] = r < nv ? db[static_cast<size_t>(r) * C] : 0.f;
+#pragma unroll
+      for (int r = 0; r < kRun; ++r) {
+        acc[KT] += d[r];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) acc[k] = fmaf(d[r], xin[r * S + k], acc[k]);
+      }
     }
   }
-  float* out = partial + (static_cast<size_t>(blockIdx.x) * C + c) * (K + 1);
+  if (ty > 0) {
 #pragma unroll
-  for (int k = 0; k < KT; ++k) if (k < K) out[k] = acc[k];
-  out[K] = acc[KT];
+    for (int k = 0; k <= KT; ++k) sm[ty - 1][k][tx] = acc[k];
+  }
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float* out = partial + (static_cast<size_t>(blockIdx.x) * C + c) * (K + 1);
+#pragma unroll
+    for (int k = 0; k <= KT; ++k) {
+      const float t = ((acc[k] + sm[0][k][tx]) + sm[1][k][tx]) + sm[2][k][tx];
+      if (k < K) out[k] = t; else if (k == KT) out[K] = t;
+    }
+  }
 }
 // dw[c][k] / db[c] from the partials (chunked fixed-order sum, see chunked_sum_32x32)
 __global__ void __launch_bounds__(1024) dwconv_wgrad_reduce_kernel(const float* __restrict__ partial, int n_partial, int C, int K,
@@ -260,21 +371,27 @@ __global__ void __launch_bounds__(1024) dwconv_wgrad_reduce_kernel(const float* 
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------------------
-size_t conv_train_work_bytes(int C, int K) { return align_up(static_cast<size_t>(kCtas) * C * std::max(K + 1, 2) * sizeof(float), 256); }
+size_t conv_train_work_bytes(int C, int K) {
+  const size_t a = static_cast<size_t>(kMaxRunCtas) * 3 * C, b = static_cast<size_t>(kColCtas) * C * std::max(K + 1, 2);
+  return align_up(std::max(a, b) * sizeof(float), 256);
+}
 
-static int ctas_for(size_t rows) { return static_cast<int>(std::min<size_t>(kCtas, std::max<size_t>(rows, 1))); }
+static int run_ctas(int B, int T_out) { return std::max(1, std::min(kMaxRunCtas, B * cdiv(T_out, kRun))); }
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int launch_dwconv_raw(int precision, const void* x, const float* w, const float* bias, int B, int T, int C, int K, int stride, float* y,
                       float* sums /* [2][C] */, float* work, cudaStream_t st) {
   EC_REQUIRE(K % 2 == 1 && K <= kMaxTaps && (stride == 1 || stride == 2), "depthwise conv: odd k <= 31, stride 1 or 2");
   const int T_out = (T - 1) / stride + 1;
-  const int ctas = ctas_for(static_cast<size_t>(B) * T_out);
+  const int ctas = run_ctas(B, T_out);
   dim3 grid(ctas, cdiv(C, 128));
-  const bool small = K <= 15;                                  // tap loops are fully unrolled: 15-tap (Efficient Conformer) or 31-tap instances
-  if (small) EC_DISPATCH_PREC(precision, (dwconv_raw_kernel_<ActT, 15><<<grid, 128, 0, st>>>(reinterpret_cast<const ActT*>(x), w, bias, B, T, T_out, C, K, stride, y, work)));
-  else EC_DISPATCH_PREC(precision, (dwconv_raw_kernel_<ActT, 31><<<grid, 128, 0, st>>>(reinterpret_cast<const ActT*>(x), w, bias, B, T, T_out, C, K, stride, y, work)));
+  // tap loops are fully unrolled: 15-tap (Efficient Conformer) or 31-tap instances, stride 1 or 2
+#define EC_RAW(KT, S) EC_DISPATCH_PREC(precision, (dwconv_run_kernel<ActT, KT, S, false><<<grid, 128, 0, st>>>(reinterpret_cast<const ActT*>(x), w, bias, B, T, T_out, C, K, y, work)))
+  if (K <= 15) { if (stride == 1) EC_RAW(15, 1); else EC_RAW(15, 2); }
+  else { if (stride == 1) EC_RAW(31, 1); else EC_RAW(31, 2); }
+#undef EC_RAW
   EC_CUDA(cudaGetLastError());
-  bn_stats_merge_kernel<<<cdiv(C, 32), 1024, 0, st>>>(work, ctas, static_cast<size_t>(B) * T_out, C, sums);
+  bn_stats_merge_kernel<<<cdiv(C, 32), 1024, 0, st>>>(work, ctas, C, sums);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -286,15 +403,20 @@ int launch_bn_finalize(const float* sums, int C, float count, float eps, float m
 }
 int launch_bn_swish_fwd(int precision, const float* y, size_t rows, int C, const float* mean, const float* rstd, const float* gamma,
                         const float* beta, void* h, cudaStream_t st) {
-  const int blocks = static_cast<int>(std::min<size_t>((rows * C + 255) / 256, 148 * 16));
+  EC_REQUIRE(C % 4 == 0 && aligned16(y) && aligned16(h) && aligned16(mean) && aligned16(rstd) && aligned16(gamma) && aligned16(beta),
+             "BatchNorm + Swish: channels must be a multiple of 4 and every pointer 16-byte aligned");
+  const int blocks = static_cast<int>(std::min<size_t>((rows * C / 4 + 255) / 256, 148 * 8));
   EC_DISPATCH_PREC(precision, (bn_swish_fwd_kernel<ActT><<<blocks, 256, 0, st>>>(y, rows, C, mean, rstd, gamma, beta, reinterpret_cast<ActT*>(h))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
 int launch_bn_swish_bwd_stats(const float* y, const float* dh, size_t rows, int C, const float* mean, const float* rstd, const float* gamma,
                               const float* beta, float* sums /* [2][C]: dbeta, dgamma */, float* work, cudaStream_t st) {
-  const int ctas = ctas_for(rows);
-  bn_swish_bwd_stats_kernel<<<dim3(ctas, cdiv(C, 128)), 128, 0, st>>>(y, dh, rows, C, mean, rstd, gamma, beta, work);
+  EC_REQUIRE(C % 4 == 0 && aligned16(y) && aligned16(dh) && aligned16(mean) && aligned16(rstd) && aligned16(gamma) && aligned16(beta),
+             "BatchNorm + Swish backward: channels must be a multiple of 4 and every pointer 16-byte aligned");
+  const int gy = cdiv(C, 128);
+  const int ctas = static_cast<int>(std::max<size_t>(1, std::min<size_t>(std::max(1, kColCtas / gy), (rows + 31) / 32)));
+  bn_swish_bwd_stats_kernel<<<dim3(ctas, gy), 256, 0, st>>>(y, dh, rows, C, mean, rstd, gamma, beta, work);
   EC_CUDA(cudaGetLastError());
   conv_partial_reduce_kernel<<<cdiv(2 * C, 32), 1024, 0, st>>>(work, ctas, 2, C, sums);
   EC_CUDA(cudaGetLastError());
@@ -302,7 +424,9 @@ int launch_bn_swish_bwd_stats(const float* y, const float* dh, size_t rows, int 
 }
 int launch_bn_swish_bwd_apply(const float* y, const float* dh, size_t rows, int C, const float* mean, const float* rstd, const float* gamma,
                               const float* beta, const float* sums, float count, float* dy, cudaStream_t st) {
-  const int blocks = static_cast<int>(std::min<size_t>((rows * C + 255) / 256, 148 * 16));
+  EC_REQUIRE(C % 4 == 0 && aligned16(y) && aligned16(dh) && aligned16(dy) && aligned16(mean) && aligned16(rstd) && aligned16(gamma) &&
+             aligned16(beta) && aligned16(sums), "BatchNorm + Swish backward: channels must be a multiple of 4 and every pointer 16-byte aligned");
+  const int blocks = static_cast<int>(std::min<size_t>((rows * C / 4 + 255) / 256, 148 * 8));
   bn_swish_bwd_apply_kernel<<<blocks, 256, 0, st>>>(y, dh, rows, C, mean, rstd, gamma, beta, sums, count, dy);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
@@ -312,15 +436,24 @@ int launch_dwconv_bwd(int precision, const float* dy, const void* x, const float
   EC_REQUIRE(K % 2 == 1 && K <= kMaxTaps && (stride == 1 || stride == 2), "depthwise conv: odd k <= 31, stride 1 or 2");
   const int T_out = (T - 1) / stride + 1;
   if (dx != nullptr) {
-    const dim3 gd(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(B) * T, 148 * 32)), cdiv(C, 128));
-    if (K <= 15) dwconv_bwd_data_kernel<15><<<gd, 128, 0, st>>>(dy, w, B, T, T_out, C, K, stride, dx);
-    else dwconv_bwd_data_kernel<31><<<gd, 128, 0, st>>>(dy, w, B, T, T_out, C, K, stride, dx);
+    if (stride == 1) {                 // correlation with the reversed taps: the forward run kernel on the fp32 gradient
+      dim3 gd(run_ctas(B, T), cdiv(C, 128));
+      if (K <= 15) dwconv_run_kernel<float, 15, 1, true><<<gd, 128, 0, st>>>(dy, w, nullptr, B, T, T, C, K, dx, nullptr);
+      else dwconv_run_kernel<float, 31, 1, true><<<gd, 128, 0, st>>>(dy, w, nullptr, B, T, T, C, K, dx, nullptr);
+    } else {
+      const dim3 gd(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(B) * T, 148 * 32)), cdiv(C, 128));
+      if (K <= 15) dwconv_bwd_data_kernel<15><<<gd, 128, 0, st>>>(dy, w, B, T, T_out, C, K, stride, dx);
+      else dwconv_bwd_data_kernel<31><<<gd, 128, 0, st>>>(dy, w, B, T, T_out, C, K, stride, dx);
+    }
     EC_CUDA(cudaGetLastError());
   }
-  const int ctas = ctas_for(static_cast<size_t>(B) * T_out);
-  dim3 grid(ctas, cdiv(C, 128));
-  if (K <= 15) EC_DISPATCH_PREC(precision, (dwconv_bwd_weight_kernel<ActT, 15><<<grid, 128, 0, st>>>(dy, reinterpret_cast<const ActT*>(x), B, T, T_out, C, K, stride, work)));
-  else EC_DISPATCH_PREC(precision, (dwconv_bwd_weight_kernel<ActT, 31><<<grid, 128, 0, st>>>(dy, reinterpret_cast<const ActT*>(x), B, T, T_out, C, K, stride, work)));
+  const int gy = cdiv(C, 128);
+  const int ctas = std::max(1, std::min(std::max(1, kColCtas / 2 / gy), cdiv(B * cdiv(T_out, kRun), 4)));
+  dim3 grid(ctas, gy);
+#define EC_WG(KT, S) EC_DISPATCH_PREC(precision, (dwconv_bwd_weight_kernel<ActT, KT, S><<<grid, 512, 0, st>>>(dy, reinterpret_cast<const ActT*>(x), B, T, T_out, C, K, work)))
+  if (K <= 15) { if (stride == 1) EC_WG(15, 1); else EC_WG(15, 2); }
+  else { if (stride == 1) EC_WG(31, 1); else EC_WG(31, 2); }
+#undef EC_WG
   EC_CUDA(cudaGetLastError());
   dwconv_wgrad_reduce_kernel<<<cdiv(C * (K + 1), 32), 1024, 0, st>>>(work, ctas, C, K, dw, db);
   EC_CUDA(cudaGetLastError());

@@ -65,6 +65,22 @@ int launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   return EC_OK;
 }
 
+// Fork / join of independent launches onto library-owned side streams (non-blocking, created once per process): `fork(st)` makes the
+// side streams wait for everything enqueued on `st` so far, `join(st, n)` makes `st` wait for the first n side streams.  Both are
+// event record / wait pairs, so they are capturable: inside a CUDA graph the launches become parallel branches.  After `join` all
+// side work is ordered before whatever the caller enqueues on `st` next (allocator-safe: the caller's stream semantics are preserved).
+struct SideStreams {
+  static constexpr int kN = 4;
+  cudaStream_t s[kN]{};
+  cudaEvent_t fork_ev{}, join_ev[kN]{};
+  bool ok = false;
+  bool init();
+  bool fork(cudaStream_t st, int n);
+  bool join(cudaStream_t st, int n);
+};
+SideStreams& side_streams();
+bool side_streams_enabled();
+
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int round_up(int a, int b) { return cdiv(a, b) * b; }
 inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
@@ -152,6 +168,28 @@ __device__ __forceinline__ float sigmoid_fn(float x) {
     return fmaf(0.5f, th, 0.5f);
   }
 }
+// ---- counter-based dropout (train_step.cu; also applied inside the GEMM epilogues of the training step) -------------------------
+// The keep bit of element i at site s of step n is a pure function of (seed, n, s, i): ctr = {seed, step} lives in device memory, so a
+// replayed CUDA graph draws fresh masks and the backward recomputes the forward mask instead of storing it.  One 64-bit draw covers the
+// 4 consecutive elements 4g .. 4g+3 (16 bits each): keep iff bits < keep16.
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ unsigned long long site_key(const unsigned long long* ctr, unsigned site) {
+  return splitmix64(ctr[0] ^ (ctr[1] * 0xD1B54A32D192ED03ull)) ^ (static_cast<unsigned long long>(site) * 0x9FB21C651E98DF25ull);
+}
+__device__ __forceinline__ float keep_factor(unsigned long long draw, int lane, unsigned keep16, float inv_keep) {
+  return ((draw >> (16 * lane)) & 0xFFFFull) < keep16 ? inv_keep : 0.f;
+}
+inline unsigned keep16_of(float p) {
+  double keep = (1.0 - static_cast<double>(p)) * 65536.0 + 0.5;
+  keep = keep < 1.0 ? 1.0 : (keep > 65536.0 ? 65536.0 : keep);
+  return static_cast<unsigned>(keep);
+}
+
 // ---- kernel launch entry points (defined in the .cu files; all stream-ordered, never synchronise) --------------
 enum GemmAct { GEMM_ACT_NONE = 0, GEMM_ACT_SWISH = 1 };
 
@@ -175,6 +213,14 @@ struct GemmArgs {
   int ln_mode; const float *ln1_g, *ln1_b, *ln2_g, *ln2_b; float ln_eps;
   void* ln_out;
   void* copy_out; int copy_stride, frames_per_seq, frames_out_per_seq;
+  // training-step epilogue options (plain variant only; element index of the masks = row * N + column, N % 4 == 0)
+  const unsigned long long* drop_ctr;  // device {seed, step} of the counter-based dropout (nullptr: no dropout anywhere in this launch)
+  float drop_p;
+  unsigned drop_site;                  // > 0: out = alpha * keep / (1 - p) * act(acc + bias) [+ residual]  (nn.Dropout after the projection)
+  void* out_act2; int ld_act2;         // second activation-type output h = dropout_{site2}(Swish(z)), z = out_act as stored (pre-activation)
+  unsigned drop_site2;
+  const void* aux_act; int aux_mode;   // aux_mode 1: acc <- acc * keep_{site_aux} / (1 - p) * Swish'(aux): data gradient through dropout(Swish(z)),
+  unsigned drop_site_aux;              //             aux = the saved pre-activation z [M, N] (activation type); excludes `residual`
 };
 int launch_gemm(int precision, const GemmArgs& a, cudaStream_t stream);
 int gemm_timeline(int enable, unsigned long long* out12);
@@ -279,8 +325,10 @@ int launch_ctc_grad(const float* logits, const float* lse, int B, int T, int V, 
                     cudaStream_t stream);
 // row / element kernels of the backward pass (backward_rows.cu)
 size_t layernorm_bwd_work_bytes(int dim);
+// emit_out (optional): activation-type copy of emit_scale * dropout_site-mask * (the accumulated x-gradient), see backward_rows.cu
 int launch_layernorm_bwd(const float* x, const float* dy, int rows, int dim, const float* gamma, float eps, float* dx, int accumulate,
-                         float* dgamma, float* dbeta, float* work, cudaStream_t stream);
+                         float* dgamma, float* dbeta, float* work, cudaStream_t stream, int emit_precision = 0, void* emit_out = nullptr,
+                         float emit_scale = 1.f, const unsigned long long* drop_ctr = nullptr, float drop_p = 0.f, unsigned drop_site = 0);
 size_t colsum_work_bytes(int cols);
 int launch_colsum(int precision, const void* m, int is_f32, int rows, int cols, float* out, float* work, cudaStream_t stream);
 int launch_transpose_cast(int precision, const float* src, int rows, int cols, void* dst, cudaStream_t stream);

@@ -103,6 +103,29 @@ __device__ __forceinline__ void slab_store_act(uint8_t* slab, int row, const flo
   }
 }
 
+// fp32 values of a 32 x 32 activation-type slab loaded by TMA (packed / TF32 words: SW128 fp32 layout; bf16: SW64 layout)
+template <typename T>
+__device__ __forceinline__ void slab_load_act(const uint8_t* slab, int row, float (&t)[32]) {
+  if constexpr (sizeof(T) == 4) {
+    slab_load_f32(slab, row, t);
+    if constexpr (IsSplit<T>::value) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[j] = split_unpack(__float_as_uint(t[j]));
+    }
+  } else {
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+      const uint4 pk = *reinterpret_cast<const uint4*>(slab + slab_b16_off(row, j8));
+      const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        t[8 * j8 + 2 * k] = __uint_as_float(w[k] << 16);
+        t[8 * j8 + 2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // host side: tensor maps
 // ------------------------------------------------------------------------------------------------------------------

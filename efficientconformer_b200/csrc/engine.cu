@@ -19,6 +19,40 @@ bool pdl_enabled() {
   return g_pdl != 0;
 }
 
+bool SideStreams::init() {
+  if (ok) return true;
+  for (int i = 0; i < kN; ++i) {
+    if (cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&join_ev[i], cudaEventDisableTiming) != cudaSuccess) return false;
+  }
+  if (cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming) != cudaSuccess) return false;
+  ok = true;
+  return true;
+}
+bool SideStreams::fork(cudaStream_t st, int n) {
+  if (!init() || n > kN) return false;
+  if (cudaEventRecord(fork_ev, st) != cudaSuccess) return false;
+  for (int i = 0; i < n; ++i)
+    if (cudaStreamWaitEvent(s[i], fork_ev, 0) != cudaSuccess) return false;
+  return true;
+}
+bool SideStreams::join(cudaStream_t st, int n) {
+  for (int i = 0; i < n; ++i) {
+    if (cudaEventRecord(join_ev[i], s[i]) != cudaSuccess) return false;
+    if (cudaStreamWaitEvent(st, join_ev[i], 0) != cudaSuccess) return false;
+  }
+  return true;
+}
+SideStreams& side_streams() {
+  static SideStreams ss;     // one device per process (one process per GPU)
+  return ss;
+}
+static int g_side = -1;      // EFFCONF_SIDE_STREAMS=0 serialises everything on the caller's stream
+bool side_streams_enabled() {
+  if (g_side < 0) { const char* e = getenv("EFFCONF_SIDE_STREAMS"); g_side = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return g_side != 0;
+}
+
 struct Arena {   // bump allocator over a caller-provided buffer (or a dry run when base == nullptr)
   uint8_t* base; size_t off;
   explicit Arena(void* b) : base(reinterpret_cast<uint8_t*>(b)), off(0) {}
@@ -658,6 +692,12 @@ int ec_op_layernorm_bwd(const float* x, const float* dy, int rows, int dim, cons
   return launch_layernorm_bwd(x, dy, rows, dim, gamma, eps, dx, accumulate, dgamma, dbeta, reinterpret_cast<float*>(work),
                               reinterpret_cast<cudaStream_t>(stream));
 }
+int ec_op_layernorm_bwd_emit(const float* x, const float* dy, int rows, int dim, const float* gamma, float eps, float* dx, int accumulate,
+                             float* dgamma, float* dbeta, void* work, int emit_precision, void* emit_out, float emit_scale,
+                             const unsigned long long* drop_counter, float drop_p, unsigned drop_site, void* stream) {
+  return launch_layernorm_bwd(x, dy, rows, dim, gamma, eps, dx, accumulate, dgamma, dbeta, reinterpret_cast<float*>(work),
+                              reinterpret_cast<cudaStream_t>(stream), emit_precision, emit_out, emit_scale, drop_counter, drop_p, drop_site);
+}
 #define EC_ST(s) reinterpret_cast<cudaStream_t>(s)
 int ec_op_cast_scaled(int precision, const float* src, float scale, size_t n, void* dst, void* stream) {
   return launch_cast_scaled(precision, src, scale, n, dst, EC_ST(stream));
@@ -782,6 +822,17 @@ int ec_op_gemm_ex(int precision, const void* A, const void* W, int M, int N, int
   g.A = A; g.W = W; g.M = M; g.N = N; g.K = K; g.bias = bias; g.alpha = alpha; g.act = act;
   g.residual = residual; g.ld_res = N; g.out_f32 = out_f32; g.ld_out = N; g.out_act = out_act; g.ld_act = N;
   g.act_f16 = (flags & 1) ? 1 : 0;
+  return launch_gemm(precision, g, reinterpret_cast<cudaStream_t>(stream));
+}
+int ec_op_gemm_train(int precision, const void* A, const void* W, int M, int N, int K, const float* bias, float alpha,
+                     const float* residual, float* out_f32, void* out_act, const unsigned long long* drop_counter, float drop_p,
+                     unsigned drop_site, void* out_act2, unsigned drop_site2, const void* aux_act, unsigned drop_site_aux, void* stream) {
+  GemmArgs g{};
+  g.A = A; g.W = W; g.M = M; g.N = N; g.K = K; g.bias = bias; g.alpha = alpha; g.act = GEMM_ACT_NONE;
+  g.residual = residual; g.ld_res = N; g.out_f32 = out_f32; g.ld_out = N; g.out_act = out_act; g.ld_act = N;
+  g.drop_ctr = drop_counter; g.drop_p = drop_p; g.drop_site = drop_site;
+  g.out_act2 = out_act2; g.ld_act2 = N; g.drop_site2 = drop_site2;
+  g.aux_act = aux_act; g.aux_mode = aux_act != nullptr ? 1 : 0; g.drop_site_aux = drop_site_aux;
   return launch_gemm(precision, g, reinterpret_cast<cudaStream_t>(stream));
 }
 int ec_attention_operand_kind(int precision, int dim, int heads, int group) {

@@ -51,6 +51,11 @@ struct GemmDev {
   int has_ln_out;
   int dbg;
   void* copy_out; int copy_stride, frames_per_seq, frames_out_per_seq;   // strided compaction of `out` (LN mode 1), activation type
+  // training-step epilogue (plain variant): counter-based dropout / Swish side output / Swish-dropout backward (see GemmArgs)
+  const unsigned long long* drop_ctr; unsigned drop_keep16; float drop_inv_keep;
+  unsigned drop_site, drop_site2, drop_site_aux;
+  int has_out_act2, aux_mode;
+  int res_tx;        // bytes of one residual / aux slab (4096; 2048 for a bf16 aux operand)
 };
 
 // Optional in-kernel timeline (SM clock stamps of CTA (0,0)), enabled through ec_debug_gemm_timeline for latency studies.
@@ -71,7 +76,8 @@ template <typename T, bool kLN>
 __global__ void __launch_bounds__(576, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmOutF,
-               const __grid_constant__ CUtensorMap tmOutA, const __grid_constant__ CUtensorMap tmLn, const GemmDev p) {
+               const __grid_constant__ CUtensorMap tmOutA, const __grid_constant__ CUtensorMap tmLn, const __grid_constant__ CUtensorMap tmOutA2,
+               const GemmDev p) {
   using Tr = ActTraits<T>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -203,7 +209,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int rmask = rdepth - 1;
     auto res_slab = [&](int i) { return res_direct ? wstage + (half + i * kHalves) * kSlabBytes : my_res + (i & rmask) * kSlabBytes; };
     auto issue_res = [&](int i) {
-      mbar_arrive_expect_tx(res_bar(ew, i & rmask), kSlabBytes);
+      mbar_arrive_expect_tx(res_bar(ew, i & rmask), static_cast<uint32_t>(p.res_tx));
       tma_load_2d(smem_u32(res_slab(i)), &tmRes, res_bar(ew, i & rmask), out_col0 + (half + i * kHalves) * 32, row0);
     };
     if (p.has_res && !res_direct && lane == 0) {
@@ -214,6 +220,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int kASlab = sizeof(T) == 4 ? kSlabBytes : kSlabBytes / 2;
     const int nbuf = p.nbuf;
     uint8_t* slabA = wstage + (kLN ? n_chunks : (p.has_out_f32 ? nbuf : 0)) * kSlabBytes + (kLN ? half * nbuf * kASlab : 0);
+    uint8_t* slabA2 = slabA + nbuf * kASlab;                 // second activation-type output (plain variant, training step)
+    // counter-based dropout: keys of the three possible sites; element index = row * N + column (groups of 4 share one 64-bit draw)
+    unsigned long long key_out = 0, key_act2 = 0, key_aux = 0;
+    if (!kLN && p.drop_ctr != nullptr) {
+      if (p.drop_site) key_out = site_key(p.drop_ctr, p.drop_site);
+      if (p.drop_site2) key_act2 = site_key(p.drop_ctr, p.drop_site2);
+      if (p.drop_site_aux) key_aux = site_key(p.drop_ctr, p.drop_site_aux);
+    }
+    const unsigned long long grow = static_cast<unsigned long long>(row0 + lane) * static_cast<unsigned long long>(n_limit);
     float* stat_x = vecs + 5 * kVecFloats;                   // [stage 2][sub 4][quarter 4][lane 32][3]
     const bool batch = p.epi_batch != 0;
     float mean = 0.f, m2 = 0.f, cnt = 0.f;                   // running LayerNorm statistics of this thread's row
@@ -255,7 +270,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) t[j] = swish_fn<T>(t[j]);
       }
-      if (p.has_res) {
+      if constexpr (!kLN) {
+        if (i >= nbuf) {                                   // the stores issued nbuf chunks ago (one bulk group per chunk) have drained this buffer
+          if (lane == 0) { if (nbuf > 1) bulk_wait_read(nbuf - 1); else bulk_wait_read0(); }
+          __syncwarp();
+        }
+        const unsigned long long g0 = (grow + static_cast<unsigned long long>(out_col0 + c0)) >> 2;   // first 4-element group of this chunk
+        if (p.has_out_act2) {
+          // side output h = dropout(Swish(z)) with z as the backward will read it (rounded to the activation type)
+          float h[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) h[j] = swish_fn<T>(Tr::from(Tr::to(t[j])));
+          if (p.drop_site2) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const unsigned long long draw = splitmix64(key_act2 + g0 + j4);
+#pragma unroll
+              for (int l = 0; l < 4; ++l) h[4 * j4 + l] *= keep_factor(draw, l, p.drop_keep16, p.drop_inv_keep);
+            }
+          }
+          slab_store_act<T>(slabA2 + (i & (nbuf - 1)) * kASlab, lane, h);
+        }
+        if (p.aux_mode == 1) {
+          // data gradient through dropout(Swish(z)): acc * keep / (1 - p) * d/dz (z sigmoid z); z tile arrives through the residual ring
+          mbar_wait(res_bar(ew, i & rmask), (i / rdepth) & 1);
+          float zz[32];
+          slab_load_act<T>(res_slab(i), lane, zz);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float sg = fast_sigmoid(zz[j]);
+            t[j] *= sg + zz[j] * sg * (1.f - sg);
+          }
+          if (p.drop_site_aux) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const unsigned long long draw = splitmix64(key_aux + g0 + j4);
+#pragma unroll
+              for (int l = 0; l < 4; ++l) t[4 * j4 + l] *= keep_factor(draw, l, p.drop_keep16, p.drop_inv_keep);
+            }
+          }
+          __syncwarp();
+          if (lane == 0 && i + rdepth < my_chunks) issue_res(i + rdepth);
+        }
+        if (p.drop_site) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const unsigned long long draw = splitmix64(key_out + g0 + j4);
+#pragma unroll
+            for (int l = 0; l < 4; ++l) t[4 * j4 + l] *= keep_factor(draw, l, p.drop_keep16, p.drop_inv_keep);
+          }
+        }
+      }
+      if (p.has_res && (kLN || p.aux_mode == 0)) {
         mbar_wait(res_bar(ew, i & rmask), (i / rdepth) & 1);
         float rr[32];
         slab_load_f32(res_slab(i), lane, rr);
@@ -289,10 +355,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else {
         const int buf = i & (nbuf - 1);
-        if (i >= nbuf) {                                   // the stores issued nbuf chunks ago have drained this buffer
-          if (lane == 0) { if (nbuf > 1) bulk_wait_read(nbuf - 1); else bulk_wait_read0(); }
-          __syncwarp();
-        }
         uint8_t* sf = wstage + buf * kSlabBytes;
         uint8_t* sa = slabA + buf * kASlab;
         if (p.has_out_f32) slab_store_f32(sf, lane, t);
@@ -306,6 +368,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) {
             if (p.has_out_f32) tma_store_2d(&tmOutF, smem_u32(sf), out_col0 + c0, row0);
             if (p.has_out_act) tma_store_2d(&tmOutA, smem_u32(sa), out_col0 + c0, row0);
+            if (p.has_out_act2) tma_store_2d(&tmOutA2, smem_u32(slabA2 + buf * kASlab), out_col0 + c0, row0);
             bulk_commit();
           }
         }
@@ -318,6 +381,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int c = half; c < n_chunks; c += kHalves) {
           if (kLN || p.has_out_f32) tma_store_2d(&tmOutF, smem_u32(wstage + c * kSlabBytes), out_col0 + c * 32, row0);
           if (!kLN && p.has_out_act) tma_store_2d(&tmOutA, smem_u32(slabA + c * kASlab), out_col0 + c * 32, row0);
+          if (!kLN && p.has_out_act2) tma_store_2d(&tmOutA2, smem_u32(slabA2 + c * kASlab), out_col0 + c * 32, row0);
         }
         bulk_commit();
       }
@@ -473,12 +537,24 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
     tiles_n = cdiv(a.N, p.block_n);
   }
   p.num_k_blocks = cdiv(a.K, Tr::kBlockK);
-  p.has_res = a.residual != nullptr; p.has_out_f32 = a.out_f32 != nullptr; p.has_out_act = a.out_act != nullptr;
+  p.has_res = (a.residual != nullptr || a.aux_mode != 0); p.has_out_f32 = a.out_f32 != nullptr; p.has_out_act = a.out_act != nullptr;
+  p.has_out_act2 = a.out_act2 != nullptr; p.aux_mode = a.aux_mode;
+  p.res_tx = (a.aux_mode != 0 && sizeof(T) == 2) ? kSlabBytes / 2 : kSlabBytes;
+  const bool train_epi = a.drop_ctr != nullptr || a.out_act2 != nullptr || a.aux_mode != 0;
+  if (train_epi) {
+    EC_REQUIRE(!kLN && a.glu_nb == 0, "the training epilogue options belong to the plain GEMM");
+    EC_REQUIRE(a.N % 4 == 0, "dropout masks are drawn in groups of 4 consecutive elements: N must be a multiple of 4");
+    EC_REQUIRE(a.aux_mode == 0 || (a.aux_mode == 1 && a.aux_act != nullptr && a.residual == nullptr), "aux_mode 1 needs the saved pre-activation and no residual");
+    EC_REQUIRE((a.drop_site | a.drop_site2 | a.drop_site_aux) == 0 || (a.drop_ctr != nullptr && a.drop_p >= 0.f && a.drop_p < 1.f), "dropout site without a counter / bad p");
+    EC_REQUIRE(a.out_act2 == nullptr || (a.out_act != nullptr && a.act == GEMM_ACT_NONE && !a.act_f16), "the Swish side output comes with the pre-activation output");
+    p.drop_ctr = a.drop_ctr; p.drop_keep16 = keep16_of(a.drop_p); p.drop_inv_keep = 65536.f / static_cast<float>(p.drop_keep16);
+    p.drop_site = a.drop_site; p.drop_site2 = a.drop_site2; p.drop_site_aux = a.drop_site_aux;
+  }
   const int stage_bytes = kATileBytes + (IsSplit<T>::value ? 2 : 1) * p.block_n * 128;
   const int n_chunks = cdiv(std::min(a.glu_nb > 0 ? a.glu_nb : p.block_n, out_cols), 32);
   const int a_slab = sizeof(T) == 4 ? kSlabBytes : kSlabBytes / 2;
   static const int epi_batch_env = [] { const char* e = getenv("EFFCONF_EPI_BATCH"); return (e != nullptr && e[0] == '1') ? 1 : 0; }();
-  const int per_chunk = (p.has_out_f32 ? kSlabBytes : 0) + (p.has_out_act ? a_slab : 0);
+  const int per_chunk = (p.has_out_f32 ? kSlabBytes : 0) + (p.has_out_act ? a_slab : 0) + (p.has_out_act2 ? a_slab : 0);
   p.res_depth = 1;
   if (kLN) {
     // per row quarter: persistent x slabs (one per chunk) + ln_out slabs for each of its four warps (one per owned chunk when
@@ -542,7 +618,7 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
     EC_REQUIRE(a.copy_out == nullptr || a.ln_mode == 1, "the strided copy is only available with a single LayerNorm");
   }
 
-  CUtensorMap tmA, tmB, tmB2, tmRes, tmOutF, tmOutA, tmLn;
+  CUtensorMap tmA, tmB, tmB2, tmRes, tmOutF, tmOutA, tmLn, tmOutA2;
   EC_TRY(make_operand_map(&tmA, precision, a.A, a.M, a.K, kBlockM));
   EC_TRY(make_operand_map(&tmB, precision, a.W, a.N, a.K, p.block_n));
   tmB2 = tmB;
@@ -551,8 +627,10 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
     EC_TRY(make_operand_map(&tmB2, precision, twin, a.N, a.K, p.block_n));
   }
   const bool act_f32 = sizeof(T) == 4;
-  tmRes = tmA; tmOutF = tmA; tmOutA = tmA; tmLn = tmA;       // placeholders for unused maps
+  tmRes = tmA; tmOutF = tmA; tmOutA = tmA; tmLn = tmA; tmOutA2 = tmA;       // placeholders for unused maps
   if (a.residual != nullptr) EC_TRY(make_slab_map(&tmRes, true, a.residual, a.M, out_cols, a.ld_res));
+  if (a.aux_mode != 0) EC_TRY(make_slab_map(&tmRes, act_f32, a.aux_act, a.M, out_cols, out_cols));
+  if (a.out_act2 != nullptr) EC_TRY(make_slab_map(&tmOutA2, act_f32, a.out_act2, a.M, out_cols, a.ld_act2));
   if (a.out_f32 != nullptr) EC_TRY(make_slab_map(&tmOutF, true, a.out_f32, a.M, out_cols, a.ld_out));
   if (a.out_act != nullptr) EC_TRY(make_slab_map(&tmOutA, act_f32 && !p.act_f16, a.out_act, a.M, out_cols, a.ld_act));
   if (kLN && a.ln_out != nullptr) EC_TRY(make_slab_map(&tmLn, act_f32, a.ln_out, a.M, a.N, a.N));
@@ -572,7 +650,7 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   });
   EC_CUDA(attr_err);
   dim3 grid(cdiv(a.M, kBlockM), tiles_n);
-  EC_TRY(launch_pdl(gemm_tc_kernel<T, kLN>, grid, dim3(576), smem, stream, tmA, tmB, tmB2, tmRes, tmOutF, tmOutA, tmLn, p));
+  EC_TRY(launch_pdl(gemm_tc_kernel<T, kLN>, grid, dim3(576), smem, stream, tmA, tmB, tmB2, tmRes, tmOutF, tmOutA, tmLn, tmOutA2, p));
   return EC_OK;
 }
 

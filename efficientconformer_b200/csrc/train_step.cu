@@ -12,25 +12,7 @@
 
 namespace ec {
 
-namespace {
-__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
-  x += 0x9E3779B97F4A7C15ull;
-  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-  return x ^ (x >> 31);
-}
-// one 64-bit draw covers 4 consecutive elements (16 bits each): keep iff bits < keep16
-__device__ __forceinline__ unsigned long long site_key(const unsigned long long* ctr, unsigned site) {
-  return splitmix64(ctr[0] ^ (ctr[1] * 0xD1B54A32D192ED03ull)) ^ (static_cast<unsigned long long>(site) * 0x9FB21C651E98DF25ull);
-}
-__device__ __forceinline__ float keep_factor(unsigned long long draw, int lane, unsigned keep16, float inv_keep) {
-  return ((draw >> (16 * lane)) & 0xFFFFull) < keep16 ? inv_keep : 0.f;
-}
-}  // namespace
 inline int grid_for(size_t n) { return static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16)); }
-namespace {
-}  // namespace
-
 __global__ void dropout_advance_kernel(unsigned long long* ctr) { ctr[1] += 1ull; }
 
 // dst[i] = TOut(scale * keep(i) / (1 - p) * src[i]); each thread owns groups of 4 consecutive elements
@@ -84,10 +66,6 @@ __global__ void __launch_bounds__(256) dropout_residual_kernel(const float* __re
   }
 }
 
-static unsigned keep16_of(float p) {
-  const double keep = (1.0 - static_cast<double>(p)) * 65536.0;
-  return static_cast<unsigned>(std::min(65536.0, std::max(1.0, keep + 0.5)));
-}
 
 int launch_dropout_advance(unsigned long long* ctr, cudaStream_t st) {
   dropout_advance_kernel<<<1, 1, 0, st>>>(ctr);

@@ -83,6 +83,28 @@ def gemm(a_act, w_act, bias, precision, alpha=1.0, act=0, residual=None, want_f3
     return of, oa
 
 
+def gemm_train(a_act, w_act, bias, precision, drop=None, alpha=1.0, residual=None, want_f32=True, want_act=False, site=0, want_act2=False,
+               site2=0, aux=None, site_aux=0):
+    """Training-step GEMM with the surrounding element work in its epilogue (ec_op_gemm_train):
+        z = a @ w^T + bias;  out_act = act(z);  out_act2 = act(dropout_site2(Swish(out_act)));
+        aux given: z <- z * dropout_site_aux-mask * Swish'(aux)  (data gradient through dropout(Swish));
+        out_f32 = alpha * dropout_site(z) + residual.
+    `drop` is the DropoutState (None or p == 0: the sites are ignored).  Returns (out_f32, out_act, out_act2)."""
+    pr = _p(precision)
+    M, K = a_act.shape
+    N = w_act.shape[0]
+    live = drop is not None and drop.p > 0.0
+    ctr = drop.counter if live else None
+    p = drop.p if live else 0.0
+    s0, s2, sa = (site, site2, site_aux) if live else (0, 0, 0)
+    of = torch.empty(M, N, dtype=torch.float32, device=a_act.device) if want_f32 else None
+    oa = torch.empty(M, N, dtype=act_dtype(pr), device=a_act.device) if want_act else None
+    o2 = torch.empty(M, N, dtype=act_dtype(pr), device=a_act.device) if want_act2 else None
+    check(lib().ec_op_gemm_train(pr, ptr(a_act), ptr(w_act), M, N, K, ptr(bias), alpha, ptr(residual), ptr(of), ptr(oa), ptr(ctr), p, s0,
+                                 ptr(o2), s2, ptr(aux), sa, stream_ptr()))
+    return of, oa, o2
+
+
 def gemm_ln(a_act, w_act, bias, precision, g1, b1, g2=None, b2=None, mode=1, alpha=1.0, residual=None, eps=1e-6,
             copy_stride=0, frames_per_seq=0):
     """GEMM with the fused LayerNorm epilogue.  Returns (out_f32, ln_out_act, copy_out_act or None)."""
@@ -174,17 +196,29 @@ def subsample_conv(mel, w_folded, b_folded, precision):
 
 
 # ---- backward operators (training step) --------------------------------------------------------------------------------
-def layernorm_bwd(x, dy, gamma, eps=1e-6, dx_accum=None):
-    """x, dy [rows, dim] fp32 -> (dx, dgamma, dbeta).  dx_accum: fp32 tensor the x-gradient is ADDED to (residual branch)."""
+def layernorm_bwd(x, dy, gamma, eps=1e-6, dx_accum=None, emit=None):
+    """x, dy [rows, dim] fp32 -> (dx, dgamma, dbeta).  dx_accum: fp32 tensor the x-gradient is ADDED to (residual branch).
+    emit = (precision, scale, drop, site): also returns, as a 4th value, the activation-type tensor
+    act(scale * dropout_site-mask * dx_total) -- the operand dropout_cast_scaled(dx_total, ...) would produce in a separate pass
+    (drop None or p == 0: a plain scaled cast)."""
     x, dy = x.float().contiguous(), dy.float().contiguous()
     rows, dim = x.numel() // x.shape[-1], x.shape[-1]
     dx = dx_accum if dx_accum is not None else torch.empty_like(x)
     dg = torch.empty(dim, dtype=torch.float32, device=x.device)
     db = torch.empty(dim, dtype=torch.float32, device=x.device)
     work = torch.empty(lib().ec_op_layernorm_bwd_work_bytes(dim), dtype=torch.uint8, device=x.device)
-    check(lib().ec_op_layernorm_bwd(ptr(x), ptr(dy), rows, dim, ptr(gamma.float().contiguous()), eps, ptr(dx), 1 if dx_accum is not None else 0,
-                                    ptr(dg), ptr(db), ptr(work), stream_ptr()))
-    return dx, dg, db
+    if emit is None:
+        check(lib().ec_op_layernorm_bwd(ptr(x), ptr(dy), rows, dim, ptr(gamma.float().contiguous()), eps, ptr(dx), 1 if dx_accum is not None else 0,
+                                        ptr(dg), ptr(db), ptr(work), stream_ptr()))
+        return dx, dg, db
+    precision, scale, drop, site = emit
+    pr = _p(precision)
+    live = drop is not None and drop.p > 0.0
+    out = torch.empty(x.shape, dtype=act_dtype(pr), device=x.device)
+    check(lib().ec_op_layernorm_bwd_emit(ptr(x), ptr(dy), rows, dim, ptr(gamma.float().contiguous()), eps, ptr(dx), 1 if dx_accum is not None else 0,
+                                         ptr(dg), ptr(db), ptr(work), pr, ptr(out), float(scale), ptr(drop.counter) if live else None,
+                                         drop.p if live else 0.0, site if live else 0, stream_ptr()))
+    return dx, dg, db, out
 
 
 def colsum(m, precision, is_f32=None):

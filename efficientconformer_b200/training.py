@@ -24,6 +24,15 @@ from .encoders import relative_sinusoid_rows
 
 _ops = _ops_module       # test seam: tests/test_train_glue_cpu.py swaps in a torch-CPU operator table to check the tape logic
 
+# Which element operators are folded into the GEMM epilogues (ec_op_gemm_train) instead of running as their own bandwidth kernels:
+#   w1   feed-forward W1: pre-activation z and dropout(Swish(z)) from one epilogue
+#   res  dropout + alpha + residual behind W2 / attention output / pointwise conv 2 / encoder.linear
+#   dz   Swish-dropout backward in the data-gradient GEMM of W2
+#   ln   every LayerNorm backward also emits the masked, scaled, activation-type operand of the next GEMM of the backward chain
+# Chosen by measurement on the B200 (profiles/r2); EFFCONF_TRAIN_FUSE=w1,res,dz overrides.
+import os as _os
+FUSE = set(filter(None, _os.environ.get("EFFCONF_TRAIN_FUSE", "w1,res,dz,ln").split(",")))
+
 
 class DropoutState:
     """Counter-based dropout: mask bit of element i of site s at step n = hash(seed, n, s, i) < keep.  The step counter lives on the
@@ -174,9 +183,11 @@ class TrainingPath:
         if mel_len is not None:
             cur_len = _len_after_stride(mel_len, 2)
         w_lin = self._w(enc.linear.weight, pr)
-        x = o.gemm(a, w_lin, enc.linear.bias, pr)[0]                           # (B*T0, D0) fp32
         site0 = drop.next_site()
-        x = o.dropout_f32(x, drop, site0)
+        if "res" in FUSE:
+            x = o.gemm_train(a, w_lin, enc.linear.bias, pr, drop, site=site0)[0]   # (B*T0, D0) fp32, dropout in the epilogue
+        else:
+            x = o.dropout_f32(o.gemm(a, w_lin, enc.linear.bias, pr)[0], drop, site0)
         tape["front"] = (a, sub_saved, w_lin, site0)
 
         Tc = T0
@@ -201,41 +212,58 @@ class TrainingPath:
         tape["T_out"] = Tc
         return x.view(B, Tc, D_last), logits, cur_len, tape
 
+    def _proj_drop_res(self, a_act, w_act, bias, pr, drop, site, alpha, residual):
+        """residual + alpha * dropout_site(a W^T + bias): one GEMM with the dropout in its epilogue, or GEMM + element kernel."""
+        o = _ops
+        if "res" in FUSE or drop.p == 0.0:
+            return o.gemm_train(a_act, w_act, bias, pr, drop, alpha=alpha, residual=residual, site=site)[0]
+        return o.dropout_residual(o.gemm(a_act, w_act, bias, pr)[0], drop, site, alpha, residual)
+
     def _ffn_forward(self, holder, x, pr, drop, alpha=0.5):
         """reference models/modules.py:378-395 + the half-step residual of models/blocks.py:122,132."""
         o = _ops
         L = holder.layers
         h0 = o.layernorm(x, L[0].weight, L[0].bias, pr, want_f32=False, want_act=True)[0]
         w1 = self._w(L[1].weight, pr)
-        z = o.gemm(h0, w1, L[1].bias, pr, want_f32=False, want_act=True)[1]
         s1 = drop.next_site()
-        s = o.swish_dropout_fwd(z, drop, s1, pr)
+        # W1: the pre-activation z (kept for the backward) and s = dropout(Swish(z)) leave the same epilogue
+        if "w1" in FUSE:
+            _, z, s = o.gemm_train(h0, w1, L[1].bias, pr, drop, want_f32=False, want_act=True, want_act2=True, site2=s1)
+        else:
+            z = o.gemm(h0, w1, L[1].bias, pr, want_f32=False, want_act=True)[1]
+            s = o.swish_dropout_fwd(z, drop, s1, pr)
         w2 = self._w(L[4].weight, pr)
         s2 = drop.next_site()
-        if drop.p > 0.0:
-            y = o.gemm(s, w2, L[4].bias, pr)[0]
-            out = o.dropout_residual(y, drop, s2, alpha, x)
-        else:
-            out = o.gemm(s, w2, L[4].bias, pr, alpha=alpha, residual=x)[0]
+        # W2: x + alpha * dropout(s W2^T + b2) in the epilogue
+        out = self._proj_drop_res(s, w2, L[4].bias, pr, drop, s2, alpha, x)
         return out, (x, h0, z, s, s1, s2, alpha)
 
-    def _ffn_backward(self, holder, saved, d_out, pr, grads, prefix):
-        """d_out: gradient w.r.t. the module output (fp32, modified in place); returns the gradient w.r.t. its input x."""
+    def _ffn_backward(self, holder, saved, d_out, pr, grads, prefix, dy=None, emit_next=None):
+        """d_out: gradient w.r.t. the module output (fp32, modified in place); returns the gradient w.r.t. its input x.
+        dy: the activation-type operand alpha * dropout_s2-mask * d_out when the producer of d_out already emitted it (LayerNorm
+        backward, ops.layernorm_bwd(emit=...)).  emit_next = (scale, site): also return that operand for the next consumer of dx."""
         o = _ops
         x, h0, z, s, s1, s2, alpha = saved
         L = holder.layers
         drop = self._drop
-        dy = o.dropout_cast_scaled(d_out, pr, alpha, drop, s2)                 # d(W2 output) in the activation type
+        if dy is None:
+            dy = o.dropout_cast_scaled(d_out, pr, alpha, drop, s2)             # d(W2 output) in the activation type
         dw_, db_ = self._wgrad(dy, s, pr)
         grads[f"{prefix}.layers.4.weight"], grads[f"{prefix}.layers.4.bias"] = dw_, db_
-        ds = self._dgrad(dy, L[4].weight, pr)
-        dz = o.swish_dropout_bwd(z, ds, drop, s1, pr)
+        # dz = dropout-mask * Swish'(z) * (dy W2) in the data-gradient GEMM's epilogue, straight into the activation type
+        if "dz" in FUSE:
+            dz = o.gemm_train(dy, self._wt(L[4].weight, pr), None, pr, drop, want_f32=False, want_act=True, aux=z, site_aux=s1)[1]
+        else:
+            dz = o.swish_dropout_bwd(z, self._dgrad(dy, L[4].weight, pr), drop, s1, pr)
         dw_, db_ = self._wgrad(dz, h0, pr)
         grads[f"{prefix}.layers.1.weight"], grads[f"{prefix}.layers.1.bias"] = dw_, db_
         dh0 = self._dgrad(dz, L[1].weight, pr)
-        dx, dg, db = o.layernorm_bwd(x, dh0, L[0].weight, dx_accum=d_out)
+        if emit_next is not None and "ln" in FUSE:
+            dx, dg, db, dnext = o.layernorm_bwd(x, dh0, L[0].weight, dx_accum=d_out, emit=(pr, emit_next[0], drop, emit_next[1]))
+        else:
+            (dx, dg, db), dnext = o.layernorm_bwd(x, dh0, L[0].weight, dx_accum=d_out), None
         grads[f"{prefix}.layers.0.weight"], grads[f"{prefix}.layers.0.bias"] = dg, db
-        return dx
+        return dx, dnext
 
     def _block_forward(self, blk, spec, x, B, T, cur_len, pr, drop, want_act_out):
         o = _ops
@@ -256,11 +284,7 @@ class TrainingPath:
         att = o.relpos_attention_act(qkv.view(B, T, 3 * D), E, m.mhsa.u, m.mhsa.v, cur_len, H, G, pr)
         wo = self._w(m.mhsa.output_layer.weight, pr)
         s_att = drop.next_site()
-        if drop.p > 0.0:
-            y = o.gemm(att.view(B * T, D), wo, m.mhsa.output_layer.bias, pr)[0]
-            x2 = o.dropout_residual(y, drop, s_att, 1.0, x1)
-        else:
-            x2 = o.gemm(att.view(B * T, D), wo, m.mhsa.output_layer.bias, pr, residual=x1)[0]
+        x2 = self._proj_drop_res(att.view(B * T, D), wo, m.mhsa.output_layer.bias, pr, drop, s_att, 1.0, x1)
         # ---- convolution module (reference models/modules.py:507-525) + block residual (blocks.py:98-114,129)
         Lc = blk.convolution_module.layers
         c_in = o.layernorm(x2, Lc[0].weight, Lc[0].bias, pr, want_f32=False, want_act=True)[0]
@@ -280,11 +304,7 @@ class TrainingPath:
             res = x2
         wpw2 = self._w(Lc[7].weight, pr)
         s_conv = drop.next_site()
-        if drop.p > 0.0:
-            y = o.gemm(h.view(B * To, De), wpw2, Lc[7].bias, pr)[0]
-            x3 = o.dropout_residual(y, drop, s_conv, 1.0, res)
-        else:
-            x3 = o.gemm(h.view(B * To, De), wpw2, Lc[7].bias, pr, residual=res)[0]
+        x3 = self._proj_drop_res(h.view(B * To, De), wpw2, Lc[7].bias, pr, drop, s_conv, 1.0, res)
         x4, ffn2 = self._ffn_forward(blk.feed_forward_module2, x3, pr, drop)
         x_act, x5 = o.layernorm(x4, blk.norm.weight, blk.norm.bias, pr, want_f32=True, want_act=want_act_out)
         tape = dict(ffn1=ffn1, x1=x1, a_in=a_in, qkv=qkv, qkv_handle=qkv_handle, E=E, R=R, att=att, cur_len=cur_len, s_att=s_att, x2=x2, c_in=c_in, zg=zg,
@@ -310,10 +330,14 @@ class TrainingPath:
             dx = self._dgrad(dl, self.head.weight, pr, residual=dx)
         if dx is None:
             raise RuntimeError("backward needs a gradient for the encoder output or the logits")
-        for i in reversed(range(len(self.specs))):
-            dx = self._block_backward(enc.blocks[i], self.specs[i], tape["blocks"][i], dx, B, pr, grads, f"encoder.blocks.{i}")
         a, sub_saved, w_lin, site0 = tape["front"]
-        d_act = o.dropout_cast_scaled(dx, pr, 1.0, self._drop, site0)
+        d_act = None
+        for i in reversed(range(len(self.specs))):
+            # block 0 hands the front end its operand (dropout mask of encoder.linear's dropout re-applied)
+            dx, d_act = self._block_backward(enc.blocks[i], self.specs[i], tape["blocks"][i], dx, B, pr, grads, f"encoder.blocks.{i}",
+                                             emit_next=(1.0, site0) if i == 0 else None)
+        if d_act is None:
+            d_act = o.dropout_cast_scaled(dx, pr, 1.0, self._drop, site0)
         dw_, db_ = self._wgrad(d_act, a, pr)
         grads["encoder.linear.weight"], grads["encoder.linear.bias"] = dw_, db_
         da = self._dgrad(d_act, enc.linear.weight, pr)
@@ -323,19 +347,29 @@ class TrainingPath:
         self._join_side(da.device)               # every weight gradient is complete before the caller reads `grads`
         return grads
 
-    def _block_backward(self, blk, spec, t, d_out, B, pr, grads, p):
+    def _block_backward(self, blk, spec, t, d_out, B, pr, grads, p, emit_next=None):
+        """Returns (gradient w.r.t. the block input, its emitted operand for `emit_next` or None).  Every LayerNorm backward of the
+        chain also emits the activation-type, dropout-masked operand its consumer needs ("ln" in FUSE), which used to be one
+        ec_op_dropout pass per site."""
         o = _ops
         D, De, H, G, st = spec.dim_model, spec.dim_expand, spec.num_heads, spec.group_size, spec.conv_stride
         T, To = t["T"], t["To"]
         drop = self._drop
+        fuse_ln = "ln" in FUSE
         # block LayerNorm (reference models/blocks.py:135)
-        dx4, dg, db = o.layernorm_bwd(t["x4"], d_out, blk.norm.weight)
+        ffn2 = t["ffn2"]
+        if fuse_ln:
+            dx4, dg, db, dy_ffn2 = o.layernorm_bwd(t["x4"], d_out, blk.norm.weight, emit=(pr, ffn2[6], drop, ffn2[5]))
+        else:
+            (dx4, dg, db), dy_ffn2 = o.layernorm_bwd(t["x4"], d_out, blk.norm.weight), None
         grads[f"{p}.norm.weight"], grads[f"{p}.norm.bias"] = dg, db
-        dx3 = self._ffn_backward(blk.feed_forward_module2, t["ffn2"], dx4, pr, grads, f"{p}.feed_forward_module2")
+        dx3, dy = self._ffn_backward(blk.feed_forward_module2, ffn2, dx4, pr, grads, f"{p}.feed_forward_module2", dy=dy_ffn2,
+                                     emit_next=(1.0, t["s_conv"]))
         # convolution module + residual
         Lc = blk.convolution_module.layers
         c = f"{p}.convolution_module.layers"
-        dy = o.dropout_cast_scaled(dx3, pr, 1.0, drop, t["s_conv"])            # gradient of the pw2 output (after its dropout)
+        if dy is None:
+            dy = o.dropout_cast_scaled(dx3, pr, 1.0, drop, t["s_conv"])        # gradient of the pw2 output (after its dropout)
         h2 = t["h"].view(B * To, De)
         dw_, db_ = self._wgrad(dy, h2, pr)
         grads[f"{c}.7.weight"], grads[f"{c}.7.bias"] = dw_.view(De, De, 1), db_
@@ -357,12 +391,15 @@ class TrainingPath:
             o.strided_rows_bwd(dxs.view(B, To, D), acc.view(B, T, D), st)
         else:
             acc = dx3                                                         # identity residual: gradient passes straight through
-        dx2, dg, db = o.layernorm_bwd(t["x2"], dc_in, Lc[0].weight, dx_accum=acc)
+        if fuse_ln:
+            dx2, dg, db, do = o.layernorm_bwd(t["x2"], dc_in, Lc[0].weight, dx_accum=acc, emit=(pr, 1.0, drop, t["s_att"]))
+        else:
+            dx2, dg, db = o.layernorm_bwd(t["x2"], dc_in, Lc[0].weight, dx_accum=acc)
+            do = o.dropout_cast_scaled(dx2, pr, 1.0, drop, t["s_att"])
         grads[f"{c}.0.weight"], grads[f"{c}.0.bias"] = dg, db
         # attention module
         m = blk.multi_head_self_attention_module
         a = f"{p}.multi_head_self_attention_module"
-        do = o.dropout_cast_scaled(dx2, pr, 1.0, drop, t["s_att"])
         att2 = t["att"].view(B * T, D)
         dw_, db_ = self._wgrad(do, att2, pr)
         grads[f"{a}.mhsa.output_layer.weight"], grads[f"{a}.mhsa.output_layer.bias"] = dw_, db_
@@ -379,9 +416,13 @@ class TrainingPath:
             grads[f"{a}.mhsa.{nm}_layer.weight"] = dwqkv[j * D:(j + 1) * D]
             grads[f"{a}.mhsa.{nm}_layer.bias"] = dbqkv[j * D:(j + 1) * D]
         da_in = self._qkv_dgrad(dqkv_act, t["qkv_handle"], pr)
-        dx1, dg, db = o.layernorm_bwd(t["x1"], da_in, m.norm.weight, dx_accum=dx2)
+        ffn1 = t["ffn1"]
+        if fuse_ln:
+            dx1, dg, db, dy_ffn1 = o.layernorm_bwd(t["x1"], da_in, m.norm.weight, dx_accum=dx2, emit=(pr, ffn1[6], drop, ffn1[5]))
+        else:
+            (dx1, dg, db), dy_ffn1 = o.layernorm_bwd(t["x1"], da_in, m.norm.weight, dx_accum=dx2), None
         grads[f"{a}.norm.weight"], grads[f"{a}.norm.bias"] = dg, db
-        return self._ffn_backward(blk.feed_forward_module1, t["ffn1"], dx1, pr, grads, f"{p}.feed_forward_module1")
+        return self._ffn_backward(blk.feed_forward_module1, ffn1, dx1, pr, grads, f"{p}.feed_forward_module1", dy=dy_ffn1, emit_next=emit_next)
 
 
 class EncoderTrainFn(torch.autograd.Function):

@@ -208,6 +208,12 @@ int ec_op_wgrad_bias(int precision, const void* dy, const void* x, int M, int N,
 size_t ec_op_layernorm_bwd_work_bytes(int dim);
 int ec_op_layernorm_bwd(const float* x, const float* dy, int rows, int dim, const float* gamma, float eps, float* dx, int accumulate,
                         float* dgamma, float* dbeta, void* work, void* stream);
+/* same, plus (emit_out != NULL) the activation-type operand of the next GEMM of the backward chain:
+ * emit_out[r, c] = act_type(emit_scale * keep_{drop_site}/(1-p) * dx[r, c]) with dx the value AFTER the residual accumulation -- what
+ * ec_op_dropout (fp32 -> activation type, scaled) computed from dx in a separate pass; drop_counter NULL = no mask (plain scaled cast) */
+int ec_op_layernorm_bwd_emit(const float* x, const float* dy, int rows, int dim, const float* gamma, float eps, float* dx, int accumulate,
+                             float* dgamma, float* dbeta, void* work, int emit_precision, void* emit_out, float emit_scale,
+                             const unsigned long long* drop_counter, float drop_p, unsigned drop_site, void* stream);
 size_t ec_op_colsum_work_bytes(int cols);
 int ec_op_colsum(int precision, const void* m, int is_f32, int rows, int cols, float* out, void* work, void* stream);
 int ec_op_transpose_cast(int precision, const float* src, int rows, int cols, void* dst, void* stream);
@@ -277,6 +283,19 @@ int ec_op_gemm(int precision, const void* A, const void* W, int M, int N, int K,
 /* flags bit 0 (EC_PREC_BF16X2 only): out_act is written as PLAIN fp16 -- the q|k|v and E operands of the attention core in split mode */
 int ec_op_gemm_ex(int precision, const void* A, const void* W, int M, int N, int K, const float* bias, float alpha, int act,
                   const float* residual, float* out_f32, void* out_act, int flags, void* stream);
+/* Training-step GEMM with the element work of the surrounding nn.Dropout / Swish modules folded into its epilogue (reference
+ * models/modules.py:386-391 feed-forward module, :486 attention dropout, :521 conv-module dropout, models/encoders.py:119):
+ *   z        = A W^T + bias
+ *   out_act  = act_type(z)                                      (optional: the pre-activation the backward needs)
+ *   out_act2 = act_type(keep_{site2}/(1-p) * Swish(out_act))    (optional: Swish + the module's first dropout = operand of the next GEMM)
+ *   aux_act  : z <- z * keep_{site_aux}/(1-p) * Swish'(aux)     (optional: data gradient through dropout(Swish(.)), aux = saved pre-activation
+ *                                                                [M, N] in the activation type; excludes `residual`)
+ *   out_f32  = alpha * keep_{site}/(1-p) * z + residual         (optional; drop_site 0 = no dropout here)
+ * drop_counter = the device {seed, step} pair of ec_op_dropout_advance (NULL when every site is 0); masks are the same function of
+ * (seed, step, site, element = row * N + column) as ec_op_dropout / ec_op_swish_dropout draw, so either may compute a forward or a backward. */
+int ec_op_gemm_train(int precision, const void* A, const void* W, int M, int N, int K, const float* bias, float alpha,
+                     const float* residual, float* out_f32, void* out_act, const unsigned long long* drop_counter, float drop_p,
+                     unsigned drop_site, void* out_act2, unsigned drop_site2, const void* aux_act, unsigned drop_site_aux, void* stream);
 /* Storage of the q|k|v and E operands that ec_op_relpos_attention / _bwd read in this mode and head layout: 0 = the activation type,
  * 1 = bf16 (EC_PREC_BF16), 2 = fp16 (EC_PREC_BF16X2 when dim % 8 == 0 and the head dim G*dim/heads is even: the 16-bit mma.sync kernels
  * then run on fp16 operands -- 11 significant bits, TF32-grade accuracy at the bf16 rate -- and write the packed output). */

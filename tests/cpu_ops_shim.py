@@ -46,6 +46,21 @@ def gemm(a_act, w_act, bias, precision, alpha=1.0, act=0, residual=None, want_f3
     return (y if want_f32 else None), (y.clone() if want_act else None)
 
 
+def gemm_train(a_act, w_act, bias, precision, drop=None, alpha=1.0, residual=None, want_f32=True, want_act=False, site=0, want_act2=False,
+               site2=0, aux=None, site_aux=0):
+    assert drop is None or drop.p == 0.0
+    z = _d(a_act) @ _d(w_act).t()
+    if bias is not None:
+        z = z + _d(bias)
+    if aux is not None:
+        s = torch.sigmoid(_d(aux))
+        z = z * (s + _d(aux) * s * (1 - s))
+    y = alpha * z
+    if residual is not None:
+        y = y + _d(residual)
+    return (y if want_f32 else None), (z.clone() if want_act else None), (z * torch.sigmoid(z) if want_act2 else None)
+
+
 def swish_fwd(z, precision):
     return z * torch.sigmoid(z)
 
@@ -67,16 +82,21 @@ def glu_bwd(zg, dy, precision):
     return torch.cat([_d(dy) * s, _d(dy) * a * s * (1 - s)], dim=1)
 
 
-def layernorm_bwd(x, dy, gamma, eps=1e-6, dx_accum=None):
+def layernorm_bwd(x, dy, gamma, eps=1e-6, dx_accum=None, emit=None):
     xr = _d(x).clone().requires_grad_(True)
     g = _d(gamma).clone().requires_grad_(True)
     b = torch.zeros_like(g).requires_grad_(True)
     with torch.enable_grad():
         F.layer_norm(xr, (x.shape[-1],), g, b, eps).backward(_d(dy))
+    dx = xr.grad
     if dx_accum is not None:
         dx_accum += xr.grad                      # in place, like the kernel's accumulate flag
-        return dx_accum, g.grad, b.grad
-    return xr.grad, g.grad, b.grad
+        dx = dx_accum
+    if emit is not None:
+        precision, scale, drop, site = emit
+        assert drop is None or drop.p == 0.0
+        return dx, g.grad, b.grad, dx.clone() * scale
+    return dx, g.grad, b.grad
 
 
 def colsum(m, precision):

@@ -102,6 +102,18 @@ def test_layernorm_backward(ops):
         dx2, dg2, db2 = ops.layernorm_bwd(x.to(DEV), dy.to(DEV), gamma.to(DEV), dx_accum=acc)
         assert rel_l2(dx2, ref_acc) < 2e-5
         assert torch.equal(dg, dg2) and torch.equal(db, db2)
+        # the emitted operand of the next GEMM: act(scale * dropout mask * accumulated dx) == the separate ec_op_dropout pass on dx
+        if dim % 4 == 0:
+            for prec in ("bf16x2", "bf16", "tf32"):
+                if prec == "bf16" and dim % 8:
+                    continue
+                for p_drop in (0.0, 0.1):
+                    drop = type("D", (), {"p": p_drop, "counter": ops.dropout_counter(DEV, 5) if p_drop > 0 else None})()
+                    acc3 = acc.clone() if trial % 2 else None
+                    dx3, dg3, db3, em = ops.layernorm_bwd(x.to(DEV), dy.to(DEV), gamma.to(DEV), dx_accum=acc3, emit=(prec, 0.5, drop, 13))
+                    ref_em = ops.dropout_cast_scaled(dx3, prec, 0.5, drop, 13)
+                    assert torch.equal(ops.unpack(em, prec), ops.unpack(ref_em, prec)), (trial, rows, dim, prec, p_drop)
+                    assert torch.equal(dg3, dg) and torch.equal(db3, db)
 
 
 @pytest.mark.parametrize("prec", ["bf16x2", "tf32", "bf16"])

@@ -85,6 +85,60 @@ def test_gemm_exact_operands(ops, prec, M, N, K):
     assert rel_l2(out3, ref3) < 3 * tol, "swish"
 
 
+class _Drop:
+    """The DropoutState the operators take: p, device {seed, step} counter."""
+    def __init__(self, ops, p, seed=77):
+        self.p = p
+        self.counter = ops.dropout_counter(DEV, seed) if p > 0 else None
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+@pytest.mark.parametrize("M,N,K", [(16000, 480, 120), (8000, 168, 672), (4000, 240, 960), (999, 120, 120), (130, 504, 168), (1, 120, 480),
+                                   (333, 256, 240), (257, 96, 64)])
+def test_gemm_train_epilogues_match_the_element_kernels(ops, prec, p_drop, M, N, K):
+    """ec_op_gemm_train (dropout / Swish side output / Swish-dropout backward folded into the GEMM epilogue) against the unfused chain
+    GEMM -> element kernel it replaces: same masks (same counter hash), same values up to the fp32 rounding of one extra product."""
+    if prec == "bf16" and ((K * 2) % 16 or (N * 2) % 16):
+        pytest.skip("bf16 row pitch must be a multiple of 16 bytes")
+    g = torch.Generator(device="cpu").manual_seed(M * 5 + N * 3 + K)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV)
+    aa, ww = ops.cast(a, prec), ops.cast_weight(w, prec)
+    drop = _Drop(ops, p_drop)
+    # (1) projection + dropout + alpha + residual (feed-forward W2, attention output, pointwise conv 2, encoder.linear)
+    y = ops.gemm(aa, ww, bias, prec)[0]
+    ref = ops.dropout_residual(y, drop, 7, 0.5, res) if p_drop > 0 else 0.5 * y + res
+    out = ops.gemm_train(aa, ww, bias, prec, drop, alpha=0.5, residual=res, site=7)[0]
+    assert rel_l2(out, ref) < 1e-6
+    if p_drop > 0:
+        kept_ref, kept = (ref != res), (out != res)
+        assert torch.equal(kept_ref, kept)                         # the very same mask
+        assert abs(float(kept.float().mean()) - (1 - p_drop)) < 0.02 or M * N < 5000
+        ref_nores = ops.dropout_f32(y, drop, 9)
+        out_nores = ops.gemm_train(aa, ww, bias, prec, drop, site=9)[0]
+        assert rel_l2(out_nores, ref_nores) < 1e-6 and torch.equal(out_nores == 0, ref_nores == 0)
+    # (2) feed-forward W1: pre-activation z and s = dropout(Swish(z)) from one epilogue
+    z_ref = ops.gemm(aa, ww, bias, prec, want_f32=False, want_act=True)[1]
+    s_ref = ops.swish_dropout_fwd(z_ref, drop, 11, prec)
+    _, z, s = ops.gemm_train(aa, ww, bias, prec, drop, want_f32=False, want_act=True, want_act2=True, site2=11)
+    assert torch.equal(z.view(torch.int32) if z.dtype == torch.float32 else z.view(torch.int16),
+                       z_ref.view(torch.int32) if z.dtype == torch.float32 else z_ref.view(torch.int16))
+    sv, sv_ref = ops.unpack(s, prec), ops.unpack(s_ref, prec)
+    assert torch.equal(sv == 0, sv_ref == 0) or p_drop == 0
+    assert rel_l2(sv, sv_ref) < (1e-2 if prec == "bf16" else 2e-3 if prec == "tf32" else 3e-5)   # hardware tanh vs exp sigmoid, then rounding
+    # (3) data gradient through dropout(Swish(z)): dz = mask * Swish'(z) * (dy W^T) straight into the activation type
+    dy = torch.randn(M, K, generator=g).to(DEV)                   # reuse [M, K] x [N, K]^T: "dy" [M, K], weight [N, K] -> ds [M, N]
+    ds = ops.gemm(ops.cast(dy, prec), ww, None, prec)[0]
+    dz_ref = ops.swish_dropout_bwd(z_ref, ds, drop, 11, prec)
+    dz = ops.gemm_train(ops.cast(dy, prec), ww, None, prec, drop, want_f32=False, want_act=True, aux=z_ref, site_aux=11)[1]
+    dv, dv_ref = ops.unpack(dz, prec), ops.unpack(dz_ref, prec)
+    assert torch.equal(dv == 0, dv_ref == 0) or p_drop == 0
+    assert rel_l2(dv, dv_ref) < (8e-3 if prec == "bf16" else 1e-3 if prec == "tf32" else 3e-5)
+
+
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("M,N,K,fps,stride", [(16000, 120, 480, 500, 2), (8000, 168, 168, 250, 2), (4000, 240, 960, 125, 1), (999, 120, 4800, 333, 2),
                                               (37, 256, 64, 37, 1), (130, 8, 40, 13, 2)])
