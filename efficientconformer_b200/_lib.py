@@ -68,6 +68,7 @@ _SIGNATURES = {
     "ec_set_pdl": (C.c_int, [C.c_int]),
     "ec_engine_set_skip_mask": (C.c_int, [C.c_void_p, C.c_uint]),
     "ec_debug_gemm_timeline": (C.c_int, [C.c_int, C.POINTER(C.c_ulonglong)]),
+    "ec_debug_gemm_block_n": (C.c_int, [C.c_int]),
     "ec_debug_ffn_timeline": (C.c_int, [C.c_int, C.POINTER(C.c_ulonglong)]),
     "ec_op_gemm_ln": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int,

@@ -37,9 +37,12 @@ __global__ void __launch_bounds__(kThreads) ctc_grad_kernel(const float* __restr
                                                             const int* __restrict__ logits_len, const long long* __restrict__ targets,
                                                             int target_stride, const long long* __restrict__ target_len,
                                                             float* __restrict__ work,        // [B][T][32*NS] alpha, then gamma
+                                                            float* __restrict__ work_lp,     // [B][T][32*NS] emissions when they do not fit on chip
                                                             float grad_scale, float* __restrict__ loss_per_utt, float* __restrict__ grad) {
-  extern __shared__ float lp_sm[];                 // [Tb][SP] emission log2-probs of the extended labels
+  extern __shared__ float lp_dyn[];                // [Tb][SP] emission log2-probs of the extended labels (or unused: work_lp)
   constexpr int SP = 32 * NS;
+  // long utterances x long transcripts (T * (2U+1) floats beyond the shared-memory budget) keep the emissions in an L2-resident scratch
+  float* __restrict__ lp_sm = work_lp != nullptr ? work_lp + static_cast<size_t>(blockIdx.x) * T * SP : lp_dyn;
   __shared__ int lab[SP];                          // extended labels l'_s (0 = blank)
   __shared__ int nxt_same[SP / 2 + 1];             // u -> next u' > u with the same label, or -1
   __shared__ unsigned char is_first[SP / 2 + 1];
@@ -191,9 +194,12 @@ __global__ void __launch_bounds__(kThreads) ctc_grad_kernel(const float* __restr
   }
 }
 
+constexpr size_t kCtcSmemBudget = 200 * 1024;
 size_t ctc_grad_work_bytes(int B, int T, int target_stride) {
-  const int ns = cdiv(2 * target_stride + 1, 32);
-  return align_up(static_cast<size_t>(B) * T * 32 * std::max(ns, 1) * sizeof(float), 256);
+  const int ns = std::max(cdiv(2 * target_stride + 1, 32), 1);
+  const size_t plane = align_up(static_cast<size_t>(B) * T * 32 * ns * sizeof(float), 256);
+  const bool global_lp = static_cast<size_t>(T) * 32 * ns * sizeof(float) > kCtcSmemBudget;
+  return plane * (global_lp ? 2 : 1);
 }
 
 int launch_ctc_grad(const float* logits, const float* lse, int B, int T, int V, const int* logits_len, const long long* targets,
@@ -201,19 +207,23 @@ int launch_ctc_grad(const float* logits, const float* lse, int B, int T, int V, 
                     cudaStream_t stream) {
   EC_REQUIRE(B > 0 && T > 0 && V > 0 && target_stride >= 0, "bad CTC shapes");
   const int ns = std::max(cdiv(2 * target_stride + 1, 32), 1);
-  EC_REQUIRE(ns <= 8, "CTC gradient supports targets of up to 127 labels");
+  // 16 extended-label states per lane = transcripts of up to 255 labels (nn.CTCLoss needs U <= T, and T_out <= 201 for the 16 s
+  // utterances of the shipped configs: train_audio_max_length 256000 samples)
+  EC_REQUIRE(ns <= 16, "CTC gradient supports targets of up to 255 labels");
 #define EC_CTC_GRAD(NS)                                                                                                              \
   case NS: {                                                                                                                         \
-    const size_t sm = static_cast<size_t>(T) * 32 * NS * sizeof(float);                                                              \
-    EC_REQUIRE(sm <= 200 * 1024, "CTC gradient: T * (2U+1) emissions do not fit in shared memory");                                  \
-    static cudaError_t attr = cudaFuncSetAttribute(ctc_grad_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);     \
+    size_t sm = static_cast<size_t>(T) * 32 * NS * sizeof(float);                                                                    \
+    float* work_lp = nullptr;                                                                                                        \
+    if (sm > kCtcSmemBudget) { work_lp = work + align_up(static_cast<size_t>(B) * T * 32 * NS * sizeof(float), 256) / sizeof(float); sm = 0; } \
+    static cudaError_t attr = cudaFuncSetAttribute(ctc_grad_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCtcSmemBudget)); \
     EC_CUDA(attr);                                                                                                                   \
-    ctc_grad_kernel<NS><<<B, kThreads, sm, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, work, grad_scale, \
-                                                     loss_per_utt, grad);                                                            \
+    ctc_grad_kernel<NS><<<B, kThreads, sm, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, work, work_lp, \
+                                                     grad_scale, loss_per_utt, grad);                                                \
     break;                                                                                                                           \
   }
   switch (ns) {
     EC_CTC_GRAD(1) EC_CTC_GRAD(2) EC_CTC_GRAD(3) EC_CTC_GRAD(4) EC_CTC_GRAD(5) EC_CTC_GRAD(6) EC_CTC_GRAD(7) EC_CTC_GRAD(8)
+    EC_CTC_GRAD(9) EC_CTC_GRAD(10) EC_CTC_GRAD(11) EC_CTC_GRAD(12) EC_CTC_GRAD(13) EC_CTC_GRAD(14) EC_CTC_GRAD(15) EC_CTC_GRAD(16)
   }
 #undef EC_CTC_GRAD
   EC_CUDA(cudaGetLastError());

@@ -224,6 +224,7 @@ struct GemmArgs {
 };
 int launch_gemm(int precision, const GemmArgs& a, cudaStream_t stream);
 int gemm_timeline(int enable, unsigned long long* out12);
+int gemm_block_n_override(int block_n);
 
 // Fused feed-forward module (bf16 operands): out = residual + 0.5 * (Swish(x_act W1^T + b1) W2^T + b2), then
 // mode 1: ln_out = LN1(out);  mode 2: out <- LN1(out), ln_out = LN2(out) (plain rounded copy when ln2_g == nullptr).

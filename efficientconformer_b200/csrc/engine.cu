@@ -622,6 +622,7 @@ int ec_engine_set_fuse_ln(ec_engine* e, int enabled) { e->fuse_ln = enabled != 0
 int ec_engine_set_fuse_ffn(ec_engine* e, int enabled) { e->fuse_ffn = enabled != 0; return EC_OK; }
 int ec_engine_set_skip_mask(ec_engine* e, unsigned mask) { e->skip_mask = mask; return EC_OK; }
 int ec_debug_gemm_timeline(int enable, unsigned long long* out12) { return gemm_timeline(enable, out12); }
+int ec_debug_gemm_block_n(int block_n) { return gemm_block_n_override(block_n); }
 int ec_debug_ffn_timeline(int enable, unsigned long long* out192) { return ffn_timeline(enable, out192); }
 int ec_set_pdl(int enabled) { g_pdl = enabled != 0 ? 1 : 0; return EC_OK; }
 int ec_engine_last_launches(const ec_engine* e) { return e->last_launches; }

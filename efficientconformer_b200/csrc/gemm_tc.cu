@@ -61,6 +61,7 @@ struct GemmDev {
 // Optional in-kernel timeline (SM clock stamps of CTA (0,0)), enabled through ec_debug_gemm_timeline for latency studies.
 __device__ unsigned long long g_gemm_timeline[16];
 static int g_timeline_enabled = 0;
+static int g_block_n_override = 0;          // debug: force the N tile of the plain GEMM (multiple of 32 when N spans several tiles)
 __device__ __forceinline__ void stamp(int enabled, int slot) {
   if (enabled && blockIdx.x == 0 && blockIdx.y == 0) g_gemm_timeline[slot] = clock64();
 }
@@ -534,6 +535,7 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
     // split mode stages two W tiles per k-block: narrower plain tiles keep a 3-4 deep ring (the fused-LayerNorm variant needs the
     // whole row in one tile and runs 2 stages for wide rows)
     p.block_n = pick_block_n(a.N, (IsSplit<T>::value && !kLN) ? 128 : 256);
+    if (!kLN && g_block_n_override > 0) p.block_n = std::min(round_up(a.N, 16), g_block_n_override);   // tile-shape studies (tools/gemm_tiles.py)
     tiles_n = cdiv(a.N, p.block_n);
   }
   p.num_k_blocks = cdiv(a.K, Tr::kBlockK);
@@ -662,6 +664,8 @@ int gemm_timeline(int enable, unsigned long long* out12) {
   if (out12 != nullptr) EC_CUDA(cudaMemcpyFromSymbol(out12, g_gemm_timeline, 12 * sizeof(unsigned long long)));
   return EC_OK;
 }
+
+int gemm_block_n_override(int block_n) { g_block_n_override = block_n; return EC_OK; }
 
 int launch_gemm(int precision, const GemmArgs& a, cudaStream_t stream) {
   if (precision == EC_PREC_TF32) return a.ln_mode ? launch_gemm_t<float, true>(precision, a, stream) : launch_gemm_t<float, false>(precision, a, stream);

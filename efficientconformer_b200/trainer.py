@@ -157,13 +157,20 @@ class ArenaWeights:
         self.desc = torch.tensor(desc, dtype=torch.int64, device=device).contiguous()
         self.desc_f = torch.tensor(desc_f, dtype=torch.int64, device=device).contiguous()
 
-    def refresh(self):
-        """Run once per step, before the forward: the parameters changed in the previous optimiser step."""
+    def refresh(self, side=None):
+        """Run once per step, before the forward: the parameters changed in the previous optimiser step.  The transposed operands are
+        only read by the backward: with `side` (a stream forked from the current one; the backward joins it before its first data
+        gradient) they are produced beside the forward."""
         if self.planes == 1:
             _ops.cast_into(self.flat.params, self.arena, self.pr)
         else:
             _ops.cast_multi(self.flat.params, self.desc_f, self.n_desc, self.arena, self.pr)
-        _ops.transpose_cast_multi(self.flat.params, self.desc, self.n_desc, self.arena_t, self.pr)
+        if side is None:
+            _ops.transpose_cast_multi(self.flat.params, self.desc, self.n_desc, self.arena_t, self.pr)
+            return
+        side.wait_stream(torch.cuda.current_stream(self.arena.device))
+        with torch.cuda.stream(side):
+            _ops.transpose_cast_multi(self.flat.params, self.desc, self.n_desc, self.arena_t, self.pr)
 
     def act(self, weight):
         return self._fwd[id(weight)]
@@ -258,7 +265,7 @@ class CTCTrainStep:
     # ---- pieces -----------------------------------------------------------------------------------------------------------
     def _forward_backward(self, mel, mel_len, targets, target_len, accumulate, tables=None):
         if self.weights is not None:
-            self.weights.refresh()
+            self.weights.refresh(side=self.path.side_stream(mel.device))
         x, logits, out_len, tape = self.path.forward(mel, mel_len, self.precision, want_logits=True)
         if out_len is None:
             out_len = torch.full((mel.shape[0],), logits.shape[1], dtype=torch.int64, device=mel.device)

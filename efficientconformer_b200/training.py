@@ -34,6 +34,14 @@ import os as _os
 FUSE = set(filter(None, _os.environ.get("EFFCONF_TRAIN_FUSE", "w1,res,dz,ln").split(",")))
 
 
+class _null_context:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 class DropoutState:
     """Counter-based dropout: mask bit of element i of site s at step n = hash(seed, n, s, i) < keep.  The step counter lives on the
     device so that a captured CUDA graph draws fresh masks on every replay; the backward recomputes the same bits from (site, i)."""
@@ -92,6 +100,7 @@ class TrainingPath:
         self.side_wgrad = True
         self._side = None
         self._side_keep = []
+        self._side_pos = None
 
     # ---- GEMM operands of the weights ----------------------------------------------------------------------------------------
     # Default: one cast / transposed cast per weight and use.  CTCTrainStep installs a provider backed by its flat parameter arena
@@ -121,8 +130,17 @@ class TrainingPath:
         self._side_keep.append((dy_act, x_act))
         return out
 
-    def _join_side(self, device):
-        if self._side is not None and self._side_keep:
+    def side_stream(self, device):
+        """The forked stream the weight gradients run on (None when they run in line); whoever enqueues other work on it must make sure
+        the main stream joins it: backward() does so before its first launch and after its last."""
+        if not self.side_wgrad or device.type != "cuda":
+            return None
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=device)
+        return self._side
+
+    def _join_side(self, device, force=False):
+        if self._side is not None and (self._side_keep or force):
             torch.cuda.current_stream(device).wait_stream(self._side)
         self._side_keep = []
 
@@ -193,9 +211,13 @@ class TrainingPath:
         Tc = T0
         n_blocks = len(self.specs)
         x_act_last = None
+        pos = self._positional_projections(T0, pr, mel.device)
         for i, (spec, blk) in enumerate(zip(self.specs, enc.blocks)):
             last = i == n_blocks - 1
-            x, Tn, bt, x_act = self._block_forward(blk, spec, x, B, Tc, cur_len, pr, drop, want_act_out=last and want_logits and self.head is not None)
+            if i == 0:
+                self._join_pos(mel.device)
+            x, Tn, bt, x_act = self._block_forward(blk, spec, x, B, Tc, cur_len, pr, drop, want_act_out=last and want_logits and self.head is not None,
+                                                   pos=pos[i])
             tape["blocks"].append(bt)
             if spec.conv_stride > 1 and cur_len is not None:
                 cur_len = _len_after_stride(cur_len, spec.conv_stride)
@@ -265,7 +287,34 @@ class TrainingPath:
         grads[f"{prefix}.layers.0.weight"], grads[f"{prefix}.layers.0.bias"] = dg, db
         return dx, dnext
 
-    def _block_forward(self, blk, spec, x, B, T, cur_len, pr, drop, want_act_out):
+    def _positional_projections(self, T0, pr, device):
+        """[(R_i, E_i)] for every block: E_i = pos_layer_i(R_i) depends on the weights only (reference models/attentions.py:678 repeats it per
+        utterance), so all of them run on a forked side stream at the start of the forward, beside the front end and the first modules."""
+        o = _ops
+        main = None
+        if device.type == "cuda":
+            if self._side_pos is None:
+                self._side_pos = torch.cuda.Stream(device=device)
+            main = torch.cuda.current_stream(device)
+            self._side_pos.wait_stream(main)           # the weight operands were refreshed on the main stream
+        out, T = [], T0
+        ctx = torch.cuda.stream(self._side_pos) if main is not None else _null_context()
+        with ctx:
+            for spec, blk in zip(self.specs, self.encoder.blocks):
+                m = blk.multi_head_self_attention_module
+                D, H, G = spec.dim_model, spec.num_heads, spec.group_size
+                R = self._table(T + (-T) % G, spec, pr, device)
+                E = o.gemm(R, self._w(m.mhsa.pos_layer.weight, pr), m.mhsa.pos_layer.bias, pr, want_f32=False, want_act=True,
+                           act_f16=o.attn_operands_f16(pr, D, H, G))[1]
+                out.append((R, E))
+                T = (T - 1) // spec.conv_stride + 1
+        return out
+
+    def _join_pos(self, device):
+        if device.type == "cuda" and self._side_pos is not None:
+            torch.cuda.current_stream(device).wait_stream(self._side_pos)
+
+    def _block_forward(self, blk, spec, x, B, T, cur_len, pr, drop, want_act_out, pos):
         o = _ops
         D, De, H, G, st = spec.dim_model, spec.dim_expand, spec.num_heads, spec.group_size, spec.conv_stride
         if st > 1 and not spec.has_conv_res_proj:
@@ -277,10 +326,7 @@ class TrainingPath:
         wqkv, bqkv, qkv_handle = self._qkv(m.mhsa, pr)
         ab16 = o.attn_operands_f16(pr, D, H, G)                      # split mode: plain fp16 q|k|v and E for the attention core
         qkv = o.gemm(a_in, wqkv, bqkv, pr, want_f32=False, want_act=True, act_f16=ab16)[1]
-        t_pad = T + (-T) % G
-        R = self._table(t_pad, spec, pr, x.device)
-        wpos = self._w(m.mhsa.pos_layer.weight, pr)
-        E = o.gemm(R, wpos, m.mhsa.pos_layer.bias, pr, want_f32=False, want_act=True, act_f16=ab16)[1]
+        R, E = pos
         att = o.relpos_attention_act(qkv.view(B, T, 3 * D), E, m.mhsa.u, m.mhsa.v, cur_len, H, G, pr)
         wo = self._w(m.mhsa.output_layer.weight, pr)
         s_att = drop.next_site()
@@ -320,6 +366,8 @@ class TrainingPath:
         enc = self.encoder
         grads = {}
         dx = None
+        if self._side is not None and (d_logits if d_logits is not None else d_x).is_cuda:
+            self._join_side((d_logits if d_logits is not None else d_x).device, force=True)   # e.g. the transposed weight operands of this step
         if d_x is not None:
             dx = o.own_f32(d_x).view(-1, d_x.shape[-1])
         if d_logits is not None:

@@ -133,6 +133,8 @@ int ec_set_pdl(int enabled);
 int ec_engine_set_skip_mask(ec_engine* e, unsigned mask);
 /* Debug: enable in-kernel SM-clock stamps in the GEMM and read the 12 stamps of the last GEMM's CTA (0,0) (synchronises). */
 int ec_debug_gemm_timeline(int enable, unsigned long long* out12);
+/* debug: force the N tile width of the plain GEMM (0 = automatic); tile-shape studies only */
+int ec_debug_gemm_block_n(int block_n);
 /* Same for the fused feed-forward kernel: 192 stamp slots of CTA 0 (see ffn_fused.cu). */
 int ec_debug_ffn_timeline(int enable, unsigned long long* out192);
 
