@@ -534,7 +534,14 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   } else {
     // split mode stages two W tiles per k-block: narrower plain tiles keep a 3-4 deep ring (the fused-LayerNorm variant needs the
     // whole row in one tile and runs 2 stages for wide rows)
-    p.block_n = pick_block_n(a.N, (IsSplit<T>::value && !kLN) ? 128 : 256);
+    // Split mode stages two W tiles per k-block.  Long contractions (K > 256) keep narrow tiles and a 3-4 deep ring; short ones are
+    // epilogue / wave bound and run fastest on wide tiles with a 2-deep ring: fewer CTAs per SM wave and no A re-reads
+    // (tools/gemm_tiles.py, profiles/r2/gemm_tiles_bf16x2.txt: W1 16000 x 480 x 120 27.8 -> 21.1 us, qkv 16000 x 360 x 120 30.8 -> 17.8 us).
+    p.block_n = pick_block_n(a.N, (IsSplit<T>::value && !kLN && a.K > 256) ? 128 : 256);
+    if (IsSplit<T>::value && !kLN && p.block_n > 128) {       // the wide tile must leave room for two ring stages next to the residual ring
+      const size_t fixed_est = ((a.residual != nullptr || a.aux_mode != 0) ? 16 * kSlabBytes : 0) + kVecBytes + kNumBars * 8 + 16 + 1024;
+      if (2 * (static_cast<size_t>(kATileBytes) + 2 * static_cast<size_t>(p.block_n) * 128) + fixed_est > 227 * 1024) p.block_n = pick_block_n(a.N, 128);
+    }
     if (!kLN && g_block_n_override > 0) p.block_n = std::min(round_up(a.N, 16), g_block_n_override);   // tile-shape studies (tools/gemm_tiles.py)
     tiles_n = cdiv(a.N, p.block_n);
   }

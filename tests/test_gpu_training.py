@@ -304,6 +304,82 @@ def test_training_with_dropout_is_reproducible_and_finite():
     assert len(set(runs[0])) == 4                                             # fresh masks every replay + parameters moving
 
 
+@pytest.mark.parametrize("graph", [True, False])
+def test_eval_after_native_training_sees_the_updated_weights(graph):
+    """ADVICE r1 (high): CTCTrainStep writes parameters and BatchNorm running statistics through raw pointers (no tensor._version bump);
+    train -> eval -> train -> eval must equal a FRESH model loaded from the trained state_dict, in graph and eager mode."""
+    from efficientconformer_b200.trainer import CTCTrainStep
+    from efficientconformer_b200.model_ctc import ModelCTC
+    sp = _small_params()
+    tp = dict(optimizer="Adam", beta1=0.9, beta2=0.98, eps=1e-9, weight_decay=1e-6, lr_schedule="Transformer", schedule_dim=96,
+              warmup_steps=3, K=2)                                           # short warm-up: the weights move visibly within a few steps
+    mel = synthetic_mel(3, 161, seed=9).to(DEV)
+    mel_len = torch.tensor([161, 120, 77], device=DEV)
+    out_len = ((((mel_len - 1) // 2 + 1) - 1) // 2 + 1)
+    y, yl = synthetic_targets(out_len.cpu(), 32, seed=4)
+    m = _model("bf16x2", 0.0, sp, vocab=32)
+    step = CTCTrainStep(m, tp, precision="bf16x2", use_cuda_graph=graph)
+    seen = []
+    for round_ in range(2):
+        for _ in range(3):
+            step.step(mel, mel_len, y.to(DEV), yl.to(DEV))
+        m.eval()
+        with torch.no_grad():
+            logits = m.forward_mel(mel, mel_len)[0].clone()
+        p = dict(sp); p["Pdrop"] = 0.0
+        fresh = ModelCTC(p, {"vocab_size": 32}, precision="bf16x2")
+        fresh.load_state_dict({k: v.detach().clone() for k, v in m.state_dict().items()}, strict=True)
+        with torch.no_grad():
+            ref = fresh.to(DEV).eval().forward_mel(mel, mel_len)[0]
+        assert torch.equal(logits, ref), (graph, round_, rel_l2(logits, ref))
+        seen.append(logits)
+        m.train()
+    assert rel_l2(seen[1], seen[0]) > 1e-3                                   # ... and the second evaluation is not the first one's weights
+
+
+def test_optimizer_checkpoint_round_trip_and_accumulated_steps():
+    """CTCTrainStep.state_dict() carries a torch.optim.Adam-layout optimizer state, the schedule step and the
+    dropout counter (the reference saves optimizer.state_dict() and scheduler.model_step, models/model.py:346-376); a run resumed from
+    it continues bit for bit.  accumulated_steps = 2 (the shipped config): parameters move on every second call only, and two
+    accumulated half-batches give the gradient step of ... the same two micro-batches (loss / 2 each, reference models/model.py:245)."""
+    from efficientconformer_b200.trainer import CTCTrainStep
+    sp = _small_params()
+    tp = dict(optimizer="Adam", beta1=0.9, beta2=0.98, eps=1e-9, weight_decay=1e-6, lr_schedule="Transformer", schedule_dim=96,
+              warmup_steps=50, K=2)
+    mels = [synthetic_mel(3, 161, seed=70 + i).to(DEV) for i in range(6)]
+    y, yl = synthetic_targets(torch.full((3,), 41), 32, seed=4)
+    y, yl = y.to(DEV), yl.to(DEV)
+    a = _model("bf16x2", 0.1, sp, vocab=32)
+    sa = CTCTrainStep(a, tp, precision="bf16x2", dropout_seed=3)
+    for mel in mels[:3]:
+        sa.step(mel, None, y, yl)
+    ckpt_opt = sa.state_dict()
+    ckpt_model = {k: v.detach().clone() for k, v in a.state_dict().items()}
+    assert ckpt_opt["model_step"] == 3 and len(ckpt_opt["optimizer"]["state"]) == len(list(a.parameters()))
+    tail_a = [float(sa.step(mel, None, y, yl)) for mel in mels[3:]]
+    b = _model("bf16x2", 0.1, sp, vocab=32)
+    b.load_state_dict(ckpt_model, strict=True)
+    sb = CTCTrainStep(b, tp, precision="bf16x2", dropout_seed=3)
+    sb.load_state_dict(ckpt_opt)
+    assert sb.steps_done() == 3 and abs(sb.lr() - sa._lr_of(4)) < 1e-12 + 1e-6 * sa._lr_of(4)
+    tail_b = [float(sb.step(mel, None, y, yl)) for mel in mels[3:]]
+    assert tail_a == tail_b                                                   # resumed run == uninterrupted run, bit for bit
+    for k, v in a.state_dict().items():
+        assert torch.equal(v, b.state_dict()[k]), k
+    # the optimizer state loads into torch.optim.Adam as it is (what the reference's Model.load does)
+    opt = torch.optim.Adam(b.parameters(), lr=1e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6)
+    opt.load_state_dict(sb.state_dict()["optimizer"])
+    # gradient accumulation
+    tp2 = dict(tp); tp2["accumulated_steps"] = 2
+    c = _model("bf16x2", 0.0, sp, vocab=32)
+    sc = CTCTrainStep(c, tp2, precision="bf16x2")
+    p0 = sc.flat.params.clone()
+    sc.step(mels[0], None, y, yl)
+    assert torch.equal(sc.flat.params, p0) and sc.steps_done() == 0           # first micro-batch: gradients only
+    sc.step(mels[1], None, y, yl)
+    assert not torch.equal(sc.flat.params, p0) and sc.steps_done() == 1
+
+
 # ---- two GPUs: utterance shards + SyncBatchNorm + one all-reduced gradient bucket == the single-GPU step on the whole batch ----------
 def _dp_worker(rank, world, port, prec, graph, q):
     import torch.distributed as dist
