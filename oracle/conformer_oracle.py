@@ -16,7 +16,29 @@ import math
 import torch
 import torch.nn.functional as F
 
-from efficientconformer_b200.config import resolve_blocks  # pure-python shape bookkeeping (no CUDA)
+from types import SimpleNamespace
+
+
+def resolve_blocks(params):
+    """Per-block hyper-parameters, restated from the reference's own constructor (reference models/encoders.py:75-95): entry i of a
+    list-valued parameter is selected by the number of expand / strided blocks strictly before (`>`) or up to (`>=`) block i.
+    Independent of the product's efficientconformer_b200.config.resolve_blocks (tests/test_host_logic.py compares the two)."""
+    def pick(v, idx):
+        return v[idx] if isinstance(v, list) else v
+    expand, strided = params.get("expand_blocks", []), params.get("strided_blocks", [])
+    out = []
+    for i in range(params["num_blocks"]):
+        gt_e, ge_e = sum(i > e for e in expand), sum(i >= e for e in expand)
+        gt_s = sum(i > st for st in strided)
+        dim_model, dim_expand = pick(params["dim_model"], gt_e), pick(params["dim_model"], ge_e)
+        heads, group = pick(params["num_heads"], gt_e), pick(params.get("att_group_size", 1), gt_s)
+        out.append(SimpleNamespace(
+            dim_model=dim_model, dim_expand=dim_expand, num_heads=heads, kernel_size=pick(params["kernel_size"], ge_e), group_size=group,
+            max_pos=params["max_pos_encoding"] // params.get("stride", 2) ** gt_s,
+            conv_stride=pick(params["conv_stride"], gt_s) if i in strided else 1, ff_ratio=params["ff_ratio"],
+            dim_head=(group * dim_model) // heads,                   # reference models/attentions.py:640 (grouped) / :47
+            has_conv_res_proj=dim_model != dim_expand))              # reference models/blocks.py:105-109
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -240,10 +240,14 @@ def test_reference_distribute_strategy_two_gpus_matches_single_gpu_whole_batch()
         assert rel_l2(t(s0[k]), t(s1[k])) < 1e-6 and rel_l2(t(s0[k]), t(sf[k])) < 1e-3, k
     norms = sorted(float(t(g).norm()) for g in gf.values())
     floor = 1e-4 * norms[len(norms) // 2]
+    # parameters whose exact gradient is zero (softmax is invariant to a per-row constant: key / positional biases and the positional
+    # columns that multiply the constant cos ~ 1 sinusoids; biases in front of a BatchNorm): their gradients are rounding noise whose
+    # value depends on the batch split (same list as tests/test_gpu_training.py)
+    noise = ("convolution_module.layers.4.bias", "subsampling_module.layers.0.0.bias", "key_layer.bias", "pos_layer.bias", "pos_layer.weight")
     worst = (0.0, "")
     for k, g in gf.items():
         assert rel_l2(t(g0[k]), t(g1[k])) < 1e-6 or float(t(g).norm()) < floor, k   # DDP: replicas hold the same averaged gradient
-        if float(t(g).norm()) >= floor:
+        if float(t(g).norm()) >= floor and not k.endswith(noise):
             worst = max(worst, (abs(float(t(g0[k]).norm()) - float(t(g).norm())) / float(t(g).norm()), k))
     print(f"2-rank distribute_strategy vs whole batch: losses {l0:.5f} {l1:.5f} | {lf:.5f}; worst gradient-norm error {worst[0]:.3e} ({worst[1]})")
     assert worst[0] < 4e-2, worst

@@ -176,3 +176,18 @@ def test_bench_both_arms_describe_the_same_config():
             assert c1 == c2 and c1["global_batch"] == 32 * n and c1["frames"] == 1000 and "workload" in c1
     assert abs(bench.flops_per_frame(*bench.SHIPPED_ENCODER_PARAMS["EfficientConformerCTCSmall"], 1000, 32) / 1e6 - 6.616) < 1e-3
     assert abs(bench.flops_per_frame(*bench.SHIPPED_ENCODER_PARAMS["ConformerCTCLarge"], 4000, 8) / 1e6 - 99.888) < 1e-2
+
+
+def test_oracle_block_shapes_are_independent_of_and_equal_to_the_product():
+    """The oracle resolves the per-block hyper-parameters itself (no import from the product package); both agree on every shipped config."""
+    import inspect
+    from oracle import conformer_oracle as O
+    from efficientconformer_b200.config import SHIPPED_ENCODER_PARAMS, resolve_blocks
+    import re
+    assert not re.search(r"^\s*(from|import)\s+efficientconformer_b200", inspect.getsource(O), re.M)
+    for name, (params, _) in SHIPPED_ENCODER_PARAMS.items():
+        a, b = O.resolve_blocks(params), resolve_blocks(params)
+        assert len(a) == len(b) == params["num_blocks"]
+        for x, y in zip(a, b):
+            for f in ("dim_model", "dim_expand", "num_heads", "kernel_size", "group_size", "max_pos", "conv_stride", "ff_ratio", "dim_head", "has_conv_res_proj"):
+                assert getattr(x, f) == getattr(y, f), (name, f)

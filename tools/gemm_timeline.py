@@ -26,11 +26,11 @@ def run(tag, fn):
     print(f"{tag:44s} " + " ".join(f"{n}={(out[i] - t0) / mhz:6.2f}" for i, n in enumerate(names) if i))
 
 
-for prec in ("bf16", "tf32"):
+for prec in (sys.argv[1:] or ["bf16", "tf32"]):
     M = 16000
     a120 = ops.cast(torch.randn(M, 120, device=dev), prec); a480 = ops.cast(torch.randn(M, 480, device=dev), prec)
-    w480 = ops.cast(torch.randn(480, 120, device=dev), prec); w120 = ops.cast(torch.randn(120, 480, device=dev), prec)
-    wsq = ops.cast(torch.randn(120, 120, device=dev), prec)
+    w480 = ops.cast_weight(torch.randn(480, 120, device=dev), prec); w120 = ops.cast_weight(torch.randn(120, 480, device=dev), prec)
+    wsq = ops.cast_weight(torch.randn(120, 120, device=dev), prec)
     b480, b120 = torch.randn(480, device=dev), torch.randn(120, device=dev)
     res = torch.randn(M, 120, device=dev)
     g1, b1 = torch.ones(120, device=dev), torch.zeros(120, device=dev)
@@ -42,8 +42,8 @@ for prec in ("bf16", "tf32"):
     run(f"{prec} W2 16000x120x480 +res LN1", lambda: ops.gemm_ln(a480, w120, b120, prec, g1, b1, mode=1, alpha=0.5, residual=res))
     run(f"{prec} W2 16000x120x480 +res LN2", lambda: ops.gemm_ln(a480, w120, b120, prec, g1, b1, g1, b1, mode=2, alpha=0.5, residual=res))
     run(f"{prec} att-out 16000x120x120 +res LN1", lambda: ops.gemm_ln(a120, wsq, b120, prec, g1, b1, mode=1, alpha=1.0, residual=res))
-    a240 = ops.cast(torch.randn(4000, 240, device=dev), prec); w240 = ops.cast(torch.randn(240, 240, device=dev), prec)
+    a240 = ops.cast(torch.randn(4000, 240, device=dev), prec); w240 = ops.cast_weight(torch.randn(240, 240, device=dev), prec)
     b240 = torch.randn(240, device=dev); res240 = torch.randn(4000, 240, device=dev); g240, z240 = torch.ones(240, device=dev), torch.zeros(240, device=dev)
     run(f"{prec} att-out 4000x240x240 +res LN1", lambda: ops.gemm_ln(a240, w240, b240, prec, g240, z240, mode=1, alpha=1.0, residual=res240))
-    w720 = ops.cast(torch.randn(720, 240, device=dev), prec); b720 = torch.randn(720, device=dev)
+    w720 = ops.cast_weight(torch.randn(720, 240, device=dev), prec); b720 = torch.randn(720, device=dev)
     run(f"{prec} qkv 4000x720x240 ->act", lambda: ops.gemm(a240, w720, b720, prec, want_f32=False, want_act=True))
