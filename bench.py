@@ -60,6 +60,25 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback of B200_PROFILING.md"}
 
 
+def ncu_traffic(precision, kernel_prefix, stem="ncu_full_train"):
+    """Average DRAM bytes (read + write) per launch of one kernel from the committed `ncu --set full` capture of the same workload
+    (profiles/r2/, produced by tools/summarize_ncu.py from tools/gpu_r2q.sh); None when no capture exists for this precision.  A
+    cross-reference measured under ncu in a separate run (cold caches, serialised), not in this run: the source file is named."""
+    path = os.path.join(ROOT, "profiles", "r2", f"{stem}_{precision}_summary.json")
+    if not os.path.exists(path):
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, n = 0.0, 0
+    for k in json.load(open(path))["kernels"]:
+        if not k["kernel"].startswith(kernel_prefix):
+            continue
+        for key in ("dram_read", "dram_write"):
+            val, unit = k[key].split()
+            tot += float(val) * scale[unit]
+        n += 1
+    return {"bytes_per_launch": round(tot / n), "launches_sampled": n, "source": os.path.relpath(path, ROOT)} if n else None
+
+
 def tensor_peak(precision, pk):
     """Algorithmic FLOP/s ceiling of an operand mode: tf32 operands run the tensor core at half the bf16 rate; the split mode issues
     two bf16 MMAs per product, so its algorithmic ceiling is also half the bf16 peak.  The reported `peak` stays the measured bf16
@@ -453,7 +472,8 @@ def forward_record(env, config, precision, B, T, steps, warmup, want_e2e=True, w
                     continue
                 ach = fl_ / ms_ / 1e9
                 roofs.append({"kernel": desc[cls], "bound": "tensor", "achieved": round(ach, 2), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                              "frac": round(ach / pk["bf16_tflops"], 4), "mode_ceiling": tensor_peak(precision, pk), "traffic": None,
+                              "frac": round(ach / pk["bf16_tflops"], 4), "mode_ceiling": tensor_peak(precision, pk),
+                              "traffic": ncu_traffic(precision, "relpos_attn" if cls == "relpos_attention" else "gemm_tc_kernel", "ncu_full_fwd"),
                               "launches": n_, "avg_launch_us": round(1e3 * ms_ / n_, 2), "share_of_forward": round(ms_ / tot, 3), "target_frac": 0.5})
             dw = acc.get("dwconv_bn_swish")
             if dw and dw[0] > 0:
@@ -560,6 +580,9 @@ def train_record(env, config, precision, B, T, steps, warmup, pdrop, graph=True,
                                 "pipeline, loss read back every step), synchronised both sides"}
         rec["e2e_loss_last"] = e2e_losses[-1]
     rec["lr_after"] = step.lr(); rec["optimizer_steps"] = step.steps_done()
+    rec["sync_bn_exchange"] = type(step.reducer).__name__ if step.reducer is not None else None
+    if hasattr(step.reducer, "error"):
+        rec["sync_bn_exchange_timeouts"] = step.reducer.error()
     return rec, step, (mel_d, y_d, yl_d, mel_h, y, y_len)
 
 
@@ -753,8 +776,10 @@ def run_ours(args, rank, world, local_rank):
                "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": pr,
                "data": "synthetic", "config": workload_config(args, "train"), "launch": rec["launch"], "sync_bn": world > 1 and not args.no_sync_bn,
                "e2e": rec["e2e"], "clocks": clocks}
-        for k in ("step_ms_min_med_max", "loss_first_last", "e2e_loss_last", "lr_after", "optimizer_steps", "whole_step"):
-            out[k] = rec[k]
+        for k in ("step_ms_min_med_max", "loss_first_last", "e2e_loss_last", "lr_after", "optimizer_steps", "whole_step", "sync_bn_exchange",
+                  "sync_bn_exchange_timeouts"):
+            if k in rec:
+                out[k] = rec[k]
         if world > 1:
             # exposed communication: the same step on the same batches with no collective at all (local BatchNorm statistics, no gradient
             # all-reduce), every rank for itself; the difference to the data-parallel step is what SyncBatchNorm + the bucket cost
@@ -764,9 +789,11 @@ def run_ours(args, rank, world, local_rank):
             local_ms /= max(10, args.steps // 2)
             lstep.close(); del lstep
             out["communication"] = {"ms_per_step_no_collectives": local_ms, "exposed_ms_per_step": rec["ms_per_step"] - local_ms,
-                                    "collectives_per_step": "16 x all_gather (SyncBatchNorm forward statistics) + 16 x all_reduce (backward sums) + "
-                                                            "1 x all_reduce of the flat 53 MB fp32 gradient bucket, all inside the captured graph"
-                                                            if not args.no_sync_bn else "1 x all_reduce of the flat fp32 gradient bucket"}
+                                    "exchanges_per_step": ("16 + 16 SyncBatchNorm exchanges (forward statistics, backward sums) as "
+                                                           + ("peer-memory kernels over NVLink (csrc/p2p_exchange.cu)" if rec.get("sync_bn_exchange") == "P2PSyncBatchNormReducer"
+                                                              else "NCCL all_gather / all_reduce")
+                                                           + " + 1 x NCCL all_reduce of the flat 53 MB fp32 gradient bucket, all inside the captured graph")
+                                                          if not args.no_sync_bn else "1 x all_reduce of the flat fp32 gradient bucket"}
         if rank == 0:
             ops, ours_k, lib_k, lib_names = train_operator_profile(env, cfg, pr, args.pdrop, batch)
             tot_ms = sum(v["ms"] for v in ops.values())
@@ -781,7 +808,8 @@ def run_ours(args, rank, world, local_rank):
             def roof(k, v):
                 a = v["flops"] / v["ms"] / 1e9
                 return {"kernel": desc.get(k, k), "bound": "tensor", "achieved": round(a, 2), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                        "frac": round(a / pk["bf16_tflops"], 4), "mode_ceiling": tensor_peak(pr, pk), "traffic": None,
+                        "frac": round(a / pk["bf16_tflops"], 4), "mode_ceiling": tensor_peak(pr, pk),
+                        "traffic": ncu_traffic(pr, "wgrad_tc_kernel" if "wgrad" in k else "gemm_tc_kernel"),
                         "peak_source": pk["source"] + " bf16 cuBLAS burst", "launches_per_step": v["calls"],
                         "avg_launch_us": round(1e3 * v["ms"] / max(v["calls"], 1), 2), "share_of_step": round(v["ms"] / tot_ms, 3),
                         "algorithmic_flops_per_step": v["flops"],

@@ -152,6 +152,10 @@ _SIGNATURES = {
     "ec_op_gemm_train": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_float, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p]),
     "ec_attention_operand_kind": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ec_p2p_mailbox_bytes": (C.c_size_t, [C.c_int]),
+    "ec_p2p_max_payload_floats": (C.c_int, []),
+    "ec_p2p_bn_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "ec_p2p_error": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "ec_op_pointwise_glu": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
     "ec_op_glu_scratch_rows": (C.c_int, [C.c_int]),

@@ -164,9 +164,49 @@ struct TcDev {
   float *dqkv, *dE, *du, *dv;
 };
 
-// ---- pack: dense per-head operands.  One thread per (bh, i, c) -------------------------------------------------------------
+// ---- pack: dense per-head operands.  One thread per (bh, i, PAIR of features c, c+1): d, D and f = h*d + c are even, so a pair
+//      never straddles a head or a frame; 32-bit stores, half the index arithmetic per element ---------------------------------
+template <typename TIn> __device__ __forceinline__ float2 load_pair(const TIn* p);
+template <> __device__ __forceinline__ float2 load_pair<bf16>(const bf16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
+template <> __device__ __forceinline__ float2 load_pair<__half>(const __half* p) { return __half22float2(*reinterpret_cast<const __half2*>(p)); }
+template <> __device__ __forceinline__ float2 load_pair<SplitBf16>(const SplitBf16* p) {
+  const uint2 w = *reinterpret_cast<const uint2*>(p);
+  return make_float2(split_unpack(w.x), split_unpack(w.y));
+}
+__device__ __forceinline__ void store_pair(bf16* p, float a, float b) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); }
+
 template <typename TIn>
 __global__ void __launch_bounds__(256) tc_pack_kernel(const TcDev p) {
+  const int hp = p.dp / 2;
+  const long long n = static_cast<long long>(p.B) * p.H * p.Tg * hp;
+  const long long row3 = 3LL * p.D;
+  for (long long idx2 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx2 < n; idx2 += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = 2 * static_cast<int>(idx2 % hp);
+    const long long r = idx2 / hp;
+    const int i = static_cast<int>(r % p.Tg);
+    const int bh = static_cast<int>(r / p.Tg);
+    const int b = bh / p.H, h = bh - b * p.H;
+    float2 qu = make_float2(0.f, 0.f), qv = qu, k = qu, v = qu, go = qu;
+    if (c < p.d) {
+      const int f = h * p.d + c, fo = f / p.D, ch = f - fo * p.D;
+      const int frame = i * p.G + fo;
+      float2 q = make_float2(0.f, 0.f);
+      if (frame < p.T) {
+        const TIn* row = reinterpret_cast<const TIn*>(p.qkv) + (static_cast<long long>(b) * p.T + frame) * row3;
+        q = load_pair<TIn>(row + ch); k = load_pair<TIn>(row + p.D + ch); v = load_pair<TIn>(row + 2 * p.D + ch);
+        go = *reinterpret_cast<const float2*>(p.dO + (static_cast<long long>(b) * p.T + frame) * p.D + ch);
+      }
+      const float2 uu = *reinterpret_cast<const float2*>(p.u + ch), vv = *reinterpret_cast<const float2*>(p.v + ch);
+      qu = make_float2(q.x + uu.x, q.y + uu.y); qv = make_float2(q.x + vv.x, q.y + vv.y);
+    }
+    const long long idx = r * p.dp + c;
+    store_pair(p.Qu + idx, qu.x, qu.y); store_pair(p.Qv + idx, qv.x, qv.y);
+    store_pair(p.Kd + idx, k.x, k.y); store_pair(p.Vd + idx, v.x, v.y); store_pair(p.dOd + idx, go.x, go.y);
+  }
+}
+// scalar variants for odd head / model dims (one thread per element)
+template <typename TIn>
+__global__ void __launch_bounds__(256) tc_pack_scalar_kernel(const TcDev p) {
   const long long n = static_cast<long long>(p.B) * p.H * p.Tg * p.dp;
   const long long row3 = 3LL * p.D;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -189,6 +229,21 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const TcDev p) {
     }
     p.Qu[idx] = __float2bfloat16_rn(qu); p.Qv[idx] = __float2bfloat16_rn(qv);
     p.Kd[idx] = __float2bfloat16_rn(k); p.Vd[idx] = __float2bfloat16_rn(v); p.dOd[idx] = __float2bfloat16_rn(go);
+  }
+}
+__global__ void __launch_bounds__(256) tc_unpack_scalar_kernel(const TcDev p) {
+  const long long n = static_cast<long long>(p.B) * p.T * p.D;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(idx % p.D);
+    const long long bt = idx / p.D;
+    const int frame = static_cast<int>(bt % p.T), b = static_cast<int>(bt / p.T);
+    const int i = frame / p.G, fo = frame - i * p.G;
+    const int f = fo * p.D + ch, h = f / p.d, c = f - h * p.d;
+    const long long src = ((static_cast<long long>(b) * p.H + h) * p.Tg + i) * p.dp + c;
+    float* out = p.dqkv + bt * 3 * p.D;
+    out[ch] = p.dQu[src] + p.dQv[src];
+    out[p.D + ch] = p.dK[src];
+    out[2 * p.D + ch] = p.dV[src];
   }
 }
 template <typename TIn>
@@ -261,20 +316,22 @@ __global__ void __launch_bounds__(256) tc_rows_kernel(const TcDev p) {
   }
 }
 
-// ---- unpack: dq = dQu + dQv, dk, dv -> dqkv [B*T, 3D] (real frames) ---------------------------------------------------------------
+// ---- unpack: dq = dQu + dQv, dk, dv -> dqkv [B*T, 3D] (real frames); one thread per channel pair (64-bit accesses) ----------------
 __global__ void __launch_bounds__(256) tc_unpack_kernel(const TcDev p) {
-  const long long n = static_cast<long long>(p.B) * p.T * p.D;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int ch = static_cast<int>(idx % p.D);
-    const long long bt = idx / p.D;
+  const int hD = p.D / 2;
+  const long long n = static_cast<long long>(p.B) * p.T * hD;
+  for (long long idx2 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx2 < n; idx2 += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = 2 * static_cast<int>(idx2 % hD);
+    const long long bt = idx2 / hD;
     const int frame = static_cast<int>(bt % p.T), b = static_cast<int>(bt / p.T);
     const int i = frame / p.G, fo = frame - i * p.G;
     const int f = fo * p.D + ch, h = f / p.d, c = f - h * p.d;
     const long long src = ((static_cast<long long>(b) * p.H + h) * p.Tg + i) * p.dp + c;
     float* out = p.dqkv + bt * 3 * p.D;
-    out[ch] = p.dQu[src] + p.dQv[src];
-    out[p.D + ch] = p.dK[src];
-    out[2 * p.D + ch] = p.dV[src];
+    const float2 a = *reinterpret_cast<const float2*>(p.dQu + src), a2 = *reinterpret_cast<const float2*>(p.dQv + src);
+    *reinterpret_cast<float2*>(out + ch) = make_float2(a.x + a2.x, a.y + a2.y);
+    *reinterpret_cast<float2*>(out + p.D + ch) = *reinterpret_cast<const float2*>(p.dK + src);
+    *reinterpret_cast<float2*>(out + 2 * p.D + ch) = *reinterpret_cast<const float2*>(p.dV + src);
   }
 }
 // column sums of dQu / dQv over the grouped rows of one (b, h): uv_part[bh][0 | 1][c].  Block = 32 columns x 32 row lanes, lane ty
@@ -390,16 +447,14 @@ int launch_relpos_attention_bwd_tc(int precision, const AttnArgs& a, const float
   const long long sE = static_cast<long long>(p.R) * dp;
   const int H = a.H;
 
-  if (precision == EC_PREC_BF16X2 && !a.in_f16) {
-    tc_pack_kernel<SplitBf16><<<egrid(static_cast<long long>(BH) * Tg * dp), 256, 0, st>>>(p);
-    tc_pack_e_kernel<SplitBf16><<<egrid(static_cast<long long>(H) * p.R * dp), 256, 0, st>>>(p);
-  } else if (precision == EC_PREC_BF16X2) {          // fp16 q|k|v / E from the forward; the backward GEMMs run on bf16 copies
-    tc_pack_kernel<__half><<<egrid(static_cast<long long>(BH) * Tg * dp), 256, 0, st>>>(p);
-    tc_pack_e_kernel<__half><<<egrid(static_cast<long long>(H) * p.R * dp), 256, 0, st>>>(p);
-  } else {
-    tc_pack_kernel<bf16><<<egrid(static_cast<long long>(BH) * Tg * dp), 256, 0, st>>>(p);
-    tc_pack_e_kernel<bf16><<<egrid(static_cast<long long>(H) * p.R * dp), 256, 0, st>>>(p);
-  }
+  const bool pairs = a.D % 2 == 0 && p.d % 2 == 0;      // feature pairs stay inside one head and one frame
+  const int pgrid = egrid(static_cast<long long>(BH) * Tg * dp / (pairs ? 2 : 1));
+#define EC_PACK(TIN) do { if (pairs) tc_pack_kernel<TIN><<<pgrid, 256, 0, st>>>(p); else tc_pack_scalar_kernel<TIN><<<pgrid, 256, 0, st>>>(p); \
+                          tc_pack_e_kernel<TIN><<<egrid(static_cast<long long>(H) * p.R * dp), 256, 0, st>>>(p); } while (0)
+  if (precision == EC_PREC_BF16X2 && !a.in_f16) EC_PACK(SplitBf16);
+  else if (precision == EC_PREC_BF16X2) EC_PACK(__half);        // fp16 q|k|v / E from the forward; the backward GEMMs run on bf16 copies
+  else EC_PACK(bf16);
+#undef EC_PACK
   EC_CUDA(cudaGetLastError());
   // Independent launches run as parallel branches (library-owned side streams, event fork / join: capturable); the critical path is
   // pack -> max(S1, Rel, dP) -> rows -> max(dV, dK, dQu, dQv) -> unpack, the parameter-gradient tail (dE, du, dv) runs beside it.
@@ -436,7 +491,8 @@ int launch_relpos_attention_bwd_tc(int precision, const AttnArgs& a, const float
     EC_CUDA(cudaEventRecord(ss.fork_ev, st));                          // (after the join: dQu / dQv are complete at this point of `st`)
     EC_CUDA(cudaStreamWaitEvent(s1, ss.fork_ev, 0));
   }
-  tc_unpack_kernel<<<egrid(static_cast<long long>(a.B) * a.T * a.D), 256, 0, st>>>(p);
+  if (pairs) tc_unpack_kernel<<<egrid(static_cast<long long>(a.B) * a.T * a.D / 2), 256, 0, st>>>(p);
+  else tc_unpack_scalar_kernel<<<egrid(static_cast<long long>(a.B) * a.T * a.D), 256, 0, st>>>(p);
   EC_CUDA(cudaGetLastError());
   tc_uv_part_kernel<<<dim3(BH, cdiv(dp, 32)), 1024, 0, s1>>>(p);
   EC_CUDA(cudaGetLastError());

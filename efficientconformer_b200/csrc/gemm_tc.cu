@@ -534,13 +534,27 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   } else {
     // split mode stages two W tiles per k-block: narrower plain tiles keep a 3-4 deep ring (the fused-LayerNorm variant needs the
     // whole row in one tile and runs 2 stages for wide rows)
-    // Split mode stages two W tiles per k-block.  Long contractions (K > 256) keep narrow tiles and a 3-4 deep ring; short ones are
-    // epilogue / wave bound and run fastest on wide tiles with a 2-deep ring: fewer CTAs per SM wave and no A re-reads
-    // (tools/gemm_tiles.py, profiles/r2/gemm_tiles_bf16x2.txt: W1 16000 x 480 x 120 27.8 -> 21.1 us, qkv 16000 x 360 x 120 30.8 -> 17.8 us).
-    p.block_n = pick_block_n(a.N, (IsSplit<T>::value && !kLN && a.K > 256) ? 128 : 256);
-    if (IsSplit<T>::value && !kLN && p.block_n > 128) {       // the wide tile must leave room for two ring stages next to the residual ring
+    // Split mode stages two W tiles per k-block.  The N tile is chosen by a small cost model fitted to the tile study
+    // (tools/gemm_tiles.py, profiles/r2/gemm_tiles_bf16x2.txt): time ~ waves x (fixed + per-column epilogue), one CTA per SM, with
+    // wide tiles only for short contractions (K <= 256: 2-deep ring) -- e.g. W1 16000 x 480 x 120: 4 x 128 (27.8 us) -> 2 x 256
+    // (21.1 us); 8000 x 672 x 168: 3 x 224 leaves a near-empty second wave, 4 x 192 fills it.
+    p.block_n = pick_block_n(a.N, 256);
+    if (IsSplit<T>::value && !kLN) {
+      const int cap = a.K > 256 ? 128 : 256;
       const size_t fixed_est = ((a.residual != nullptr || a.aux_mode != 0) ? 16 * kSlabBytes : 0) + kVecBytes + kNumBars * 8 + 16 + 1024;
-      if (2 * (static_cast<size_t>(kATileBytes) + 2 * static_cast<size_t>(p.block_n) * 128) + fixed_est > 227 * 1024) p.block_n = pick_block_n(a.N, 128);
+      const int m_tiles = cdiv(a.M, kBlockM);
+      double best = 1e30; int best_bn = 0;
+      auto consider = [&](int bn) {
+        if (bn > cap || bn < 16) return;
+        if (2 * (static_cast<size_t>(kATileBytes) + 2 * static_cast<size_t>(bn) * 128) + fixed_est > 227 * 1024) return;
+        const int waves = cdiv(m_tiles * cdiv(a.N, bn), 148);
+        const double cost = waves * (4.0 + 0.004 * a.K + 0.02 * bn);
+        if (cost < best - 1e-9 || (cost < best + 1e-9 && bn > best_bn)) { best = cost; best_bn = bn; }
+      };
+      consider(round_up(a.N, 16));                       // the whole row in one tile
+      for (int bn = 64; bn <= 256; bn += 32) if (bn < a.N) consider(bn);
+      if (best_bn == 0) best_bn = pick_block_n(a.N, 128);
+      p.block_n = best_bn;
     }
     if (!kLN && g_block_n_override > 0) p.block_n = std::min(round_up(a.N, 16), g_block_n_override);   // tile-shape studies (tools/gemm_tiles.py)
     tiles_n = cdiv(a.N, p.block_n);

@@ -86,3 +86,77 @@ class SyncBatchNormReducer:
     def backward_sums(self, sums):
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
         return sums
+
+
+class P2PSyncBatchNormReducer(SyncBatchNormReducer):
+    """The same two exchange steps as ONE kernel each over NVLink / NVSwitch peer memory (csrc/p2p_exchange.cu) instead of
+    {pack, NCCL collective, unpack, merge}: the statistics are stored straight into every rank's mailbox (symmetric memory mapped by
+    torch.distributed._symmetric_memory), flags are raised with release / acquire at system scope, and every rank merges the W payloads
+    of its own mailbox in rank order (bit-identical results on all ranks).  Construction raises when symmetric memory cannot be set up
+    on this machine (no P2P mapping, unsupported driver): callers fall back to the NCCL reducer (`make_sync_bn_reducer`)."""
+
+    def __init__(self, group=None, device="cuda", uniform=True):
+        super().__init__(group, device, uniform)
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        L = _lib.lib()
+        self._lib, self._C = _lib, C
+        n_bytes = L.ec_p2p_mailbox_bytes(self.world)
+        self.mailbox = symm.empty(n_bytes // 4, dtype=torch.float32, device=device)
+        self.mailbox.zero_()
+        torch.cuda.synchronize(device)
+        self.handle = symm.rendezvous(self.mailbox, group if group is not None else dist.group.WORLD)
+        if self.handle.world_size != self.world:
+            raise RuntimeError("symmetric-memory rendezvous returned a different world size")
+        self.rank = self.handle.rank
+        self.peer_ptrs = (C.c_ulonglong * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
+        self.max_floats = L.ec_p2p_max_payload_floats()
+        self.handle.barrier()                          # every mailbox is zeroed before anybody stores into it
+        torch.cuda.synchronize(device)
+        self._count_out = torch.zeros(1, dtype=torch.float32, device=device)
+
+    def _exchange(self, data, n, mode, count):
+        if n > self.max_floats:
+            raise RuntimeError(f"BatchNorm payload of {n} floats exceeds the peer mailbox slot ({self.max_floats})")
+        _l = self._lib
+        _l.check(_l.lib().ec_p2p_bn_exchange(self.peer_ptrs, self.rank, self.world, _l.ptr(data), n, mode, float(count),
+                                             _l.ptr(self._count_out), _l.stream_ptr()))
+
+    def forward_stats(self, stats, count):
+        assert stats.is_contiguous() and stats.dtype == torch.float32
+        self._exchange(stats, stats.numel(), 1, count)
+        if self.uniform:
+            return float(count) * self.world
+        return float(self._count_out.item())
+
+    def backward_sums(self, sums):
+        assert sums.is_contiguous() and sums.dtype == torch.float32
+        self._exchange(sums, sums.numel(), 0, 0.0)
+        return sums
+
+    def error(self):
+        """1 when a peer failed to arrive within the kernel's time-out at any exchange so far (synchronises)."""
+        out = self._C.c_int(0)
+        self._lib.check(self._lib.lib().ec_p2p_error(self.peer_ptrs, self.rank, self.world, self._C.byref(out)))
+        return out.value
+
+
+def make_sync_bn_reducer(group, device, uniform=True):
+    """Peer-memory exchange when this machine supports it (and EFFCONF_P2P_BN != 0), else the NCCL reducer.  All ranks must take
+    the same branch: the decision is agreed with one all_reduce(MIN)."""
+    import os
+    want = os.environ.get("EFFCONF_P2P_BN", "1") != "0" and torch.device(device).type == "cuda"
+    red, ok = None, 0
+    if want:
+        try:
+            red = P2PSyncBatchNormReducer(group, device, uniform)
+            ok = 1
+        except Exception as ex:                          # noqa: BLE001 -- any failure to map peer memory means "use NCCL"
+            import warnings
+            warnings.warn(f"peer-memory SyncBatchNorm exchange unavailable ({type(ex).__name__}: {ex}); using NCCL collectives")
+    flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 1:
+        return red
+    return SyncBatchNormReducer(group, device, uniform)

@@ -227,8 +227,8 @@ class CTCTrainStep:
             raise ValueError("accumulated_steps must be >= 1")
         reducer = None
         if self.world > 1 and sync_bn:
-            from .distributed import SyncBatchNormReducer
-            reducer = SyncBatchNormReducer(process_group, self.device)
+            from .distributed import make_sync_bn_reducer
+            reducer = make_sync_bn_reducer(process_group, self.device)      # peer-memory exchange kernel, or NCCL collectives
         self.reducer = reducer
         self.path = TrainingPath(model.encoder, model.fc, stats_reducer=reducer, dropout_seed=dropout_seed)
         self.flat = FlatParams(_qkv_adjacent_order(self.path.param_list()), self.device)

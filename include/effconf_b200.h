@@ -332,6 +332,17 @@ int ec_op_dwconv_bn_swish(int precision, const void* x, const float* w_folded, c
 int ec_op_subsample_conv(int precision, const float* mel, const float* w_folded, const float* b_folded, int batch,
                          int n_mels, int t, int channels, void* y, void* stream);
 
+/* ---- SyncBatchNorm exchange over NVLink / NVSwitch peer memory (csrc/p2p_exchange.cu; reference models/model_ctc.py:70-75:
+ * nn.SyncBatchNorm under DistributedDataParallel).  One kernel per exchange: store the payload into every rank's mailbox, raise flags
+ * (release / acquire at system scope), wait, merge in rank order.  peer_ptrs [world] (HOST array) = this process's mapped addresses of
+ * every rank's mailbox (ec_p2p_mailbox_bytes each, zero-initialised, symmetric memory); mode 0: data [n] <- sum over ranks;
+ * mode 1: data [2, n/2] = (mean, M2) with `count` local frames <- Chan merge over ranks, total count to out_count (device, optional). */
+size_t ec_p2p_mailbox_bytes(int world);
+int ec_p2p_max_payload_floats(void);
+int ec_p2p_bn_exchange(const unsigned long long* peer_ptrs, int rank, int world, float* data, int n, int mode, float count,
+                       float* out_count, void* stream);
+int ec_p2p_error(const unsigned long long* peer_ptrs, int rank, int world, int* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,7 +70,8 @@ def _syncbn_worker(rank, world, port, q):
             lo, hi = bounds[rank]
             x = full[lo:hi]
             stats = torch.stack([x.mean(0), ((x - x.mean(0)) ** 2).sum(0)])
-            red = D.SyncBatchNormReducer(None, "cpu", uniform=uniform)
+            red = D.make_sync_bn_reducer(None, "cpu", uniform=uniform)        # no peer memory on CPU: every rank agrees on the NCCL / gloo reducer
+            assert type(red) is D.SyncBatchNormReducer
             n = red.forward_stats(stats, float(hi - lo))
             sums = torch.stack([x.sum(0), (x * x).sum(0)])
             red.backward_sums(sums)
