@@ -344,13 +344,14 @@ static bool tc_path_enabled() {
 }
 
 int launch_relpos_attention_bwd(int precision, const AttnArgs& a, const float* dO, float* dqkv, float* dE, float* du, float* dv, void* work,
-                                cudaStream_t stream) {
+                                cudaStream_t stream, void* dqkv_act) {
   EC_REQUIRE(a.G >= 1 && a.G % 2 == 1 && (a.G * a.D) % a.H == 0, "attention backward: bad head layout");
-  EC_REQUIRE(dO && dqkv && dE && du && dv && work, "attention backward: null argument");
+  EC_REQUIRE(dO && (dqkv || dqkv_act) && dE && du && dv && work, "attention backward: null argument");
   // bf16 operand mode: batched tensor-core GEMMs (attention_bwd_tc.cu); the CUDA-core kernels below are the TF32 parity path
   // (split mode: the packed operands are rounded to bf16 while packing -- the gradients of the attention core are bf16 grade)
   if ((precision == EC_PREC_BF16 || precision == EC_PREC_BF16X2) && tc_path_enabled() && (a.T + a.G - 1) / a.G <= 1024)
-    return launch_relpos_attention_bwd_tc(precision, a, dO, dqkv, dE, du, dv, work, stream);
+    return launch_relpos_attention_bwd_tc(precision, a, dO, dqkv, dE, du, dv, work, stream, dqkv_act);
+  EC_REQUIRE(dqkv != nullptr, "attention backward (CUDA-core parity path): the fp32 dqkv buffer is required");
   EC_REQUIRE(precision != EC_PREC_BF16X2, "attention backward: the split mode needs the tensor-core path (<= 1024 grouped frames)");
   BwdDev p{};
   p.qkv = a.qkv; p.E = a.E; p.u = a.u; p.v = a.v; p.x_len = a.x_len; p.dO = dO;
@@ -390,6 +391,7 @@ int launch_relpos_attention_bwd(int precision, const AttnArgs& a, const float* d
   EC_CUDA(cudaGetLastError());
   attn_bwd_uv_reduce_kernel<<<cdiv(p.D, 128), 128, 0, stream>>>(p.du_part, p.dv_part, p.B * p.H, p.D, du, dv);
   EC_CUDA(cudaGetLastError());
+  if (dqkv_act != nullptr) EC_TRY(launch_cast_rows(precision, dqkv, dqkv_act, static_cast<size_t>(a.B) * a.T * 3 * a.D, stream));
   return EC_OK;
 }
 

@@ -162,6 +162,7 @@ struct TcDev {
   float *dV, *dK, *dQu, *dQv, *dEp;          // [BH, Tg, dp] x4, [BH, R, dp]
   float *uv_part;                            // [BH][2][dp]
   float *dqkv, *dE, *du, *dv;
+  void* dqkv_act; int act_prec;              // optional: dq | dk | dv straight in the activation type (operand of the QKV weight / data gradient GEMMs)
 };
 
 // ---- pack: dense per-head operands.  One thread per (bh, i, PAIR of features c, c+1): d, D and f = h*d + c are even, so a pair
@@ -317,7 +318,22 @@ __global__ void __launch_bounds__(256) tc_rows_kernel(const TcDev p) {
 }
 
 // ---- unpack: dq = dQu + dQv, dk, dv -> dqkv [B*T, 3D] (real frames); one thread per channel pair (64-bit accesses) ----------------
-__global__ void __launch_bounds__(256) tc_unpack_kernel(const TcDev p) {
+template <typename TO> __device__ __forceinline__ void unpack_store(void* base, long long i, float a, float b);
+template <> __device__ __forceinline__ void unpack_store<float>(void* base, long long i, float a, float b) {
+  *reinterpret_cast<float2*>(reinterpret_cast<float*>(base) + i) = make_float2(a, b);
+}
+struct Tf32Out {};
+template <> __device__ __forceinline__ void unpack_store<Tf32Out>(void* base, long long i, float a, float b) {
+  *reinterpret_cast<float2*>(reinterpret_cast<float*>(base) + i) = make_float2(round_tf32(a), round_tf32(b));
+}
+template <> __device__ __forceinline__ void unpack_store<bf16>(void* base, long long i, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<bf16*>(base) + i) = __floats2bfloat162_rn(a, b);
+}
+template <> __device__ __forceinline__ void unpack_store<SplitBf16>(void* base, long long i, float a, float b) {
+  *reinterpret_cast<uint2*>(reinterpret_cast<uint32_t*>(base) + i) = make_uint2(split_pack(a), split_pack(b));
+}
+template <typename TO>
+__global__ void __launch_bounds__(256) tc_unpack_kernel(const TcDev p, void* __restrict__ out_base) {
   const int hD = p.D / 2;
   const long long n = static_cast<long long>(p.B) * p.T * hD;
   for (long long idx2 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx2 < n; idx2 += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -327,11 +343,12 @@ __global__ void __launch_bounds__(256) tc_unpack_kernel(const TcDev p) {
     const int i = frame / p.G, fo = frame - i * p.G;
     const int f = fo * p.D + ch, h = f / p.d, c = f - h * p.d;
     const long long src = ((static_cast<long long>(b) * p.H + h) * p.Tg + i) * p.dp + c;
-    float* out = p.dqkv + bt * 3 * p.D;
+    const long long o = bt * 3 * p.D + ch;
     const float2 a = *reinterpret_cast<const float2*>(p.dQu + src), a2 = *reinterpret_cast<const float2*>(p.dQv + src);
-    *reinterpret_cast<float2*>(out + ch) = make_float2(a.x + a2.x, a.y + a2.y);
-    *reinterpret_cast<float2*>(out + p.D + ch) = *reinterpret_cast<const float2*>(p.dK + src);
-    *reinterpret_cast<float2*>(out + 2 * p.D + ch) = *reinterpret_cast<const float2*>(p.dV + src);
+    const float2 k = *reinterpret_cast<const float2*>(p.dK + src), v = *reinterpret_cast<const float2*>(p.dV + src);
+    unpack_store<TO>(out_base, o, a.x + a2.x, a.y + a2.y);
+    unpack_store<TO>(out_base, o + p.D, k.x, k.y);
+    unpack_store<TO>(out_base, o + 2 * p.D, v.x, v.y);
   }
 }
 // column sums of dQu / dQv over the grouped rows of one (b, h): uv_part[bh][0 | 1][c].  Block = 32 columns x 32 row lanes, lane ty
@@ -423,7 +440,7 @@ inline int egrid(long long n) { return static_cast<int>(std::min<long long>((n +
 size_t attention_bwd_tc_work_bytes(int B, int T, int D, int H, int G) { return tc_layout(B, T, D, H, G).total; }
 
 int launch_relpos_attention_bwd_tc(int precision, const AttnArgs& a, const float* dO, float* dqkv, float* dE, float* du, float* dv, void* work,
-                                   cudaStream_t st) {
+                                   cudaStream_t st, void* dqkv_act) {
   TcDev p{};
   p.qkv = a.qkv; p.E = a.E; p.u = a.u; p.v = a.v; p.x_len = a.x_len; p.dO = dO;
   p.B = a.B; p.T = a.T; p.D = a.D; p.H = a.H; p.G = a.G;
@@ -441,7 +458,7 @@ int launch_relpos_attention_bwd_tc(int precision, const AttnArgs& a, const float
   p.P = reinterpret_cast<bf16*>(at(9)); p.dS = reinterpret_cast<bf16*>(at(10)); p.dRel = reinterpret_cast<bf16*>(at(11));
   p.dV = reinterpret_cast<float*>(at(12)); p.dK = reinterpret_cast<float*>(at(13)); p.dQu = reinterpret_cast<float*>(at(14));
   p.dQv = reinterpret_cast<float*>(at(15)); p.dEp = reinterpret_cast<float*>(at(16)); p.uv_part = reinterpret_cast<float*>(at(17));
-  p.dqkv = dqkv; p.dE = dE; p.du = du; p.dv = dv;
+  p.dqkv = dqkv; p.dE = dE; p.du = du; p.dv = dv; p.dqkv_act = dqkv_act; p.act_prec = precision;
   const int BH = a.B * a.H, Tg = p.Tg, dp = p.dp;
   const long long sD = static_cast<long long>(Tg) * dp, sS = static_cast<long long>(Tg) * p.Tp, sR = static_cast<long long>(Tg) * p.Rp;
   const long long sE = static_cast<long long>(p.R) * dp;
@@ -491,8 +508,18 @@ int launch_relpos_attention_bwd_tc(int precision, const AttnArgs& a, const float
     EC_CUDA(cudaEventRecord(ss.fork_ev, st));                          // (after the join: dQu / dQv are complete at this point of `st`)
     EC_CUDA(cudaStreamWaitEvent(s1, ss.fork_ev, 0));
   }
-  if (pairs) tc_unpack_kernel<<<egrid(static_cast<long long>(a.B) * a.T * a.D / 2), 256, 0, st>>>(p);
-  else tc_unpack_scalar_kernel<<<egrid(static_cast<long long>(a.B) * a.T * a.D), 256, 0, st>>>(p);
+  const int ugrid = egrid(static_cast<long long>(a.B) * a.T * a.D / 2);
+  if (pairs && p.dqkv_act != nullptr) {             // the consumer only reads the activation-type copy: skip the fp32 tensor
+    if (p.act_prec == EC_PREC_BF16) tc_unpack_kernel<bf16><<<ugrid, 256, 0, st>>>(p, p.dqkv_act);
+    else if (p.act_prec == EC_PREC_BF16X2) tc_unpack_kernel<SplitBf16><<<ugrid, 256, 0, st>>>(p, p.dqkv_act);
+    else tc_unpack_kernel<Tf32Out><<<ugrid, 256, 0, st>>>(p, p.dqkv_act);
+  } else {
+    EC_REQUIRE(p.dqkv != nullptr, "attention backward: no fp32 dqkv buffer");
+    if (pairs) tc_unpack_kernel<float><<<ugrid, 256, 0, st>>>(p, p.dqkv);
+    else tc_unpack_scalar_kernel<<<egrid(static_cast<long long>(a.B) * a.T * a.D), 256, 0, st>>>(p);
+    EC_CUDA(cudaGetLastError());
+    if (p.dqkv_act != nullptr) EC_TRY(launch_cast_rows(p.act_prec, p.dqkv, p.dqkv_act, static_cast<size_t>(a.B) * a.T * 3 * a.D, st));
+  }
   EC_CUDA(cudaGetLastError());
   tc_uv_part_kernel<<<dim3(BH, cdiv(dp, 32)), 1024, 0, s1>>>(p);
   EC_CUDA(cudaGetLastError());

@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(1024) partial_reduce_kernel(const float* __res
   float s = 0.f;
   if (i < n) {
     const int j = i / dim, c = i - j * dim;
+#pragma unroll 8
     for (int p = p0; p < p1; ++p) s += partial[(static_cast<size_t>(p) * n_out + j) * dim + c];
   }
   sm[ty][tx] = s;

@@ -19,7 +19,8 @@ namespace ec {
 
 namespace {
 constexpr int kRun = 16;        // output frames per thread run (register sliding window over the taps)
-constexpr int kMaxRunCtas = 2048;
+constexpr int kMaxRunCtas = 2048;   // data-gradient runs
+constexpr int kStatRunCtas = 444;   // forward runs (3 CTAs / SM): every CTA leaves one (count, mean, M2) partial per channel
 constexpr int kColCtas = 592;   // 4 per SM: CTAs of the column-reduction kernels
 constexpr int kMaxTaps = 31;
 }  // namespace
@@ -126,8 +127,10 @@ __device__ __forceinline__ float chunked_sum_32x32(const float* __restrict__ par
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int per = (n_partial + 31) / 32, p0 = ty * per, p1 = min(n_partial, p0 + per);
   float s = 0.f;
-  if (ok)
+  if (ok) {
+#pragma unroll 8
     for (int p = p0; p < p1; ++p) s += partial[static_cast<size_t>(p) * stride + i];
+  }
   sm[ty][tx] = s;
   __syncthreads();
   float t = 0.f;
@@ -372,7 +375,7 @@ __global__ void __launch_bounds__(1024) dwconv_wgrad_reduce_kernel(const float* 
 
 // ---- host side -----------------------------------------------------------------------------------------------------------------
 size_t conv_train_work_bytes(int C, int K) {
-  const size_t a = static_cast<size_t>(kMaxRunCtas) * 3 * C, b = static_cast<size_t>(kColCtas) * C * std::max(K + 1, 2);
+  const size_t a = static_cast<size_t>(kStatRunCtas) * 3 * C, b = static_cast<size_t>(kColCtas) * C * std::max(K + 1, 2);
   return align_up(std::max(a, b) * sizeof(float), 256);
 }
 
@@ -383,7 +386,7 @@ int launch_dwconv_raw(int precision, const void* x, const float* w, const float*
                       float* sums /* [2][C] */, float* work, cudaStream_t st) {
   EC_REQUIRE(K % 2 == 1 && K <= kMaxTaps && (stride == 1 || stride == 2), "depthwise conv: odd k <= 31, stride 1 or 2");
   const int T_out = (T - 1) / stride + 1;
-  const int ctas = run_ctas(B, T_out);
+  const int ctas = std::min(run_ctas(B, T_out), kStatRunCtas);
   dim3 grid(ctas, cdiv(C, 128));
   // tap loops are fully unrolled: 15-tap (Efficient Conformer) or 31-tap instances, stride 1 or 2
 #define EC_RAW(KT, S) EC_DISPATCH_PREC(precision, (dwconv_run_kernel<ActT, KT, S, false><<<grid, 128, 0, st>>>(reinterpret_cast<const ActT*>(x), w, bias, B, T, T_out, C, K, y, work)))

@@ -274,10 +274,11 @@ int try_launch_relpos_attention_tma(const AttnArgs& a, cudaStream_t stream, bool
 size_t attention_bwd_work_bytes(int B, int T, int D, int H, int G);
 size_t attention_bwd_tc_work_bytes(int B, int T, int D, int H, int G);
 struct AttnArgs;
+// dqkv_act (optional): dq | dk | dv in the activation type; the tensor-core path then skips the fp32 dqkv (which may be null)
 int launch_relpos_attention_bwd_tc(int precision, const AttnArgs& a, const float* dO, float* dqkv, float* dE, float* du, float* dv, void* work,
-                                   cudaStream_t stream);
+                                   cudaStream_t stream, void* dqkv_act = nullptr);
 int launch_relpos_attention_bwd(int precision, const AttnArgs& a, const float* dO, float* dqkv, float* dE, float* du, float* dv, void* work,
-                                cudaStream_t stream);
+                                cudaStream_t stream, void* dqkv_act = nullptr);
 
 struct DwConvArgs {
   const void* x;         // [B, T, C] activation type (GLU output)

@@ -746,6 +746,13 @@ int ec_op_relpos_attention_bwd(int precision, const void* qkv, const void* E, co
              (precision == EC_PREC_BF16X2 && attn_operands_f16(dim, heads, group)) ? 1 : 0};
   return launch_relpos_attention_bwd(precision, a, d_out, dqkv, dE, du, dv, work, reinterpret_cast<cudaStream_t>(stream));
 }
+int ec_op_relpos_attention_bwd_act(int precision, const void* qkv, const void* E, const float* u, const float* v, const int32_t* x_len, int batch,
+                                   int t, int dim, int heads, int group, const float* d_out, float* dqkv_f32, void* dqkv_act, float* dE,
+                                   float* du, float* dv, void* work, void* stream) {
+  AttnArgs a{qkv, E, u, v, x_len, batch, t, dim, heads, group, nullptr, dim, 0,
+             (precision == EC_PREC_BF16X2 && attn_operands_f16(dim, heads, group)) ? 1 : 0};
+  return launch_relpos_attention_bwd(precision, a, d_out, dqkv_f32, dE, du, dv, work, reinterpret_cast<cudaStream_t>(stream), dqkv_act);
+}
 size_t ec_op_conv_train_work_bytes(int channels, int k) { return conv_train_work_bytes(channels, k); }
 int ec_op_dwconv_raw(int precision, const void* x, const float* w, const float* bias, int batch, int t, int channels, int k, int stride,
                      float* y, float* sums, void* work, void* stream) {

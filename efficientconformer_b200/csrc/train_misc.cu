@@ -96,31 +96,97 @@ int launch_strided_rows_bwd(const float* d, int B, int T_in, int D, int stride, 
 }
 
 // ---- per-column statistics of an fp32 matrix: stats[0][c] = mean, stats[1][c] = centred sum of squares (two-pass per CTA + Chan) ----
-__global__ void __launch_bounds__(128) col_stats_kernel(const float* __restrict__ y, size_t rows, int cols, float* __restrict__ partial) {
-  const int c = blockIdx.y * 128 + threadIdx.x;
-  if (c >= cols) return;
-  size_t r0, r1; cta_rows(rows, r0, r1);
-  float s1 = 0.f, s2 = 0.f;
-  for (size_t r = r0; r < r1; ++r) s1 += y[r * cols + c];
-  const float lm = r1 > r0 ? s1 / static_cast<float>(r1 - r0) : 0.f;
-  for (size_t r = r0; r < r1; ++r) { const float d = y[r * cols + c] - lm; s2 = fmaf(d, d, s2); }
-  partial[(static_cast<size_t>(blockIdx.x) * 2) * cols + c] = lm;
-  partial[(static_cast<size_t>(blockIdx.x) * 2 + 1) * cols + c] = s2;
-}
-__global__ void col_stats_merge_kernel(const float* __restrict__ partial, int n_partial, size_t rows, int cols, float* __restrict__ stats) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  const size_t per = (rows + n_partial - 1) / n_partial;
-  double n = 0.0, mean = 0.0, m2 = 0.0;
-  for (int p = 0; p < n_partial; ++p) {
-    const size_t r0 = min(rows, per * p), r1 = min(rows, r0 + per);
-    const double nb = static_cast<double>(r1 - r0);
-    if (nb == 0.0) continue;
-    const double mb = partial[(static_cast<size_t>(p) * 2) * cols + c], qb = partial[(static_cast<size_t>(p) * 2 + 1) * cols + c];
-    const double tot = n + nb, dl = mb - mean;
-    mean += dl * nb / tot; m2 += qb + dl * dl * n * nb / tot; n = tot;
+// thread = 4 consecutive columns (128-bit loads), block = 32 column quads x 8 row lanes over a contiguous row range; two passes over the
+// CTA's rows (mean, then centred squares: sum of squares minus mean^2 loses every digit when |mean| >> std), 4 rows in flight per
+// thread; the 8 row lanes are Chan-merged in shared memory in lane order.  partial[cta.x] = (count, mean, M2) per column.
+__global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict__ y, size_t rows, int cols, float* __restrict__ partial) {
+  __shared__ float sm[3][8][132];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.y * 128 + tx * 4;
+  const bool ok = c < cols;
+  const size_t per = (rows + gridDim.x - 1) / gridDim.x;
+  const size_t r0 = min(rows, per * blockIdx.x), r1 = min(rows, r0 + per);
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  int cnt = 0;
+  if (ok) {
+    for (size_t r = r0 + ty; r < r1; r += 32) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const size_t rr = r + 8 * u; v[u] = rr < r1 ? *reinterpret_cast<const float4*>(y + rr * cols + c) : make_float4(0, 0, 0, 0); cnt += rr < r1; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s1[0] += v[u].x; s1[1] += v[u].y; s1[2] += v[u].z; s1[3] += v[u].w; }
+    }
+    float lm[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) lm[l] = cnt > 0 ? s1[l] / static_cast<float>(cnt) : 0.f;
+    for (size_t r = r0 + ty; r < r1; r += 32) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const size_t rr = r + 8 * u; v[u] = rr < r1 ? *reinterpret_cast<const float4*>(y + rr * cols + c) : make_float4(lm[0], lm[1], lm[2], lm[3]); }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float d0 = v[u].x - lm[0], d1 = v[u].y - lm[1], d2 = v[u].z - lm[2], d3 = v[u].w - lm[3];
+        s2[0] = fmaf(d0, d0, s2[0]); s2[1] = fmaf(d1, d1, s2[1]); s2[2] = fmaf(d2, d2, s2[2]); s2[3] = fmaf(d3, d3, s2[3]);
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) { sm[0][ty][tx * 4 + l] = static_cast<float>(cnt); sm[1][ty][tx * 4 + l] = lm[l]; sm[2][ty][tx * 4 + l] = s2[l]; }
+  } else {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) { sm[0][ty][tx * 4 + l] = 0.f; sm[1][ty][tx * 4 + l] = 0.f; sm[2][ty][tx * 4 + l] = 0.f; }
   }
-  stats[c] = static_cast<float>(mean); stats[cols + c] = static_cast<float>(m2);
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int col = threadIdx.x, cc = blockIdx.y * 128 + col;
+    float n = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float nb = sm[0][q][col];
+      if (nb == 0.f) continue;
+      const float tot = n + nb, dl = sm[1][q][col] - mean, f = nb / tot;
+      mean = fmaf(dl, f, mean);
+      m2 += sm[2][q][col] + dl * dl * n * f;
+      n = tot;
+    }
+    if (cc < cols) {
+      float* o = partial + static_cast<size_t>(blockIdx.x) * 3 * cols + cc;
+      o[0] = n; o[cols] = mean; o[2 * static_cast<size_t>(cols)] = m2;
+    }
+  }
+}
+// (count, mean, M2) partials -> stats[0][c] = mean, stats[1][c] = M2: block = 32 columns x 32 lanes, lane ty merges the contiguous chunk
+// ty of the partials in order, the 32 chunk results are merged in lane order in double (fixed order, short dependent chains)
+__global__ void __launch_bounds__(1024) col_stats_merge_kernel(const float* __restrict__ partial, int n_partial, int cols, float* __restrict__ stats) {
+  __shared__ float sn[32][33], smean[32][33], sm2[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int chunk = (n_partial + 31) / 32, p0 = ty * chunk, p1 = min(n_partial, p0 + chunk);
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  if (c < cols) {
+    for (int p = p0; p < p1; ++p) {
+      const float* q = partial + static_cast<size_t>(p) * 3 * cols + c;
+      const float nb = q[0];
+      if (nb == 0.f) continue;
+      const float tot = n + nb, dl = q[cols] - mean, f = nb / tot;
+      mean = fmaf(dl, f, mean);
+      m2 += q[2 * static_cast<size_t>(cols)] + dl * dl * n * f;
+      n = tot;
+    }
+  }
+  sn[ty][tx] = n; smean[ty][tx] = mean; sm2[ty][tx] = m2;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    double dn = 0.0, dmean = 0.0, dm2 = 0.0;
+    for (int q = 0; q < 32; ++q) {
+      const double nb = sn[q][tx];
+      if (nb == 0.0) continue;
+      const double tot = dn + nb, dl = static_cast<double>(smean[q][tx]) - dmean;
+      dmean += dl * nb / tot;
+      dm2 += static_cast<double>(sm2[q][tx]) + dl * dl * dn * nb / tot;
+      dn = tot;
+    }
+    stats[c] = static_cast<float>(dmean); stats[cols + c] = static_cast<float>(dm2);
+  }
 }
 // channel c owns the `group` consecutive columns c*group .. : merge their (mean, M2) (each over `rows` samples) -> [2][C]
 __global__ void group_stats_merge_kernel(const float* __restrict__ col_stats, int C, int group, double rows, float* __restrict__ ch_stats) {
@@ -152,12 +218,18 @@ __global__ void group_sum_kernel(const float* __restrict__ in, int n_vec, int C,
   out[i] = s;
 }
 
-size_t col_stats_work_bytes(int cols) { return align_up(static_cast<size_t>(kCtas) * 2 * cols * sizeof(float), 256); }
+static constexpr int kColStatCtas = 592;
+static int col_stat_ctas(size_t rows, int cols) {
+  const int gy = cdiv(cols, 128);
+  return static_cast<int>(std::max<size_t>(1, std::min<size_t>(std::max(1, kColStatCtas / gy), (rows + 31) / 32)));
+}
+size_t col_stats_work_bytes(int cols) { return align_up(static_cast<size_t>(kColStatCtas) * 3 * cols * sizeof(float), 256); }
 int launch_col_stats(const float* y, size_t rows, int cols, float* stats, float* work, cudaStream_t st) {
-  const int ctas = static_cast<int>(std::min<size_t>(kCtas, std::max<size_t>(rows, 1)));
-  col_stats_kernel<<<dim3(ctas, cdiv(cols, 128)), 128, 0, st>>>(y, rows, cols, work);
+  EC_REQUIRE(cols % 4 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "column statistics: columns must be a multiple of 4, 16-byte aligned rows");
+  const int ctas = col_stat_ctas(rows, cols);
+  col_stats_kernel<<<dim3(ctas, cdiv(cols, 128)), 256, 0, st>>>(y, rows, cols, work);
   EC_CUDA(cudaGetLastError());
-  col_stats_merge_kernel<<<cdiv(cols, 128), 128, 0, st>>>(work, ctas, rows, cols, stats);
+  col_stats_merge_kernel<<<cdiv(cols, 32), 1024, 0, st>>>(work, ctas, cols, stats);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -194,60 +266,74 @@ __global__ void __launch_bounds__(256) subsample_melT_kernel(const float* __rest
     melT[i] = (fi >= 0 && fi < F && ti >= 0 && ti < T_in) ? mel[(static_cast<size_t>(b) * F + fi) * T_in + ti] : 0.f;
   }
 }
+// Block = CPB channels x F2 frequency threads (CPB = 128 / F2), CTA = a contiguous row range: thread (c, f) accumulates its 9 tap
+// gradients and the bias gradient over the rows, the F2 threads of a channel are then summed in shared memory in frequency order:
+// partial[cta.x][c][10] (the round-1 kernel wrote one partial per COLUMN: 114 MB of partials at C = 120).
 __global__ void __launch_bounds__(128) subsample_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ melT, int B, int F, int T_in,
-                                                              int T_out, int C, float* __restrict__ partial) {
+                                                              int T_out, int C, int cpb, float* __restrict__ partial) {
+  extern __shared__ float wg_sm[];              // [cpb * F2][10]
   const int F2 = F / 2, cols = C * F2, Fp = F + 2, Tp = T_in + 2;
-  const int col = blockIdx.y * 128 + threadIdx.x;
-  if (col >= cols) return;
-  const int f = col % F2;
+  const int nthr = cpb * F2;
+  const int c_local = threadIdx.x / F2, f = threadIdx.x - c_local * F2;
+  const int c = blockIdx.y * cpb + c_local;
+  const bool ok = threadIdx.x < nthr && c < C;
+  const int col = c * F2 + f;
   float acc[10];
 #pragma unroll
   for (int k = 0; k < 10; ++k) acc[k] = 0.f;
-  size_t r0, r1; cta_rows(static_cast<size_t>(B) * T_out, r0, r1);
-  for (size_t r = r0; r < r1; ++r) {
-    const int b = static_cast<int>(r / T_out), t = static_cast<int>(r - static_cast<size_t>(b) * T_out);
-    const float d = dy[r * cols + col];
-    // rows 2t-1 .. 2t+1 of the input are rows 2t .. 2t+2 of the bordered copy (2t+2 <= T_in+1 always); same for the frequencies
-    const float* base = melT + (static_cast<size_t>(b) * Tp + 2 * t) * Fp + 2 * f;
-    acc[9] += d;
+  const size_t rows = static_cast<size_t>(B) * T_out;
+  const size_t per = (rows + gridDim.x - 1) / gridDim.x;
+  const size_t r0 = min(rows, per * blockIdx.x), r1 = min(rows, r0 + per);
+  if (ok) {
+    for (size_t r = r0; r < r1; ++r) {
+      const int b = static_cast<int>(r / T_out), t = static_cast<int>(r - static_cast<size_t>(b) * T_out);
+      const float d = dy[r * cols + col];
+      // rows 2t-1 .. 2t+1 of the input are rows 2t .. 2t+2 of the bordered copy (2t+2 <= T_in+1 always); same for the frequencies
+      const float* base = melT + (static_cast<size_t>(b) * Tp + 2 * t) * Fp + 2 * f;
+      acc[9] += d;
 #pragma unroll
-    for (int kw = 0; kw < 3; ++kw)
+      for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh) acc[kh * 3 + kw] = fmaf(d, base[kw * Fp + kh], acc[kh * 3 + kw]);
+        for (int kh = 0; kh < 3; ++kh) acc[kh * 3 + kw] = fmaf(d, base[kw * Fp + kh], acc[kh * 3 + kw]);
+    }
   }
-  float* out = partial + (static_cast<size_t>(blockIdx.x) * cols + col) * 10;
+  if (threadIdx.x < nthr) {
 #pragma unroll
-  for (int k = 0; k < 10; ++k) out[k] = acc[k];
-}
-// block = channel c: 256 threads stride over the (partial, f) pairs, then a fixed-order shared-memory tree per tap
-__global__ void __launch_bounds__(256) subsample_wgrad_reduce_kernel(const float* __restrict__ partial, int n_partial, int C, int F2,
-                                                                     float* __restrict__ dw, float* __restrict__ db) {
-  __shared__ float sm[256][11];
-  const int c = blockIdx.x, cols = C * F2, tid = threadIdx.x;
-  float acc[10];
-#pragma unroll
-  for (int k = 0; k < 10; ++k) acc[k] = 0.f;
-  for (int idx = tid; idx < n_partial * F2; idx += 256) {
-    const int p = idx / F2, f = idx - p * F2;
-    const float* src = partial + (static_cast<size_t>(p) * cols + c * F2 + f) * 10;
-#pragma unroll
-    for (int k = 0; k < 10; ++k) acc[k] += src[k];
+    for (int k = 0; k < 10; ++k) wg_sm[threadIdx.x * 10 + k] = acc[k];
   }
-#pragma unroll
-  for (int k = 0; k < 10; ++k) sm[tid][k] = acc[k];
   __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (tid < s)
-#pragma unroll
-      for (int k = 0; k < 10; ++k) sm[tid][k] += sm[tid + s][k];
-    __syncthreads();
+  if (threadIdx.x < cpb * 10) {
+    const int cl = threadIdx.x / 10, k = threadIdx.x - cl * 10, cc = blockIdx.y * cpb + cl;
+    if (cc < C) {
+      float s_ = 0.f;
+      for (int ff = 0; ff < F2; ++ff) s_ += wg_sm[(cl * F2 + ff) * 10 + k];
+      partial[(static_cast<size_t>(blockIdx.x) * C + cc) * 10 + k] = s_;
+    }
   }
-  if (tid < 9) dw[c * 9 + tid] = sm[0][tid];
-  if (tid == 9) db[c] = sm[0][9];
+}
+// out[c][k] = sum over the CTA partials in order: block = 32 outputs x 32 lanes (chunked fixed-order sum)
+__global__ void __launch_bounds__(1024) subsample_wgrad_reduce_kernel(const float* __restrict__ partial, int n_partial, int C,
+                                                                      float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float sm[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + tx, n = C * 10;
+  const int per = (n_partial + 31) / 32, p0 = ty * per, p1 = min(n_partial, p0 + per);
+  float s_ = 0.f;
+  if (i < n)
+    for (int p = p0; p < p1; ++p) s_ += partial[static_cast<size_t>(p) * n + i];
+  sm[ty][tx] = s_;
+  __syncthreads();
+  if (ty == 0 && i < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) t += sm[q][tx];
+    const int c = i / 10, k = i - c * 10;
+    if (k < 9) dw[c * 9 + k] = t; else db[c] = t;
+  }
 }
 static constexpr int kWgCtas = 592;
 static size_t melT_bytes(int B, int F, int T) { return align_up(static_cast<size_t>(B) * (T + 2) * (F + 2) * sizeof(float), 256); }
-static size_t wg_partial_bytes(int C, int F) { return align_up(static_cast<size_t>(kWgCtas) * C * (F / 2) * 10 * sizeof(float), 256); }
+static size_t wg_partial_bytes(int C, int F) { (void)F; return align_up(static_cast<size_t>(kWgCtas) * C * 10 * sizeof(float), 256); }
 size_t subsample_wgrad_work_bytes(int C, int F, int B, int T) { return wg_partial_bytes(C, F) + melT_bytes(B, F, T); }
 int launch_subsample_wgrad(const float* dy, const float* mel, int B, int F, int T, int C, float* dw, float* db, float* work, cudaStream_t st) {
   EC_REQUIRE(F % 2 == 0, "Conv2d subsampling weight gradient: even number of mel bins");
@@ -256,9 +342,14 @@ int launch_subsample_wgrad(const float* dy, const float* mel, int B, int F, int 
   float* melT = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(work) + wg_partial_bytes(C, F));
   subsample_melT_kernel<<<grid_for(static_cast<size_t>(B) * (T + 2) * (F + 2)), 256, 0, st>>>(mel, B, F, T, melT);
   EC_CUDA(cudaGetLastError());
-  subsample_wgrad_kernel<<<dim3(ctas, cdiv(cols, 128)), 128, 0, st>>>(dy, melT, B, F, T, T_out, C, work);
+  const int F2 = F / 2;
+  EC_REQUIRE(F2 <= 128, "Conv2d subsampling weight gradient: at most 256 mel bins");
+  const int cpb = std::max(1, 128 / F2), gy = cdiv(C, cpb);
+  const int ctas_x = std::max(1, std::min(ctas, kWgCtas));      // row ranges of ~27 rows: 2.9 M threads in flight, 2.8 MB of partials
+  (void)cols;
+  subsample_wgrad_kernel<<<dim3(ctas_x, gy), 128, static_cast<size_t>(cpb) * F2 * 10 * sizeof(float), st>>>(dy, melT, B, F, T, T_out, C, cpb, work);
   EC_CUDA(cudaGetLastError());
-  subsample_wgrad_reduce_kernel<<<C, 256, 0, st>>>(work, ctas, C, F / 2, dw, db);
+  subsample_wgrad_reduce_kernel<<<cdiv(C * 10, 32), 1024, 0, st>>>(work, ctas_x, C, dw, db);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }

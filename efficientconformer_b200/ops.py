@@ -369,6 +369,29 @@ def relpos_attention_bwd(qkv_act, E_act, u, v, x_len, heads, group, d_out, preci
     return dqkv, dE, du, dv
 
 
+def relpos_attention_bwd_act(qkv_act, E_act, u, v, x_len, heads, group, d_out, precision):
+    """relpos_attention_bwd with dq | dk | dv delivered in the activation type (what the QKV weight / data gradient GEMMs read):
+    -> (dqkv_act [B,T,3D], dE fp32, du, dv)."""
+    pr = _p(precision)
+    B, T, D3 = qkv_act.shape
+    D = D3 // 3
+    dev = qkv_act.device
+    xl = x_len.to(torch.int32).contiguous() if x_len is not None else None
+    tc = pr != PREC_TF32
+    dqkv32 = None if tc else torch.empty(B, T, D3, dtype=torch.float32, device=dev)     # scratch of the TF32 CUDA-core path
+    dqkv = torch.empty(B, T, D3, dtype=act_dtype(pr), device=dev)
+    dE = torch.empty(E_act.shape, dtype=torch.float32, device=dev)
+    du = torch.empty(D, dtype=torch.float32, device=dev)
+    dv = torch.empty(D, dtype=torch.float32, device=dev)
+    work = torch.empty(lib().ec_op_relpos_attention_bwd_work_bytes(B, T, D, heads, group), dtype=torch.uint8, device=dev)
+    if tc and (D % 2 or ((group * D) // heads) % 2 or (T + group - 1) // group > 1024):
+        dqkv32 = torch.empty(B, T, D3, dtype=torch.float32, device=dev)                  # odd head layouts / very long utterances: fp32 first
+    check(lib().ec_op_relpos_attention_bwd_act(pr, ptr(qkv_act.contiguous()), ptr(E_act.contiguous()), ptr(u.float().contiguous()),
+                                               ptr(v.float().contiguous()), ptr(xl), B, T, D, heads, group, ptr(d_out.float().contiguous()),
+                                               ptr(dqkv32), ptr(dqkv), ptr(dE), ptr(du), ptr(dv), ptr(work), stream_ptr()))
+    return dqkv, dE, du, dv
+
+
 def cast_scaled(x, precision, scale):
     pr = _p(precision)
     x = x.float().contiguous()

@@ -117,17 +117,19 @@ class TrainingPath:
             return self.weights.act_t(weight)
         return _ops.transpose_cast(_w2(weight), pr)
 
-    def _wgrad(self, dy_act, x_act, pr):
-        """(dW, db) of a Linear on the side stream.  The operands are kept alive until the join at the end of backward()."""
+    def _wgrad(self, dy_act, x_act, pr, cast_first=False):
+        """(dW, db) of a Linear on the side stream.  The operands are kept alive until the join at the end of backward().
+        cast_first: dy_act is still an fp32 gradient; its cast to the activation type runs on the side stream as well."""
         if not self.side_wgrad or not dy_act.is_cuda:
-            return _ops.linear_wgrad_bias(dy_act, x_act, pr)
+            return _ops.linear_wgrad_bias(_ops.cast(dy_act, pr) if cast_first else dy_act, x_act, pr)
         if self._side is None:
             self._side = torch.cuda.Stream(device=dy_act.device)
         main = torch.cuda.current_stream(dy_act.device)
         self._side.wait_stream(main)             # dy was produced on the main stream
         with torch.cuda.stream(self._side):
-            out = _ops.linear_wgrad_bias(dy_act, x_act, pr)
-        self._side_keep.append((dy_act, x_act))
+            d = _ops.cast(dy_act, pr) if cast_first else dy_act
+            out = _ops.linear_wgrad_bias(d, x_act, pr)
+        self._side_keep.append((dy_act, d, x_act))
         return out
 
     def side_stream(self, device):
@@ -452,13 +454,12 @@ class TrainingPath:
         dw_, db_ = self._wgrad(do, att2, pr)
         grads[f"{a}.mhsa.output_layer.weight"], grads[f"{a}.mhsa.output_layer.bias"] = dw_, db_
         datt = self._dgrad(do, m.mhsa.output_layer.weight, pr)
-        dqkv, dE, du, dv = o.relpos_attention_bwd(t["qkv"].view(B, T, 3 * D), t["E"], m.mhsa.u, m.mhsa.v, t["cur_len"], H, G,
-                                                  datt.view(B, T, D), pr)
+        dqkv_act, dE, du, dv = o.relpos_attention_bwd_act(t["qkv"].view(B, T, 3 * D), t["E"], m.mhsa.u, m.mhsa.v, t["cur_len"], H, G,
+                                                          datt.view(B, T, D), pr)          # dq | dk | dv leave in the activation type
+        dqkv_act = dqkv_act.view(B * T, 3 * D)
         grads[f"{a}.mhsa.u"], grads[f"{a}.mhsa.v"] = du, dv
-        dE_act = o.cast(dE, pr)
-        dw_, db_ = self._wgrad(dE_act, t["R"], pr)
+        dw_, db_ = self._wgrad(dE, t["R"], pr, cast_first=True)         # cast + weight gradient of the positional projection: side stream
         grads[f"{a}.mhsa.pos_layer.weight"], grads[f"{a}.mhsa.pos_layer.bias"] = dw_, db_
-        dqkv_act = o.cast(dqkv.view(B * T, 3 * D), pr)
         dwqkv, dbqkv = self._wgrad(dqkv_act, t["a_in"], pr)            # [3D, D]: rows q | k | v
         for j, nm in enumerate(("query", "key", "value")):
             grads[f"{a}.mhsa.{nm}_layer.weight"] = dwqkv[j * D:(j + 1) * D]

@@ -180,6 +180,11 @@ size_t ec_op_relpos_attention_bwd_work_bytes(int batch, int t, int dim, int head
 int ec_op_relpos_attention_bwd(int precision, const void* qkv, const void* E, const float* u, const float* v, const int32_t* x_len, int batch,
                                int t, int dim, int heads, int group, const float* d_out, float* dqkv, float* dE, float* du, float* dv,
                                void* work, void* stream);
+/* same, with dq | dk | dv delivered in the activation type (dqkv_act, [B*T, 3D]): the operand of the QKV weight- and data-gradient GEMMs.
+ * The tensor-core path then never writes the fp32 tensor (dqkv_f32 may be NULL there; the TF32 CUDA-core path needs it as scratch). */
+int ec_op_relpos_attention_bwd_act(int precision, const void* qkv, const void* E, const float* u, const float* v, const int32_t* x_len, int batch,
+                                   int t, int dim, int heads, int group, const float* d_out, float* dqkv_f32, void* dqkv_act, float* dE,
+                                   float* du, float* dv, void* work, void* stream);
 /* Training-mode depthwise stage of the convolution module (reference models/modules.py:515-517 under model.train()) and its
  * backward, in stages so that the host can all-reduce the statistics across ranks between them (SyncBatchNorm):
  *   ec_op_dwconv_raw        y [B, T_out, C] fp32 = depthwise conv (raw taps w [C, k], bias); stats [2][C] = mean, centred sum of squares

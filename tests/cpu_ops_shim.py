@@ -152,6 +152,10 @@ def relpos_attention_act(qkv_act, E_act, u, v, x_len, heads, group, precision):
     return _attention(_d(qkv_act), _d(E_act), _d(u), _d(v), x_len, heads, group).contiguous()
 
 
+def relpos_attention_bwd_act(qkv_act, E_act, u, v, x_len, heads, group, d_out, precision):
+    return relpos_attention_bwd(qkv_act, E_act, u, v, x_len, heads, group, d_out, precision)
+
+
 def relpos_attention_bwd(qkv_act, E_act, u, v, x_len, heads, group, d_out, precision):
     leaves = [_d(t).clone().requires_grad_(True) for t in (qkv_act, E_act, u, v)]
     with torch.enable_grad():
