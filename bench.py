@@ -897,10 +897,39 @@ def run_ours(args, rank, world, local_rank):
                     torch.cuda.empty_cache()
                 res["ConformerCTCLarge_forward_B8_sweep"] = rows
                 res["precision"] = pr
+                # the same kernels at the shapes where they are not latency bound: plain bf16 operands (fused feed-forward cluster kernel),
+                # D = 512 / 720 -- what the tcgen05 path reaches when a tile has work (per-kernel rooflines of the T = 4000 run included)
+                big = {}
+                f = forward_record(env, "EfficientConformerCTCLarge", "bf16", 32, 1000, 10, 3, want_e2e=False, want_kernels=False)
+                big["EfficientConformerCTCLarge_forward_B32_T1000"] = {k: f[k] for k in ("value", "ms_per_step", "whole_forward_tflops", "whole_forward_frac_of_bf16_peak")}
+                f = forward_record(env, "ConformerCTCLarge", "bf16", 8, 4000, 10, 3, want_e2e=False, want_kernels=True)
+                big["ConformerCTCLarge_forward_B8_T4000"] = {k: f[k] for k in ("value", "ms_per_step", "whole_forward_tflops", "whole_forward_frac_of_bf16_peak", "rooflines")}
+                res["bf16_mode"] = big
                 return res
             guarded("configs", out, configs)
             _log(rank, "configs done")
         if world == 1:
+            def transducer_joint():
+                # configs[3] (EfficientConformerTransducerMedium): the joint network + RNN-T loss forward on the lattice of a
+                # B = 16 x 1000-frame batch (T' = 125 encoder frames, U = 50 labels; encoder 360 / decoder 640 / joint 640 / vocab 1000)
+                from efficientconformer_b200.transducer import JointNetwork, rnnt_loss
+                Bj, Tj, Uj, Denc, Ddec, J, Vj = 16, 125, 50, 360, 640, 640, 1000
+                g = torch.Generator().manual_seed(3)
+                jn = JointNetwork(Denc, Ddec, Vj, {"joint_mode": "sum", "dim_model": J, "act": "tanh"}, precision=pr).to(env.dev).eval()
+                f, gd = torch.randn(Bj, Tj, Denc, generator=g).to(env.dev), torch.randn(Bj, Uj + 1, Ddec, generator=g).to(env.dev)
+                y = torch.randint(1, Vj, (Bj, Uj), generator=g).to(env.dev)
+                fl, yl = torch.full((Bj,), Tj, device=env.dev), torch.full((Bj,), Uj, device=env.dev)
+
+                def one():
+                    with torch.no_grad():
+                        return rnnt_loss(jn(f, gd), y, fl, yl)[0]
+                ms, _ = timed_steps(env, one, 10, 3)
+                ms /= 10
+                flops = 2.0 * Bj * Tj * (Uj + 1) * J * Vj
+                return {"workload": "JointNetwork.forward + RNN-T loss (forward only; backward not built), B=16, T'=125, U=50, 360/640/640/1000",
+                        "precision": pr, "ms": ms, "lattice_nodes_per_s": Bj * Tj * (Uj + 1) / (ms / 1e3), "output_projection_tflops": round(flops / ms / 1e9, 1),
+                        "loss": float(one())}
+            guarded("transducer_joint_forward", out, transducer_joint)
             guarded("torch_eager_b200", out, lambda: torch_eager_reference(env, small, B, T))
             _log(rank, "torch eager done")
     if env.dist is not None:

@@ -155,6 +155,14 @@ _SIGNATURES = {
     "ec_op_gemm_train": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_float, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p]),
     "ec_attention_operand_kind": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ec_op_joint_hidden": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ec_rnnt_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "ec_rnnt_loss": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ec_rnnt_loss_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+    "ec_op_joint_hidden_bwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
     "ec_p2p_mailbox_bytes": (C.c_size_t, [C.c_int]),
     "ec_p2p_max_payload_floats": (C.c_int, []),
     "ec_p2p_bn_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),

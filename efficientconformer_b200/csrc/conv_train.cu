@@ -438,6 +438,14 @@ int launch_dwconv_bwd(int precision, const float* dy, const void* x, const float
                       float* dw, float* db, float* work, cudaStream_t st) {
   EC_REQUIRE(K % 2 == 1 && K <= kMaxTaps && (stride == 1 || stride == 2), "depthwise conv: odd k <= 31, stride 1 or 2");
   const int T_out = (T - 1) / stride + 1;
+  // the weight / bias gradient only feeds the optimiser: it runs beside the data gradient on a library side stream (fork / join)
+  SideStreams& ss = side_streams();
+  const bool par = dx != nullptr && side_streams_enabled() && ss.init();
+  cudaStream_t sw = par ? ss.s[3] : st;
+  if (par) {
+    EC_CUDA(cudaEventRecord(ss.fork_ev, st));
+    EC_CUDA(cudaStreamWaitEvent(sw, ss.fork_ev, 0));
+  }
   if (dx != nullptr) {
     if (stride == 1) {                 // correlation with the reversed taps: the forward run kernel on the fp32 gradient
       dim3 gd(run_ctas(B, T), cdiv(C, 128));
@@ -453,13 +461,17 @@ int launch_dwconv_bwd(int precision, const float* dy, const void* x, const float
   const int gy = cdiv(C, 128);
   const int ctas = std::max(1, std::min(std::max(1, kColCtas / 2 / gy), cdiv(B * cdiv(T_out, kRun), 4)));
   dim3 grid(ctas, gy);
-#define EC_WG(KT, S) EC_DISPATCH_PREC(precision, (dwconv_bwd_weight_kernel<ActT, KT, S><<<grid, 512, 0, st>>>(dy, reinterpret_cast<const ActT*>(x), B, T, T_out, C, K, work)))
+#define EC_WG(KT, S) EC_DISPATCH_PREC(precision, (dwconv_bwd_weight_kernel<ActT, KT, S><<<grid, 512, 0, sw>>>(dy, reinterpret_cast<const ActT*>(x), B, T, T_out, C, K, work)))
   if (K <= 15) { if (stride == 1) EC_WG(15, 1); else EC_WG(15, 2); }
   else { if (stride == 1) EC_WG(31, 1); else EC_WG(31, 2); }
 #undef EC_WG
   EC_CUDA(cudaGetLastError());
-  dwconv_wgrad_reduce_kernel<<<cdiv(C * (K + 1), 32), 1024, 0, st>>>(work, ctas, C, K, dw, db);
+  dwconv_wgrad_reduce_kernel<<<cdiv(C * (K + 1), 32), 1024, 0, sw>>>(work, ctas, C, K, dw, db);
   EC_CUDA(cudaGetLastError());
+  if (par) {
+    EC_CUDA(cudaEventRecord(ss.join_ev[3], sw));
+    EC_CUDA(cudaStreamWaitEvent(st, ss.join_ev[3], 0));
+  }
   return EC_OK;
 }
 

@@ -33,8 +33,10 @@ def _greedy_search_decoding(self, x, x_len):
     return self.tokenizer.decode(ids) if getattr(self, "tokenizer", None) is not None else ids
 
 
-def patch_reference(modules=("models.encoders", "models.model_ctc", "models.transducer"), loss=True, greedy=True):
-    """Returns the list of rebound names ("module.attr")."""
+def patch_reference(modules=("models.encoders", "models.model_ctc", "models.transducer"), loss=True, greedy=True, joint=False):
+    """Returns the list of rebound names ("module.attr").  joint=True also rebinds the Transducer's JointNetwork and LossRNNT to the CUDA
+    versions (efficientconformer_b200/transducer.py; forward and backward).  Off by default: the reference's own loss needs the
+    uninstalled third-party warp_rnnt, so the Transducer route cannot be compared with the reference end to end in this environment."""
     from .encoders import ConformerEncoder
     from .model_ctc import LossCTC
     patched = []
@@ -63,4 +65,15 @@ def patch_reference(modules=("models.encoders", "models.model_ctc", "models.tran
                 patched.append("models.model_ctc.ModelCTC.gready_search_decoding")
         except Exception:
             pass
+    if joint:
+        from .transducer import JointNetwork, LossRNNT
+        for name, attr, obj in (("models.joint_networks", "JointNetwork", JointNetwork), ("models.transducer", "JointNetwork", JointNetwork),
+                                ("models.losses", "LossRNNT", LossRNNT), ("models.transducer", "LossRNNT", LossRNNT)):
+            try:
+                mod = sys.modules.get(name) or importlib.import_module(name)
+            except Exception:
+                continue
+            if hasattr(mod, attr):
+                setattr(mod, attr, obj)
+                patched.append(f"{name}.{attr}")
     return patched

@@ -377,7 +377,7 @@ def relpos_attention_bwd_act(qkv_act, E_act, u, v, x_len, heads, group, d_out, p
     D = D3 // 3
     dev = qkv_act.device
     xl = x_len.to(torch.int32).contiguous() if x_len is not None else None
-    tc = pr != PREC_TF32
+    tc = pr != PRECISIONS["tf32"]
     dqkv32 = None if tc else torch.empty(B, T, D3, dtype=torch.float32, device=dev)     # scratch of the TF32 CUDA-core path
     dqkv = torch.empty(B, T, D3, dtype=act_dtype(pr), device=dev)
     dE = torch.empty(E_act.shape, dtype=torch.float32, device=dev)

@@ -348,6 +348,30 @@ int ec_p2p_bn_exchange(const unsigned long long* peer_ptrs, int rank, int world,
                        float* out_count, void* stream);
 int ec_p2p_error(const unsigned long long* peer_ptrs, int rank, int world, int* out);
 
+/* ---- Transducer joint network + RNN-T loss, forward (csrc/rnnt.cu) ----------------------------------------------
+ * ec_op_joint_hidden : hidden[(b,t,u), :] = act_type(act(fe[b,t,:] + gd[b,u,:])), fe [B*T, J] = Linear_enc(f), gd [B*U1, J] = Linear_dec(g)
+ *                      (both fp32, from ec_op_gemm); act 0 none, 1 tanh, 2 relu, 3 swish.  Replaces the two `repeat`s, the sum and the
+ *                      activation of reference models/joint_networks.py:84-99 (joint_mode "sum"); the output projection
+ *                      (joint_networks.py:102) is ec_op_gemm on `hidden`.
+ * ec_rnnt_loss       : logits [B, T, U1, V] fp32 (U1 = U + 1), labels [B, label_stride] int64, frame_len / label_len [B] int64 ->
+ *                      loss_per_utt [B] = -log p(labels | frames) (Graves 2012), loss_mean [1] = their mean: what the reference gets from
+ *                      warp_rnnt.rnnt_loss(log_softmax(logits), ..., average_frames=False, reduction='mean', blank=0, gather=True)
+ *                      (models/losses.py:22-46).  scratch: ec_rnnt_scratch_bytes(B, T, U1). */
+int ec_op_joint_hidden(int precision, const float* fe, const float* gd, int batch, int t, int u1, int dim_joint, int act, void* hidden, void* stream);
+size_t ec_rnnt_scratch_bytes(int batch, int t, int u1);
+int ec_rnnt_loss(const float* logits, int batch, int t, int u1, int vocab, const long long* labels, int label_stride, const long long* frame_len,
+                 const long long* label_len, int blank, void* scratch, float* loss_per_utt, float* loss_mean, void* stream);
+/* ec_rnnt_loss_grad  : the same plus grad [B, T, U1, V] = grad_scale * d(sum_b nll_b) / d logits with the log_softmax folded in (alpha and
+ *                      beta wavefronts, Graves 2012 eq. 16-20): what autograd computes through warp_rnnt.rnnt_loss and F.log_softmax
+ *                      (models/losses.py:36-44); grad_scale = 1 / B for reduction = 'mean'.
+ * ec_op_joint_hidden_bwd : gradient through hidden = act(fe + gd) and the two broadcasts (`repeat`s of models/joint_networks.py:88-89):
+ *                      dfe [B*T, J] = sum_u d_hidden * act'(hidden), dgd [B*U1, J] = sum_t ...; act' from the stored output (none / tanh / relu). */
+int ec_rnnt_loss_grad(const float* logits, int batch, int t, int u1, int vocab, const long long* labels, int label_stride,
+                      const long long* frame_len, const long long* label_len, int blank, void* scratch, float* loss_per_utt, float* loss_mean,
+                      float grad_scale, float* grad, void* stream);
+int ec_op_joint_hidden_bwd(int precision, const void* hidden, const float* d_hidden, int batch, int t, int u1, int dim_joint, int act, float* dfe,
+                           float* dgd, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

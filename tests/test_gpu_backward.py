@@ -273,6 +273,26 @@ def test_relpos_attention_backward(ops, prec):
 
 
 @pytest.mark.parametrize("prec", ["bf16x2", "tf32", "bf16"])
+def test_relpos_attention_backward_activation_type_output(ops, prec):
+    """ec_op_relpos_attention_bwd_act writes dq | dk | dv straight in the activation type: equal to casting the fp32 result, for the
+    paired (even dims) and the scalar (odd head dim) unpack kernels."""
+    for (B, T, D, H, G) in ((3, 50, 120, 4, 3), (2, 33, 168, 4, 1), (2, 40, 100, 4, 3)):
+        if prec == "bf16" and D % 8:
+            continue
+        g = torch.Generator().manual_seed(B * 100 + T)
+        qkv = ops.cast_attn_operand(torch.randn(B, T, 3 * D, generator=g).to(DEV), prec, D, H, G)
+        Tp = T + (-T) % G
+        E = ops.cast_attn_operand((0.3 * torch.randn(2 * Tp - G, D, generator=g)).to(DEV), prec, D, H, G)
+        u, v = (0.2 * torch.randn(D, generator=g)).to(DEV), (0.2 * torch.randn(D, generator=g)).to(DEV)
+        x_len = torch.tensor([T] + [max(1, T - 7 * b) for b in range(1, B)], device=DEV)
+        dout = torch.randn(B, T, D, generator=g).to(DEV)
+        dqkv, dE, du, dv = ops.relpos_attention_bwd(qkv, E, u, v, x_len, H, G, dout, prec)
+        dq2, dE2, du2, dv2 = ops.relpos_attention_bwd_act(qkv, E, u, v, x_len, H, G, dout, prec)
+        assert torch.equal(ops.unpack(dq2, prec), ops.unpack(ops.cast(dqkv, prec), prec)), (prec, B, T, D, H, G)
+        assert torch.equal(dE, dE2) and torch.equal(du, du2) and torch.equal(dv, dv2)
+
+
+@pytest.mark.parametrize("prec", ["bf16x2", "tf32", "bf16"])
 def test_subsampling_conv2d_batchnorm2d_training_forward_backward(ops, prec):
     """Train-mode Conv2d(1->C,3x3,s2) -> BatchNorm2d (batch statistics) -> Swish in the layout of the following Linear, and the
     weight / bias / BatchNorm gradients, against fp64 autograd over torch's conv2d / batch_norm."""

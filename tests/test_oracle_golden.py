@@ -229,3 +229,17 @@ def test_training_step_medium_config_loss_gradients_and_running_stats(golden_dir
     assert worst < 2e-3, worst
     for k, ref in g["running_stats"].items():
         assert rel_l2(bn["updates"][k[len("encoder."):]], ref) < 1e-5, k
+
+
+def test_rnnt_oracle_against_reference_joint_and_torchaudio_loss(golden_dir):
+    """the joint restatement against the real reference JointNetwork's logits, the RNN-T recursion against
+    torchaudio.functional.rnnt_loss values (tests/golden/make_golden_rnnt.py)."""
+    from oracle import rnnt_oracle as R
+    cases = torch.load(os.path.join(golden_dir, "rnnt_joint_small.pt"))
+    for name, c in cases.items():
+        logits = R.joint_forward(c["state_dict"], c["f"], c["g"])
+        ref = c["logits"]
+        assert rel_l2(logits[:, :ref.shape[1]], ref) < 2e-6, name
+        mean, per = R.rnnt_loss(logits.double(), c["y"], c["f_len"], c["y_len"])
+        assert torch.allclose(per.float(), c["loss_per_utt"], rtol=2e-5, atol=1e-4), (name, per, c["loss_per_utt"])
+        assert abs(float(mean) - float(c["loss_mean"])) < 2e-5 * abs(float(c["loss_mean"]))
