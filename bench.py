@@ -735,15 +735,30 @@ def torch_eager_reference(env, config, B, T, steps=5):
 
 
 def _finish(env, step):
-    """Leave a multi-rank run: drop the captured graphs (they hold NCCL kernels), then exit without waiting on communicator teardown."""
+    """Leave a multi-rank run in order: drop the captured graphs (they hold NCCL kernels), synchronise, destroy the process group.  The
+    communicator teardown runs under a 20 s guard: should it stall (seen in round 1 while graphs still referenced NCCL kernels) the
+    result is already printed and the process leaves without it."""
     if env.dist is None:
         return
     if step is not None:
         step.close()
     import gc
+    import threading
     gc.collect()
+    torch.cuda.synchronize()
     sys.stdout.flush(); sys.stderr.flush()
-    os._exit(0)
+    done = threading.Event()
+
+    def teardown():
+        try:
+            env.dist.destroy_process_group()
+        finally:
+            done.set()
+    threading.Thread(target=teardown, daemon=True).start()
+    if not done.wait(20.0):
+        sys.stderr.write(f"[bench rank {env.rank}] process-group teardown did not finish within 20 s; leaving without it\n")
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def guarded(name, out, fn):

@@ -154,6 +154,8 @@ _SIGNATURES = {
                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ec_op_gemm_train": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_float, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p]),
+    "ec_op_gemm_ln_train": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.c_uint, C.c_void_p]),
     "ec_attention_operand_kind": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ec_op_joint_hidden": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ec_rnnt_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
@@ -205,7 +207,7 @@ class OpProfile:
     """Measurement hook (bench.py, tools/): while active, every operator entry point (ec_op_*, ec_ctc_*, ec_adam_step) is bracketed by
     a CUDA-event pair on the launching stream; `summary()` returns per-entry-point launch counts, device time and the algorithmic
     FLOPs of the tensor-core operators (2*M*N*K from the call's own arguments).  Eager launches only (not under graph capture)."""
-    _GEMM_ARGS = {"ec_op_gemm": (3, 4, 5), "ec_op_gemm_ex": (3, 4, 5), "ec_op_gemm_train": (3, 4, 5), "ec_op_wgrad": (3, 4, 5), "ec_op_wgrad_bias": (3, 4, 5), "ec_op_gemm_ln": (3, 4, 5)}
+    _GEMM_ARGS = {"ec_op_gemm": (3, 4, 5), "ec_op_gemm_ex": (3, 4, 5), "ec_op_gemm_train": (3, 4, 5), "ec_op_gemm_ln_train": (3, 4, 5), "ec_op_wgrad": (3, 4, 5), "ec_op_wgrad_bias": (3, 4, 5), "ec_op_gemm_ln": (3, 4, 5)}
 
     def __init__(self):
         self.records = []

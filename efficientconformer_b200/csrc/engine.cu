@@ -856,6 +856,16 @@ int ec_op_gemm_ln(int precision, const void* A, const void* W, int M, int N, int
   g.copy_out = copy_out; g.copy_stride = copy_stride; g.frames_per_seq = frames_per_seq; g.frames_out_per_seq = frames_out_per_seq;
   return launch_gemm(precision, g, reinterpret_cast<cudaStream_t>(stream));
 }
+int ec_op_gemm_ln_train(int precision, const void* A, const void* W, int M, int N, int K, const float* bias, float alpha, const float* residual,
+                        float* out_f32, const float* g1, const float* b1, float eps, void* ln_out, const unsigned long long* drop_counter,
+                        float drop_p, unsigned drop_site, void* stream) {
+  GemmArgs g{};
+  g.A = A; g.W = W; g.M = M; g.N = N; g.K = K; g.bias = bias; g.alpha = alpha; g.act = GEMM_ACT_NONE;
+  g.residual = residual; g.ld_res = N; g.out_f32 = out_f32; g.ld_out = N;
+  g.ln_mode = 1; g.ln1_g = g1; g.ln1_b = b1; g.ln_eps = eps; g.ln_out = ln_out;
+  g.drop_ctr = drop_counter; g.drop_p = drop_p; g.drop_site = drop_site;
+  return launch_gemm(precision, g, reinterpret_cast<cudaStream_t>(stream));
+}
 int ec_op_ffn(const void* x_act, const void* w1, const float* b1, const void* w2, const float* b2, int M, int D, int hidden,
               const float* residual, float* out_f32, int ln_mode, const float* g1, const float* be1, const float* g2, const float* be2,
               float eps, void* ln_out, int cluster, void* stream) {

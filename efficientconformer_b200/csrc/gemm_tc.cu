@@ -224,8 +224,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* slabA2 = slabA + nbuf * kASlab;                 // second activation-type output (plain variant, training step)
     // counter-based dropout: keys of the three possible sites; element index = row * N + column (groups of 4 share one 64-bit draw)
     unsigned long long key_out = 0, key_act2 = 0, key_aux = 0;
+    if (p.drop_ctr != nullptr && p.drop_site) key_out = site_key(p.drop_ctr, p.drop_site);      // (also in the fused-LayerNorm variant)
     if (!kLN && p.drop_ctr != nullptr) {
-      if (p.drop_site) key_out = site_key(p.drop_ctr, p.drop_site);
       if (p.drop_site2) key_act2 = site_key(p.drop_ctr, p.drop_site2);
       if (p.drop_site_aux) key_aux = site_key(p.drop_ctr, p.drop_site_aux);
     }
@@ -313,13 +313,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           if (lane == 0 && i + rdepth < my_chunks) issue_res(i + rdepth);
         }
-        if (p.drop_site) {
+      }
+      if (p.drop_site) {                                   // nn.Dropout behind the projection (both variants)
+        const unsigned long long gd0 = (grow + static_cast<unsigned long long>(out_col0 + c0)) >> 2;
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const unsigned long long draw = splitmix64(key_out + g0 + j4);
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const unsigned long long draw = splitmix64(key_out + gd0 + j4);
 #pragma unroll
-            for (int l = 0; l < 4; ++l) t[4 * j4 + l] *= keep_factor(draw, l, p.drop_keep16, p.drop_inv_keep);
-          }
+          for (int l = 0; l < 4; ++l) t[4 * j4 + l] *= keep_factor(draw, l, p.drop_keep16, p.drop_inv_keep);
         }
       }
       if (p.has_res && (kLN || p.aux_mode == 0)) {
@@ -565,7 +566,8 @@ static int launch_gemm_t(int precision, const GemmArgs& a, cudaStream_t stream) 
   p.res_tx = (a.aux_mode != 0 && sizeof(T) == 2) ? kSlabBytes / 2 : kSlabBytes;
   const bool train_epi = a.drop_ctr != nullptr || a.out_act2 != nullptr || a.aux_mode != 0;
   if (train_epi) {
-    EC_REQUIRE(!kLN && a.glu_nb == 0, "the training epilogue options belong to the plain GEMM");
+    EC_REQUIRE(a.glu_nb == 0 && (!kLN || (a.out_act2 == nullptr && a.aux_mode == 0)),
+               "the Swish side output / Swish backward belong to the plain GEMM (the fused-LayerNorm variant takes the dropout site only)");
     EC_REQUIRE(a.N % 4 == 0, "dropout masks are drawn in groups of 4 consecutive elements: N must be a multiple of 4");
     EC_REQUIRE(a.aux_mode == 0 || (a.aux_mode == 1 && a.aux_act != nullptr && a.residual == nullptr), "aux_mode 1 needs the saved pre-activation and no residual");
     EC_REQUIRE((a.drop_site | a.drop_site2 | a.drop_site_aux) == 0 || (a.drop_ctr != nullptr && a.drop_p >= 0.f && a.drop_p < 1.f), "dropout site without a counter / bad p");

@@ -105,6 +105,21 @@ def gemm_train(a_act, w_act, bias, precision, drop=None, alpha=1.0, residual=Non
     return of, oa, o2
 
 
+def gemm_ln_train(a_act, w_act, bias, precision, ln_g, ln_b, drop=None, alpha=1.0, residual=None, site=0, eps=1e-6):
+    """Training-step projection + dropout + residual with the NEXT module's LayerNorm fused (N <= 256, ec_op_gemm_ln_train):
+    -> (out_f32 [M, N], ln_out [M, N] activation type)."""
+    pr = _p(precision)
+    M, K = a_act.shape
+    N = w_act.shape[0]
+    live = drop is not None and drop.p > 0.0
+    of = torch.empty(M, N, dtype=torch.float32, device=a_act.device)
+    ya = torch.empty(M, N, dtype=act_dtype(pr), device=a_act.device)
+    check(lib().ec_op_gemm_ln_train(pr, ptr(a_act), ptr(w_act), M, N, K, ptr(bias), alpha, ptr(residual), ptr(of), ptr(ln_g.float().contiguous()),
+                                    ptr(ln_b.float().contiguous()), eps, ptr(ya), ptr(drop.counter) if live else None, drop.p if live else 0.0,
+                                    site if live else 0, stream_ptr()))
+    return of, ya
+
+
 def gemm_ln(a_act, w_act, bias, precision, g1, b1, g2=None, b2=None, mode=1, alpha=1.0, residual=None, eps=1e-6,
             copy_stride=0, frames_per_seq=0):
     """GEMM with the fused LayerNorm epilogue.  Returns (out_f32, ln_out_act, copy_out_act or None)."""

@@ -29,9 +29,11 @@ _ops = _ops_module       # test seam: tests/test_train_glue_cpu.py swaps in a to
 #   res  dropout + alpha + residual behind W2 / attention output / pointwise conv 2 / encoder.linear
 #   dz   Swish-dropout backward in the data-gradient GEMM of W2
 #   ln   every LayerNorm backward also emits the masked, scaled, activation-type operand of the next GEMM of the backward chain
+#   lnf  forward: the LayerNorm of the NEXT module is computed in the epilogue of the producing projection (ec_op_gemm_ln_train, rows of
+#        up to 256 features): feed-forward 1 -> attention norm, attention output -> conv-module norm, pointwise conv 2 -> feed-forward 2 norm
 # Chosen by measurement on the B200 (profiles/r2); EFFCONF_TRAIN_FUSE=w1,res,dz overrides.
 import os as _os
-FUSE = set(filter(None, _os.environ.get("EFFCONF_TRAIN_FUSE", "w1,res,dz,ln").split(",")))
+FUSE = set(filter(None, _os.environ.get("EFFCONF_TRAIN_FUSE", "w1,res,dz,ln,lnf").split(",")))
 
 
 class _null_context:
@@ -236,18 +238,28 @@ class TrainingPath:
         tape["T_out"] = Tc
         return x.view(B, Tc, D_last), logits, cur_len, tape
 
-    def _proj_drop_res(self, a_act, w_act, bias, pr, drop, site, alpha, residual):
-        """residual + alpha * dropout_site(a W^T + bias): one GEMM with the dropout in its epilogue, or GEMM + element kernel."""
+    def _proj_drop_res(self, a_act, w_act, bias, pr, drop, site, alpha, residual, next_ln=None):
+        """out = residual + alpha * dropout_site(a W^T + bias): one GEMM with the dropout in its epilogue, or GEMM + element kernel.
+        next_ln = (gamma, beta) of the LayerNorm that consumes `out`: returns (out, LN(out) in the activation type), from the same GEMM
+        epilogue when the row fits one tile (<= 256 features), else from the LayerNorm kernel."""
         o = _ops
+        if next_ln is not None and "lnf" in FUSE and "res" in FUSE and w_act.shape[0] <= 256:
+            return o.gemm_ln_train(a_act, w_act, bias, pr, next_ln[0], next_ln[1], drop, alpha=alpha, residual=residual, site=site)
         if "res" in FUSE or drop.p == 0.0:
-            return o.gemm_train(a_act, w_act, bias, pr, drop, alpha=alpha, residual=residual, site=site)[0]
-        return o.dropout_residual(o.gemm(a_act, w_act, bias, pr)[0], drop, site, alpha, residual)
+            out = o.gemm_train(a_act, w_act, bias, pr, drop, alpha=alpha, residual=residual, site=site)[0]
+        else:
+            out = o.dropout_residual(o.gemm(a_act, w_act, bias, pr)[0], drop, site, alpha, residual)
+        if next_ln is None:
+            return out
+        return out, o.layernorm(out, next_ln[0], next_ln[1], pr, want_f32=False, want_act=True)[0]
 
-    def _ffn_forward(self, holder, x, pr, drop, alpha=0.5):
-        """reference models/modules.py:378-395 + the half-step residual of models/blocks.py:122,132."""
+    def _ffn_forward(self, holder, x, pr, drop, alpha=0.5, h0=None, next_ln=None):
+        """reference models/modules.py:378-395 + the half-step residual of models/blocks.py:122,132.  h0: the module's LayerNorm output
+        when the producer of x already computed it; next_ln: see _proj_drop_res (then returns (out, saved, LN_next(out)))."""
         o = _ops
         L = holder.layers
-        h0 = o.layernorm(x, L[0].weight, L[0].bias, pr, want_f32=False, want_act=True)[0]
+        if h0 is None:
+            h0 = o.layernorm(x, L[0].weight, L[0].bias, pr, want_f32=False, want_act=True)[0]
         w1 = self._w(L[1].weight, pr)
         s1 = drop.next_site()
         # W1: the pre-activation z (kept for the backward) and s = dropout(Swish(z)) leave the same epilogue
@@ -259,8 +271,12 @@ class TrainingPath:
         w2 = self._w(L[4].weight, pr)
         s2 = drop.next_site()
         # W2: x + alpha * dropout(s W2^T + b2) in the epilogue
+        saved = lambda: (x, h0, z, s, s1, s2, alpha)
+        if next_ln is not None:
+            out, nxt = self._proj_drop_res(s, w2, L[4].bias, pr, drop, s2, alpha, x, next_ln=next_ln)
+            return out, saved(), nxt
         out = self._proj_drop_res(s, w2, L[4].bias, pr, drop, s2, alpha, x)
-        return out, (x, h0, z, s, s1, s2, alpha)
+        return out, saved()
 
     def _ffn_backward(self, holder, saved, d_out, pr, grads, prefix, dy=None, emit_next=None):
         """d_out: gradient w.r.t. the module output (fp32, modified in place); returns the gradient w.r.t. its input x.
@@ -321,10 +337,9 @@ class TrainingPath:
         D, De, H, G, st = spec.dim_model, spec.dim_expand, spec.num_heads, spec.group_size, spec.conv_stride
         if st > 1 and not spec.has_conv_res_proj:
             raise NotImplementedError("strided block without channel expansion (MaxPool residual) is not used by any shipped config")
-        x1, ffn1 = self._ffn_forward(blk.feed_forward_module1, x, pr, drop)
-        # ---- attention module (reference models/modules.py:472-488, attentions.py:549-718)
         m = blk.multi_head_self_attention_module
-        a_in = o.layernorm(x1, m.norm.weight, m.norm.bias, pr, want_f32=False, want_act=True)[0]
+        x1, ffn1, a_in = self._ffn_forward(blk.feed_forward_module1, x, pr, drop, next_ln=(m.norm.weight, m.norm.bias))
+        # ---- attention module (reference models/modules.py:472-488, attentions.py:549-718)
         wqkv, bqkv, qkv_handle = self._qkv(m.mhsa, pr)
         ab16 = o.attn_operands_f16(pr, D, H, G)                      # split mode: plain fp16 q|k|v and E for the attention core
         qkv = o.gemm(a_in, wqkv, bqkv, pr, want_f32=False, want_act=True, act_f16=ab16)[1]
@@ -332,10 +347,9 @@ class TrainingPath:
         att = o.relpos_attention_act(qkv.view(B, T, 3 * D), E, m.mhsa.u, m.mhsa.v, cur_len, H, G, pr)
         wo = self._w(m.mhsa.output_layer.weight, pr)
         s_att = drop.next_site()
-        x2 = self._proj_drop_res(att.view(B * T, D), wo, m.mhsa.output_layer.bias, pr, drop, s_att, 1.0, x1)
         # ---- convolution module (reference models/modules.py:507-525) + block residual (blocks.py:98-114,129)
         Lc = blk.convolution_module.layers
-        c_in = o.layernorm(x2, Lc[0].weight, Lc[0].bias, pr, want_f32=False, want_act=True)[0]
+        x2, c_in = self._proj_drop_res(att.view(B * T, D), wo, m.mhsa.output_layer.bias, pr, drop, s_att, 1.0, x1, next_ln=(Lc[0].weight, Lc[0].bias))
         wpw1 = self._w(Lc[2].weight, pr)
         zg = o.gemm(c_in, wpw1, Lc[2].bias, pr, want_f32=False, want_act=True)[1]
         gl = o.glu_fwd(zg, pr)
@@ -352,8 +366,9 @@ class TrainingPath:
             res = x2
         wpw2 = self._w(Lc[7].weight, pr)
         s_conv = drop.next_site()
-        x3 = self._proj_drop_res(h.view(B * To, De), wpw2, Lc[7].bias, pr, drop, s_conv, 1.0, res)
-        x4, ffn2 = self._ffn_forward(blk.feed_forward_module2, x3, pr, drop)
+        L2 = blk.feed_forward_module2.layers
+        x3, h0_2 = self._proj_drop_res(h.view(B * To, De), wpw2, Lc[7].bias, pr, drop, s_conv, 1.0, res, next_ln=(L2[0].weight, L2[0].bias))
+        x4, ffn2 = self._ffn_forward(blk.feed_forward_module2, x3, pr, drop, h0=h0_2)
         x_act, x5 = o.layernorm(x4, blk.norm.weight, blk.norm.bias, pr, want_f32=True, want_act=want_act_out)
         tape = dict(ffn1=ffn1, x1=x1, a_in=a_in, qkv=qkv, qkv_handle=qkv_handle, E=E, R=R, att=att, cur_len=cur_len, s_att=s_att, x2=x2, c_in=c_in, zg=zg,
                     h=h, dw_saved=dw_saved, xs=xs, s_conv=s_conv, ffn2=ffn2, x4=x4, T=T, To=To)

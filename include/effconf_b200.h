@@ -303,6 +303,12 @@ int ec_op_gemm_ex(int precision, const void* A, const void* W, int M, int N, int
 int ec_op_gemm_train(int precision, const void* A, const void* W, int M, int N, int K, const float* bias, float alpha,
                      const float* residual, float* out_f32, void* out_act, const unsigned long long* drop_counter, float drop_p,
                      unsigned drop_site, void* out_act2, unsigned drop_site2, const void* aux_act, unsigned drop_site_aux, void* stream);
+/* Training-step projection with the LayerNorm of the NEXT module fused (N <= 256): out_f32 = alpha * keep_{site}/(1-p) * (A W^T + bias) +
+ * residual (kept for the backward), ln_out = act_type(LN(out_f32; g1, b1, eps)) = the next GEMM's operand.  Replaces a projection, its
+ * nn.Dropout, the residual add and the following nn.LayerNorm (reference models/modules.py:386-391,433,486,511,521; blocks.py:122-132). */
+int ec_op_gemm_ln_train(int precision, const void* A, const void* W, int M, int N, int K, const float* bias, float alpha, const float* residual,
+                        float* out_f32, const float* g1, const float* b1, float eps, void* ln_out, const unsigned long long* drop_counter,
+                        float drop_p, unsigned drop_site, void* stream);
 /* Storage of the q|k|v and E operands that ec_op_relpos_attention / _bwd read in this mode and head layout: 0 = the activation type,
  * 1 = bf16 (EC_PREC_BF16), 2 = fp16 (EC_PREC_BF16X2 when dim % 8 == 0 and the head dim G*dim/heads is even: the 16-bit mma.sync kernels
  * then run on fp16 operands -- 11 significant bits, TF32-grade accuracy at the bf16 rate -- and write the packed output). */

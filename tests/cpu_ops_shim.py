@@ -61,6 +61,11 @@ def gemm_train(a_act, w_act, bias, precision, drop=None, alpha=1.0, residual=Non
     return (y if want_f32 else None), (z.clone() if want_act else None), (z * torch.sigmoid(z) if want_act2 else None)
 
 
+def gemm_ln_train(a_act, w_act, bias, precision, ln_g, ln_b, drop=None, alpha=1.0, residual=None, site=0, eps=1e-6):
+    out = gemm_train(a_act, w_act, bias, precision, drop, alpha=alpha, residual=residual, site=site)[0]
+    return out, F.layer_norm(out, (out.shape[-1],), _d(ln_g), _d(ln_b), eps)
+
+
 def swish_fwd(z, precision):
     return z * torch.sigmoid(z)
 

@@ -140,6 +140,30 @@ def test_gemm_train_epilogues_match_the_element_kernels(ops, prec, p_drop, M, N,
 
 
 @pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+@pytest.mark.parametrize("M,N,K", [(16000, 120, 480), (8000, 168, 168), (4000, 240, 960), (999, 120, 120), (130, 256, 64), (1, 96, 96)])
+def test_gemm_ln_train_matches_gemm_train_plus_layernorm(ops, prec, p_drop, M, N, K):
+    """ec_op_gemm_ln_train (projection + dropout + residual + the next module's LayerNorm in one epilogue) == ec_op_gemm_train followed
+    by the stand-alone LayerNorm kernel: same dropout mask, same fp32 output, LayerNorm output up to one rounding of the operand type."""
+    if prec == "bf16" and ((K * 2) % 16 or (N * 2) % 16):
+        pytest.skip("bf16 row pitch must be a multiple of 16 bytes")
+    g = torch.Generator(device="cpu").manual_seed(M + N * 3 + K * 7)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+    bias, res = torch.randn(N, generator=g).to(DEV), torch.randn(M, N, generator=g).to(DEV)
+    lg, lb = (1 + 0.1 * torch.randn(N, generator=g)).to(DEV), (0.1 * torch.randn(N, generator=g)).to(DEV)
+    aa, ww = ops.cast(a, prec), ops.cast_weight(w, prec)
+    drop = _Drop(ops, p_drop)
+    ref = ops.gemm_train(aa, ww, bias, prec, drop, alpha=0.5, residual=res, site=5)[0]
+    ref_ln = ops.layernorm(ref, lg, lb, prec, want_f32=False, want_act=True)[0]
+    out, ln = ops.gemm_ln_train(aa, ww, bias, prec, lg, lb, drop, alpha=0.5, residual=res, site=5)
+    assert rel_l2(out, ref) < 1e-6
+    if p_drop > 0:
+        assert torch.equal(out == res, ref == res)                 # the very same mask
+    assert rel_l2(ops.unpack(ln, prec), ops.unpack(ref_ln, prec)) < (8e-3 if prec == "bf16" else 1e-3 if prec == "tf32" else 3e-5)
+
+
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("M,N,K,fps,stride", [(16000, 120, 480, 500, 2), (8000, 168, 168, 250, 2), (4000, 240, 960, 125, 1), (999, 120, 4800, 333, 2),
                                               (37, 256, 64, 37, 1), (130, 8, 40, 13, 2)])
 def test_gemm_fused_layernorm(ops, prec, M, N, K, fps, stride):
