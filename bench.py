@@ -23,6 +23,8 @@ Sub-records of the same line (skipped with --no-extras), each measured in this r
   modes        the other operand modes (bf16, tf32) on the headline shapes
   ragged       configs[1] as literally worded: LibriSpeech-shaped batches, T ~ U{200..1600}, sorted and padded like collate_fn_pad
   configs      configs[2] EfficientConformerCTCLarge forward + CTC (B = 32) and configs[4] ConformerCTCLarge B = 8, T in 500..4000
+               (+ the same two in plain bf16 with per-kernel rooflines: what the tcgen05 kernels reach when a tile has work)
+  transducer_joint   configs[3]: the Transducer joint network + RNN-T loss, forward and forward + backward, on a B = 16 lattice
   torch_eager_b200   the UNMODIFIED reference modules (staged under baseline/_ref by tools/stage_reference.py) run eagerly on this GPU
                in fp32 and under autocast -- SURVEY.md 8(d) "the real bar"; N = 1 only
 --impl reference times the CPU oracle port of the same step on the host cores (the reference arm of the task contract).
@@ -516,6 +518,7 @@ def count_launches(fn):
             torch.cuda.synchronize()
         ours = lib_k = 0
         names = {}
+        KERNEL_US.clear()
         for e in prof.events():
             if e.device_type != torch.autograd.DeviceType.CUDA:
                 continue
@@ -524,11 +527,17 @@ def count_launches(fn):
                 continue
             if "ec::" in n:
                 ours += 1
+                key = n.split("ec::", 1)[1].replace("<unnamed>::", "").replace("(anonymous namespace)::", "").split("<")[0].split("(")[0]
+                ent = KERNEL_US.setdefault(key, [0, 0.0])
+                ent[0] += 1; ent[1] += float(e.time_range.elapsed_us())
             else:
                 lib_k += 1; names[n.split("<")[0][:60]] = names.get(n.split("<")[0][:60], 0) + 1
         return ours, lib_k, names
     except Exception as ex:                                          # profiler unavailable
         return None, None, {"error": repr(ex)}
+
+
+KERNEL_US = {}       # kernel name -> [launches, device microseconds] of the last count_launches() pass (CUPTI kernel records)
 
 
 def make_train_step(env, config, precision, pdrop, graph, sync_bn=True, accumulated_steps=1, data_parallel=True):
@@ -833,6 +842,21 @@ def run_ours(args, rank, world, local_rank):
             if tensor_ops:
                 out["roofline"] = roof(*tensor_ops[0])
                 out["rooflines_other"] = [roof(k2, v2) for k2, v2 in tensor_ops[1:]]
+            # the same operators by KERNEL duration (CUPTI records of one eager step, no host launch gaps): cross-check of the event-based
+            # figures above, which include the gaps between an operator's launch and the previous kernel's end in an eager step
+            if KERNEL_US:
+                gemm_flops = sum(v["flops"] for k, v in ops.items() if k in ("ec_op_gemm", "ec_op_gemm_ex", "ec_op_gemm_train", "ec_op_gemm_ln_train"))
+                wg_flops = sum(v["flops"] for k, v in ops.items() if k.startswith("ec_op_wgrad"))
+                kt = {}
+                for kern, fl in (("gemm_tc_kernel", gemm_flops), ("wgrad_tc_kernel", wg_flops)):
+                    if kern in KERNEL_US and KERNEL_US[kern][1] > 0:
+                        n_, us_ = KERNEL_US[kern]
+                        kt[kern] = {"launches": n_, "kernel_ms": round(us_ / 1e3, 4), "avg_us": round(us_ / n_, 2),
+                                    "achieved_tflops": round(fl / us_ / 1e6, 2), "frac_of_bf16_peak": round(fl / us_ / 1e6 / pk["bf16_tflops"], 4)}
+                top = sorted(KERNEL_US.items(), key=lambda kv: -kv[1][1])[:12]
+                out["kernel_time"] = {"tensor_kernels": kt, "top_kernels_ms": {k: round(v[1] / 1e3, 3) for k, v in top},
+                                      "total_kernel_ms": round(sum(v[1] for v in KERNEL_US.values()) / 1e3, 3),
+                                      "source": "torch.profiler (CUPTI) kernel records of ONE eager step of this run, warm caches; diagnostic only"}
             out["eager_profiled_step_ms"] = round(tot_ms, 3)
             launches = ours_k if ours_k is not None else 1267
             out["gpu_launches"] = launches * args.steps
@@ -940,11 +964,24 @@ def run_ours(args, rank, world, local_rank):
                         return rnnt_loss(jn(f, gd), y, fl, yl)[0]
                 ms, _ = timed_steps(env, one, 10, 3)
                 ms /= 10
+                from efficientconformer_b200.transducer import LossRNNT
+                crit = LossRNNT()
+                fg, gg = f.clone().requires_grad_(True), gd.clone().requires_grad_(True)
+
+                def train():
+                    jn.zero_grad(set_to_none=True); fg.grad = None; gg.grad = None
+                    loss = crit((None, y, None, yl), (jn(fg, gg), fl, None))
+                    loss.backward()
+                    return loss
+                jn.train()
+                ms_train, _ = timed_steps(env, train, 10, 3)
+                ms_train /= 10
                 flops = 2.0 * Bj * Tj * (Uj + 1) * J * Vj
-                return {"workload": "JointNetwork.forward + RNN-T loss (forward only; backward not built), B=16, T'=125, U=50, 360/640/640/1000",
-                        "precision": pr, "ms": ms, "lattice_nodes_per_s": Bj * Tj * (Uj + 1) / (ms / 1e3), "output_projection_tflops": round(flops / ms / 1e9, 1),
-                        "loss": float(one())}
-            guarded("transducer_joint_forward", out, transducer_joint)
+                return {"workload": "Transducer JointNetwork.forward + LossRNNT (and + loss.backward() through both autograd nodes), B=16, T'=125, U=50, "
+                                    "encoder 360 / decoder 640 / joint 640 / vocab 1000; eager launches",
+                        "precision": pr, "forward_ms": ms, "forward_backward_ms": ms_train, "lattice_nodes_per_s_forward": Bj * Tj * (Uj + 1) / (ms / 1e3),
+                        "output_projection_tflops_forward": round(flops / ms / 1e9, 1), "loss": float(one())}
+            guarded("transducer_joint", out, transducer_joint)
             guarded("torch_eager_b200", out, lambda: torch_eager_reference(env, small, B, T))
             _log(rank, "torch eager done")
     if env.dist is not None:

@@ -337,6 +337,10 @@ int ec_engine_create(const ec_config* cfg, int precision, ec_engine** out) {
   ec_engine* e = new ec_engine();
   e->cfg = *cfg; if (e->cfg.sub_layers == 0) e->cfg.sub_layers = 1;
   e->precision = precision; e->esize = act_esize(precision); e->prepared = false;
+  // Fused-LayerNorm GEMM epilogues pay off with 2-byte (bf16) and TF32 operands; in the split mode the LayerNorm passes inside a
+  // one-CTA-per-SM epilogue cost more than the stand-alone row kernel at full occupancy (B = 32 x 1000 forward: 2.97 ms fused,
+  // 2.77 ms unfused; tools/fwd_options.py, profiles/r2/forward_fusion_options.txt).  ec_engine_set_fuse_ln overrides.
+  e->fuse_ln = precision != EC_PREC_BF16X2;
   e->weight_bytes = layout_weights(e, nullptr);
   *out = e;
   return EC_OK;
