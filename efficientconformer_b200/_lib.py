@@ -65,6 +65,7 @@ _SIGNATURES = {
                                          C.POINTER(C.c_int32)]),
     "ec_engine_set_fuse_ln": (C.c_int, [C.c_void_p, C.c_int]),
     "ec_engine_set_fuse_ffn": (C.c_int, [C.c_void_p, C.c_int]),
+    "ec_engine_set_fuse_front": (C.c_int, [C.c_void_p, C.c_int]),
     "ec_set_pdl": (C.c_int, [C.c_int]),
     "ec_engine_set_skip_mask": (C.c_int, [C.c_void_p, C.c_uint]),
     "ec_debug_gemm_timeline": (C.c_int, [C.c_int, C.POINTER(C.c_ulonglong)]),

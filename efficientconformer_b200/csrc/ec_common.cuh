@@ -297,12 +297,24 @@ struct SubsampleArgs {
   void* y;               // [B, T_out, C*F/2] activation type, feature = c*(F/2) + f
 };
 int launch_subsample_conv(int precision, const SubsampleArgs& a, cudaStream_t stream);
+// one-kernel front end (subsample_fused.cu): conv + BN + Swish producer warps -> swizzled A tiles -> tcgen05 Linear; lin_w_perm = the
+// Linear weight with its columns permuted to k' = f*Cp + c (launch_linear_weight_permute with Cp = subsample_fused_cpad), activation
+// type ([2, D0, K'] in split mode)
+struct SubFusedArgs {
+  const float* mel; const float* w; const float* b;      // [B, F, T]; BatchNorm-folded taps [C, 9] and bias [C]
+  const void* lin_w_perm; const float* lin_b;
+  int B, F, T, C, D0;
+  float* out;                                            // [B * T_out, D0] fp32
+};
+bool subsample_fused_fits(int precision, int F, int C, int D0);
+int subsample_fused_cpad(int precision, int C);     // channel pitch Cp of the permuted weight (C rounded up to a producer run)
+int launch_subsample_linear_fused(int precision, const SubFusedArgs& a, cudaStream_t stream);
 // two-layer front end: channels-last layer 0 (y = [B, T_out, F/2, C]), im2col for the 3x3/s2 layer 1, weight preparation
 int launch_subsample_conv_cl(int precision, const SubsampleArgs& a, cudaStream_t stream);
 int launch_im2col_3x3s2(int precision, const void* y0, int B, int T1, int F1, int C, void* A, cudaStream_t stream);
 int launch_conv2_weight_prep(int precision, const float* w, const float* b, const float* g, const float* beta, const float* rm,
                              const float* rv, float eps, int C2, int C, void* w_out, float* b_out, cudaStream_t stream);
-int launch_linear_weight_permute(int precision, const float* w, int D, int C, int Fq, void* out, cudaStream_t stream);
+int launch_linear_weight_permute(int precision, const float* w, int D, int C, int Fq, void* out, cudaStream_t stream, int Cp = 0);
 
 int launch_cast_rows(int precision, const float* src, void* dst, size_t n, cudaStream_t stream);   // fp32 -> activation type
 // weight operand: cast + (split mode) the swapped plane at dst + twin_elems elements

@@ -75,6 +75,7 @@ struct BlockW {
 };
 struct Weights {
   float *sub_w, *sub_b; void* sub2_w; float* sub2_b; void* lin_w; float* lin_b; void* fc_w; float* fc_b;
+  void* lin_w_perm;      // one-layer front end: the Linear weight with columns in k' = f*Cp + c order (fused front-end kernel)
   BlockW blk[EC_MAX_BLOCKS];
 };
 
@@ -107,6 +108,7 @@ struct ec_engine {
   unsigned skip_mask = 0;  // debug (ec_engine_set_skip_mask): kernel categories NOT launched -- marginal-cost studies only, results are garbage
   bool fuse_ffn = true;    // bf16 mode: whole feed-forward module in one cluster kernel (needs fuse_ln)
   bool fuse_ln = true;     // LayerNorms in the epilogue of the producing GEMM (needs dim <= 256)
+  bool fuse_front = true;  // Conv2d subsampling + Linear as one kernel (subsample_fused.cu; one-layer front end, first dim <= 256)
   // the positional projections E_i = pos_layer_i(R) depend on weights only: they run on a forked stream, off the critical path
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -139,6 +141,7 @@ static size_t layout_weights(ec_engine* e, void* arena) {
   if (c.sub_layers == 2) { w.sub2_w = act(static_cast<size_t>(c.sub_filters2) * 9 * C); w.sub2_b = f32(c.sub_filters2); }
   else { w.sub2_w = nullptr; w.sub2_b = nullptr; }
   w.lin_w = act(static_cast<size_t>(D0) * sub_features(c)); w.lin_b = f32(D0);
+  w.lin_w_perm = c.sub_layers == 1 ? act(static_cast<size_t>(D0) * subsample_fused_cpad(e->precision, C) * (c.n_mels / 2)) : nullptr;
   for (int i = 0; i < c.num_blocks; ++i) {
     const ec_block_cfg& bc = c.blocks[i];
     const int D = bc.dim_model, De = bc.dim_expand, Fr = bc.ff_ratio;
@@ -403,6 +406,7 @@ int ec_engine_prepare(ec_engine* e, const ec_raw_weights* raw, void* arena, void
     EC_TRY(launch_linear_weight_permute(prec, raw->lin_w, D0, c.sub_filters2, c.n_mels / 4, w.lin_w, st));
   } else {
     EC_TRY(cast(w.lin_w, raw->lin_w, static_cast<size_t>(D0) * sub_features(c)));
+    EC_TRY(launch_linear_weight_permute(prec, raw->lin_w, D0, C, c.n_mels / 2, w.lin_w_perm, st, subsample_fused_cpad(prec, C)));
   }
   EC_TRY(cp(w.lin_b, raw->lin_b, D0));
   for (int i = 0; i < c.num_blocks; ++i) {
@@ -507,12 +511,14 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
       EC_TRY(launch_im2col_3x3s2(prec, ws.sub_y0, B, T1, F1, C, ws.sub_col, st));
     }
     EC_TRY(gemm(e, st, PC_SUB_CONV2, ws.sub_col, w.sub2_w, B * T2 * F2, C2, 9 * C, w.sub2_b, 1.f, GEMM_ACT_SWISH, nullptr, nullptr, ws.sub_a));
-  } else {
+  }
+  const int D0 = c.blocks[0].dim_model;
+  const bool front_fused = c.sub_layers == 1 && e->fuse_front && subsample_fused_fits(prec, c.n_mels, c.sub_filters, D0);
+  if (c.sub_layers == 1 && !front_fused) {
     SubsampleArgs sa{mel, w.sub_w, w.sub_b, B, c.n_mels, t_mel, c.sub_filters, ws.sub_a};
     ProfScope ps(e, st, PC_SUBSAMPLE, 18.0 * B * sh.t0 * feat, 4.0 * B * c.n_mels * t_mel + es * B * sh.t0 * feat);
     if (!(e->skip_mask >> PC_SUBSAMPLE & 1u)) EC_TRY(launch_subsample_conv(prec, sa, st));
   }
-  const int D0 = c.blocks[0].dim_model;
   float* x = ws.xa; float* x_alt = ws.xb;
 
   // GEMM followed by the LayerNorm(s) the next module needs: in the GEMM's own epilogue when the row fits one tile (N <= 256) and
@@ -538,7 +544,18 @@ int ec_engine_forward(ec_engine* e, int B, int t_mel, const float* mel, const lo
   {
     LnFuse ln;   // x0 = Linear(sub), xn = LN_ffn1(x0) for block 0
     ln.mode = 1; ln.g1 = w.blk[0].ffn1.ln_w; ln.b1 = w.blk[0].ffn1.ln_b; ln.y = ws.xn;
-    EC_TRY(gemm_ln(PC_LIN, ws.sub_a, w.lin_w, B * sh.t0, D0, feat, w.lin_b, 1.f, nullptr, x, ln));
+    if (front_fused) {
+      // conv + BN + Swish producers feed the Linear's A tiles in shared memory: the (B*T/2) x (C*F/2) operand is never written
+      {
+        SubFusedArgs fa{mel, w.sub_w, w.sub_b, w.lin_w_perm, w.lin_b, B, c.n_mels, t_mel, c.sub_filters, D0, x};
+        ProfScope ps(e, st, PC_SUBSAMPLE, (18.0 + 2.0 * D0) * B * sh.t0 * feat,
+                     4.0 * B * c.n_mels * t_mel + es * static_cast<double>(D0) * feat + 4.0 * B * sh.t0 * D0);
+        if (!(e->skip_mask >> PC_SUBSAMPLE & 1u)) EC_TRY(launch_subsample_linear_fused(prec, fa, st));
+      }
+      EC_TRY(lnorm(e, st, x, B * sh.t0, D0, ln.g1, ln.b1, ln.y, nullptr, ln.copy_out, ln.copy_stride, ln.fps, ln.fops));
+    } else {
+      EC_TRY(gemm_ln(PC_LIN, ws.sub_a, w.lin_w, B * sh.t0, D0, feat, w.lin_b, 1.f, nullptr, x, ln));
+    }
   }
 
   for (int i = 0; i < c.num_blocks; ++i) {
@@ -624,6 +641,7 @@ int ec_engine_set_profiling(ec_engine* e, int enabled) { e->prof_enabled = enabl
 /* option 0: fuse LayerNorm into the GEMM epilogues (default 1).  Global option via ec_set_pdl: programmatic dependent launch. */
 int ec_engine_set_fuse_ln(ec_engine* e, int enabled) { e->fuse_ln = enabled != 0; return EC_OK; }
 int ec_engine_set_fuse_ffn(ec_engine* e, int enabled) { e->fuse_ffn = enabled != 0; return EC_OK; }
+int ec_engine_set_fuse_front(ec_engine* e, int enabled) { e->fuse_front = enabled != 0; return EC_OK; }
 int ec_engine_set_skip_mask(ec_engine* e, unsigned mask) { e->skip_mask = mask; return EC_OK; }
 int ec_debug_gemm_timeline(int enable, unsigned long long* out12) { return gemm_timeline(enable, out12); }
 int ec_debug_gemm_block_n(int block_n) { return gemm_block_n_override(block_n); }

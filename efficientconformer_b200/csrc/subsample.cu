@@ -221,22 +221,24 @@ int launch_conv2_weight_prep(int precision, const float* w, const float* b, cons
   return EC_OK;
 }
 
-// Linear weight [D, C*Fq] with reference feature order c*Fq + f  ->  [D, Fq*C] with order f*C + c (channels-last operand).
+// Linear weight [D, C*Fq] with reference feature order c*Fq + f  ->  [D, Fq*Cp] with order f*Cp + c (channels-last operand; Cp >= C,
+// zero columns for the pad channels c >= C).
 template <typename T>
-__global__ void linear_weight_permute_kernel(const float* __restrict__ w, int D, int C, int Fq, T* __restrict__ out) {
+__global__ void linear_weight_permute_kernel(const float* __restrict__ w, int D, int C, int Cp, int Fq, T* __restrict__ out) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t K = static_cast<size_t>(C) * Fq;
-  if (i >= D * K) return;
-  const size_t d = i / K, r = i % K;
-  const int f = static_cast<int>(r / C), c = static_cast<int>(r % C);
-  const T v = ActTraits<T>::to(w[d * K + static_cast<size_t>(c) * Fq + f]);
+  const size_t K = static_cast<size_t>(C) * Fq, Kp = static_cast<size_t>(Cp) * Fq;
+  if (i >= D * Kp) return;
+  const size_t d = i / Kp, r = i % Kp;
+  const int f = static_cast<int>(r / Cp), c = static_cast<int>(r % Cp);
+  const T v = ActTraits<T>::to(c < C ? w[d * K + static_cast<size_t>(c) * Fq + f] : 0.f);
   out[i] = v;
-  if constexpr (IsSplit<T>::value) out[D * K + i] = SplitBf16{split_swap(v.bits)};   // swapped plane
+  if constexpr (IsSplit<T>::value) out[D * Kp + i] = SplitBf16{split_swap(v.bits)};   // swapped plane
 }
-int launch_linear_weight_permute(int precision, const float* w, int D, int C, int Fq, void* out, cudaStream_t stream) {
-  const size_t n = static_cast<size_t>(D) * C * Fq;
+int launch_linear_weight_permute(int precision, const float* w, int D, int C, int Fq, void* out, cudaStream_t stream, int Cp) {
+  if (Cp < C) Cp = C;
+  const size_t n = static_cast<size_t>(D) * Cp * Fq;
   const int blocks = static_cast<int>((n + 255) / 256);
-  EC_DISPATCH_PREC(precision, (linear_weight_permute_kernel<ActT><<<blocks, 256, 0, stream>>>(w, D, C, Fq, reinterpret_cast<ActT*>(out))));
+  EC_DISPATCH_PREC(precision, (linear_weight_permute_kernel<ActT><<<blocks, 256, 0, stream>>>(w, D, C, Cp, Fq, reinterpret_cast<ActT*>(out))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }

@@ -127,6 +127,8 @@ int ec_engine_set_fuse_ln(ec_engine* e, int enabled);
 /* fuse_ffn (per engine, default 1; EC_PREC_BF16 with fuse_ln only): each feed-forward module runs as ONE cluster kernel
  * (W1 -> Swish -> W2 -> half-step residual -> LayerNorm) whose hidden activation never leaves the SM. */
 int ec_engine_set_fuse_ffn(ec_engine* e, int enabled);
+/* one-layer Conv2d subsampling + Linear as one kernel (the 4800-wide operand stays in shared memory); default on where it fits */
+int ec_engine_set_fuse_front(ec_engine* e, int enabled);
 int ec_set_pdl(int enabled);
 /* Debug / measurement only: bit c set = the kernels of profile category c are NOT launched (outputs are garbage).  Used by
  * tools/marginal_cost.py to measure what each kernel category really costs inside the replayed CUDA graph (PDL overlap included). */

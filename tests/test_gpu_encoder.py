@@ -239,6 +239,34 @@ def test_execution_options_do_not_change_results(sd, fuse_ln, pdl):
     assert rel_l2(ref_gpu, ref) < TOL_TF32
 
 
+@pytest.mark.parametrize("precision,tol", [("bf16x2", 5e-4), ("tf32", 1e-3), ("bf16", 8e-3)])
+def test_fused_front_end_matches_two_kernel_path(sd, precision, tol):
+    """The one-kernel front end (conv + BN + Swish producer warps -> swizzled A tiles -> tcgen05 Linear, subsample_fused.cu) against the
+    two-kernel path (materialised 4800-wide operand + K = 4800 GEMM): same operand values, only the contraction order over k differs.
+    Ragged lengths, frame counts off the 128-frame tile grid, odd T; both must meet the parity gate against the oracle on their own."""
+    from oracle import conformer_oracle as O
+    from efficientconformer_b200 import _lib
+    L = _lib.lib()
+    for (B, T, lens) in ((3, 333, [333, 200, 77]), (2, 1000, [1000, 611]), (1, 257, [257]), (2, 16, [16, 9])):
+        mel = synthetic_mel(B, T, seed=90 + T)
+        mel_len = torch.tensor(lens)
+        outs = []
+        for fused in (1, 0):
+            m = make_model(sd, precision)
+            m.forward_mel(mel.to(DEV), mel_len.to(DEV))                   # creates the engine
+            eng = m.encoder._engines[_lib.PRECISIONS[precision]][0]
+            L.ec_engine_set_fuse_front(eng, fused)
+            m.encoder._plans.clear()                                      # drop graphs captured with the old option
+            lg, ol, _ = m.forward_mel(mel.to(DEV), mel_len.to(DEV))
+            outs.append(lg.clone())
+        e = rel_l2(outs[0], outs[1])
+        print(f"[{precision}] B={B} T={T}: fused vs two-kernel front end rel-L2 {e:.3e}")
+        assert e < tol, (precision, B, T, e)
+        if precision == "bf16x2" and T <= 400:
+            ref, _ = O.model_ctc_forward_mel(sd, P, mel, mel_len)
+            assert rel_l2(outs[0], ref) < TOL_TF32 and rel_l2(outs[1], ref) < TOL_TF32
+
+
 def test_fused_ffn_matches_unfused_bf16(sd):
     """Fast mode: the fused feed-forward cluster kernel (default) and the W1 / W2 GEMM pair compute the same module; both stay
     at the bf16 operand-noise level against the oracle (TOL_BF16), and agree with each other at that level."""
