@@ -816,7 +816,10 @@ def run_ours(args, rank, world, local_rank):
                                     "exchanges_per_step": ("16 + 16 SyncBatchNorm exchanges (forward statistics, backward sums) as "
                                                            + ("peer-memory kernels over NVLink (csrc/p2p_exchange.cu)" if rec.get("sync_bn_exchange") == "P2PSyncBatchNormReducer"
                                                               else "NCCL all_gather / all_reduce")
-                                                           + " + 1 x NCCL all_reduce of the flat 53 MB fp32 gradient bucket, all inside the captured graph")
+                                                           + (f" + {len(step._buckets) + 1} NCCL all_reduces over the flat 53 MB fp32 gradient arena (buckets: last third of the "
+                                                              "blocks + head, middle third, rest; the first two leave on a communication stream while the "
+                                                              "backward of the earlier blocks runs), all inside the captured graph" if getattr(step, "_buckets", None)
+                                                              else " + 1 x NCCL all_reduce of the flat 53 MB fp32 gradient bucket, all inside the captured graph"))
                                                           if not args.no_sync_bn else "1 x all_reduce of the flat fp32 gradient bucket"}
         if rank == 0:
             ops, ours_k, lib_k, lib_names = train_operator_profile(env, cfg, pr, args.pdrop, batch)

@@ -166,6 +166,10 @@ _SIGNATURES = {
                                     C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "ec_op_joint_hidden_bwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p]),
+    "ec_op_logmel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                               C.c_float, C.c_void_p, C.c_void_p]),
+    "ec_op_specaugment": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
+                                    C.c_void_p]),
     "ec_p2p_mailbox_bytes": (C.c_size_t, [C.c_int]),
     "ec_p2p_max_payload_floats": (C.c_int, []),
     "ec_p2p_bn_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libeffconf_b200.so")
-SOURCES = ["gemm_tc.cu", "ffn_fused.cu", "elementwise.cu", "attention.cu", "attention_bf16.cu", "attention_tma.cu", "dwconv.cu", "subsample.cu", "subsample_fused.cu", "ctc.cu", "ctc_grad.cu", "backward_rows.cu", "wgrad_tc.cu", "conv_train.cu", "attention_bwd.cu", "attention_bwd_tc.cu", "train_misc.cu", "train_step.cu", "p2p_exchange.cu", "rnnt.cu", "engine.cu"]
+SOURCES = ["gemm_tc.cu", "ffn_fused.cu", "elementwise.cu", "attention.cu", "attention_bf16.cu", "attention_tma.cu", "dwconv.cu", "subsample.cu", "subsample_fused.cu", "ctc.cu", "ctc_grad.cu", "backward_rows.cu", "wgrad_tc.cu", "conv_train.cu", "attention_bwd.cu", "attention_bwd_tc.cu", "train_misc.cu", "train_step.cu", "p2p_exchange.cu", "rnnt.cu", "frontend.cu", "engine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -5,12 +5,12 @@ Same constructor (`ConformerEncoder(params)` with the `encoder_params` dict), sa
 the reference in tests/test_oracle_golden.py and tests/test_host_logic.py), a `.blocks` list whose items carry `.stride`.
 The modules below are PARAMETER HOLDERS only: nothing here runs PyTorch math on the hot path.  `forward` hands raw
 device pointers to the sm_100a CUDA library (efficientconformer_b200/csrc, C ABI in include/effconf_b200.h); the audio
-front end (STFT -> mel -> log, reference models/modules.py:87-106) stays host PyTorch/torchaudio as in the reference.
+front end (STFT -> mel -> log, reference models/modules.py:87-106) is one kernel for audio on the GPU and torchaudio for CPU tensors.
 
 `.eval()`: the fused inference engine (ec_engine_forward, CUDA-graph replay) -- what `Model.evaluate`, `gready_search_decoding`
 and `eval_time_encoder` use.  `.train()`: the training operator schedule of efficientconformer_b200/training.py (batch-statistics
 BatchNorm, dropout, one autograd node whose backward is the CUDA backward schedule); SpecAugment
-stays host PyTorch (batched torch ops on the mel tensor) and is applied inside `forward` when training, as the reference does.  There is no fallback path: without the CUDA library or on a
+(one kernel, batched; csrc/frontend.cu) is applied inside `forward` when training, as the reference does.  There is no fallback path: without the CUDA library or on a
 non-sm_100 device, forward raises.
 """
 import ctypes as C
@@ -86,8 +86,17 @@ class ConformerBlockHolder(nn.Module):    # reference models/blocks.py:32-117
         self.spec = spec
 
 
+def _device_front_end():
+    """EFFCONF_DEVICE_FRONTEND=0 keeps torchaudio / torch ops for the front end on CUDA tensors as well (diagnostics)."""
+    import os
+    return os.environ.get("EFFCONF_DEVICE_FRONTEND", "1") != "0"
+
+
 class _PreprocessingHolder(nn.Module):
-    """reference models/modules.py:55-106 (AudioPreprocessing): torchaudio Spectrogram + MelScale + log; stays host PyTorch."""
+    """reference models/modules.py:55-106 (AudioPreprocessing): Spectrogram + MelScale + log.  The torchaudio transforms are kept as the
+    holders of the module's state (Hann window, mel filter bank) and as the path for CPU tensors; audio that is
+    already on the GPU goes through ONE kernel (ec_op_logmel, csrc/frontend.cu: framing, window, shared-memory FFT, power, mel, log)
+    with the same window and filter-bank buffers."""
 
     def __init__(self, params):
         super().__init__()
@@ -99,7 +108,32 @@ class _PreprocessingHolder(nn.Module):
                                                        n_stft=params["n_fft"] // 2 + 1)
         self.normalize, self.mean, self.std = params["normalize"], params["mean"], params["std"]
 
+    def _device_tables(self, device):
+        win, fb = self.Spectrogram.window, self.MelScale.fb
+        key = (str(device), win.data_ptr(), fb.data_ptr())
+        if getattr(self, "_tables_key", None) != key:
+            n_fft = self.Spectrogram.n_fft
+            left = (n_fft - win.numel()) // 2
+            w = torch.nn.functional.pad(win.detach().float().to(device), (left, n_fft - win.numel() - left)).contiguous()
+            f = fb.detach().float().to(device).contiguous()
+            nz = f > 0                                        # filter m covers the bins [first, last] with a non-zero weight
+            idx = torch.arange(f.shape[0], device=device)[:, None]
+            lo = torch.where(nz, idx, f.shape[0]).amin(0)
+            hi = torch.where(nz, idx + 1, 0).amax(0)
+            kr = torch.stack([torch.minimum(lo, hi), hi], 1).to(torch.int32).contiguous()
+            self._tables, self._tables_key = (w, f, kr), key
+        return self._tables
+
     def forward(self, x, x_len):
+        if x.is_cuda and _device_front_end():
+            from . import ops
+            w, f, kr = self._device_tables(x.device)
+            with torch.cuda.device(x.device):
+                x = ops.logmel(x.detach().float().reshape(-1, x.shape[-1]), w, f, kr, self.hop_length, self.normalize, self.mean,
+                               self.std).reshape(*x.shape[:-1], f.shape[1], -1)
+            if x_len is not None:
+                x_len = torch.div(x_len, self.hop_length, rounding_mode="floor") + 1
+            return x, x_len
         x = self.MelScale(self.Spectrogram(x))
         x = (x.float() + 1e-9).log().type(x.dtype)
         if x_len is not None:
@@ -110,14 +144,16 @@ class _PreprocessingHolder(nn.Module):
 
 
 class SpecAugment(nn.Module):
-    """Host-PyTorch SpecAugment with the reference's semantics (reference models/modules.py:108-151; SURVEY.md section 8 row a3: it stays
-    torch ops on the mel tensor, called inside the train-mode forward like reference models/encoders.py:103-104):
+    """SpecAugment with the reference's semantics (reference models/modules.py:108-151), called inside
+    the train-mode forward like reference models/encoders.py:103-104:
       * mF frequency masks shared by the whole batch, width floor(U(0, F)), start floor(U(0, n_mels - width))
         (torchaudio FrequencyMasking(F, iid_masks=False) -> mask_along_axis);
       * per utterance b, mT time masks inside its valid frames [0, x_len[b]), width floor(U(0, int(pS * x_len[b]))),
         start floor(U(0, x_len[b] - width)); masked cells are set to 0.
     The reference loops over the batch with one host read of x_len[b] per utterance; here all B * mT masks are drawn and applied with
-    batched device ops (no host synchronisation).  Random streams differ from the reference's, the distribution is the same."""
+    batched device ops (no host synchronisation).  Random streams differ from the reference's, the distribution is the same.
+    fp32 CUDA tensors: one kernel (ec_op_specaugment) draws every mask from the counter-based hash the dropout sites use (seeded from
+    torch.initial_seed(), {seed, step} on the device) and writes only the masked cells of a copy; other tensors: the torch ops below."""
 
     def __init__(self, spec_augment, mF, F, mT, pS):
         super().__init__()
@@ -128,6 +164,16 @@ class SpecAugment(nn.Module):
             return x
         B, n_mels, T = x.shape
         dev = x.device
+        if x.is_cuda and x.dtype == torch.float32 and _device_front_end():
+            from . import ops
+            with torch.cuda.device(dev):
+                ctr = getattr(self, "_counter", None)
+                if ctr is None or ctr.device != dev:
+                    ctr = self._counter = ops.dropout_counter(dev, torch.initial_seed())
+                ops.dropout_advance(ctr)
+                lens = None if x_len is None else x_len.to(device=dev, dtype=torch.int64).contiguous()
+                return ops.specaugment_(x.detach().clone(memory_format=torch.contiguous_format), lens, self.mF, min(self.F, n_mels), self.mT,
+                                        self.pS, ctr)
         keep = torch.ones(B, n_mels, T, dtype=torch.bool, device=dev)
         if self.mF > 0:
             value = torch.rand(self.mF, device=dev) * self.F

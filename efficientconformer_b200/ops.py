@@ -639,3 +639,24 @@ def transpose_cast_multi(src_arena, desc_dev, n, dst_arena, precision, ctas_per_
     """desc_dev int64 [n, 4] = (src offset, rows, cols, dst offset): every W^T operand of the data-gradient GEMMs in one launch."""
     check(lib().ec_op_transpose_cast_multi(_p(precision), ptr(src_arena), ptr(desc_dev), n, ctas_per_tensor, ptr(dst_arena), stream_ptr()))
     return dst_arena
+
+
+# ---- front end on the device (csrc/frontend.cu; SURVEY.md section 8f row 4) -----------------------------------------------------------
+def logmel(audio, window, fb, krange, hop, normalize=False, mean=0.0, std=1.0):
+    """audio (B, L) fp32 -> (B, n_mels, L // hop + 1) fp32: reference models/modules.py:87-106 (STFT power -> mel -> log [-> normalise]).
+    window (n_fft,) = analysis window centred / zero padded to n_fft; fb (n_fft // 2 + 1, n_mels); krange (n_mels, 2) int32 or None."""
+    audio = audio.contiguous()
+    B, L = audio.shape
+    n_fft, n_mels = window.numel(), fb.shape[1]
+    out = torch.empty(B, n_mels, L // hop + 1, dtype=torch.float32, device=audio.device)
+    check(lib().ec_op_logmel(ptr(audio), B, L, n_fft, int(hop), ptr(window), ptr(fb), ptr(krange) if krange is not None else None, n_mels,
+                             1 if normalize else 0, float(mean), float(std), ptr(out), stream_ptr()))
+    return out
+
+
+def specaugment_(mel, x_len, mF, F, mT, pS, counter):
+    """In place on mel (B, n_mels, T) fp32: reference models/modules.py:136-151 with counter-based draws ({seed, step} device pair)."""
+    B, n_mels, T = mel.shape
+    check(lib().ec_op_specaugment(ptr(mel), ptr(x_len) if x_len is not None else None, B, n_mels, T, int(mF), int(F), int(mT), float(pS),
+                                  ptr(counter), stream_ptr()))
+    return mel

@@ -11,6 +11,9 @@ the flat parameter arena (ec_adam_step).  Parameters of the holder modules are r
 batch shape the whole step (collectives excluded) is captured once into a CUDA graph and replayed.
 
 Everything outside this step -- epochs, data loading, checkpoints, evaluation, WER -- stays the reference's own Python."""
+import ctypes as C
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -51,7 +54,7 @@ class FlatParams:
         # rewrites a table whose host-to-device copy has not executed yet
         pin = torch.cuda.is_available()
         self._slots = []
-        for _ in range(4):
+        for _ in range(12):
             host = torch.empty(len(self.names), dtype=torch.int64)
             self._slots.append([host.pin_memory() if pin else host, torch.empty(len(self.names), dtype=torch.int64, device=device), None])
         self._slot = 0
@@ -66,9 +69,17 @@ class FlatParams:
         host = torch.empty(len(self.names), dtype=torch.int64)
         return (host.pin_memory() if torch.cuda.is_available() else host, torch.empty(len(self.names), dtype=torch.int64, device=self.grads.device))
 
-    def pack(self, grads, accumulate=False, tables=None):
-        """Gather the per-parameter gradient tensors (dict name -> contiguous fp32 tensor) into `self.grads` (accumulate: add to it)."""
+    def arena_range(self, lo, hi):
+        """Float offsets [a, b) of the arena covered by the parameters lo .. hi-1 (arena order)."""
+        return self.offsets[lo], (self.offsets[hi] if hi < len(self.names) else self.total)
+
+    def pack(self, grads, accumulate=False, tables=None, lo=0, hi=None):
+        """Gather the per-parameter gradient tensors (dict name -> contiguous fp32 tensor) into `self.grads` (accumulate: add to it);
+        lo / hi restrict the call to the parameters lo .. hi-1 of the arena order (one gradient bucket)."""
         keep = []
+        hi = len(self.names) if hi is None else hi
+        if hi <= lo:
+            return keep
         capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
         if capturing and tables is None:
             raise RuntimeError("FlatParams.pack under CUDA-graph capture needs private pointer tables (new_tables())")
@@ -78,18 +89,20 @@ class FlatParams:
             host, dev, ev = self._slots[self._slot]
             if ev is not None:
                 ev.synchronize()                  # the copy that last read this host table has executed
-        for i, n in enumerate(self.names):
+        for i in range(lo, hi):
+            n = self.names[i]
             g = grads[n]
             if g.dtype != torch.float32 or not g.is_contiguous():
                 g = g.float().contiguous(); keep.append(g)
             assert g.numel() == self.sizes[i], n
             host[i] = g.data_ptr()
-        dev.copy_(host, non_blocking=True)
+        dev[lo:hi].copy_(host[lo:hi], non_blocking=True)
         if torch.cuda.is_available() and tables is None:
             ev = torch.cuda.Event(); ev.record()
             self._slots[self._slot][2] = ev
             self._slot = (self._slot + 1) % len(self._slots)
-        _lib.check(_lib.lib().ec_op_pack_flat_acc(_lib.ptr(dev), _lib.ptr(self.offsets_dev), _lib.ptr(self.sizes_dev), len(self.names),
+        at = lambda t: C.c_void_p(t.data_ptr() + 8 * lo)
+        _lib.check(_lib.lib().ec_op_pack_flat_acc(at(dev), at(self.offsets_dev), at(self.sizes_dev), hi - lo,
                                                   _lib.ptr(self.grads), 1 if accumulate else 0, _lib.stream_ptr()))
         return keep
 
@@ -242,6 +255,9 @@ class CTCTrainStep:
         self.schedule = 1 if sched == "Transformer" else 0
         self._set_schedule_step(0)
         self.use_cuda_graph = use_cuda_graph
+        # EFFCONF_BUCKET_OVERLAP=0: one gradient bucket, all-reduced after the whole backward (the round-1 behaviour)
+        self._buckets = self._plan_buckets(model) if self.world > 1 and os.environ.get("EFFCONF_BUCKET_OVERLAP", "1") != "0" else {}
+        self._comm, self._pending = None, None
         self.max_graphs = max_graphs
         self._graphs = {}                                   # (shape key, accumulate, final) -> [graph(s), static inputs, keep-alive]
         self._micro = 0                                     # micro-batches accumulated since the last optimiser step
@@ -263,15 +279,61 @@ class CTCTrainStep:
         self.state.copy_(st)
 
     # ---- pieces -----------------------------------------------------------------------------------------------------------
-    def _forward_backward(self, mel, mel_len, targets, target_len, accumulate, tables=None):
+    def _plan_buckets(self, model):
+        """Gradient buckets for the overlapped data-parallel all-reduce: the arena is cut where the last third and the middle third of
+        the blocks begin, so that bucket 0 = {blocks >= b1, head} is complete -- and its all-reduce can start on the communication
+        stream -- while the backward of the earlier blocks is still running; the last bucket (first blocks + front end) goes out
+        after the backward.  Returns {block index: (lo, hi) parameter range} (empty: one bucket after the backward)."""
+        n = len(model.encoder.blocks)
+        names = self.flat.names
+        plan, hi = {}, len(names)
+        for b in sorted({(2 * n) // 3, n // 3}, reverse=True):
+            if b <= 0 or b >= n:
+                continue
+            first = [i for i, nm in enumerate(names) if nm.startswith(f"encoder.blocks.{b}.")]
+            if not first:
+                return {}
+            lo = min(first)
+            for i, nm in enumerate(names):                   # contiguity: everything from `lo` on belongs to blocks >= b or the head
+                later = nm.startswith("fc.") or (nm.startswith("encoder.blocks.") and int(nm.split(".")[2]) >= b)
+                if (i >= lo) != later:
+                    return {}
+            plan[b] = (lo, hi)
+            hi = lo
+        return plan
+
+    def _forward_backward(self, mel, mel_len, targets, target_len, accumulate, tables=None, final=False):
         if self.weights is not None:
             self.weights.refresh(side=self.path.side_stream(mel.device))
         x, logits, out_len, tape = self.path.forward(mel, mel_len, self.precision, want_logits=True)
         if out_len is None:
             out_len = torch.full((mel.shape[0],), logits.shape[1], dtype=torch.int64, device=mel.device)
         mean, per, dlogits = ctc_loss_and_grad(logits, out_len, targets, target_len)
-        grads = self.path.backward(tape, None, dlogits)
-        keep = self.flat.pack(grads, accumulate=accumulate, tables=tables)
+        hook, keep, works, rest_hi = None, [], [], len(self.flat.names)
+        capturing = mel.is_cuda and torch.cuda.is_current_stream_capturing()
+        if final and self.world > 1 and self._buckets and mel.is_cuda and (self.reducer is not None or not capturing):
+            # buckets leave on the communication stream as soon as their blocks' gradients are enqueued (main + weight-gradient streams)
+            if self._comm is None:
+                self._comm = torch.cuda.Stream(device=mel.device)
+            comm, rest_hi = self._comm, min(lo for lo, _ in self._buckets.values())
+
+            def hook(i, grads):
+                rng = self._buckets.get(i)
+                if rng is None:
+                    return
+                comm.wait_stream(torch.cuda.current_stream(mel.device))
+                side = self.path.side_stream(mel.device)
+                if side is not None:
+                    comm.wait_stream(side)
+                with torch.cuda.stream(comm):
+                    keep.extend(self.flat.pack(grads, accumulate=accumulate, tables=tables, lo=rng[0], hi=rng[1]))
+                    a, b = self.flat.arena_range(*rng)
+                    works.append(dist.all_reduce(self.flat.grads[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        grads = self.path.backward(tape, None, dlogits, stage_hook=hook)
+        keep.extend(self.flat.pack(grads, accumulate=accumulate, tables=tables, lo=0, hi=rest_hi))
+        if hook is not None:
+            keep.append(grads)                               # read by the communication stream: alive until the step has joined it
+            self._pending = (works, self.flat.arena_range(0, rest_hi))
         self.loss.copy_(mean)
         return keep
 
@@ -284,12 +346,20 @@ class CTCTrainStep:
                        warmup=float(tp.get("warmup_steps", 1.0)))
 
     def _all_reduce(self):
-        if self.world > 1:
-            dist.all_reduce(self.flat.grads, op=dist.ReduceOp.SUM, group=self.group)     # ONE bucket; the mean is folded into Adam
+        if self.world <= 1:
+            return
+        if self._pending is not None:                        # overlapped buckets are in flight: the last one, then join
+            (works, (a, b)), self._pending = self._pending, None
+            dist.all_reduce(self.flat.grads[a:b], op=dist.ReduceOp.SUM, group=self.group)
+            for w in works:
+                w.wait()
+            torch.cuda.current_stream(self.device).wait_stream(self._comm)
+            return
+        dist.all_reduce(self.flat.grads, op=dist.ReduceOp.SUM, group=self.group)         # ONE bucket; the mean is folded into Adam
 
     def _step_eager(self, mel, mel_len, targets, target_len, accumulate, final):
         with torch.no_grad():
-            keep = self._forward_backward(mel, mel_len, targets, target_len, accumulate)
+            keep = self._forward_backward(mel, mel_len, targets, target_len, accumulate, final=final)
             if final:
                 self._all_reduce()
                 self._optimizer()
@@ -349,7 +419,7 @@ class CTCTrainStep:
         mode = {"capture_error_mode": "thread_local"} if self.world > 1 else {}
         with torch.no_grad():
             with torch.cuda.graph(g1, **mode):
-                keep = self._forward_backward(s_mel, s_len, s_y, s_yl, accumulate, tables=tables)
+                keep = self._forward_backward(s_mel, s_len, s_y, s_yl, accumulate, tables=tables, final=final)
                 if final and not split:
                     self._all_reduce()
                     self._optimizer()

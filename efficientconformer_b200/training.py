@@ -377,9 +377,10 @@ class TrainingPath:
         return x5, To, tape, x_act
 
     # ---- backward -----------------------------------------------------------------------------------------------------
-    def backward(self, tape, d_x=None, d_logits=None):
+    def backward(self, tape, d_x=None, d_logits=None, stage_hook=None):
         """d_x (B, T_out, D_last) and / or d_logits (B, T_out, V) fp32 -> {parameter name: gradient} (fp32, reference names with
-        `encoder.` / `fc.` prefixes)."""
+        `encoder.` / `fc.` prefixes).  stage_hook(i, grads) is called after block i's backward has been enqueued: every gradient of
+        the head and of the blocks >= i is then in `grads` (the weight gradients possibly still running on side_stream())."""
         o = _ops
         pr, B = tape["pr"], tape["B"]
         enc = self.encoder
@@ -403,6 +404,8 @@ class TrainingPath:
             # block 0 hands the front end its operand (dropout mask of encoder.linear's dropout re-applied)
             dx, d_act = self._block_backward(enc.blocks[i], self.specs[i], tape["blocks"][i], dx, B, pr, grads, f"encoder.blocks.{i}",
                                              emit_next=(1.0, site0) if i == 0 else None)
+            if stage_hook is not None:
+                stage_hook(i, grads)
         if d_act is None:
             d_act = o.dropout_cast_scaled(dx, pr, 1.0, self._drop, site0)
         dw_, db_ = self._wgrad(d_act, a, pr)

@@ -380,6 +380,24 @@ int ec_rnnt_loss_grad(const float* logits, int batch, int t, int u1, int vocab, 
 int ec_op_joint_hidden_bwd(int precision, const void* hidden, const float* d_hidden, int batch, int t, int u1, int dim_joint, int act, float* dfe,
                            float* dgd, void* stream);
 
+/* ---- Front end on the device (csrc/frontend.cu) -------------------------------------------------------------------
+ * ec_op_logmel      : audio [B, samples] fp32 -> out [B, n_mels, samples / hop + 1] fp32 =
+ *                       log(fb^T |STFT|^2 + 1e-9), then (x - mean) / std when `normalize`
+ *                     = reference models/modules.py:87-106 AudioPreprocessing.forward (torchaudio Spectrogram(n_fft, win, hop, power 2,
+ *                     centre / reflect padding, one-sided) -> MelScale -> log) in one kernel.  window [n_fft]: the analysis window already
+ *                     centred and zero padded to n_fft (torch.stft's own padding of a win_length window); fb [n_fft/2 + 1, n_mels]: the
+ *                     MelScale filter bank (a state buffer of the reference module); krange [n_mels][2] (optional, device): first / one past
+ *                     last non-zero bin of each filter.  n_fft a power of two in [64, 2048]; samples > n_fft / 2 (as torch.stft).
+ * ec_op_specaugment : mel [B, n_mels, T] fp32 in place <- reference models/modules.py:136-151 SpecAugment.forward: mF frequency masks shared
+ *                     by the batch (torchaudio FrequencyMasking(F, iid_masks=False)), mT time masks per utterance inside its x_len[b] valid
+ *                     frames with parameter int(pS * x_len[b]); mask_along_axis arithmetic: value = U * param, start = floor(U' * (size -
+ *                     value)), end = start + floor(value); masked cells <- 0.  U, U' are counter-based draws of the device {seed, step} pair
+ *                     of ec_op_dropout_advance (so a replayed CUDA graph draws new masks); x_len NULL = every utterance is T frames long. */
+int ec_op_logmel(const float* audio, int batch, int samples, int n_fft, int hop, const float* window, const float* fb, const int* krange,
+                 int n_mels, int normalize, float mean, float stdv, float* out, void* stream);
+int ec_op_specaugment(float* mel, const long long* x_len, int batch, int n_mels, int t, int mF, int F, int mT, float pS,
+                      const unsigned long long* counter, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -243,3 +243,27 @@ def test_rnnt_oracle_against_reference_joint_and_torchaudio_loss(golden_dir):
         mean, per = R.rnnt_loss(logits.double(), c["y"], c["f_len"], c["y_len"])
         assert torch.allclose(per.float(), c["loss_per_utt"], rtol=2e-5, atol=1e-4), (name, per, c["loss_per_utt"])
         assert abs(float(mean) - float(c["loss_mean"])) < 2e-5 * abs(float(c["loss_mean"]))
+
+
+def test_frontend_oracle_against_reference_golden(golden_dir):
+    """oracle/frontend_oracle.py pinned: log-mel against the REAL reference AudioPreprocessing, the SpecAugment span arithmetic against
+    torchaudio's mask_along_axis with preset uniforms (tests/golden/make_golden_frontend.py)."""
+    import numpy as np
+    from oracle import frontend_oracle as FO
+    g = torch.load(os.path.join(golden_dir, "frontend_small.pt"))
+    for name, c in g["logmel"].items():
+        mel, mel_len = FO.logmel(c["audio"].numpy(), normalize=c["normalize"], mean=c["mean"], std=c["std"], audio_len=c["audio_len"].numpy())
+        ref = c["mel"].double().numpy()
+        assert mel.shape == ref.shape and (mel_len == c["mel_len"].numpy()).all()
+        assert np.abs(mel - ref).max() < 2e-4 and np.linalg.norm(mel - ref) / np.linalg.norm(ref) < 5e-6, name
+    for s in g["spans"]:
+        st, en = FO.span_from_uniforms(s["u1"], s["u2"], s["param"], s["size"])
+        assert max(en - st, 0) == s["width"] and (s["width"] == 0 or (st, en) == (s["start"], s["end"])), s
+    # the counter-based application: masks inside the valid frames, frequency masks shared by the batch, deterministic in (seed, step)
+    mel = np.ones((3, 80, 200), dtype=np.float32)
+    a = FO.specaugment_apply(mel, [200, 120, 7], 5, 1, 2, 27, 5, 0.05)
+    b = FO.specaugment_apply(mel, [200, 120, 7], 5, 1, 2, 27, 5, 0.05)
+    c2 = FO.specaugment_apply(mel, [200, 120, 7], 5, 2, 2, 27, 5, 0.05)
+    assert (a == b).all() and not (a == c2).all()
+    assert ((a == 0).all(2) == (a == 0).all(2)[0:1]).all()
+    assert not (a[1] == 0).all(0)[120:].any() and not (a[2] == 0).all(0)[7:].any()
