@@ -381,8 +381,9 @@ def test_optimizer_checkpoint_round_trip_and_accumulated_steps():
 
 
 # ---- two GPUs: utterance shards + SyncBatchNorm + one all-reduced gradient bucket == the single-GPU step on the whole batch ----------
-def _dp_worker(rank, world, port, prec, graph, q):
+def _dp_worker(rank, world, port, prec, graph, q, overlap=False):
     import torch.distributed as dist
+    os.environ["EFFCONF_BUCKET_OVERLAP"] = "1" if overlap else "0"     # gradient buckets leaving during the backward, or one after it
     from efficientconformer_b200.trainer import CTCTrainStep
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -404,6 +405,7 @@ def _dp_worker(rank, world, port, prec, graph, q):
             m.load_state_dict(seeded_state_dict(sp, V2, seed=0, prefix_encoder="encoder."), strict=False)
             m = m.to(dev).train()
             st = CTCTrainStep(m, tp, precision=prec, use_cuda_graph=graph, sync_bn=True, data_parallel=data_parallel)
+            assert bool(st._buckets) == (overlap and data_parallel)
             ls = [float(st.step(mel[sl].to(dev), None, y[sl].to(dev), yl[sl].to(dev))) for mel in mels]
             # numpy: pickled by value (tensors travel through a queue as shared-memory handles that die with the worker)
             return ls, st.flat.exp_avg.cpu().numpy().copy(), st.flat.params.cpu().numpy().copy(), \
@@ -418,14 +420,14 @@ def _dp_worker(rank, world, port, prec, graph, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_two_gpu_data_parallel_step_matches_single_gpu_full_batch(graph):
+@pytest.mark.parametrize("graph,overlap", [(False, False), (True, False), (False, True), (True, True)])
+def test_two_gpu_data_parallel_step_matches_single_gpu_full_batch(graph, overlap):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_dp_worker, args=(r, 2, 29761 + int(graph), "tf32", graph, q)) for r in range(2)]
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, 29761 + int(graph) + 2 * int(overlap), "tf32", graph, q, overlap)) for r in range(2)]
     for p in procs:
         p.start()
     res = {}
@@ -446,5 +448,5 @@ def test_two_gpu_data_parallel_step_matches_single_gpu_full_batch(graph):
         assert rel_l2(s0[k], sf[k]) < 3e-4, k                                 # == statistics of the whole batch (3 Adam steps apart: 1.2e-4 measured)
     for a, b, f in zip(l0, l1, lf):
         assert abs(0.5 * (a + b) - f) < 1e-4 * abs(f), (l0, l1, lf)           # mean of the shard losses == loss of the whole batch
-    print(f"\n[2 GPUs graph={graph}] shard losses {l0} {l1} | whole batch {lf} | exp_avg rel-L2 {rel_l2(m0, mf):.2e}")
+    print(f"\n[2 GPUs graph={graph} overlapped buckets={overlap}] shard losses {l0} {l1} | whole batch {lf} | exp_avg rel-L2 {rel_l2(m0, mf):.2e}")
     assert rel_l2(m0, mf) < 2e-3
