@@ -45,6 +45,8 @@ __device__ __forceinline__ void locate(int h, int d, int D, int c, int& fo, int&
 // ---- kernel 1: per (b, h, 16 query rows): P, dS, dQu, dQv (+ the grouped dense copies Qu, Qv, dO) ---------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kThreads) attn_bwd_rows_kernel(const BwdDev p) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   extern __shared__ float sm[];
   const int Tg = p.Tg, d = p.d, dp = p.dp, D = p.D, G = p.G, Tt = p.T;
   float* Sb = sm;                                   // [kRows][Tg]   scores -> P
@@ -224,6 +226,8 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_rows_kernel(const BwdDev p)
 
 // ---- kernel 2: per (b, h, 16 key rows): dV_j = sum_i P_ij dO_i, dK_j = sum_i dS_ij Qu_i ------------------------------------------
 __global__ void __launch_bounds__(kThreads) attn_bwd_cols_kernel(const BwdDev p) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   extern __shared__ float sm[];
   const int Tg = p.Tg, d = p.d, dp = p.dp, D = p.D, G = p.G, Tt = p.T;
   float* Gs = sm;                                   // [kTile][dp]  dO rows of the query tile
@@ -283,6 +287,8 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_cols_kernel(const BwdDev p)
 
 // ---- kernel 3: dE[e, h*d + c] = sum_b sum_i dS[b,h,i,i+e-(T'-1)] Qv[b,h,i,c];  du / dv partial rows per (b, h) -----------------------
 __global__ void __launch_bounds__(128) attn_bwd_e_kernel(const BwdDev p) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int Tg = p.Tg, d = p.d;
   const int e = blockIdx.x, h = blockIdx.y;
   const int off = e - (Tg - 1);                     // j = i + off
@@ -301,6 +307,8 @@ __global__ void __launch_bounds__(128) attn_bwd_e_kernel(const BwdDev p) {
 // du_part[bh][ch] / dv_part[bh][ch] = sum_i dQu / dQv over the rows of one (b, h) (features of one head map to distinct channels
 // only when d <= D; for grouped heads d = G*D/H may exceed D: several features share a channel and are added in feature order)
 __global__ void __launch_bounds__(128) attn_bwd_uv_kernel(const BwdDev p) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int Tg = p.Tg, d = p.d, D = p.D;
   const int h = blockIdx.x, b = blockIdx.y;
   const size_t bh = static_cast<size_t>(b) * p.H + h;
@@ -316,6 +324,8 @@ __global__ void __launch_bounds__(128) attn_bwd_uv_kernel(const BwdDev p) {
 }
 __global__ void attn_bwd_uv_reduce_kernel(const float* __restrict__ du_part, const float* __restrict__ dv_part, int n, int D,
                                           float* __restrict__ du, float* __restrict__ dv) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= D) return;
   float su = 0.f, sv = 0.f;
@@ -375,21 +385,21 @@ int launch_relpos_attention_bwd(int precision, const AttnArgs& a, const float* d
   if (precision == EC_PREC_TF32) {
     static cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     EC_CUDA(e1);
-    attn_bwd_rows_kernel<float><<<g1, kThreads, sm1, stream>>>(p);
+    (void)launch_dep(attn_bwd_rows_kernel<float>, dim3(g1), dim3(kThreads), sm1, stream, p);
   } else {
     static cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_rows_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     EC_CUDA(e2);
-    attn_bwd_rows_kernel<__nv_bfloat16><<<g1, kThreads, sm1, stream>>>(p);
+    (void)launch_dep(attn_bwd_rows_kernel<__nv_bfloat16>, dim3(g1), dim3(kThreads), sm1, stream, p);
   }
   EC_CUDA(cudaGetLastError());
   const size_t sm2 = sizeof(float) * (2 * static_cast<size_t>(kTile) * p.dp + 2 * kTile * (kRows + 1));
-  attn_bwd_cols_kernel<<<g1, kThreads, sm2, stream>>>(p);
+  (void)launch_dep(attn_bwd_cols_kernel, dim3(g1), dim3(kThreads), sm2, stream, p);
   EC_CUDA(cudaGetLastError());
-  attn_bwd_e_kernel<<<dim3(2 * p.Tg - 1, p.H), 128, 0, stream>>>(p);
+  (void)launch_dep(attn_bwd_e_kernel, dim3(dim3(2 * p.Tg - 1, p.H)), dim3(128), 0, stream, p);
   EC_CUDA(cudaGetLastError());
-  attn_bwd_uv_kernel<<<dim3(p.H, p.B), 128, 0, stream>>>(p);
+  (void)launch_dep(attn_bwd_uv_kernel, dim3(dim3(p.H, p.B)), dim3(128), 0, stream, p);
   EC_CUDA(cudaGetLastError());
-  attn_bwd_uv_reduce_kernel<<<cdiv(p.D, 128), 128, 0, stream>>>(p.du_part, p.dv_part, p.B * p.H, p.D, du, dv);
+  (void)launch_dep(attn_bwd_uv_reduce_kernel, dim3(cdiv(p.D, 128)), dim3(128), 0, stream, p.du_part, p.dv_part, p.B * p.H, p.D, du, dv);
   EC_CUDA(cudaGetLastError());
   if (dqkv_act != nullptr) EC_TRY(launch_cast_rows(precision, dqkv, dqkv_act, static_cast<size_t>(a.B) * a.T * 3 * a.D, stream));
   return EC_OK;

@@ -51,6 +51,8 @@ struct BGemm {
 //                                      BKN = false: B is [N, K] (K contiguous); BKN = true: B is stored [K, N] (N contiguous).
 template <bool TA, bool BKN>
 __global__ void __launch_bounds__(128) bgemm_kernel(const BGemm g) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   __shared__ __align__(16) bf16 As[2][TA ? BK * kPitchM : BM * kPitchK];
   __shared__ __align__(16) bf16 Bs[2][BKN ? BK * kPitchM : BN * kPitchK];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -178,6 +180,8 @@ __device__ __forceinline__ void store_pair(bf16* p, float a, float b) { *reinter
 
 template <typename TIn>
 __global__ void __launch_bounds__(256) tc_pack_kernel(const TcDev p) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int hp = p.dp / 2;
   const long long n = static_cast<long long>(p.B) * p.H * p.Tg * hp;
   const long long row3 = 3LL * p.D;
@@ -208,6 +212,8 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const TcDev p) {
 // scalar variants for odd head / model dims (one thread per element)
 template <typename TIn>
 __global__ void __launch_bounds__(256) tc_pack_scalar_kernel(const TcDev p) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const long long n = static_cast<long long>(p.B) * p.H * p.Tg * p.dp;
   const long long row3 = 3LL * p.D;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -233,6 +239,8 @@ __global__ void __launch_bounds__(256) tc_pack_scalar_kernel(const TcDev p) {
   }
 }
 __global__ void __launch_bounds__(256) tc_unpack_scalar_kernel(const TcDev p) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const long long n = static_cast<long long>(p.B) * p.T * p.D;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int ch = static_cast<int>(idx % p.D);
@@ -249,6 +257,8 @@ __global__ void __launch_bounds__(256) tc_unpack_scalar_kernel(const TcDev p) {
 }
 template <typename TIn>
 __global__ void __launch_bounds__(256) tc_pack_e_kernel(const TcDev p) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const long long n = static_cast<long long>(p.H) * p.R * p.dp;
   const long long e_row = static_cast<long long>(p.H) * p.d;            // = G * D
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -262,6 +272,8 @@ __global__ void __launch_bounds__(256) tc_pack_e_kernel(const TcDev p) {
 // ---- rows: softmax, dS, dRel.  One warp per (bh, i); NPL = score elements per lane -----------------------------------------------
 template <int NPL>
 __global__ void __launch_bounds__(256) tc_rows_kernel(const TcDev p) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
   if (row >= static_cast<long long>(p.B) * p.H * p.Tg) return;
@@ -334,6 +346,8 @@ template <> __device__ __forceinline__ void unpack_store<SplitBf16>(void* base, 
 }
 template <typename TO>
 __global__ void __launch_bounds__(256) tc_unpack_kernel(const TcDev p, void* __restrict__ out_base) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int hD = p.D / 2;
   const long long n = static_cast<long long>(p.B) * p.T * hD;
   for (long long idx2 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx2 < n; idx2 += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -354,6 +368,8 @@ __global__ void __launch_bounds__(256) tc_unpack_kernel(const TcDev p, void* __r
 // column sums of dQu / dQv over the grouped rows of one (b, h): uv_part[bh][0 | 1][c].  Block = 32 columns x 32 row lanes, lane ty
 // adds the contiguous row chunk ty, chunk sums added in lane order (fixed order).
 __global__ void __launch_bounds__(1024) tc_uv_part_kernel(const TcDev p) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   __shared__ float su_s[32][33], sv_s[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int bh = blockIdx.x, c = blockIdx.y * 32 + tx;
@@ -376,6 +392,8 @@ __global__ void __launch_bounds__(1024) tc_uv_part_kernel(const TcDev p) {
 }
 // du[ch] = sum_b sum_fo part[b, h(fo, ch), c(fo, ch)]: 32 channels x 32 batch lanes per block (fixed order)
 __global__ void __launch_bounds__(1024) tc_uv_reduce_kernel(const TcDev p) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   __shared__ float su_s[32][33], sv_s[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int ch = blockIdx.x * 32 + tx;
@@ -399,6 +417,8 @@ __global__ void __launch_bounds__(1024) tc_uv_reduce_kernel(const TcDev p) {
 }
 // dE[e, h*d + c] = sum_b dEp[b, h, e, c]
 __global__ void __launch_bounds__(128) tc_de_reduce_kernel(const TcDev p) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int e = blockIdx.x, h = blockIdx.y;
   for (int c = threadIdx.x; c < p.d; c += blockDim.x) {
     float s = 0.f;
@@ -430,7 +450,7 @@ TcLayout tc_layout(int B, int T, int D, int H, int G) {
 template <bool TA, bool BKN>
 int run_gemm(const BGemm& g, int BH, cudaStream_t st) {
   dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), BH);
-  bgemm_kernel<TA, BKN><<<grid, 128, 0, st>>>(g);
+  (void)launch_dep(bgemm_kernel<TA, BKN>, dim3(grid), dim3(128), 0, st, g);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -466,8 +486,8 @@ int launch_relpos_attention_bwd_tc(int precision, const AttnArgs& a, const float
 
   const bool pairs = a.D % 2 == 0 && p.d % 2 == 0;      // feature pairs stay inside one head and one frame
   const int pgrid = egrid(static_cast<long long>(BH) * Tg * dp / (pairs ? 2 : 1));
-#define EC_PACK(TIN) do { if (pairs) tc_pack_kernel<TIN><<<pgrid, 256, 0, st>>>(p); else tc_pack_scalar_kernel<TIN><<<pgrid, 256, 0, st>>>(p); \
-                          tc_pack_e_kernel<TIN><<<egrid(static_cast<long long>(H) * p.R * dp), 256, 0, st>>>(p); } while (0)
+#define EC_PACK(TIN) do { if (pairs) (void)launch_dep(tc_pack_kernel<TIN>, dim3(pgrid), dim3(256), 0, st, p); else (void)launch_dep(tc_pack_scalar_kernel<TIN>, dim3(pgrid), dim3(256), 0, st, p); \
+                          (void)launch_dep(tc_pack_e_kernel<TIN>, dim3(egrid(static_cast<long long>(H) * p.R * dp)), dim3(256), 0, st, p); } while (0)
   if (precision == EC_PREC_BF16X2 && !a.in_f16) EC_PACK(SplitBf16);
   else if (precision == EC_PREC_BF16X2) EC_PACK(__half);        // fp16 q|k|v / E from the forward; the backward GEMMs run on bf16 copies
   else EC_PACK(bf16);
@@ -486,10 +506,10 @@ int launch_relpos_attention_bwd_tc(int precision, const AttnArgs& a, const float
   if (par) EC_REQUIRE(ss.join(st, 2), "side-stream join failed");
   const long long rows = static_cast<long long>(BH) * Tg;
   const int rgrid = static_cast<int>((rows + 7) / 8);
-  if (Tg <= 128) tc_rows_kernel<4><<<rgrid, 256, 0, st>>>(p);
-  else if (Tg <= 256) tc_rows_kernel<8><<<rgrid, 256, 0, st>>>(p);
-  else if (Tg <= 512) tc_rows_kernel<16><<<rgrid, 256, 0, st>>>(p);
-  else tc_rows_kernel<32><<<rgrid, 256, 0, st>>>(p);
+  if (Tg <= 128) (void)launch_dep(tc_rows_kernel<4>, dim3(rgrid), dim3(256), 0, st, p);
+  else if (Tg <= 256) (void)launch_dep(tc_rows_kernel<8>, dim3(rgrid), dim3(256), 0, st, p);
+  else if (Tg <= 512) (void)launch_dep(tc_rows_kernel<16>, dim3(rgrid), dim3(256), 0, st, p);
+  else (void)launch_dep(tc_rows_kernel<32>, dim3(rgrid), dim3(256), 0, st, p);
   EC_CUDA(cudaGetLastError());
   if (par) EC_REQUIRE(ss.fork(st, 3), "side-stream fork failed");
   // dQv = dRel Eh (longest contraction: R) on the caller's stream; dV = P^T dO, dK = dS^T Qu (contraction over the query rows: A stored
@@ -500,7 +520,7 @@ int launch_relpos_attention_bwd_tc(int precision, const AttnArgs& a, const float
   EC_TRY((run_gemm<false, true>(BGemm{p.dS, p.Kd, p.dQu, Tg, dp, Tg, p.Tp, dp, dp, sS * H, sS, sD * H, sD, sD * H, sD, H, 0}, BH, s2)));
   // parameter-gradient tail on the third branch: dE_b = dRel^T Qv (per (b, h) partials) reduced over b
   EC_TRY((run_gemm<true, true>(BGemm{p.dRel, p.Qv, p.dEp, p.R, dp, Tg, p.Rp, dp, dp, sR * H, sR, sD * H, sD, sE * H, sE, H, 0}, BH, s3)));
-  tc_de_reduce_kernel<<<dim3(p.R, H), 128, 0, s3>>>(p);
+  (void)launch_dep(tc_de_reduce_kernel, dim3(dim3(p.R, H)), dim3(128), 0, s3, p);
   EC_CUDA(cudaGetLastError());
   if (par) EC_REQUIRE(ss.join(st, 2), "side-stream join failed");      // dV, dK, dQu, dQv complete
   // du / dv from dQu / dQv: parameter gradients, beside the unpack
@@ -510,20 +530,20 @@ int launch_relpos_attention_bwd_tc(int precision, const AttnArgs& a, const float
   }
   const int ugrid = egrid(static_cast<long long>(a.B) * a.T * a.D / 2);
   if (pairs && p.dqkv_act != nullptr) {             // the consumer only reads the activation-type copy: skip the fp32 tensor
-    if (p.act_prec == EC_PREC_BF16) tc_unpack_kernel<bf16><<<ugrid, 256, 0, st>>>(p, p.dqkv_act);
-    else if (p.act_prec == EC_PREC_BF16X2) tc_unpack_kernel<SplitBf16><<<ugrid, 256, 0, st>>>(p, p.dqkv_act);
-    else tc_unpack_kernel<Tf32Out><<<ugrid, 256, 0, st>>>(p, p.dqkv_act);
+    if (p.act_prec == EC_PREC_BF16) (void)launch_dep(tc_unpack_kernel<bf16>, dim3(ugrid), dim3(256), 0, st, p, p.dqkv_act);
+    else if (p.act_prec == EC_PREC_BF16X2) (void)launch_dep(tc_unpack_kernel<SplitBf16>, dim3(ugrid), dim3(256), 0, st, p, p.dqkv_act);
+    else (void)launch_dep(tc_unpack_kernel<Tf32Out>, dim3(ugrid), dim3(256), 0, st, p, p.dqkv_act);
   } else {
     EC_REQUIRE(p.dqkv != nullptr, "attention backward: no fp32 dqkv buffer");
-    if (pairs) tc_unpack_kernel<float><<<ugrid, 256, 0, st>>>(p, p.dqkv);
-    else tc_unpack_scalar_kernel<<<egrid(static_cast<long long>(a.B) * a.T * a.D), 256, 0, st>>>(p);
+    if (pairs) (void)launch_dep(tc_unpack_kernel<float>, dim3(ugrid), dim3(256), 0, st, p, p.dqkv);
+    else (void)launch_dep(tc_unpack_scalar_kernel, dim3(egrid(static_cast<long long>(a.B) * a.T * a.D)), dim3(256), 0, st, p);
     EC_CUDA(cudaGetLastError());
     if (p.dqkv_act != nullptr) EC_TRY(launch_cast_rows(p.act_prec, p.dqkv, p.dqkv_act, static_cast<size_t>(a.B) * a.T * 3 * a.D, st));
   }
   EC_CUDA(cudaGetLastError());
-  tc_uv_part_kernel<<<dim3(BH, cdiv(dp, 32)), 1024, 0, s1>>>(p);
+  (void)launch_dep(tc_uv_part_kernel, dim3(dim3(BH, cdiv(dp, 32))), dim3(1024), 0, s1, p);
   EC_CUDA(cudaGetLastError());
-  tc_uv_reduce_kernel<<<cdiv(a.D, 32), 1024, 0, s1>>>(p);
+  (void)launch_dep(tc_uv_reduce_kernel, dim3(cdiv(a.D, 32)), dim3(1024), 0, s1, p);
   EC_CUDA(cudaGetLastError());
   if (par) {
     EC_CUDA(cudaEventRecord(ss.join_ev[0], s1)); EC_CUDA(cudaStreamWaitEvent(st, ss.join_ev[0], 0));

@@ -32,6 +32,8 @@ template <int NPL, typename TE>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int rows, int dim,
                                                             const float* __restrict__ gamma, float eps, float* __restrict__ dx,
                                                             int accumulate, float* __restrict__ partial /* [gridDim.x][2][dim] */, const LnEmit em) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   constexpr bool kEmit = !std::is_same<TE, void>::value;
   __shared__ float red[8][32 * NPL];        // cross-warp merge buffer, used for dgamma then dbeta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -137,6 +139,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 // bit-reproducible, and a 32x shorter dependent chain than one thread per column.
 __global__ void __launch_bounds__(1024) partial_reduce_kernel(const float* __restrict__ partial, int n_partial, int n_out, int dim,
                                                               float* __restrict__ out0, float* __restrict__ out1) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   __shared__ float sm[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + tx, n = n_out * dim;
@@ -163,10 +167,10 @@ size_t layernorm_bwd_work_bytes(int dim) { return align_up(static_cast<size_t>(k
 template <typename TE>
 static void launch_ln_bwd_t(int ctas, const float* x, const float* dy, int rows, int dim, const float* gamma, float eps, float* dx, int accumulate,
                             float* work, const LnEmit& em, cudaStream_t stream) {
-  if (dim <= 128) layernorm_bwd_kernel<4, TE><<<ctas, 256, 0, stream>>>(x, dy, rows, dim, gamma, eps, dx, accumulate, work, em);
-  else if (dim <= 256) layernorm_bwd_kernel<8, TE><<<ctas, 256, 0, stream>>>(x, dy, rows, dim, gamma, eps, dx, accumulate, work, em);
-  else if (dim <= 512) layernorm_bwd_kernel<16, TE><<<ctas, 256, 0, stream>>>(x, dy, rows, dim, gamma, eps, dx, accumulate, work, em);
-  else layernorm_bwd_kernel<32, TE><<<ctas, 256, 0, stream>>>(x, dy, rows, dim, gamma, eps, dx, accumulate, work, em);
+  if (dim <= 128) (void)launch_dep(layernorm_bwd_kernel<4, TE>, dim3(ctas), dim3(256), 0, stream, x, dy, rows, dim, gamma, eps, dx, accumulate, work, em);
+  else if (dim <= 256) (void)launch_dep(layernorm_bwd_kernel<8, TE>, dim3(ctas), dim3(256), 0, stream, x, dy, rows, dim, gamma, eps, dx, accumulate, work, em);
+  else if (dim <= 512) (void)launch_dep(layernorm_bwd_kernel<16, TE>, dim3(ctas), dim3(256), 0, stream, x, dy, rows, dim, gamma, eps, dx, accumulate, work, em);
+  else (void)launch_dep(layernorm_bwd_kernel<32, TE>, dim3(ctas), dim3(256), 0, stream, x, dy, rows, dim, gamma, eps, dx, accumulate, work, em);
 }
 
 int launch_layernorm_bwd(const float* x, const float* dy, int rows, int dim, const float* gamma, float eps, float* dx, int accumulate,
@@ -183,7 +187,7 @@ int launch_layernorm_bwd(const float* x, const float* dy, int rows, int dim, con
   else if (emit_precision == EC_PREC_BF16X2) launch_ln_bwd_t<SplitBf16>(ctas, x, dy, rows, dim, gamma, eps, dx, accumulate, work, em, stream);
   else EC_FAIL("unknown precision");
   EC_CUDA(cudaGetLastError());
-  partial_reduce_kernel<<<cdiv(2 * dim, 32), 1024, 0, stream>>>(work, ctas, 2, dim, dgamma, dbeta);
+  (void)launch_dep(partial_reduce_kernel, dim3(cdiv(2 * dim, 32)), dim3(1024), 0, stream, work, ctas, 2, dim, dgamma, dbeta);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -193,6 +197,8 @@ int launch_layernorm_bwd(const float* x, const float* dy, int rows, int dim, con
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ m, int rows, int cols, float* __restrict__ partial) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   // thread = column (blockIdx.y tiles the columns by 256), CTA blockIdx.x walks rows blockIdx.x, + gridDim.x, ...: coalesced rows
   const int c = blockIdx.y * 256 + threadIdx.x;
   if (c >= cols) return;
@@ -209,9 +215,9 @@ int launch_colsum(int precision, const void* m, int is_f32, int rows, int cols, 
   const int ctas = std::min(kBwdCtas, rows);
   dim3 grid(ctas, cdiv(cols, 256));
   if (is_f32) precision = EC_PREC_TF32;
-  EC_DISPATCH_PREC(precision, (colsum_kernel<ActT><<<grid, 256, 0, stream>>>(reinterpret_cast<const ActT*>(m), rows, cols, work)));
+  EC_DISPATCH_PREC(precision, ((void)launch_dep(colsum_kernel<ActT>, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const ActT*>(m), rows, cols, work)));
   EC_CUDA(cudaGetLastError());
-  partial_reduce_kernel<<<cdiv(cols, 32), 1024, 0, stream>>>(work, ctas, 1, cols, out, out);
+  (void)launch_dep(partial_reduce_kernel, dim3(cdiv(cols, 32)), dim3(1024), 0, stream, work, ctas, 1, cols, out, out);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -221,6 +227,8 @@ int launch_colsum(int precision, const void* m, int is_f32, int rows, int cols, 
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __restrict__ src, int rows, int cols, T* __restrict__ dst) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __rest
 int launch_transpose_cast(int precision, const float* src, int rows, int cols, void* dst, cudaStream_t stream) {
   EC_REQUIRE(rows > 0 && cols > 0 && src && dst, "transpose: bad arguments");
   dim3 grid(cdiv(cols, 32), cdiv(rows, 32));
-  EC_DISPATCH_PREC(precision, (transpose_cast_kernel<ActT><<<grid, 256, 0, stream>>>(src, rows, cols, reinterpret_cast<ActT*>(dst))));
+  EC_DISPATCH_PREC(precision, ((void)launch_dep(transpose_cast_kernel<ActT>, dim3(grid), dim3(256), 0, stream, src, rows, cols, reinterpret_cast<ActT*>(dst))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -255,6 +263,8 @@ int launch_transpose_cast(int precision, const float* src, int rows, int cols, v
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) swish_bwd_kernel(const T* __restrict__ z, const float* __restrict__ dy, size_t n, T* __restrict__ dz) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float zz = ActTraits<T>::from(z[i]);
@@ -265,6 +275,8 @@ __global__ void __launch_bounds__(256) swish_bwd_kernel(const T* __restrict__ z,
 template <typename T>
 __global__ void __launch_bounds__(256) glu_bwd_kernel(const T* __restrict__ zg, const float* __restrict__ dy, size_t rows, int C,
                                                       T* __restrict__ dzg) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const size_t n = rows * C;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -280,14 +292,14 @@ __global__ void __launch_bounds__(256) glu_bwd_kernel(const T* __restrict__ zg, 
 int launch_swish_bwd(int precision, const void* z, const float* dy, size_t n, void* dz, cudaStream_t stream) {
   EC_REQUIRE(z && dy && dz && n > 0, "swish backward: bad arguments");
   const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
-  EC_DISPATCH_PREC(precision, (swish_bwd_kernel<ActT><<<blocks, 256, 0, stream>>>(reinterpret_cast<const ActT*>(z), dy, n, reinterpret_cast<ActT*>(dz))));
+  EC_DISPATCH_PREC(precision, ((void)launch_dep(swish_bwd_kernel<ActT>, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const ActT*>(z), dy, n, reinterpret_cast<ActT*>(dz))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
 int launch_glu_bwd(int precision, const void* zg, const float* dy, size_t rows, int C, void* dzg, cudaStream_t stream) {
   EC_REQUIRE(zg && dy && dzg && rows > 0 && C > 0, "GLU backward: bad arguments");
   const int blocks = static_cast<int>(std::min<size_t>((rows * C + 255) / 256, 148 * 16));
-  EC_DISPATCH_PREC(precision, (glu_bwd_kernel<ActT><<<blocks, 256, 0, stream>>>(reinterpret_cast<const ActT*>(zg), dy, rows, C, reinterpret_cast<ActT*>(dzg))));
+  EC_DISPATCH_PREC(precision, ((void)launch_dep(glu_bwd_kernel<ActT>, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const ActT*>(zg), dy, rows, C, reinterpret_cast<ActT*>(dzg))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }

@@ -34,6 +34,8 @@ template <typename T, int KT, int S, bool kFlip>
 __global__ void __launch_bounds__(128) dwconv_run_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                                          int B, int T_in, int T_out, int C, int K, float* __restrict__ y,
                                                          float* __restrict__ partial /* [gridDim.x][3][C] or nullptr */) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int c = blockIdx.y * 128 + threadIdx.x;
   if (c >= C) return;
   float wk[KT];
@@ -85,8 +87,10 @@ __global__ void __launch_bounds__(128) dwconv_run_kernel(const T* __restrict__ x
 
 // (count, mean, M2) partials merged with Chan's update: stats[0][c] = mean, stats[1][c] = M2.
 // Block = 32 channels x 32 lanes: lane ty merges the contiguous chunk ty of the partials in CTA order, then the 32 chunk results
-// are merged in lane order in double (fixed order: bit-reproducible; the dependent chain is n_partial / 32 + 32 steps).
+// are merged as a fixed binary tree (chan_tree_merge_32x32: bit-reproducible; the dependent chain is n_partial / 32 + 5 steps).
 __global__ void __launch_bounds__(1024) bn_stats_merge_kernel(const float* __restrict__ partial, int n_partial, int C, float* __restrict__ stats) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   __shared__ float sn[32][33], smean[32][33], sm2[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -105,19 +109,10 @@ __global__ void __launch_bounds__(1024) bn_stats_merge_kernel(const float* __res
     }
   }
   sn[ty][tx] = n; smean[ty][tx] = mean; sm2[ty][tx] = m2;
-  __syncthreads();
+  chan_tree_merge_32x32(sn, smean, sm2);
   if (ty == 0 && c < C) {
-    double dn = 0.0, dmean = 0.0, dm2 = 0.0;
-    for (int q = 0; q < 32; ++q) {
-      const double nb = sn[q][tx];
-      if (nb == 0.0) continue;
-      const double tot = dn + nb, dl = static_cast<double>(smean[q][tx]) - dmean;
-      dmean += dl * nb / tot;
-      dm2 += static_cast<double>(sm2[q][tx]) + dl * dl * dn * nb / tot;
-      dn = tot;
-    }
-    stats[c] = static_cast<float>(dmean);
-    stats[C + c] = static_cast<float>(dm2);
+    stats[c] = smean[0][tx];
+    stats[C + c] = sm2[0][tx];
   }
 }
 
@@ -142,6 +137,8 @@ __device__ __forceinline__ float chunked_sum_32x32(const float* __restrict__ par
 }
 __global__ void __launch_bounds__(1024) conv_partial_reduce_kernel(const float* __restrict__ partial, int n_partial, int n_out, int dim,
                                                                    float* __restrict__ out) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   __shared__ float sm[32][33];
   const int i = blockIdx.x * 32 + (threadIdx.x & 31), n = n_out * dim;
   const float t = chunked_sum_32x32(partial, n_partial, static_cast<size_t>(n), i, i < n, sm);
@@ -151,6 +148,8 @@ __global__ void __launch_bounds__(1024) conv_partial_reduce_kernel(const float* 
 // stats [2][C] (mean, centred sum of squares M2) over `count` frames -> mean / rstd (biased variance) and the running-statistics update
 __global__ void bn_finalize_kernel(const float* __restrict__ sums, int C, float count, float eps, float momentum, float* __restrict__ mean,
                                    float* __restrict__ rstd, float* __restrict__ running_mean, float* __restrict__ running_var) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float m = sums[c];
@@ -180,6 +179,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) bn_swish_fwd_kernel(const float* __restrict__ y, size_t rows, int C, const float* __restrict__ mean,
                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, T* __restrict__ h) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const size_t n4 = rows * C / 4, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t g = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < n4; g += stride) {
     const int c = static_cast<int>((g * 4) % C);
@@ -204,6 +205,8 @@ __global__ void __launch_bounds__(256) bn_swish_bwd_stats_kernel(const float* __
                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                  float* __restrict__ partial) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   __shared__ float sm[2][8][132];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.y * 128 + tx * 4;
@@ -257,6 +260,8 @@ __global__ void __launch_bounds__(256) bn_swish_bwd_apply_kernel(const float* __
                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                  const float* __restrict__ sums /* [2][C] */, float count,
                                                                  float* __restrict__ dy) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const size_t n4 = rows * C / 4, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   const float inv = 1.f / count;
   for (size_t g = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < n4; g += stride) {
@@ -283,6 +288,8 @@ __global__ void __launch_bounds__(256) bn_swish_bwd_apply_kernel(const float* __
 template <int KT>
 __global__ void __launch_bounds__(128) dwconv_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, int B, int T_in,
                                                               int T_out, int C, int K, int stride, float* __restrict__ dx) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int c = blockIdx.y * 128 + threadIdx.x;
   if (c >= C) return;
   float wk[KT];
@@ -314,6 +321,8 @@ __global__ void __launch_bounds__(128) dwconv_bwd_data_kernel(const float* __res
 template <typename T, int KT, int S>
 __global__ void __launch_bounds__(512) dwconv_bwd_weight_kernel(const float* __restrict__ dy, const T* __restrict__ x, int B, int T_in, int T_out,
                                                                 int C, int K, float* __restrict__ partial) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   __shared__ float sm[3][KT + 1][128];
   const int tx = threadIdx.x & 127, ty = threadIdx.x >> 7;
   const int c = blockIdx.y * 128 + tx;
@@ -364,6 +373,8 @@ __global__ void __launch_bounds__(512) dwconv_bwd_weight_kernel(const float* __r
 // dw[c][k] / db[c] from the partials (chunked fixed-order sum, see chunked_sum_32x32)
 __global__ void __launch_bounds__(1024) dwconv_wgrad_reduce_kernel(const float* __restrict__ partial, int n_partial, int C, int K,
                                                                    float* __restrict__ dw, float* __restrict__ db) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   __shared__ float sm[32][33];
   const int i = blockIdx.x * 32 + (threadIdx.x & 31), n = C * (K + 1);
   const float t = chunked_sum_32x32(partial, n_partial, static_cast<size_t>(n), i, i < n, sm);
@@ -389,18 +400,18 @@ int launch_dwconv_raw(int precision, const void* x, const float* w, const float*
   const int ctas = std::min(run_ctas(B, T_out), kStatRunCtas);
   dim3 grid(ctas, cdiv(C, 128));
   // tap loops are fully unrolled: 15-tap (Efficient Conformer) or 31-tap instances, stride 1 or 2
-#define EC_RAW(KT, S) EC_DISPATCH_PREC(precision, (dwconv_run_kernel<ActT, KT, S, false><<<grid, 128, 0, st>>>(reinterpret_cast<const ActT*>(x), w, bias, B, T, T_out, C, K, y, work)))
+#define EC_RAW(KT, S) EC_DISPATCH_PREC(precision, ((void)launch_dep(dwconv_run_kernel<ActT, KT, S, false>, dim3(grid), dim3(128), 0, st, reinterpret_cast<const ActT*>(x), w, bias, B, T, T_out, C, K, y, work)))
   if (K <= 15) { if (stride == 1) EC_RAW(15, 1); else EC_RAW(15, 2); }
   else { if (stride == 1) EC_RAW(31, 1); else EC_RAW(31, 2); }
 #undef EC_RAW
   EC_CUDA(cudaGetLastError());
-  bn_stats_merge_kernel<<<cdiv(C, 32), 1024, 0, st>>>(work, ctas, C, sums);
+  (void)launch_dep(bn_stats_merge_kernel, dim3(cdiv(C, 32)), dim3(1024), 0, st, work, ctas, C, sums);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
 int launch_bn_finalize(const float* sums, int C, float count, float eps, float momentum, float* mean, float* rstd, float* running_mean,
                        float* running_var, cudaStream_t st) {
-  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(sums, C, count, eps, momentum, mean, rstd, running_mean, running_var);
+  (void)launch_dep(bn_finalize_kernel, dim3(cdiv(C, 128)), dim3(128), 0, st, sums, C, count, eps, momentum, mean, rstd, running_mean, running_var);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -409,7 +420,7 @@ int launch_bn_swish_fwd(int precision, const float* y, size_t rows, int C, const
   EC_REQUIRE(C % 4 == 0 && aligned16(y) && aligned16(h) && aligned16(mean) && aligned16(rstd) && aligned16(gamma) && aligned16(beta),
              "BatchNorm + Swish: channels must be a multiple of 4 and every pointer 16-byte aligned");
   const int blocks = static_cast<int>(std::min<size_t>((rows * C / 4 + 255) / 256, 148 * 8));
-  EC_DISPATCH_PREC(precision, (bn_swish_fwd_kernel<ActT><<<blocks, 256, 0, st>>>(y, rows, C, mean, rstd, gamma, beta, reinterpret_cast<ActT*>(h))));
+  EC_DISPATCH_PREC(precision, ((void)launch_dep(bn_swish_fwd_kernel<ActT>, dim3(blocks), dim3(256), 0, st, y, rows, C, mean, rstd, gamma, beta, reinterpret_cast<ActT*>(h))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -419,9 +430,9 @@ int launch_bn_swish_bwd_stats(const float* y, const float* dh, size_t rows, int 
              "BatchNorm + Swish backward: channels must be a multiple of 4 and every pointer 16-byte aligned");
   const int gy = cdiv(C, 128);
   const int ctas = static_cast<int>(std::max<size_t>(1, std::min<size_t>(std::max(1, kColCtas / gy), (rows + 31) / 32)));
-  bn_swish_bwd_stats_kernel<<<dim3(ctas, gy), 256, 0, st>>>(y, dh, rows, C, mean, rstd, gamma, beta, work);
+  (void)launch_dep(bn_swish_bwd_stats_kernel, dim3(dim3(ctas, gy)), dim3(256), 0, st, y, dh, rows, C, mean, rstd, gamma, beta, work);
   EC_CUDA(cudaGetLastError());
-  conv_partial_reduce_kernel<<<cdiv(2 * C, 32), 1024, 0, st>>>(work, ctas, 2, C, sums);
+  (void)launch_dep(conv_partial_reduce_kernel, dim3(cdiv(2 * C, 32)), dim3(1024), 0, st, work, ctas, 2, C, sums);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -430,7 +441,7 @@ int launch_bn_swish_bwd_apply(const float* y, const float* dh, size_t rows, int 
   EC_REQUIRE(C % 4 == 0 && aligned16(y) && aligned16(dh) && aligned16(dy) && aligned16(mean) && aligned16(rstd) && aligned16(gamma) &&
              aligned16(beta) && aligned16(sums), "BatchNorm + Swish backward: channels must be a multiple of 4 and every pointer 16-byte aligned");
   const int blocks = static_cast<int>(std::min<size_t>((rows * C / 4 + 255) / 256, 148 * 8));
-  bn_swish_bwd_apply_kernel<<<blocks, 256, 0, st>>>(y, dh, rows, C, mean, rstd, gamma, beta, sums, count, dy);
+  (void)launch_dep(bn_swish_bwd_apply_kernel, dim3(blocks), dim3(256), 0, st, y, dh, rows, C, mean, rstd, gamma, beta, sums, count, dy);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -449,24 +460,24 @@ int launch_dwconv_bwd(int precision, const float* dy, const void* x, const float
   if (dx != nullptr) {
     if (stride == 1) {                 // correlation with the reversed taps: the forward run kernel on the fp32 gradient
       dim3 gd(run_ctas(B, T), cdiv(C, 128));
-      if (K <= 15) dwconv_run_kernel<float, 15, 1, true><<<gd, 128, 0, st>>>(dy, w, nullptr, B, T, T, C, K, dx, nullptr);
-      else dwconv_run_kernel<float, 31, 1, true><<<gd, 128, 0, st>>>(dy, w, nullptr, B, T, T, C, K, dx, nullptr);
+      if (K <= 15) (void)launch_dep(dwconv_run_kernel<float, 15, 1, true>, dim3(gd), dim3(128), 0, st, dy, w, nullptr, B, T, T, C, K, dx, nullptr);
+      else (void)launch_dep(dwconv_run_kernel<float, 31, 1, true>, dim3(gd), dim3(128), 0, st, dy, w, nullptr, B, T, T, C, K, dx, nullptr);
     } else {
       const dim3 gd(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(B) * T, 148 * 32)), cdiv(C, 128));
-      if (K <= 15) dwconv_bwd_data_kernel<15><<<gd, 128, 0, st>>>(dy, w, B, T, T_out, C, K, stride, dx);
-      else dwconv_bwd_data_kernel<31><<<gd, 128, 0, st>>>(dy, w, B, T, T_out, C, K, stride, dx);
+      if (K <= 15) (void)launch_dep(dwconv_bwd_data_kernel<15>, dim3(gd), dim3(128), 0, st, dy, w, B, T, T_out, C, K, stride, dx);
+      else (void)launch_dep(dwconv_bwd_data_kernel<31>, dim3(gd), dim3(128), 0, st, dy, w, B, T, T_out, C, K, stride, dx);
     }
     EC_CUDA(cudaGetLastError());
   }
   const int gy = cdiv(C, 128);
   const int ctas = std::max(1, std::min(std::max(1, kColCtas / 2 / gy), cdiv(B * cdiv(T_out, kRun), 4)));
   dim3 grid(ctas, gy);
-#define EC_WG(KT, S) EC_DISPATCH_PREC(precision, (dwconv_bwd_weight_kernel<ActT, KT, S><<<grid, 512, 0, sw>>>(dy, reinterpret_cast<const ActT*>(x), B, T, T_out, C, K, work)))
+#define EC_WG(KT, S) EC_DISPATCH_PREC(precision, ((void)launch_dep(dwconv_bwd_weight_kernel<ActT, KT, S>, dim3(grid), dim3(512), 0, sw, dy, reinterpret_cast<const ActT*>(x), B, T, T_out, C, K, work)))
   if (K <= 15) { if (stride == 1) EC_WG(15, 1); else EC_WG(15, 2); }
   else { if (stride == 1) EC_WG(31, 1); else EC_WG(31, 2); }
 #undef EC_WG
   EC_CUDA(cudaGetLastError());
-  dwconv_wgrad_reduce_kernel<<<cdiv(C * (K + 1), 32), 1024, 0, sw>>>(work, ctas, C, K, dw, db);
+  (void)launch_dep(dwconv_wgrad_reduce_kernel, dim3(cdiv(C * (K + 1), 32)), dim3(1024), 0, sw, work, ctas, C, K, dw, db);
   EC_CUDA(cudaGetLastError());
   if (par) {
     EC_CUDA(cudaEventRecord(ss.join_ev[3], sw));

@@ -10,6 +10,8 @@ namespace ec {
 
 __global__ void __launch_bounds__(256) logsoftmax_argmax_kernel(const float* __restrict__ logits, int rows, int V,
                                                                 float* __restrict__ lse, int* __restrict__ amax) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -34,7 +36,7 @@ __global__ void __launch_bounds__(256) logsoftmax_argmax_kernel(const float* __r
 
 int launch_logsoftmax_argmax(const float* logits, int rows, int V, float* lse, int* argmax, cudaStream_t stream) {
   if (rows == 0) return EC_OK;
-  logsoftmax_argmax_kernel<<<cdiv(rows, 8), 256, 0, stream>>>(logits, rows, V, lse, argmax);
+  (void)launch_dep(logsoftmax_argmax_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, stream, logits, rows, V, lse, argmax);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -50,6 +52,8 @@ __global__ void __launch_bounds__(256) ctc_alpha_kernel(const float* __restrict_
                                                         const int* __restrict__ logits_len, const long long* __restrict__ targets,
                                                         int target_stride, const long long* __restrict__ target_len,
                                                         float* __restrict__ loss_per_utt) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   extern __shared__ float alpha_sm[];
   const int b = blockIdx.x;
   const int U = static_cast<int>(target_len[b]);
@@ -188,6 +192,8 @@ __global__ void __launch_bounds__(kCtcGatherThreads) ctc_alpha_warp_kernel(const
 }
 
 __global__ void mean_kernel(const float* x, int n, float* out) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += 32) s += x[i];
 #pragma unroll
@@ -196,7 +202,7 @@ __global__ void mean_kernel(const float* x, int n, float* out) {
 }
 
 int launch_mean(const float* x, int n, float* out, cudaStream_t stream) {
-  mean_kernel<<<1, 32, 0, stream>>>(x, n, out);
+  (void)launch_dep(mean_kernel, dim3(1), dim3(32), 0, stream, x, n, out);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -214,7 +220,7 @@ int launch_ctc_loss(const float* logits, const float* lse, int B, int T, int V, 
     if (sm <= 200 * 1024) {                                                                                                \
       static cudaError_t attr = cudaFuncSetAttribute(ctc_alpha_warp_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
       EC_CUDA(attr);                                                                                                       \
-      ctc_alpha_warp_kernel<NS><<<B, kCtcGatherThreads, sm, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, loss_per_utt); \
+      (void)launch_dep(ctc_alpha_warp_kernel<NS>, dim3(B), dim3(kCtcGatherThreads), sm, stream, logits, lse, T, V, logits_len, targets, target_stride, target_len, loss_per_utt); \
       launched = true;                                                                                                     \
     }                                                                                                                      \
   }
@@ -225,10 +231,10 @@ int launch_ctc_loss(const float* logits, const float* lse, int B, int T, int V, 
   else if (s_max <= 192) EC_CTC_WARP(6)
   else if (s_max <= 256) EC_CTC_WARP(8)
 #undef EC_CTC_WARP
-  if (!launched) ctc_alpha_kernel<<<B, 256, smem, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, loss_per_utt);
+  if (!launched) (void)launch_dep(ctc_alpha_kernel, dim3(B), dim3(256), smem, stream, logits, lse, T, V, logits_len, targets, target_stride, target_len, loss_per_utt);
   EC_CUDA(cudaGetLastError());
   if (loss_mean != nullptr) {
-    mean_kernel<<<1, 32, 0, stream>>>(loss_per_utt, B, loss_mean);
+    (void)launch_dep(mean_kernel, dim3(1), dim3(32), 0, stream, loss_per_utt, B, loss_mean);
     EC_CUDA(cudaGetLastError());
   }
   return EC_OK;
@@ -236,6 +242,8 @@ int launch_ctc_loss(const float* logits, const float* lse, int B, int T, int V, 
 
 __global__ void greedy_collapse_kernel(const int* __restrict__ amax, int B, int T, const int* __restrict__ logits_len,
                                        int* __restrict__ ids, int* __restrict__ counts) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   int n = 0, prev = 0;
@@ -253,7 +261,7 @@ __global__ void greedy_collapse_kernel(const int* __restrict__ amax, int B, int 
 }
 
 int launch_greedy_collapse(const int* argmax, int B, int T, const int* logits_len, int* ids, int* counts, cudaStream_t stream) {
-  greedy_collapse_kernel<<<cdiv(B, 64), 64, 0, stream>>>(argmax, B, T, logits_len, ids, counts);
+  (void)launch_dep(greedy_collapse_kernel, dim3(cdiv(B, 64)), dim3(64), 0, stream, argmax, B, T, logits_len, ids, counts);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }

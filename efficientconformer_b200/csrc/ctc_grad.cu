@@ -39,6 +39,8 @@ __global__ void __launch_bounds__(kThreads) ctc_grad_kernel(const float* __restr
                                                             float* __restrict__ work,        // [B][T][32*NS] alpha, then gamma
                                                             float* __restrict__ work_lp,     // [B][T][32*NS] emissions when they do not fit on chip
                                                             float grad_scale, float* __restrict__ loss_per_utt, float* __restrict__ grad) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   extern __shared__ float lp_dyn[];                // [Tb][SP] emission log2-probs of the extended labels (or unused: work_lp)
   constexpr int SP = 32 * NS;
   // long utterances x long transcripts (T * (2U+1) floats beyond the shared-memory budget) keep the emissions in an L2-resident scratch
@@ -217,7 +219,7 @@ int launch_ctc_grad(const float* logits, const float* lse, int B, int T, int V, 
     if (sm > kCtcSmemBudget) { work_lp = work + align_up(static_cast<size_t>(B) * T * 32 * NS * sizeof(float), 256) / sizeof(float); sm = 0; } \
     static cudaError_t attr = cudaFuncSetAttribute(ctc_grad_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCtcSmemBudget)); \
     EC_CUDA(attr);                                                                                                                   \
-    ctc_grad_kernel<NS><<<B, kThreads, sm, stream>>>(logits, lse, T, V, logits_len, targets, target_stride, target_len, work, work_lp, \
+    (void)launch_dep(ctc_grad_kernel<NS>, dim3(B), dim3(kThreads), sm, stream, logits, lse, T, V, logits_len, targets, target_stride, target_len, work, work_lp, \
                                                      grad_scale, loss_per_utt, grad);                                                \
     break;                                                                                                                           \
   }

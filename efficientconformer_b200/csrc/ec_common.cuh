@@ -50,6 +50,23 @@ int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cud
   return EC_OK;
 }
 
+// The same attribute for the kernels of the TRAINING step (element / reduction / batched-GEMM kernels of the backward and the train-mode
+// forward).  Every one of them executes griddepcontrol.wait as its first statement (no read or write of global memory before it) and
+// then griddepcontrol.launch_dependents, so its successor's launch and prologue overlap this kernel's run and only the successor's own
+// wait orders the data.  EFFCONF_PDL_TRAIN=0 launches them as plain stream-ordered kernels (A/B measurement).
+bool pdl_train_enabled();
+template <typename... KArgs, typename... Args>
+int launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = (pdl_enabled() && pdl_train_enabled()) ? 1 : 0;
+  EC_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+  return EC_OK;
+}
+
 // Same, as thread-block clusters of `cluster_x` CTAs along x.
 template <typename... KArgs, typename... Args>
 int launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args&&... args) {
@@ -172,6 +189,30 @@ __device__ __forceinline__ float sigmoid_fn(float x) {
 // The keep bit of element i at site s of step n is a pure function of (seed, n, s, i): ctr = {seed, step} lives in device memory, so a
 // replayed CUDA graph draws fresh masks and the backward recomputes the forward mask instead of storing it.  One 64-bit draw covers the
 // 4 consecutive elements 4g .. 4g+3 (16 bits each): keep iff bits < keep16.
+// (count, mean, M2) <- (count, mean, M2) (+) (nb, mb, qb): Chan's parallel update, single precision
+__device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, float nb, float mb, float qb) {
+  if (nb == 0.f) return;
+  const float tot = n + nb, dl = mb - mean, f = nb / tot;
+  mean = fmaf(dl, f, mean);
+  m2 += qb + dl * dl * n * f;
+  n = tot;
+}
+// 32 per-lane-row (count, mean, M2) triples per column (block = 32 columns x 32 rows, arrays [32][33]) merged as a fixed binary tree
+// in shared memory: 5 dependent merges instead of a 32-step chain (which, in double precision with two divisions per step, was 70 % of
+// the merge kernels' time); the result is left in row 0.  Fixed order: bit-reproducible.
+__device__ __forceinline__ void chan_tree_merge_32x32(float (*sn)[33], float (*smean)[33], float (*sm2)[33]) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    __syncthreads();
+    if ((ty & (2 * off - 1)) == 0) {
+      float n = sn[ty][tx], mean = smean[ty][tx], m2 = sm2[ty][tx];
+      chan_merge(n, mean, m2, sn[ty + off][tx], smean[ty + off][tx], sm2[ty + off][tx]);
+      sn[ty][tx] = n; smean[ty][tx] = mean; sm2[ty][tx] = m2;
+    }
+  }
+  __syncthreads();
+}
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
   x += 0x9E3779B97F4A7C15ull;
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;

@@ -84,6 +84,8 @@ int launch_layernorm(int precision, const LayerNormArgs& a, cudaStream_t stream)
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void cast_kernel(const float* __restrict__ src, T* __restrict__ dst, size_t n) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = ActTraits<T>::to(src[i]);
 }
@@ -92,7 +94,7 @@ int launch_cast_rows(int precision, const float* src, void* dst, size_t n, cudaS
   if (n == 0) return EC_OK;
   const int threads = 256;
   const int blocks = static_cast<int>(std::min<size_t>((n + threads - 1) / threads, 148 * 8));
-  EC_DISPATCH_PREC(precision, (cast_kernel<ActT><<<blocks, threads, 0, stream>>>(src, reinterpret_cast<ActT*>(dst), n)));
+  EC_DISPATCH_PREC(precision, ((void)launch_dep(cast_kernel<ActT>, dim3(blocks), dim3(threads), 0, stream, src, reinterpret_cast<ActT*>(dst), n)));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -100,6 +102,8 @@ int launch_cast_rows(int precision, const float* src, void* dst, size_t n, cudaS
 // Weight operand of a GEMM: the activation-type cast and, in split mode, the second plane with the halves swapped at
 // dst + twin_elems (see effconf_b200.h, EC_PREC_BF16X2).
 __global__ void cast_weight_split_kernel(const float* __restrict__ src, uint32_t* __restrict__ dst, size_t n, size_t twin_elems) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint32_t v = split_pack(src[i]);
@@ -111,7 +115,7 @@ int launch_cast_weight(int precision, const float* src, void* dst, size_t n, siz
   if (precision != EC_PREC_BF16X2) return launch_cast_rows(precision, src, dst, n, stream);
   if (n == 0) return EC_OK;
   const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 8));
-  cast_weight_split_kernel<<<blocks, 256, 0, stream>>>(src, reinterpret_cast<uint32_t*>(dst), n, twin_elems);
+  (void)launch_dep(cast_weight_split_kernel, dim3(blocks), dim3(256), 0, stream, src, reinterpret_cast<uint32_t*>(dst), n, twin_elems);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -123,6 +127,8 @@ int launch_cast_weight(int precision, const float* src, void* dst, size_t n, siz
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void fold_bn_kernel(const float* w, const float* b, const float* g, const float* beta, const float* rm, const float* rv,
                                float eps, int C, int taps, float* w_out, float* b_out) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C * taps) return;
   const int c = i / taps;
@@ -133,7 +139,7 @@ __global__ void fold_bn_kernel(const float* w, const float* b, const float* g, c
 
 int launch_fold_bn(const float* w, const float* b, const float* g, const float* beta, const float* rm, const float* rv,
                    float eps, int C, int taps, float* w_out, float* b_out, cudaStream_t stream) {
-  fold_bn_kernel<<<cdiv(C * taps, 256), 256, 0, stream>>>(w, b, g, beta, rm, rv, eps, C, taps, w_out, b_out);
+  (void)launch_dep(fold_bn_kernel, dim3(cdiv(C * taps, 256)), dim3(256), 0, stream, w, b, g, beta, rm, rv, eps, C, taps, w_out, b_out);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -145,6 +151,8 @@ int launch_fold_bn(const float* w, const float* b, const float* g, const float* 
 template <typename T>
 __global__ void glu_interleave_kernel(const float* __restrict__ w, const float* __restrict__ b, int C, int K, int nb, int tiles,
                                       T* __restrict__ w_out, float* __restrict__ b_out) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int row = blockIdx.x;               // output row in [0, tiles*2*nb)
   const int tile = row / (2 * nb), r = row % (2 * nb);
   const bool gate = r >= nb;
@@ -163,7 +171,7 @@ __global__ void glu_interleave_kernel(const float* __restrict__ w, const float* 
 int launch_glu_interleave(int precision, const float* w, const float* b, int channels, int K, int nb, int tiles,
                           void* w_out, float* b_out, cudaStream_t stream) {
   const int rows = tiles * 2 * nb;
-  EC_DISPATCH_PREC(precision, (glu_interleave_kernel<ActT><<<rows, 128, 0, stream>>>(w, b, channels, K, nb, tiles, reinterpret_cast<ActT*>(w_out), b_out)));
+  EC_DISPATCH_PREC(precision, ((void)launch_dep(glu_interleave_kernel<ActT>, dim3(rows), dim3(128), 0, stream, w, b, channels, K, nb, tiles, reinterpret_cast<ActT*>(w_out), b_out)));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -188,12 +196,14 @@ __global__ void stage_lengths_kernel(const long long* x_len, int B, int t_mel, B
 }
 
 int launch_stage_lengths(const long long* x_len, int B, int t_mel, const BlockStrides& st, int* out, cudaStream_t stream) {
-  stage_lengths_kernel<<<cdiv(B, 128), 128, 0, stream>>>(x_len, B, t_mel, st, out);
+  (void)launch_dep(stage_lengths_kernel, dim3(cdiv(B, 128)), dim3(128), 0, stream, x_len, B, t_mel, st, out);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
 
 __global__ void i64_to_i32_kernel(const long long* src, int n, int* dst, int clamp_max) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { long long v = src[i]; if (v > clamp_max) v = clamp_max; if (v < 0) v = 0; dst[i] = static_cast<int>(v); }
 }
@@ -203,12 +213,12 @@ __global__ void i32_to_i64_kernel(const int* src, int n, long long* dst) {
   if (i < n) dst[i] = src[i];
 }
 int launch_i64_to_i32(const long long* src, int n, int* dst, int clamp_max, cudaStream_t stream) {
-  i64_to_i32_kernel<<<cdiv(n, 128), 128, 0, stream>>>(src, n, dst, clamp_max);
+  (void)launch_dep(i64_to_i32_kernel, dim3(cdiv(n, 128)), dim3(128), 0, stream, src, n, dst, clamp_max);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
 int launch_i32_to_i64(const int* src, int n, long long* dst, cudaStream_t stream) {
-  i32_to_i64_kernel<<<cdiv(n, 128), 128, 0, stream>>>(src, n, dst);
+  (void)launch_dep(i32_to_i64_kernel, dim3(cdiv(n, 128)), dim3(128), 0, stream, src, n, dst);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }

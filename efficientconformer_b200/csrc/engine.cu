@@ -19,6 +19,12 @@ bool pdl_enabled() {
   return g_pdl != 0;
 }
 
+static int g_pdl_train = -1;
+bool pdl_train_enabled() {
+  if (g_pdl_train < 0) { const char* e = getenv("EFFCONF_PDL_TRAIN"); g_pdl_train = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return g_pdl_train != 0;
+}
+
 bool SideStreams::init() {
   if (ok) return true;
   for (int i = 0; i < kN; ++i) {

@@ -20,6 +20,8 @@ __device__ __forceinline__ void cta_rows(size_t rows, size_t& r0, size_t& r1) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) swish_fwd_kernel(const T* __restrict__ z, size_t n, T* __restrict__ h) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float v = ActTraits<T>::from(z[i]);
@@ -28,6 +30,8 @@ __global__ void __launch_bounds__(256) swish_fwd_kernel(const T* __restrict__ z,
 }
 template <typename T>
 __global__ void __launch_bounds__(256) glu_fwd_kernel(const T* __restrict__ zg, size_t rows, int C, T* __restrict__ out) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const size_t n = rows * C, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const size_t r = i / C; const int c = static_cast<int>(i - r * C);
@@ -38,6 +42,8 @@ __global__ void __launch_bounds__(256) glu_fwd_kernel(const T* __restrict__ zg, 
 template <typename T>
 __global__ void __launch_bounds__(256) strided_rows_kernel(const float* __restrict__ x, int B, int T_in, int T_out, int D, int stride,
                                                            T* __restrict__ out) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const size_t n = static_cast<size_t>(B) * T_out * D, st = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += st) {
     const int c = static_cast<int>(i % D);
@@ -49,6 +55,8 @@ __global__ void __launch_bounds__(256) strided_rows_kernel(const float* __restri
 // scatter back: dx[b, t*s, :] += d[b, t, :]  (the gradient of the strided copy, added to the residual-stream gradient)
 __global__ void __launch_bounds__(256) strided_rows_bwd_kernel(const float* __restrict__ d, int B, int T_in, int T_out, int D, int stride,
                                                                float* __restrict__ dx) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const size_t n = static_cast<size_t>(B) * T_out * D, st = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += st) {
     const int c = static_cast<int>(i % D);
@@ -60,37 +68,39 @@ __global__ void __launch_bounds__(256) strided_rows_bwd_kernel(const float* __re
 
 template <typename T>
 __global__ void __launch_bounds__(256) cast_scaled_kernel(const float* __restrict__ src, float scale, size_t n, T* __restrict__ dst) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = ActTraits<T>::to(scale * src[i]);
 }
 static int grid_for(size_t n);
 int launch_cast_scaled(int precision, const float* src, float scale, size_t n, void* dst, cudaStream_t st) {
-  EC_DISPATCH_PREC(precision, (cast_scaled_kernel<ActT><<<grid_for(n), 256, 0, st>>>(src, scale, n, reinterpret_cast<ActT*>(dst))));
+  EC_DISPATCH_PREC(precision, ((void)launch_dep(cast_scaled_kernel<ActT>, dim3(grid_for(n)), dim3(256), 0, st, src, scale, n, reinterpret_cast<ActT*>(dst))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
 static int grid_for(size_t n) { return static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16)); }
 
 int launch_swish_fwd(int precision, const void* z, size_t n, void* h, cudaStream_t st) {
-  EC_DISPATCH_PREC(precision, (swish_fwd_kernel<ActT><<<grid_for(n), 256, 0, st>>>(reinterpret_cast<const ActT*>(z), n, reinterpret_cast<ActT*>(h))));
+  EC_DISPATCH_PREC(precision, ((void)launch_dep(swish_fwd_kernel<ActT>, dim3(grid_for(n)), dim3(256), 0, st, reinterpret_cast<const ActT*>(z), n, reinterpret_cast<ActT*>(h))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
 int launch_glu_fwd(int precision, const void* zg, size_t rows, int C, void* out, cudaStream_t st) {
-  EC_DISPATCH_PREC(precision, (glu_fwd_kernel<ActT><<<grid_for(rows * C), 256, 0, st>>>(reinterpret_cast<const ActT*>(zg), rows, C, reinterpret_cast<ActT*>(out))));
+  EC_DISPATCH_PREC(precision, ((void)launch_dep(glu_fwd_kernel<ActT>, dim3(grid_for(rows * C)), dim3(256), 0, st, reinterpret_cast<const ActT*>(zg), rows, C, reinterpret_cast<ActT*>(out))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
 int launch_strided_rows(int precision, const float* x, int B, int T_in, int D, int stride, void* out, cudaStream_t st) {
   const int T_out = (T_in - 1) / stride + 1;
   const size_t n = static_cast<size_t>(B) * T_out * D;
-  EC_DISPATCH_PREC(precision, (strided_rows_kernel<ActT><<<grid_for(n), 256, 0, st>>>(x, B, T_in, T_out, D, stride, reinterpret_cast<ActT*>(out))));
+  EC_DISPATCH_PREC(precision, ((void)launch_dep(strided_rows_kernel<ActT>, dim3(grid_for(n)), dim3(256), 0, st, x, B, T_in, T_out, D, stride, reinterpret_cast<ActT*>(out))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
 int launch_strided_rows_bwd(const float* d, int B, int T_in, int D, int stride, float* dx, cudaStream_t st) {
   const int T_out = (T_in - 1) / stride + 1;
-  strided_rows_bwd_kernel<<<grid_for(static_cast<size_t>(B) * T_out * D), 256, 0, st>>>(d, B, T_in, T_out, D, stride, dx);
+  (void)launch_dep(strided_rows_bwd_kernel, dim3(grid_for(static_cast<size_t>(B) * T_out * D)), dim3(256), 0, st, d, B, T_in, T_out, D, stride, dx);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -100,6 +110,8 @@ int launch_strided_rows_bwd(const float* d, int B, int T_in, int D, int stride, 
 // CTA's rows (mean, then centred squares: sum of squares minus mean^2 loses every digit when |mean| >> std), 4 rows in flight per
 // thread; the 8 row lanes are Chan-merged in shared memory in lane order.  partial[cta.x] = (count, mean, M2) per column.
 __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict__ y, size_t rows, int cols, float* __restrict__ partial) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   __shared__ float sm[3][8][132];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.y * 128 + tx * 4;
@@ -155,8 +167,10 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict_
   }
 }
 // (count, mean, M2) partials -> stats[0][c] = mean, stats[1][c] = M2: block = 32 columns x 32 lanes, lane ty merges the contiguous chunk
-// ty of the partials in order, the 32 chunk results are merged in lane order in double (fixed order, short dependent chains)
+// ty of the partials in order, the 32 chunk results are merged as a fixed binary tree (chan_tree_merge_32x32)
 __global__ void __launch_bounds__(1024) col_stats_merge_kernel(const float* __restrict__ partial, int n_partial, int cols, float* __restrict__ stats) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   __shared__ float sn[32][33], smean[32][33], sm2[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -174,35 +188,31 @@ __global__ void __launch_bounds__(1024) col_stats_merge_kernel(const float* __re
     }
   }
   sn[ty][tx] = n; smean[ty][tx] = mean; sm2[ty][tx] = m2;
-  __syncthreads();
+  chan_tree_merge_32x32(sn, smean, sm2);
   if (ty == 0 && c < cols) {
-    double dn = 0.0, dmean = 0.0, dm2 = 0.0;
-    for (int q = 0; q < 32; ++q) {
-      const double nb = sn[q][tx];
-      if (nb == 0.0) continue;
-      const double tot = dn + nb, dl = static_cast<double>(smean[q][tx]) - dmean;
-      dmean += dl * nb / tot;
-      dm2 += static_cast<double>(sm2[q][tx]) + dl * dl * dn * nb / tot;
-      dn = tot;
-    }
-    stats[c] = static_cast<float>(dmean); stats[cols + c] = static_cast<float>(dm2);
+    stats[c] = smean[0][tx];
+    stats[cols + c] = sm2[0][tx];
   }
 }
 // channel c owns the `group` consecutive columns c*group .. : merge their (mean, M2) (each over `rows` samples) -> [2][C]
 __global__ void group_stats_merge_kernel(const float* __restrict__ col_stats, int C, int group, double rows, float* __restrict__ ch_stats) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const int cols = C * group;
-  double n = 0.0, mean = 0.0, m2 = 0.0;
-  for (int f = 0; f < group; ++f) {
-    const double mb = col_stats[c * group + f], qb = col_stats[cols + c * group + f];
-    const double tot = n + rows, dl = mb - mean;
-    mean += dl * rows / tot; m2 += qb + dl * dl * n * rows / tot; n = tot;
-  }
-  ch_stats[c] = static_cast<float>(mean); ch_stats[C + c] = static_cast<float>(m2);
+  // equal counts: mean of the column means, M2 = sum of the column M2 + rows * sum (column mean - mean)^2 (no dependent division chain)
+  double sum = 0.0, m2 = 0.0;
+  for (int f = 0; f < group; ++f) { sum += col_stats[c * group + f]; m2 += col_stats[cols + c * group + f]; }
+  const double mean = sum / group;
+  double dev = 0.0;
+  for (int f = 0; f < group; ++f) { const double d = col_stats[c * group + f] - mean; dev += d * d; }
+  ch_stats[c] = static_cast<float>(mean); ch_stats[C + c] = static_cast<float>(m2 + rows * dev);
 }
 // out[j][c*group + f] = in[j][c]  (per-channel vectors expanded to per-column vectors);  n_vec stacked vectors
 __global__ void group_expand_kernel(const float* __restrict__ in, int n_vec, int C, int group, float* __restrict__ out) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_vec * C * group) return;
   const int j = i / (C * group), col = i - j * C * group;
@@ -210,6 +220,8 @@ __global__ void group_expand_kernel(const float* __restrict__ in, int n_vec, int
 }
 // out[j][c] = sum_f in[j][c*group + f]  (column sums folded into channel sums, fixed order)
 __global__ void group_sum_kernel(const float* __restrict__ in, int n_vec, int C, int group, float* __restrict__ out) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_vec * C) return;
   const int j = i / C, c = i - j * C;
@@ -227,24 +239,24 @@ size_t col_stats_work_bytes(int cols) { return align_up(static_cast<size_t>(kCol
 int launch_col_stats(const float* y, size_t rows, int cols, float* stats, float* work, cudaStream_t st) {
   EC_REQUIRE(cols % 4 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "column statistics: columns must be a multiple of 4, 16-byte aligned rows");
   const int ctas = col_stat_ctas(rows, cols);
-  col_stats_kernel<<<dim3(ctas, cdiv(cols, 128)), 256, 0, st>>>(y, rows, cols, work);
+  (void)launch_dep(col_stats_kernel, dim3(dim3(ctas, cdiv(cols, 128))), dim3(256), 0, st, y, rows, cols, work);
   EC_CUDA(cudaGetLastError());
-  col_stats_merge_kernel<<<cdiv(cols, 32), 1024, 0, st>>>(work, ctas, cols, stats);
+  (void)launch_dep(col_stats_merge_kernel, dim3(cdiv(cols, 32)), dim3(1024), 0, st, work, ctas, cols, stats);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
 int launch_group_stats_merge(const float* col_stats, int C, int group, size_t rows, float* ch_stats, cudaStream_t st) {
-  group_stats_merge_kernel<<<cdiv(C, 128), 128, 0, st>>>(col_stats, C, group, static_cast<double>(rows), ch_stats);
+  (void)launch_dep(group_stats_merge_kernel, dim3(cdiv(C, 128)), dim3(128), 0, st, col_stats, C, group, static_cast<double>(rows), ch_stats);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
 int launch_group_expand(const float* in, int n_vec, int C, int group, float* out, cudaStream_t st) {
-  group_expand_kernel<<<cdiv(n_vec * C * group, 256), 256, 0, st>>>(in, n_vec, C, group, out);
+  (void)launch_dep(group_expand_kernel, dim3(cdiv(n_vec * C * group, 256)), dim3(256), 0, st, in, n_vec, C, group, out);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
 int launch_group_sum(const float* in, int n_vec, int C, int group, float* out, cudaStream_t st) {
-  group_sum_kernel<<<cdiv(n_vec * C, 256), 256, 0, st>>>(in, n_vec, C, group, out);
+  (void)launch_dep(group_sum_kernel, dim3(cdiv(n_vec * C, 256)), dim3(256), 0, st, in, n_vec, C, group, out);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -256,6 +268,8 @@ int launch_group_sum(const float* in, int n_vec, int C, int group, float* out, c
 // Main kernel: thread = output column (c, f), CTA = row range; 9 + 1 accumulators; partial[cta][col][10]; then one block per channel
 // adds the partials of its F2 columns in a fixed order.
 __global__ void __launch_bounds__(256) subsample_melT_kernel(const float* __restrict__ mel, int B, int F, int T_in, float* __restrict__ melT) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int Fp = F + 2, Tp = T_in + 2;
   const size_t n = static_cast<size_t>(B) * Tp * Fp, st = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += st) {
@@ -271,6 +285,8 @@ __global__ void __launch_bounds__(256) subsample_melT_kernel(const float* __rest
 // partial[cta.x][c][10] (the round-1 kernel wrote one partial per COLUMN: 114 MB of partials at C = 120).
 __global__ void __launch_bounds__(128) subsample_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ melT, int B, int F, int T_in,
                                                               int T_out, int C, int cpb, float* __restrict__ partial) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   extern __shared__ float wg_sm[];              // [cpb * F2][10]
   const int F2 = F / 2, cols = C * F2, Fp = F + 2, Tp = T_in + 2;
   const int nthr = cpb * F2;
@@ -314,6 +330,8 @@ __global__ void __launch_bounds__(128) subsample_wgrad_kernel(const float* __res
 // out[c][k] = sum over the CTA partials in order: block = 32 outputs x 32 lanes (chunked fixed-order sum)
 __global__ void __launch_bounds__(1024) subsample_wgrad_reduce_kernel(const float* __restrict__ partial, int n_partial, int C,
                                                                       float* __restrict__ dw, float* __restrict__ db) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   __shared__ float sm[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + tx, n = C * 10;
@@ -340,16 +358,16 @@ int launch_subsample_wgrad(const float* dy, const float* mel, int B, int F, int 
   const int T_out = (T - 1) / 2 + 1, cols = C * (F / 2);
   const int ctas = static_cast<int>(std::min<size_t>(kWgCtas, static_cast<size_t>(B) * T_out));
   float* melT = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(work) + wg_partial_bytes(C, F));
-  subsample_melT_kernel<<<grid_for(static_cast<size_t>(B) * (T + 2) * (F + 2)), 256, 0, st>>>(mel, B, F, T, melT);
+  (void)launch_dep(subsample_melT_kernel, dim3(grid_for(static_cast<size_t>(B) * (T + 2) * (F + 2))), dim3(256), 0, st, mel, B, F, T, melT);
   EC_CUDA(cudaGetLastError());
   const int F2 = F / 2;
   EC_REQUIRE(F2 <= 128, "Conv2d subsampling weight gradient: at most 256 mel bins");
   const int cpb = std::max(1, 128 / F2), gy = cdiv(C, cpb);
   const int ctas_x = std::max(1, std::min(ctas, kWgCtas));      // row ranges of ~27 rows: 2.9 M threads in flight, 2.8 MB of partials
   (void)cols;
-  subsample_wgrad_kernel<<<dim3(ctas_x, gy), 128, static_cast<size_t>(cpb) * F2 * 10 * sizeof(float), st>>>(dy, melT, B, F, T, T_out, C, cpb, work);
+  (void)launch_dep(subsample_wgrad_kernel, dim3(dim3(ctas_x, gy)), dim3(128), static_cast<size_t>(cpb) * F2 * 10 * sizeof(float), st, dy, melT, B, F, T, T_out, C, cpb, work);
   EC_CUDA(cudaGetLastError());
-  subsample_wgrad_reduce_kernel<<<cdiv(C * 10, 32), 1024, 0, st>>>(work, ctas_x, C, dw, db);
+  (void)launch_dep(subsample_wgrad_reduce_kernel, dim3(cdiv(C * 10, 32)), dim3(1024), 0, st, work, ctas_x, C, dw, db);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }

@@ -13,7 +13,9 @@
 namespace ec {
 
 inline int grid_for(size_t n) { return static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16)); }
-__global__ void dropout_advance_kernel(unsigned long long* ctr) { ctr[1] += 1ull; }
+__global__ void dropout_advance_kernel(unsigned long long* ctr) {
+  grid_dependency_wait();
+  grid_launch_dependents(); ctr[1] += 1ull; }
 
 // dst[i] = TOut(scale * keep(i) / (1 - p) * src[i]); each thread owns groups of 4 consecutive elements
 template <typename TOut, bool kRound> __device__ __forceinline__ TOut drop_store(float x);
@@ -24,6 +26,8 @@ template <> __device__ __forceinline__ SplitBf16 drop_store<SplitBf16, true>(flo
 template <typename TIn, typename TOut, bool kRound>
 __global__ void __launch_bounds__(256) dropout_kernel(const TIn* __restrict__ src, float scale, size_t n, TOut* __restrict__ dst,
                                                       const unsigned long long* __restrict__ ctr, unsigned site, unsigned keep16) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const unsigned long long key = site_key(ctr, site);
   const float inv_keep = scale * 65536.f / static_cast<float>(keep16);
   const size_t groups = (n + 3) / 4, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -41,6 +45,8 @@ __global__ void __launch_bounds__(256) dropout_kernel(const TIn* __restrict__ sr
 __global__ void __launch_bounds__(256) dropout_residual_kernel(const float* __restrict__ y, const float* __restrict__ residual, float alpha,
                                                                size_t n, float* __restrict__ out, const unsigned long long* __restrict__ ctr,
                                                                unsigned site, unsigned keep16) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const unsigned long long key = site_key(ctr, site);
   const float inv_keep = alpha * 65536.f / static_cast<float>(keep16);
   const size_t groups = (n + 3) / 4, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -68,7 +74,7 @@ __global__ void __launch_bounds__(256) dropout_residual_kernel(const float* __re
 
 
 int launch_dropout_advance(unsigned long long* ctr, cudaStream_t st) {
-  dropout_advance_kernel<<<1, 1, 0, st>>>(ctr);
+  (void)launch_dep(dropout_advance_kernel, dim3(1), dim3(1), 0, st, ctr);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -83,17 +89,17 @@ int launch_dropout(int precision, const void* src, int src_f32, float scale, siz
   const float* s32 = static_cast<const float*>(src); const bf* s16 = static_cast<const bf*>(src); const SplitBf16* sx = static_cast<const SplitBf16*>(src);
   float* d32 = static_cast<float*>(dst); bf* d16 = static_cast<bf*>(dst); SplitBf16* dx = static_cast<SplitBf16*>(dst);
   if (dst_f32) {
-    if (sf) dropout_kernel<float, float, false><<<grid, 256, 0, st>>>(s32, scale, n, d32, ctr, site, k);
-    else if (precision == EC_PREC_BF16X2) dropout_kernel<SplitBf16, float, false><<<grid, 256, 0, st>>>(sx, scale, n, d32, ctr, site, k);
-    else dropout_kernel<bf, float, false><<<grid, 256, 0, st>>>(s16, scale, n, d32, ctr, site, k);
+    if (sf) (void)launch_dep(dropout_kernel<float, float, false>, dim3(grid), dim3(256), 0, st, s32, scale, n, d32, ctr, site, k);
+    else if (precision == EC_PREC_BF16X2) (void)launch_dep(dropout_kernel<SplitBf16, float, false>, dim3(grid), dim3(256), 0, st, sx, scale, n, d32, ctr, site, k);
+    else (void)launch_dep(dropout_kernel<bf, float, false>, dim3(grid), dim3(256), 0, st, s16, scale, n, d32, ctr, site, k);
   } else if (precision == EC_PREC_TF32) {
-    dropout_kernel<float, float, true><<<grid, 256, 0, st>>>(s32, scale, n, d32, ctr, site, k);
+    (void)launch_dep(dropout_kernel<float, float, true>, dim3(grid), dim3(256), 0, st, s32, scale, n, d32, ctr, site, k);
   } else if (precision == EC_PREC_BF16X2) {
-    if (sf) dropout_kernel<float, SplitBf16, true><<<grid, 256, 0, st>>>(s32, scale, n, dx, ctr, site, k);
-    else dropout_kernel<SplitBf16, SplitBf16, true><<<grid, 256, 0, st>>>(sx, scale, n, dx, ctr, site, k);
+    if (sf) (void)launch_dep(dropout_kernel<float, SplitBf16, true>, dim3(grid), dim3(256), 0, st, s32, scale, n, dx, ctr, site, k);
+    else (void)launch_dep(dropout_kernel<SplitBf16, SplitBf16, true>, dim3(grid), dim3(256), 0, st, sx, scale, n, dx, ctr, site, k);
   } else {
-    if (sf) dropout_kernel<float, bf, true><<<grid, 256, 0, st>>>(s32, scale, n, d16, ctr, site, k);
-    else dropout_kernel<bf, bf, true><<<grid, 256, 0, st>>>(s16, scale, n, d16, ctr, site, k);
+    if (sf) (void)launch_dep(dropout_kernel<float, bf, true>, dim3(grid), dim3(256), 0, st, s32, scale, n, d16, ctr, site, k);
+    else (void)launch_dep(dropout_kernel<bf, bf, true>, dim3(grid), dim3(256), 0, st, s16, scale, n, d16, ctr, site, k);
   }
   EC_CUDA(cudaGetLastError());
   return EC_OK;
@@ -102,7 +108,7 @@ int launch_dropout_residual(const float* y, const float* residual, float alpha, 
                             unsigned site, cudaStream_t st) {
   EC_REQUIRE(p >= 0.f && p < 1.f, "dropout probability must be in [0, 1)");
   if (n == 0) return EC_OK;
-  dropout_residual_kernel<<<grid_for((n + 3) / 4), 256, 0, st>>>(y, residual, alpha, n, out, ctr, site, keep16_of(p));
+  (void)launch_dep(dropout_residual_kernel, dim3(grid_for((n + 3) / 4)), dim3(256), 0, st, y, residual, alpha, n, out, ctr, site, keep16_of(p));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -112,6 +118,8 @@ int launch_dropout_residual(const float* y, const float* residual, float alpha, 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, size_t n, const int* __restrict__ state, float beta1, float beta2,
                                                    float eps, float weight_decay, float grad_scale) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const float lr = __int_as_float(state[0]);
   const float t = static_cast<float>(state[1] + 1);
   const float bc1 = 1.f - powf(beta1, t), bc2 = 1.f - powf(beta2, t);
@@ -140,6 +148,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 }
 // after the update: t += 1; schedule mode 1 (Transformer): s += 1, lr = K * d^-0.5 * min(s^-0.5, s * warmup^-1.5); mode 0: lr unchanged
 __global__ void adam_advance_kernel(int* state, int mode, float K, float dim, float warmup) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   state[1] += 1;
   if (mode == 1) {
     state[2] += 1;
@@ -153,9 +163,9 @@ int launch_adam(float* p, const float* g, float* m, float* v, size_t n, int* sta
   EC_REQUIRE(p && g && m && v && state, "null argument");
   EC_REQUIRE((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) % 16 == 0,
              "Adam arenas must be 16-byte aligned");
-  if (n) adam_kernel<<<grid_for((n + 3) / 4), 256, 0, st>>>(p, g, m, v, n, state, beta1, beta2, eps, weight_decay, grad_scale);
+  if (n) (void)launch_dep(adam_kernel, dim3(grid_for((n + 3) / 4)), dim3(256), 0, st, p, g, m, v, n, state, beta1, beta2, eps, weight_decay, grad_scale);
   EC_CUDA(cudaGetLastError());
-  adam_advance_kernel<<<1, 1, 0, st>>>(state, schedule, K, dim, warmup);
+  (void)launch_dep(adam_advance_kernel, dim3(1), dim3(1), 0, st, state, schedule, K, dim, warmup);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -163,6 +173,8 @@ int launch_adam(float* p, const float* g, float* m, float* v, size_t n, int* sta
 // ---- SyncBatchNorm forward: merge the (mean, M2) pairs of `world` ranks (Chan et al.), rank r holding counts[r] frames -----------
 __global__ void stats_merge_ranks_kernel(const float* __restrict__ gathered, const float* __restrict__ counts, int world, int C,
                                          float* __restrict__ out) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double n = 0.0, mean = 0.0, m2 = 0.0;
@@ -180,7 +192,7 @@ __global__ void stats_merge_ranks_kernel(const float* __restrict__ gathered, con
 }
 int launch_stats_merge_ranks(const float* gathered, const float* counts, int world, int C, float* out, cudaStream_t st) {
   EC_REQUIRE(gathered && counts && out && world >= 1 && C >= 1, "bad argument");
-  stats_merge_ranks_kernel<<<(C + 127) / 128, 128, 0, st>>>(gathered, counts, world, C, out);
+  (void)launch_dep(stats_merge_ranks_kernel, dim3((C + 127) / 128), dim3(128), 0, st, gathered, counts, world, C, out);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -220,6 +232,8 @@ namespace ec {
 template <bool kAcc>
 __global__ void __launch_bounds__(256) pack_flat_kernel(const float* const* __restrict__ srcs, const long long* __restrict__ offsets,
                                                         const long long* __restrict__ sizes, float* __restrict__ arena) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const float* __restrict__ src = srcs[blockIdx.y];
   float* __restrict__ dst = arena + offsets[blockIdx.y];
   const long long n = sizes[blockIdx.y];
@@ -231,8 +245,8 @@ extern "C" int ec_op_pack_flat_acc(const float* const* srcs, const long long* of
                                    void* stream) {
   EC_REQUIRE(srcs && offsets && sizes && arena && n >= 0 && n <= 65535, "bad argument");
   if (n == 0) return EC_OK;
-  if (accumulate) ec::pack_flat_kernel<true><<<dim3(8, n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(srcs, offsets, sizes, arena);
-  else ec::pack_flat_kernel<false><<<dim3(8, n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(srcs, offsets, sizes, arena);
+  if (accumulate) (void)launch_dep(ec::pack_flat_kernel<true>, dim3(dim3(8, n)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), srcs, offsets, sizes, arena);
+  else (void)launch_dep(ec::pack_flat_kernel<false>, dim3(dim3(8, n)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), srcs, offsets, sizes, arena);
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -247,6 +261,8 @@ namespace ec {
 template <typename T, bool kBwd>
 __global__ void __launch_bounds__(256) swish_dropout_kernel(const T* __restrict__ z, const float* __restrict__ dy, size_t n, T* __restrict__ out,
                                                             const unsigned long long* __restrict__ ctr, unsigned site, unsigned keep16) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const unsigned long long key = site_key(ctr, site);
   const float inv_keep = 65536.f / static_cast<float>(keep16);
   const size_t groups = (n + 3) / 4, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -268,6 +284,8 @@ __global__ void __launch_bounds__(256) swish_dropout_kernel(const T* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_cast_multi_kernel(const float* __restrict__ src_arena, const long long* __restrict__ desc,
                                                                    T* __restrict__ dst_arena) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   __shared__ float tile[32][33];
   const long long* d = desc + static_cast<long long>(blockIdx.y) * 4;
   const int rows = static_cast<int>(d[1]), cols = static_cast<int>(d[2]);
@@ -299,6 +317,8 @@ __global__ void __launch_bounds__(256) transpose_cast_multi_kernel(const float* 
 template <typename T>
 __global__ void __launch_bounds__(256) cast_multi_kernel(const float* __restrict__ src_arena, const long long* __restrict__ desc,
                                                          T* __restrict__ dst_arena) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const long long* d = desc + static_cast<long long>(blockIdx.y) * 4;
   const size_t n = static_cast<size_t>(d[1]) * static_cast<size_t>(d[2]);
   const float* __restrict__ src = src_arena + d[0];
@@ -318,8 +338,8 @@ int ec_op_swish_dropout(int precision, const void* z, const float* dy, size_t n,
   const int grid = ec::grid_for((n + 3) / 4);
   const unsigned k = ec::keep16_of(p);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dy) EC_DISPATCH_PREC(precision, (ec::swish_dropout_kernel<ActT, true><<<grid, 256, 0, st>>>(static_cast<const ActT*>(z), dy, n, static_cast<ActT*>(out), counter, site, k)));
-  else EC_DISPATCH_PREC(precision, (ec::swish_dropout_kernel<ActT, false><<<grid, 256, 0, st>>>(static_cast<const ActT*>(z), dy, n, static_cast<ActT*>(out), counter, site, k)));
+  if (dy) EC_DISPATCH_PREC(precision, ((void)launch_dep(ec::swish_dropout_kernel<ActT, true>, dim3(grid), dim3(256), 0, st, static_cast<const ActT*>(z), dy, n, static_cast<ActT*>(out), counter, site, k)));
+  else EC_DISPATCH_PREC(precision, ((void)launch_dep(ec::swish_dropout_kernel<ActT, false>, dim3(grid), dim3(256), 0, st, static_cast<const ActT*>(z), dy, n, static_cast<ActT*>(out), counter, site, k)));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -329,7 +349,7 @@ int ec_op_transpose_cast_multi(int precision, const float* src_arena, const long
   if (n == 0) return EC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(ctas_per_tensor, n);
-  EC_DISPATCH_PREC(precision, (ec::transpose_cast_multi_kernel<ActT><<<grid, 256, 0, st>>>(src_arena, desc, static_cast<ActT*>(dst_arena))));
+  EC_DISPATCH_PREC(precision, ((void)launch_dep(ec::transpose_cast_multi_kernel<ActT>, dim3(grid), dim3(256), 0, st, src_arena, desc, static_cast<ActT*>(dst_arena))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
@@ -338,7 +358,7 @@ int ec_op_cast_multi(int precision, const float* src_arena, const long long* des
   if (n == 0) return EC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(ctas_per_tensor, n);
-  EC_DISPATCH_PREC(precision, (ec::cast_multi_kernel<ActT><<<grid, 256, 0, st>>>(src_arena, desc, static_cast<ActT*>(dst_arena))));
+  EC_DISPATCH_PREC(precision, ((void)launch_dep(ec::cast_multi_kernel<ActT>, dim3(grid), dim3(256), 0, st, src_arena, desc, static_cast<ActT*>(dst_arena))));
   EC_CUDA(cudaGetLastError());
   return EC_OK;
 }
