@@ -300,17 +300,27 @@ __global__ void __launch_bounds__(128) subsample_wgrad_kernel(const float* __res
   const size_t rows = static_cast<size_t>(B) * T_out;
   const size_t per = (rows + gridDim.x - 1) / gridDim.x;
   const size_t r0 = min(rows, per * blockIdx.x), r1 = min(rows, r0 + per);
-  if (ok) {
+  if (ok && r0 < r1) {
+    // (utterance, frame) of the row advance with the loop: no 64-bit division per row (it was most of this kernel's instructions)
+    int b = static_cast<int>(r0 / T_out), t = static_cast<int>(r0 - static_cast<size_t>(b) * T_out);
+    const float* dp = dy + r0 * cols + col;
+    // rows 2t-1 .. 2t+1 of the input are rows 2t .. 2t+2 of the bordered copy (2t+2 <= T_in+1 always); same for the frequencies
+    const float* base = melT + (static_cast<size_t>(b) * Tp + 2 * t) * Fp + 2 * f;
     for (size_t r = r0; r < r1; ++r) {
-      const int b = static_cast<int>(r / T_out), t = static_cast<int>(r - static_cast<size_t>(b) * T_out);
-      const float d = dy[r * cols + col];
-      // rows 2t-1 .. 2t+1 of the input are rows 2t .. 2t+2 of the bordered copy (2t+2 <= T_in+1 always); same for the frequencies
-      const float* base = melT + (static_cast<size_t>(b) * Tp + 2 * t) * Fp + 2 * f;
+      const float d = *dp;
+      float m[9];
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) m[kw * 3 + kh] = base[kw * Fp + kh];
       acc[9] += d;
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) acc[kh * 3 + kw] = fmaf(d, base[kw * Fp + kh], acc[kh * 3 + kw]);
+        for (int kh = 0; kh < 3; ++kh) acc[kh * 3 + kw] = fmaf(d, m[kw * 3 + kh], acc[kh * 3 + kw]);
+      dp += cols;
+      if (++t == T_out) { t = 0; ++b; base = melT + static_cast<size_t>(b) * Tp * Fp + 2 * f; }
+      else base += 2 * Fp;
     }
   }
   if (threadIdx.x < nthr) {

@@ -68,10 +68,11 @@ class DropoutState:
         return self.site
 
 
-def _bump_batches_tracked(bn):
-    """nn.BatchNorm*.num_batches_tracked += 1 in training mode (a state_dict entry of the reference)."""
+def _bump_batches_tracked(bn, sink):
+    """nn.BatchNorm*.num_batches_tracked += 1 in training mode (a state_dict entry of the reference): collected in `sink`, all 16
+    counters advance in ONE multi-tensor launch at the end of the forward (16 separate one-element kernels sat on the critical path)."""
     if getattr(bn, "num_batches_tracked", None) is not None:
-        bn.num_batches_tracked.add_(1)
+        sink.append(bn.num_batches_tracked)
 
 
 def _len_after_stride(length, stride):
@@ -201,7 +202,8 @@ class TrainingPath:
         sub = enc.subsampling_module.layers[0]
         a, sub_saved = o.SubsampleTrain.forward(mel, sub[0].weight, sub[0].bias, sub[1].weight, sub[1].bias, sub[1].running_mean,
                                                 sub[1].running_var, pr, reduce_stats=self.stats_reducer)
-        _bump_batches_tracked(sub[1])
+        self._tracked = []
+        _bump_batches_tracked(sub[1], self._tracked)
         T0 = (T - 1) // 2 + 1
         cur_len = None
         if mel_len is not None:
@@ -238,6 +240,9 @@ class TrainingPath:
             logits = o.gemm(x_act_last, w_fc, self.head.bias, pr)[0].view(B, Tc, -1)
             tape["head"] = (x_act_last, w_fc)
         tape["T_out"] = Tc
+        if self._tracked:
+            torch._foreach_add_(self._tracked, 1)
+            self._tracked = []
         return x.view(B, Tc, D_last), logits, cur_len, tape
 
     def _proj_drop_res(self, a_act, w_act, bias, pr, drop, site, alpha, residual, next_ln=None):
@@ -357,7 +362,7 @@ class TrainingPath:
         gl = o.glu_fwd(zg, pr)
         h, dw_saved = o.DwConvTrain.forward(gl.view(B, T, De), Lc[4].weight, Lc[4].bias, Lc[5].weight, Lc[5].bias, Lc[5].running_mean,
                                             Lc[5].running_var, st, pr, reduce_stats=self.stats_reducer)
-        _bump_batches_tracked(Lc[5])
+        _bump_batches_tracked(Lc[5], self._tracked)
         To = (T - 1) // st + 1
         xs = None
         if spec.has_conv_res_proj:
