@@ -5,6 +5,7 @@
 //   Swish / GLU backward         (reference models/activations.py:28-29, 37-39)
 // Every reduction has a fixed order (per-CTA partials + a second pass), so gradients are bit-reproducible.
 #include "ec_common.cuh"
+#include <cstdlib>
 #include <algorithm>
 #include <type_traits>
 
@@ -179,7 +180,9 @@ int launch_layernorm_bwd(const float* x, const float* dy, int rows, int dim, con
   EC_REQUIRE(rows > 0 && dim > 0 && dim <= 1024, "LayerNorm backward: bad shape (dim <= 1024)");
   EC_REQUIRE(x && dy && gamma && dx && dgamma && dbeta && work, "null argument");
   EC_REQUIRE(drop_ctr == nullptr || (drop_p >= 0.f && drop_p < 1.f && dim % 4 == 0), "bad dropout arguments (dim must be a multiple of 4)");
-  const int ctas = std::min(kBwdCtas, cdiv(rows, 8));
+  // EFFCONF_LNBWD_CTAS (<= kBwdCtas): grid-size study of the row-strided LayerNorm backward (fewer CTAs = fewer partials to reduce)
+  static const int cta_cap = [] { const char* e = getenv("EFFCONF_LNBWD_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? std::min(v, kBwdCtas) : kBwdCtas; }();
+  const int ctas = std::min(cta_cap, cdiv(rows, 8));
   LnEmit em{emit_out, emit_scale, drop_ctr, drop_site, drop_ctr != nullptr ? keep16_of(drop_p) : 65536u};
   if (emit_out == nullptr) launch_ln_bwd_t<void>(ctas, x, dy, rows, dim, gamma, eps, dx, accumulate, work, em, stream);
   else if (emit_precision == EC_PREC_TF32) launch_ln_bwd_t<float>(ctas, x, dy, rows, dim, gamma, eps, dx, accumulate, work, em, stream);
