@@ -144,6 +144,32 @@ def test_flat_parameter_arena_and_operand_views_bookkeeping():
         w.act(blk.convolution_module.layers[4].weight)                                             # the depthwise taps are not a GEMM operand
 
 
+def test_gradient_bucket_plan_covers_the_arena_in_backward_order():
+    """Overlapped gradient buckets (trainer.CTCTrainStep._plan_buckets, EFFCONF_BUCKET_OVERLAP=1), no GPU: the arena is cut at block
+    boundaries, bucket b holds exactly the head and the blocks >= b that no later-cut bucket holds, the buckets plus the remainder tile
+    the parameter list without gaps or overlap, and a model whose arena order would break contiguity gets no plan (one bucket)."""
+    from types import SimpleNamespace
+    from efficientconformer_b200.model_ctc import ModelCTC
+    from efficientconformer_b200 import trainer
+    from efficientconformer_b200.training import TrainingPath
+    m = ModelCTC(P, {"vocab_size": V})
+    path = TrainingPath(m.encoder, m.fc)
+    flat = trainer.FlatParams(trainer._qkv_adjacent_order(path.param_list()), "cpu")
+    plan = trainer.CTCTrainStep._plan_buckets(SimpleNamespace(flat=flat), m)
+    assert sorted(plan) == [5, 10]                                         # 15 blocks: the middle and the last third
+    (lo1, hi1), (lo0, hi0) = plan[5], plan[10]
+    assert hi0 == len(flat.names) and hi1 == lo0 and 0 < lo1 < lo0         # backward order: bucket 10 first, then 5, then [0, lo1)
+    block_of = lambda n: int(n.split(".")[2]) if n.startswith("encoder.blocks.") else (99 if n.startswith("fc.") else -1)
+    assert all(block_of(n) >= 10 for n in flat.names[lo0:hi0]) and all(5 <= block_of(n) < 10 for n in flat.names[lo1:hi1])
+    assert all(block_of(n) < 5 for n in flat.names[:lo1])
+    a0, b0 = flat.arena_range(lo0, hi0); a1, b1 = flat.arena_range(lo1, hi1); a2, b2 = flat.arena_range(0, lo1)
+    assert (a2, b2, b1, b0) == (0, a1, a0, flat.total)                    # float ranges tile the arena
+    assert 0.5 < (b0 - a0) / flat.total < 0.56                             # the last third of the blocks owns half of the bytes (D = 240)
+    # an arena whose order interleaves the head with the encoder cannot be cut: no plan
+    shuffled = SimpleNamespace(names=[flat.names[-1]] + flat.names[:-1])
+    assert trainer.CTCTrainStep._plan_buckets(SimpleNamespace(flat=shuffled), m) == {}
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver times next to ours) in both modes on a tiny shape: one JSON line with
     the contract keys."""
