@@ -122,3 +122,24 @@ def test_specaugment_module_statistics_and_streams():
     mean_w = sum(f_widths) / len(f_widths)                                # two masks of E[floor(27 U)] = 13 each, minus overlaps
     print("mean masked mel bins per step", mean_w)
     assert 18.0 < mean_w < 27.0
+
+
+def test_device_batch_prefetcher_preserves_order_and_values_under_overlap():
+    """reference models/model.py:229 `batch = [elt.to(device) for elt in batch]` replaced by the pinned, stream-overlapped pipeline:
+    same batches, same order, while a compute stream is busy and the allocator recycles the staging memory."""
+    from efficientconformer_b200 import DeviceBatchPrefetcher
+    g = torch.Generator().manual_seed(5)
+    host = [(torch.randn(4, 16000 + 160 * i, generator=g), torch.randint(1, 30, (4, 12), generator=g), torch.full((4,), 16000 + 160 * i),
+             torch.full((4,), 12), "meta%d" % i) for i in range(9)]
+    busy = torch.randn(2048, 2048, device=DEV)
+    seen = 0
+    for k, batch in enumerate(DeviceBatchPrefetcher(host, DEV, depth=2)):
+        x, y, xl, yl, meta = batch
+        for _ in range(3):
+            busy = busy @ busy * 1e-3                       # keep the consumer stream behind the copy stream
+        assert x.is_cuda and y.is_cuda and meta == "meta%d" % k
+        assert torch.equal(x.cpu(), host[k][0]) and torch.equal(y.cpu(), host[k][1]) and torch.equal(xl.cpu(), host[k][2])
+        seen += 1
+    assert seen == len(host)
+    with pytest.raises(RuntimeError, match="CUDA path only"):
+        DeviceBatchPrefetcher(host, "cpu")

@@ -144,6 +144,14 @@ def test_flat_parameter_arena_and_operand_views_bookkeeping():
         w.act(blk.convolution_module.layers[4].weight)                                             # the depthwise taps are not a GEMM operand
 
 
+def test_batch_prefetcher_refuses_non_cuda_devices():
+    from efficientconformer_b200 import DeviceBatchPrefetcher
+    with pytest.raises(RuntimeError, match="CUDA path only"):
+        DeviceBatchPrefetcher([(torch.zeros(1),)], "cpu")
+    with pytest.raises(ValueError):
+        DeviceBatchPrefetcher([(torch.zeros(1),)], "cuda", depth=0)
+
+
 def test_gradient_bucket_plan_covers_the_arena_in_backward_order():
     """Overlapped gradient buckets (trainer.CTCTrainStep._plan_buckets, EFFCONF_BUCKET_OVERLAP=1), no GPU: the arena is cut at block
     boundaries, bucket b holds exactly the head and the blocks >= b that no later-cut bucket holds, the buckets plus the remainder tile
