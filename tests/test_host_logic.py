@@ -144,6 +144,67 @@ def test_flat_parameter_arena_and_operand_views_bookkeeping():
         w.act(blk.convolution_module.layers[4].weight)                                             # the depthwise taps are not a GEMM operand
 
 
+def test_every_programmatically_launched_kernel_waits_for_its_predecessor():
+    """Source-level invariant behind programmatic dependent launch (csrc/ec_common.cuh launch_pdl / launch_dep): a kernel launched
+    with the attribute may start while its predecessor still runs, so its body must execute griddepcontrol.wait -- for the training kernels
+    (launch_dep) before anything but a few declarations, with no pointer parameter mentioned ahead of it; for the hand-written
+    pipelines (launch_pdl) somewhere before the first access to predecessor data (checked by the GPU parity tests).  A kernel added to a launch_dep call without the wait would race silently; this test fails instead."""
+    src_dir = os.path.join(ROOT, "efficientconformer_b200", "csrc")
+    texts = {f: open(os.path.join(src_dir, f)).read() for f in os.listdir(src_dir) if f.endswith((".cu", ".cuh"))}
+
+    def body_of(text, start):
+        i = text.index("(", start)
+        depth = 0
+        while True:                                            # parameter list (skipping __launch_bounds__(...))
+            depth += text[i] == "("; depth -= text[i] == ")"
+            i += 1
+            if depth == 0:
+                j = i
+                while text[j] in " \n\t":
+                    j += 1
+                if text[j] == "{":
+                    break
+                if text[j] == ";":
+                    return None
+                i = text.index("(", j)
+        depth, k = 0, j
+        while True:
+            depth += text[k] == "{"; depth -= text[k] == "}"
+            k += 1
+            if depth == 0:
+                return text[j + 1:k - 1]
+
+    bodies = {}
+    for f, text in texts.items():
+        for m in re.finditer(r"__global__", text):
+            b = body_of(text, m.end())
+            if b is None:
+                continue
+            head = text[m.end():text.index("{", m.end())]
+            head = re.sub(r"__launch_bounds__\s*\([^)]*\)", "", head)
+            name = re.findall(r"(\w+)\s*\(", head)[0]
+            pointers = set(re.findall(r"\*\s*(?:__restrict__\s+)?(\w+)\s*[,)/]", head))      # pointer parameters of the kernel
+            bodies[name] = (b, pointers)
+    launched_dep, launched_pdl = set(), set()
+    for text in texts.values():
+        launched_dep |= set(re.findall(r"launch_dep\(\s*(?:\w+::)*([A-Za-z_]\w*)", text))
+        launched_pdl |= set(re.findall(r"launch_pdl(?:_cluster)?\(\s*(?:\w+::)*([A-Za-z_]\w*)", text))
+    launched_dep -= {"kernel", "void"}; launched_pdl -= {"kernel", "void"}   # the helper templates' own declarations
+    assert len(launched_dep) > 40 and len(launched_pdl) >= 8
+    for k in sorted(launched_dep):
+        assert k in bodies, k
+        body, pointers = bodies[k]
+        assert "grid_dependency_wait()" in body, k
+        before = body.split("grid_dependency_wait()")[0]      # only declarations may precede the wait: no pointer parameter is touched
+        before = re.sub(r"//[^\n]*", "", before)
+        assert not any(re.search(r"\b%s\b" % p_, before) for p_ in pointers), (k, before)
+        assert before.count(";") <= 3, (k, before)
+    for k in sorted(launched_pdl):
+        assert k in bodies and "grid_dependency_wait()" in bodies[k][0], k
+    # and the spin-waiting peer-memory exchange is never launched programmatically
+    assert "p2p_exchange_kernel" not in launched_dep | launched_pdl
+
+
 def test_batch_prefetcher_refuses_non_cuda_devices():
     from efficientconformer_b200 import DeviceBatchPrefetcher
     with pytest.raises(RuntimeError, match="CUDA path only"):
