@@ -267,3 +267,35 @@ def test_frontend_oracle_against_reference_golden(golden_dir):
     assert (a == b).all() and not (a == c2).all()
     assert ((a == 0).all(2) == (a == 0).all(2)[0:1]).all()
     assert not (a[1] == 0).all(0)[120:].any() and not (a[2] == 0).all(0)[7:].any()
+
+
+def test_specaugment_torch_path_follows_the_pinned_mask_arithmetic():
+    """The CPU-tensor route of encoders.SpecAugment (batched torch ops) fed with preset uniforms draws exactly the spans the pinned
+    arithmetic (oracle span_from_uniforms == torchaudio mask_along_axis, see the golden above) gives: frequency masks shared by the
+    batch, time masks per utterance inside its valid frames with parameter int(pS * x_len[b])."""
+    import numpy as np
+    from oracle import frontend_oracle as FO
+    from efficientconformer_b200.encoders import SpecAugment
+    B, F, T, mF, Fp, mT, pS = 3, 80, 400, 2, 27, 5, 0.05
+    lens = torch.tensor([400, 250, 37])
+    rng = np.random.default_rng(7)
+    draws = [torch.tensor(rng.random(mF), dtype=torch.float32), torch.tensor(rng.random(mF), dtype=torch.float32),
+             torch.tensor(rng.random((B, mT)), dtype=torch.float32), torch.tensor(rng.random((B, mT)), dtype=torch.float32)]
+    seq = iter(draws)
+    real_rand = torch.rand
+    torch.rand = lambda *a, **k: next(seq)
+    try:
+        y = SpecAugment(True, mF, Fp, mT, pS)(torch.ones(B, F, T), lens)
+    finally:
+        torch.rand = real_rand
+    ref = np.ones((B, F, T), dtype=np.float32)
+    for i in range(mF):
+        s0, e0 = FO.span_from_uniforms(float(draws[0][i]), float(draws[1][i]), Fp, F)
+        ref[:, s0:e0, :] = 0
+    for b in range(B):
+        ln = int(lens[b]); Tp = int(np.float32(pS) * np.float32(ln))
+        for j in range(mT):
+            s0, e0 = FO.span_from_uniforms(float(draws[2][b, j]), float(draws[3][b, j]), Tp, ln)
+            ref[b, :, s0:min(e0, ln)] = 0
+    assert torch.equal(y, torch.from_numpy(ref))
+    assert not SpecAugment(False, mF, Fp, mT, pS)(torch.ones(B, F, T), lens).eq(0).any()
